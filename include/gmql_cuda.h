@@ -1,0 +1,212 @@
+/*
+ * gmql_cuda.h — C ABI of libgmqlcuda.so, the B200 (sm_100a) back end for GMQL's
+ * region-operator hot path: genometric MAP, COVER/FLAT/SUMMIT/HISTOGRAM and JOIN.
+ *
+ * The reference (DEIB-GECO/GMQL) has no FFI: its plug-in point is the Scala class
+ * `Implementation` (GMQL-Server/.../GMQLServer/Implementation.scala:22-71) and the
+ * operator dispatch `GMQLSparkExecutor.implement_rd`
+ * (GMQL-Spark/.../implementation/GMQLSparkExecutor.scala:251-285).  The entry points
+ * below are what a JNI shim under a `GMQLCudaExecutor extends GMQLSparkExecutor`
+ * binds for the three IR nodes it overrides (INTEGRATION.md shows that binding):
+ *
+ *   gmql_map    replaces GenometricMap71.apply   (RegionsOperators/GenometricMap/GenometricMap71.scala:28)
+ *   gmql_cover  replaces GenometricCover.apply   (RegionsOperators/GenometricCover/GenometricCover.scala:30)
+ *                        + GMAP4.apply           (RegionsOperators/GenometricMap/GMAP4.scala:20)
+ *   gmql_join   replaces GenometricJoin.apply    (RegionsOperators/GenometricJoin.scala:21)
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *  - every call returns 0 on success or a negative gmql_status; the message is
+ *    available from gmql_last_error(ctx) (reference convention: operators throw,
+ *    GMQLSparkExecutor.scala:190-207 rethrows — the JNI shim turns <0 into an exception);
+ *  - a context is used by one thread at a time; distinct contexts are independent
+ *    (no global mutable state), matching GMQLExecute's 5-job pool (GMQLExecute.scala:29-30);
+ *  - inputs are owned by the caller and must stay alive for the duration of the call;
+ *    results are owned by the library until gmql_result_free;
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef GMQL_CUDA_H
+#define GMQL_CUDA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMQL_ABI_VERSION 1
+
+typedef enum {
+  GMQL_OK = 0,
+  GMQL_ERR_INVALID = -1,      /* bad argument / inconsistent table */
+  GMQL_ERR_UNSUPPORTED = -2,  /* semantically valid in GMQL but not accelerated (no silent fallback) */
+  GMQL_ERR_CUDA = -3,         /* CUDA runtime error, message has the cudaError string */
+  GMQL_ERR_NOMEM = -4,
+  GMQL_ERR_NODEVICE = -5
+} gmql_status;
+
+typedef struct gmql_ctx gmql_ctx;       /* opaque: device, stream, memory pool, last error */
+typedef struct gmql_result gmql_result; /* opaque: device-resident result columns */
+
+/* strand encoding (GRecordKey.strand, core/GRecordKey.scala:8; BedParser.scala:166-170) */
+enum { GMQL_STRAND_BOTH = 0 /* '*' */, GMQL_STRAND_PLUS = 1 /* '+' */, GMQL_STRAND_MINUS = 2 /* '-' */ };
+
+enum { GMQL_LOC_HOST = 0, GMQL_LOC_DEVICE = 1 };
+
+/*
+ * A region dataset as structure-of-arrays: the columnar image of RDD[GRECORD]
+ * (GRECORD = (GRecordKey(id, chrom, start, stop, strand), Array[GValue]),
+ * core/DataTypes.scala:62).  String columns stay on the host and are re-attached by
+ * row index; numeric GValues are doubles (BedParser.scala:35-42) with a validity byte
+ * (0 = GNull).
+ */
+typedef struct {
+  int64_t n;                    /* number of regions (< 2^31 in this version) */
+  int32_t location;             /* GMQL_LOC_HOST (pinned or pageable) or GMQL_LOC_DEVICE: applies to every array below */
+  int32_t coord_bits;           /* 32: start/stop are int32_t[]; 64: int64_t[] */
+  const int32_t* chrom;         /* [n] chromosome index 0..n_chrom-1 into the caller's name dictionary */
+  const void* start;            /* [n] 0-based, half-open [start, stop) */
+  const void* stop;             /* [n] */
+  const int8_t* strand;         /* [n] GMQL_STRAND_*; NULL = every region is '*' */
+  const int32_t* sample;        /* [n] index 0..n_samples-1 into sample_ids; NULL = all sample 0 */
+  int32_t n_chrom;
+  int32_t n_samples;
+  const int64_t* sample_ids;    /* [n_samples] HOST array: GMQL sample ids (md5-derived, Loaders.scala:203-208) */
+  int32_t n_cols;               /* numeric value columns available to aggregates */
+  const double* const* cols;    /* HOST array of n_cols pointers (each [n], in `location`) */
+  const uint8_t* const* valid;  /* HOST array of n_cols pointers or NULL; valid[c]==NULL = no GNull in column c */
+  const int32_t* dup_of;        /* [n] or NULL.  dup_of[i] = lowest row index whose full record (sample, coords,
+                                   strand, ALL values incl. host-side strings) equals row i (== i if unique).
+                                   Lets the device reproduce the MapKey collapse (GenometricMap71.scala:93,123,186-203;
+                                   GenometricJoin.scala:134-136) whose value equality only the host can decide. */
+} gmql_regions;
+
+/* aggregates: DefaultRegionsToRegionFactory (GMQL-Server/.../DefaultRegionsToRegionFactory.scala:13-31),
+ * dispatched on RegionsToRegion.function_identifier + index (RegionsToRegion.scala:9-17). */
+typedef enum {
+  GMQL_AGG_COUNT = 0, GMQL_AGG_SUM = 1, GMQL_AGG_MIN = 2, GMQL_AGG_MAX = 3,
+  GMQL_AGG_AVG = 4, GMQL_AGG_MEDIAN = 5 /* pairwise-fold artefact == MIN, see oracle */,
+  GMQL_AGG_BAG = 6, GMQL_AGG_BAGD = 7   /* device emits matched row lists; strings are built on the host */
+} gmql_agg_kind;
+typedef struct { int32_t kind; int32_t col; } gmql_agg;
+
+/* (left/ref sample, right/exp sample) pairs from implement_mjd (MetaJoinMJD2.scala:26-111);
+ * the output sample id md5(left_id, right_id) is computed by the host side (GenometricMap71.scala:174). */
+typedef struct { int32_t left_sample; int32_t right_sample; } gmql_pair;
+
+/* COVER variants (CoverParameters/CoverFlag; GenometricCover.scala:112-117) */
+typedef enum { GMQL_COVER = 0, GMQL_FLAT = 1, GMQL_SUMMIT = 2, GMQL_HISTOGRAM = 3 } gmql_cover_flag;
+
+/* JOIN atoms after the Compiler's rewriting (GmqlParsers.scala:462-487):
+ * DLE(n)->DISTLESS(n+1), DGE(n)->DISTGREATER(n-1); predicates are strict (GenometricJoin.scala:250-251). */
+typedef enum { GMQL_J_DISTLESS = 0, GMQL_J_DISTGREATER = 1, GMQL_J_MINDIST = 2, GMQL_J_UPSTREAM = 3, GMQL_J_DOWNSTREAM = 4 } gmql_atom_kind;
+typedef struct { int32_t kind; int64_t arg; } gmql_atom;
+
+/* RegionBuilder (JoinParametersRD/RegionBuilder.scala:7-12; GenometricJoin.scala:345-372) */
+typedef enum { GMQL_B_LEFT = 0, GMQL_B_LEFT_DISTINCT = 1, GMQL_B_RIGHT = 2, GMQL_B_RIGHT_DISTINCT = 3,
+               GMQL_B_CONTIG = 4, GMQL_B_INTERSECTION = 5, GMQL_B_BOTH = 6 } gmql_builder;
+
+/* ---- context ------------------------------------------------------------------------- */
+int  gmql_abi_version(void);
+/* device: CUDA ordinal; stream: a cudaStream_t to launch on (e.g. the caller's current stream) or NULL to create one */
+int  gmql_ctx_create(int device, void* stream, gmql_ctx** out);
+void gmql_ctx_destroy(gmql_ctx* ctx);
+const char* gmql_last_error(const gmql_ctx* ctx);
+int  gmql_ctx_sync(gmql_ctx* ctx);                      /* cudaStreamSynchronize on the context stream */
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t gmql_ctx_launch_count(const gmql_ctx* ctx);
+/* pinned host memory for the SoA columns (JNI: wrap with NewDirectByteBuffer) */
+int  gmql_host_alloc(size_t bytes, void** out);
+void gmql_host_free(void* p);
+
+/* ---- MAP -------------------------------------------------------------------------------
+ * For every pair (a, b) and every ref region r of sample a: S = { e in exp sample b : e.chrom == r.chrom,
+ * r.start < e.stop, e.start < r.stop, strands compatible }; emits count = |S| (also when 0) and the
+ * aggregates over S (GenometricMap71.scala:81-147; bin-invariant).
+ *
+ * Result columns (gmql_result_column): rows are grouped by pair in pair-list order; inside pair (a, b)
+ * the rows follow sample a's regions in ascending original row index.
+ *   GMQL_COL_MAP_ROW_OFFSETS  int64 [n_pairs+1]   first row of each pair
+ *   GMQL_COL_MAP_REF_ROW      int32 [n_ref]       ref row indices grouped by ref sample (ascending inside a sample)
+ *   GMQL_COL_MAP_REF_SAMPLE_OFFSETS int64 [n_ref_samples+1]  offsets into REF_ROW
+ *   GMQL_COL_MAP_COUNT        int32 [n_rows]      |S|; -1 = row collapsed into its dup_of row (not emitted by GMQL)
+ *   GMQL_COL_AGG_VALUE + k    double [n_rows]     aggregate k (BAG/BAGD: unused)
+ *   GMQL_COL_AGG_VALID + k    uint8 [n_rows]      0 = GNull
+ *   GMQL_COL_BAG_OFFSETS      int64 [n_rows+1], GMQL_COL_BAG_ROWS int32 [...]  matched exp rows (only if a BAG/BAGD is requested)
+ */
+int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp,
+             const gmql_pair* pairs, int64_t n_pairs,
+             const gmql_agg* aggs, int32_t n_aggs, gmql_result** out);
+
+/* ---- COVER family ----------------------------------------------------------------------
+ * sample_group: HOST [in->n_samples] group index 0..n_groups-1 per sample (implement_mgd,
+ * MetaGroupMGD.scala:20-79) or NULL = one group (id 0L).  min_acc/max_acc: HOST [n_groups] thresholds
+ * already resolved from N/ANY/ALL (GenometricCover.scala:57-79); use gmql_cover_count_samples for the
+ * ungrouped ALL case.  bin_size = BinSize.Cover (2000): observable in results (stop%bin==0 extension,
+ * SUMMIT bin cuts; GenometricCover.scala:345-360, 269-316).
+ *
+ * Result columns: one row per output region, sorted by (group, strand, chrom, start):
+ *   GMQL_COL_COV_GROUP int32, GMQL_COL_COV_CHROM int32, GMQL_COL_COV_START int64, GMQL_COL_COV_STOP int64,
+ *   GMQL_COL_COV_STRAND int8, GMQL_COL_COV_ACC int32 (AccIndex), GMQL_COL_COV_JACC_INTERSECT double,
+ *   GMQL_COL_COV_JACC_RESULT double, GMQL_COL_AGG_VALUE/VALID + k.
+ */
+int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups,
+               int32_t flag, const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size,
+               const gmql_agg* aggs, int32_t n_aggs, gmql_result** out);
+/* number of samples that own at least one region (GenometricCover.scala:64) */
+int gmql_cover_count_samples(gmql_ctx* ctx, const gmql_regions* in, int32_t* out_count);
+
+/* ---- JOIN ------------------------------------------------------------------------------
+ * atoms: one JoinQuadruple's atomic conditions in script order (<= 4).  bin_size = BinSize.Join (5000) and
+ * max_bin_distance (100000) define the candidate window exactly as GenometricJoin.scala:75-79,284-342.
+ * left_eq/right_eq: optional per-row int64 codes; when both non-NULL a pair also needs equal codes
+ * (joinOnAttributes, GenometricJoin.scala:102-114; the host dictionary-encodes the attribute tuple).
+ *
+ * Result columns: one row per output record (unordered, as the RDD is):
+ *   GMQL_COL_JOIN_LEFT_ROW int32, GMQL_COL_JOIN_RIGHT_ROW int32 (-1 for LEFT_DISTINCT),
+ *   GMQL_COL_JOIN_PAIR int32 (index into pairs), GMQL_COL_JOIN_START int64, GMQL_COL_JOIN_STOP int64,
+ *   GMQL_COL_JOIN_STRAND int8, GMQL_COL_JOIN_CHROM int32 (built region, GenometricJoin.scala:345-372).
+ */
+int gmql_join(gmql_ctx* ctx, const gmql_regions* left, const gmql_regions* right,
+              const gmql_pair* pairs, int64_t n_pairs,
+              const gmql_atom* atoms, int32_t n_atoms, int32_t builder,
+              int64_t bin_size, int64_t max_bin_distance,
+              const int64_t* left_eq, const int64_t* right_eq,
+              gmql_result** out);
+
+/* ---- results --------------------------------------------------------------------------- */
+enum {
+  GMQL_COL_MAP_ROW_OFFSETS = 1, GMQL_COL_MAP_REF_ROW = 2, GMQL_COL_MAP_REF_SAMPLE_OFFSETS = 3, GMQL_COL_MAP_COUNT = 4,
+  GMQL_COL_BAG_OFFSETS = 5, GMQL_COL_BAG_ROWS = 6,
+  GMQL_COL_COV_GROUP = 16, GMQL_COL_COV_CHROM = 17, GMQL_COL_COV_START = 18, GMQL_COL_COV_STOP = 19,
+  GMQL_COL_COV_STRAND = 20, GMQL_COL_COV_ACC = 21, GMQL_COL_COV_JACC_INTERSECT = 22, GMQL_COL_COV_JACC_RESULT = 23,
+  GMQL_COL_JOIN_LEFT_ROW = 32, GMQL_COL_JOIN_RIGHT_ROW = 33, GMQL_COL_JOIN_PAIR = 34, GMQL_COL_JOIN_START = 35,
+  GMQL_COL_JOIN_STOP = 36, GMQL_COL_JOIN_STRAND = 37, GMQL_COL_JOIN_CHROM = 38,
+  GMQL_COL_AGG_VALUE = 256, /* + aggregate index */
+  GMQL_COL_AGG_VALID = 512  /* + aggregate index */
+};
+int64_t gmql_result_rows(const gmql_result* r);                 /* output rows (regions / pairs) */
+/* element count and element size of a column; <0 if the result has no such column */
+int64_t gmql_result_column_len(const gmql_result* r, int32_t col);
+int32_t gmql_result_column_elem_size(const gmql_result* r, int32_t col);
+/* device pointer of a column (valid until gmql_result_free), NULL if absent */
+const void* gmql_result_column_device(const gmql_result* r, int32_t col);
+/* copy a column to host memory (dst must hold len*elem_size bytes); synchronises the context stream */
+int  gmql_result_column_copy(gmql_ctx* ctx, const gmql_result* r, int32_t col, void* dst);
+/* COVER results only: a device-located gmql_regions view (sample = group index, one value column = AccIndex)
+ * so that `C = COVER(..) E; M = MAP() C E` chains without a host round trip (the analogue of the reference's
+ * per-node memo, GMQLSparkExecutor.scala:252-253).  `storage` keeps the small host arrays the view points at. */
+typedef struct { int64_t sample_ids[1]; const double* cols[1]; const uint8_t* valid[1]; } gmql_view_storage;
+int  gmql_result_as_regions(gmql_ctx* ctx, const gmql_result* r, gmql_regions* view, gmql_view_storage* storage);
+void gmql_result_free(gmql_ctx* ctx, gmql_result* r);
+
+/* device time (ms, CUDA events on the context stream) of the last operator call: first kernel -> last kernel,
+ * host<->device copies excluded (BASELINE.md §2 t_device), and the H2D part separately */
+double gmql_last_device_ms(const gmql_ctx* ctx);
+double gmql_last_h2d_ms(const gmql_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMQL_CUDA_H */
