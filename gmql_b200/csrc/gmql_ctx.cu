@@ -1,0 +1,164 @@
+// gmql_ctx.cu — context, dataset upload, result accessors of the C ABI (include/gmql_cuda.h).
+#include "common.cuh"
+
+extern "C" int gmql_abi_version(void) { return GMQL_ABI_VERSION; }
+
+extern "C" int gmql_ctx_create(int device, void* stream, gmql_ctx** out) {
+  if (!out) return GMQL_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) { cudaGetLastError(); return GMQL_ERR_NODEVICE; }
+  if (device < 0 || device >= count) return GMQL_ERR_INVALID;
+  gmql_ctx* c = new gmql_ctx();
+  c->device = device;
+  try {
+    CUDA_TRY(cudaSetDevice(device));
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaEventCreate(&c->ev_k0));
+    CUDA_TRY(cudaEventCreate(&c->ev_k1));
+    CUDA_TRY(cudaEventCreate(&c->ev_h0));
+    CUDA_TRY(cudaEventCreate(&c->ev_h1));
+    // keep freed blocks cached in the stream-ordered pool (operators allocate scratch every call)
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ull;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  } catch (const gmql_error& ex) {
+    delete c;
+    return ex.code;
+  }
+  *out = c;
+  return GMQL_OK;
+}
+
+extern "C" void gmql_ctx_destroy(gmql_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->ev_k0) cudaEventDestroy(c->ev_k0);
+  if (c->ev_k1) cudaEventDestroy(c->ev_k1);
+  if (c->ev_h0) cudaEventDestroy(c->ev_h0);
+  if (c->ev_h1) cudaEventDestroy(c->ev_h1);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char* gmql_last_error(const gmql_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int gmql_ctx_sync(gmql_ctx* c) {
+  if (!c) return GMQL_ERR_INVALID;
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return GMQL_ERR_CUDA; }
+  return GMQL_OK;
+}
+
+extern "C" int64_t gmql_ctx_launch_count(const gmql_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int gmql_host_alloc(size_t bytes, void** out) {
+  if (!out) return GMQL_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return GMQL_ERR_NOMEM; }
+  return GMQL_OK;
+}
+extern "C" void gmql_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" double gmql_last_device_ms(const gmql_ctx* c) {
+  if (!c) return -1.0;
+  float ms = 0.f;
+  if (cudaEventSynchronize(c->ev_k1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+  return (double)ms;
+}
+extern "C" double gmql_last_h2d_ms(const gmql_ctx* c) {
+  if (!c) return -1.0;
+  float ms = 0.f;
+  if (cudaEventSynchronize(c->ev_h1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, c->ev_h0, c->ev_h1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+  return (double)ms;
+}
+
+// ------------------------------------------------------------------------------------------------
+static const void* upload_array(gmql_ctx* ctx, const void* src, size_t bytes, int location, DevRegions* out) {
+  if (!src) return nullptr;
+  if (location == GMQL_LOC_DEVICE) return src;
+  DevBuf<uint8_t> b(ctx, (int64_t)(bytes ? bytes : 1));
+  if (bytes) CUDA_TRY(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  out->h2d_bytes += (int64_t)bytes;
+  const void* p = b.p;
+  out->owned.push_back(std::move(b));
+  return p;
+}
+
+void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector<int>& need_cols, DevRegions* out) {
+  GMQL_REQUIRE(r != nullptr, GMQL_ERR_INVALID, "null gmql_regions");
+  GMQL_REQUIRE(r->n >= 0 && r->n < (int64_t)0x7fffffff, GMQL_ERR_UNSUPPORTED, "datasets of >= 2^31 regions are not supported in this version");
+  GMQL_REQUIRE(r->coord_bits == 32 || r->coord_bits == 64, GMQL_ERR_INVALID, "coord_bits must be 32 or 64");
+  GMQL_REQUIRE(r->n == 0 || (r->chrom && r->start && r->stop), GMQL_ERR_INVALID, "chrom/start/stop are required");
+  GMQL_REQUIRE(r->n_chrom > 0 && r->n_samples > 0, GMQL_ERR_INVALID, "n_chrom and n_samples must be positive");
+  out->n = r->n;
+  out->coord_bits = r->coord_bits;
+  out->n_chrom = r->n_chrom;
+  out->n_samples = r->n_samples;
+  out->n_cols = r->n_cols;
+  size_t cb = (size_t)(r->coord_bits / 8);
+  size_t n = (size_t)r->n;
+  out->chrom = (const int32_t*)upload_array(ctx, r->chrom, n * 4, r->location, out);
+  out->start = upload_array(ctx, r->start, n * cb, r->location, out);
+  out->stop = upload_array(ctx, r->stop, n * cb, r->location, out);
+  out->strand = (const int8_t*)upload_array(ctx, r->strand, n, r->location, out);
+  out->sample = (const int32_t*)upload_array(ctx, r->sample, n * 4, r->location, out);
+  out->dup_of = (const int32_t*)upload_array(ctx, r->dup_of, n * 4, r->location, out);
+  out->cols.assign((size_t)std::max(0, r->n_cols), nullptr);
+  out->valid.assign((size_t)std::max(0, r->n_cols), nullptr);
+  for (int c : need_cols) {
+    GMQL_REQUIRE(c >= 0 && c < r->n_cols && r->cols && r->cols[c], GMQL_ERR_INVALID, "aggregate refers to a value column that is not provided");
+    if (out->cols[c]) continue;
+    out->cols[c] = (const double*)upload_array(ctx, r->cols[c], n * 8, r->location, out);
+    if (r->valid && r->valid[c]) out->valid[c] = (const uint8_t*)upload_array(ctx, r->valid[c], n, r->location, out);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t gmql_result_rows(const gmql_result* r) { return r ? r->rows : -1; }
+
+extern "C" int64_t gmql_result_column_len(const gmql_result* r, int32_t col) {
+  if (!r) return -1;
+  auto it = r->cols.find(col);
+  return it == r->cols.end() ? -1 : it->second.len;
+}
+extern "C" int32_t gmql_result_column_elem_size(const gmql_result* r, int32_t col) {
+  if (!r) return -1;
+  auto it = r->cols.find(col);
+  return it == r->cols.end() ? -1 : it->second.elem;
+}
+extern "C" const void* gmql_result_column_device(const gmql_result* r, int32_t col) {
+  if (!r) return nullptr;
+  auto it = r->cols.find(col);
+  return it == r->cols.end() ? nullptr : it->second.p;
+}
+extern "C" int gmql_result_column_copy(gmql_ctx* ctx, const gmql_result* r, int32_t col, void* dst) {
+  if (!ctx || !r) return GMQL_ERR_INVALID;
+  auto it = r->cols.find(col);
+  if (it == r->cols.end()) { ctx->err = "result has no such column"; return GMQL_ERR_INVALID; }
+  size_t bytes = (size_t)it->second.len * (size_t)it->second.elem;
+  if (bytes) {
+    if (!dst) { ctx->err = "null destination"; return GMQL_ERR_INVALID; }
+    cudaError_t e = cudaMemcpyAsync(dst, it->second.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return GMQL_ERR_CUDA; }
+  }
+  return GMQL_OK;
+}
+
+extern "C" void gmql_result_free(gmql_ctx* ctx, gmql_result* r) {
+  if (!r) return;
+  for (auto& kv : r->cols)
+    if (kv.second.p) { if (ctx) cudaFreeAsync(kv.second.p, ctx->stream); else cudaFree(kv.second.p); }
+  if (r->view_acc_double) { if (ctx) cudaFreeAsync(r->view_acc_double, ctx->stream); else cudaFree(r->view_acc_double); }
+  delete r;
+}

@@ -1,0 +1,378 @@
+// gmql_map.cu — genometric MAP on the device.
+//
+// Replaces GenometricMap71.apply/execute (GMQL-Spark/.../RegionsOperators/GenometricMap/GenometricMap71.scala:28-150)
+// and the aggregate folds of DefaultRegionsToRegionFactory (GMQL-Server/.../DefaultRegionsToRegionFactory.scala:58-126).
+//
+// Design (not a port of the bin/cogroup/reduceByKey plan): the *small* side (reference regions, all ref samples
+// pooled) becomes an interval index (sorted linear starts + running max stop); the *large* side (experiment regions)
+// is streamed once from HBM in its original order, each region finds the reference regions it overlaps and
+// accumulates straight into the output row of (pair, ref region).  The output table — one row per (pair, ref region),
+// zero rows included (GenometricMap71.scala:115-116) — is written by a fill kernel and a finalise kernel.
+#include "index.cuh"
+
+namespace {
+
+struct MapAggPlan {
+  // per distinct input column
+  int n_cols = 0;
+  int col_id[8];
+  int need_sum[8], need_min[8], need_max[8];
+  // per aggregate
+  int n_aggs = 0;
+  int kind[16], slot[16];  // slot = index into the distinct-column tables
+};
+
+struct MapAcc {
+  int* count;                    // [n_rows]
+  int* nn[8];                    // non-null contributors per distinct column
+  double* sum[8];
+  unsigned long long* mn[8];
+  unsigned long long* mx[8];
+};
+
+struct ExpCols {
+  const double* v[8];
+  const uint8_t* ok[8];
+};
+
+__device__ __forceinline__ unsigned long long dbl_key_min(double v) {
+  // order-preserving map double -> uint64 (-0.0 < +0.0 as in java.lang.Math.min); NaN maps to 0 so that it wins a min
+  if (v != v) return 0ull;
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ unsigned long long dbl_key_max(double v) {
+  if (v != v) return ~0ull;  // NaN wins a max (Math.max)
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dbl_from_key(unsigned long long k) {
+  unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// ---- reference bookkeeping ---------------------------------------------------------------------
+__global__ void k_sample_keys(const int32_t* __restrict__ sample, int64_t n, int n_samples, uint32_t* __restrict__ keys, uint32_t* __restrict__ rows, unsigned int* __restrict__ counts, int* __restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int s = sample ? sample[i] : 0;
+    if (s < 0 || s >= n_samples) { *bad = 1; s = 0; }
+    keys[i] = (uint32_t)s;
+    rows[i] = (uint32_t)i;
+    atomicAdd(&counts[s], 1u);
+  }
+}
+
+// rank of each ref row inside its sample (ascending original row index), for canonical rows of dup groups
+__global__ void k_ref_rank(const uint32_t* __restrict__ rows_by_sample, const uint32_t* __restrict__ keys_sorted, const int64_t* __restrict__ sample_off, int64_t n, uint32_t* __restrict__ rank_of_row) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t row = rows_by_sample[k];
+    rank_of_row[row] = (uint32_t)(k - sample_off[keys_sorted[k]]);
+  }
+}
+
+__global__ void k_pair_rows(const int32_t* __restrict__ pl, const int32_t* __restrict__ pr, int64_t n_pairs, int n_ls, int n_rs, const unsigned int* __restrict__ sample_cnt, int64_t* __restrict__ rows_of_pair, int* __restrict__ bad) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (int64_t)gridDim.x * blockDim.x) {
+    int a = pl[p], b = pr[p];
+    if (a < 0 || a >= n_ls || b < 0 || b >= n_rs) { *bad = 1; rows_of_pair[p] = 0; continue; }
+    rows_of_pair[p] = (int64_t)sample_cnt[a];
+  }
+}
+
+__global__ void k_pair_base(const int32_t* __restrict__ pl, const int32_t* __restrict__ pr, int64_t n_pairs, int n_rs, const int64_t* __restrict__ row_off, long long* __restrict__ pair_base, int* __restrict__ bad) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cell = (int64_t)pl[p] * n_rs + pr[p];
+    long long old = atomicExch((unsigned long long*)&pair_base[cell], (unsigned long long)row_off[p]);
+    if (old != -1ll) *bad = 2;  // the same (ref, exp) pair listed twice
+  }
+}
+
+// per sorted index entry: sample of the ref row and the rank of its canonical (dup_of) row
+__global__ void k_index_payload(const uint32_t* __restrict__ rows, int64_t n, const int32_t* __restrict__ sample, const int8_t* __restrict__ strand, const int32_t* __restrict__ dup_of,
+                                const uint32_t* __restrict__ rank_of_row, int32_t* __restrict__ s_sample, uint32_t* __restrict__ s_rank, int8_t* __restrict__ s_strand) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t row = rows[k];
+    s_sample[k] = sample ? sample[row] : 0;
+    s_strand[k] = strand ? strand[row] : (int8_t)0;
+    uint32_t canon = dup_of ? (uint32_t)dup_of[row] : row;
+    s_rank[k] = rank_of_row[canon];
+  }
+}
+
+// ---- the streaming kernel ------------------------------------------------------------------------
+template <typename K>
+__global__ void __launch_bounds__(256) k_map_stream(
+    const int32_t* __restrict__ e_chrom, const void* __restrict__ e_start, const void* __restrict__ e_stop, int e_bits,
+    const int8_t* __restrict__ e_strand, const int32_t* __restrict__ e_sample, int64_t n_exp, int n_exp_samples,
+    LinMap lm, const K* __restrict__ r_start, const K* __restrict__ r_stop, const K* __restrict__ r_pmax, int64_t n_ref,
+    const int32_t* __restrict__ r_sample, const uint32_t* __restrict__ r_rank, const int8_t* __restrict__ r_strand,
+    const long long* __restrict__ pair_base, MapAggPlan plan, ExpCols ec, MapAcc acc, int* __restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_exp; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = e_chrom[i];
+    if (c < 0 || c >= lm.n_chrom) { *bad = 1; continue; }
+    int64_t s = ld_coord(e_start, e_bits, i);
+    int64_t e = ld_coord(e_stop, e_bits, i);
+    int64_t span = lm.span[c];
+    if (s >= span || e <= 0) continue;  // no reference region can satisfy r.start < e.stop && e.start < r.stop
+    if (s < 0) { *bad = 1; continue; }
+    if (e > span + 1) e = span + 1;
+    int b = e_sample ? e_sample[i] : 0;
+    if (b < 0 || b >= n_exp_samples) { *bad = 1; continue; }
+    int st = e_strand ? (int)e_strand[i] : 0;
+    K ls = (K)(lm.coff[c] + (uint64_t)s);
+    K le = (K)(lm.coff[c] + (uint64_t)e);
+    int64_t hi = lower_bound_dev<K>(r_start, n_ref, le);  // ref entries with start < e.stop
+    for (int64_t k = hi - 1; k >= 0 && r_pmax[k] > ls; --k) {
+      if (r_stop[k] <= ls) continue;
+      if (!strand_ok((int)r_strand[k], st)) continue;
+      long long base = pair_base[(int64_t)r_sample[k] * n_exp_samples + b];
+      if (base < 0) continue;
+      int64_t row = base + r_rank[k];
+      atomicAdd(&acc.count[row], 1);
+      for (int q = 0; q < plan.n_cols; ++q) {
+        if (ec.ok[q] && !ec.ok[q][i]) continue;
+        double v = ec.v[q][i];
+        atomicAdd(&acc.nn[q][row], 1);
+        if (plan.need_sum[q]) atomicAdd(&acc.sum[q][row], v);
+        if (plan.need_min[q]) atomicMin(&acc.mn[q][row], dbl_key_min(v));
+        if (plan.need_max[q]) atomicMax(&acc.mx[q][row], dbl_key_max(v));
+      }
+    }
+  }
+}
+
+// rows of non-canonical duplicates are not emitted by the reference (MapKey collapse): flag them with count = -1
+__global__ void k_mark_dups(const int32_t* __restrict__ pl, const int64_t* __restrict__ row_off, int64_t n_pairs, const int64_t* __restrict__ sample_off,
+                            const uint32_t* __restrict__ rows_by_sample, const int32_t* __restrict__ dup_of, int* __restrict__ count) {
+  // one block per pair (grid-stride), threads over the ref rows of the pair's sample
+  for (int64_t p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+    int a = pl[p];
+    int64_t s0 = sample_off[a], s1 = sample_off[a + 1];
+    for (int64_t k = s0 + threadIdx.x; k < s1; k += blockDim.x) {
+      uint32_t row = rows_by_sample[k];
+      if ((uint32_t)dup_of[row] != row) count[row_off[p] + (k - s0)] = -1;
+    }
+  }
+}
+
+struct MapOut {
+  double* value[16];
+  uint8_t* valid[16];
+};
+
+__global__ void __launch_bounds__(256) k_map_finalize(int64_t n_rows, MapAggPlan plan, MapAcc acc, MapOut out) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+    int cnt = acc.count[r];
+    for (int a = 0; a < plan.n_aggs; ++a) {
+      int kind = plan.kind[a], q = plan.slot[a];
+      double v = 0.0;
+      uint8_t ok = 0;
+      if (kind == GMQL_AGG_COUNT) { v = (double)(cnt < 0 ? 0 : cnt); ok = 1; }  // funOut = GDouble(count), DefaultRegionsToRegionFactory.scala:62
+      else {
+        int nn = acc.nn[q][r];
+        if (nn > 0) {
+          ok = 1;
+          if (kind == GMQL_AGG_SUM) v = acc.sum[q][r];                       // :69-82
+          else if (kind == GMQL_AGG_AVG) v = acc.sum[q][r] / (double)nn;     // :112-126
+          else if (kind == GMQL_AGG_MIN) v = dbl_from_key(acc.mn[q][r]);     // :84-96
+          else if (kind == GMQL_AGG_MAX) v = dbl_from_key(acc.mx[q][r]);     // :98-110
+          else if (kind == GMQL_AGG_MEDIAN) {                                // :33-56 pairwise fold => min; (m+m)/2 once two values met
+            double m = dbl_from_key(acc.mn[q][r]);
+            v = nn >= 2 ? (m + m) / 2 : m;
+          }
+        }
+      }
+      out.value[a][r] = v;
+      out.valid[a][r] = ok;
+    }
+  }
+}
+
+static void plan_aggs(const gmql_agg* aggs, int n_aggs, int n_cols_avail, MapAggPlan* plan, std::vector<int>* need_cols) {
+  GMQL_REQUIRE(n_aggs >= 0 && n_aggs <= 16, GMQL_ERR_UNSUPPORTED, "at most 16 aggregates per call");
+  GMQL_REQUIRE(n_aggs == 0 || aggs != nullptr, GMQL_ERR_INVALID, "null aggregate list");
+  *plan = MapAggPlan();
+  plan->n_aggs = n_aggs;
+  for (int a = 0; a < n_aggs; ++a) {
+    int kind = aggs[a].kind;
+    plan->kind[a] = kind;
+    plan->slot[a] = -1;
+    if (kind == GMQL_AGG_COUNT) continue;
+    GMQL_REQUIRE(kind != GMQL_AGG_BAG && kind != GMQL_AGG_BAGD, GMQL_ERR_UNSUPPORTED,
+                 "BAG/BAGD aggregates are built on the host from gmql_join-style match lists; not available in gmql_map yet");
+    GMQL_REQUIRE(kind >= GMQL_AGG_SUM && kind <= GMQL_AGG_MEDIAN, GMQL_ERR_INVALID,
+                 "unknown aggregate kind (user closures have no function_identifier and cannot run on the device)");
+    int col = aggs[a].col;
+    GMQL_REQUIRE(col >= 0 && col < n_cols_avail, GMQL_ERR_INVALID, "aggregate column index out of range");
+    int q = -1;
+    for (int j = 0; j < plan->n_cols; ++j) if (plan->col_id[j] == col) q = j;
+    if (q < 0) {
+      GMQL_REQUIRE(plan->n_cols < 8, GMQL_ERR_UNSUPPORTED, "at most 8 distinct aggregated columns per call");
+      q = plan->n_cols++;
+      plan->col_id[q] = col;
+      need_cols->push_back(col);
+    }
+    plan->slot[a] = q;
+    if (kind == GMQL_AGG_SUM || kind == GMQL_AGG_AVG) plan->need_sum[q] = 1;
+    if (kind == GMQL_AGG_MIN || kind == GMQL_AGG_MEDIAN) plan->need_min[q] = 1;
+    if (kind == GMQL_AGG_MAX) plan->need_max[q] = 1;
+  }
+}
+
+template <typename K>
+static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp, const gmql_pair* pairs, int64_t n_pairs,
+                    const MapAggPlan& plan, gmql_result* res) {
+  const int64_t n_ref = ref.n, n_exp = exp.n;
+  const int n_ls = ref.n_samples, n_rs = exp.n_samples;
+
+  // pairs -> device
+  std::vector<int32_t> h_pl((size_t)n_pairs), h_pr((size_t)n_pairs);
+  for (int64_t p = 0; p < n_pairs; ++p) { h_pl[p] = pairs[p].left_sample; h_pr[p] = pairs[p].right_sample; }
+  DevBuf<int32_t> d_pl(ctx, n_pairs), d_pr(ctx, n_pairs);
+  if (n_pairs) {
+    CUDA_TRY(cudaMemcpyAsync(d_pl.p, h_pl.data(), 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_pr.p, h_pr.data(), 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  cudaEventRecord(ctx->ev_h1, ctx->stream);
+  DeviceTimer timer(ctx);
+
+  DevBuf<int> bad(ctx, 1);
+  bad.zero();
+
+  // reference rows grouped by sample (stable: ascending row index inside a sample)
+  DevBuf<uint32_t> sk_a(ctx, n_ref), sk_b(ctx, n_ref), sr_a(ctx, n_ref), sr_b(ctx, n_ref);
+  DevBuf<unsigned int> sample_cnt(ctx, n_ls);
+  sample_cnt.zero();
+  DevBuf<int64_t> sample_off(ctx, (int64_t)n_ls + 1);
+  if (n_ref) LAUNCH(ctx, k_sample_keys, grid_for(ctx, n_ref, 256), 256, 0, ref.sample, n_ref, n_ls, sk_a.p, sr_a.p, sample_cnt.p, bad.p);
+  uint32_t* keys_sorted = sk_a.p; uint32_t* rows_by_sample = sr_a.p;
+  radix_sort<uint32_t>(ctx, sk_a.p, sk_b.p, sr_a.p, sr_b.p, n_ref, bits_for((uint64_t)(n_ls - 1)), &keys_sorted, &rows_by_sample);
+  device_scan<unsigned int, int64_t, OpSum<int64_t>, false>(ctx, sample_cnt.p, sample_off.p, n_ls, sample_off.p + n_ls);
+  DevBuf<uint32_t> rank_of_row(ctx, n_ref);
+  if (n_ref) LAUNCH(ctx, k_ref_rank, grid_for(ctx, n_ref, 256), 256, 0, rows_by_sample, keys_sorted, sample_off.p, n_ref, rank_of_row.p);
+
+  // rows per pair, row offsets, dense (ref sample x exp sample) -> first row table
+  DevBuf<int64_t> row_off(ctx, n_pairs + 1);
+  DevBuf<long long> pair_base(ctx, (int64_t)n_ls * n_rs);
+  pair_base.fill_byte(0xff);
+  if (n_pairs) {
+    LAUNCH(ctx, k_pair_rows, grid_for(ctx, n_pairs, 256), 256, 0, d_pl.p, d_pr.p, n_pairs, n_ls, n_rs, sample_cnt.p, row_off.p, bad.p);
+    device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, row_off.p, row_off.p, n_pairs, row_off.p + n_pairs);
+  } else {
+    row_off.zero();
+  }
+  int64_t n_rows = 0;
+  int h_bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n_rows, row_off.p + n_pairs, sizeof n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "sample index out of range (regions or pair list)");
+  if (n_pairs) LAUNCH(ctx, k_pair_base, grid_for(ctx, n_pairs, 256), 256, 0, d_pl.p, d_pr.p, n_pairs, n_rs, row_off.p, pair_base.p, bad.p);
+
+  // interval index over the reference
+  SpanTable spans;
+  build_span_table(ctx, &ref, nullptr, &spans);
+  LinMap lm = spans.map();
+  IntervalIndex<K> ix;
+  build_index<K>(ctx, ref, nullptr, 1, lm, &ix);
+  DevBuf<int32_t> s_sample(ctx, n_ref);
+  DevBuf<uint32_t> s_rank(ctx, n_ref);
+  DevBuf<int8_t> s_strand(ctx, n_ref);
+  if (n_ref) LAUNCH(ctx, k_index_payload, grid_for(ctx, n_ref, 256), 256, 0, ix.row, n_ref, ref.sample, ref.strand, ref.dup_of, rank_of_row.p, s_sample.p, s_rank.p, s_strand.p);
+
+  // accumulators
+  MapAcc acc;
+  memset(&acc, 0, sizeof acc);
+  DevBuf<int> count(ctx, n_rows);
+  count.zero();
+  acc.count = count.p;
+  DevBuf<int> nn[8];
+  DevBuf<double> sum[8];
+  DevBuf<unsigned long long> mn[8], mx[8];
+  ExpCols ec;
+  memset(&ec, 0, sizeof ec);
+  for (int q = 0; q < plan.n_cols; ++q) {
+    nn[q].alloc(ctx, n_rows); nn[q].zero(); acc.nn[q] = nn[q].p;
+    if (plan.need_sum[q]) { sum[q].alloc(ctx, n_rows); sum[q].zero(); acc.sum[q] = sum[q].p; }
+    if (plan.need_min[q]) { mn[q].alloc(ctx, n_rows); mn[q].fill_byte(0xff); acc.mn[q] = mn[q].p; }
+    if (plan.need_max[q]) { mx[q].alloc(ctx, n_rows); mx[q].zero(); acc.mx[q] = mx[q].p; }
+    ec.v[q] = exp.cols[plan.col_id[q]];
+    ec.ok[q] = exp.valid[plan.col_id[q]];
+  }
+
+  if (n_exp && n_ref && n_rows) {
+    int g = grid_for(ctx, n_exp, 256, 2);
+    LAUNCH(ctx, (k_map_stream<K>), g, 256, 0, exp.chrom, exp.start, exp.stop, exp.coord_bits, exp.strand, exp.sample, n_exp, n_rs,
+           lm, ix.start, ix.stop.p, ix.pmax.p, n_ref, s_sample.p, s_rank.p, s_strand.p, pair_base.p, plan, ec, acc, bad.p);
+  }
+  if (ref.dup_of && n_pairs && n_rows)
+    LAUNCH(ctx, k_mark_dups, (int)std::min<int64_t>(n_pairs, (int64_t)ctx->num_sms * 8), 128, 0, d_pl.p, row_off.p, n_pairs, sample_off.p, rows_by_sample, ref.dup_of, count.p);
+
+  // outputs
+  MapOut mo;
+  memset(&mo, 0, sizeof mo);
+  std::vector<DevBuf<double>> ov((size_t)plan.n_aggs);
+  std::vector<DevBuf<uint8_t>> ok((size_t)plan.n_aggs);
+  for (int a = 0; a < plan.n_aggs; ++a) {
+    ov[a].alloc(ctx, n_rows); ok[a].alloc(ctx, n_rows);
+    mo.value[a] = ov[a].p; mo.valid[a] = ok[a].p;
+  }
+  if (plan.n_aggs && n_rows) LAUNCH(ctx, k_map_finalize, grid_for(ctx, n_rows, 256), 256, 0, n_rows, plan, acc, mo);
+  timer.stop();
+
+  CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  GMQL_REQUIRE(h_bad != 2, GMQL_ERR_INVALID, "the same (ref sample, exp sample) pair is listed twice");
+  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "experiment region with chromosome/sample index out of range or negative start");
+
+  res->rows = n_rows;
+  res->kind = 1;
+  result_add(res, GMQL_COL_MAP_ROW_OFFSETS, row_off);
+  // REF_ROW: copy out of the ping-pong buffer that holds it
+  {
+    DevBuf<int32_t> rr(ctx, n_ref);
+    if (n_ref) CUDA_TRY(cudaMemcpyAsync(rr.p, rows_by_sample, 4 * (size_t)n_ref, cudaMemcpyDeviceToDevice, ctx->stream));
+    result_add(res, GMQL_COL_MAP_REF_ROW, rr);
+  }
+  result_add(res, GMQL_COL_MAP_REF_SAMPLE_OFFSETS, sample_off);
+  result_add(res, GMQL_COL_MAP_COUNT, count);
+  for (int a = 0; a < plan.n_aggs; ++a) {
+    result_add(res, GMQL_COL_AGG_VALUE + a, ov[a]);
+    result_add(res, GMQL_COL_AGG_VALID + a, ok[a]);
+  }
+}
+
+}  // namespace
+
+extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp, const gmql_pair* pairs, int64_t n_pairs,
+                        const gmql_agg* aggs, int32_t n_aggs, gmql_result** out) {
+  if (!ctx || !out) return GMQL_ERR_INVALID;
+  *out = nullptr;
+  gmql_result* res = nullptr;
+  try {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    GMQL_REQUIRE(ref && exp, GMQL_ERR_INVALID, "null dataset");
+    GMQL_REQUIRE(n_pairs >= 0 && (n_pairs == 0 || pairs), GMQL_ERR_INVALID, "bad pair list");
+    GMQL_REQUIRE(ref->n_chrom == exp->n_chrom, GMQL_ERR_INVALID, "ref and exp must share one chromosome dictionary (n_chrom differs)");
+    MapAggPlan plan;
+    std::vector<int> need_cols;
+    plan_aggs(aggs, n_aggs, exp->n_cols, &plan, &need_cols);
+    cudaEventRecord(ctx->ev_h0, ctx->stream);
+    DevRegions dref, dexp;
+    gmql_upload_regions(ctx, ref, std::vector<int>(), &dref);
+    gmql_upload_regions(ctx, exp, need_cols, &dexp);
+    res = new gmql_result();
+    run_map<uint64_t>(ctx, dref, dexp, pairs, n_pairs, plan, res);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = res;
+    return GMQL_OK;
+  } catch (const gmql_error& ex) {
+    ctx->err = ex.what();
+    if (res) gmql_result_free(ctx, res);
+    cudaStreamSynchronize(ctx->stream);
+    return ex.code;
+  } catch (const std::exception& ex) {
+    ctx->err = ex.what();
+    if (res) gmql_result_free(ctx, res);
+    return GMQL_ERR_INVALID;
+  }
+}

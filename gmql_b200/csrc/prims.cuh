@@ -1,0 +1,316 @@
+// prims.cuh — hand-written device primitives: LSD radix sort (32/64-bit keys, optional 32-bit payload),
+// device-wide scans, lower/upper bound.  HBM-bound integer work: coalesced warp-striped loads, shared-memory
+// ranking, grids sized as multiples of the SM count (148 on B200).
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// binary searches over sorted device arrays
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+__device__ __forceinline__ int64_t lower_bound_dev(const K* __restrict__ a, int64_t n, K x) {
+  int64_t lo = 0, hi = n;  // first index with a[i] >= x
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+template <typename K>
+__device__ __forceinline__ int64_t upper_bound_dev(const K* __restrict__ a, int64_t n, K x) {
+  int64_t lo = 0, hi = n;  // first index with a[i] > x
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (a[mid] <= x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-wide scan (reduce -> scan partials -> apply); Op is an associative functor with identity()
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct OpSum { __device__ __forceinline__ T operator()(T a, T b) const { return a + b; } __device__ __forceinline__ static T identity() { return (T)0; } };
+template <typename T> struct OpMax { __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; } __device__ __forceinline__ static T identity() { return (T)0; } };
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_scan_excl(T v, T* total, Op op) {
+  // exclusive scan of one value per thread across a 256-thread block
+  __shared__ T warp_tot[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x = op(y, x);
+  }
+  if (lane == 31) warp_tot[w] = x;
+  __syncthreads();
+  T base = Op::identity();
+  for (int i = 0; i < w; ++i) base = op(base, warp_tot[i]);
+  T tot = Op::identity();
+  for (int i = 0; i < SCAN_THREADS / 32; ++i) tot = op(tot, warp_tot[i]);
+  T incl = op(base, x);
+  T prev = __shfl_up_sync(0xffffffffu, incl, 1);
+  T excl = lane == 0 ? base : prev;
+  __syncthreads();
+  *total = tot;
+  return excl;
+}
+
+template <typename Tin, typename T, typename Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const Tin* __restrict__ in, int64_t n, T* __restrict__ partials, int64_t tiles_per_block) {
+  Op op;
+  T acc = Op::identity();
+  int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
+  for (int64_t t = t0; t < t0 + tiles_per_block; ++t) {
+    int64_t base = t * SCAN_TILE;
+    if (base >= n) break;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      int64_t i = base + (int64_t)j * SCAN_THREADS + threadIdx.x;
+      if (i < n) acc = op(acc, (T)in[i]);
+    }
+  }
+  __shared__ T red[SCAN_THREADS];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = SCAN_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = op(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = red[0];
+}
+
+template <typename T, typename Op>
+__global__ void __launch_bounds__(1024) k_scan_partials(T* partials, int nb, T* total_out) {
+  // single block: exclusive scan of nb partials (nb <= a few thousand)
+  Op op;
+  __shared__ T sh[1024];
+  __shared__ T carry;
+  if (threadIdx.x == 0) carry = Op::identity();
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int i = base + threadIdx.x;
+    T v = i < nb ? partials[i] : Op::identity();
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      T y = threadIdx.x >= o ? sh[threadIdx.x - o] : Op::identity();
+      __syncthreads();
+      sh[threadIdx.x] = op(y, sh[threadIdx.x]);
+      __syncthreads();
+    }
+    T incl = sh[threadIdx.x];
+    T c = carry;
+    T excl = threadIdx.x == 0 ? c : op(c, sh[threadIdx.x - 1]);
+    if (i < nb) partials[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = op(c, incl);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+template <typename Tin, typename T, typename Op, bool INCLUSIVE>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin* __restrict__ in, T* __restrict__ out, int64_t n, const T* __restrict__ partials, int64_t tiles_per_block) {
+  Op op;
+  T carry = partials[blockIdx.x];
+  int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
+  for (int64_t t = t0; t < t0 + tiles_per_block; ++t) {
+    int64_t base = t * SCAN_TILE;
+    if (base >= n) break;
+    // blocked arrangement: thread owns SCAN_ITEMS consecutive elements
+    T v[SCAN_ITEMS];
+    int64_t i0 = base + (int64_t)threadIdx.x * SCAN_ITEMS;
+    T tsum = Op::identity();
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      v[j] = (i0 + j < n) ? (T)in[i0 + j] : Op::identity();
+      tsum = op(tsum, v[j]);
+    }
+    T tile_total;
+    T excl = block_scan_excl<T, Op>(tsum, &tile_total, op);
+    T run = op(carry, excl);
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      if (INCLUSIVE) { run = op(run, v[j]); if (i0 + j < n) out[i0 + j] = run; }
+      else { if (i0 + j < n) out[i0 + j] = run; run = op(run, v[j]); }
+    }
+    carry = op(carry, tile_total);
+  }
+}
+
+// out may alias in when Tin == T.  total (device pointer, optional) receives the reduction of all inputs.
+template <typename Tin, typename T, typename Op, bool INCLUSIVE>
+static void device_scan(gmql_ctx* ctx, const Tin* in, T* out, int64_t n, T* total_dev) {
+  if (n <= 0) {
+    if (total_dev) CUDA_TRY(cudaMemsetAsync(total_dev, 0, sizeof(T), ctx->stream));
+    return;
+  }
+  int64_t tiles = ceil_div64(n, SCAN_TILE);
+  int nb = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 8);
+  int64_t tpb = ceil_div64(tiles, nb);
+  nb = (int)ceil_div64(tiles, tpb);
+  DevBuf<T> partials(ctx, nb);
+  LAUNCH(ctx, (k_scan_reduce<Tin, T, Op>), nb, SCAN_THREADS, 0, in, n, partials.p, tpb);
+  LAUNCH(ctx, (k_scan_partials<T, Op>), 1, 1024, 0, partials.p, nb, total_dev);
+  LAUNCH(ctx, (k_scan_apply<Tin, T, Op, INCLUSIVE>), nb, SCAN_THREADS, 0, in, out, n, partials.p, tpb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, stable.  Per pass: block histograms -> digit-major scan -> ranked scatter.
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_BITS = 8;
+constexpr int RS_RADIX = 1 << RS_BITS;
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ counts, int nblocks, int64_t tiles_per_block) {
+  __shared__ uint32_t h[RS_RADIX];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t begin = (int64_t)blockIdx.x * tiles_per_block * RS_TILE;
+  int64_t end = begin + tiles_per_block * RS_TILE;
+  if (end > n) end = n;
+  for (int64_t i = begin + threadIdx.x; i < end; i += RS_THREADS) {
+    uint32_t d = (uint32_t)(keys[i] >> shift) & (RS_RADIX - 1);
+    atomicAdd(&h[d], 1u);
+  }
+  __syncthreads();
+  counts[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+template <typename K, bool HAS_VAL>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
+                                                           int64_t n, int shift, const uint32_t* __restrict__ offsets, int nblocks, int64_t tiles_per_block) {
+  __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
+  __shared__ uint32_t digit_base[RS_RADIX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  digit_base[threadIdx.x] = offsets[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+  int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
+  for (int64_t t = t0; t < t0 + tiles_per_block; ++t) {
+    int64_t base = t * RS_TILE;
+    if (base >= n) break;
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ++ww) warp_cnt[ww][threadIdx.x] = 0;
+    __syncthreads();
+    K key[RS_ITEMS];
+    uint32_t val[RS_ITEMS];
+    uint32_t lrank[RS_ITEMS];
+    int64_t wbase = base + (int64_t)w * (32 * RS_ITEMS) + lane;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      int64_t i = wbase + j * 32;
+      if (i < n) { key[j] = kin[i]; if (HAS_VAL) val[j] = vin[i]; }
+    }
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      int64_t i = wbase + j * 32;
+      bool ok = i < n;
+      uint32_t d = ok ? ((uint32_t)(key[j] >> shift) & (RS_RADIX - 1)) : RS_RADIX;  // invalid lanes form their own group
+      uint32_t peers = __match_any_sync(0xffffffffu, d);
+      uint32_t r = __popc(peers & lt_mask);
+      uint32_t pre = ok ? warp_cnt[w][d] : 0;
+      __syncwarp();
+      if (ok && r == 0) warp_cnt[w][d] = pre + __popc(peers);
+      __syncwarp();
+      lrank[j] = pre + r;
+    }
+    __syncthreads();
+    {
+      uint32_t run = digit_base[threadIdx.x];
+#pragma unroll
+      for (int ww = 0; ww < RS_WARPS; ++ww) {
+        uint32_t c = warp_cnt[ww][threadIdx.x];
+        warp_cnt[ww][threadIdx.x] = run;
+        run += c;
+      }
+      digit_base[threadIdx.x] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      int64_t i = wbase + j * 32;
+      if (i < n) {
+        uint32_t d = (uint32_t)(key[j] >> shift) & (RS_RADIX - 1);
+        uint32_t pos = warp_cnt[w][d] + lrank[j];
+        kout[pos] = key[j];
+        if (HAS_VAL) vout[pos] = val[j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* counts, int total) {
+  // single block exclusive scan over `total` counters (digit-major layout)
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int per = 8;
+  for (int base = 0; base < total; base += 1024 * per) {
+    uint32_t v[per];
+    uint32_t s = 0;
+    int i0 = base + threadIdx.x * per;
+#pragma unroll
+    for (int j = 0; j < per; ++j) { v[j] = (i0 + j < total) ? counts[i0 + j] : 0; s += v[j]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      uint32_t y = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += y;
+      __syncthreads();
+    }
+    uint32_t excl = carry + (threadIdx.x == 0 ? 0 : sh[threadIdx.x - 1]);
+    uint32_t tot = sh[1023];
+#pragma unroll
+    for (int j = 0; j < per; ++j) { if (i0 + j < total) counts[i0 + j] = excl; excl += v[j]; }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+}
+
+// Sorts keys (and a 32-bit payload when vals != nullptr) on bits [0, key_bits).  Buffers ping-pong; on return
+// *keys_out / *vals_out point at whichever buffer holds the sorted data.  n must be < 2^32.
+template <typename K>
+static void radix_sort(gmql_ctx* ctx, K* keys, K* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n, int key_bits, K** keys_out, uint32_t** vals_out) {
+  K* kin = keys; K* kout = keys_alt;
+  uint32_t* vin = vals; uint32_t* vout = vals_alt;
+  if (n > 1 && key_bits > 0) {
+    GMQL_REQUIRE(n < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "radix_sort: more than 2^32-1 elements");
+    int64_t tiles = ceil_div64(n, RS_TILE);
+    int nb = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 8);
+    int64_t tpb = ceil_div64(tiles, nb);
+    nb = (int)ceil_div64(tiles, tpb);
+    DevBuf<uint32_t> counts(ctx, (int64_t)RS_RADIX * nb);
+    int passes = (key_bits + RS_BITS - 1) / RS_BITS;
+    for (int p = 0; p < passes; ++p) {
+      int shift = p * RS_BITS;
+      LAUNCH(ctx, (k_rs_hist<K>), nb, RS_THREADS, 0, kin, n, shift, counts.p, nb, tpb);
+      LAUNCH(ctx, k_rs_scan, 1, 1024, 0, counts.p, RS_RADIX * nb);
+      if (vals) LAUNCH(ctx, (k_rs_scatter<K, true>), nb, RS_THREADS, 0, kin, kout, vin, vout, n, shift, counts.p, nb, tpb);
+      else LAUNCH(ctx, (k_rs_scatter<K, false>), nb, RS_THREADS, 0, kin, kout, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, shift, counts.p, nb, tpb);
+      std::swap(kin, kout);
+      std::swap(vin, vout);
+    }
+  }
+  *keys_out = kin;
+  if (vals_out) *vals_out = vin;
+}
+
+static inline int bits_for(uint64_t max_value) {
+  int b = 0;
+  while (b < 64 && (max_value >> b) != 0) ++b;
+  return b;
+}

@@ -1,0 +1,291 @@
+"""GMQLCudaExecutor — host-side mirror of the three operator entry points the CUDA back end replaces.
+
+Reference interface being mirrored (same argument meaning, same error behaviour: every failure raises):
+  GenometricMap71.apply(executor, grouping, aggregator, reference, experiments, BINNING_PARAMETER, REF_PARALLILISM, sc)
+      RegionsOperators/GenometricMap/GenometricMap71.scala:28
+  GenometricCover.apply(executor, coverFlag, min, max, aggregators, grouping, inputDataset, binSize, sc)
+      RegionsOperators/GenometricCover/GenometricCover.scala:30
+  GenometricJoin.apply(executor, metajoinCondition, distanceJoinCondition, regionBuilder, leftDataset, rightDataset,
+                       joinOnAttributes, BINNING_PARAMETER, MAXIMUM_DISTANCE, sc)
+      RegionsOperators/GenometricJoin.scala:21-30
+with the executor constants of GMQLSparkExecutor(binSize = BinSize(), maxBinDistance = 100000, ...)
+(GMQLSparkExecutor.scala:43-47).  The metadata-driven inputs (`grouping` -> sample pairs, `groups` -> sample->group)
+arrive already evaluated, as they do from implement_mjd / implement_mgd.
+
+All arithmetic happens in libgmqlcuda.so; this module only packs columns, resolves thresholds/ids and re-attaches
+host-side (string) values.  No CPU fallback exists.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .ids import pair_id
+from .params import Agg, BinSize, CoverFlag, RegionBuilder, atom_tuple
+from .regions import RegionDataset
+
+INT_MAX = 2 ** 31 - 1
+
+
+class _Result:
+    """Owns a gmql_result handle and copies columns out on demand."""
+
+    def __init__(self, ex, handle):
+        self.ex, self.h = ex, handle
+
+    def rows(self):
+        return int(self.ex.lib.gmql_result_rows(self.h))
+
+    def has(self, col):
+        return self.ex.lib.gmql_result_column_len(self.h, col) >= 0
+
+    def column(self, col, dtype):
+        n = self.ex.lib.gmql_result_column_len(self.h, col)
+        if n < 0:
+            raise KeyError(col)
+        out = np.empty(int(n), dtype=dtype)
+        assert out.itemsize == self.ex.lib.gmql_result_column_elem_size(self.h, col)
+        self.ex._check(self.ex.lib.gmql_result_column_copy(self.ex.ctx, self.h, col, out.ctypes.data))
+        return out
+
+    def device_ptr(self, col):
+        return self.ex.lib.gmql_result_column_device(self.h, col)
+
+    def free(self):
+        if self.h:
+            self.ex.lib.gmql_result_free(self.ex.ctx, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class GMQLCudaExecutor:
+    def __init__(self, binSize=BinSize(), maxBinDistance=100000, device=0, stream=None):
+        self.binSize = binSize
+        self.maxBinDistance = maxBinDistance
+        self.lib = L.load_library()
+        ctx = C.c_void_p()
+        rc = self.lib.gmql_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(ctx))
+        if rc != 0:
+            raise L.GmqlCudaError(rc, "cannot create a CUDA context (no CUDA device? this back end has no CPU fallback)")
+        self.ctx = ctx
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.gmql_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise L.GmqlCudaError(rc, self.lib.gmql_last_error(self.ctx).decode("utf-8", "replace"))
+
+    def last_device_ms(self):
+        return float(self.lib.gmql_last_device_ms(self.ctx))
+
+    def launch_count(self):
+        return int(self.lib.gmql_ctx_launch_count(self.ctx))
+
+    # ---- helpers ----------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _c_aggs(aggs, ds):
+        colmap = ds.numeric_col_map()
+        arr = (L.Agg * max(1, len(aggs)))()
+        for i, a in enumerate(aggs):
+            arr[i].kind = a.kind
+            if a.function_identifier.upper() == "COUNT":
+                arr[i].col = 0
+            else:
+                if a.index not in colmap:
+                    raise L.GmqlCudaError(-2, "aggregate %s on a non-numeric column (index %d) cannot run on the device" % (a.function_identifier, a.index))
+                arr[i].col = colmap[a.index]
+        return arr
+
+    @staticmethod
+    def _c_pairs(pairs, left, right):
+        lidx = {int(s): i for i, s in enumerate(left.sample_ids)}
+        ridx = {int(s): i for i, s in enumerate(right.sample_ids)}
+        use = [(l, r) for (l, r) in pairs if l in lidx and r in ridx]
+        arr = (L.Pair * max(1, len(use)))()
+        for i, (l, r) in enumerate(use):
+            arr[i].left_sample = lidx[l]
+            arr[i].right_sample = ridx[r]
+        return arr, use
+
+    # ---- MAP --------------------------------------------------------------------------------------------------------------
+    def map_raw(self, pairs, aggregator, reference, experiments):
+        """Runs gmql_map; returns (result handle wrapper, used pair list).  pairs: [(ref_sample_id, exp_sample_id)]."""
+        names = sorted(set(reference.chrom_names) | set(experiments.chrom_names))
+        ref = reference.with_chrom_names(names)
+        exp = experiments.with_chrom_names(names)
+        c_ref, k1 = ref.as_c(dup_of=ref.dup_of())
+        c_exp, k2 = exp.as_c()
+        c_pairs, used = self._c_pairs(pairs, ref, exp)
+        c_aggs = self._c_aggs(aggregator, exp)
+        out = C.c_void_p()
+        self._check(self.lib.gmql_map(self.ctx, C.byref(c_ref), C.byref(c_exp), c_pairs, len(used), c_aggs, len(aggregator), C.byref(out)))
+        del k1, k2
+        return _Result(self, out), used, ref
+
+    def GenometricMap71(self, grouping, aggregator, reference, experiments):
+        """MAP.  grouping: list of (ref_sample_id, exp_sample_id) pairs (implement_mjd flattened), or None for every
+        ref sample x every exp sample (MetaJoinMJD2.scala:105-109).  Returns the output as records
+        (new_id, chrom, start, stop, strand, refValues ++ [count] ++ aggregates), one per (pair, distinct ref region)."""
+        if grouping is None:
+            grouping = [(int(a), int(b)) for a in reference.sample_ids for b in experiments.sample_ids]
+        res, used, ref = self.map_raw(grouping, aggregator, reference, experiments)
+        row_off = res.column(L.COL_MAP_ROW_OFFSETS, np.int64)
+        ref_rows = res.column(L.COL_MAP_REF_ROW, np.int32)
+        s_off = res.column(L.COL_MAP_REF_SAMPLE_OFFSETS, np.int64)
+        count = res.column(L.COL_MAP_COUNT, np.int32)
+        vals = [res.column(L.COL_AGG_VALUE + k, np.float64) for k in range(len(aggregator))]
+        oks = [res.column(L.COL_AGG_VALID + k, np.uint8) for k in range(len(aggregator))]
+        res.free()
+        ref_records = ref.to_records()
+        lidx = {int(s): i for i, s in enumerate(ref.sample_ids)}
+        out = []
+        for p, (l, r) in enumerate(used):
+            new_id = pair_id(l, r)
+            a = lidx[l]
+            rows = ref_rows[s_off[a]:s_off[a + 1]]
+            base = int(row_off[p])
+            for k, row in enumerate(rows):
+                c = int(count[base + k])
+                if c < 0:
+                    continue  # collapsed duplicate (MapKey)
+                rec = ref_records[row]
+                aggs = tuple((float(vals[q][base + k]) if oks[q][base + k] else None) for q in range(len(aggregator)))
+                out.append((new_id, rec[1], rec[2], rec[3], rec[4], tuple(rec[5]) + (float(c),) + aggs))
+        return out
+
+    # ---- COVER ------------------------------------------------------------------------------------------------------------
+    def cover_raw(self, coverFlag, min, max, aggregators, groups, ds):
+        c_ds, keep = ds.as_c()
+        n_s = int(ds.sample_ids.shape[0])
+        if groups is not None:
+            gids = sorted(set(groups.values()))
+            gpos = {g: i for i, g in enumerate(gids)}
+            try:
+                sample_group = np.array([gpos[groups[int(s)]] for s in ds.sample_ids], dtype=np.int32)
+            except KeyError as e:  # plain Map.apply in assignGroups throws (GenometricCover.scala:341)
+                raise L.GmqlCudaError(-1, "sample %s has no group" % e)
+            sizes = {}
+            for _s, g in groups.items():
+                sizes[g] = sizes.get(g, 0) + 1
+        else:
+            gids = [0]
+            sample_group = None
+            sizes = None
+        # thresholds (GenometricCover.scala:57-79)
+        if min.kind == "ALL" or max.kind == "ALL":
+            if sizes is not None:
+                all_value = {g: sizes[g] for g in gids}
+            else:
+                cnt = C.c_int32()
+                self._check(self.lib.gmql_cover_count_samples(self.ctx, C.byref(c_ds), C.byref(cnt)))
+                all_value = {0: int(cnt.value)}
+        else:
+            all_value = {g: 0 for g in gids}
+        mn = np.array([(min.fun(all_value[g]) if min.kind == "ALL" else (1 if min.kind == "ANY" else min.n)) for g in gids], dtype=np.int32)
+        mx = np.array([(max.fun(all_value[g]) if max.kind == "ALL" else (INT_MAX if max.kind == "ANY" else max.n)) for g in gids], dtype=np.int32)
+        c_aggs = self._c_aggs(aggregators, ds)
+        out = C.c_void_p()
+        self._check(self.lib.gmql_cover(self.ctx, C.byref(c_ds), sample_group.ctypes.data if sample_group is not None else None,
+                                        len(gids), CoverFlag.CODE[coverFlag], mn.ctypes.data, mx.ctypes.data,
+                                        self.binSize.Cover, c_aggs, len(aggregators), C.byref(out)))
+        del keep
+        return _Result(self, out), gids
+
+    def GenometricCover(self, coverFlag, min, max, aggregators, groups, ds):
+        """COVER / FLAT / SUMMIT / HISTOGRAM.  groups: dict sample_id -> group_id (implement_mgd) or None.  Returns records
+        (group_id, chrom, start, stop, strand, (AccIndex, JaccardIntersect, JaccardResult, aggregates...))."""
+        res, gids = self.cover_raw(coverFlag, min, max, aggregators, groups, ds)
+        g = res.column(L.COL_COV_GROUP, np.int32)
+        chrom = res.column(L.COL_COV_CHROM, np.int32)
+        start = res.column(L.COL_COV_START, np.int64)
+        stop = res.column(L.COL_COV_STOP, np.int64)
+        strand = res.column(L.COL_COV_STRAND, np.int8)
+        acc = res.column(L.COL_COV_ACC, np.int32)
+        j1 = res.column(L.COL_COV_J1, np.float64)
+        j2 = res.column(L.COL_COV_J2, np.float64)
+        vals = [res.column(L.COL_AGG_VALUE + k, np.float64) for k in range(len(aggregators))]
+        oks = [res.column(L.COL_AGG_VALID + k, np.uint8) for k in range(len(aggregators))]
+        res.free()
+        sc = "*+-"
+        out = []
+        for i in range(len(g)):
+            aggs = tuple((float(vals[q][i]) if oks[q][i] else None) for q in range(len(aggregators)))
+            out.append((gids[g[i]], ds.chrom_names[chrom[i]], int(start[i]), int(stop[i]), sc[strand[i]],
+                        (float(acc[i]), float(j1[i]), float(j2[i])) + aggs))
+        return out
+
+    # ---- JOIN -------------------------------------------------------------------------------------------------------------
+    def join_raw(self, pairs, atoms, regionBuilder, left, right, left_eq=None, right_eq=None, dedup=True):
+        names = sorted(set(left.chrom_names) | set(right.chrom_names))
+        l = left.with_chrom_names(names)
+        r = right.with_chrom_names(names)
+        c_l, k1 = l.as_c(dup_of=l.dup_of() if dedup else None)
+        c_r, k2 = r.as_c(dup_of=r.dup_of() if dedup else None)
+        c_pairs, used = self._c_pairs(pairs, l, r)
+        c_atoms = (L.Atom * max(1, len(atoms)))()
+        for i, a in enumerate(atoms):
+            code, arg, _ = atom_tuple(a)
+            c_atoms[i].kind, c_atoms[i].arg = code, arg
+        le = np.ascontiguousarray(left_eq, dtype=np.int64) if left_eq is not None else None
+        re_ = np.ascontiguousarray(right_eq, dtype=np.int64) if right_eq is not None else None
+        out = C.c_void_p()
+        self._check(self.lib.gmql_join(self.ctx, C.byref(c_l), C.byref(c_r), c_pairs, len(used), c_atoms, len(atoms),
+                                       RegionBuilder.CODE[regionBuilder], self.binSize.Join, self.maxBinDistance,
+                                       le.ctypes.data if le is not None else None, re_.ctypes.data if re_ is not None else None,
+                                       C.byref(out)))
+        del k1, k2
+        return _Result(self, out), used, l, r
+
+    def GenometricJoin(self, metajoin_pairs, distanceJoinCondition, regionBuilder, leftDataset, rightDataset, joinOnAttributes=None):
+        """JOIN for one JoinQuadruple.  metajoin_pairs: list of (left_sample_id, right_sample_id) or None = all pairs.
+        distanceJoinCondition: list of AtomicCondition in script order.  joinOnAttributes: optional list of
+        (left_value_index, right_value_index).  Returns built records as joinRegions does (GenometricJoin.scala:345-372)."""
+        if metajoin_pairs is None:
+            metajoin_pairs = [(int(a), int(b)) for a in leftDataset.sample_ids for b in rightDataset.sample_ids]
+        left_eq = right_eq = None
+        lrec = leftDataset.to_records()
+        rrec = rightDataset.to_records()
+        if joinOnAttributes:
+            codes = {}
+            left_eq = np.array([codes.setdefault(tuple(rec[5][i] for (i, _j) in joinOnAttributes), len(codes)) for rec in lrec], dtype=np.int64)
+            right_eq = np.array([codes.get(tuple(rec[5][j] for (_i, j) in joinOnAttributes), -1) for rec in rrec], dtype=np.int64)
+        res, used, l, r = self.join_raw(metajoin_pairs, distanceJoinCondition, regionBuilder, leftDataset, rightDataset, left_eq, right_eq)
+        lrow = res.column(L.COL_JOIN_LEFT_ROW, np.int32)
+        rrow = res.column(L.COL_JOIN_RIGHT_ROW, np.int32)
+        pidx = res.column(L.COL_JOIN_PAIR, np.int32)
+        start = res.column(L.COL_JOIN_START, np.int64)
+        stop = res.column(L.COL_JOIN_STOP, np.int64)
+        strand = res.column(L.COL_JOIN_STRAND, np.int8)
+        chrom = res.column(L.COL_JOIN_CHROM, np.int32)
+        res.free()
+        ids = [pair_id(a, b) for (a, b) in used]
+        sc = "*+-"
+        out = []
+        for i in range(len(lrow)):
+            lv = tuple(lrec[lrow[i]][5]) if lrow[i] >= 0 else ()
+            rv = tuple(rrec[rrow[i]][5]) if rrow[i] >= 0 else ()
+            if regionBuilder == RegionBuilder.LEFT_DISTINCT:
+                vals = lv
+            elif regionBuilder == RegionBuilder.RIGHT_DISTINCT:
+                vals = rv
+            elif regionBuilder == RegionBuilder.BOTH:
+                rr = rrec[rrow[i]]
+                vals = lv + (rr[1], float(rr[2]), float(rr[3]), rr[4]) + rv
+            else:
+                vals = lv + rv
+            out.append((ids[pidx[i]], l.chrom_names[chrom[i]], int(start[i]), int(stop[i]), sc[strand[i]], vals))
+        return out

@@ -196,9 +196,9 @@ const void* gmql_result_column_device(const gmql_result* r, int32_t col);
 int  gmql_result_column_copy(gmql_ctx* ctx, const gmql_result* r, int32_t col, void* dst);
 /* COVER results only: a device-located gmql_regions view (sample = group index, one value column = AccIndex)
  * so that `C = COVER(..) E; M = MAP() C E` chains without a host round trip (the analogue of the reference's
- * per-node memo, GMQLSparkExecutor.scala:252-253).  `storage` keeps the small host arrays the view points at. */
-typedef struct { int64_t sample_ids[1]; const double* cols[1]; const uint8_t* valid[1]; } gmql_view_storage;
-int  gmql_result_as_regions(gmql_ctx* ctx, const gmql_result* r, gmql_regions* view, gmql_view_storage* storage);
+ * per-node memo, GMQLSparkExecutor.scala:252-253).  The small host arrays the view points at (sample_ids, cols)
+ * are owned by the result and live until gmql_result_free. */
+int  gmql_result_as_regions(gmql_ctx* ctx, gmql_result* r, gmql_regions* view);
 void gmql_result_free(gmql_ctx* ctx, gmql_result* r);
 
 /* device time (ms, CUDA events on the context stream) of the last operator call: first kernel -> last kernel,
