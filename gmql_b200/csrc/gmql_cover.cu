@@ -1,16 +1,910 @@
-// gmql_cover.cu — COVER / FLAT / SUMMIT / HISTOGRAM on the device (placeholder until the kernels land).
-#include "common.cuh"
-extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions*, const int32_t*, int32_t, int32_t, const int32_t*, const int32_t*, int64_t,
-                          const gmql_agg*, int32_t, gmql_result** out) {
-  if (out) *out = nullptr;
-  if (ctx) ctx->err = "gmql_cover: not built yet";
-  return GMQL_ERR_UNSUPPORTED;
+// gmql_cover.cu — COVER / FLAT / HISTOGRAM / SUMMIT on the device, both phases.
+//
+// Replaces GenometricCover.apply (GMQL-Spark/.../RegionsOperators/GenometricCover/GenometricCover.scala:30-158: assignGroups,
+// extractor, per-bin coverHelper/histogramHelper/summitHelper, the boundary merge) and its second phase GMAP4.apply
+// (RegionsOperators/GenometricMap/GMAP4.scala:20-100).
+//
+// Design (not a port of the per-bin HashMap/reduceByKey plan):
+//  * every (group, unified strand) class gets its own block of a linearised genome coordinate, so ONE sort and ONE sweep
+//    cover all groups, strands and chromosomes;
+//  * COVER/FLAT/HISTOGRAM: the reference's per-2000bp-bin sweep + boundary merge equals a global sweep over
+//    (start:+1, stop':-1), stop' = stop+1 when stop % bin == 0 and the region crosses a bin edge (extractor :353-354);
+//    starts and stops' are radix-sorted separately (keys only) and merged on the fly (merge path): the depth after the
+//    first m merged events is simply (#starts - #stops) consumed, so no prefix sum is needed;
+//  * SUMMIT is bin-dependent in the reference (each bin restarts at depth 0, summitHelper :269-316), so the per-bin event
+//    lists are emulated exactly: events are expanded per bin, sorted by (class, chrom, bin, offset), coalesced (zero-net
+//    points kept) and each bin's state machine runs in one thread, followed by the cross-bin merge (:121-152);
+//  * phase 2 (GMAP4): every phase-1 region queries the interval index of the input (sorted linear starts + running
+//    max stop) with one warp, reducing count / startMin / endMax / startMax / endMin / aggregates over the overlapping
+//    inputs; regions without contributors are dropped (:33-34,48).
+#include "index.cuh"
+
+namespace {
+
+constexpr int MP_THREADS = 256;
+constexpr int MP_ITEMS = 8;
+constexpr int MP_TILE = MP_THREADS * MP_ITEMS;
+
+struct CoverCfg {
+  int n_groups;
+  int n_classes;        // strand classes per group: 1 when unified, 2 ('+','-') otherwise
+  int unified;
+  int64_t B;            // BinSize.Cover
+  const int32_t* sample_group;  // device [n_samples] or null
+  const int32_t* mn;    // device [n_groups]
+  const int32_t* mx;    // device [n_groups]
+};
+
+// ---- input scan: strand unification flag, samples that own a region, zero-length regions ----------------------------
+__global__ void k_cover_inspect(const int8_t* __restrict__ strand, const int32_t* __restrict__ sample, const void* __restrict__ start, const void* __restrict__ stop, int bits,
+                                int64_t n, int n_samples, int* __restrict__ flags /*[0]=has '*', [1]=zero-length, [2]=bad*/, int* __restrict__ sample_seen) {
+  int has_star = 0, zero = 0, bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int st = strand ? (int)strand[i] : 0;
+    if (st == 0) has_star = 1;
+    if (st < 0 || st > 2) bad = 1;
+    int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+    if (s == e) zero = 1;
+    if (s > e || s < 0) bad = 1;
+    int sm = sample ? sample[i] : 0;
+    if (sm < 0 || sm >= n_samples) bad = 1;
+    else if (!sample_seen[sm]) sample_seen[sm] = 1;
+  }
+  if (__any_sync(0xffffffffu, has_star) && (threadIdx.x & 31) == 0) flags[0] = 1;
+  if (__any_sync(0xffffffffu, zero) && (threadIdx.x & 31) == 0) flags[1] = 1;
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) flags[2] = 1;
 }
-extern "C" int gmql_cover_count_samples(gmql_ctx* ctx, const gmql_regions*, int32_t*) {
-  if (ctx) ctx->err = "gmql_cover_count_samples: not built yet";
-  return GMQL_ERR_UNSUPPORTED;
+
+__global__ void k_count_flags(const int* __restrict__ seen, int n, int* __restrict__ out) {
+  int c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += seen[i] ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
-extern "C" int gmql_result_as_regions(gmql_ctx* ctx, gmql_result*, gmql_regions*) {
-  if (ctx) ctx->err = "gmql_result_as_regions: not built yet";
-  return GMQL_ERR_UNSUPPORTED;
+
+__device__ __forceinline__ uint32_t class_of(const CoverCfg& cfg, int sample, int strand) {
+  int g = cfg.sample_group ? cfg.sample_group[sample] : 0;
+  int sc = cfg.unified ? 0 : (strand - 1);
+  return (uint32_t)(g * cfg.n_classes + sc);
+}
+
+__global__ void k_cover_classes(const int8_t* __restrict__ strand, const int32_t* __restrict__ sample, int64_t n, CoverCfg cfg, uint32_t* __restrict__ cls) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    cls[i] = class_of(cfg, sample ? sample[i] : 0, strand ? (int)strand[i] : 0);
+}
+
+// ---- phase 1 (COVER / FLAT / HISTOGRAM): event keys -------------------------------------------------------------------
+// start key / stop' key of every region in the linear space (extractor semantics, GenometricCover.scala:345-360)
+template <typename K>
+__global__ void k_cover_event_keys(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls,
+                                   int64_t n, LinMap lm, int64_t B, K* __restrict__ skeys /*may be null*/, K* __restrict__ ekeys) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+    uint64_t base = (cls ? (uint64_t)cls[i] : 0ull) * lm.G + lm.coff[chrom[i]];
+    int64_t ks, ke;
+    if (s == e) {           // HashMap(off->1, off->-1) keeps only the -1 (:351); its effect ends with the bin
+      ks = (s / B + 1) * B;
+      ke = s;
+    } else {
+      ks = s;
+      ke = (e % B == 0 && s / B != e / B) ? e + 1 : e;   // stopOff == 0 is replaced by 1 (:354)
+    }
+    if (skeys) skeys[i] = (K)(base + (uint64_t)ks);
+    ekeys[i] = (K)(base + (uint64_t)ke);
+  }
+}
+
+// ---- merge path ----------------------------------------------------------------------------------------------------------
+template <typename K>
+__device__ __forceinline__ int64_t merge_path(const K* __restrict__ A, int64_t nA, const K* __restrict__ Bv, int64_t nB, int64_t d) {
+  // number of A elements among the first d of merge(A, B), ties: A first
+  int64_t lo = d > nB ? d - nB : 0, hi = d < nA ? d : nA;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (A[mid] <= Bv[d - 1 - mid]) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// One pass over merge(starts, stops').  Emits one point (x, depth after x) per distinct position.
+// WRITE == false: per-tile point counts; WRITE == true: points are written at tile_off[tile] + rank.
+template <typename K, bool WRITE>
+__global__ void __launch_bounds__(MP_THREADS) k_cover_points(const K* __restrict__ A, int64_t nA, const K* __restrict__ Bv, int64_t nB, int64_t n_tiles,
+                                                             int64_t* __restrict__ tile_cnt, const int64_t* __restrict__ tile_off,
+                                                             K* __restrict__ px, int32_t* __restrict__ pd) {
+  __shared__ K sA[MP_TILE + 1];
+  __shared__ K sB[MP_TILE + 1];
+  __shared__ int64_t split[2];
+  __shared__ int warp_tot[MP_THREADS / 32];
+  const int64_t total = nA + nB;
+  const K KMAX = ~(K)0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int64_t d0 = tile * MP_TILE, d1 = d0 + MP_TILE;
+    if (d1 > total) d1 = total;
+    if (threadIdx.x < 2) split[threadIdx.x] = merge_path<K>(A, nA, Bv, nB, threadIdx.x == 0 ? d0 : d1);
+    __syncthreads();
+    const int64_t i0 = split[0], i1 = split[1];
+    const int64_t j0 = d0 - i0, j1 = d1 - i1;
+    const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+    for (int t = threadIdx.x; t <= na; t += MP_THREADS) sA[t] = (i0 + t < nA) ? A[i0 + t] : KMAX;
+    for (int t = threadIdx.x; t <= nb; t += MP_THREADS) sB[t] = (j0 + t < nB) ? Bv[j0 + t] : KMAX;
+    __syncthreads();
+    int ld = threadIdx.x * MP_ITEMS;
+    int len = (int)(d1 - d0);
+    if (ld > len) ld = len;
+    int ai;
+    {  // local merge path in shared memory (lookahead slots are never consumed: bounded by na / nb)
+      int lo = ld > nb ? ld - nb : 0, hi = ld < na ? ld : na;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (sA[mid] <= sB[ld - 1 - mid]) lo = mid + 1; else hi = mid;
+      }
+      ai = lo;
+    }
+    int bi = ld - ai;
+    K xs[MP_ITEMS];
+    int32_t ds[MP_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int s = 0; s < MP_ITEMS; ++s) {
+      if (ld + s < len) {
+        bool takeA = (bi >= nb) || (ai < na && sA[ai] <= sB[bi]);
+        K x = takeA ? sA[ai] : sB[bi];
+        if (takeA) ++ai; else ++bi;
+        K nxt = sA[ai] < sB[bi] ? sA[ai] : sB[bi];   // lookahead slots hold the next global elements (or KMAX)
+        if (nxt != x) {
+          xs[cnt] = x;
+          ds[cnt] = (int32_t)((i0 + ai) - (j0 + bi));
+          ++cnt;
+        }
+      }
+    }
+    // block exclusive scan of cnt
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int q = 0; q < MP_THREADS / 32; ++q) { if (q < w) base += warp_tot[q]; tot += warp_tot[q]; }
+    if (!WRITE) {
+      if (threadIdx.x == 0) tile_cnt[tile] = tot;
+    } else {
+      int64_t o = tile_off[tile] + base + incl - cnt;
+      for (int s = 0; s < cnt; ++s) { px[o + s] = xs[s]; pd[o + s] = ds[s]; }
+    }
+    __syncthreads();
+  }
+}
+
+// group of a linear coordinate
+template <typename K>
+__device__ __forceinline__ int group_of_lin(K x, uint64_t G, int n_classes) { return (int)(((uint64_t)x / G) / (uint64_t)n_classes); }
+
+// ---- COVER / FLAT run detection over the point list --------------------------------------------------------------------
+template <typename K>
+__global__ void k_cover_open_flags(const K* __restrict__ px, const int32_t* __restrict__ pd, int64_t np, uint64_t G, CoverCfg cfg, int32_t* __restrict__ open) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < np; m += (int64_t)gridDim.x * blockDim.x) {
+    int g = group_of_lin<K>(px[m], G, cfg.n_classes);
+    int d = pd[m];
+    bool inr = d >= cfg.mn[g] && d <= cfg.mx[g];
+    bool prev = false;
+    if (m > 0) { int gp = group_of_lin<K>(px[m - 1], G, cfg.n_classes); int dp = pd[m - 1]; prev = dp >= cfg.mn[gp] && dp <= cfg.mx[gp]; }
+    open[m] = (inr && !prev) ? 1 : 0;
+  }
+}
+
+template <typename K>
+__global__ void k_cover_runs(const K* __restrict__ px, const int32_t* __restrict__ pd, int64_t np, uint64_t G, CoverCfg cfg, const int64_t* __restrict__ open_excl,
+                             K* __restrict__ rs, K* __restrict__ re, int32_t* __restrict__ racc) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < np; m += (int64_t)gridDim.x * blockDim.x) {
+    int g = group_of_lin<K>(px[m], G, cfg.n_classes);
+    int d = pd[m];
+    bool inr = d >= cfg.mn[g] && d <= cfg.mx[g];
+    bool prev = false;
+    if (m > 0) { int gp = group_of_lin<K>(px[m - 1], G, cfg.n_classes); int dp = pd[m - 1]; prev = dp >= cfg.mn[gp] && dp <= cfg.mx[gp]; }
+    int64_t before = open_excl[m];
+    if (inr) {
+      int64_t run = prev ? before - 1 : before;
+      if (!prev) rs[run] = px[m];
+      atomicMax(&racc[run], d);            // AccIndex = max depth in the run (coverHelper countMax, :183-192)
+    } else if (prev) {
+      re[before - 1] = px[m];
+    }
+  }
+}
+
+// ---- HISTOGRAM segments ----------------------------------------------------------------------------------------------------
+template <typename K>
+__global__ void k_hist_flags(const K* __restrict__ px, const int32_t* __restrict__ pd, int64_t np, uint64_t G, CoverCfg cfg, int32_t* __restrict__ emit) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < np; m += (int64_t)gridDim.x * blockDim.x) {
+    int d = pd[m];
+    int dp = m > 0 ? pd[m - 1] : 0;
+    int g = group_of_lin<K>(px[m], G, cfg.n_classes);
+    // a segment starts at every point that changes the depth to an accepted, non-zero value (histogramHelper :241-250)
+    emit[m] = (d != dp && d != 0 && d >= cfg.mn[g] && d <= cfg.mx[g]) ? 1 : 0;
+  }
+}
+
+template <typename K>
+__global__ void k_hist_segments(const K* __restrict__ px, const int32_t* __restrict__ pd, int64_t np, const int32_t* __restrict__ emit, const int64_t* __restrict__ emit_excl,
+                                K* __restrict__ rs, K* __restrict__ re, int32_t* __restrict__ racc) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < np; m += (int64_t)gridDim.x * blockDim.x) {
+    if (!emit[m]) continue;
+    int d = pd[m];
+    int64_t q = m + 1;
+    while (q < np && pd[q] == d) ++q;      // zero-net points do not cut a segment (newCount != count, :247)
+    int64_t o = emit_excl[m];
+    rs[o] = px[m];
+    re[o] = q < np ? px[q] : px[m];
+    racc[o] = d;
+  }
+}
+
+// linear -> (class, chrom, pos)
+template <typename K>
+__global__ void k_lin_to_regions(const K* __restrict__ rs, const K* __restrict__ re, int64_t n, LinMap lm, uint32_t* __restrict__ ocls, int32_t* __restrict__ ochrom,
+                                 int64_t* __restrict__ ostart, int64_t* __restrict__ ostop) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t x = (uint64_t)rs[k];
+    uint64_t cls = x / lm.G;
+    uint64_t r = x - cls * lm.G;
+    int lo = 0, hi = lm.n_chrom;           // last chrom with coff <= r
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (lm.coff[mid] <= r) lo = mid; else hi = mid; }
+    ocls[k] = (uint32_t)cls;
+    ochrom[k] = lo;
+    ostart[k] = (int64_t)(r - lm.coff[lo]);
+    ostop[k] = (int64_t)((uint64_t)re[k] - cls * lm.G - lm.coff[lo]);
+  }
+}
+
+// ---- SUMMIT: per-bin emulation ---------------------------------------------------------------------------------------------
+// bin-space linearisation: lin2(class, chrom, bin, off) = class*G2 + coff2[chrom] + bin*(B+1) + off, off in [0, B]
+__global__ void k_summit_offsets(const unsigned long long* __restrict__ span, int n_chrom, int64_t B, uint64_t* __restrict__ coff2) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    uint64_t run = 0;
+    for (int c = 0; c < n_chrom; ++c) { coff2[c] = run; run += (span[c] / (uint64_t)B + 2ull) * (uint64_t)(B + 1); }
+    coff2[n_chrom] = run;
+  }
+}
+
+__global__ void k_summit_event_counts(const void* __restrict__ start, const void* __restrict__ stop, int bits, int64_t n, int64_t B, int64_t* __restrict__ cnt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+    int64_t sb = s / B, eb = e / B;
+    cnt[i] = (s == e) ? 1 : 2 * (eb - sb + 1);
+  }
+}
+
+// event key = lin2 << 1 | (delta > 0)
+__global__ void k_summit_events(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls,
+                                int64_t n, int64_t B, const uint64_t* __restrict__ coff2, uint64_t G2, const int64_t* __restrict__ off, uint64_t* __restrict__ keys) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+    int64_t sb = s / B, eb = e / B;
+    uint64_t base = (cls ? (uint64_t)cls[i] : 0ull) * G2 + coff2[chrom[i]];
+    uint64_t W = (uint64_t)(B + 1);
+    int64_t o = off[i];
+    if (s == e) {                                        // only the -1 survives (:351)
+      keys[o] = ((base + (uint64_t)sb * W + (uint64_t)(s - sb * B)) << 1);
+    } else if (sb == eb) {
+      keys[o] = ((base + (uint64_t)sb * W + (uint64_t)(s - sb * B)) << 1) | 1ull;
+      keys[o + 1] = ((base + (uint64_t)sb * W + (uint64_t)(e - sb * B)) << 1);
+    } else {
+      keys[o++] = ((base + (uint64_t)sb * W + (uint64_t)(s - sb * B)) << 1) | 1ull;   // map_start (:353)
+      keys[o++] = ((base + (uint64_t)sb * W + (uint64_t)B) << 1);
+      for (int64_t b = sb + 1; b < eb; ++b) {                                           // map_int (:355)
+        keys[o++] = ((base + (uint64_t)b * W) << 1) | 1ull;
+        keys[o++] = ((base + (uint64_t)b * W + (uint64_t)B) << 1);
+      }
+      int64_t eo = e - eb * B;
+      keys[o++] = ((base + (uint64_t)eb * W) << 1) | 1ull;                              // map_stop (:354)
+      keys[o++] = ((base + (uint64_t)eb * W + (uint64_t)(eo != 0 ? eo : 1)) << 1);
+    }
+  }
+}
+
+__global__ void k_summit_heads(const uint64_t* __restrict__ keys, int64_t ne, int32_t* __restrict__ head) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < ne; m += (int64_t)gridDim.x * blockDim.x)
+    head[m] = (m == 0 || (keys[m] >> 1) != (keys[m - 1] >> 1)) ? 1 : 0;
+}
+
+// coalesce coincident events (reduceByKey :98-108): one point per distinct lin2, zero-net points kept
+__global__ void k_summit_points(const uint64_t* __restrict__ keys, int64_t ne, const int32_t* __restrict__ head, const int64_t* __restrict__ head_excl,
+                                uint64_t* __restrict__ pkey, int32_t* __restrict__ pdelta) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < ne; m += (int64_t)gridDim.x * blockDim.x) {
+    if (!head[m]) continue;
+    uint64_t k = keys[m] >> 1;
+    int net = 0;
+    for (int64_t q = m; q < ne && (keys[q] >> 1) == k; ++q) net += (keys[q] & 1ull) ? 1 : -1;
+    int64_t o = head_excl[m];
+    pkey[o] = k;
+    pdelta[o] = net;
+  }
+}
+
+// one thread per bin: summitHelper (:269-316).  A piece is stored at the index of the point that emits it.
+__global__ void k_summit_bins(const uint64_t* __restrict__ pkey, const int32_t* __restrict__ pdelta, int64_t np, int64_t B, uint64_t G2, CoverCfg cfg,
+                              int32_t* __restrict__ emit, int64_t* __restrict__ pstart_off, int32_t* __restrict__ pval) {
+  const uint64_t W = (uint64_t)(B + 1);
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < np; m += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t bin = pkey[m] / W;
+    if (m > 0 && pkey[m - 1] / W == bin) continue;     // not the first point of its bin
+    int g = (int)((pkey[m] / G2) / (uint64_t)cfg.n_classes);
+    int mn = cfg.mn[g], mx = cfg.mx[g];
+    int64_t start = 0;
+    int count = 0;
+    bool valid = false, reentered = false, growing = false;
+    for (int64_t q = m; q < np && pkey[q] / W == bin; ++q) {
+      int64_t off = (int64_t)(pkey[q] % W);
+      int nc = count + pdelta[q];
+      bool nvalid = nc >= mn && nc <= mx;
+      bool ngrow = nc > count || (growing && nc == count);
+      bool nre = !valid && nvalid;
+      int64_t nstart = (nvalid && nc != count) ? off : start;
+      bool out = ((valid && growing && (!ngrow || !nvalid)) || (reentered && !ngrow)) && count != 0;
+      emit[q] = out ? 1 : 0;
+      if (out) { pstart_off[q] = start; pval[q] = count; }
+      start = nstart; count = nc; valid = nvalid; reentered = nre; growing = ngrow;
+    }
+  }
+}
+
+// compact emitted pieces into (class, chrom, start, stop, value) in genome order
+__global__ void k_summit_pieces(const uint64_t* __restrict__ pkey, int64_t np, int64_t B, uint64_t G2, const uint64_t* __restrict__ coff2, int n_chrom,
+                                const int32_t* __restrict__ emit, const int64_t* __restrict__ emit_excl, const int64_t* __restrict__ pstart_off, const int32_t* __restrict__ pval,
+                                uint32_t* __restrict__ ocls, int32_t* __restrict__ ochrom, int64_t* __restrict__ ostart, int64_t* __restrict__ ostop, int32_t* __restrict__ oval) {
+  const uint64_t W = (uint64_t)(B + 1);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < np; q += (int64_t)gridDim.x * blockDim.x) {
+    if (!emit[q]) continue;
+    uint64_t x = pkey[q];
+    uint64_t cls = x / G2, r = x - cls * G2;
+    int lo = 0, hi = n_chrom;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (coff2[mid] <= r) lo = mid; else hi = mid; }
+    uint64_t inchr = r - coff2[lo];
+    int64_t bin = (int64_t)(inchr / W), off = (int64_t)(inchr % W);
+    int64_t o = emit_excl[q];
+    ocls[o] = (uint32_t)cls;
+    ochrom[o] = lo;
+    ostart[o] = pstart_off[q] + bin * B;
+    ostop[o] = (off > B ? B : off) + bin * B;
+    oval[o] = pval[q];
+  }
+}
+
+// cross-bin merge (GenometricCover.scala:121-152): pieces touching a bin edge chain when prev.stop == cur.start
+__global__ void k_chain_heads(const uint32_t* __restrict__ cls, const int32_t* __restrict__ chrom, const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, int64_t B, int32_t* __restrict__ head) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    bool merge = false;
+    if (k > 0) {
+      bool nv = (s[k] % B == 0) || (e[k] % B == 0);
+      bool nvp = (s[k - 1] % B == 0) || (e[k - 1] % B == 0);
+      merge = nv && nvp && cls[k] == cls[k - 1] && chrom[k] == chrom[k - 1] && e[k - 1] == s[k];
+    }
+    head[k] = merge ? 0 : 1;
+  }
+}
+__global__ void k_chain_merge(const uint32_t* __restrict__ cls, const int32_t* __restrict__ chrom, const int64_t* __restrict__ s, const int64_t* __restrict__ e, const int32_t* __restrict__ v, int64_t n,
+                              const int32_t* __restrict__ head, const int64_t* __restrict__ head_excl,
+                              uint32_t* __restrict__ ocls, int32_t* __restrict__ ochrom, int64_t* __restrict__ os, int64_t* __restrict__ oe, int32_t* __restrict__ ov) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    int64_t o = head[k] ? head_excl[k] : head_excl[k] - 1;
+    if (head[k]) { ocls[o] = cls[k]; ochrom[o] = chrom[k]; os[o] = s[k]; }
+    if (k + 1 == n || head[k + 1]) oe[o] = e[k];
+    atomicMax(&ov[o], v[k]);
+  }
+}
+
+// ---- phase 2: GMAP4 ------------------------------------------------------------------------------------------------------------
+struct CovAggPlan {
+  int n_cols = 0;
+  int col_id[8];
+  int n_aggs = 0;
+  int kind[16], slot[16];
+};
+struct CovCols { const double* v[8]; const uint8_t* ok[8]; };
+struct CovOut { double* value[16]; uint8_t* valid[16]; };
+
+__device__ __forceinline__ unsigned long long cov_key_min(double v) {
+  if (v != v) return 0ull;
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ unsigned long long cov_key_max(double v) {
+  if (v != v) return ~0ull;
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double cov_from_key(unsigned long long k) {
+  unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// one warp per phase-1 region
+template <typename K>
+__global__ void __launch_bounds__(256) k_gmap4(const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom, const int64_t* __restrict__ cstart, const int64_t* __restrict__ cstop, int64_t nc,
+                                               LinMap lm, const K* __restrict__ xs, const K* __restrict__ xe, const K* __restrict__ xpmax, const uint32_t* __restrict__ xrow, int64_t nx,
+                                               CovAggPlan plan, CovCols cc, int flat,
+                                               int32_t* __restrict__ keep, int64_t* __restrict__ fstart, int64_t* __restrict__ fstop, double* __restrict__ j1, double* __restrict__ j2,
+                                               int32_t* __restrict__ ocount, CovOut out) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp; c < nc; c += nwarps) {
+    uint64_t base = (uint64_t)ccls[c] * lm.G + lm.coff[cchrom[c]];
+    K cs = (K)(base + (uint64_t)cstart[c]), ce = (K)(base + (uint64_t)cstop[c]);
+    int64_t hi = lower_bound_dev<K>(xs, nx, ce);            // inputs with start < c.stop
+    int64_t lo = upper_bound_dev<K>(xpmax, hi, cs);          // first index whose running max stop exceeds c.start
+    long long cnt = 0;
+    unsigned long long smin = ~0ull, emax = 0ull, smax = 0ull, emin = ~0ull;
+    int nn[8];
+    double sum[8];
+    unsigned long long vmin[8], vmax[8];
+    for (int q = 0; q < plan.n_cols; ++q) { nn[q] = 0; sum[q] = 0.0; vmin[q] = ~0ull; vmax[q] = 0ull; }
+    for (int64_t k = lo + lane; k < hi; k += 32) {
+      K e = xe[k];
+      if (e <= cs) continue;                                 // strict overlap (GMAP4.scala:41)
+      K s = xs[k];
+      ++cnt;
+      if ((unsigned long long)s < smin) smin = s;
+      if ((unsigned long long)e > emax) emax = e;
+      if ((unsigned long long)s > smax) smax = s;
+      if ((unsigned long long)e < emin) emin = e;
+      if (plan.n_cols) {
+        uint32_t row = xrow[k];
+        for (int q = 0; q < plan.n_cols; ++q) {
+          if (cc.ok[q] && !cc.ok[q][row]) continue;
+          double v = cc.v[q][row];
+          nn[q]++; sum[q] += v;
+          unsigned long long a = cov_key_min(v), b = cov_key_max(v);
+          if (a < vmin[q]) vmin[q] = a;
+          if (b > vmax[q]) vmax[q] = b;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      unsigned long long t;
+      t = __shfl_xor_sync(0xffffffffu, smin, o); if (t < smin) smin = t;
+      t = __shfl_xor_sync(0xffffffffu, emax, o); if (t > emax) emax = t;
+      t = __shfl_xor_sync(0xffffffffu, smax, o); if (t > smax) smax = t;
+      t = __shfl_xor_sync(0xffffffffu, emin, o); if (t < emin) emin = t;
+    }
+    for (int q = 0; q < plan.n_cols; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        nn[q] += __shfl_xor_sync(0xffffffffu, nn[q], o);
+        sum[q] += __shfl_xor_sync(0xffffffffu, sum[q], o);
+        unsigned long long t;
+        t = __shfl_xor_sync(0xffffffffu, vmin[q], o); if (t < vmin[q]) vmin[q] = t;
+        t = __shfl_xor_sync(0xffffffffu, vmax[q], o); if (t > vmax[q]) vmax[q] = t;
+      }
+    }
+    if (lane == 0) {
+      keep[c] = cnt > 0 ? 1 : 0;                             // dropped when nothing overlaps (:33-34,48)
+      ocount[c] = (int32_t)cnt;
+      if (cnt > 0) {
+        int64_t start_min = (int64_t)(smin - base), end_max = (int64_t)(emax - base);
+        int64_t os = flat ? start_min : cstart[c], oe = flat ? end_max : cstop[c];   // :83-84
+        fstart[c] = os; fstop[c] = oe;
+        long long den = (long long)(emax - smin);
+        double num2;
+        if (cnt == 1) num2 = (double)(long long)(emin - smax);                        // single contributor: raw (start, stop)
+        else num2 = smax < emin ? (double)(long long)(emin - smax) : 0.0;            // (0,0) once the intersection is empty (:74)
+        j1[c] = den != 0 ? fabs(((double)oe - (double)os) / (double)den) : 0.0;      // :91
+        j2[c] = den != 0 ? fabs(num2 / (double)den) : 0.0;                           // :93
+      } else { fstart[c] = cstart[c]; fstop[c] = cstop[c]; j1[c] = 0.0; j2[c] = 0.0; }
+      for (int a = 0; a < plan.n_aggs; ++a) {
+        int kind = plan.kind[a], q = plan.slot[a];
+        double v = 0.0; uint8_t ok = 0;
+        if (kind == GMQL_AGG_COUNT) { v = (double)cnt; ok = 1; }
+        else if (nn[q] > 0) {
+          ok = 1;
+          if (kind == GMQL_AGG_SUM) v = sum[q];
+          else if (kind == GMQL_AGG_AVG) v = sum[q] / (double)nn[q];
+          else if (kind == GMQL_AGG_MIN) v = cov_from_key(vmin[q]);
+          else if (kind == GMQL_AGG_MAX) v = cov_from_key(vmax[q]);
+          else if (kind == GMQL_AGG_MEDIAN) { double m = cov_from_key(vmin[q]); v = nn[q] >= 2 ? (m + m) / 2 : m; }
+        }
+        out.value[a][c] = v;
+        out.valid[a][c] = ok;
+      }
+    }
+  }
+}
+
+struct FinalCols {
+  int32_t* group; int32_t* chrom; int64_t* start; int64_t* stop; int8_t* strand; int32_t* acc; double* j1; double* j2;
+  double* value[16]; uint8_t* valid[16];
+};
+__global__ void k_cover_compact(int64_t nc, const int32_t* __restrict__ keep, const int64_t* __restrict__ keep_excl, const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom,
+                                const int64_t* __restrict__ fstart, const int64_t* __restrict__ fstop, const int32_t* __restrict__ cacc, const double* __restrict__ j1, const double* __restrict__ j2,
+                                CovOut in, int n_aggs, int n_classes, int unified, FinalCols f) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    if (!keep[c]) continue;
+    int64_t o = keep_excl[c];
+    uint32_t cls = ccls[c];
+    f.group[o] = (int32_t)(cls / (uint32_t)n_classes);
+    f.strand[o] = unified ? (int8_t)0 : (int8_t)(cls % (uint32_t)n_classes + 1);
+    f.chrom[o] = cchrom[c];
+    f.start[o] = fstart[c];
+    f.stop[o] = fstop[c];
+    f.acc[o] = cacc[c];
+    f.j1[o] = j1[c];
+    f.j2[o] = j2[c];
+    for (int a = 0; a < n_aggs; ++a) { f.value[a][o] = in.value[a][c]; f.valid[a][o] = in.valid[a][c]; }
+  }
+}
+
+static void plan_cov_aggs(const gmql_agg* aggs, int n_aggs, int n_cols_avail, CovAggPlan* plan, std::vector<int>* need_cols) {
+  GMQL_REQUIRE(n_aggs >= 0 && n_aggs <= 16, GMQL_ERR_UNSUPPORTED, "at most 16 aggregates per call");
+  GMQL_REQUIRE(n_aggs == 0 || aggs != nullptr, GMQL_ERR_INVALID, "null aggregate list");
+  *plan = CovAggPlan();
+  plan->n_aggs = n_aggs;
+  for (int a = 0; a < n_aggs; ++a) {
+    int kind = aggs[a].kind;
+    plan->kind[a] = kind;
+    plan->slot[a] = -1;
+    if (kind == GMQL_AGG_COUNT) continue;
+    GMQL_REQUIRE(kind != GMQL_AGG_BAG && kind != GMQL_AGG_BAGD, GMQL_ERR_UNSUPPORTED, "BAG/BAGD aggregates are not available in gmql_cover yet");
+    GMQL_REQUIRE(kind >= GMQL_AGG_SUM && kind <= GMQL_AGG_MEDIAN, GMQL_ERR_INVALID, "unknown aggregate kind");
+    int col = aggs[a].col;
+    GMQL_REQUIRE(col >= 0 && col < n_cols_avail, GMQL_ERR_INVALID, "aggregate column index out of range");
+    int q = -1;
+    for (int j = 0; j < plan->n_cols; ++j) if (plan->col_id[j] == col) q = j;
+    if (q < 0) {
+      GMQL_REQUIRE(plan->n_cols < 8, GMQL_ERR_UNSUPPORTED, "at most 8 distinct aggregated columns per call");
+      q = plan->n_cols++;
+      plan->col_id[q] = col;
+      need_cols->push_back(col);
+    }
+    plan->slot[a] = q;
+  }
+}
+
+struct Phase1Out {
+  DevBuf<uint32_t> cls; DevBuf<int32_t> chrom; DevBuf<int64_t> start, stop; DevBuf<int32_t> acc;
+  int64_t n = 0;
+};
+
+template <typename T>
+static int64_t read_back(gmql_ctx* ctx, const T* dev) {
+  T v;
+  CUDA_TRY(cudaMemcpyAsync(&v, dev, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return (int64_t)v;
+}
+
+template <typename K>
+static void phase1_sweep(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total,
+                         const K* sorted_starts /*may be null*/, Phase1Out* p1) {
+  const int64_t n = in.n;
+  int g = grid_for(ctx, n, 256);
+  DevBuf<K> sk_a, sk_b, ek_a(ctx, n), ek_b(ctx, n);
+  K* starts = const_cast<K*>(sorted_starts);
+  int key_bits = bits_for(n_classes_total * lm.G);
+  if (!starts) { sk_a.alloc(ctx, n); sk_b.alloc(ctx, n); }
+  LAUNCH(ctx, (k_cover_event_keys<K>), g, 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, starts ? (K*)nullptr : sk_a.p, ek_a.p);
+  if (!starts) radix_sort<K>(ctx, sk_a.p, sk_b.p, nullptr, nullptr, n, key_bits, &starts, nullptr);
+  K* stops = nullptr;
+  radix_sort<K>(ctx, ek_a.p, ek_b.p, nullptr, nullptr, n, key_bits, &stops, nullptr);
+
+  // distinct positions with the depth after them
+  int64_t total = 2 * n;
+  int64_t n_tiles = ceil_div64(total, MP_TILE);
+  DevBuf<int64_t> tile_cnt(ctx, n_tiles + 1);
+  int mg = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->num_sms * 8);
+  LAUNCH(ctx, (k_cover_points<K, false>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, tile_cnt.p, (const int64_t*)nullptr, (K*)nullptr, (int32_t*)nullptr);
+  device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, tile_cnt.p, tile_cnt.p, n_tiles, tile_cnt.p + n_tiles);
+  int64_t np = read_back<int64_t>(ctx, tile_cnt.p + n_tiles);
+  DevBuf<K> px(ctx, np);
+  DevBuf<int32_t> pd(ctx, np);
+  LAUNCH(ctx, (k_cover_points<K, true>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, (int64_t*)nullptr, tile_cnt.p, px.p, pd.p);
+  sk_a.release(); sk_b.release(); ek_a.release(); ek_b.release();
+
+  DevBuf<int32_t> flags(ctx, np);
+  DevBuf<int64_t> excl(ctx, np + 1);
+  int pg = grid_for(ctx, np, 256);
+  DevBuf<K> rs, re;
+  if (flag == GMQL_HISTOGRAM) {
+    if (np) LAUNCH(ctx, (k_hist_flags<K>), pg, 256, 0, px.p, pd.p, np, lm.G, cfg, flags.p);
+  } else {
+    if (np) LAUNCH(ctx, (k_cover_open_flags<K>), pg, 256, 0, px.p, pd.p, np, lm.G, cfg, flags.p);
+  }
+  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, flags.p, excl.p, np, excl.p + np);
+  int64_t nr = read_back<int64_t>(ctx, excl.p + np);
+  rs.alloc(ctx, nr); re.alloc(ctx, nr);
+  p1->acc.alloc(ctx, nr);
+  p1->acc.zero();
+  if (nr) {
+    if (flag == GMQL_HISTOGRAM) LAUNCH(ctx, (k_hist_segments<K>), pg, 256, 0, px.p, pd.p, np, flags.p, excl.p, rs.p, re.p, p1->acc.p);
+    else LAUNCH(ctx, (k_cover_runs<K>), pg, 256, 0, px.p, pd.p, np, lm.G, cfg, excl.p, rs.p, re.p, p1->acc.p);
+  }
+  p1->n = nr;
+  p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->start.alloc(ctx, nr); p1->stop.alloc(ctx, nr);
+  if (nr) LAUNCH(ctx, (k_lin_to_regions<K>), grid_for(ctx, nr, 256), 256, 0, rs.p, re.p, nr, lm, p1->cls.p, p1->chrom.p, p1->start.p, p1->stop.p);
+}
+
+static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const SpanTable& spans, const CoverCfg& cfg, uint64_t n_classes_total, Phase1Out* p1) {
+  const int64_t n = in.n;
+  const int64_t B = cfg.B;
+  int g = grid_for(ctx, n, 256);
+  DevBuf<uint64_t> coff2(ctx, spans.n_chrom + 1);
+  LAUNCH(ctx, k_summit_offsets, 1, 32, 0, spans.span.p, spans.n_chrom, B, coff2.p);
+  DevBuf<int64_t> ecnt(ctx, n + 1);
+  LAUNCH(ctx, k_summit_event_counts, g, 256, 0, in.start, in.stop, in.coord_bits, n, B, ecnt.p);
+  device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, ecnt.p, ecnt.p, n, ecnt.p + n);
+  uint64_t G2 = 0;
+  int64_t ne = 0;
+  CUDA_TRY(cudaMemcpyAsync(&G2, coff2.p + spans.n_chrom, sizeof G2, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&ne, ecnt.p + n, sizeof ne, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  GMQL_REQUIRE(ne < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "SUMMIT: more than 2^32 per-bin events");
+  GMQL_REQUIRE(bits_for(n_classes_total * G2) < 63, GMQL_ERR_UNSUPPORTED, "SUMMIT: coordinate space too large");
+  DevBuf<uint64_t> ka(ctx, ne), kb(ctx, ne);
+  LAUNCH(ctx, k_summit_events, g, 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, B, coff2.p, G2, ecnt.p, ka.p);
+  uint64_t* keys = nullptr;
+  radix_sort<uint64_t>(ctx, ka.p, kb.p, nullptr, nullptr, ne, bits_for(n_classes_total * G2) + 1, &keys, nullptr);
+  // coalesce
+  DevBuf<int32_t> head(ctx, ne);
+  DevBuf<int64_t> head_excl(ctx, ne + 1);
+  int eg = grid_for(ctx, ne, 256);
+  if (ne) LAUNCH(ctx, k_summit_heads, eg, 256, 0, keys, ne, head.p);
+  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, head.p, head_excl.p, ne, head_excl.p + ne);
+  int64_t np = read_back<int64_t>(ctx, head_excl.p + ne);
+  DevBuf<uint64_t> pkey(ctx, np);
+  DevBuf<int32_t> pdelta(ctx, np);
+  if (ne) LAUNCH(ctx, k_summit_points, eg, 256, 0, keys, ne, head.p, head_excl.p, pkey.p, pdelta.p);
+  ka.release(); kb.release(); head.release(); head_excl.release();
+  // per-bin state machines
+  DevBuf<int32_t> emit(ctx, np), pval(ctx, np);
+  DevBuf<int64_t> pso(ctx, np), emit_excl(ctx, np + 1);
+  emit.zero();
+  int pg = grid_for(ctx, np, 128, 1);
+  if (np) LAUNCH(ctx, k_summit_bins, pg, 128, 0, pkey.p, pdelta.p, np, B, G2, cfg, emit.p, pso.p, pval.p);
+  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, emit.p, emit_excl.p, np, emit_excl.p + np);
+  int64_t npieces = read_back<int64_t>(ctx, emit_excl.p + np);
+  DevBuf<uint32_t> qcls(ctx, npieces); DevBuf<int32_t> qchrom(ctx, npieces), qval(ctx, npieces); DevBuf<int64_t> qs(ctx, npieces), qe(ctx, npieces);
+  if (npieces) LAUNCH(ctx, k_summit_pieces, grid_for(ctx, np, 256), 256, 0, pkey.p, np, B, G2, coff2.p, spans.n_chrom, emit.p, emit_excl.p, pso.p, pval.p,
+                      qcls.p, qchrom.p, qs.p, qe.p, qval.p);
+  // cross-bin merge
+  DevBuf<int32_t> chead(ctx, npieces);
+  DevBuf<int64_t> chead_excl(ctx, npieces + 1);
+  int qg = grid_for(ctx, npieces, 256);
+  if (npieces) LAUNCH(ctx, k_chain_heads, qg, 256, 0, qcls.p, qchrom.p, qs.p, qe.p, npieces, B, chead.p);
+  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, chead.p, chead_excl.p, npieces, chead_excl.p + npieces);
+  int64_t nr = read_back<int64_t>(ctx, chead_excl.p + npieces);
+  p1->n = nr;
+  p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->start.alloc(ctx, nr); p1->stop.alloc(ctx, nr); p1->acc.alloc(ctx, nr);
+  p1->acc.zero();
+  if (nr) LAUNCH(ctx, k_chain_merge, qg, 256, 0, qcls.p, qchrom.p, qs.p, qe.p, qval.p, npieces, chead.p, chead_excl.p, p1->cls.p, p1->chrom.p, p1->start.p, p1->stop.p, p1->acc.p);
+}
+
+template <typename K>
+static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_sample_group, int n_groups, int flag, const int32_t* h_mn, const int32_t* h_mx, int64_t B,
+                      const CovAggPlan& plan, const SpanTable& spans, bool unified, bool has_zero, gmql_result* res) {
+  const int64_t n = in.n;
+  CoverCfg cfg;
+  cfg.n_groups = n_groups;
+  cfg.unified = unified ? 1 : 0;
+  cfg.n_classes = unified ? 1 : 2;
+  cfg.B = B;
+  DevBuf<int32_t> d_sg, d_mn(ctx, n_groups), d_mx(ctx, n_groups);
+  if (h_sample_group) {
+    d_sg.alloc(ctx, in.n_samples);
+    CUDA_TRY(cudaMemcpyAsync(d_sg.p, h_sample_group, 4 * (size_t)in.n_samples, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(d_mn.p, h_mn, 4 * (size_t)n_groups, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_mx.p, h_mx, 4 * (size_t)n_groups, cudaMemcpyHostToDevice, ctx->stream));
+  cfg.sample_group = d_sg.p;
+  cfg.mn = d_mn.p;
+  cfg.mx = d_mx.p;
+  const uint64_t n_classes_total = (uint64_t)n_groups * (uint64_t)cfg.n_classes;
+  LinMap lm = spans.map();
+
+  // class of every region (only materialised when there is more than one class)
+  DevBuf<uint32_t> cls;
+  if (n_classes_total > 1) {
+    cls.alloc(ctx, n);
+    if (n) LAUNCH(ctx, k_cover_classes, grid_for(ctx, n, 256), 256, 0, in.strand, in.sample, n, cfg, cls.p);
+  }
+
+  // interval index over the ORIGINAL coordinates (phase 2 contributors, GMAP4 uses the un-extended inputs)
+  IntervalIndex<K> ix;
+  build_index<K>(ctx, in, cls.p, n_classes_total, lm, &ix);
+
+  Phase1Out p1;
+  if (n == 0) {
+    p1.n = 0;
+  } else if (flag == GMQL_SUMMIT) {
+    phase1_summit(ctx, in, cls.p, spans, cfg, n_classes_total, &p1);
+  } else {
+    // without zero-length regions the phase-1 start keys are exactly the index's sorted starts: reuse them
+    phase1_sweep<K>(ctx, in, cls.p, lm, cfg, flag, n_classes_total, has_zero ? (const K*)nullptr : ix.start, &p1);
+  }
+
+  // phase 2
+  const int64_t nc = p1.n;
+  DevBuf<int32_t> keep(ctx, nc), ocount(ctx, nc);
+  DevBuf<int64_t> keep_excl(ctx, nc + 1), fstart(ctx, nc), fstop(ctx, nc);
+  DevBuf<double> j1(ctx, nc), j2(ctx, nc);
+  CovCols cc;
+  memset(&cc, 0, sizeof cc);
+  for (int q = 0; q < plan.n_cols; ++q) { cc.v[q] = in.cols[plan.col_id[q]]; cc.ok[q] = in.valid[plan.col_id[q]]; }
+  CovOut tmp;
+  memset(&tmp, 0, sizeof tmp);
+  std::vector<DevBuf<double>> tv((size_t)plan.n_aggs);
+  std::vector<DevBuf<uint8_t>> tk((size_t)plan.n_aggs);
+  for (int a = 0; a < plan.n_aggs; ++a) { tv[a].alloc(ctx, nc); tk[a].alloc(ctx, nc); tmp.value[a] = tv[a].p; tmp.valid[a] = tk[a].p; }
+  if (nc) {
+    int64_t warps_needed = nc;
+    int blocks = (int)std::min<int64_t>(ceil_div64(warps_needed, 8), (int64_t)ctx->num_sms * 16);
+    LAUNCH(ctx, (k_gmap4<K>), blocks, 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, ix.start, ix.stop.p, ix.pmax.p, ix.row, n,
+           plan, cc, flag == GMQL_FLAT ? 1 : 0, keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp);
+  }
+  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, keep.p, keep_excl.p, nc, keep_excl.p + nc);
+  int64_t n_out = read_back<int64_t>(ctx, keep_excl.p + nc);
+
+  DevBuf<int32_t> o_group(ctx, n_out), o_chrom(ctx, n_out), o_acc(ctx, n_out);
+  DevBuf<int64_t> o_start(ctx, n_out), o_stop(ctx, n_out);
+  DevBuf<int8_t> o_strand(ctx, n_out);
+  DevBuf<double> o_j1(ctx, n_out), o_j2(ctx, n_out);
+  std::vector<DevBuf<double>> ov((size_t)plan.n_aggs);
+  std::vector<DevBuf<uint8_t>> ok((size_t)plan.n_aggs);
+  FinalCols f;
+  memset(&f, 0, sizeof f);
+  f.group = o_group.p; f.chrom = o_chrom.p; f.start = o_start.p; f.stop = o_stop.p; f.strand = o_strand.p; f.acc = o_acc.p; f.j1 = o_j1.p; f.j2 = o_j2.p;
+  for (int a = 0; a < plan.n_aggs; ++a) { ov[a].alloc(ctx, n_out); ok[a].alloc(ctx, n_out); f.value[a] = ov[a].p; f.valid[a] = ok[a].p; }
+  if (nc && n_out) LAUNCH(ctx, k_cover_compact, grid_for(ctx, nc, 256), 256, 0, nc, keep.p, keep_excl.p, p1.cls.p, p1.chrom.p, fstart.p, fstop.p, p1.acc.p, j1.p, j2.p,
+                          tmp, plan.n_aggs, cfg.n_classes, cfg.unified, f);
+  cudaEventRecord(ctx->ev_k1, ctx->stream);
+
+  res->rows = n_out;
+  res->kind = 2;
+  res->n_chrom = in.n_chrom;
+  res->group_ids.resize((size_t)n_groups);
+  for (int gi = 0; gi < n_groups; ++gi) res->group_ids[gi] = gi;
+  result_add(res, GMQL_COL_COV_GROUP, o_group);
+  result_add(res, GMQL_COL_COV_CHROM, o_chrom);
+  result_add(res, GMQL_COL_COV_START, o_start);
+  result_add(res, GMQL_COL_COV_STOP, o_stop);
+  result_add(res, GMQL_COL_COV_STRAND, o_strand);
+  result_add(res, GMQL_COL_COV_ACC, o_acc);
+  result_add(res, GMQL_COL_COV_JACC_INTERSECT, o_j1);
+  result_add(res, GMQL_COL_COV_JACC_RESULT, o_j2);
+  for (int a = 0; a < plan.n_aggs; ++a) {
+    result_add(res, GMQL_COL_AGG_VALUE + a, ov[a]);
+    result_add(res, GMQL_COL_AGG_VALID + a, ok[a]);
+  }
+}
+
+struct Inspect { int has_star = 0, has_zero = 0, samples_with_regions = 0; };
+
+static void inspect_input(gmql_ctx* ctx, const DevRegions& in, Inspect* out) {
+  DevBuf<int> flags(ctx, 4), seen(ctx, in.n_samples);
+  flags.zero();
+  seen.zero();
+  if (in.n) {
+    LAUNCH(ctx, k_cover_inspect, grid_for(ctx, in.n, 256), 256, 0, in.strand, in.sample, in.start, in.stop, in.coord_bits, in.n, in.n_samples, flags.p, seen.p);
+    LAUNCH(ctx, k_count_flags, (int)std::min<int64_t>(ceil_div64(in.n_samples, 256), 64), 256, 0, seen.p, in.n_samples, flags.p + 3);
+  }
+  int h[4];
+  CUDA_TRY(cudaMemcpyAsync(h, flags.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  GMQL_REQUIRE(!h[2], GMQL_ERR_INVALID, "region with start > stop, negative start, bad strand code or sample index out of range");
+  out->has_star = h[0];
+  out->has_zero = h[1];
+  out->samples_with_regions = h[3];
+}
+
+}  // namespace
+
+extern "C" int gmql_cover_count_samples(gmql_ctx* ctx, const gmql_regions* in, int32_t* out_count) {
+  if (!ctx || !in || !out_count) return GMQL_ERR_INVALID;
+  try {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // only the sample column matters, but the shared upload keeps the call simple (tiny next to gmql_cover itself)
+    DevRegions d;
+    gmql_upload_regions(ctx, in, std::vector<int>(), &d);
+    Inspect ins;
+    inspect_input(ctx, d, &ins);
+    *out_count = ins.samples_with_regions;
+    return GMQL_OK;
+  } catch (const gmql_error& ex) {
+    ctx->err = ex.what();
+    cudaStreamSynchronize(ctx->stream);
+    return ex.code;
+  }
+}
+
+extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups, int32_t flag,
+                          const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size, const gmql_agg* aggs, int32_t n_aggs, gmql_result** out) {
+  if (!ctx || !out) return GMQL_ERR_INVALID;
+  *out = nullptr;
+  gmql_result* res = nullptr;
+  try {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    GMQL_REQUIRE(in != nullptr, GMQL_ERR_INVALID, "null dataset");
+    GMQL_REQUIRE(n_groups >= 1 && min_acc && max_acc, GMQL_ERR_INVALID, "n_groups >= 1 and per-group thresholds are required");
+    GMQL_REQUIRE(flag >= GMQL_COVER && flag <= GMQL_HISTOGRAM, GMQL_ERR_INVALID, "unknown cover flag");
+    GMQL_REQUIRE(bin_size > 0, GMQL_ERR_INVALID, "bin_size must be positive (BinSize.Cover = 2000)");
+    for (int g = 0; g < n_groups; ++g)
+      GMQL_REQUIRE(min_acc[g] >= 1, GMQL_ERR_UNSUPPORTED, "COVER minAcc < 1 makes the reference's result depend on empty bins; not accelerated");
+    if (sample_group)
+      for (int s = 0; s < in->n_samples; ++s)
+        GMQL_REQUIRE(sample_group[s] >= 0 && sample_group[s] < n_groups, GMQL_ERR_INVALID, "sample_group entry out of range");
+    CovAggPlan plan;
+    std::vector<int> need_cols;
+    plan_cov_aggs(aggs, n_aggs, in->n_cols, &plan, &need_cols);
+    cudaEventRecord(ctx->ev_h0, ctx->stream);
+    DevRegions d;
+    gmql_upload_regions(ctx, in, need_cols, &d);
+    cudaEventRecord(ctx->ev_h1, ctx->stream);
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    Inspect ins;
+    inspect_input(ctx, d, &ins);
+    bool unified = ins.has_star != 0 || d.strand == nullptr || d.n == 0;   // assignGroups (:328-341)
+    SpanTable spans;
+    build_span_table(ctx, &d, nullptr, &spans, (unsigned long long)bin_size + 2ull);
+    uint64_t total = (uint64_t)n_groups * (unified ? 1ull : 2ull) * spans.G;
+    res = new gmql_result();
+    if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, res);
+    else run_cover<uint64_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, res);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = res;
+    return GMQL_OK;
+  } catch (const gmql_error& ex) {
+    ctx->err = ex.what();
+    if (res) gmql_result_free(ctx, res);
+    cudaStreamSynchronize(ctx->stream);
+    return ex.code;
+  } catch (const std::exception& ex) {
+    ctx->err = ex.what();
+    if (res) gmql_result_free(ctx, res);
+    return GMQL_ERR_INVALID;
+  }
+}
+
+__global__ void k_i32_to_f64(const int32_t* __restrict__ in, int64_t n, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+extern "C" int gmql_result_as_regions(gmql_ctx* ctx, gmql_result* r, gmql_regions* view) {
+  if (!ctx || !r || !view) return GMQL_ERR_INVALID;
+  if (r->kind != 2) { ctx->err = "gmql_result_as_regions: only COVER results can be viewed as regions"; return GMQL_ERR_INVALID; }
+  try {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int64_t n = r->rows;
+    if (!r->view_acc_double) {
+      void* p = nullptr;
+      CUDA_TRY(cudaMallocAsync(&p, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
+      r->view_acc_double = p;
+      if (n) LAUNCH(ctx, k_i32_to_f64, grid_for(ctx, n, 256), 256, 0, (const int32_t*)r->cols[GMQL_COL_COV_ACC].p, n, (double*)p);
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      r->view_cols.assign(1, (const double*)p);
+      r->view_valid.assign(1, nullptr);
+    }
+    memset(view, 0, sizeof *view);
+    view->n = n;
+    view->location = GMQL_LOC_DEVICE;
+    view->coord_bits = 64;
+    view->chrom = (const int32_t*)r->cols[GMQL_COL_COV_CHROM].p;
+    view->start = r->cols[GMQL_COL_COV_START].p;
+    view->stop = r->cols[GMQL_COL_COV_STOP].p;
+    view->strand = (const int8_t*)r->cols[GMQL_COL_COV_STRAND].p;
+    view->sample = (const int32_t*)r->cols[GMQL_COL_COV_GROUP].p;
+    view->n_chrom = r->n_chrom;
+    view->n_samples = (int32_t)r->group_ids.size();
+    view->sample_ids = r->group_ids.data();
+    view->n_cols = 1;
+    view->cols = r->view_cols.data();
+    view->valid = r->view_valid.data();
+    view->dup_of = nullptr;
+    return GMQL_OK;
+  } catch (const gmql_error& ex) {
+    ctx->err = ex.what();
+    return ex.code;
+  }
 }

@@ -18,7 +18,7 @@ struct LinMap {
   int n_chrom;
 };
 
-__global__ void k_chrom_span(const int32_t* __restrict__ chrom, const void* __restrict__ stop, int bits, int64_t n, int n_chrom, unsigned long long* __restrict__ span, int* __restrict__ bad) {
+static __global__ void k_chrom_span(const int32_t* __restrict__ chrom, const void* __restrict__ stop, int bits, int64_t n, int n_chrom, unsigned long long* __restrict__ span, int* __restrict__ bad) {
   extern __shared__ unsigned long long sspan[];
   bool use_sh = n_chrom <= 4096;
   if (use_sh) {
@@ -39,11 +39,11 @@ __global__ void k_chrom_span(const int32_t* __restrict__ chrom, const void* __re
   }
 }
 
-__global__ void k_chrom_offsets(const unsigned long long* __restrict__ span, int n_chrom, uint64_t* __restrict__ coff) {
+static __global__ void k_chrom_offsets(const unsigned long long* __restrict__ span, int n_chrom, uint64_t* __restrict__ coff, unsigned long long pad) {
   // tiny: one thread (n_chrom is tens to a few thousand)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     uint64_t run = 0;
-    for (int c = 0; c < n_chrom; ++c) { coff[c] = run; run += span[c] + 2ull; }
+    for (int c = 0; c < n_chrom; ++c) { coff[c] = run; run += span[c] + pad; }
     coff[n_chrom] = run;
   }
 }
@@ -66,7 +66,7 @@ struct SpanTable {
 };
 
 // builds the chromosome offset table from one or two datasets; synchronises once to read G
-static void build_span_table(gmql_ctx* ctx, const DevRegions* a, const DevRegions* b, SpanTable* t) {
+static void build_span_table(gmql_ctx* ctx, const DevRegions* a, const DevRegions* b, SpanTable* t, unsigned long long pad = 2ull) {
   int n_chrom = a->n_chrom;
   t->n_chrom = n_chrom;
   t->span.alloc(ctx, n_chrom);
@@ -76,7 +76,7 @@ static void build_span_table(gmql_ctx* ctx, const DevRegions* a, const DevRegion
   t->bad.zero();
   accumulate_spans(ctx, *a, t->span.p, t->bad.p);
   if (b) accumulate_spans(ctx, *b, t->span.p, t->bad.p);
-  LAUNCH(ctx, k_chrom_offsets, 1, 32, 0, t->span.p, n_chrom, t->coff.p);
+  LAUNCH(ctx, k_chrom_offsets, 1, 32, 0, t->span.p, n_chrom, t->coff.p, pad);
   uint64_t G = 0;
   int bad = 0;
   CUDA_TRY(cudaMemcpyAsync(&G, t->coff.p + n_chrom, sizeof G, cudaMemcpyDeviceToHost, ctx->stream));

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* counts, int total) {
+static __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* counts, int total) {
   // single block exclusive scan over `total` counters (digit-major layout)
   __shared__ uint32_t sh[1024];
   __shared__ uint32_t carry;

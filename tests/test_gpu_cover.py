@@ -1,0 +1,98 @@
+"""COVER / FLAT / SUMMIT / HISTOGRAM parity: CUDA path (through the C ABI) vs the oracle's literal restatement of
+GenometricCover + GMAP4 (per-2000bp-bin sweeps, boundary merge, second-phase join).  Coordinates, AccIndex, the two
+Jaccard doubles and MIN/MAX/COUNT are exact; SUM/AVG within rel 1e-9 (test values are multiples of 0.25: exact)."""
+import random
+
+import pytest
+
+from oracle import gmql_oracle as O
+from tests.randgen import rand_regions, canon
+
+pytestmark = pytest.mark.gpu
+
+FLAGS = ["COVER", "FLAT", "SUMMIT", "HISTOGRAM"]
+
+
+@pytest.fixture(scope="module")
+def ex():
+    from gmql_b200 import GMQLCudaExecutor
+    e = GMQLCudaExecutor()
+    yield e
+    e.close()
+
+
+def _params():
+    import gmql_b200 as G
+    return [
+        ((G.N(1), G.N(2)), (O.CoverParam.N(1), O.CoverParam.N(2))),
+        ((G.N(2), G.N(2)), (O.CoverParam.N(2), O.CoverParam.N(2))),
+        ((G.N(1), G.ANY()), (O.CoverParam.N(1), O.CoverParam.ANY())),
+        ((G.N(2), G.ANY()), (O.CoverParam.N(2), O.CoverParam.ANY())),
+        ((G.N(1), G.ALL()), (O.CoverParam.N(1), O.CoverParam.ALL())),
+        ((G.ANY(), G.ANY()), (O.CoverParam.ANY(), O.CoverParam.ANY())),
+        ((G.ANY(), G.ALL()), (O.CoverParam.ANY(), O.CoverParam.ALL())),
+        ((G.ALL(), G.ANY()), (O.CoverParam.ALL(), O.CoverParam.ANY())),
+        ((G.ALL(div=2), G.ANY()), (O.CoverParam.ALL(div=2), O.CoverParam.ANY())),
+        ((G.ALL(add=1, div=2), G.ALL()), (O.CoverParam.ALL(add=1, div=2), O.CoverParam.ALL())),
+    ]
+
+
+def _check(ex, flag, ds, sample_ids, groups, gp, op, aggs):
+    from gmql_b200 import RegionDataset, Agg
+    d = RegionDataset.from_records(ds, sample_ids=sample_ids)
+    got = ex.GenometricCover(flag, gp[0], gp[1], [Agg(k, i) for (k, i) in aggs], groups, d)
+    want = O.cover_reference(flag, op[0], op[1], [O.Agg(k, i) for (k, i) in aggs], ds, groups, 2000)
+    assert canon(got, 9) == canon(want, 9), (flag, gp)
+
+
+@pytest.mark.parametrize("flag", FLAGS)
+@pytest.mark.parametrize("seed", range(4))
+def test_cover_random(ex, flag, seed):
+    rng = random.Random(300 + seed)
+    ids = [1, 2, 3, 4, 5]
+    strands = "+-*" if seed % 2 == 0 else "+-"
+    ds = rand_regions(rng, 260, ids, strands=strands, n_vals=1, min_len=(0 if seed == 3 else 1))
+    groups = None if seed < 2 else {1: 50, 2: 50, 3: 90, 4: 90, 5: 90}
+    for gp, op in _params():
+        _check(ex, flag, ds, ids, groups, gp, op, [("SUM", 0), ("MIN", 0), ("COUNT", 0), ("AVG", 0), ("MAX", 0)])
+
+
+@pytest.mark.parametrize("flag", FLAGS)
+def test_cover_conf_shape(ex, flag):
+    """conf/test_cover.xml / test_Summit_Flat_Histo.xml shape: 10 files x 1 chr x 20 regions, chromlen 10000, len 5-200."""
+    rng = random.Random(11)
+    ids = list(range(1, 11))
+    ds = rand_regions(rng, 200, ids, chroms=("chr1",), strands="*", span=10000, max_len=200, min_len=5, n_vals=1, aligned_p=0.1, null_p=0.0)
+    groups = {i: (100 if i <= 5 else 200) for i in ids}
+    for gp, op in _params():
+        _check(ex, flag, ds, ids, None, gp, op, [("SUM", 0)])
+        _check(ex, flag, ds, ids, groups, gp, op, [("SUM", 0), ("MIN", 0)])
+
+
+@pytest.mark.parametrize("flag", FLAGS)
+def test_cover_dense_long_regions(ex, flag):
+    """regions spanning many 2000-bp bins, deep pile-ups, many bin-aligned coordinates"""
+    rng = random.Random(77)
+    ids = list(range(8))
+    ds = rand_regions(rng, 600, ids, chroms=("chr1", "chr11", "chrX"), strands="+-", span=60000, max_len=15000, n_vals=1, aligned_p=0.5)
+    import gmql_b200 as G
+    _check(ex, flag, ds, ids, None, (G.N(2), G.ANY()), (O.CoverParam.N(2), O.CoverParam.ANY()), [("SUM", 0)])
+    _check(ex, flag, ds, ids, None, (G.N(3), G.N(6)), (O.CoverParam.N(3), O.CoverParam.N(6)), [])
+
+
+def test_cover_stop_on_bin_edge(ex):
+    import gmql_b200 as G
+    ds = [(1, "chr1", 3000, 4000, "*", (1.0,)), (2, "chr1", 3500, 6000, "*", (2.0,)), (2, "chr1", 4000, 4500, "*", (None,))]
+    for flag in FLAGS:
+        _check(ex, flag, ds, [1, 2], None, (G.N(1), G.ANY()), (O.CoverParam.N(1), O.CoverParam.ANY()), [("SUM", 0)])
+        _check(ex, flag, ds, [1, 2], None, (G.N(1), G.N(1)), (O.CoverParam.N(1), O.CoverParam.N(1)), [("SUM", 0)])
+
+
+def test_cover_empty_and_single(ex):
+    import gmql_b200 as G
+    from gmql_b200 import RegionDataset
+    d = RegionDataset.from_records([(1, "chr1", 5, 9, "+", ())], sample_ids=[1])
+    got = ex.GenometricCover("COVER", G.N(1), G.ANY(), [], None, d)
+    assert got == [(0, "chr1", 5, 9, "+", (1.0, 1.0, 1.0))]
+    got = ex.GenometricCover("COVER", G.N(2), G.ANY(), [], None, d)
+    assert got == []
