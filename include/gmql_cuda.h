@@ -106,6 +106,9 @@ typedef struct { int32_t kind; int64_t arg; } gmql_atom;
 /* RegionBuilder (JoinParametersRD/RegionBuilder.scala:7-12; GenometricJoin.scala:345-372) */
 typedef enum { GMQL_B_LEFT = 0, GMQL_B_LEFT_DISTINCT = 1, GMQL_B_RIGHT = 2, GMQL_B_RIGHT_DISTINCT = 3,
                GMQL_B_CONTIG = 4, GMQL_B_INTERSECTION = 5, GMQL_B_BOTH = 6 } gmql_builder;
+/* OR-ed into `builder`: emit only LEFT_ROW / RIGHT_ROW / PAIR (8+4 B per output record); the built coordinates are
+ * derivable from the rows and can be materialised by the caller */
+#define GMQL_JOIN_ROWS_ONLY 0x100
 
 /* ---- context ------------------------------------------------------------------------- */
 int  gmql_abi_version(void);

@@ -1,0 +1,129 @@
+"""Genometric JOIN parity: CUDA path (through the C ABI) vs the oracle's literal restatement of GenometricJoin
+(bin-replicated join on (bin, chrom), first-bin de-duplication, MD(k) with ties, second round, builders, DISTINCT).
+Everything is integer work: exact."""
+import random
+
+import pytest
+
+from oracle import gmql_oracle as O
+from tests.randgen import rand_regions, canon
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ex():
+    from gmql_b200 import GMQLCudaExecutor
+    e = GMQLCudaExecutor()
+    yield e
+    e.close()
+
+
+def _atoms(spec):
+    import gmql_b200 as G
+    m = {"DISTLESS": G.DistLess, "DISTGREATER": G.DistGreater, "MD": G.MinDistance}
+    out = []
+    for k, a in spec:
+        if k == "UP":
+            out.append(G.Upstream())
+        elif k == "DOWN":
+            out.append(G.DownStream())
+        else:
+            out.append(m[k](a))
+    return out
+
+
+ATOM_SETS = [
+    [("DISTLESS", 1001)],                                   # distance <= 1000  (conf/test_join.xml)
+    [("DISTLESS", 1000)],                                   # distance < 1000
+    [("MD", 1)],                                            # minDistance(1): pure-MD bin-quantised window
+    [("DISTGREATER", 250), ("MD", 1)],                      # distance > 250, minDistance(1)
+    [("DISTLESS", 1000), ("DISTGREATER", 100)],
+    [("MD", 2), ("DOWN", 0)],
+    [("DOWN", 0), ("MD", 1)],
+    [("UP", 0), ("MD", 2)],
+    [("DISTLESS", 50000), ("UP", 0), ("MD", 3), ("DISTGREATER", 10)],
+    [("MD", 1), ("DISTLESS", 3000)],
+    [("DISTLESS", 10001), ("MD", 1), ("DOWN", 0)],
+    [("DISTLESS", 0)],                                      # only overlapping (negative distance)
+    [("DISTLESS", -5)],
+]
+
+
+def _check(ex, left, right, lids, rids, pairs, spec, builder, join_on=None):
+    from gmql_b200 import RegionDataset
+    l = RegionDataset.from_records(left, sample_ids=lids)
+    r = RegionDataset.from_records(right, sample_ids=rids)
+    got = ex.GenometricJoin(list(pairs.keys()), _atoms(spec), builder, l, r, join_on)
+    want = O.join_reference(left, right, pairs, spec, builder, 5000, 100000, join_on)
+    assert canon(got) == canon(want), (spec, builder)
+    return got
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_join_random(ex, seed):
+    rng = random.Random(500 + seed)
+    left = rand_regions(rng, 50, [1, 2], span=400000, max_len=3000, n_vals=1, bin_mults=(5000,))
+    right = rand_regions(rng, 400, [10, 11, 12], span=400000, max_len=3000, n_vals=1, bin_mults=(5000,))
+    pairs = {(1, 10): O.md5_pair_id(1, 10), (1, 11): O.md5_pair_id(1, 11), (2, 10): O.md5_pair_id(2, 10), (2, 12): O.md5_pair_id(2, 12)}
+    for spec in ATOM_SETS:
+        _check(ex, left, right, [1, 2], [10, 11, 12], pairs, spec, "LEFT")
+
+
+@pytest.mark.parametrize("builder", ["LEFT", "LEFT_DISTINCT", "RIGHT", "RIGHT_DISTINCT", "CONTIG", "INTERSECTION", "BOTH"])
+def test_join_builders(ex, builder):
+    rng = random.Random(42)
+    left = rand_regions(rng, 40, [1, 2], span=60000, max_len=4000, n_vals=1, bin_mults=(5000,))
+    right = rand_regions(rng, 200, [10, 11], span=60000, max_len=4000, n_vals=1, bin_mults=(5000,))
+    left = left + left[:5]       # identical left records: MapKey pooling / DISTINCT
+    right = right + right[:7]
+    pairs = {(a, b): O.md5_pair_id(a, b) for a in (1, 2) for b in (10, 11)}
+    for spec in ([("DISTLESS", 2001)], [("MD", 1)], [("MD", 2), ("DISTLESS", 30000)], [("DISTLESS", 5000), ("MD", 3)]):
+        _check(ex, left, right, [1, 2], [10, 11], pairs, spec, builder)
+
+
+def test_join_pure_md_window_edges(ex):
+    """pure MD(k): candidates are bin-quantised around +-100000 (A-J3): 99 999 / 100 000 / 104 999 / 105 000 bp away."""
+    left = [(1, "chr1", 200000, 200100, "+", ())]
+    right = []
+    for gap in (99999, 100000, 104899, 104999, 105000, 110000):
+        right.append((10 + len(right), "chr1", 200100 + gap, 200100 + gap + 50, "*", ()))
+    rids = [r[0] for r in right]
+    pairs = {(1, b): O.md5_pair_id(1, b) for b in rids}
+    _check(ex, left, right, [1], rids, pairs, [("MD", 1)], "RIGHT")
+    _check(ex, left, right, [1], rids, pairs, [("MD", 1), ("DOWN", 0)], "RIGHT")
+    _check(ex, left, right, [1], rids, pairs, [("DISTGREATER", 100000), ("MD", 1)], "RIGHT")
+
+
+def test_join_md_ties_and_strands(ex):
+    left = [(1, "chr1", 1000, 1100, "+", ()), (1, "chr1", 1000, 1100, "-", ()), (1, "chr1", 1000, 1100, "*", ())]
+    right = [(10, "chr1", 800, 900, "*", ()), (10, "chr1", 1200, 1300, "*", ()), (10, "chr1", 1200, 1250, "+", ()),
+             (10, "chr1", 1050, 1060, "-", ()), (10, "chr1", 500, 600, "+", ())]
+    pairs = {(1, 10): 7}
+    for spec in ([("MD", 1)], [("MD", 2)], [("MD", 1), ("UP", 0)], [("UP", 0), ("MD", 1)], [("DOWN", 0), ("MD", 2)], [("MD", 10)]):
+        _check(ex, left, right, [1], [10], pairs, spec, "LEFT")
+
+
+def test_join_on_attributes(ex):
+    rng = random.Random(9)
+    left = rand_regions(rng, 30, [1], span=30000, max_len=2000, n_vals=1, null_p=0.0)
+    right = rand_regions(rng, 150, [10], span=30000, max_len=2000, n_vals=1, null_p=0.0)
+    pairs = {(1, 10): 3}
+    _check(ex, left, right, [1], [10], pairs, [("DISTLESS", 20000)], "LEFT", join_on=[(0, 0)])
+    _check(ex, left, right, [1], [10], pairs, [("MD", 2)], "LEFT", join_on=[(0, 0)])
+
+
+def test_join_conf_test_join_shape(ex):
+    """conf/test_join.xml: 5x5 files x 5 chr; distance<1000 with left|contig|int, minDistance(1) right, ..."""
+    rng = random.Random(3)
+    chroms = ["chr%d" % i for i in range(1, 6)]
+    lids, rids = list(range(1, 6)), list(range(11, 16))
+    left = rand_regions(rng, 300, lids, chroms=chroms, span=100000, max_len=500, min_len=20, n_vals=1, aligned_p=0.05)
+    right = rand_regions(rng, 600, rids, chroms=chroms, span=100000, max_len=500, min_len=20, n_vals=1, aligned_p=0.05)
+    pairs = {(a, b): O.md5_pair_id(a, b) for a in lids for b in rids}
+    _check(ex, left, right, lids, rids, pairs, [("DISTLESS", 1000)], "LEFT")
+    _check(ex, left, right, lids, rids, pairs, [("DISTLESS", 1000)], "CONTIG")
+    _check(ex, left, right, lids, rids, pairs, [("DISTLESS", 1000)], "INTERSECTION")
+    _check(ex, left, right, lids, rids, pairs, [("MD", 1)], "RIGHT")
+    _check(ex, left, right, lids, rids, pairs, [("DISTGREATER", 250), ("MD", 1)], "LEFT")
+    _check(ex, left, right, lids, rids, pairs, [("DISTLESS", 1000), ("DISTGREATER", 100)], "LEFT")
