@@ -99,7 +99,7 @@ def test_join_md_ties_and_strands(ex):
     left = [(1, "chr1", 1000, 1100, "+", ()), (1, "chr1", 1000, 1100, "-", ()), (1, "chr1", 1000, 1100, "*", ())]
     right = [(10, "chr1", 800, 900, "*", ()), (10, "chr1", 1200, 1300, "*", ()), (10, "chr1", 1200, 1250, "+", ()),
              (10, "chr1", 1050, 1060, "-", ()), (10, "chr1", 500, 600, "+", ())]
-    pairs = {(1, 10): 7}
+    pairs = {(1, 10): O.md5_pair_id(1, 10)}
     for spec in ([("MD", 1)], [("MD", 2)], [("MD", 1), ("UP", 0)], [("UP", 0), ("MD", 1)], [("DOWN", 0), ("MD", 2)], [("MD", 10)]):
         _check(ex, left, right, [1], [10], pairs, spec, "LEFT")
 
@@ -108,7 +108,7 @@ def test_join_on_attributes(ex):
     rng = random.Random(9)
     left = rand_regions(rng, 30, [1], span=30000, max_len=2000, n_vals=1, null_p=0.0)
     right = rand_regions(rng, 150, [10], span=30000, max_len=2000, n_vals=1, null_p=0.0)
-    pairs = {(1, 10): 3}
+    pairs = {(1, 10): O.md5_pair_id(1, 10)}
     _check(ex, left, right, [1], [10], pairs, [("DISTLESS", 20000)], "LEFT", join_on=[(0, 0)])
     _check(ex, left, right, [1], [10], pairs, [("MD", 2)], "LEFT", join_on=[(0, 0)])
 
