@@ -41,6 +41,7 @@ EXPORTS = [
     "gmql_cover_count_samples", "gmql_join", "gmql_result_rows", "gmql_result_column_len",
     "gmql_result_column_elem_size", "gmql_result_column_device", "gmql_result_column_copy",
     "gmql_result_as_regions", "gmql_result_free", "gmql_last_device_ms", "gmql_last_h2d_ms",
+    "gmql_dataset_upload", "gmql_dataset_free", "gmql_ctx_set_profiling", "gmql_ctx_profile_report",
 ]
 
 _lib = None
@@ -88,6 +89,11 @@ def load_library(path=None):
     lib.gmql_last_device_ms.restype = C.c_double
     lib.gmql_last_h2d_ms.argtypes = [vp]
     lib.gmql_last_h2d_ms.restype = C.c_double
+    lib.gmql_dataset_upload.argtypes = [vp, C.POINTER(Regions), C.POINTER(vp), C.POINTER(Regions)]
+    lib.gmql_dataset_free.argtypes = [vp, vp]
+    lib.gmql_dataset_free.restype = None
+    lib.gmql_ctx_set_profiling.argtypes = [vp, C.c_int]
+    lib.gmql_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
     if path is None:
         _lib = lib
     return lib

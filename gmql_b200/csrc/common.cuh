@@ -27,7 +27,19 @@ struct gmql_ctx {
   int64_t launches = 0;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_h0 = nullptr, ev_h1 = nullptr;
   double last_device_ms = 0.0, last_h2d_ms = 0.0;
+  // optional per-launch profiling
+  bool profiling = false;
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
 };
+
+static inline void gmql_prof_begin(gmql_ctx* c, const char* name) {
+  gmql_ctx::ProfRec r; r.name = name;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, c->stream);
+  c->prof.push_back(r);
+}
+static inline void gmql_prof_end(gmql_ctx* c) { cudaEventRecord(c->prof.back().b, c->stream); }
 
 #define CUDA_TRY(expr)                                                                        \
   do {                                                                                        \
@@ -47,7 +59,9 @@ struct gmql_ctx {
 // kernel launch on the context stream; counts launches for bench.py's gpu_launches
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                           \
   do {                                                                                        \
+    if ((ctx)->profiling) gmql_prof_begin((ctx), #kernel);                                    \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
+    if ((ctx)->profiling) gmql_prof_end((ctx));                                               \
     (ctx)->launches++;                                                                        \
     CUDA_TRY(cudaGetLastError());                                                             \
   } while (0)

@@ -1,5 +1,6 @@
 // gmql_ctx.cu — context, dataset upload, result accessors of the C ABI (include/gmql_cuda.h).
 #include "common.cuh"
+#include <algorithm>
 
 extern "C" int gmql_abi_version(void) { return GMQL_ABI_VERSION; }
 
@@ -161,4 +162,92 @@ extern "C" void gmql_result_free(gmql_ctx* ctx, gmql_result* r) {
     if (kv.second.p) { if (ctx) cudaFreeAsync(kv.second.p, ctx->stream); else cudaFree(kv.second.p); }
   if (r->view_acc_double) { if (ctx) cudaFreeAsync(r->view_acc_double, ctx->stream); else cudaFree(r->view_acc_double); }
   delete r;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct gmql_dataset {
+  DevRegions dev;
+  std::vector<int64_t> sample_ids;
+  std::vector<const double*> cols;
+  std::vector<const uint8_t*> valid;
+};
+
+extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql_dataset** out, gmql_regions* view) {
+  if (!ctx || !host || !out || !view) return GMQL_ERR_INVALID;
+  *out = nullptr;
+  gmql_dataset* d = new gmql_dataset();
+  try {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<int> all;
+    for (int c = 0; c < host->n_cols; ++c) all.push_back(c);
+    cudaEventRecord(ctx->ev_h0, ctx->stream);
+    gmql_upload_regions(ctx, host, all, &d->dev);
+    cudaEventRecord(ctx->ev_h1, ctx->stream);
+    if (host->sample_ids) d->sample_ids.assign(host->sample_ids, host->sample_ids + host->n_samples);
+    else d->sample_ids.assign((size_t)host->n_samples, 0);
+    d->cols = d->dev.cols;
+    d->valid = d->dev.valid;
+    memset(view, 0, sizeof *view);
+    view->n = d->dev.n;
+    view->location = GMQL_LOC_DEVICE;
+    view->coord_bits = d->dev.coord_bits;
+    view->chrom = d->dev.chrom;
+    view->start = d->dev.start;
+    view->stop = d->dev.stop;
+    view->strand = d->dev.strand;
+    view->sample = d->dev.sample;
+    view->n_chrom = d->dev.n_chrom;
+    view->n_samples = d->dev.n_samples;
+    view->sample_ids = d->sample_ids.data();
+    view->n_cols = d->dev.n_cols;
+    view->cols = d->cols.empty() ? nullptr : d->cols.data();
+    view->valid = d->valid.empty() ? nullptr : d->valid.data();
+    view->dup_of = d->dev.dup_of;
+    *out = d;
+    return GMQL_OK;
+  } catch (const gmql_error& ex) {
+    ctx->err = ex.what();
+    delete d;
+    return ex.code;
+  }
+}
+
+extern "C" void gmql_dataset_free(gmql_ctx* ctx, gmql_dataset* d) {
+  (void)ctx;
+  delete d;  // DevBuf destructors release on the owning context's stream
+}
+
+extern "C" int gmql_ctx_set_profiling(gmql_ctx* c, int enabled) {
+  if (!c) return GMQL_ERR_INVALID;
+  c->profiling = enabled != 0;
+  return GMQL_OK;
+}
+
+extern "C" int gmql_ctx_profile_report(gmql_ctx* c, char* buf, size_t cap) {
+  if (!c || !buf || cap == 0) return GMQL_ERR_INVALID;
+  cudaStreamSynchronize(c->stream);
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : c->prof) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.b);
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    auto& e = agg[r.name];
+    e.first++;
+    e.second += ms;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  c->prof.clear();
+  std::vector<std::pair<std::string, std::pair<int, double>>> v(agg.begin(), agg.end());
+  std::sort(v.begin(), v.end(), [](const auto& x, const auto& y) { return x.second.second > y.second.second; });
+  std::string s;
+  for (auto& e : v) {
+    char line[512];
+    snprintf(line, sizeof line, "%s %d %.6f\n", e.first.c_str(), e.second.first, e.second.second);
+    s += line;
+  }
+  size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+  memcpy(buf, s.data(), n);
+  buf[n] = 0;
+  return GMQL_OK;
 }

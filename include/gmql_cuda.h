@@ -123,6 +123,21 @@ int64_t gmql_ctx_launch_count(const gmql_ctx* ctx);
 int  gmql_host_alloc(size_t bytes, void** out);
 void gmql_host_free(void* p);
 
+/* Device-resident copy of a host dataset: the analogue of the per-IR-node memo (IROperator.intermediateResult,
+ * GMQLSparkExecutor.scala:252-253,282) so that a dataset consumed by several operators (`C = COVER(..) E; M = MAP() C E`)
+ * crosses PCIe once.  `view` is filled with device pointers (location = GMQL_LOC_DEVICE) that stay valid until
+ * gmql_dataset_free; the small host arrays of the view (sample_ids, cols, valid) are owned by the dataset too.
+ * All n_cols value columns are uploaded.  The copy is asynchronous on the context stream. */
+typedef struct gmql_dataset gmql_dataset;
+int  gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql_dataset** out, gmql_regions* view);
+void gmql_dataset_free(gmql_ctx* ctx, gmql_dataset* d);
+
+/* Per-kernel device timing (CUDA events around every launch of this context).  Off by default; meant for one extra
+ * profiled step, not for the timed region.  gmql_ctx_profile_report writes lines "kernel_name launches total_ms"
+ * sorted by total time into buf (NUL-terminated, truncated to cap) and clears the log. */
+int  gmql_ctx_set_profiling(gmql_ctx* ctx, int enabled);
+int  gmql_ctx_profile_report(gmql_ctx* ctx, char* buf, size_t cap);
+
 /* ---- MAP -------------------------------------------------------------------------------
  * For every pair (a, b) and every ref region r of sample a: S = { e in exp sample b : e.chrom == r.chrom,
  * r.start < e.stop, e.start < r.stop, strands compatible }; emits count = |S| (also when 0) and the
