@@ -178,6 +178,130 @@ __global__ void __launch_bounds__(MP_THREADS) k_cover_points(const K* __restrict
   }
 }
 
+// group of a linear coordinate (forward declaration for the fused sweep)
+template <typename K>
+__device__ __forceinline__ int group_of_lin(K x, uint64_t G, int n_classes);
+
+// COVER / FLAT fused sweep: the same merge as k_cover_points, but run opens/closes are decided on the fly, so the
+// point list is never materialised.  A run opens at the first distinct position whose depth enters [min, max] and
+// closes at the first one that leaves it (coverHelper :181-208 + boundary merge :130-150 == maximal runs).
+// WRITE == false: per-tile number of opens; WRITE == true: run k gets start (at its open), stop (at its close) and
+// AccIndex = max depth (atomicMax, one per thread and run).
+template <typename K, bool WRITE>
+__global__ void __launch_bounds__(MP_THREADS) k_cover_runs_fused(const K* __restrict__ A, int64_t nA, const K* __restrict__ Bv, int64_t nB, int64_t n_tiles, uint64_t G, CoverCfg cfg,
+                                                                 int64_t* __restrict__ tile_cnt, const int64_t* __restrict__ tile_off,
+                                                                 K* __restrict__ rs, K* __restrict__ re, int32_t* __restrict__ racc) {
+  __shared__ K sAm[MP_TILE + 2];
+  __shared__ K sBm[MP_TILE + 2];
+  __shared__ int64_t split[2];
+  __shared__ int warp_tot[MP_THREADS / 32];
+  K* sA = sAm + 1;   // sA[-1] = look-behind element
+  K* sB = sBm + 1;
+  const int64_t total = nA + nB;
+  const K KMAX = ~(K)0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int64_t d0 = tile * MP_TILE, d1 = d0 + MP_TILE;
+    if (d1 > total) d1 = total;
+    if (threadIdx.x < 2) split[threadIdx.x] = merge_path<K>(A, nA, Bv, nB, threadIdx.x == 0 ? d0 : d1);
+    __syncthreads();
+    const int64_t i0 = split[0], i1 = split[1];
+    const int64_t j0 = d0 - i0, j1 = d1 - i1;
+    const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+    for (int t = threadIdx.x; t <= na + 1; t += MP_THREADS) { int64_t g = i0 - 1 + t; sAm[t] = (g >= 0 && g < nA) ? A[g] : KMAX; }
+    for (int t = threadIdx.x; t <= nb + 1; t += MP_THREADS) { int64_t g = j0 - 1 + t; sBm[t] = (g >= 0 && g < nB) ? Bv[g] : KMAX; }
+    __syncthreads();
+    int len = (int)(d1 - d0);
+    int ld = threadIdx.x * MP_ITEMS;
+    if (ld > len) ld = len;
+    int ai;
+    {
+      int lo = ld > nb ? ld - nb : 0, hi = ld < na ? ld : na;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (sA[mid] <= sB[ld - 1 - mid]) lo = mid + 1; else hi = mid;
+      }
+      ai = lo;
+    }
+    int bi = ld - ai;
+    // depth at the last position boundary at or before this thread's first element
+    int32_t prev_depth = 0;
+    bool active = ld < len;
+    if (active) {
+      K xn = sA[ai] < sB[bi] ? sA[ai] : sB[bi];
+      if (ai >= na) xn = sB[bi]; else if (bi >= nb) xn = sA[ai];
+      bool has_prev = (i0 + ai) > 0 || (j0 + bi) > 0;
+      K xp = 0;
+      if (has_prev) {
+        bool pa = (i0 + ai) > 0, pb = (j0 + bi) > 0;
+        K va = pa ? sA[ai - 1] : 0, vb = pb ? sB[bi - 1] : 0;
+        xp = (pa && pb) ? (va > vb ? va : vb) : (pa ? va : vb);
+      }
+      if (!has_prev) prev_depth = 0;
+      else if (xp != xn) prev_depth = (int32_t)((i0 + ai) - (j0 + bi));
+      else {
+        // the chunk starts inside a group of equal positions: depth before the group = #(A < x) - #(B < x)
+        int la = 0, ha = ai;
+        while (la < ha) { int mid = (la + ha) >> 1; if (sA[mid] < xn) la = mid + 1; else ha = mid; }
+        int lb = 0, hb = bi;
+        while (lb < hb) { int mid = (lb + hb) >> 1; if (sB[mid] < xn) lb = mid + 1; else hb = mid; }
+        int64_t ga = (la > 0 || i0 == 0) ? i0 + la : lower_bound_dev<K>(A, i0, xn);
+        int64_t gb = (lb > 0 || j0 == 0) ? j0 + lb : lower_bound_dev<K>(Bv, j0, xn);
+        prev_depth = (int32_t)(ga - gb);
+      }
+    }
+    K ev_x[MP_ITEMS];
+    int8_t ev_kind[MP_ITEMS];      // 1 = open, 2 = close
+    int32_t ev_max[MP_ITEMS];      // at a close / chunk end: max depth seen in the run part owned by this thread
+    int nev = 0, nopen = 0;
+    bool prev_in = false;
+    int32_t run_max = 0;
+    if (active) {
+      K xfirst = (ai < na && (bi >= nb || sA[ai] <= sB[bi])) ? sA[ai] : sB[bi];
+      int g = group_of_lin<K>(xfirst, G, cfg.n_classes);
+      prev_in = prev_depth >= cfg.mn[g] && prev_depth <= cfg.mx[g];
+    }
+    bool in_at_start = prev_in;
+#pragma unroll
+    for (int s = 0; s < MP_ITEMS; ++s) {
+      if (ld + s < len) {
+        bool takeA = (bi >= nb) || (ai < na && sA[ai] <= sB[bi]);
+        K x = takeA ? sA[ai] : sB[bi];
+        if (takeA) ++ai; else ++bi;
+        K nxt = sA[ai] < sB[bi] ? sA[ai] : sB[bi];
+        if (nxt != x) {
+          int32_t d = (int32_t)((i0 + ai) - (j0 + bi));
+          int g = group_of_lin<K>(x, G, cfg.n_classes);
+          bool cur_in = d >= cfg.mn[g] && d <= cfg.mx[g];
+          if (cur_in) { if (!prev_in) { ev_x[nev] = x; ev_kind[nev] = 1; ev_max[nev] = 0; ++nev; ++nopen; run_max = d; } else if (d > run_max) run_max = d; }
+          else if (prev_in) { ev_x[nev] = x; ev_kind[nev] = 2; ev_max[nev] = run_max; ++nev; run_max = 0; }
+          prev_in = cur_in;
+        }
+      }
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = nopen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int q = 0; q < MP_THREADS / 32; ++q) { if (q < w) base += warp_tot[q]; tot += warp_tot[q]; }
+    if (!WRITE) {
+      if (threadIdx.x == 0) tile_cnt[tile] = tot;
+    } else {
+      int64_t opens_before = tile_off[tile] + base + incl - nopen;   // opens strictly before this thread's chunk
+      int64_t cur_run = opens_before - 1;                              // run open at chunk start (valid if in_at_start)
+      (void)in_at_start;
+      for (int s = 0; s < nev; ++s) {
+        if (ev_kind[s] == 1) { ++cur_run; rs[cur_run] = ev_x[s]; }
+        else { re[cur_run] = ev_x[s]; if (ev_max[s] > 0) atomicMax(&racc[cur_run], ev_max[s]); }
+      }
+      if (prev_in && run_max > 0) atomicMax(&racc[cur_run], run_max);   // run continues past this chunk
+    }
+    __syncthreads();
+  }
+}
+
 // group of a linear coordinate
 template <typename K>
 __device__ __forceinline__ int group_of_lin(K x, uint64_t G, int n_classes) { return (int)(((uint64_t)x / G) / (uint64_t)n_classes); }
@@ -591,36 +715,41 @@ static void phase1_sweep(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cl
   K* stops = nullptr;
   radix_sort<K>(ctx, ek_a.p, ek_b.p, nullptr, nullptr, n, key_bits, &stops, nullptr);
 
-  // distinct positions with the depth after them
   int64_t total = 2 * n;
   int64_t n_tiles = ceil_div64(total, MP_TILE);
   DevBuf<int64_t> tile_cnt(ctx, n_tiles + 1);
   int mg = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->num_sms * 8);
-  LAUNCH(ctx, (k_cover_points<K, false>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, tile_cnt.p, (const int64_t*)nullptr, (K*)nullptr, (int32_t*)nullptr);
-  device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, tile_cnt.p, tile_cnt.p, n_tiles, tile_cnt.p + n_tiles);
-  int64_t np = read_back<int64_t>(ctx, tile_cnt.p + n_tiles);
-  DevBuf<K> px(ctx, np);
-  DevBuf<int32_t> pd(ctx, np);
-  LAUNCH(ctx, (k_cover_points<K, true>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, (int64_t*)nullptr, tile_cnt.p, px.p, pd.p);
-  sk_a.release(); sk_b.release(); ek_a.release(); ek_b.release();
-
-  DevBuf<int32_t> flags(ctx, np);
-  DevBuf<int64_t> excl(ctx, np + 1);
-  int pg = grid_for(ctx, np, 256);
   DevBuf<K> rs, re;
-  if (flag == GMQL_HISTOGRAM) {
-    if (np) LAUNCH(ctx, (k_hist_flags<K>), pg, 256, 0, px.p, pd.p, np, lm.G, cfg, flags.p);
+  int64_t nr = 0;
+  if (flag != GMQL_HISTOGRAM) {
+    // COVER / FLAT: fused merge + run detection (no point list)
+    LAUNCH(ctx, (k_cover_runs_fused<K, false>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, lm.G, cfg, tile_cnt.p, (const int64_t*)nullptr, (K*)nullptr, (K*)nullptr, (int32_t*)nullptr);
+    device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, tile_cnt.p, tile_cnt.p, n_tiles, tile_cnt.p + n_tiles);
+    nr = read_back<int64_t>(ctx, tile_cnt.p + n_tiles);
+    rs.alloc(ctx, nr); re.alloc(ctx, nr);
+    p1->acc.alloc(ctx, nr);
+    p1->acc.zero();
+    if (nr) LAUNCH(ctx, (k_cover_runs_fused<K, true>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, lm.G, cfg, (int64_t*)nullptr, tile_cnt.p, rs.p, re.p, p1->acc.p);
+    sk_a.release(); sk_b.release(); ek_a.release(); ek_b.release();
   } else {
-    if (np) LAUNCH(ctx, (k_cover_open_flags<K>), pg, 256, 0, px.p, pd.p, np, lm.G, cfg, flags.p);
-  }
-  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, flags.p, excl.p, np, excl.p + np);
-  int64_t nr = read_back<int64_t>(ctx, excl.p + np);
-  rs.alloc(ctx, nr); re.alloc(ctx, nr);
-  p1->acc.alloc(ctx, nr);
-  p1->acc.zero();
-  if (nr) {
-    if (flag == GMQL_HISTOGRAM) LAUNCH(ctx, (k_hist_segments<K>), pg, 256, 0, px.p, pd.p, np, flags.p, excl.p, rs.p, re.p, p1->acc.p);
-    else LAUNCH(ctx, (k_cover_runs<K>), pg, 256, 0, px.p, pd.p, np, lm.G, cfg, excl.p, rs.p, re.p, p1->acc.p);
+    // HISTOGRAM: distinct positions with the depth after them, then one segment per depth change
+    LAUNCH(ctx, (k_cover_points<K, false>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, tile_cnt.p, (const int64_t*)nullptr, (K*)nullptr, (int32_t*)nullptr);
+    device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, tile_cnt.p, tile_cnt.p, n_tiles, tile_cnt.p + n_tiles);
+    int64_t np = read_back<int64_t>(ctx, tile_cnt.p + n_tiles);
+    DevBuf<K> px(ctx, np);
+    DevBuf<int32_t> pd(ctx, np);
+    LAUNCH(ctx, (k_cover_points<K, true>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, (int64_t*)nullptr, tile_cnt.p, px.p, pd.p);
+    sk_a.release(); sk_b.release(); ek_a.release(); ek_b.release();
+    DevBuf<int32_t> flags(ctx, np);
+    DevBuf<int64_t> excl(ctx, np + 1);
+    int pg = grid_for(ctx, np, 256);
+    if (np) LAUNCH(ctx, (k_hist_flags<K>), pg, 256, 0, px.p, pd.p, np, lm.G, cfg, flags.p);
+    device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, flags.p, excl.p, np, excl.p + np);
+    nr = read_back<int64_t>(ctx, excl.p + np);
+    rs.alloc(ctx, nr); re.alloc(ctx, nr);
+    p1->acc.alloc(ctx, nr);
+    p1->acc.zero();
+    if (nr) LAUNCH(ctx, (k_hist_segments<K>), pg, 256, 0, px.p, pd.p, np, flags.p, excl.p, rs.p, re.p, p1->acc.p);
   }
   p1->n = nr;
   p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->start.alloc(ctx, nr); p1->stop.alloc(ctx, nr);
@@ -713,7 +842,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
 
   // interval index over the ORIGINAL coordinates (phase 2 contributors, GMAP4 uses the un-extended inputs)
   IntervalIndex<K> ix;
-  build_index<K>(ctx, in, cls.p, n_classes_total, lm, &ix);
+  build_index<K>(ctx, in, cls.p, n_classes_total, lm, &ix, /*payload_len=*/plan.n_cols == 0 && spans.G < 0xffffffffull);
 
   Phase1Out p1;
   if (n == 0) {

@@ -58,7 +58,10 @@ __global__ void k_sample_keys(const int32_t* __restrict__ sample, int64_t n, int
     if (s < 0 || s >= n_samples) { *bad = 1; s = 0; }
     keys[i] = (uint32_t)s;
     rows[i] = (uint32_t)i;
-    atomicAdd(&counts[s], 1u);
+    // warp-aggregated histogram: neighbouring rows usually belong to one sample
+    unsigned act = __activemask();
+    unsigned peers = __match_any_sync(act, s);
+    if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&counts[s], (unsigned)__popc(peers));
   }
 }
 

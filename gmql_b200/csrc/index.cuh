@@ -98,15 +98,22 @@ struct IntervalIndex {
 };
 
 // block_of(i) = class block of row i (0 when blocks == nullptr)
+// payload = original row, or (stop - start) when `stop` is given (no later gather needed; rows are then unavailable)
 template <typename K>
-__global__ void k_index_keys(const int32_t* __restrict__ chrom, const void* __restrict__ start, int bits, const uint32_t* __restrict__ blocks,
+__global__ void k_index_keys(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ blocks,
                              int64_t n, LinMap lm, K* __restrict__ keys, uint32_t* __restrict__ rows) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint64_t blk = blocks ? blocks[i] : 0u;
-    uint64_t lin = blk * lm.G + lm.coff[chrom[i]] + (uint64_t)ld_coord(start, bits, i);
+    int64_t s = ld_coord(start, bits, i);
+    uint64_t lin = blk * lm.G + lm.coff[chrom[i]] + (uint64_t)s;
     keys[i] = (K)lin;
-    rows[i] = (uint32_t)i;
+    rows[i] = stop ? (uint32_t)(ld_coord(stop, bits, i) - s) : (uint32_t)i;
   }
+}
+
+template <typename K>
+__global__ void k_index_stops_from_len(const K* __restrict__ starts, const uint32_t* __restrict__ lens, int64_t n, K* __restrict__ out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) out[k] = starts[k] + (K)lens[k];
 }
 
 template <typename K>
@@ -128,7 +135,7 @@ static inline int grid_for(gmql_ctx* ctx, int64_t n, int threads, int per_thread
 }
 
 template <typename K>
-static void build_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix) {
+static void build_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix, bool payload_len = false) {
   ix->n = r.n;
   int64_t n = r.n;
   ix->start_a.alloc(ctx, n); ix->start_b.alloc(ctx, n);
@@ -136,9 +143,11 @@ static void build_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* bloc
   ix->stop.alloc(ctx, n); ix->pmax.alloc(ctx, n);
   if (n == 0) { ix->start = ix->start_a.p; ix->row = ix->row_a.p; return; }
   int g = grid_for(ctx, n, 256);
-  LAUNCH(ctx, (k_index_keys<K>), g, 256, 0, r.chrom, r.start, r.coord_bits, blocks, n, lm, ix->start_a.p, ix->row_a.p);
+  // payload_len requires region lengths < 2^32 (checked by the caller through the span table)
+  LAUNCH(ctx, (k_index_keys<K>), g, 256, 0, r.chrom, r.start, payload_len ? r.stop : (const void*)nullptr, r.coord_bits, blocks, n, lm, ix->start_a.p, ix->row_a.p);
   uint64_t max_lin = n_blocks * lm.G;
   radix_sort<K>(ctx, ix->start_a.p, ix->start_b.p, ix->row_a.p, ix->row_b.p, n, bits_for(max_lin), &ix->start, &ix->row);
-  LAUNCH(ctx, (k_index_stops<K>), g, 256, 0, r.chrom, r.stop, r.coord_bits, blocks, n, lm, ix->row, ix->stop.p);
+  if (payload_len) LAUNCH(ctx, (k_index_stops_from_len<K>), g, 256, 0, ix->start, ix->row, n, ix->stop.p);
+  else LAUNCH(ctx, (k_index_stops<K>), g, 256, 0, r.chrom, r.stop, r.coord_bits, blocks, n, lm, ix->row, ix->stop.p);
   device_scan<K, K, OpMax<K>, true>(ctx, ix->stop.p, ix->pmax.p, n, (K*)nullptr);
 }

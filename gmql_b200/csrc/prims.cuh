@@ -162,145 +162,176 @@ static void device_scan(gmql_ctx* ctx, const Tin* in, T* out, int64_t n, T* tota
 }
 
 // ------------------------------------------------------------------------------------------------
-// LSD radix sort, 8-bit digits, stable.  Per pass: block histograms -> digit-major scan -> ranked scatter.
+// LSD radix sort, 8-bit digits, stable, "onesweep" organisation:
+//   * one upfront kernel histograms every digit place in a single read of the keys;
+//   * each pass is ONE kernel: a tile (256 threads x ITEMS keys) ranks its keys in shared memory, obtains its global
+//     per-digit offsets by decoupled look-back over the tiles before it (tile ids are handed out by an atomic ticket,
+//     so every predecessor is already running), reorders the tile in shared memory and writes digit runs with
+//     coalesced stores.  Traffic per pass = read n + write n elements.
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_BITS = 8;
 constexpr int RS_RADIX = 1 << RS_BITS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per tile
+constexpr uint32_t OS_FLAG_AGG = 1u << 30;
+constexpr uint32_t OS_FLAG_INCL = 1u << 31;
+constexpr uint32_t OS_VALUE_MASK = (1u << 30) - 1u;
+template <typename K> struct OsCfg {
+  static constexpr int ITEMS = sizeof(K) == 4 ? 16 : 8;
+  static constexpr int TILE = RS_THREADS * ITEMS;
+};
 
 template <typename K>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ counts, int nblocks, int64_t tiles_per_block) {
-  __shared__ uint32_t h[RS_RADIX];
-  h[threadIdx.x] = 0;
+__global__ void __launch_bounds__(RS_THREADS) k_os_hist(const K* __restrict__ keys, int64_t n, int passes, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[8][RS_RADIX];
+  for (int p = 0; p < passes; ++p) h[p][threadIdx.x] = 0;
   __syncthreads();
-  int64_t begin = (int64_t)blockIdx.x * tiles_per_block * RS_TILE;
-  int64_t end = begin + tiles_per_block * RS_TILE;
-  if (end > n) end = n;
-  for (int64_t i = begin + threadIdx.x; i < end; i += RS_THREADS) {
-    uint32_t d = (uint32_t)(keys[i] >> shift) & (RS_RADIX - 1);
-    atomicAdd(&h[d], 1u);
+  for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RS_THREADS) {
+    K k = keys[i];
+    for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(uint32_t)(k >> (p * RS_BITS)) & (RS_RADIX - 1)], 1u);
   }
   __syncthreads();
-  counts[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  for (int p = 0; p < passes; ++p) {
+    uint32_t c = h[p][threadIdx.x];
+    if (c) atomicAdd(&hist[p * RS_RADIX + threadIdx.x], c);
+  }
+}
+
+// <<<passes, 256>>>: exclusive scan of each digit place's 256 counters, in place
+static __global__ void __launch_bounds__(RS_RADIX) k_os_scan_hist(uint32_t* hist) {
+  __shared__ uint32_t wt[RS_RADIX / 32];
+  uint32_t* h = hist + blockIdx.x * RS_RADIX;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t v = h[threadIdx.x], x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) wt[w] = x;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int q = 0; q < w; ++q) base += wt[q];
+  h[threadIdx.x] = base + x - v;
 }
 
 template <typename K, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
-                                                           int64_t n, int shift, const uint32_t* __restrict__ offsets, int nblocks, int64_t tiles_per_block) {
+__global__ void __launch_bounds__(RS_THREADS) k_os_pass(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
+                                                        int64_t n, int shift, const uint32_t* __restrict__ digit_start, volatile uint32_t* tile_state, uint32_t* ticket) {
+  constexpr int ITEMS = OsCfg<K>::ITEMS;
+  constexpr int TILE = OsCfg<K>::TILE;
   __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
-  __shared__ uint32_t digit_base[RS_RADIX];
+  __shared__ uint32_t tile_excl[RS_RADIX];
+  __shared__ uint32_t glob_base[RS_RADIX];
+  __shared__ uint32_t wtot[RS_WARPS];
+  __shared__ K skeys[TILE];
+  __shared__ uint32_t svals[HAS_VAL ? TILE : 1];
+  __shared__ uint32_t s_tile;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  digit_base[threadIdx.x] = offsets[(int64_t)threadIdx.x * nblocks + blockIdx.x];
-  int64_t t0 = (int64_t)blockIdx.x * tiles_per_block;
-  for (int64_t t = t0; t < t0 + tiles_per_block; ++t) {
-    int64_t base = t * RS_TILE;
-    if (base >= n) break;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
-    for (int ww = 0; ww < RS_WARPS; ++ww) warp_cnt[ww][threadIdx.x] = 0;
-    __syncthreads();
-    K key[RS_ITEMS];
-    uint32_t val[RS_ITEMS];
-    uint32_t lrank[RS_ITEMS];
-    int64_t wbase = base + (int64_t)w * (32 * RS_ITEMS) + lane;
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-      int64_t i = wbase + j * 32;
-      if (i < n) { key[j] = kin[i]; if (HAS_VAL) val[j] = vin[i]; }
-    }
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-      int64_t i = wbase + j * 32;
-      bool ok = i < n;
-      uint32_t d = ok ? ((uint32_t)(key[j] >> shift) & (RS_RADIX - 1)) : RS_RADIX;  // invalid lanes form their own group
-      uint32_t peers = __match_any_sync(0xffffffffu, d);
-      uint32_t r = __popc(peers & lt_mask);
-      uint32_t pre = ok ? warp_cnt[w][d] : 0;
-      __syncwarp();
-      if (ok && r == 0) warp_cnt[w][d] = pre + __popc(peers);
-      __syncwarp();
-      lrank[j] = pre + r;
-    }
-    __syncthreads();
-    {
-      uint32_t run = digit_base[threadIdx.x];
-#pragma unroll
-      for (int ww = 0; ww < RS_WARPS; ++ww) {
-        uint32_t c = warp_cnt[ww][threadIdx.x];
-        warp_cnt[ww][threadIdx.x] = run;
-        run += c;
-      }
-      digit_base[threadIdx.x] = run;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-      int64_t i = wbase + j * 32;
-      if (i < n) {
-        uint32_t d = (uint32_t)(key[j] >> shift) & (RS_RADIX - 1);
-        uint32_t pos = warp_cnt[w][d] + lrank[j];
-        kout[pos] = key[j];
-        if (HAS_VAL) vout[pos] = val[j];
-      }
-    }
-    __syncthreads();
-  }
-}
-
-static __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* counts, int total) {
-  // single block exclusive scan over `total` counters (digit-major layout)
-  __shared__ uint32_t sh[1024];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
+  for (int ww = 0; ww < RS_WARPS; ++ww) warp_cnt[ww][threadIdx.x] = 0;
   __syncthreads();
-  const int per = 8;
-  for (int base = 0; base < total; base += 1024 * per) {
-    uint32_t v[per];
-    uint32_t s = 0;
-    int i0 = base + threadIdx.x * per;
+  const uint32_t tile = s_tile;
+  const int64_t base = (int64_t)tile * TILE;
+  const int64_t wbase = base + (int64_t)w * (32 * ITEMS) + lane;
+
+  K key[ITEMS];
+  uint32_t lrank[ITEMS];
 #pragma unroll
-    for (int j = 0; j < per; ++j) { v[j] = (i0 + j < total) ? counts[i0 + j] : 0; s += v[j]; }
-    sh[threadIdx.x] = s;
+  for (int j = 0; j < ITEMS; ++j) {
+    int64_t i = wbase + j * 32;
+    if (i < n) key[j] = kin[i];
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    int64_t i = wbase + j * 32;
+    bool ok = i < n;
+    uint32_t d = ok ? ((uint32_t)(key[j] >> shift) & (RS_RADIX - 1)) : RS_RADIX;   // invalid lanes form their own group
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t r = __popc(peers & lt_mask);
+    uint32_t pre = ok ? warp_cnt[w][d] : 0;
+    __syncwarp();
+    if (ok && r == 0) warp_cnt[w][d] = pre + __popc(peers);
+    __syncwarp();
+    lrank[j] = pre + r;
+  }
+  __syncthreads();
+  // thread d owns digit d: exclusive offsets of the warps inside the digit, the tile's count, publish, look back
+  uint32_t tot = 0;
+#pragma unroll
+  for (int ww = 0; ww < RS_WARPS; ++ww) { uint32_t c = warp_cnt[ww][threadIdx.x]; warp_cnt[ww][threadIdx.x] = tot; tot += c; }
+  tile_state[(int64_t)tile * RS_RADIX + threadIdx.x] = tot | (tile == 0 ? OS_FLAG_INCL : OS_FLAG_AGG);
+  {
+    uint32_t x = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wtot[w] = x;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      uint32_t y = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += y;
-      __syncthreads();
+    uint32_t b = 0;
+    for (int q = 0; q < w; ++q) b += wtot[q];
+    tile_excl[threadIdx.x] = b + x - tot;
+  }
+  uint32_t look = 0;
+  if (tile > 0) {
+    int64_t p = (int64_t)tile - 1;
+    while (true) {
+      uint32_t s = tile_state[p * RS_RADIX + threadIdx.x];
+      if ((s & (OS_FLAG_AGG | OS_FLAG_INCL)) == 0) continue;
+      look += s & OS_VALUE_MASK;
+      if (s & OS_FLAG_INCL) break;
+      --p;
     }
-    uint32_t excl = carry + (threadIdx.x == 0 ? 0 : sh[threadIdx.x - 1]);
-    uint32_t tot = sh[1023];
+    tile_state[(int64_t)tile * RS_RADIX + threadIdx.x] = ((look + tot) & OS_VALUE_MASK) | OS_FLAG_INCL;
+  }
+  glob_base[threadIdx.x] = digit_start[threadIdx.x] + look - tile_excl[threadIdx.x];
+  __syncthreads();
 #pragma unroll
-    for (int j = 0; j < per; ++j) { if (i0 + j < total) counts[i0 + j] = excl; excl += v[j]; }
-    __syncthreads();
-    if (threadIdx.x == 0) carry += tot;
-    __syncthreads();
+  for (int j = 0; j < ITEMS; ++j) {
+    int64_t i = wbase + j * 32;
+    if (i < n) {
+      uint32_t d = (uint32_t)(key[j] >> shift) & (RS_RADIX - 1);
+      uint32_t pos = tile_excl[d] + warp_cnt[w][d] + lrank[j];
+      skeys[pos] = key[j];
+      if (HAS_VAL) svals[pos] = vin[i];
+    }
+  }
+  __syncthreads();
+  int64_t rem = n - base;
+  int cnt = rem < TILE ? (int)rem : TILE;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    int i = threadIdx.x + j * RS_THREADS;
+    if (i < cnt) {
+      K k = skeys[i];
+      uint32_t d = (uint32_t)(k >> shift) & (RS_RADIX - 1);
+      uint32_t g = glob_base[d] + (uint32_t)i;
+      kout[g] = k;
+      if (HAS_VAL) vout[g] = svals[i];
+    }
   }
 }
 
 // Sorts keys (and a 32-bit payload when vals != nullptr) on bits [0, key_bits).  Buffers ping-pong; on return
-// *keys_out / *vals_out point at whichever buffer holds the sorted data.  n must be < 2^32.
+// *keys_out / *vals_out point at whichever buffer holds the sorted data.  n must be < 2^30.
 template <typename K>
 static void radix_sort(gmql_ctx* ctx, K* keys, K* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n, int key_bits, K** keys_out, uint32_t** vals_out) {
   K* kin = keys; K* kout = keys_alt;
   uint32_t* vin = vals; uint32_t* vout = vals_alt;
   if (n > 1 && key_bits > 0) {
-    GMQL_REQUIRE(n < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "radix_sort: more than 2^32-1 elements");
-    int64_t tiles = ceil_div64(n, RS_TILE);
-    int nb = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 8);
-    int64_t tpb = ceil_div64(tiles, nb);
-    nb = (int)ceil_div64(tiles, tpb);
-    DevBuf<uint32_t> counts(ctx, (int64_t)RS_RADIX * nb);
+    GMQL_REQUIRE(n < (int64_t)(1 << 30), GMQL_ERR_UNSUPPORTED, "radix_sort: 2^30 or more elements in one sort");
     int passes = (key_bits + RS_BITS - 1) / RS_BITS;
+    int64_t tiles = ceil_div64(n, OsCfg<K>::TILE);
+    DevBuf<uint32_t> hist(ctx, (int64_t)8 * RS_RADIX);
+    DevBuf<uint32_t> state(ctx, tiles * RS_RADIX + 32);
+    hist.zero();
+    int hb = (int)std::min<int64_t>(ceil_div64(n, RS_THREADS * 16), (int64_t)ctx->num_sms * 8);
+    LAUNCH(ctx, (k_os_hist<K>), hb, RS_THREADS, 0, kin, n, passes, hist.p);
+    LAUNCH(ctx, k_os_scan_hist, passes, RS_RADIX, 0, hist.p);
     for (int p = 0; p < passes; ++p) {
       int shift = p * RS_BITS;
-      LAUNCH(ctx, (k_rs_hist<K>), nb, RS_THREADS, 0, kin, n, shift, counts.p, nb, tpb);
-      LAUNCH(ctx, k_rs_scan, 1, 1024, 0, counts.p, RS_RADIX * nb);
-      if (vals) LAUNCH(ctx, (k_rs_scatter<K, true>), nb, RS_THREADS, 0, kin, kout, vin, vout, n, shift, counts.p, nb, tpb);
-      else LAUNCH(ctx, (k_rs_scatter<K, false>), nb, RS_THREADS, 0, kin, kout, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, shift, counts.p, nb, tpb);
+      state.zero();
+      uint32_t* ticket = state.p + tiles * RS_RADIX;
+      if (vals) LAUNCH(ctx, (k_os_pass<K, true>), (unsigned)tiles, RS_THREADS, 0, kin, kout, vin, vout, n, shift, hist.p + p * RS_RADIX, state.p, ticket);
+      else LAUNCH(ctx, (k_os_pass<K, false>), (unsigned)tiles, RS_THREADS, 0, kin, kout, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, shift, hist.p + p * RS_RADIX, state.p, ticket);
       std::swap(kin, kout);
       std::swap(vin, vout);
     }
