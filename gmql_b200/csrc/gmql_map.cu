@@ -101,6 +101,17 @@ __global__ void k_index_payload(const uint32_t* __restrict__ rows, int64_t n, co
   }
 }
 
+// bucket table over the linear coordinate: tbl[b] = lower_bound(r_start, b << shift).  A query then binary-searches only
+// inside [tbl[b], tbl[b+1]] (usually 0-2 entries) instead of doing ~log2(n_ref) dependent L1/L2 loads.
+template <typename K>
+__global__ void k_bucket_table(const K* __restrict__ r_start, int64_t n_ref, int shift, int64_t n_buckets, uint32_t* __restrict__ tbl) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t x = (uint64_t)b << shift;
+    K kx = (x > (uint64_t)(~(K)0)) ? ~(K)0 : (K)x;
+    tbl[b] = (uint32_t)lower_bound_dev<K>(r_start, n_ref, kx);
+  }
+}
+
 // ---- the streaming kernel ------------------------------------------------------------------------
 template <typename K>
 __global__ void __launch_bounds__(256) k_map_stream(
@@ -108,7 +119,8 @@ __global__ void __launch_bounds__(256) k_map_stream(
     const int8_t* __restrict__ e_strand, const int32_t* __restrict__ e_sample, int64_t n_exp, int n_exp_samples,
     LinMap lm, const K* __restrict__ r_start, const K* __restrict__ r_stop, const K* __restrict__ r_pmax, int64_t n_ref,
     const int32_t* __restrict__ r_sample, const uint32_t* __restrict__ r_rank, const int8_t* __restrict__ r_strand,
-    const long long* __restrict__ pair_base, MapAggPlan plan, ExpCols ec, MapAcc acc, int* __restrict__ bad) {
+    const long long* __restrict__ pair_base, MapAggPlan plan, ExpCols ec, MapAcc acc, int* __restrict__ bad,
+    const uint32_t* __restrict__ tbl, int tbl_shift) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_exp; i += (int64_t)gridDim.x * blockDim.x) {
     int c = e_chrom[i];
     if (c < 0 || c >= lm.n_chrom) { *bad = 1; continue; }
@@ -123,7 +135,13 @@ __global__ void __launch_bounds__(256) k_map_stream(
     int st = e_strand ? (int)e_strand[i] : 0;
     K ls = (K)(lm.coff[c] + (uint64_t)s);
     K le = (K)(lm.coff[c] + (uint64_t)e);
-    int64_t hi = lower_bound_dev<K>(r_start, n_ref, le);  // ref entries with start < e.stop
+    int64_t hi;                                            // ref entries with start < e.stop
+    {
+      uint64_t b = (uint64_t)le >> tbl_shift;
+      int64_t lo2 = tbl[b], hi2 = tbl[b + 1];
+      while (lo2 < hi2) { int64_t mid = (lo2 + hi2) >> 1; if (r_start[mid] < le) lo2 = mid + 1; else hi2 = mid; }
+      hi = lo2;
+    }
     for (int64_t k = hi - 1; k >= 0 && r_pmax[k] > ls; --k) {
       if (r_stop[k] <= ls) continue;
       if (!strand_ok((int)r_strand[k], st)) continue;
@@ -223,7 +241,7 @@ static void plan_aggs(const gmql_agg* aggs, int n_aggs, int n_cols_avail, MapAgg
 
 template <typename K>
 static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp, const gmql_pair* pairs, int64_t n_pairs,
-                    const MapAggPlan& plan, gmql_result* res) {
+                    const MapAggPlan& plan, const SpanTable& spans, gmql_result* res) {
   const int64_t n_ref = ref.n, n_exp = exp.n;
   const int n_ls = ref.n_samples, n_rs = exp.n_samples;
 
@@ -236,7 +254,6 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     CUDA_TRY(cudaMemcpyAsync(d_pr.p, h_pr.data(), 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
   }
   cudaEventRecord(ctx->ev_h1, ctx->stream);
-  DeviceTimer timer(ctx);
 
   DevBuf<int> bad(ctx, 1);
   bad.zero();
@@ -272,11 +289,18 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   if (n_pairs) LAUNCH(ctx, k_pair_base, grid_for(ctx, n_pairs, 256), 256, 0, d_pl.p, d_pr.p, n_pairs, n_rs, row_off.p, pair_base.p, bad.p);
 
   // interval index over the reference
-  SpanTable spans;
-  build_span_table(ctx, &ref, nullptr, &spans);
   LinMap lm = spans.map();
   IntervalIndex<K> ix;
   build_index<K>(ctx, ref, nullptr, 1, lm, &ix);
+  // bucket table: about 4 buckets per reference region, between 2^10 and 2^22 buckets
+  int tbl_shift = 0;
+  {
+    int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)1 << 22, 4 * n_ref));
+    while (tbl_shift < 62 && (int64_t)(lm.G >> tbl_shift) + 2 > want) ++tbl_shift;
+  }
+  int64_t n_buckets = (int64_t)(lm.G >> tbl_shift) + 1;
+  DevBuf<uint32_t> tbl(ctx, n_buckets + 2);
+  LAUNCH(ctx, (k_bucket_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, n_ref, tbl_shift, n_buckets, tbl.p);
   DevBuf<int32_t> s_sample(ctx, n_ref);
   DevBuf<uint32_t> s_rank(ctx, n_ref);
   DevBuf<int8_t> s_strand(ctx, n_ref);
@@ -305,7 +329,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   if (n_exp && n_ref && n_rows) {
     int g = grid_for(ctx, n_exp, 256, 2);
     LAUNCH(ctx, (k_map_stream<K>), g, 256, 0, exp.chrom, exp.start, exp.stop, exp.coord_bits, exp.strand, exp.sample, n_exp, n_rs,
-           lm, ix.start, ix.stop.p, ix.pmax.p, n_ref, s_sample.p, s_rank.p, s_strand.p, pair_base.p, plan, ec, acc, bad.p);
+           lm, ix.start, ix.stop.p, ix.pmax.p, n_ref, s_sample.p, s_rank.p, s_strand.p, pair_base.p, plan, ec, acc, bad.p, tbl.p, tbl_shift);
   }
   if (ref.dup_of && n_pairs && n_rows)
     LAUNCH(ctx, k_mark_dups, (int)std::min<int64_t>(n_pairs, (int64_t)ctx->num_sms * 8), 128, 0, d_pl.p, row_off.p, n_pairs, sample_off.p, rows_by_sample, ref.dup_of, count.p);
@@ -320,7 +344,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     mo.value[a] = ov[a].p; mo.valid[a] = ok[a].p;
   }
   if (plan.n_aggs && n_rows) LAUNCH(ctx, k_map_finalize, grid_for(ctx, n_rows, 256), 256, 0, n_rows, plan, acc, mo);
-  timer.stop();
+  cudaEventRecord(ctx->ev_k1, ctx->stream);
 
   CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -363,8 +387,12 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
     DevRegions dref, dexp;
     gmql_upload_regions(ctx, ref, std::vector<int>(), &dref);
     gmql_upload_regions(ctx, exp, need_cols, &dexp);
+    SpanTable spans;
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    build_span_table(ctx, &dref, nullptr, &spans);
     res = new gmql_result();
-    run_map<uint64_t>(ctx, dref, dexp, pairs, n_pairs, plan, res);
+    if (spans.G < 0xffffffffull) run_map<uint32_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
+    else run_map<uint64_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     *out = res;
     return GMQL_OK;

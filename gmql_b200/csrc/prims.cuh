@@ -246,7 +246,14 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const K* __restrict__ ki
     int64_t i = wbase + j * 32;
     bool ok = i < n;
     uint32_t d = ok ? ((uint32_t)(key[j] >> shift) & (RS_RADIX - 1)) : RS_RADIX;   // invalid lanes form their own group
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    // lanes holding the same digit, by bit-wise ballots (match.any runs on the slow ADU pipe: ~60 cycles per warp)
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b <= RS_BITS; ++b) {
+      uint32_t bit = (d >> b) & 1u;
+      uint32_t bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
+    }
     uint32_t r = __popc(peers & lt_mask);
     uint32_t pre = ok ? warp_cnt[w][d] : 0;
     __syncwarp();
