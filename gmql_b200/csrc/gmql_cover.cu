@@ -55,6 +55,36 @@ __global__ void k_cover_inspect(const int8_t* __restrict__ strand, const int32_t
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) flags[2] = 1;
 }
 
+// gmql_cover's own prepass: per-chromosome max stop (span table) and the input flags in ONE read of the columns
+__global__ void k_cover_prepass(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const int8_t* __restrict__ strand,
+                                const int32_t* __restrict__ sample, int64_t n, int n_chrom, int n_samples, unsigned long long* __restrict__ span, int* __restrict__ flags) {
+  extern __shared__ unsigned long long sspan[];
+  bool use_sh = n_chrom <= 4096;
+  if (use_sh) {
+    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) sspan[c] = 0ull;
+    __syncthreads();
+  }
+  int has_star = 0, zero = 0, bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = chrom[i];
+    int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+    int st = strand ? (int)strand[i] : 0;
+    int sm = sample ? sample[i] : 0;
+    if (st == 0) has_star = 1;
+    if (s == e) zero = 1;
+    if (c < 0 || c >= n_chrom || s < 0 || s > e || st < 0 || st > 2 || sm < 0 || sm >= n_samples) { bad = 1; continue; }
+    if (use_sh) atomicMax(&sspan[c], (unsigned long long)e); else atomicMax(&span[c], (unsigned long long)e);
+  }
+  if (__any_sync(0xffffffffu, has_star) && (threadIdx.x & 31) == 0) flags[0] = 1;
+  if (__any_sync(0xffffffffu, zero) && (threadIdx.x & 31) == 0) flags[1] = 1;
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) flags[2] = 1;
+  if (use_sh) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x)
+      if (sspan[c]) atomicMax(&span[c], sspan[c]);
+  }
+}
+
 __global__ void k_count_flags(const int* __restrict__ seen, int n, int* __restrict__ out) {
   int c = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += seen[i] ? 1 : 0;
@@ -94,6 +124,21 @@ __global__ void k_cover_event_keys(const int32_t* __restrict__ chrom, const void
   }
 }
 
+// no zero-length regions: the index's start keys ARE the phase-1 start keys, so one kernel writes the start key, the
+// length payload and the stop' key
+template <typename K>
+__global__ void k_cover_all_keys(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls,
+                                 int64_t n, LinMap lm, int64_t B, K* __restrict__ skeys, uint32_t* __restrict__ lens, K* __restrict__ ekeys) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+    uint64_t base = (cls ? (uint64_t)cls[i] : 0ull) * lm.G + lm.coff[chrom[i]];
+    int64_t ke = (e % B == 0 && s / B != e / B) ? e + 1 : e;
+    skeys[i] = (K)(base + (uint64_t)s);
+    lens[i] = (uint32_t)(e - s);
+    ekeys[i] = (K)(base + (uint64_t)ke);
+  }
+}
+
 // ---- merge path ----------------------------------------------------------------------------------------------------------
 template <typename K>
 __device__ __forceinline__ int64_t merge_path(const K* __restrict__ A, int64_t nA, const K* __restrict__ Bv, int64_t nB, int64_t d) {
@@ -106,24 +151,33 @@ __device__ __forceinline__ int64_t merge_path(const K* __restrict__ A, int64_t n
   return lo;
 }
 
+// merge-path split of every tile boundary, computed once (one thread per boundary) instead of by two threads of each
+// tile while the other 254 wait at the barrier
+template <typename K>
+__global__ void k_merge_splits(const K* __restrict__ A, int64_t nA, const K* __restrict__ Bv, int64_t nB, int64_t n_tiles, int64_t* __restrict__ splits) {
+  int64_t total = nA + nB;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= n_tiles; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t d = t * MP_TILE;
+    if (d > total) d = total;
+    splits[t] = merge_path<K>(A, nA, Bv, nB, d);
+  }
+}
+
 // One pass over merge(starts, stops').  Emits one point (x, depth after x) per distinct position.
 // WRITE == false: per-tile point counts; WRITE == true: points are written at tile_off[tile] + rank.
 template <typename K, bool WRITE>
 __global__ void __launch_bounds__(MP_THREADS) k_cover_points(const K* __restrict__ A, int64_t nA, const K* __restrict__ Bv, int64_t nB, int64_t n_tiles,
-                                                             int64_t* __restrict__ tile_cnt, const int64_t* __restrict__ tile_off,
+                                                             const int64_t* __restrict__ splits, int64_t* __restrict__ tile_cnt, const int64_t* __restrict__ tile_off,
                                                              K* __restrict__ px, int32_t* __restrict__ pd) {
   __shared__ K sA[MP_TILE + 1];
   __shared__ K sB[MP_TILE + 1];
-  __shared__ int64_t split[2];
   __shared__ int warp_tot[MP_THREADS / 32];
   const int64_t total = nA + nB;
   const K KMAX = ~(K)0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     int64_t d0 = tile * MP_TILE, d1 = d0 + MP_TILE;
     if (d1 > total) d1 = total;
-    if (threadIdx.x < 2) split[threadIdx.x] = merge_path<K>(A, nA, Bv, nB, threadIdx.x == 0 ? d0 : d1);
-    __syncthreads();
-    const int64_t i0 = split[0], i1 = split[1];
+    const int64_t i0 = splits[tile], i1 = splits[tile + 1];
     const int64_t j0 = d0 - i0, j1 = d1 - i1;
     const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
     for (int t = threadIdx.x; t <= na; t += MP_THREADS) sA[t] = (i0 + t < nA) ? A[i0 + t] : KMAX;
@@ -189,11 +243,10 @@ __device__ __forceinline__ int group_of_lin(K x, uint64_t G, int n_classes);
 // AccIndex = max depth (atomicMax, one per thread and run).
 template <typename K, bool WRITE>
 __global__ void __launch_bounds__(MP_THREADS) k_cover_runs_fused(const K* __restrict__ A, int64_t nA, const K* __restrict__ Bv, int64_t nB, int64_t n_tiles, uint64_t G, CoverCfg cfg,
-                                                                 int64_t* __restrict__ tile_cnt, const int64_t* __restrict__ tile_off,
+                                                                 const int64_t* __restrict__ splits, int64_t* __restrict__ tile_cnt, const int64_t* __restrict__ tile_off,
                                                                  K* __restrict__ rs, K* __restrict__ re, int32_t* __restrict__ racc) {
   __shared__ K sAm[MP_TILE + 2];
   __shared__ K sBm[MP_TILE + 2];
-  __shared__ int64_t split[2];
   __shared__ int warp_tot[MP_THREADS / 32];
   K* sA = sAm + 1;   // sA[-1] = look-behind element
   K* sB = sBm + 1;
@@ -202,9 +255,7 @@ __global__ void __launch_bounds__(MP_THREADS) k_cover_runs_fused(const K* __rest
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     int64_t d0 = tile * MP_TILE, d1 = d0 + MP_TILE;
     if (d1 > total) d1 = total;
-    if (threadIdx.x < 2) split[threadIdx.x] = merge_path<K>(A, nA, Bv, nB, threadIdx.x == 0 ? d0 : d1);
-    __syncthreads();
-    const int64_t i0 = split[0], i1 = split[1];
+    const int64_t i0 = splits[tile], i1 = splits[tile + 1];
     const int64_t j0 = d0 - i0, j1 = d1 - i1;
     const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
     for (int t = threadIdx.x; t <= na + 1; t += MP_THREADS) { int64_t g = i0 - 1 + t; sAm[t] = (g >= 0 && g < nA) ? A[g] : KMAX; }
@@ -703,42 +754,43 @@ static int64_t read_back(gmql_ctx* ctx, const T* dev) {
 
 template <typename K>
 static void phase1_sweep(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total,
-                         const K* sorted_starts /*may be null*/, Phase1Out* p1) {
+                         const K* sorted_starts /*may be null*/, DevBuf<K>& ek_a, bool ek_filled, Phase1Out* p1) {
   const int64_t n = in.n;
   int g = grid_for(ctx, n, 256);
-  DevBuf<K> sk_a, sk_b, ek_a(ctx, n), ek_b(ctx, n);
+  DevBuf<K> sk_a, sk_b, ek_b(ctx, n);
   K* starts = const_cast<K*>(sorted_starts);
   int key_bits = bits_for(n_classes_total * lm.G);
   if (!starts) { sk_a.alloc(ctx, n); sk_b.alloc(ctx, n); }
-  LAUNCH(ctx, (k_cover_event_keys<K>), g, 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, starts ? (K*)nullptr : sk_a.p, ek_a.p);
+  if (!ek_filled) LAUNCH(ctx, (k_cover_event_keys<K>), g, 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, starts ? (K*)nullptr : sk_a.p, ek_a.p);
   if (!starts) radix_sort<K>(ctx, sk_a.p, sk_b.p, nullptr, nullptr, n, key_bits, &starts, nullptr);
   K* stops = nullptr;
   radix_sort<K>(ctx, ek_a.p, ek_b.p, nullptr, nullptr, n, key_bits, &stops, nullptr);
 
   int64_t total = 2 * n;
   int64_t n_tiles = ceil_div64(total, MP_TILE);
-  DevBuf<int64_t> tile_cnt(ctx, n_tiles + 1);
+  DevBuf<int64_t> tile_cnt(ctx, n_tiles + 1), splits(ctx, n_tiles + 1);
   int mg = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->num_sms * 8);
+  LAUNCH(ctx, (k_merge_splits<K>), grid_for(ctx, n_tiles + 1, 128, 1), 128, 0, starts, n, stops, n, n_tiles, splits.p);
   DevBuf<K> rs, re;
   int64_t nr = 0;
   if (flag != GMQL_HISTOGRAM) {
     // COVER / FLAT: fused merge + run detection (no point list)
-    LAUNCH(ctx, (k_cover_runs_fused<K, false>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, lm.G, cfg, tile_cnt.p, (const int64_t*)nullptr, (K*)nullptr, (K*)nullptr, (int32_t*)nullptr);
+    LAUNCH(ctx, (k_cover_runs_fused<K, false>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, lm.G, cfg, splits.p, tile_cnt.p, (const int64_t*)nullptr, (K*)nullptr, (K*)nullptr, (int32_t*)nullptr);
     device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, tile_cnt.p, tile_cnt.p, n_tiles, tile_cnt.p + n_tiles);
     nr = read_back<int64_t>(ctx, tile_cnt.p + n_tiles);
     rs.alloc(ctx, nr); re.alloc(ctx, nr);
     p1->acc.alloc(ctx, nr);
     p1->acc.zero();
-    if (nr) LAUNCH(ctx, (k_cover_runs_fused<K, true>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, lm.G, cfg, (int64_t*)nullptr, tile_cnt.p, rs.p, re.p, p1->acc.p);
+    if (nr) LAUNCH(ctx, (k_cover_runs_fused<K, true>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, lm.G, cfg, splits.p, (int64_t*)nullptr, tile_cnt.p, rs.p, re.p, p1->acc.p);
     sk_a.release(); sk_b.release(); ek_a.release(); ek_b.release();
   } else {
     // HISTOGRAM: distinct positions with the depth after them, then one segment per depth change
-    LAUNCH(ctx, (k_cover_points<K, false>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, tile_cnt.p, (const int64_t*)nullptr, (K*)nullptr, (int32_t*)nullptr);
+    LAUNCH(ctx, (k_cover_points<K, false>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, splits.p, tile_cnt.p, (const int64_t*)nullptr, (K*)nullptr, (int32_t*)nullptr);
     device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, tile_cnt.p, tile_cnt.p, n_tiles, tile_cnt.p + n_tiles);
     int64_t np = read_back<int64_t>(ctx, tile_cnt.p + n_tiles);
     DevBuf<K> px(ctx, np);
     DevBuf<int32_t> pd(ctx, np);
-    LAUNCH(ctx, (k_cover_points<K, true>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, (int64_t*)nullptr, tile_cnt.p, px.p, pd.p);
+    LAUNCH(ctx, (k_cover_points<K, true>), mg, MP_THREADS, 0, starts, n, stops, n, n_tiles, splits.p, (int64_t*)nullptr, tile_cnt.p, px.p, pd.p);
     sk_a.release(); sk_b.release(); ek_a.release(); ek_b.release();
     DevBuf<int32_t> flags(ctx, np);
     DevBuf<int64_t> excl(ctx, np + 1);
@@ -842,7 +894,16 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
 
   // interval index over the ORIGINAL coordinates (phase 2 contributors, GMAP4 uses the un-extended inputs)
   IntervalIndex<K> ix;
-  build_index<K>(ctx, in, cls.p, n_classes_total, lm, &ix, /*payload_len=*/plan.n_cols == 0 && spans.G < 0xffffffffull);
+  const bool payload_len = plan.n_cols == 0 && spans.G < 0xffffffffull;
+  const bool fused_keys = payload_len && !has_zero && flag != GMQL_SUMMIT && n > 0;
+  DevBuf<K> ek_a(ctx, flag != GMQL_SUMMIT ? n : 0);
+  if (fused_keys) {
+    alloc_index<K>(ctx, n, &ix);
+    LAUNCH(ctx, (k_cover_all_keys<K>), grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls.p, n, lm, cfg.B, ix.start_a.p, ix.row_a.p, ek_a.p);
+    finish_index<K>(ctx, in, cls.p, n_classes_total, lm, &ix, true);
+  } else {
+    build_index<K>(ctx, in, cls.p, n_classes_total, lm, &ix, payload_len);
+  }
 
   Phase1Out p1;
   if (n == 0) {
@@ -851,7 +912,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     phase1_summit(ctx, in, cls.p, spans, cfg, n_classes_total, &p1);
   } else {
     // without zero-length regions the phase-1 start keys are exactly the index's sorted starts: reuse them
-    phase1_sweep<K>(ctx, in, cls.p, lm, cfg, flag, n_classes_total, has_zero ? (const K*)nullptr : ix.start, &p1);
+    phase1_sweep<K>(ctx, in, cls.p, lm, cfg, flag, n_classes_total, has_zero ? (const K*)nullptr : ix.start, ek_a, fused_keys, &p1);
   }
 
   // phase 2
@@ -972,11 +1033,30 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     gmql_upload_regions(ctx, in, need_cols, &d);
     cudaEventRecord(ctx->ev_h1, ctx->stream);
     cudaEventRecord(ctx->ev_k0, ctx->stream);
-    Inspect ins;
-    inspect_input(ctx, d, &ins);
-    bool unified = ins.has_star != 0 || d.strand == nullptr || d.n == 0;   // assignGroups (:328-341)
+    // one read of the columns: chromosome spans + input flags
     SpanTable spans;
-    build_span_table(ctx, &d, nullptr, &spans, (unsigned long long)bin_size + 2ull);
+    spans.n_chrom = d.n_chrom;
+    spans.span.alloc(ctx, d.n_chrom); spans.span.zero();
+    spans.coff.alloc(ctx, d.n_chrom + 1);
+    DevBuf<int> flags(ctx, 4);
+    flags.zero();
+    if (d.n) {
+      int nb = (int)std::min<int64_t>(ceil_div64(d.n, 256 * 8), (int64_t)ctx->num_sms * 8);
+      size_t sh = d.n_chrom <= 4096 ? sizeof(unsigned long long) * (size_t)d.n_chrom : 0;
+      LAUNCH(ctx, k_cover_prepass, nb, 256, sh, d.chrom, d.start, d.stop, d.coord_bits, d.strand, d.sample, d.n, d.n_chrom, d.n_samples, spans.span.p, flags.p);
+    }
+    LAUNCH(ctx, k_chrom_offsets, 1, 32, 0, spans.span.p, d.n_chrom, spans.coff.p, (unsigned long long)bin_size + 2ull);
+    int hf[4];
+    uint64_t G = 0;
+    CUDA_TRY(cudaMemcpyAsync(hf, flags.p, sizeof hf, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&G, spans.coff.p + d.n_chrom, sizeof G, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    GMQL_REQUIRE(!hf[2], GMQL_ERR_INVALID, "region with chromosome/sample index out of range, start > stop, negative start or bad strand code");
+    spans.G = G;
+    Inspect ins;
+    ins.has_star = hf[0];
+    ins.has_zero = hf[1];
+    bool unified = ins.has_star != 0 || d.strand == nullptr || d.n == 0;   // assignGroups (:328-341)
     uint64_t total = (uint64_t)n_groups * (unified ? 1ull : 2ull) * spans.G;
     res = new gmql_result();
     if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, res);

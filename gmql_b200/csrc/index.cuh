@@ -135,19 +135,32 @@ static inline int grid_for(gmql_ctx* ctx, int64_t n, int threads, int per_thread
 }
 
 template <typename K>
-static void build_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix, bool payload_len = false) {
-  ix->n = r.n;
-  int64_t n = r.n;
+static void alloc_index(gmql_ctx* ctx, int64_t n, IntervalIndex<K>* ix) {
+  ix->n = n;
   ix->start_a.alloc(ctx, n); ix->start_b.alloc(ctx, n);
   ix->row_a.alloc(ctx, n); ix->row_b.alloc(ctx, n);
   ix->stop.alloc(ctx, n); ix->pmax.alloc(ctx, n);
-  if (n == 0) { ix->start = ix->start_a.p; ix->row = ix->row_a.p; return; }
+  ix->start = ix->start_a.p; ix->row = ix->row_a.p;
+}
+
+// start_a / row_a hold the unsorted keys and payloads (row, or length when payload_len): sort, derive stops, running max
+template <typename K>
+static void finish_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix, bool payload_len) {
+  int64_t n = ix->n;
+  if (n == 0) return;
   int g = grid_for(ctx, n, 256);
-  // payload_len requires region lengths < 2^32 (checked by the caller through the span table)
-  LAUNCH(ctx, (k_index_keys<K>), g, 256, 0, r.chrom, r.start, payload_len ? r.stop : (const void*)nullptr, r.coord_bits, blocks, n, lm, ix->start_a.p, ix->row_a.p);
   uint64_t max_lin = n_blocks * lm.G;
   radix_sort<K>(ctx, ix->start_a.p, ix->start_b.p, ix->row_a.p, ix->row_b.p, n, bits_for(max_lin), &ix->start, &ix->row);
   if (payload_len) LAUNCH(ctx, (k_index_stops_from_len<K>), g, 256, 0, ix->start, ix->row, n, ix->stop.p);
   else LAUNCH(ctx, (k_index_stops<K>), g, 256, 0, r.chrom, r.stop, r.coord_bits, blocks, n, lm, ix->row, ix->stop.p);
   device_scan<K, K, OpMax<K>, true>(ctx, ix->stop.p, ix->pmax.p, n, (K*)nullptr);
+}
+
+template <typename K>
+static void build_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix, bool payload_len = false) {
+  alloc_index<K>(ctx, r.n, ix);
+  if (r.n == 0) return;
+  // payload_len requires region lengths < 2^32 (checked by the caller through the span table)
+  LAUNCH(ctx, (k_index_keys<K>), grid_for(ctx, r.n, 256), 256, 0, r.chrom, r.start, payload_len ? r.stop : (const void*)nullptr, r.coord_bits, blocks, r.n, lm, ix->start_a.p, ix->row_a.p);
+  finish_index<K>(ctx, r, blocks, n_blocks, lm, ix, payload_len);
 }

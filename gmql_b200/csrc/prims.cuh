@@ -173,9 +173,9 @@ constexpr int RS_BITS = 8;
 constexpr int RS_RADIX = 1 << RS_BITS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr uint32_t OS_FLAG_AGG = 1u << 30;
-constexpr uint32_t OS_FLAG_INCL = 1u << 31;
-constexpr uint32_t OS_VALUE_MASK = (1u << 30) - 1u;
+#define OS_FLAG_AGG (1u << 30)
+#define OS_FLAG_INCL (1u << 31)
+#define OS_VALUE_MASK ((1u << 30) - 1u)
 template <typename K> struct OsCfg {
   static constexpr int ITEMS = sizeof(K) == 4 ? 16 : 8;
   static constexpr int TILE = RS_THREADS * ITEMS;
@@ -277,20 +277,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const K* __restrict__ ki
     for (int q = 0; q < w; ++q) b += wtot[q];
     tile_excl[threadIdx.x] = b + x - tot;
   }
-  uint32_t look = 0;
-  if (tile > 0) {
-    int64_t p = (int64_t)tile - 1;
-    while (true) {
-      uint32_t s = tile_state[p * RS_RADIX + threadIdx.x];
-      if ((s & (OS_FLAG_AGG | OS_FLAG_INCL)) == 0) continue;
-      look += s & OS_VALUE_MASK;
-      if (s & OS_FLAG_INCL) break;
-      --p;
-    }
-    tile_state[(int64_t)tile * RS_RADIX + threadIdx.x] = ((look + tot) & OS_VALUE_MASK) | OS_FLAG_INCL;
-  }
-  glob_base[threadIdx.x] = digit_start[threadIdx.x] + look - tile_excl[threadIdx.x];
   __syncthreads();
+  // reorder the tile in shared memory first (needs only tile-local offsets); the look-back below then finds more
+  // predecessors already finished
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     int64_t i = wbase + j * 32;
@@ -301,6 +290,28 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const K* __restrict__ ki
       if (HAS_VAL) svals[pos] = vin[i];
     }
   }
+  // decoupled look-back, 8 predecessors per round trip
+  uint32_t look = 0;
+  if (tile > 0) {
+    int64_t p = (int64_t)tile - 1;
+    bool done = false;
+    while (!done) {
+      uint32_t s8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s8[q] = (p - q >= 0) ? tile_state[(p - q) * RS_RADIX + threadIdx.x] : OS_FLAG_INCL;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (done) break;
+        uint32_t sv = s8[q];
+        if ((sv & (OS_FLAG_AGG | OS_FLAG_INCL)) == 0) break;     // not published yet: poll again from here
+        look += sv & OS_VALUE_MASK;
+        --p;
+        if (sv & OS_FLAG_INCL) done = true;
+      }
+    }
+    tile_state[(int64_t)tile * RS_RADIX + threadIdx.x] = ((look + tot) & OS_VALUE_MASK) | OS_FLAG_INCL;
+  }
+  glob_base[threadIdx.x] = digit_start[threadIdx.x] + look - tile_excl[threadIdx.x];
   __syncthreads();
   int64_t rem = n - base;
   int cnt = rem < TILE ? (int)rem : TILE;
