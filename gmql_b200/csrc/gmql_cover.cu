@@ -1018,6 +1018,8 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     CUDA_TRY(cudaSetDevice(ctx->device));
     GMQL_REQUIRE(in != nullptr, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_groups >= 1 && min_acc && max_acc, GMQL_ERR_INVALID, "n_groups >= 1 and per-group thresholds are required");
+    const bool force_unified = (flag & GMQL_COVER_FORCE_UNIFIED) != 0;
+    flag &= ~GMQL_COVER_FORCE_UNIFIED;
     GMQL_REQUIRE(flag >= GMQL_COVER && flag <= GMQL_HISTOGRAM, GMQL_ERR_INVALID, "unknown cover flag");
     GMQL_REQUIRE(bin_size > 0, GMQL_ERR_INVALID, "bin_size must be positive (BinSize.Cover = 2000)");
     for (int g = 0; g < n_groups; ++g)
@@ -1056,7 +1058,7 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     Inspect ins;
     ins.has_star = hf[0];
     ins.has_zero = hf[1];
-    bool unified = ins.has_star != 0 || d.strand == nullptr || d.n == 0;   // assignGroups (:328-341)
+    bool unified = force_unified || ins.has_star != 0 || d.strand == nullptr || d.n == 0;   // assignGroups (:328-341)
     uint64_t total = (uint64_t)n_groups * (unified ? 1ull : 2ull) * spans.G;
     res = new gmql_result();
     if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, res);

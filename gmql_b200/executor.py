@@ -168,7 +168,7 @@ class GMQLCudaExecutor:
         return out
 
     # ---- COVER ------------------------------------------------------------------------------------------------------------
-    def cover_raw(self, coverFlag, min, max, aggregators, groups, ds):
+    def cover_raw(self, coverFlag, min, max, aggregators, groups, ds, force_unified=False):
         c_ds, keep = ds.as_c()
         n_s = int(ds.sample_ids.shape[0])
         if groups is not None:
@@ -200,15 +200,16 @@ class GMQLCudaExecutor:
         c_aggs = self._c_aggs(aggregators, ds)
         out = C.c_void_p()
         self._check(self.lib.gmql_cover(self.ctx, C.byref(c_ds), sample_group.ctypes.data if sample_group is not None else None,
-                                        len(gids), CoverFlag.CODE[coverFlag], mn.ctypes.data, mx.ctypes.data,
+                                        len(gids), CoverFlag.CODE[coverFlag] | (0x100 if force_unified else 0), mn.ctypes.data, mx.ctypes.data,
                                         self.binSize.Cover, c_aggs, len(aggregators), C.byref(out)))
         del keep
         return _Result(self, out), gids
 
-    def GenometricCover(self, coverFlag, min, max, aggregators, groups, ds):
+    def GenometricCover(self, coverFlag, min, max, aggregators, groups, ds, force_unified=False):
         """COVER / FLAT / SUMMIT / HISTOGRAM.  groups: dict sample_id -> group_id (implement_mgd) or None.  Returns records
-        (group_id, chrom, start, stop, strand, (AccIndex, JaccardIntersect, JaccardResult, aggregates...))."""
-        res, gids = self.cover_raw(coverFlag, min, max, aggregators, groups, ds)
+        (group_id, chrom, start, stop, strand, (AccIndex, JaccardIntersect, JaccardResult, aggregates...)).
+        force_unified: the caller sharded the dataset and some OTHER shard holds a '*' region (strand unification is global)."""
+        res, gids = self.cover_raw(coverFlag, min, max, aggregators, groups, ds, force_unified)
         g = res.column(L.COL_COV_GROUP, np.int32)
         chrom = res.column(L.COL_COV_CHROM, np.int32)
         start = res.column(L.COL_COV_START, np.int64)

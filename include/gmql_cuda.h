@@ -97,6 +97,10 @@ typedef struct { int32_t left_sample; int32_t right_sample; } gmql_pair;
 
 /* COVER variants (CoverParameters/CoverFlag; GenometricCover.scala:112-117) */
 typedef enum { GMQL_COVER = 0, GMQL_FLAT = 1, GMQL_SUMMIT = 2, GMQL_HISTOGRAM = 3 } gmql_cover_flag;
+/* OR-ed into `flag`: treat the dataset as containing a '*' region.  Strand unification is decided on the WHOLE dataset
+ * (assignGroups, GenometricCover.scala:328); a caller that shards the input (by chromosome, across GPUs) passes the
+ * global answer to every shard. */
+#define GMQL_COVER_FORCE_UNIFIED 0x100
 
 /* JOIN atoms after the Compiler's rewriting (GmqlParsers.scala:462-487):
  * DLE(n)->DISTLESS(n+1), DGE(n)->DISTGREATER(n-1); predicates are strict (GenometricJoin.scala:250-251). */
