@@ -1,0 +1,383 @@
+// cover_tiled.cuh — tile-resident COVER / FLAT (both phases) for dense inputs with 32-bit linear coordinates.
+//
+// Instead of fully sorting 2n events and merging them, the linear genome is cut into tiles of W = 2^logw positions
+// (W <= 65 536).  Regions (linear start, length) are only PARTITIONED by the tile of their start (radix passes on the
+// top key bits; the order inside a tile is irrelevant).  One thread block then owns a tile:
+//   * its events are the +1 of every region that starts in the tile and the -1 (at stop', the extractor's extended stop,
+//     GenometricCover.scala:353-354) of every region of this tile or the previous one whose stop' falls inside; regions
+//     are shorter than W, so no other tile can contribute, and the depth entering the tile is simply the number of
+//     regions of the previous tile that are still open;
+//   * the tile's distinct event positions are marked in a W-bit occupancy bitmap in shared memory; a popcount prefix
+//     over the bitmap words RANKS every position, i.e. sorts the distinct positions without sorting anything;
+//   * +1 / -1 are summed per rank with shared-memory atomics — coincident events are summed exactly as the reference's
+//     reduceByKey does (:98-108) — and a block-wide prefix sum over the (sparse) ranks gives the depth profile;
+//   * in-range stretches become PIECES (clipped at tile edges, like the reference's bins :110-118);
+//   * GMAP4 (GMAP4.scala:20-100) runs region-driven inside the tile: every region of the tile (and the regions of the
+//     previous tile that reach into it) finds the pieces it overlaps and accumulates count / startMin / endMax /
+//     startMax / endMin with warp-aggregated shared-memory atomics.  A (run, region) pair is accounted exactly once, in
+//     tile max(tile(run.start), tile(region.start)) — the reference's own first-bin rule (GMAP4.scala:44-45) at tile
+//     granularity;
+//   * a small stitch pass fuses pieces that touch at tile edges (the reference's boundary merge, :121-152).
+// Work per tile is proportional to its events (plus W/32 bitmap words), not to W.
+// Preconditions (checked by the caller, which otherwise uses the sort-and-merge path): uint32 keys, COVER or FLAT,
+// no zero-length regions, no aggregates, max region length < W - 2.  Capacity overflows (distinct positions, pieces or
+// halo regions of one tile) raise `fail` and the caller falls back as well.
+#pragma once
+#include "index.cuh"
+
+namespace tiled {
+
+constexpr int MAX_LOGW = 16;
+constexpr int THREADS = 512;
+constexpr int NWARPS = THREADS / 32;
+constexpr int MAXWORDS = (1 << MAX_LOGW) / 32;
+constexpr int CAP_EV = 12288;           // distinct event positions per tile
+constexpr int MAXP = 512;               // pieces per tile
+constexpr int HCAP = 512;               // regions of the previous tile still open at the tile start
+constexpr uint32_t EXT = 0x80000000u;   // length payload bit: stop' = stop + 1
+constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 4 * CAP_EV + 2 * CAP_EV + 8 * HCAP + 32 * MAXP;
+
+struct Cfg {
+  int n_groups, n_classes;
+  const int32_t* mn;
+  const int32_t* mx;
+  int32_t mn0, mx0;    // thresholds of group 0 (fast path when n_groups == 1)
+  uint64_t G;
+};
+
+struct Pieces {
+  uint32_t* pstart; uint32_t* pend; int32_t* acc; int32_t* cnt;
+  uint32_t* smin; uint32_t* emax; uint32_t* smax; uint32_t* emin; uint8_t* flags;   // bit0: continues from the previous tile, bit1: reaches the tile end
+  unsigned long long* cursor;
+  int64_t cap;
+  int* fail;   // 1: output capacity, 2: distinct positions, 3: pieces, 4: halo regions of one tile
+};
+
+__device__ __forceinline__ bool in_range(const Cfg& c, int32_t d, uint64_t pos) {
+  if (c.n_groups == 1) return d >= c.mn0 && d <= c.mx0;
+  int g = (int)((pos / c.G) / (uint64_t)c.n_classes);
+  return d >= c.mn[g] && d <= c.mx[g];
+}
+
+// linear start key and length payload (bit 31: the extractor's one-base extension, GenometricCover.scala:353-354)
+static __global__ void k_tile_keys(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls,
+                                   int64_t n, LinMap lm, int64_t B, uint32_t* __restrict__ skeys, uint32_t* __restrict__ lens) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+    uint64_t base = (cls ? (uint64_t)cls[i] : 0ull) * lm.G + lm.coff[chrom[i]];
+    bool ext = (e % B == 0 && s / B != e / B);
+    skeys[i] = (uint32_t)(base + (uint64_t)s);
+    lens[i] = (uint32_t)(e - s) | (ext ? EXT : 0u);
+  }
+}
+
+// keys partitioned by tile -> first index of every tile (off[nT] = n)
+static __global__ void k_tile_offsets(const uint32_t* __restrict__ keys, int64_t n, int64_t nT, int logw, uint32_t* __restrict__ off) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = keys[i] >> logw;
+    int64_t tp = i > 0 ? (int64_t)(keys[i - 1] >> logw) : -1;
+    for (int64_t u = tp + 1; u <= t; ++u) off[u] = (uint32_t)i;
+    if (i == n - 1) for (int64_t u = t + 1; u <= nT; ++u) off[u] = (uint32_t)n;
+  }
+}
+
+__device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t* total, int32_t* scratch /*[NWARPS]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) scratch[w] = x;
+  __syncthreads();
+  int32_t base = 0, tot = 0;
+#pragma unroll
+  for (int q = 0; q < NWARPS; ++q) { int32_t c = scratch[q]; if (q < w) base += c; tot += c; }
+  __syncthreads();
+  *total = tot;
+  return base + x - v;
+}
+
+static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t* __restrict__ S_key, const uint32_t* __restrict__ S_len, const uint32_t* __restrict__ offS,
+                                                                  int64_t nT, int logw, Cfg cfg, Pieces out) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
+  uint16_t* wpre = (uint16_t*)(bitmap + MAXWORDS);         // [MAXWORDS] set bits before each word
+  int32_t* delta = (int32_t*)(wpre + MAXWORDS);            // [CAP_EV] net +1/-1 per distinct position (by rank)
+  uint16_t* epos = (uint16_t*)(delta + CAP_EV);            // [CAP_EV] tile-local position of each rank
+  uint32_t* hS = (uint32_t*)(epos + CAP_EV);               // [HCAP] halo regions: start, length payload
+  uint32_t* hL = hS + HCAP;
+  uint32_t* pst = hL + HCAP;                               // [MAXP] x 8: the tile's pieces and their GMAP4 accumulators
+  uint32_t* pen = pst + MAXP;
+  int32_t* pacc = (int32_t*)(pen + MAXP);
+  int32_t* pcnt = pacc + MAXP;
+  uint32_t* psmin = (uint32_t*)(pcnt + MAXP);
+  uint32_t* pemax = psmin + MAXP;
+  uint32_t* psmax = pemax + MAXP;
+  uint32_t* pemin = psmax + MAXP;
+  __shared__ int32_t scratch[NWARPS];
+  __shared__ int s_nh;
+  __shared__ long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t W = 1u << logw;
+  const int nW = (int)(W >> 5) > 0 ? (int)(W >> 5) : 1;
+  const int WPT = (nW + THREADS - 1) / THREADS;            // bitmap words per thread (consecutive)
+
+  for (int64_t tile = blockIdx.x; tile < nT; tile += gridDim.x) {
+    const uint32_t s0 = offS[tile], s1 = offS[tile + 1];
+    const uint32_t h0 = tile > 0 ? offS[tile - 1] : s0;
+    const uint32_t tile_lo = (uint32_t)tile << logw;
+    if (s0 == s1 && h0 == s0) continue;                    // nothing starts here and nothing can reach in: depth 0 throughout
+    // ---- phase 0: clear the bitmap
+    for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;
+    if (tid == 0) s_nh = 0;
+    __syncthreads();
+    // ---- phase 1: mark event positions; collect the previous tile's regions that are still open
+    for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
+      uint32_t i = i0 + tid;
+      bool reach = false;
+      uint32_t rs = 0, lp = 0, ee = 0;
+      if (i < s0) { rs = S_key[i]; lp = S_len[i]; ee = rs + (lp & ~EXT) + (lp >> 31); reach = ee >= tile_lo; }
+      unsigned bal = __ballot_sync(0xffffffffu, reach);
+      if (bal) {
+        int basew = 0;
+        if (lane == 0) basew = atomicAdd(&s_nh, __popc(bal));
+        basew = __shfl_sync(0xffffffffu, basew, 0);
+        if (reach) {
+          int slot = basew + __popc(bal & ((1u << lane) - 1u));
+          if (slot < HCAP) { hS[slot] = rs; hL[slot] = lp; }
+          uint32_t q = ee - tile_lo;
+          atomicOr(&bitmap[q >> 5], 1u << (q & 31));
+        }
+      }
+    }
+    for (uint32_t i = s0 + tid; i < s1; i += THREADS) {
+      uint32_t rs = S_key[i], lp = S_len[i];
+      uint32_t q = rs - tile_lo;
+      atomicOr(&bitmap[q >> 5], 1u << (q & 31));
+      uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
+      if (qe < W) atomicOr(&bitmap[qe >> 5], 1u << (qe & 31));
+    }
+    __syncthreads();
+    const int nh = s_nh;
+    const int32_t depth_in = nh;                           // regions still open when the tile begins
+    // ---- phase 2: rank = popcount prefix over the bitmap
+    int32_t total;
+    {
+      int32_t c = 0;
+      const int w0 = tid * WPT;
+      for (int q = 0; q < WPT; ++q) if (w0 + q < nW) c += __popc(bitmap[w0 + q]);
+      int32_t pre = block_excl_scan(c, &total, scratch);
+      for (int q = 0; q < WPT; ++q) if (w0 + q < nW) { wpre[w0 + q] = (uint16_t)pre; pre += __popc(bitmap[w0 + q]); }
+    }
+    if (nh > HCAP || total > CAP_EV) {                     // uniform across the block
+      if (tid == 0) *out.fail = nh > HCAP ? 4 : 2;
+      __syncthreads();
+      continue;
+    }
+    for (int k = tid; k < total; k += THREADS) delta[k] = 0;
+    __syncthreads();
+    // ---- phase 3: sum +1 / -1 per distinct position
+    for (int k = tid; k < nh; k += THREADS) {
+      uint32_t lp = hL[k];
+      uint32_t q = hS[k] + (lp & ~EXT) + (lp >> 31) - tile_lo;
+      int r = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
+      atomicAdd(&delta[r], -1);
+      epos[r] = (uint16_t)q;
+    }
+    for (uint32_t i = s0 + tid; i < s1; i += THREADS) {
+      uint32_t rs = S_key[i], lp = S_len[i];
+      uint32_t q = rs - tile_lo;
+      int r = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
+      atomicAdd(&delta[r], 1);
+      epos[r] = (uint16_t)q;
+      uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
+      if (qe < W) {
+        int r2 = wpre[qe >> 5] + __popc(bitmap[qe >> 5] & ((1u << (qe & 31)) - 1u));
+        atomicAdd(&delta[r2], -1);
+        epos[r2] = (uint16_t)qe;
+      }
+    }
+    __syncthreads();
+    // ---- phase 4: depth profile over the distinct positions, pieces
+    const bool cont0 = in_range(cfg, depth_in, tile_lo);
+    const int IT = ((total + THREADS - 1) / THREADS) | 1;  // ranks per thread; odd stride: conflict-free shared-memory access
+    const int k0 = tid * IT < total ? tid * IT : total;
+    const int k1 = k0 + IT < total ? k0 + IT : total;
+    int32_t csum = 0;
+    for (int k = k0; k < k1; ++k) csum += delta[k];
+    int32_t tile_net;
+    const int32_t d_start = depth_in + block_excl_scan(csum, &tile_net, scratch);
+    // the state just before my first rank: in range iff the depth there is (the previous position belongs to the same
+    // class unless the depth is 0, which is never in range)
+    const bool in0 = k0 < total ? in_range(cfg, d_start, (uint64_t)tile_lo + epos[k0]) : false;
+    int nopen = 0;
+    {
+      int32_t d = d_start;
+      bool prev_in = k0 == 0 ? cont0 : in0;
+      for (int k = k0; k < k1; ++k) {
+        d += delta[k];
+        bool cur = in_range(cfg, d, (uint64_t)tile_lo + epos[k]);
+        nopen += (cur && !prev_in) ? 1 : 0;
+        prev_in = cur;
+      }
+    }
+    int32_t open_total;
+    const int32_t open_pre = block_excl_scan(nopen, &open_total, scratch);
+    const int np_all = (cont0 ? 1 : 0) + open_total;
+    if (np_all > MAXP) {
+      if (tid == 0) *out.fail = 3;
+      __syncthreads();
+      continue;
+    }
+    const int np = np_all;
+    for (int k = tid; k < np; k += THREADS) { pacc[k] = 0; pcnt[k] = 0; psmin[k] = 0xffffffffu; pemax[k] = 0; psmax[k] = 0; pemin[k] = 0xffffffffu; pen[k] = 0; }
+    if (tid == 0 && cont0) pst[0] = tile_lo;
+    __syncthreads();
+    if (tid == 0 && cont0) atomicMax(&pacc[0], depth_in);
+    {
+      int32_t d = d_start;
+      bool prev_in = k0 == 0 ? cont0 : in0;
+      int cur = (cont0 ? 1 : 0) + open_pre - 1;             // piece open at my first rank (when prev_in)
+      int32_t run_max = 0;
+      for (int k = k0; k < k1; ++k) {
+        d += delta[k];
+        uint32_t pos = tile_lo + epos[k];
+        bool cin = in_range(cfg, d, pos);
+        if (cin) {
+          if (!prev_in) { ++cur; pst[cur] = pos; run_max = d; }
+          else if (d > run_max) run_max = d;
+        } else if (prev_in) {
+          pen[cur] = pos;
+          if (run_max > 0) atomicMax(&pacc[cur], run_max);
+          run_max = 0;
+        }
+        prev_in = cin;
+      }
+      if (prev_in && run_max > 0 && cur >= 0) atomicMax(&pacc[cur], run_max);
+    }
+    // depth after the tile's last event, judged with that event's group (tile_lo + W - 1 may lie beyond the last class)
+    const bool reach_end = np > 0 && in_range(cfg, depth_in + tile_net, (uint64_t)tile_lo + (total > 0 ? epos[total - 1] : 0));
+    __syncthreads();
+    if (tid == 0 && reach_end) pen[np - 1] = tile_lo + W;
+    __syncthreads();
+    // ---- phase 5: GMAP4, region-driven: the still-open regions of the previous tile, then the tile's own
+    if (np > 0) {
+      const uint32_t nS = s1 - s0;
+      const uint32_t n_h_rounds = ((uint32_t)nh + THREADS - 1) / THREADS, n_o_rounds = (nS + THREADS - 1) / THREADS;
+      for (uint32_t round = 0; round < n_h_rounds + n_o_rounds; ++round) {
+        const bool own = round >= n_h_rounds;
+        bool valid;
+        uint32_t rs = 0, re = 0;
+        if (!own) {
+          uint32_t i = round * THREADS + tid;
+          valid = i < (uint32_t)nh;
+          if (valid) { rs = hS[i]; re = rs + (hL[i] & ~EXT); valid = re > tile_lo; }
+        } else {
+          uint32_t i = (round - n_h_rounds) * THREADS + tid;
+          valid = i < nS;
+          if (valid) { rs = S_key[s0 + i]; re = rs + (S_len[s0 + i] & ~EXT); }
+        }
+        int j = np;
+        if (valid) {
+          int lo = 0, hi = np;                 // first piece with end > rs
+          while (lo < hi) { int mid = (lo + hi) >> 1; if (pen[mid] > rs) hi = mid; else lo = mid + 1; }
+          j = lo;
+        }
+        while (true) {
+          bool ov = valid && j < np && pst[j] < re;
+          unsigned bal = __ballot_sync(0xffffffffu, ov);
+          if (!bal) break;
+          int J = __shfl_sync(0xffffffffu, j, __ffs(bal) - 1);
+          bool mine = ov && j == J;
+          bool add = mine && (own || !(J == 0 && cont0));   // halo regions only feed runs that START in this tile
+          unsigned m = __ballot_sync(0xffffffffu, add);
+          if (m) {
+            uint32_t a_smin = __reduce_min_sync(0xffffffffu, add ? rs : 0xffffffffu);
+            uint32_t a_emax = __reduce_max_sync(0xffffffffu, add ? re : 0u);
+            uint32_t a_smax = __reduce_max_sync(0xffffffffu, add ? rs : 0u);
+            uint32_t a_emin = __reduce_min_sync(0xffffffffu, add ? re : 0xffffffffu);
+            if (lane == (__ffs(m) - 1)) {
+              atomicAdd(&pcnt[J], __popc(m));
+              atomicMin(&psmin[J], a_smin); atomicMax(&pemax[J], a_emax);
+              atomicMax(&psmax[J], a_smax); atomicMin(&pemin[J], a_emin);
+            }
+          }
+          if (mine) ++j;
+        }
+      }
+      __syncthreads();
+      // ---- publish the tile's pieces
+      if (tid == 0) {
+        unsigned long long b = atomicAdd(out.cursor, (unsigned long long)np);
+        if ((int64_t)(b + np) > out.cap) { *out.fail = 1; s_base = -1; } else s_base = (long long)b;
+      }
+      __syncthreads();
+      const long long gb = s_base;
+      if (gb >= 0) {
+        for (int k = tid; k < np; k += THREADS) {
+          out.pstart[gb + k] = pst[k]; out.pend[gb + k] = pen[k]; out.acc[gb + k] = pacc[k]; out.cnt[gb + k] = pcnt[k];
+          out.smin[gb + k] = psmin[k]; out.emax[gb + k] = pemax[k]; out.smax[gb + k] = psmax[k]; out.emin[gb + k] = pemin[k];
+          out.flags[gb + k] = (uint8_t)(((k == 0 && cont0) ? 1 : 0) | ((k == np - 1 && reach_end) ? 2 : 0));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- stitch: pieces sorted by start -> runs ------------------------------------------------------------------------
+static __global__ void k_piece_heads(const uint32_t* __restrict__ order, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend, const uint8_t* __restrict__ flags, int64_t np, int32_t* __restrict__ head) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+    bool merge = false;
+    if (k > 0) {
+      uint32_t a = order[k - 1], b = order[k];
+      merge = (flags[b] & 1) && (flags[a] & 2) && pend[a] == pstart[b];
+    }
+    head[k] = merge ? 0 : 1;
+  }
+}
+
+struct Runs {
+  uint32_t* rstart; uint32_t* rend; int32_t* acc; int32_t* cnt; uint32_t* smin; uint32_t* emax; uint32_t* smax; uint32_t* emin;
+};
+
+static __global__ void k_piece_merge(const uint32_t* __restrict__ order, Pieces p, int64_t np, const int32_t* __restrict__ head, const int64_t* __restrict__ head_excl, Runs r) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t a = order[k];
+    int64_t o = head[k] ? head_excl[k] : head_excl[k] - 1;
+    if (head[k]) r.rstart[o] = p.pstart[a];
+    if (k + 1 == np || head[k + 1]) r.rend[o] = p.pend[a];
+    atomicMax(&r.acc[o], p.acc[a]);
+    if (p.cnt[a]) {
+      atomicAdd(&r.cnt[o], p.cnt[a]);
+      atomicMin(&r.smin[o], p.smin[a]); atomicMax(&r.emax[o], p.emax[a]);
+      atomicMax(&r.smax[o], p.smax[a]); atomicMin(&r.emin[o], p.emin[a]);
+    }
+  }
+}
+
+// runs -> the arrays the common output stage (k_cover_compact) consumes
+static __global__ void k_runs_finalize(Runs r, int64_t nr, LinMap lm, int flat, uint32_t* __restrict__ ocls, int32_t* __restrict__ ochrom, int64_t* __restrict__ fstart, int64_t* __restrict__ fstop,
+                                       int32_t* __restrict__ oacc, int32_t* __restrict__ keep, double* __restrict__ j1, double* __restrict__ j2) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nr; k += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t x = r.rstart[k];
+    uint64_t cls = x / lm.G, rem = x - cls * lm.G;
+    int lo = 0, hi = lm.n_chrom;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (lm.coff[mid] <= rem) lo = mid; else hi = mid; }
+    uint64_t base = cls * lm.G + lm.coff[lo];
+    int64_t cs = (int64_t)(x - base), ce = (int64_t)((uint64_t)r.rend[k] - base);
+    int32_t cnt = r.cnt[k];
+    ocls[k] = (uint32_t)cls; ochrom[k] = lo; oacc[k] = r.acc[k];
+    keep[k] = cnt > 0 ? 1 : 0;                                     // GMAP4.scala:33-34,48
+    if (cnt > 0) {
+      uint64_t smin = r.smin[k], emax = r.emax[k], smax = r.smax[k], emin = r.emin[k];
+      int64_t os = flat ? (int64_t)(smin - base) : cs, oe = flat ? (int64_t)(emax - base) : ce;   // :83-84
+      fstart[k] = os; fstop[k] = oe;
+      long long den = (long long)(emax - smin);
+      double num2 = cnt == 1 ? (double)(long long)(emin - smax) : (smax < emin ? (double)(long long)(emin - smax) : 0.0);   // :74
+      j1[k] = den != 0 ? fabs(((double)oe - (double)os) / (double)den) : 0.0;                      // :91
+      j2[k] = den != 0 ? fabs(num2 / (double)den) : 0.0;                                           // :93
+    } else { fstart[k] = cs; fstop[k] = ce; j1[k] = 0.0; j2[k] = 0.0; }
+  }
+}
+
+}  // namespace tiled

@@ -18,6 +18,8 @@
 //    max stop) with one warp, reducing count / startMin / endMax / startMax / endMin / aggregates over the overlapping
 //    inputs; regions without contributors are dropped (:33-34,48).
 #include "index.cuh"
+#include "cover_tiled.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -65,6 +67,7 @@ __global__ void k_cover_prepass(const int32_t* __restrict__ chrom, const void* _
     __syncthreads();
   }
   int has_star = 0, zero = 0, bad = 0;
+  long long maxlen = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int c = chrom[i];
     int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
@@ -72,17 +75,27 @@ __global__ void k_cover_prepass(const int32_t* __restrict__ chrom, const void* _
     int sm = sample ? sample[i] : 0;
     if (st == 0) has_star = 1;
     if (s == e) zero = 1;
+    if (e - s > maxlen) maxlen = e - s;
     if (c < 0 || c >= n_chrom || s < 0 || s > e || st < 0 || st > 2 || sm < 0 || sm >= n_samples) { bad = 1; continue; }
     if (use_sh) atomicMax(&sspan[c], (unsigned long long)e); else atomicMax(&span[c], (unsigned long long)e);
   }
   if (__any_sync(0xffffffffu, has_star) && (threadIdx.x & 31) == 0) flags[0] = 1;
   if (__any_sync(0xffffffffu, zero) && (threadIdx.x & 31) == 0) flags[1] = 1;
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) flags[2] = 1;
+  {
+    int ml = maxlen > 0x7fffffffLL ? 0x7fffffff : (int)maxlen;
+    ml = __reduce_max_sync(0xffffffffu, ml);
+    if ((threadIdx.x & 31) == 0 && ml > 0) atomicMax(&flags[3], ml);
+  }
   if (use_sh) {
     __syncthreads();
     for (int c = threadIdx.x; c < n_chrom; c += blockDim.x)
       if (sspan[c]) atomicMax(&span[c], sspan[c]);
   }
+}
+
+__global__ void k_iota_u32(uint32_t* __restrict__ p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
 }
 
 __global__ void k_count_flags(const int* __restrict__ seen, int n, int* __restrict__ out) {
@@ -863,9 +876,74 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
   if (nr) LAUNCH(ctx, k_chain_merge, qg, 256, 0, qcls.p, qchrom.p, qs.p, qe.p, qval.p, npieces, chead.p, chead_excl.p, p1->cls.p, p1->chrom.p, p1->start.p, p1->stop.p, p1->acc.p);
 }
 
+// host side of the tile-resident path; returns false (nothing consumed) when a capacity limit was hit and the caller must
+// fall back to the sort-and-merge path
+static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total, int logw,
+                            const int32_t* h_mn, const int32_t* h_mx, Phase1Out* p1, DevBuf<int32_t>& keep, DevBuf<int64_t>& fstart, DevBuf<int64_t>& fstop,
+                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out) {
+  const int64_t n = in.n;
+  const int key_bits = bits_for(n_classes_total * lm.G);
+  const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
+  DevBuf<uint32_t> sk_a(ctx, n), sk_b(ctx, n), sl_a(ctx, n), sl_b(ctx, n);
+  LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, sk_a.p, sl_a.p);
+  uint32_t *S_key, *S_len;
+  radix_sort<uint32_t>(ctx, sk_a.p, sk_b.p, sl_a.p, sl_b.p, n, key_bits, &S_key, &S_len, logw);   // partition by tile only
+  DevBuf<uint32_t> offS(ctx, nT + 1);
+  LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, S_key, n, nT, logw, offS.p);
+
+  int64_t cap = std::max<int64_t>((int64_t)1 << 20, n / 16 + 2 * nT);
+  DevBuf<uint32_t> pstart(ctx, cap), pend(ctx, cap), smin(ctx, cap), emax(ctx, cap), smax(ctx, cap), emin(ctx, cap);
+  DevBuf<int32_t> acc(ctx, cap), cnt(ctx, cap);
+  DevBuf<uint8_t> pflags(ctx, cap);
+  DevBuf<unsigned long long> cursor(ctx, 1);
+  DevBuf<int> fail(ctx, 1);
+  cursor.zero(); fail.zero();
+  tiled::Cfg tc;
+  tc.n_groups = cfg.n_groups; tc.n_classes = cfg.n_classes; tc.mn = cfg.mn; tc.mx = cfg.mx; tc.mn0 = h_mn[0]; tc.mx0 = h_mx[0]; tc.G = lm.G;
+  tiled::Pieces pc;
+  pc.pstart = pstart.p; pc.pend = pend.p; pc.acc = acc.p; pc.cnt = cnt.p; pc.smin = smin.p; pc.emax = emax.p; pc.smax = smax.p; pc.emin = emin.p;
+  pc.flags = pflags.p; pc.cursor = cursor.p; pc.cap = cap; pc.fail = fail.p;
+  CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
+  LAUNCH(ctx, tiled::k_cover_tile, (unsigned)std::min<int64_t>(nT, (int64_t)ctx->num_sms * 32), tiled::THREADS, tiled::SMEM_BYTES, S_key, S_len, offS.p, nT, logw, tc, pc);
+  unsigned long long h_np = 0;
+  int h_fail = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h_np, cursor.p, sizeof h_np, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&h_fail, fail.p, sizeof h_fail, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (h_fail) return false;
+  const int64_t np = (int64_t)h_np;
+  sk_a.release(); sk_b.release(); sl_a.release(); sl_b.release();
+
+  // order the pieces by start, fuse the ones that touch at a tile edge
+  DevBuf<uint32_t> ok_a(ctx, np), ok_b(ctx, np), oi_a(ctx, np), oi_b(ctx, np);
+  if (np) {
+    CUDA_TRY(cudaMemcpyAsync(ok_a.p, pstart.p, 4 * (size_t)np, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(ctx, k_iota_u32, grid_for(ctx, np, 256), 256, 0, oi_a.p, np);
+  }
+  uint32_t *okeys = ok_a.p, *order = oi_a.p;
+  radix_sort<uint32_t>(ctx, ok_a.p, ok_b.p, oi_a.p, oi_b.p, np, key_bits, &okeys, &order);
+  DevBuf<int32_t> head(ctx, np);
+  DevBuf<int64_t> head_excl(ctx, np + 1);
+  if (np) LAUNCH(ctx, tiled::k_piece_heads, grid_for(ctx, np, 256), 256, 0, order, pstart.p, pend.p, pflags.p, np, head.p);
+  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, head.p, head_excl.p, np, head_excl.p + np);
+  const int64_t nr = read_back<int64_t>(ctx, head_excl.p + np);
+  DevBuf<uint32_t> rstart(ctx, nr), rend(ctx, nr), rsmin(ctx, nr), remax(ctx, nr), rsmax(ctx, nr), remin(ctx, nr);
+  DevBuf<int32_t> racc(ctx, nr), rcnt(ctx, nr);
+  racc.zero(); rcnt.zero(); remax.zero(); rsmax.zero(); rsmin.fill_byte(0xff); remin.fill_byte(0xff);
+  tiled::Runs rr;
+  rr.rstart = rstart.p; rr.rend = rend.p; rr.acc = racc.p; rr.cnt = rcnt.p; rr.smin = rsmin.p; rr.emax = remax.p; rr.smax = rsmax.p; rr.emin = remin.p;
+  if (np) LAUNCH(ctx, tiled::k_piece_merge, grid_for(ctx, np, 256), 256, 0, order, pc, np, head.p, head_excl.p, rr);
+  p1->n = nr;
+  p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->acc.alloc(ctx, nr);
+  keep.alloc(ctx, nr); fstart.alloc(ctx, nr); fstop.alloc(ctx, nr); j1.alloc(ctx, nr); j2.alloc(ctx, nr);
+  if (nr) LAUNCH(ctx, tiled::k_runs_finalize, grid_for(ctx, nr, 256), 256, 0, rr, nr, lm, flag == GMQL_FLAT ? 1 : 0, p1->cls.p, p1->chrom.p, fstart.p, fstop.p, p1->acc.p, keep.p, j1.p, j2.p);
+  *nc_out = nr;
+  return true;
+}
+
 template <typename K>
 static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_sample_group, int n_groups, int flag, const int32_t* h_mn, const int32_t* h_mx, int64_t B,
-                      const CovAggPlan& plan, const SpanTable& spans, bool unified, bool has_zero, gmql_result* res) {
+                      const CovAggPlan& plan, const SpanTable& spans, bool unified, bool has_zero, int64_t maxlen, gmql_result* res) {
   const int64_t n = in.n;
   CoverCfg cfg;
   cfg.n_groups = n_groups;
@@ -892,6 +970,35 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     if (n) LAUNCH(ctx, k_cover_classes, grid_for(ctx, n, 256), 256, 0, in.strand, in.sample, n, cfg, cls.p);
   }
 
+  Phase1Out p1;
+  DevBuf<int32_t> keep, ocount;
+  DevBuf<int64_t> keep_excl, fstart, fstop;
+  DevBuf<double> j1, j2;
+  CovOut tmp;
+  memset(&tmp, 0, sizeof tmp);
+  std::vector<DevBuf<double>> tv((size_t)plan.n_aggs);
+  std::vector<DevBuf<uint8_t>> tk((size_t)plan.n_aggs);
+  int64_t nc = 0;
+
+  // ---- tile-resident path (cover_tiled.cuh): dense inputs, 32-bit keys, COVER / FLAT without aggregates
+  bool done = false;
+  if (sizeof(K) == 4 && n > 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) && !has_zero && plan.n_aggs == 0 &&
+      n_classes_total * lm.G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
+    // widest tile whose expected number of events leaves headroom in the kernel's tables
+    const double total = (double)(n_classes_total * lm.G);
+    int logw = tiled::MAX_LOGW;
+    while (logw > 8 && 2.0 * (double)n * (double)(1ull << logw) / total > tiled::CAP_EV / 2.5) --logw;
+    const char* force = getenv("GMQL_COVER_PATH");   // "tiled" / "sort": test hook; default = density heuristic
+    const char* flw = getenv("GMQL_COVER_LOGW");
+    if (flw) logw = atoi(flw);
+    bool fits = logw >= 8 && logw <= tiled::MAX_LOGW && maxlen < (int64_t)(1ll << logw) - 2;
+    bool want = fits && (double)n * (double)(1ull << logw) / total >= 256.0;   // enough regions per tile for the tile pass to pay
+    if (force && !strcmp(force, "tiled")) want = fits;
+    if (force && !strcmp(force, "sort")) want = false;
+    if (want) done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, logw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc);
+  }
+
+  if (!done) {
   // interval index over the ORIGINAL coordinates (phase 2 contributors, GMAP4 uses the un-extended inputs)
   IntervalIndex<K> ix;
   const bool payload_len = plan.n_cols == 0 && spans.G < 0xffffffffull;
@@ -905,7 +1012,6 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     build_index<K>(ctx, in, cls.p, n_classes_total, lm, &ix, payload_len);
   }
 
-  Phase1Out p1;
   if (n == 0) {
     p1.n = 0;
   } else if (flag == GMQL_SUMMIT) {
@@ -916,17 +1022,13 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   }
 
   // phase 2
-  const int64_t nc = p1.n;
-  DevBuf<int32_t> keep(ctx, nc), ocount(ctx, nc);
-  DevBuf<int64_t> keep_excl(ctx, nc + 1), fstart(ctx, nc), fstop(ctx, nc);
-  DevBuf<double> j1(ctx, nc), j2(ctx, nc);
+  nc = p1.n;
+  keep.alloc(ctx, nc); ocount.alloc(ctx, nc);
+  fstart.alloc(ctx, nc); fstop.alloc(ctx, nc);
+  j1.alloc(ctx, nc); j2.alloc(ctx, nc);
   CovCols cc;
   memset(&cc, 0, sizeof cc);
   for (int q = 0; q < plan.n_cols; ++q) { cc.v[q] = in.cols[plan.col_id[q]]; cc.ok[q] = in.valid[plan.col_id[q]]; }
-  CovOut tmp;
-  memset(&tmp, 0, sizeof tmp);
-  std::vector<DevBuf<double>> tv((size_t)plan.n_aggs);
-  std::vector<DevBuf<uint8_t>> tk((size_t)plan.n_aggs);
   for (int a = 0; a < plan.n_aggs; ++a) { tv[a].alloc(ctx, nc); tk[a].alloc(ctx, nc); tmp.value[a] = tv[a].p; tmp.valid[a] = tk[a].p; }
   if (nc) {
     int64_t warps_needed = nc;
@@ -934,6 +1036,8 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     LAUNCH(ctx, (k_gmap4<K>), blocks, 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, ix.start, ix.stop.p, ix.pmax.p, ix.row, n,
            plan, cc, flag == GMQL_FLAT ? 1 : 0, keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp);
   }
+  }  // !done
+  keep_excl.alloc(ctx, nc + 1);
   device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, keep.p, keep_excl.p, nc, keep_excl.p + nc);
   int64_t n_out = read_back<int64_t>(ctx, keep_excl.p + nc);
 
@@ -1061,8 +1165,8 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     bool unified = force_unified || ins.has_star != 0 || d.strand == nullptr || d.n == 0;   // assignGroups (:328-341)
     uint64_t total = (uint64_t)n_groups * (unified ? 1ull : 2ull) * spans.G;
     res = new gmql_result();
-    if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, res);
-    else run_cover<uint64_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, res);
+    if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
+    else run_cover<uint64_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     *out = res;
     return GMQL_OK;

@@ -182,13 +182,13 @@ template <typename K> struct OsCfg {
 };
 
 template <typename K>
-__global__ void __launch_bounds__(RS_THREADS) k_os_hist(const K* __restrict__ keys, int64_t n, int passes, uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(RS_THREADS) k_os_hist(const K* __restrict__ keys, int64_t n, int passes, int begin_bit, uint32_t* __restrict__ hist) {
   __shared__ uint32_t h[8][RS_RADIX];
   for (int p = 0; p < passes; ++p) h[p][threadIdx.x] = 0;
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RS_THREADS) {
     K k = keys[i];
-    for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(uint32_t)(k >> (p * RS_BITS)) & (RS_RADIX - 1)], 1u);
+    for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(uint32_t)(k >> (begin_bit + p * RS_BITS)) & (RS_RADIX - 1)], 1u);
   }
   __syncthreads();
   for (int p = 0; p < passes; ++p) {
@@ -329,23 +329,24 @@ __global__ void __launch_bounds__(RS_THREADS) k_os_pass(const K* __restrict__ ki
 }
 
 // Sorts keys (and a 32-bit payload when vals != nullptr) on bits [0, key_bits).  Buffers ping-pong; on return
-// *keys_out / *vals_out point at whichever buffer holds the sorted data.  n must be < 2^30.
+// *keys_out / *vals_out point at whichever buffer holds the sorted data.  n must be < 2^30.  With begin_bit > 0 only
+// bits [begin_bit, key_bits) are ordered (a stable partition by the high bits).
 template <typename K>
-static void radix_sort(gmql_ctx* ctx, K* keys, K* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n, int key_bits, K** keys_out, uint32_t** vals_out) {
+static void radix_sort(gmql_ctx* ctx, K* keys, K* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n, int key_bits, K** keys_out, uint32_t** vals_out, int begin_bit = 0) {
   K* kin = keys; K* kout = keys_alt;
   uint32_t* vin = vals; uint32_t* vout = vals_alt;
-  if (n > 1 && key_bits > 0) {
+  if (n > 1 && key_bits > begin_bit) {
     GMQL_REQUIRE(n < (int64_t)(1 << 30), GMQL_ERR_UNSUPPORTED, "radix_sort: 2^30 or more elements in one sort");
-    int passes = (key_bits + RS_BITS - 1) / RS_BITS;
+    int passes = (key_bits - begin_bit + RS_BITS - 1) / RS_BITS;
     int64_t tiles = ceil_div64(n, OsCfg<K>::TILE);
     DevBuf<uint32_t> hist(ctx, (int64_t)8 * RS_RADIX);
     DevBuf<uint32_t> state(ctx, tiles * RS_RADIX + 32);
     hist.zero();
     int hb = (int)std::min<int64_t>(ceil_div64(n, RS_THREADS * 16), (int64_t)ctx->num_sms * 8);
-    LAUNCH(ctx, (k_os_hist<K>), hb, RS_THREADS, 0, kin, n, passes, hist.p);
+    LAUNCH(ctx, (k_os_hist<K>), hb, RS_THREADS, 0, kin, n, passes, begin_bit, hist.p);
     LAUNCH(ctx, k_os_scan_hist, passes, RS_RADIX, 0, hist.p);
     for (int p = 0; p < passes; ++p) {
-      int shift = p * RS_BITS;
+      int shift = begin_bit + p * RS_BITS;
       state.zero();
       uint32_t* ticket = state.p + tiles * RS_RADIX;
       if (vals) LAUNCH(ctx, (k_os_pass<K, true>), (unsigned)tiles, RS_THREADS, 0, kin, kout, vin, vout, n, shift, hist.p + p * RS_RADIX, state.p, ticket);

@@ -1,0 +1,170 @@
+"""Tile-resident COVER / FLAT path (gmql_b200/csrc/cover_tiled.cuh) against the oracle.
+
+The path is chosen by a density heuristic; the tests force it (GMQL_COVER_PATH=tiled) and shrink the tile width
+(GMQL_COVER_LOGW) so that small inputs cross many tile edges: runs spanning several tiles, regions of the previous tile
+still open at a tile start, events exactly on a tile edge, the one-base extension of GenometricCover.scala:353-354 and
+GMAP4's exactly-once accounting (GMAP4.scala:44-45).  Every test checks from the per-kernel profile that the tile kernel
+ran and the sort-and-merge sweep did not (no silent fall-back)."""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import gmql_oracle as O
+from tests.randgen import rand_regions, canon
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ex():
+    from gmql_b200 import GMQLCudaExecutor
+    e = GMQLCudaExecutor()
+    yield e
+    e.close()
+
+
+class forced:
+    """Force the tiled path at a given tile width and record which kernels ran."""
+
+    def __init__(self, ex, logw):
+        self.ex, self.logw = ex, logw
+
+    def __enter__(self):
+        from gmql_b200 import _lib as L
+        os.environ["GMQL_COVER_PATH"] = "tiled"
+        os.environ["GMQL_COVER_LOGW"] = str(self.logw)
+        self.ex.lib.gmql_ctx_set_profiling(self.ex.ctx, 1)
+        return self
+
+    def __exit__(self, *a):
+        from gmql_b200 import _lib as L
+        os.environ.pop("GMQL_COVER_PATH", None)
+        os.environ.pop("GMQL_COVER_LOGW", None)
+        buf = C.create_string_buffer(1 << 16)
+        self.ex.lib.gmql_ctx_profile_report(self.ex.ctx, buf, len(buf))
+        self.ex.lib.gmql_ctx_set_profiling(self.ex.ctx, 0)
+        self.kernels = buf.value.decode()
+        return False
+
+    def assert_tiled(self):
+        assert "k_cover_tile" in self.kernels, self.kernels
+        assert "k_cover_runs_fused" not in self.kernels, "fell back to the sort-and-merge path"
+
+
+def _params():
+    import gmql_b200 as G
+    return [
+        ((G.N(1), G.N(2)), (O.CoverParam.N(1), O.CoverParam.N(2))),
+        ((G.N(2), G.N(2)), (O.CoverParam.N(2), O.CoverParam.N(2))),
+        ((G.N(1), G.ANY()), (O.CoverParam.N(1), O.CoverParam.ANY())),
+        ((G.N(2), G.ANY()), (O.CoverParam.N(2), O.CoverParam.ANY())),
+        ((G.N(3), G.N(6)), (O.CoverParam.N(3), O.CoverParam.N(6))),
+        ((G.ANY(), G.ALL()), (O.CoverParam.ANY(), O.CoverParam.ALL())),
+        ((G.ALL(div=2), G.ANY()), (O.CoverParam.ALL(div=2), O.CoverParam.ANY())),
+    ]
+
+
+def _clamp(rng, ds, max_len):
+    """regions strictly shorter than max_len (the aligned variants of rand_regions can stretch a region), keeping an
+    aligned stop aligned"""
+    out = []
+    for (sid, chrom, start, stop, strand, vals) in ds:
+        if stop - start >= max_len:
+            ln = rng.randrange(1, max_len)
+            if stop % 64 == 0 and stop - ln >= 0:
+                start = stop - ln
+            else:
+                stop = start + ln
+        out.append((sid, chrom, start, stop, strand, vals))
+    return out
+
+
+def _check(ex, flag, ds, sample_ids, groups, gp, op):
+    from gmql_b200 import RegionDataset
+    d = RegionDataset.from_records(ds, sample_ids=sample_ids)
+    got = ex.GenometricCover(flag, gp[0], gp[1], [], groups, d)
+    want = O.cover_reference(flag, op[0], op[1], [], ds, groups, 2000)
+    assert canon(got, 9) == canon(want, 9), (flag, gp)
+
+
+@pytest.mark.parametrize("flag", ["COVER", "FLAT"])
+@pytest.mark.parametrize("logw", [8, 10, 12, 16])
+@pytest.mark.parametrize("seed", range(3))
+def test_tiled_random(ex, flag, logw, seed):
+    rng = random.Random(900 + seed)
+    ids = [1, 2, 3, 4, 5]
+    strands = "+-*" if seed == 0 else "+-"
+    max_len = min(4500, (1 << logw) - 3)
+    mults = (2000, 5000, 50000) if logw >= 12 else (64, 256, 2000)     # coordinates on tile edges and bin edges
+    ds = _clamp(rng, rand_regions(rng, 400, ids, strands=strands, n_vals=0, max_len=max_len, aligned_p=0.4, bin_mults=mults), max_len)
+    groups = None if seed < 2 else {1: 50, 2: 50, 3: 90, 4: 90, 5: 90}
+    with forced(ex, logw) as f:
+        for gp, op in _params():
+            _check(ex, flag, ds, ids, groups, gp, op)
+    f.assert_tiled()
+
+
+@pytest.mark.parametrize("flag", ["COVER", "FLAT"])
+def test_tiled_tile_edge_events(ex, flag):
+    """starts, stops and extended stops exactly on tile edges (W = 256: multiples of 256; bin edge 2000 -> stop + 1)"""
+    import gmql_b200 as G
+    ds = [(1, "chr1", 3, 256, "*", ()), (2, "chr1", 260, 512, "*", ()), (1, "chr1", 256, 300, "*", ()), (1, "chr1", 255, 257, "*", ()), (2, "chr1", 520, 768, "*", ()),
+          (1, "chr1", 1800, 2000, "*", ()), (2, "chr1", 1999, 2048, "*", ()), (1, "chr1", 2047, 2049, "*", ()), (2, "chr1", 1900, 2000, "*", ()),
+          (1, "chr1", 3840, 4000, "*", ()), (2, "chr1", 3900, 4095, "*", ()), (1, "chr1", 4000, 4096, "*", ()), (2, "chr1", 4096, 4100, "*", ()),
+          (1, "chr2", 0, 250, "*", ()), (2, "chr2", 10, 20, "*", ()), (1, "chr2", 100, 300, "*", ())]
+    with forced(ex, 8) as f:
+        for mn, mx in ((1, None), (2, None), (1, 1), (2, 2), (1, 2)):
+            gp = (G.N(mn), G.ANY() if mx is None else G.N(mx))
+            op = (O.CoverParam.N(mn), O.CoverParam.ANY() if mx is None else O.CoverParam.N(mx))
+            _check(ex, flag, ds, [1, 2], None, gp, op)
+    f.assert_tiled()
+
+
+@pytest.mark.parametrize("flag", ["COVER", "FLAT"])
+def test_tiled_against_c_oracle_medium(ex, flag):
+    """60 narrowPeak samples x 20 000 regions (C2 shape, thinned) at the production tile width and at a narrow one."""
+    from gmql_b200 import synth, N, ANY, _lib as L
+    from oracle import c_oracle as CO
+    sizes = synth.HG38_SIZES[[18, 19, 20, 21]] // 2
+    ds = synth.peak_samples(60, 20000, 2, with_values=(), sizes=sizes)
+    code = {"COVER": 0, "FLAT": 1}[flag]
+    for logw in (16, 13):
+        for (mn, mx, gmin, gmax) in ((2, 2 ** 31 - 1, N(2), ANY()), (3, 7, N(3), N(7))):
+            with forced(ex, logw) as f:
+                res, gids = ex.cover_raw(flag, gmin, gmax, [], None, ds)
+            f.assert_tiled()
+            g = {k: res.column(c, dt) for k, c, dt in (("chrom", L.COL_COV_CHROM, np.int32), ("start", L.COL_COV_START, np.int64),
+                                                       ("stop", L.COL_COV_STOP, np.int64), ("acc", L.COL_COV_ACC, np.int32),
+                                                       ("j1", L.COL_COV_J1, np.float64), ("j2", L.COL_COV_J2, np.float64))}
+            res.free()
+            w = CO.cover_rows(ds, code, [mn], [mx], None, 2000, val=None, valid=None)
+            og = np.lexsort((g["j2"], g["j1"], g["acc"], g["stop"], g["start"], g["chrom"]))
+            ow = np.lexsort((w["j2"], w["j1"], w["acc"], w["stop"], w["start"], w["chrom"]))
+            assert len(og) == len(ow) and len(og) > 50
+            for k in ("chrom", "start", "stop", "acc", "j1", "j2"):
+                assert np.array_equal(g[k][og], w[k][ow]), (flag, logw, mn, k)
+
+
+def test_tiled_equals_sort_path_at_scale(ex):
+    """4e6 regions: the two device paths agree row for row (COVER(2,ANY) and FLAT(1,3))."""
+    from gmql_b200 import synth, N, ANY, _lib as L
+    ds = synth.peak_samples(80, 50000, 5, with_values=())
+    for flag, gmin, gmax in (("COVER", N(2), ANY()), ("FLAT", N(1), N(3))):
+        out = {}
+        for path in ("tiled", "sort"):
+            os.environ["GMQL_COVER_PATH"] = path
+            try:
+                res, _ = ex.cover_raw(flag, gmin, gmax, [], None, ds)
+            finally:
+                os.environ.pop("GMQL_COVER_PATH", None)
+            cols = [res.column(c, dt) for c, dt in ((L.COL_COV_CHROM, np.int32), (L.COL_COV_START, np.int64), (L.COL_COV_STOP, np.int64),
+                                                    (L.COL_COV_ACC, np.int32), (L.COL_COV_J1, np.float64), (L.COL_COV_J2, np.float64))]
+            res.free()
+            o = np.lexsort(tuple(reversed(cols)))
+            out[path] = [c[o] for c in cols]
+        assert len(out["tiled"][0]) > 1000
+        for a, b in zip(out["tiled"], out["sort"]):
+            assert np.array_equal(a, b), flag
