@@ -132,16 +132,20 @@ class Pipeline:
             self.lib.gmql_result_free(self.ex.ctx, h)
 
 
-def host_struct(L, cols, n, n_chrom, n_samples, sample_ids):
+def host_struct(L, cols, n, n_chrom, n_samples, sample_ids, sample_offsets):
+    """gmql_regions over pinned host columns, in the ABI's compact encodings: 8-bit chromosome index, int32 start/stop,
+    no strand column (narrowPeak '.' -> every region '*') and sample_offsets (one run of rows per sample file)."""
     r = L.Regions()
     r.n = n
     r.location = 0
     r.coord_bits = 32
     r.chrom = cols["chrom"].data_ptr()
+    r.chrom_bits = 8
     r.start = cols["start"].data_ptr()
     r.stop = cols["stop"].data_ptr()
-    r.strand = None                      # narrowPeak '.' -> every region '*'
-    r.sample = cols["sample"].data_ptr()
+    r.strand = None
+    r.sample = None
+    r.sample_offsets = sample_offsets.ctypes.data
     r.n_chrom = n_chrom
     r.n_samples = n_samples
     r.sample_ids = sample_ids.ctypes.data
@@ -165,18 +169,19 @@ def run_ours(args):
     parts = synth.chrom_partition(world)[rank] if world > 1 else None
     ds = make_c5(n_samples, n_regions, parts)
     n_in = ds.n
+    assert len(ds.chrom_names) <= 256 and np.all(np.diff(ds.sample) >= 0)
     cols = {
-        "chrom": torch.from_numpy(ds.chrom).pin_memory(),
+        "chrom": torch.from_numpy(ds.chrom.astype(np.uint8)).pin_memory(),
         "start": torch.from_numpy(ds.start.astype(np.int32)).pin_memory(),
         "stop": torch.from_numpy(ds.stop.astype(np.int32)).pin_memory(),
-        "sample": torch.from_numpy(ds.sample).pin_memory(),
     }
-    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in cols.values())
+    sample_offsets = np.searchsorted(ds.sample, np.arange(n_samples + 1), side="left").astype(np.int64)
+    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in cols.values()) + int(sample_offsets.nbytes)
     stream = torch.cuda.current_stream()
     ex = GMQLCudaExecutor(device=local, stream=stream.cuda_stream)
     lib, ctx = ex.lib, ex.ctx
     pipe = Pipeline(ex, ds, n_samples)
-    host = host_struct(L, cols, n_in, len(ds.chrom_names), n_samples, ds.sample_ids)
+    host = host_struct(L, cols, n_in, len(ds.chrom_names), n_samples, ds.sample_ids, sample_offsets)
 
     def barrier():
         torch.cuda.synchronize()
@@ -282,7 +287,7 @@ def run_ours(args):
             "config": {"workload": "C5: C = COVER(2,ANY) E; M = MAP() C E  (BASELINE.json configs[4])", "samples": n_samples,
                        "regions_per_sample": n_regions, "input_regions": int(tot_in), "cover_regions": int(tot_cover),
                        "map_rows": int(tot_rows), "sharding": "by chromosome (LPT packing), no collective on the data path" if world > 1 else "single GPU",
-                       "l2": "inputs (%.2f GB per rank) larger than the 126 MB L2" % (h2d_bytes / 1e9), "map_count_checksum": int(tot_check)},
+                       "l2": "device-resident inputs (%.2f GB per rank) larger than the 126 MB L2" % (16.0 * n_in / 1e9), "map_count_checksum": int(tot_check)},
             "e2e": {"value": tot_in / (ms_e2e_max * 1e-3), "unit": "input regions/s", "ms_per_step": ms_e2e_max,
                     "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h), "steps": e2e_steps},
             "gpu_launches": int(tot_launch),

@@ -95,6 +95,19 @@ static const void* upload_array(gmql_ctx* ctx, const void* src, size_t bytes, in
   return p;
 }
 
+template <typename T>
+static __global__ void k_widen_chrom(const T* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
+}
+
+// sample_offsets (one run of rows per sample) -> per-row sample index; one block per sample, grid-stride
+static __global__ void k_expand_sample_offsets(const int64_t* __restrict__ off, int n_samples, int32_t* __restrict__ sample) {
+  for (int s = blockIdx.x; s < n_samples; s += gridDim.x) {
+    const int64_t a = off[s], b = off[s + 1];
+    for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) sample[i] = s;
+  }
+}
+
 void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector<int>& need_cols, DevRegions* out) {
   GMQL_REQUIRE(r != nullptr, GMQL_ERR_INVALID, "null gmql_regions");
   GMQL_REQUIRE(r->n >= 0 && r->n < (int64_t)0x7fffffff, GMQL_ERR_UNSUPPORTED, "datasets of >= 2^31 regions are not supported in this version");
@@ -108,11 +121,40 @@ void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector
   out->n_cols = r->n_cols;
   size_t cb = (size_t)(r->coord_bits / 8);
   size_t n = (size_t)r->n;
-  out->chrom = (const int32_t*)upload_array(ctx, r->chrom, n * 4, r->location, out);
+  GMQL_REQUIRE(r->chrom_bits == 0 || r->chrom_bits == 8 || r->chrom_bits == 16 || r->chrom_bits == 32, GMQL_ERR_INVALID, "chrom_bits must be 0, 8, 16 or 32");
+  if (r->chrom_bits == 8 || r->chrom_bits == 16) {
+    GMQL_REQUIRE(r->n_chrom <= (r->chrom_bits == 8 ? 256 : 65536), GMQL_ERR_INVALID, "n_chrom does not fit chrom_bits");
+    const size_t cw = (size_t)(r->chrom_bits / 8);
+    const void* raw = upload_array(ctx, r->chrom, n * cw, r->location, out);
+    DevBuf<uint8_t> wide(ctx, (int64_t)(n * 4 ? n * 4 : 1));
+    if (n) {
+      int g = (int)std::min<int64_t>(ceil_div64((int64_t)n, 256 * 4), (int64_t)ctx->num_sms * 16);
+      if (r->chrom_bits == 8) LAUNCH(ctx, (k_widen_chrom<uint8_t>), g, 256, 0, (const uint8_t*)raw, (int64_t)n, (int32_t*)wide.p);
+      else LAUNCH(ctx, (k_widen_chrom<uint16_t>), g, 256, 0, (const uint16_t*)raw, (int64_t)n, (int32_t*)wide.p);
+    }
+    out->chrom = (const int32_t*)wide.p;
+    if (r->location != GMQL_LOC_DEVICE) out->owned.pop_back();   // the narrow copy is released in stream order
+    out->owned.push_back(std::move(wide));
+  } else {
+    out->chrom = (const int32_t*)upload_array(ctx, r->chrom, n * 4, r->location, out);
+  }
   out->start = upload_array(ctx, r->start, n * cb, r->location, out);
   out->stop = upload_array(ctx, r->stop, n * cb, r->location, out);
   out->strand = (const int8_t*)upload_array(ctx, r->strand, n, r->location, out);
-  out->sample = (const int32_t*)upload_array(ctx, r->sample, n * 4, r->location, out);
+  if (!r->sample && r->sample_offsets) {
+    const int64_t* off = r->sample_offsets;   // host array by contract
+    GMQL_REQUIRE(off[0] == 0 && off[r->n_samples] == r->n, GMQL_ERR_INVALID, "sample_offsets must start at 0 and end at n");
+    for (int s = 0; s < r->n_samples; ++s) GMQL_REQUIRE(off[s] <= off[s + 1], GMQL_ERR_INVALID, "sample_offsets must be non-decreasing");
+    DevBuf<uint8_t> doff(ctx, (int64_t)(8 * ((size_t)r->n_samples + 1)));
+    CUDA_TRY(cudaMemcpyAsync(doff.p, off, 8 * ((size_t)r->n_samples + 1), cudaMemcpyHostToDevice, ctx->stream));
+    out->h2d_bytes += 8 * ((int64_t)r->n_samples + 1);
+    DevBuf<uint8_t> smp(ctx, (int64_t)(n * 4 ? n * 4 : 1));
+    if (n) LAUNCH(ctx, k_expand_sample_offsets, (int)std::min<int64_t>(r->n_samples, (int64_t)ctx->num_sms * 16), 256, 0, (const int64_t*)doff.p, r->n_samples, (int32_t*)smp.p);
+    out->sample = (const int32_t*)smp.p;
+    out->owned.push_back(std::move(smp));
+  } else {
+    out->sample = (const int32_t*)upload_array(ctx, r->sample, n * 4, r->location, out);
+  }
   out->dup_of = (const int32_t*)upload_array(ctx, r->dup_of, n * 4, r->location, out);
   out->cols.assign((size_t)std::max(0, r->n_cols), nullptr);
   out->valid.assign((size_t)std::max(0, r->n_cols), nullptr);

@@ -64,8 +64,9 @@ class _Result:
 
 
 class GMQLCudaExecutor:
-    def __init__(self, binSize=BinSize(), maxBinDistance=100000, device=0, stream=None):
+    def __init__(self, binSize=BinSize(), maxBinDistance=100000, device=0, stream=None, narrow=False):
         self.binSize = binSize
+        self.narrow = narrow     # compact ABI encodings (8/16-bit chrom, sample_offsets) where they apply
         self.maxBinDistance = maxBinDistance
         self.lib = L.load_library()
         ctx = C.c_void_p()
@@ -127,8 +128,8 @@ class GMQLCudaExecutor:
         names = sorted(set(reference.chrom_names) | set(experiments.chrom_names))
         ref = reference.with_chrom_names(names)
         exp = experiments.with_chrom_names(names)
-        c_ref, k1 = ref.as_c(dup_of=ref.dup_of())
-        c_exp, k2 = exp.as_c()
+        c_ref, k1 = ref.as_c(dup_of=ref.dup_of(), narrow=self.narrow)
+        c_exp, k2 = exp.as_c(narrow=self.narrow)
         c_pairs, used = self._c_pairs(pairs, ref, exp)
         c_aggs = self._c_aggs(aggregator, exp)
         out = C.c_void_p()
@@ -169,7 +170,7 @@ class GMQLCudaExecutor:
 
     # ---- COVER ------------------------------------------------------------------------------------------------------------
     def cover_raw(self, coverFlag, min, max, aggregators, groups, ds, force_unified=False):
-        c_ds, keep = ds.as_c()
+        c_ds, keep = ds.as_c(narrow=self.narrow)
         n_s = int(ds.sample_ids.shape[0])
         if groups is not None:
             gids = sorted(set(groups.values()))
@@ -234,8 +235,8 @@ class GMQLCudaExecutor:
         names = sorted(set(left.chrom_names) | set(right.chrom_names))
         l = left.with_chrom_names(names)
         r = right.with_chrom_names(names)
-        c_l, k1 = l.as_c(dup_of=l.dup_of() if dedup else None)
-        c_r, k2 = r.as_c(dup_of=r.dup_of() if dedup else None)
+        c_l, k1 = l.as_c(dup_of=l.dup_of() if dedup else None, narrow=self.narrow)
+        c_r, k2 = r.as_c(dup_of=r.dup_of() if dedup else None, narrow=self.narrow)
         c_pairs, used = self._c_pairs(pairs, l, r)
         c_atoms = (L.Atom * max(1, len(atoms)))()
         for i, a in enumerate(atoms):

@@ -155,8 +155,10 @@ class RegionDataset:
                 k += 1
         return m
 
-    def as_c(self, dup_of=None, coord32=None):
-        """Builds the gmql_regions struct over this dataset's numpy buffers.  Returns (struct, keepalive)."""
+    def as_c(self, dup_of=None, coord32=None, narrow=False):
+        """Builds the gmql_regions struct over this dataset's numpy buffers.  Returns (struct, keepalive).
+        narrow=True uses the ABI's compact encodings where they apply: 8/16-bit chromosome indices and, when the rows are
+        ordered by sample, sample_offsets instead of a per-row sample column."""
         keep = []
         n = self.n
         if coord32 is None:
@@ -180,6 +182,17 @@ class RegionDataset:
         r.n_chrom = max(1, len(self.chrom_names))
         r.n_samples = max(1, int(self.sample_ids.shape[0]))
         r.sample_ids = self.sample_ids.ctypes.data
+        if narrow and n:
+            if r.n_chrom <= 65536:
+                cn = self.chrom.astype(np.uint8 if r.n_chrom <= 256 else np.uint16)
+                keep.append(cn)
+                r.chrom = cn.ctypes.data
+                r.chrom_bits = 8 if r.n_chrom <= 256 else 16
+            if np.all(np.diff(self.sample) >= 0):
+                off = np.searchsorted(self.sample, np.arange(r.n_samples + 1), side="left").astype(np.int64)
+                keep.append(off)
+                r.sample = None
+                r.sample_offsets = off.ctypes.data
         nums = [c for c in self.columns if c[0] == "num"]
         r.n_cols = len(nums)
         if nums:

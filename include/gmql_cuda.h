@@ -80,6 +80,11 @@ typedef struct {
                                    strand, ALL values incl. host-side strings) equals row i (== i if unique).
                                    Lets the device reproduce the MapKey collapse (GenometricMap71.scala:93,123,186-203;
                                    GenometricJoin.scala:134-136) whose value equality only the host can decide. */
+  /* optional narrow encodings (fewer bytes over PCIe); zero / NULL = not used */
+  int32_t chrom_bits;           /* 0 or 32: chrom is int32_t[]; 8: uint8_t[]; 16: uint16_t[] (n_chrom must fit) */
+  const int64_t* sample_offsets;/* HOST array [n_samples+1], used when sample == NULL: rows [off[s], off[s+1]) belong to
+                                   sample s (regions arrive one sample file after the other, Loaders.scala:203-208);
+                                   off[0] = 0, off[n_samples] = n, non-decreasing */
 } gmql_regions;
 
 /* aggregates: DefaultRegionsToRegionFactory (GMQL-Server/.../DefaultRegionsToRegionFactory.scala:13-31),
