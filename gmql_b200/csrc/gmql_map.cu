@@ -89,15 +89,29 @@ __global__ void k_pair_base(const int32_t* __restrict__ pl, const int32_t* __res
   }
 }
 
-// per sorted index entry: sample of the ref row and the rank of its canonical (dup_of) row
-__global__ void k_index_payload(const uint32_t* __restrict__ rows, int64_t n, const int32_t* __restrict__ sample, const int8_t* __restrict__ strand, const int32_t* __restrict__ dup_of,
-                                const uint32_t* __restrict__ rank_of_row, int32_t* __restrict__ s_sample, uint32_t* __restrict__ s_rank, int8_t* __restrict__ s_strand) {
+// One packed record per sorted index entry: everything the streaming kernel needs about a candidate in ONE 16-byte
+// (32-bit keys) or 32-byte (64-bit keys) load.  pmax_prev = running max of the stops of the entries BEFORE this one, so
+// the backward walk knows whether to continue without touching the next record.
+template <typename K>
+struct alignas(16) RefEntry {
+  K stop;
+  K pmax_prev;
+  uint32_t rank;   // rank of the canonical (dup_of) row inside its ref sample = output row offset
+  uint32_t meta;   // ref sample << 2 | strand
+};
+
+template <typename K>
+__global__ void k_index_entries(const uint32_t* __restrict__ rows, int64_t n, const K* __restrict__ stop, const K* __restrict__ pmax, const int32_t* __restrict__ sample,
+                                const int8_t* __restrict__ strand, const int32_t* __restrict__ dup_of, const uint32_t* __restrict__ rank_of_row, RefEntry<K>* __restrict__ out) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     uint32_t row = rows[k];
-    s_sample[k] = sample ? sample[row] : 0;
-    s_strand[k] = strand ? strand[row] : (int8_t)0;
     uint32_t canon = dup_of ? (uint32_t)dup_of[row] : row;
-    s_rank[k] = rank_of_row[canon];
+    RefEntry<K> e;
+    e.stop = stop[k];
+    e.pmax_prev = k > 0 ? pmax[k - 1] : (K)0;
+    e.rank = rank_of_row[canon];
+    e.meta = ((uint32_t)(sample ? sample[row] : 0) << 2) | (uint32_t)(strand ? strand[row] : (int8_t)0);
+    out[k] = e;
   }
 }
 
@@ -113,49 +127,114 @@ __global__ void k_bucket_table(const K* __restrict__ r_start, int64_t n_ref, int
 }
 
 // ---- the streaming kernel ------------------------------------------------------------------------
+// Persistent blocks (one per SM).  The bucket table (and the per-chromosome offsets) are staged in shared memory, so a
+// query costs one shared-memory lookup, usually no search at all (most buckets hold no reference start), one packed
+// RefEntry load per candidate and the accumulating REDs.  Every thread handles four consecutive experiment regions per
+// iteration (128-bit column loads; four independent candidate loads in flight).
+constexpr int MS_THREADS = 1024;
+constexpr int MS_PER = 4;
+constexpr int MS_MAX_TBL = 46 * 1024;      // bucket-table entries kept in shared memory (184 KB)
+constexpr int MS_MAX_CHROM = 1024;         // chromosomes whose offset/span are kept in shared memory
+
 template <typename K>
-__global__ void __launch_bounds__(256) k_map_stream(
-    const int32_t* __restrict__ e_chrom, const void* __restrict__ e_start, const void* __restrict__ e_stop, int e_bits,
-    const int8_t* __restrict__ e_strand, const int32_t* __restrict__ e_sample, int64_t n_exp, int n_exp_samples,
-    LinMap lm, const K* __restrict__ r_start, const K* __restrict__ r_stop, const K* __restrict__ r_pmax, int64_t n_ref,
-    const int32_t* __restrict__ r_sample, const uint32_t* __restrict__ r_rank, const int8_t* __restrict__ r_strand,
-    const long long* __restrict__ pair_base, MapAggPlan plan, ExpCols ec, MapAcc acc, int* __restrict__ bad,
-    const uint32_t* __restrict__ tbl, int tbl_shift) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_exp; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = e_chrom[i];
-    if (c < 0 || c >= lm.n_chrom) { *bad = 1; continue; }
-    int64_t s = ld_coord(e_start, e_bits, i);
-    int64_t e = ld_coord(e_stop, e_bits, i);
-    int64_t span = lm.span[c];
-    if (s >= span || e <= 0) continue;  // no reference region can satisfy r.start < e.stop && e.start < r.stop
-    if (s < 0) { *bad = 1; continue; }
-    if (e > span + 1) e = span + 1;
-    int b = e_sample ? e_sample[i] : 0;
-    if (b < 0 || b >= n_exp_samples) { *bad = 1; continue; }
-    int st = e_strand ? (int)e_strand[i] : 0;
-    K ls = (K)(lm.coff[c] + (uint64_t)s);
-    K le = (K)(lm.coff[c] + (uint64_t)e);
-    int64_t hi;                                            // ref entries with start < e.stop
-    {
-      uint64_t b = (uint64_t)le >> tbl_shift;
-      int64_t lo2 = tbl[b], hi2 = tbl[b + 1];
-      while (lo2 < hi2) { int64_t mid = (lo2 + hi2) >> 1; if (r_start[mid] < le) lo2 = mid + 1; else hi2 = mid; }
-      hi = lo2;
+struct MapStreamArgs {
+  const int32_t* e_chrom; const void* e_start; const void* e_stop; int e_bits;
+  const int8_t* e_strand; const int32_t* e_sample; int64_t n_exp; int n_exp_samples;
+  LinMap lm; const K* r_start; const RefEntry<K>* entries; int64_t n_ref;
+  const long long* pair_base; int* bad;
+  const uint32_t* tbl; int tbl_shift; int n_tbl;   // n_tbl = entries of tbl (buckets + 2)
+  int vec_ok;                                        // column pointers are 16-byte aligned
+};
+
+template <typename K>
+__device__ __forceinline__ void map_hit(const MapStreamArgs<K>& a, const MapAggPlan& plan, const ExpCols& ec, const MapAcc& acc, const RefEntry<K>& e, int b, int st, int64_t i) {
+  if (!strand_ok((int)(e.meta & 3u), st)) return;
+  long long base = a.pair_base[(int64_t)(e.meta >> 2) * a.n_exp_samples + b];
+  if (base < 0) return;
+  int64_t row = base + e.rank;
+  atomicAdd(&acc.count[row], 1);
+  for (int q = 0; q < plan.n_cols; ++q) {
+    if (ec.ok[q] && !ec.ok[q][i]) continue;
+    double v = ec.v[q][i];
+    atomicAdd(&acc.nn[q][row], 1);
+    if (plan.need_sum[q]) atomicAdd(&acc.sum[q][row], v);
+    if (plan.need_min[q]) atomicMin(&acc.mn[q][row], dbl_key_min(v));
+    if (plan.need_max[q]) atomicMax(&acc.mx[q][row], dbl_key_max(v));
+  }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(MS_THREADS, 1) k_map_stream(MapStreamArgs<K> a, MapAggPlan plan, ExpCols ec, MapAcc acc) {
+  extern __shared__ uint32_t s_tbl[];                   // [n_tbl] bucket table, then chromosome offsets / spans
+  const bool chrom_sh = a.lm.n_chrom <= MS_MAX_CHROM;
+  uint64_t* s_coff = (uint64_t*)(s_tbl + ((a.n_tbl + 3) & ~3));
+  int64_t* s_span = (int64_t*)(s_coff + (chrom_sh ? a.lm.n_chrom : 0));
+  for (int k = threadIdx.x; k < a.n_tbl; k += MS_THREADS) s_tbl[k] = a.tbl[k];
+  if (chrom_sh) for (int k = threadIdx.x; k < a.lm.n_chrom; k += MS_THREADS) { s_coff[k] = a.lm.coff[k]; s_span[k] = a.lm.span[k]; }
+  __syncthreads();
+  const uint64_t* coff = chrom_sh ? s_coff : a.lm.coff;
+  const int64_t* span = chrom_sh ? s_span : a.lm.span;
+
+  for (int64_t i0 = ((int64_t)blockIdx.x * MS_THREADS + threadIdx.x) * MS_PER; i0 < a.n_exp; i0 += (int64_t)gridDim.x * MS_THREADS * MS_PER) {
+    int c[MS_PER], smp[MS_PER], st[MS_PER];
+    int64_t s[MS_PER], e[MS_PER];
+    const bool full = i0 + MS_PER <= a.n_exp;
+    if (full && a.vec_ok && a.e_bits == 32) {
+      int4 vc = *(const int4*)(a.e_chrom + i0), vs = *(const int4*)((const int32_t*)a.e_start + i0), ve = *(const int4*)((const int32_t*)a.e_stop + i0);
+      c[0] = vc.x; c[1] = vc.y; c[2] = vc.z; c[3] = vc.w;
+      s[0] = vs.x; s[1] = vs.y; s[2] = vs.z; s[3] = vs.w;
+      e[0] = ve.x; e[1] = ve.y; e[2] = ve.z; e[3] = ve.w;
+      if (a.e_sample) { int4 vb = *(const int4*)(a.e_sample + i0); smp[0] = vb.x; smp[1] = vb.y; smp[2] = vb.z; smp[3] = vb.w; }
+      else { smp[0] = smp[1] = smp[2] = smp[3] = 0; }
+      if (a.e_strand) { uint32_t w = *(const uint32_t*)(a.e_strand + i0); st[0] = (int)(int8_t)(w & 0xff); st[1] = (int)(int8_t)((w >> 8) & 0xff); st[2] = (int)(int8_t)((w >> 16) & 0xff); st[3] = (int)(int8_t)(w >> 24); }
+      else { st[0] = st[1] = st[2] = st[3] = 0; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < MS_PER; ++j) {
+        int64_t i = i0 + j;
+        bool ok = i < a.n_exp;
+        c[j] = ok ? a.e_chrom[i] : -2;                  // -2: padding lane, skipped silently
+        s[j] = ok ? ld_coord(a.e_start, a.e_bits, i) : 0;
+        e[j] = ok ? ld_coord(a.e_stop, a.e_bits, i) : 0;
+        smp[j] = ok && a.e_sample ? a.e_sample[i] : 0;
+        st[j] = ok && a.e_strand ? (int)a.e_strand[i] : 0;
+      }
     }
-    for (int64_t k = hi - 1; k >= 0 && r_pmax[k] > ls; --k) {
-      if (r_stop[k] <= ls) continue;
-      if (!strand_ok((int)r_strand[k], st)) continue;
-      long long base = pair_base[(int64_t)r_sample[k] * n_exp_samples + b];
-      if (base < 0) continue;
-      int64_t row = base + r_rank[k];
-      atomicAdd(&acc.count[row], 1);
-      for (int q = 0; q < plan.n_cols; ++q) {
-        if (ec.ok[q] && !ec.ok[q][i]) continue;
-        double v = ec.v[q][i];
-        atomicAdd(&acc.nn[q][row], 1);
-        if (plan.need_sum[q]) atomicAdd(&acc.sum[q][row], v);
-        if (plan.need_min[q]) atomicMin(&acc.mn[q][row], dbl_key_min(v));
-        if (plan.need_max[q]) atomicMax(&acc.mx[q][row], dbl_key_max(v));
+    // ---- candidate range of every region: hi = number of reference entries with start < region.stop
+    K ls[MS_PER];
+    int hi[MS_PER];
+#pragma unroll
+    for (int j = 0; j < MS_PER; ++j) {
+      hi[j] = 0; ls[j] = 0;
+      if (c[j] == -2) continue;
+      if (c[j] < 0 || c[j] >= a.lm.n_chrom) { *a.bad = 1; continue; }
+      int64_t sp = span[c[j]];
+      if (s[j] >= sp || e[j] <= 0) continue;            // no reference region can satisfy r.start < e.stop && e.start < r.stop
+      if (s[j] < 0) { *a.bad = 1; continue; }
+      if (e[j] > sp + 1) e[j] = sp + 1;
+      if (smp[j] < 0 || smp[j] >= a.n_exp_samples) { *a.bad = 1; continue; }
+      uint64_t co = coff[c[j]];
+      ls[j] = (K)(co + (uint64_t)s[j]);
+      K le = (K)(co + (uint64_t)e[j]);
+      uint64_t b = (uint64_t)le >> a.tbl_shift;
+      int lo2 = (int)s_tbl[b], hi2 = (int)s_tbl[b + 1];
+      while (lo2 < hi2) { int mid = (lo2 + hi2) >> 1; if (a.r_start[mid] < le) lo2 = mid + 1; else hi2 = mid; }
+      hi[j] = lo2;
+    }
+    // ---- first candidate of each region: independent loads, all in flight together
+    RefEntry<K> ent[MS_PER];
+#pragma unroll
+    for (int j = 0; j < MS_PER; ++j) if (hi[j] > 0) ent[j] = a.entries[hi[j] - 1];
+#pragma unroll
+    for (int j = 0; j < MS_PER; ++j) {
+      if (hi[j] <= 0) continue;
+      int k = hi[j] - 1;
+      RefEntry<K> en = ent[j];
+      while (true) {
+        if (en.stop > ls[j]) map_hit<K>(a, plan, ec, acc, en, smp[j], st[j], i0 + j);
+        if (k == 0 || en.pmax_prev <= ls[j]) break;
+        --k;
+        en = a.entries[k];
       }
     }
   }
@@ -292,19 +371,18 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   LinMap lm = spans.map();
   IntervalIndex<K> ix;
   build_index<K>(ctx, ref, nullptr, 1, lm, &ix);
-  // bucket table: about 4 buckets per reference region, between 2^10 and 2^22 buckets
+  // bucket table, resident in the streaming kernel's shared memory: as fine as fits (most buckets then hold no start
+  // and a query needs no search at all), at least 2^10 buckets
   int tbl_shift = 0;
   {
-    int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)1 << 22, 4 * n_ref));
+    int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)MS_MAX_TBL - 2, 16 * std::max<int64_t>(n_ref, 1)));
     while (tbl_shift < 62 && (int64_t)(lm.G >> tbl_shift) + 2 > want) ++tbl_shift;
   }
   int64_t n_buckets = (int64_t)(lm.G >> tbl_shift) + 1;
   DevBuf<uint32_t> tbl(ctx, n_buckets + 2);
   LAUNCH(ctx, (k_bucket_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, n_ref, tbl_shift, n_buckets, tbl.p);
-  DevBuf<int32_t> s_sample(ctx, n_ref);
-  DevBuf<uint32_t> s_rank(ctx, n_ref);
-  DevBuf<int8_t> s_strand(ctx, n_ref);
-  if (n_ref) LAUNCH(ctx, k_index_payload, grid_for(ctx, n_ref, 256), 256, 0, ix.row, n_ref, ref.sample, ref.strand, ref.dup_of, rank_of_row.p, s_sample.p, s_rank.p, s_strand.p);
+  DevBuf<RefEntry<K>> entries(ctx, n_ref);
+  if (n_ref) LAUNCH(ctx, (k_index_entries<K>), grid_for(ctx, n_ref, 256), 256, 0, ix.row, n_ref, ix.stop.p, ix.pmax.p, ref.sample, ref.strand, ref.dup_of, rank_of_row.p, entries.p);
 
   // accumulators
   MapAcc acc;
@@ -327,9 +405,18 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   }
 
   if (n_exp && n_ref && n_rows) {
-    int g = grid_for(ctx, n_exp, 256, 2);
-    LAUNCH(ctx, (k_map_stream<K>), g, 256, 0, exp.chrom, exp.start, exp.stop, exp.coord_bits, exp.strand, exp.sample, n_exp, n_rs,
-           lm, ix.start, ix.stop.p, ix.pmax.p, n_ref, s_sample.p, s_rank.p, s_strand.p, pair_base.p, plan, ec, acc, bad.p, tbl.p, tbl_shift);
+    MapStreamArgs<K> ma;
+    ma.e_chrom = exp.chrom; ma.e_start = exp.start; ma.e_stop = exp.stop; ma.e_bits = exp.coord_bits;
+    ma.e_strand = exp.strand; ma.e_sample = exp.sample; ma.n_exp = n_exp; ma.n_exp_samples = n_rs;
+    ma.lm = lm; ma.r_start = ix.start; ma.entries = entries.p; ma.n_ref = n_ref;
+    ma.pair_base = pair_base.p; ma.bad = bad.p;
+    ma.tbl = tbl.p; ma.tbl_shift = tbl_shift; ma.n_tbl = (int)(n_buckets + 2);
+    auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
+    ma.vec_ok = al16(exp.chrom) && al16(exp.start) && al16(exp.stop) && al16(exp.sample) && ((uintptr_t)exp.strand & 3u) == 0;
+    size_t sh = sizeof(uint32_t) * (size_t)((ma.n_tbl + 3) & ~3) + (lm.n_chrom <= MS_MAX_CHROM ? 16 * (size_t)lm.n_chrom : 0);
+    CUDA_TRY(cudaFuncSetAttribute(k_map_stream<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    int g = (int)std::min<int64_t>(ceil_div64(n_exp, (int64_t)MS_THREADS * MS_PER), (int64_t)ctx->num_sms);
+    LAUNCH(ctx, (k_map_stream<K>), g, MS_THREADS, sh, ma, plan, ec, acc);
   }
   if (ref.dup_of && n_pairs && n_rows)
     LAUNCH(ctx, k_mark_dups, (int)std::min<int64_t>(n_pairs, (int64_t)ctx->num_sms * 8), 128, 0, d_pl.p, row_off.p, n_pairs, sample_off.p, rows_by_sample, ref.dup_of, count.p);
