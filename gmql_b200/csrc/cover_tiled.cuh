@@ -35,7 +35,7 @@ constexpr int CAP_EV = 12288;           // distinct event positions per tile
 constexpr int MAXP = 512;               // pieces per tile
 constexpr int HCAP = 512;               // regions of the previous tile still open at the tile start
 constexpr uint32_t EXT = 0x80000000u;   // length payload bit: stop' = stop + 1
-constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 4 * CAP_EV + 2 * CAP_EV + 8 * HCAP + 32 * MAXP;
+constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 4 * CAP_EV + 2 * CAP_EV + 16 * HCAP + 32 * MAXP;
 
 struct Cfg {
   int n_groups, n_classes;
@@ -88,24 +88,75 @@ __device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t* total, in
   for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
   if (lane == 31) scratch[w] = x;
   __syncthreads();
-  int32_t base = 0, tot = 0;
+  int32_t t = lane < NWARPS ? scratch[lane] : 0;           // every warp scans the NWARPS warp totals itself
 #pragma unroll
-  for (int q = 0; q < NWARPS; ++q) { int32_t c = scratch[q]; if (q < w) base += c; tot += c; }
+  for (int o = 1; o < NWARPS; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+  const int32_t tot = __shfl_sync(0xffffffffu, t, NWARPS - 1);
+  const int32_t below = __shfl_sync(0xffffffffu, t, w > 0 ? w - 1 : 0);
   __syncthreads();
   *total = tot;
-  return base + x - v;
+  return (w > 0 ? below : 0) + x - v;
 }
 
+template <bool MULTI>
+__device__ __forceinline__ bool in_rng(const Cfg& c, int32_t mn0, int32_t mx0, int32_t d, uint64_t pos) {
+  if (!MULTI) return d >= mn0 && d <= mx0;
+  int g = (int)((pos / c.G) / (uint64_t)c.n_classes);
+  return d >= c.mn[g] && d <= c.mx[g];
+}
+
+constexpr int RC = 6;   // regions of the tile each thread keeps in registers (the rest are re-read from L1/L2)
+
+// GMAP4 contribution of one region per thread (block-uniform call): find the pieces it overlaps, accumulate with
+// warp-aggregated shared-memory atomics
+__device__ __forceinline__ void gmap4_round(bool valid, uint32_t rs, uint32_t re, bool own, bool cont0, int np, const uint32_t* pst, const uint32_t* pen,
+                                            int32_t* pcnt, uint32_t* psmin, uint32_t* pemax, uint32_t* psmax, uint32_t* pemin) {
+  const int lane = threadIdx.x & 31;
+  int j = np;
+  if (valid) {
+    int lo = 0, hi = np;                 // first piece with end > rs
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (pen[mid] > rs) hi = mid; else lo = mid + 1; }
+    j = lo;
+  }
+  while (true) {
+    bool ov = valid && j < np && pst[j] < re;
+    unsigned bal = __ballot_sync(0xffffffffu, ov);
+    if (!bal) break;
+    int J = __shfl_sync(0xffffffffu, j, __ffs(bal) - 1);
+    bool mine = ov && j == J;
+    bool add = mine && (own || !(J == 0 && cont0));   // halo regions only feed runs that START in this tile
+    unsigned m = __ballot_sync(0xffffffffu, add);
+    if (m) {
+      uint32_t a_smin = __reduce_min_sync(0xffffffffu, add ? rs : 0xffffffffu);
+      uint32_t a_emax = __reduce_max_sync(0xffffffffu, add ? re : 0u);
+      uint32_t a_smax = __reduce_max_sync(0xffffffffu, add ? rs : 0u);
+      uint32_t a_emin = __reduce_min_sync(0xffffffffu, add ? re : 0xffffffffu);
+      if (lane == (__ffs(m) - 1)) {
+        atomicAdd(&pcnt[J], __popc(m));
+        atomicMin(&psmin[J], a_smin); atomicMax(&pemax[J], a_emax);
+        atomicMax(&psmax[J], a_smax); atomicMin(&pemin[J], a_emin);
+      }
+    }
+    if (mine) ++j;
+  }
+}
+
+// Every block owns a CONTIGUOUS range of tiles holding an equal share of the regions.  Inside its range the regions
+// still open at a tile's end are handed to the next tile through shared memory; only the first tile of a range scans
+// its predecessor's regions in global memory.
+template <bool MULTI>
 static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t* __restrict__ S_key, const uint32_t* __restrict__ S_len, const uint32_t* __restrict__ offS,
-                                                                  int64_t nT, int logw, Cfg cfg, Pieces out) {
+                                                                  int64_t nT, int64_t n, int logw, Cfg cfg, Pieces out) {
   extern __shared__ uint32_t sm[];
   uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
   uint16_t* wpre = (uint16_t*)(bitmap + MAXWORDS);         // [MAXWORDS] set bits before each word
   int32_t* delta = (int32_t*)(wpre + MAXWORDS);            // [CAP_EV] net +1/-1 per distinct position (by rank)
   uint16_t* epos = (uint16_t*)(delta + CAP_EV);            // [CAP_EV] tile-local position of each rank
-  uint32_t* hS = (uint32_t*)(epos + CAP_EV);               // [HCAP] halo regions: start, length payload
-  uint32_t* hL = hS + HCAP;
-  uint32_t* pst = hL + HCAP;                               // [MAXP] x 8: the tile's pieces and their GMAP4 accumulators
+  uint32_t* hinS = (uint32_t*)(epos + CAP_EV);             // [HCAP] regions still open at the tile start: start, length payload
+  uint32_t* hinL = hinS + HCAP;
+  uint32_t* houtS = hinL + HCAP;                           // [HCAP] regions still open at the tile end (next tile's hin)
+  uint32_t* houtL = houtS + HCAP;
+  uint32_t* pst = houtL + HCAP;                            // [MAXP] x 8: the tile's pieces and their GMAP4 accumulators
   uint32_t* pen = pst + MAXP;
   int32_t* pacc = (int32_t*)(pen + MAXP);
   int32_t* pcnt = pacc + MAXP;
@@ -114,50 +165,94 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
   uint32_t* psmax = pemax + MAXP;
   uint32_t* pemin = psmax + MAXP;
   __shared__ int32_t scratch[NWARPS];
-  __shared__ int s_nh;
+  __shared__ int s_nh, s_nout;
   __shared__ long long s_base;
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t W = 1u << logw;
   const int nW = (int)(W >> 5) > 0 ? (int)(W >> 5) : 1;
   const int WPT = (nW + THREADS - 1) / THREADS;            // bitmap words per thread (consecutive)
+  const int32_t mn0 = cfg.mn0, mx0 = cfg.mx0;
 
-  for (int64_t tile = blockIdx.x; tile < nT; tile += gridDim.x) {
-    const uint32_t s0 = offS[tile], s1 = offS[tile + 1];
-    const uint32_t h0 = tile > 0 ? offS[tile - 1] : s0;
-    const uint32_t tile_lo = (uint32_t)tile << logw;
-    if (s0 == s1 && h0 == s0) continue;                    // nothing starts here and nothing can reach in: depth 0 throughout
-    // ---- phase 0: clear the bitmap
-    for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;
-    if (tid == 0) s_nh = 0;
-    __syncthreads();
-    // ---- phase 1: mark event positions; collect the previous tile's regions that are still open
-    for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
-      uint32_t i = i0 + tid;
-      bool reach = false;
-      uint32_t rs = 0, lp = 0, ee = 0;
-      if (i < s0) { rs = S_key[i]; lp = S_len[i]; ee = rs + (lp & ~EXT) + (lp >> 31); reach = ee >= tile_lo; }
-      unsigned bal = __ballot_sync(0xffffffffu, reach);
-      if (bal) {
-        int basew = 0;
-        if (lane == 0) basew = atomicAdd(&s_nh, __popc(bal));
-        basew = __shfl_sync(0xffffffffu, basew, 0);
-        if (reach) {
-          int slot = basew + __popc(bal & ((1u << lane) - 1u));
-          if (slot < HCAP) { hS[slot] = rs; hL[slot] = lp; }
-          uint32_t q = ee - tile_lo;
-          atomicOr(&bitmap[q >> 5], 1u << (q & 31));
-        }
+  // this block's tile range: first tile whose region offset reaches the block's share
+  int64_t t_begin, t_end;
+  {
+    int64_t bounds[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int64_t c = (int64_t)blockIdx.x + q;
+      if (c <= 0) bounds[q] = 0;
+      else if (c >= (int64_t)gridDim.x) bounds[q] = nT;
+      else {
+        const uint32_t target = (uint32_t)((n * c) / (int64_t)gridDim.x);
+        int64_t lo = 0, hi = nT;
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (offS[mid] < target) lo = mid + 1; else hi = mid; }
+        bounds[q] = lo;
       }
     }
-    for (uint32_t i = s0 + tid; i < s1; i += THREADS) {
+    t_begin = bounds[0]; t_end = bounds[1];
+  }
+  int nh_carry = -1;                                       // -1: the open regions must be found by scanning the previous tile
+
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    const uint32_t s0 = offS[tile], s1 = offS[tile + 1];
+    const uint32_t nS = s1 - s0;
+    const bool scan_prev = nh_carry < 0;
+    const uint32_t h0 = (scan_prev && tile > 0) ? offS[tile - 1] : s0;
+    const uint32_t tile_lo = (uint32_t)tile << logw;
+    if (nS == 0 && (scan_prev ? h0 == s0 : nh_carry == 0)) { nh_carry = 0; continue; }   // depth 0 throughout, nothing left open
+    // ---- phase 0: clear the bitmap
+    for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;
+    if (tid == 0) { s_nh = scan_prev ? 0 : nh_carry; s_nout = 0; }
+    __syncthreads();
+    // ---- phase 1: mark event positions; regions of the previous tile that are still open; own regions into registers
+    if (scan_prev) {
+      for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
+        uint32_t i = i0 + tid;
+        if (i < s0) {
+          uint32_t rs = S_key[i], lp = S_len[i];
+          uint32_t ee = rs + (lp & ~EXT) + (lp >> 31);
+          if (ee >= tile_lo) {
+            int slot = atomicAdd(&s_nh, 1);
+            if (slot < HCAP) { hinS[slot] = rs; hinL[slot] = lp; }
+            uint32_t q = ee - tile_lo;
+            atomicOr(&bitmap[q >> 5], 1u << (q & 31));
+          }
+        }
+      }
+    } else {
+      for (int k = tid; k < nh_carry; k += THREADS) {
+        uint32_t lp = hinL[k];
+        uint32_t q = hinS[k] + (lp & ~EXT) + (lp >> 31) - tile_lo;
+        atomicOr(&bitmap[q >> 5], 1u << (q & 31));
+      }
+    }
+    uint32_t rsr[RC], lpr[RC];
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      uint32_t i = s0 + tid + r * THREADS;
+      rsr[r] = 0; lpr[r] = 0;
+      if (i < s1) { rsr[r] = S_key[i]; lpr[r] = S_len[i]; }
+    }
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      if (s0 + tid + r * THREADS < s1) {
+        uint32_t q = rsr[r] - tile_lo;
+        atomicOr(&bitmap[q >> 5], 1u << (q & 31));
+        uint32_t qe = q + (lpr[r] & ~EXT) + (lpr[r] >> 31);
+        if (qe < W) atomicOr(&bitmap[qe >> 5], 1u << (qe & 31));
+        else { int slot = atomicAdd(&s_nout, 1); if (slot < HCAP) { houtS[slot] = rsr[r]; houtL[slot] = lpr[r]; } }
+      }
+    }
+    for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
       uint32_t rs = S_key[i], lp = S_len[i];
       uint32_t q = rs - tile_lo;
       atomicOr(&bitmap[q >> 5], 1u << (q & 31));
       uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
       if (qe < W) atomicOr(&bitmap[qe >> 5], 1u << (qe & 31));
+      else { int slot = atomicAdd(&s_nout, 1); if (slot < HCAP) { houtS[slot] = rs; houtL[slot] = lp; } }
     }
     __syncthreads();
-    const int nh = s_nh;
+    const int nh = s_nh, nout = s_nout;
     const int32_t depth_in = nh;                           // regions still open when the tile begins
     // ---- phase 2: rank = popcount prefix over the bitmap
     int32_t total;
@@ -168,8 +263,9 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
       int32_t pre = block_excl_scan(c, &total, scratch);
       for (int q = 0; q < WPT; ++q) if (w0 + q < nW) { wpre[w0 + q] = (uint16_t)pre; pre += __popc(bitmap[w0 + q]); }
     }
-    if (nh > HCAP || total > CAP_EV) {                     // uniform across the block
-      if (tid == 0) *out.fail = nh > HCAP ? 4 : 2;
+    if (nh > HCAP || nout > HCAP || total > CAP_EV) {      // uniform across the block
+      if (tid == 0) *out.fail = total > CAP_EV ? 2 : 4;
+      nh_carry = -1;
       __syncthreads();
       continue;
     }
@@ -177,18 +273,33 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
     __syncthreads();
     // ---- phase 3: sum +1 / -1 per distinct position
     for (int k = tid; k < nh; k += THREADS) {
-      uint32_t lp = hL[k];
-      uint32_t q = hS[k] + (lp & ~EXT) + (lp >> 31) - tile_lo;
+      uint32_t lp = hinL[k];
+      uint32_t q = hinS[k] + (lp & ~EXT) + (lp >> 31) - tile_lo;
       int r = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
       atomicAdd(&delta[r], -1);
       epos[r] = (uint16_t)q;
     }
-    for (uint32_t i = s0 + tid; i < s1; i += THREADS) {
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      if (s0 + tid + r * THREADS < s1) {
+        uint32_t q = rsr[r] - tile_lo;
+        int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
+        atomicAdd(&delta[rk], 1);
+        epos[rk] = (uint16_t)q;
+        uint32_t qe = q + (lpr[r] & ~EXT) + (lpr[r] >> 31);
+        if (qe < W) {
+          int r2 = wpre[qe >> 5] + __popc(bitmap[qe >> 5] & ((1u << (qe & 31)) - 1u));
+          atomicAdd(&delta[r2], -1);
+          epos[r2] = (uint16_t)qe;
+        }
+      }
+    }
+    for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
       uint32_t rs = S_key[i], lp = S_len[i];
       uint32_t q = rs - tile_lo;
-      int r = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
-      atomicAdd(&delta[r], 1);
-      epos[r] = (uint16_t)q;
+      int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
+      atomicAdd(&delta[rk], 1);
+      epos[rk] = (uint16_t)q;
       uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
       if (qe < W) {
         int r2 = wpre[qe >> 5] + __popc(bitmap[qe >> 5] & ((1u << (qe & 31)) - 1u));
@@ -198,7 +309,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
     }
     __syncthreads();
     // ---- phase 4: depth profile over the distinct positions, pieces
-    const bool cont0 = in_range(cfg, depth_in, tile_lo);
+    const bool cont0 = in_rng<MULTI>(cfg, mn0, mx0, depth_in, tile_lo);
     const int IT = ((total + THREADS - 1) / THREADS) | 1;  // ranks per thread; odd stride: conflict-free shared-memory access
     const int k0 = tid * IT < total ? tid * IT : total;
     const int k1 = k0 + IT < total ? k0 + IT : total;
@@ -208,27 +319,27 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
     const int32_t d_start = depth_in + block_excl_scan(csum, &tile_net, scratch);
     // the state just before my first rank: in range iff the depth there is (the previous position belongs to the same
     // class unless the depth is 0, which is never in range)
-    const bool in0 = k0 < total ? in_range(cfg, d_start, (uint64_t)tile_lo + epos[k0]) : false;
+    const bool in0 = k0 < total ? in_rng<MULTI>(cfg, mn0, mx0, d_start, (uint64_t)tile_lo + epos[k0]) : false;
     int nopen = 0;
     {
       int32_t d = d_start;
       bool prev_in = k0 == 0 ? cont0 : in0;
       for (int k = k0; k < k1; ++k) {
         d += delta[k];
-        bool cur = in_range(cfg, d, (uint64_t)tile_lo + epos[k]);
+        bool cur = in_rng<MULTI>(cfg, mn0, mx0, d, (uint64_t)tile_lo + epos[k]);
         nopen += (cur && !prev_in) ? 1 : 0;
         prev_in = cur;
       }
     }
     int32_t open_total;
     const int32_t open_pre = block_excl_scan(nopen, &open_total, scratch);
-    const int np_all = (cont0 ? 1 : 0) + open_total;
-    if (np_all > MAXP) {
+    const int np = (cont0 ? 1 : 0) + open_total;
+    if (np > MAXP) {
       if (tid == 0) *out.fail = 3;
+      nh_carry = -1;
       __syncthreads();
       continue;
     }
-    const int np = np_all;
     for (int k = tid; k < np; k += THREADS) { pacc[k] = 0; pcnt[k] = 0; psmin[k] = 0xffffffffu; pemax[k] = 0; psmax[k] = 0; pemin[k] = 0xffffffffu; pen[k] = 0; }
     if (tid == 0 && cont0) pst[0] = tile_lo;
     __syncthreads();
@@ -241,7 +352,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
       for (int k = k0; k < k1; ++k) {
         d += delta[k];
         uint32_t pos = tile_lo + epos[k];
-        bool cin = in_range(cfg, d, pos);
+        bool cin = in_rng<MULTI>(cfg, mn0, mx0, d, pos);
         if (cin) {
           if (!prev_in) { ++cur; pst[cur] = pos; run_max = d; }
           else if (d > run_max) run_max = d;
@@ -255,54 +366,32 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
       if (prev_in && run_max > 0 && cur >= 0) atomicMax(&pacc[cur], run_max);
     }
     // depth after the tile's last event, judged with that event's group (tile_lo + W - 1 may lie beyond the last class)
-    const bool reach_end = np > 0 && in_range(cfg, depth_in + tile_net, (uint64_t)tile_lo + (total > 0 ? epos[total - 1] : 0));
+    const bool reach_end = np > 0 && in_rng<MULTI>(cfg, mn0, mx0, depth_in + tile_net, (uint64_t)tile_lo + (total > 0 ? epos[total - 1] : 0));
     __syncthreads();
     if (tid == 0 && reach_end) pen[np - 1] = tile_lo + W;
     __syncthreads();
-    // ---- phase 5: GMAP4, region-driven: the still-open regions of the previous tile, then the tile's own
+    // ---- phase 5: GMAP4, region-driven: the regions open at the tile start, then the tile's own
     if (np > 0) {
-      const uint32_t nS = s1 - s0;
-      const uint32_t n_h_rounds = ((uint32_t)nh + THREADS - 1) / THREADS, n_o_rounds = (nS + THREADS - 1) / THREADS;
-      for (uint32_t round = 0; round < n_h_rounds + n_o_rounds; ++round) {
-        const bool own = round >= n_h_rounds;
-        bool valid;
+      for (int k0h = 0; k0h < nh; k0h += THREADS) {
+        int k = k0h + tid;
+        bool valid = k < nh;
         uint32_t rs = 0, re = 0;
-        if (!own) {
-          uint32_t i = round * THREADS + tid;
-          valid = i < (uint32_t)nh;
-          if (valid) { rs = hS[i]; re = rs + (hL[i] & ~EXT); valid = re > tile_lo; }
-        } else {
-          uint32_t i = (round - n_h_rounds) * THREADS + tid;
-          valid = i < nS;
-          if (valid) { rs = S_key[s0 + i]; re = rs + (S_len[s0 + i] & ~EXT); }
+        if (valid) { rs = hinS[k]; re = rs + (hinL[k] & ~EXT); valid = re > tile_lo; }
+        gmap4_round(valid, rs, re, false, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
+      }
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        if ((uint32_t)(r * THREADS) < nS) {                 // block-uniform
+          bool valid = s0 + tid + r * THREADS < s1;
+          gmap4_round(valid, rsr[r], rsr[r] + (lpr[r] & ~EXT), true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
         }
-        int j = np;
-        if (valid) {
-          int lo = 0, hi = np;                 // first piece with end > rs
-          while (lo < hi) { int mid = (lo + hi) >> 1; if (pen[mid] > rs) hi = mid; else lo = mid + 1; }
-          j = lo;
-        }
-        while (true) {
-          bool ov = valid && j < np && pst[j] < re;
-          unsigned bal = __ballot_sync(0xffffffffu, ov);
-          if (!bal) break;
-          int J = __shfl_sync(0xffffffffu, j, __ffs(bal) - 1);
-          bool mine = ov && j == J;
-          bool add = mine && (own || !(J == 0 && cont0));   // halo regions only feed runs that START in this tile
-          unsigned m = __ballot_sync(0xffffffffu, add);
-          if (m) {
-            uint32_t a_smin = __reduce_min_sync(0xffffffffu, add ? rs : 0xffffffffu);
-            uint32_t a_emax = __reduce_max_sync(0xffffffffu, add ? re : 0u);
-            uint32_t a_smax = __reduce_max_sync(0xffffffffu, add ? rs : 0u);
-            uint32_t a_emin = __reduce_min_sync(0xffffffffu, add ? re : 0xffffffffu);
-            if (lane == (__ffs(m) - 1)) {
-              atomicAdd(&pcnt[J], __popc(m));
-              atomicMin(&psmin[J], a_smin); atomicMax(&pemax[J], a_emax);
-              atomicMax(&psmax[J], a_smax); atomicMin(&pemin[J], a_emin);
-            }
-          }
-          if (mine) ++j;
-        }
+      }
+      for (uint32_t i0 = s0 + RC * THREADS; i0 < s1; i0 += THREADS) {
+        uint32_t i = i0 + tid;
+        bool valid = i < s1;
+        uint32_t rs = 0, re = 0;
+        if (valid) { rs = S_key[i]; re = rs + (S_len[i] & ~EXT); }
+        gmap4_round(valid, rs, re, true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
       __syncthreads();
       // ---- publish the tile's pieces
@@ -321,6 +410,9 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
       }
     }
     __syncthreads();
+    // the regions still open at the tile end are the next tile's open regions
+    { uint32_t* t = hinS; hinS = houtS; houtS = t; t = hinL; hinL = houtL; houtL = t; }
+    nh_carry = nout;
   }
 }
 

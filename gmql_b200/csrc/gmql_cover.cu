@@ -903,8 +903,15 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   tiled::Pieces pc;
   pc.pstart = pstart.p; pc.pend = pend.p; pc.acc = acc.p; pc.cnt = cnt.p; pc.smin = smin.p; pc.emax = emax.p; pc.smax = smax.p; pc.emin = emin.p;
   pc.flags = pflags.p; pc.cursor = cursor.p; pc.cap = cap; pc.fail = fail.p;
-  CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-  LAUNCH(ctx, tiled::k_cover_tile, (unsigned)std::min<int64_t>(nT, (int64_t)ctx->num_sms * 32), tiled::THREADS, tiled::SMEM_BYTES, S_key, S_len, offS.p, nT, logw, tc, pc);
+  // two resident blocks per SM; four ranges per resident block even out the tail
+  const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nT, (int64_t)ctx->num_sms * 8));
+  if (cfg.n_groups > 1) {
+    CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
+    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, S_key, S_len, offS.p, nT, n, logw, tc, pc);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
+    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, S_key, S_len, offS.p, nT, n, logw, tc, pc);
+  }
   unsigned long long h_np = 0;
   int h_fail = 0;
   CUDA_TRY(cudaMemcpyAsync(&h_np, cursor.p, sizeof h_np, cudaMemcpyDeviceToHost, ctx->stream));
