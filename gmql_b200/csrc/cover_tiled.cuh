@@ -371,7 +371,37 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
     if (tid == 0 && reach_end) pen[np - 1] = tile_lo + W;
     __syncthreads();
     // ---- phase 5: GMAP4, region-driven: the regions open at the tile start, then the tile's own
-    if (np > 0) {
+    if (np == 1) {
+      // one piece (the usual case under dense coverage): no search, thread-local accumulation, one reduction per warp
+      const uint32_t p0 = pst[0], p1 = pen[0];
+      int32_t cnt = 0;
+      uint32_t a_smin = 0xffffffffu, a_emax = 0, a_smax = 0, a_emin = 0xffffffffu;
+      if (!cont0) {                                         // the open regions only feed a run that STARTS in this tile
+        for (int k = tid; k < nh; k += THREADS) {
+          uint32_t rs = hinS[k], re = rs + (hinL[k] & ~EXT);
+          if (re > tile_lo && p1 > rs && p0 < re) { ++cnt; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        if (s0 + tid + r * THREADS < s1) {
+          uint32_t rs = rsr[r], re = rs + (lpr[r] & ~EXT);
+          if (p1 > rs && p0 < re) { ++cnt; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
+        }
+      }
+      for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
+        uint32_t rs = S_key[i], re = rs + (S_len[i] & ~EXT);
+        if (p1 > rs && p0 < re) { ++cnt; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
+      }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      a_smin = __reduce_min_sync(0xffffffffu, a_smin); a_emax = __reduce_max_sync(0xffffffffu, a_emax);
+      a_smax = __reduce_max_sync(0xffffffffu, a_smax); a_emin = __reduce_min_sync(0xffffffffu, a_emin);
+      if (lane == 0 && cnt > 0) {
+        atomicAdd(&pcnt[0], cnt);
+        atomicMin(&psmin[0], a_smin); atomicMax(&pemax[0], a_emax);
+        atomicMax(&psmax[0], a_smax); atomicMin(&pemin[0], a_emin);
+      }
+    } else if (np > 1) {
       for (int k0h = 0; k0h < nh; k0h += THREADS) {
         int k = k0h + tid;
         bool valid = k < nh;
@@ -393,6 +423,8 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
         if (valid) { rs = S_key[i]; re = rs + (S_len[i] & ~EXT); }
         gmap4_round(valid, rs, re, true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
+    }
+    if (np > 0) {
       __syncthreads();
       // ---- publish the tile's pieces
       if (tid == 0) {
