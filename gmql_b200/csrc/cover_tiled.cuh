@@ -59,23 +59,23 @@ __device__ __forceinline__ bool in_range(const Cfg& c, int32_t d, uint64_t pos) 
   return d >= c.mn[g] && d <= c.mx[g];
 }
 
-// linear start key and length payload (bit 31: the extractor's one-base extension, GenometricCover.scala:353-354)
+// one packed 64-bit record per region: linear start key (high word) and length payload (low word; bit 31: the
+// extractor's one-base extension, GenometricCover.scala:353-354).  Partitioning sorts on the high bits only.
 static __global__ void k_tile_keys(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls,
-                                   int64_t n, LinMap lm, int64_t B, uint32_t* __restrict__ skeys, uint32_t* __restrict__ lens) {
+                                   int64_t n, LinMap lm, int64_t B, uint64_t* __restrict__ packed) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
     uint64_t base = (cls ? (uint64_t)cls[i] : 0ull) * lm.G + lm.coff[chrom[i]];
     bool ext = (e % B == 0 && s / B != e / B);
-    skeys[i] = (uint32_t)(base + (uint64_t)s);
-    lens[i] = (uint32_t)(e - s) | (ext ? EXT : 0u);
+    packed[i] = ((base + (uint64_t)s) << 32) | (uint64_t)((uint32_t)(e - s) | (ext ? EXT : 0u));
   }
 }
 
-// keys partitioned by tile -> first index of every tile (off[nT] = n)
-static __global__ void k_tile_offsets(const uint32_t* __restrict__ keys, int64_t n, int64_t nT, int logw, uint32_t* __restrict__ off) {
+// records partitioned by tile -> first index of every tile (off[nT] = n)
+static __global__ void k_tile_offsets(const uint64_t* __restrict__ packed, int64_t n, int64_t nT, int logw, uint32_t* __restrict__ off) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = keys[i] >> logw;
-    int64_t tp = i > 0 ? (int64_t)(keys[i - 1] >> logw) : -1;
+    int64_t t = (int64_t)(packed[i] >> (32 + logw));
+    int64_t tp = i > 0 ? (int64_t)(packed[i - 1] >> (32 + logw)) : -1;
     for (int64_t u = tp + 1; u <= t; ++u) off[u] = (uint32_t)i;
     if (i == n - 1) for (int64_t u = t + 1; u <= nT; ++u) off[u] = (uint32_t)n;
   }
@@ -145,7 +145,7 @@ __device__ __forceinline__ void gmap4_round(bool valid, uint32_t rs, uint32_t re
 // still open at a tile's end are handed to the next tile through shared memory; only the first tile of a range scans
 // its predecessor's regions in global memory.
 template <bool MULTI>
-static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t* __restrict__ S_key, const uint32_t* __restrict__ S_len, const uint32_t* __restrict__ offS,
+static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* __restrict__ P /* .y = start key, .x = length payload */, const uint32_t* __restrict__ offS,
                                                                   int64_t nT, int64_t n, int logw, Cfg cfg, Pieces out) {
   extern __shared__ uint32_t sm[];
   uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
@@ -209,7 +209,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
       for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
         uint32_t i = i0 + tid;
         if (i < s0) {
-          uint32_t rs = S_key[i], lp = S_len[i];
+          const uint2 pr = P[i]; uint32_t rs = pr.y, lp = pr.x;
           uint32_t ee = rs + (lp & ~EXT) + (lp >> 31);
           if (ee >= tile_lo) {
             int slot = atomicAdd(&s_nh, 1);
@@ -231,7 +231,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
     for (int r = 0; r < RC; ++r) {
       uint32_t i = s0 + tid + r * THREADS;
       rsr[r] = 0; lpr[r] = 0;
-      if (i < s1) { rsr[r] = S_key[i]; lpr[r] = S_len[i]; }
+      if (i < s1) { const uint2 pr = P[i]; rsr[r] = pr.y; lpr[r] = pr.x; }
     }
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
@@ -244,7 +244,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
       }
     }
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      uint32_t rs = S_key[i], lp = S_len[i];
+      const uint2 pr = P[i]; uint32_t rs = pr.y, lp = pr.x;
       uint32_t q = rs - tile_lo;
       atomicOr(&bitmap[q >> 5], 1u << (q & 31));
       uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
@@ -295,7 +295,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
       }
     }
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      uint32_t rs = S_key[i], lp = S_len[i];
+      const uint2 pr = P[i]; uint32_t rs = pr.y, lp = pr.x;
       uint32_t q = rs - tile_lo;
       int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
       atomicAdd(&delta[rk], 1);
@@ -390,7 +390,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
         }
       }
       for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-        uint32_t rs = S_key[i], re = rs + (S_len[i] & ~EXT);
+        const uint2 pr = P[i]; uint32_t rs = pr.y, re = rs + (pr.x & ~EXT);
         if (p1 > rs && p0 < re) { ++cnt; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
       }
       cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -420,7 +420,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint32_t
         uint32_t i = i0 + tid;
         bool valid = i < s1;
         uint32_t rs = 0, re = 0;
-        if (valid) { rs = S_key[i]; re = rs + (S_len[i] & ~EXT); }
+        if (valid) { const uint2 pr = P[i]; rs = pr.y; re = rs + (pr.x & ~EXT); }
         gmap4_round(valid, rs, re, true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
     }

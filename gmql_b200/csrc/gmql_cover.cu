@@ -884,12 +884,12 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   const int64_t n = in.n;
   const int key_bits = bits_for(n_classes_total * lm.G);
   const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
-  DevBuf<uint32_t> sk_a(ctx, n), sk_b(ctx, n), sl_a(ctx, n), sl_b(ctx, n);
-  LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, sk_a.p, sl_a.p);
-  uint32_t *S_key, *S_len;
-  radix_sort<uint32_t>(ctx, sk_a.p, sk_b.p, sl_a.p, sl_b.p, n, key_bits, &S_key, &S_len, logw);   // partition by tile only
+  DevBuf<uint64_t> pk_a(ctx, n), pk_b(ctx, n);
+  LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, pk_a.p);
+  uint64_t* P;
+  radix_sort<uint64_t>(ctx, pk_a.p, pk_b.p, nullptr, nullptr, n, 32 + key_bits, &P, nullptr, 32 + logw);   // partition by tile only
   DevBuf<uint32_t> offS(ctx, nT + 1);
-  LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, S_key, n, nT, logw, offS.p);
+  LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, P, n, nT, logw, offS.p);
 
   int64_t cap = std::max<int64_t>((int64_t)1 << 20, n / 16 + 2 * nT);
   DevBuf<uint32_t> pstart(ctx, cap), pend(ctx, cap), smin(ctx, cap), emax(ctx, cap), smax(ctx, cap), emin(ctx, cap);
@@ -907,10 +907,10 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nT, (int64_t)ctx->num_sms * 8));
   if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, S_key, S_len, offS.p, nT, n, logw, tc, pc);
+    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, nT, n, logw, tc, pc);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, S_key, S_len, offS.p, nT, n, logw, tc, pc);
+    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, nT, n, logw, tc, pc);
   }
   unsigned long long h_np = 0;
   int h_fail = 0;
@@ -919,7 +919,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (h_fail) return false;
   const int64_t np = (int64_t)h_np;
-  sk_a.release(); sk_b.release(); sl_a.release(); sl_b.release();
+  pk_a.release(); pk_b.release();
 
   // order the pieces by start, fuse the ones that touch at a tile edge
   DevBuf<uint32_t> ok_a(ctx, np), ok_b(ctx, np), oi_a(ctx, np), oi_b(ctx, np);
