@@ -71,6 +71,137 @@ static __global__ void k_tile_keys(const int32_t* __restrict__ chrom, const void
   }
 }
 
+// ---- partition of the regions by tile: counting + two multisplit passes ----------------------------------------------
+// The order inside a tile is irrelevant, so no stable ranking is needed: a block counts its records per bin with
+// shared-memory atomics (the returned value is the record's rank inside the block), reserves the output range of every
+// bin with ONE global atomicAdd on a cursor that starts at the bin's final offset, regroups the records in shared memory
+// and writes each bin's run coalesced.  Pass 1 splits by coarse bin (256 tiles) straight from the input columns (the
+// packed record never exists unpartitioned); pass 2 splits every coarse bin into its tiles.
+constexpr int MSP_THREADS = 512;
+constexpr int MSP_ITEMS = 8;
+constexpr int MSP_TILE = MSP_THREADS * MSP_ITEMS;
+constexpr int MSP_BINS = 1024;          // block-local bins (pass 2: tiles reachable from the block's first coarse bin)
+constexpr int HIST_CAP = 54 * 1024;     // tiles whose counters fit one block's shared memory
+
+__device__ __forceinline__ uint64_t make_record(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits,
+                                                const uint32_t* __restrict__ cls, const uint64_t* coff, uint64_t G, int64_t B, int64_t i) {
+  int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+  uint64_t base = (cls ? (uint64_t)cls[i] : 0ull) * G + coff[chrom[i]];
+  bool ext;
+  if (bits == 32 && B > 0 && B < 0x7fffffffLL) { uint32_t b = (uint32_t)B, us = (uint32_t)s, ue = (uint32_t)e; ext = (ue % b == 0) && (us / b != ue / b); }
+  else ext = (e % B == 0 && s / B != e / B);
+  return ((base + (uint64_t)s) << 32) | (uint64_t)((uint32_t)(e - s) | (ext ? EXT : 0u));
+}
+
+// regions per tile: block-private counters in shared memory, merged with one RED per non-empty counter
+static __global__ void __launch_bounds__(1024, 1) k_tile_hist(const int32_t* __restrict__ chrom, const void* __restrict__ start, int bits, const uint32_t* __restrict__ cls,
+                                                               int64_t n, LinMap lm, int logw, int nT, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t sh_hist[];                    // [nT] then chromosome offsets
+  uint64_t* s_coff = (uint64_t*)(sh_hist + ((nT + 1) & ~1));
+  const bool chrom_sh = lm.n_chrom <= 1024;
+  for (int k = threadIdx.x; k < nT; k += blockDim.x) sh_hist[k] = 0;
+  if (chrom_sh) for (int k = threadIdx.x; k < lm.n_chrom; k += blockDim.x) s_coff[k] = lm.coff[k];
+  __syncthreads();
+  const uint64_t* coff = chrom_sh ? s_coff : lm.coff;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t key = (cls ? (uint64_t)cls[i] : 0ull) * lm.G + coff[chrom[i]] + (uint64_t)ld_coord(start, bits, i);
+    atomicAdd(&sh_hist[key >> logw], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nT; k += blockDim.x) { uint32_t c = sh_hist[k]; if (c) atomicAdd(&hist[k], c); }
+}
+
+// cursors: every tile / coarse bin starts at its final offset
+static __global__ void k_init_cursors(const uint32_t* __restrict__ off, int nT, uint32_t* __restrict__ cur_tile, uint32_t* __restrict__ cur_coarse, int n_coarse) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nT; k += gridDim.x * blockDim.x) cur_tile[k] = off[k];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_coarse; k += gridDim.x * blockDim.x) cur_coarse[k] = off[min(k << 8, nT)];
+}
+
+// FUSED: records are built from the input columns and split by coarse bin (tile >> 8); otherwise records are read from
+// `in` and split by tile.  bin_shift = 32 + logw (+ 8 for the coarse pass).
+template <bool FUSED>
+static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint64_t* __restrict__ in, const int32_t* __restrict__ chrom, const void* __restrict__ start,
+                                                                      const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls, LinMap lm, int64_t B,
+                                                                      int64_t n, int bin_shift, uint32_t* __restrict__ cursor, uint64_t* __restrict__ out) {
+  __shared__ uint64_t sdata[MSP_TILE];
+  __shared__ uint32_t cnt[MSP_BINS], lexcl[MSP_BINS], gbase[MSP_BINS];
+  __shared__ uint64_t s_coff[FUSED ? 256 : 1];
+  __shared__ uint32_t wtot[MSP_THREADS / 32];
+  __shared__ uint32_t s_base_bin;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool chrom_sh = FUSED && lm.n_chrom <= 256;
+  if (chrom_sh) for (int k = tid; k < lm.n_chrom; k += MSP_THREADS) s_coff[k] = lm.coff[k];
+  const uint64_t* coff = chrom_sh ? s_coff : lm.coff;
+  const int64_t n_tiles = (n + MSP_TILE - 1) / MSP_TILE;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t base = t * MSP_TILE;
+    const int count = (int)((n - base) < (int64_t)MSP_TILE ? (n - base) : (int64_t)MSP_TILE);
+    for (int k = tid; k < MSP_BINS; k += MSP_THREADS) cnt[k] = 0;
+    __syncthreads();                                       // also orders s_coff and the previous iteration's reads
+    uint64_t rec[MSP_ITEMS];
+#pragma unroll
+    for (int j = 0; j < MSP_ITEMS; ++j) {
+      const int idx = j * MSP_THREADS + tid;
+      rec[j] = 0;
+      if (idx < count) rec[j] = FUSED ? make_record(chrom, start, stop, bits, cls, coff, lm.G, B, base + idx) : in[base + idx];
+    }
+    if (!FUSED) {
+      // local bins are counted from the coarse bin of the tile's first record
+      if (tid == 0) s_base_bin = (uint32_t)(rec[0] >> bin_shift) & ~255u;
+      __syncthreads();
+    }
+    const uint32_t base_bin = FUSED ? 0u : s_base_bin;
+    uint32_t rk[MSP_ITEMS];
+#pragma unroll
+    for (int j = 0; j < MSP_ITEMS; ++j) {
+      const int idx = j * MSP_THREADS + tid;
+      rk[j] = 0xffffffffu;
+      if (idx < count) {
+        uint32_t lb = (uint32_t)(rec[j] >> bin_shift) - base_bin;
+        if (lb < (uint32_t)MSP_BINS) rk[j] = atomicAdd(&cnt[lb], 1u);
+        else {                                             // far bin (tiny coarse bins only): placed directly
+          uint32_t g = atomicAdd(&cursor[(uint32_t)(rec[j] >> bin_shift)], 1u);
+          out[g] = rec[j];
+        }
+      }
+    }
+    __syncthreads();
+    // reserve every bin's output range; exclusive offsets of the bins inside the block
+    {
+      uint32_t c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
+      if (c0) gbase[2 * tid] = atomicAdd(&cursor[base_bin + 2 * tid], c0);
+      if (c1) gbase[2 * tid + 1] = atomicAdd(&cursor[base_bin + 2 * tid + 1], c1);
+      uint32_t v = c0 + c1, x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      if (lane == 31) wtot[w] = x;
+      __syncthreads();
+      uint32_t tt = lane < MSP_THREADS / 32 ? wtot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < MSP_THREADS / 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, tt, o); if (lane >= o) tt += y; }
+      uint32_t below = __shfl_sync(0xffffffffu, tt, w > 0 ? w - 1 : 0);
+      uint32_t ex = (w > 0 ? below : 0) + x - v;
+      lexcl[2 * tid] = ex; lexcl[2 * tid + 1] = ex + c0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < MSP_ITEMS; ++j) {
+      if (rk[j] != 0xffffffffu) {
+        uint32_t lb = (uint32_t)(rec[j] >> bin_shift) - base_bin;
+        sdata[lexcl[lb] + rk[j]] = rec[j];
+      }
+    }
+    __syncthreads();
+    const int local_total = (int)(lexcl[MSP_BINS - 1] + cnt[MSP_BINS - 1]);
+    for (int i = tid; i < local_total; i += MSP_THREADS) {
+      uint64_t r = sdata[i];
+      uint32_t lb = (uint32_t)(r >> bin_shift) - base_bin;
+      out[gbase[lb] + ((uint32_t)i - lexcl[lb])] = r;
+    }
+    __syncthreads();
+  }
+}
+
 // records partitioned by tile -> first index of every tile (off[nT] = n)
 static __global__ void k_tile_offsets(const uint64_t* __restrict__ packed, int64_t n, int64_t nT, int logw, uint32_t* __restrict__ off) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

@@ -885,11 +885,28 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   const int key_bits = bits_for(n_classes_total * lm.G);
   const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
   DevBuf<uint64_t> pk_a(ctx, n), pk_b(ctx, n);
-  LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, pk_a.p);
-  uint64_t* P;
-  radix_sort<uint64_t>(ctx, pk_a.p, pk_b.p, nullptr, nullptr, n, 32 + key_bits, &P, nullptr, 32 + logw);   // partition by tile only
   DevBuf<uint32_t> offS(ctx, nT + 1);
-  LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, P, n, nT, logw, offS.p);
+  uint64_t* P;
+  if (nT <= tiled::HIST_CAP) {
+    // counting + two multisplit passes (cover_tiled.cuh): the packed record never exists unpartitioned
+    const int n_coarse = (int)((nT + 255) >> 8) + 1;
+    DevBuf<uint32_t> hist(ctx, nT + 1), cur_tile(ctx, nT + 1), cur_coarse(ctx, n_coarse);
+    hist.zero();
+    size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + (lm.n_chrom <= 1024 ? 8 * (size_t)lm.n_chrom : 0);
+    CUDA_TRY(cudaFuncSetAttribute(tiled::k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
+    LAUNCH(ctx, tiled::k_tile_hist, (unsigned)std::min<int64_t>(ceil_div64(n, 1024 * 16), (int64_t)ctx->num_sms), 1024, hsh, in.chrom, in.start, in.coord_bits, cls, n, lm, logw, (int)nT, hist.p);
+    device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, hist.p, offS.p, nT, offS.p + nT);
+    LAUNCH(ctx, tiled::k_init_cursors, grid_for(ctx, nT, 256), 256, 0, offS.p, (int)nT, cur_tile.p, cur_coarse.p, n_coarse);
+    const unsigned mg = (unsigned)std::min<int64_t>(ceil_div64(n, tiled::MSP_TILE), (int64_t)ctx->num_sms * 16);
+    LAUNCH(ctx, tiled::k_multisplit<true>, mg, tiled::MSP_THREADS, 0, (const uint64_t*)nullptr, in.chrom, in.start, in.stop, in.coord_bits, cls, lm, cfg.B, n, 32 + logw + 8, cur_coarse.p, pk_a.p);
+    LAUNCH(ctx, tiled::k_multisplit<false>, mg, tiled::MSP_THREADS, 0, (const uint64_t*)pk_a.p, (const int32_t*)nullptr, (const void*)nullptr, (const void*)nullptr, 0, (const uint32_t*)nullptr, lm, cfg.B, n,
+           32 + logw, cur_tile.p, pk_b.p);
+    P = pk_b.p;
+  } else {
+    LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, pk_a.p);
+    radix_sort<uint64_t>(ctx, pk_a.p, pk_b.p, nullptr, nullptr, n, 32 + key_bits, &P, nullptr, 32 + logw);   // partition by tile only
+    LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, P, n, nT, logw, offS.p);
+  }
 
   int64_t cap = std::max<int64_t>((int64_t)1 << 20, n / 16 + 2 * nT);
   DevBuf<uint32_t> pstart(ctx, cap), pend(ctx, cap), smin(ctx, cap), emax(ctx, cap), smax(ctx, cap), emin(ctx, cap);
