@@ -87,9 +87,11 @@ __device__ __forceinline__ uint64_t make_record(const int32_t* __restrict__ chro
                                                 const uint32_t* __restrict__ cls, const uint64_t* coff, uint64_t G, int64_t B, int64_t i) {
   int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
   uint64_t base = (cls ? (uint64_t)cls[i] : 0ull) * G + coff[chrom[i]];
+  // stop on a bin multiple and the region crosses a bin edge; with stop = q*B the second condition (start / B != q)
+  // is simply start < stop
   bool ext;
-  if (bits == 32 && B > 0 && B < 0x7fffffffLL) { uint32_t b = (uint32_t)B, us = (uint32_t)s, ue = (uint32_t)e; ext = (ue % b == 0) && (us / b != ue / b); }
-  else ext = (e % B == 0 && s / B != e / B);
+  if (bits == 32 && B > 0 && B < 0x7fffffffLL) ext = ((uint32_t)e % (uint32_t)B == 0) && s < e;
+  else ext = (e % B == 0) && s < e;
   return ((base + (uint64_t)s) << 32) | (uint64_t)((uint32_t)(e - s) | (ext ? EXT : 0u));
 }
 
@@ -103,9 +105,23 @@ static __global__ void __launch_bounds__(1024, 1) k_tile_hist(const int32_t* __r
   if (chrom_sh) for (int k = threadIdx.x; k < lm.n_chrom; k += blockDim.x) s_coff[k] = lm.coff[k];
   __syncthreads();
   const uint64_t* coff = chrom_sh ? s_coff : lm.coff;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t key = (cls ? (uint64_t)cls[i] : 0ull) * lm.G + coff[chrom[i]] + (uint64_t)ld_coord(start, bits, i);
-    atomicAdd(&sh_hist[key >> logw], 1u);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+    int c[4]; int64_t st[4]; uint32_t cl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t q = i + j * stride;
+      bool ok = q < n;
+      c[j] = ok ? chrom[q] : -1;
+      st[j] = ok ? ld_coord(start, bits, q) : 0;
+      cl[j] = ok && cls ? cls[q] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c[j] < 0) continue;
+      uint64_t key = (uint64_t)cl[j] * lm.G + coff[c[j]] + (uint64_t)st[j];
+      atomicAdd(&sh_hist[key >> logw], 1u);
+    }
   }
   __syncthreads();
   for (int k = threadIdx.x; k < nT; k += blockDim.x) { uint32_t c = sh_hist[k]; if (c) atomicAdd(&hist[k], c); }
@@ -122,7 +138,7 @@ static __global__ void k_init_cursors(const uint32_t* __restrict__ off, int nT, 
 template <bool FUSED>
 static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint64_t* __restrict__ in, const int32_t* __restrict__ chrom, const void* __restrict__ start,
                                                                       const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls, LinMap lm, int64_t B,
-                                                                      int64_t n, int bin_shift, uint32_t* __restrict__ cursor, uint64_t* __restrict__ out) {
+                                                                      int64_t n, int bin_shift, uint32_t* __restrict__ cursor, uint64_t* __restrict__ out, int vec_ok) {
   __shared__ uint64_t sdata[MSP_TILE];
   __shared__ uint32_t cnt[MSP_BINS], lexcl[MSP_BINS], gbase[MSP_BINS];
   __shared__ uint64_t s_coff[FUSED ? 256 : 1];
@@ -138,12 +154,37 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
     const int count = (int)((n - base) < (int64_t)MSP_TILE ? (n - base) : (int64_t)MSP_TILE);
     for (int k = tid; k < MSP_BINS; k += MSP_THREADS) cnt[k] = 0;
     __syncthreads();                                       // also orders s_coff and the previous iteration's reads
+    // item j of a thread is record idx_of(j) of the tile: striped for packed input, four consecutive regions per
+    // 128-bit column load when the records are built from the columns
     uint64_t rec[MSP_ITEMS];
+    if (FUSED) {
 #pragma unroll
-    for (int j = 0; j < MSP_ITEMS; ++j) {
-      const int idx = j * MSP_THREADS + tid;
-      rec[j] = 0;
-      if (idx < count) rec[j] = FUSED ? make_record(chrom, start, stop, bits, cls, coff, lm.G, B, base + idx) : in[base + idx];
+      for (int j4 = 0; j4 < MSP_ITEMS / 4; ++j4) {
+        const int idx0 = (j4 * MSP_THREADS + tid) * 4;
+        const int64_t i0 = base + idx0;
+        if (idx0 + 4 <= count && vec_ok && bits == 32) {
+          const int4 vc = *(const int4*)(chrom + i0), vs = *(const int4*)((const int32_t*)start + i0), ve = *(const int4*)((const int32_t*)stop + i0);
+          uint4 vk = make_uint4(0u, 0u, 0u, 0u);
+          if (cls) vk = *(const uint4*)(cls + i0);
+          const int cc[4] = {vc.x, vc.y, vc.z, vc.w}, ss[4] = {vs.x, vs.y, vs.z, vs.w}, ee[4] = {ve.x, ve.y, ve.z, ve.w};
+          const uint32_t kk[4] = {vk.x, vk.y, vk.z, vk.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t key = (uint32_t)((uint64_t)kk[q] * lm.G + coff[cc[q]]) + (uint32_t)ss[q];
+            const bool ext = ((uint32_t)ee[q] % (uint32_t)B == 0) && ss[q] < ee[q];
+            rec[j4 * 4 + q] = ((uint64_t)key << 32) | (uint64_t)((uint32_t)(ee[q] - ss[q]) | (ext ? EXT : 0u));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rec[j4 * 4 + q] = idx0 + q < count ? make_record(chrom, start, stop, bits, cls, coff, lm.G, B, i0 + q) : 0ull;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < MSP_ITEMS; ++j) {
+        const int idx = j * MSP_THREADS + tid;
+        rec[j] = idx < count ? in[base + idx] : 0ull;
+      }
     }
     if (!FUSED) {
       // local bins are counted from the coarse bin of the tile's first record
@@ -154,7 +195,7 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
     uint32_t rk[MSP_ITEMS];
 #pragma unroll
     for (int j = 0; j < MSP_ITEMS; ++j) {
-      const int idx = j * MSP_THREADS + tid;
+      const int idx = FUSED ? ((j >> 2) * MSP_THREADS + tid) * 4 + (j & 3) : j * MSP_THREADS + tid;
       rk[j] = 0xffffffffu;
       if (idx < count) {
         uint32_t lb = (uint32_t)(rec[j] >> bin_shift) - base_bin;

@@ -57,27 +57,57 @@ __global__ void k_cover_inspect(const int8_t* __restrict__ strand, const int32_t
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) flags[2] = 1;
 }
 
-// gmql_cover's own prepass: per-chromosome max stop (span table) and the input flags in ONE read of the columns
-__global__ void k_cover_prepass(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const int8_t* __restrict__ strand,
-                                const int32_t* __restrict__ sample, int64_t n, int n_chrom, int n_samples, unsigned long long* __restrict__ span, int* __restrict__ flags) {
+// gmql_cover's own prepass: per-chromosome max stop (span table) and the input flags in ONE read of the columns.
+// Four consecutive regions per thread and iteration (128-bit column loads when the coordinates are 32-bit and the
+// columns 16-byte aligned); the per-chromosome maxima live in shared memory (native 32-bit atomicMax for 32-bit coords).
+__global__ void __launch_bounds__(256) k_cover_prepass(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits,
+                                                       const int8_t* __restrict__ strand, const int32_t* __restrict__ sample, int64_t n, int n_chrom, int n_samples,
+                                                       unsigned long long* __restrict__ span, int* __restrict__ flags, int vec_ok) {
   extern __shared__ unsigned long long sspan[];
-  bool use_sh = n_chrom <= 4096;
+  uint32_t* sspan32 = (uint32_t*)sspan;
+  const bool use_sh = n_chrom <= 4096;
+  const bool sh32 = use_sh && bits == 32;
   if (use_sh) {
-    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) sspan[c] = 0ull;
+    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) { if (sh32) sspan32[c] = 0u; else sspan[c] = 0ull; }
     __syncthreads();
   }
   int has_star = 0, zero = 0, bad = 0;
   long long maxlen = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = chrom[i];
-    int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
-    int st = strand ? (int)strand[i] : 0;
-    int sm = sample ? sample[i] : 0;
-    if (st == 0) has_star = 1;
-    if (s == e) zero = 1;
-    if (e - s > maxlen) maxlen = e - s;
-    if (c < 0 || c >= n_chrom || s < 0 || s > e || st < 0 || st > 2 || sm < 0 || sm >= n_samples) { bad = 1; continue; }
-    if (use_sh) atomicMax(&sspan[c], (unsigned long long)e); else atomicMax(&span[c], (unsigned long long)e);
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x * 4) {
+    int c[4], st[4], sm[4];
+    int64_t s[4], e[4];
+    if (i0 + 4 <= n && vec_ok && bits == 32) {
+      int4 vc = *(const int4*)(chrom + i0), vs = *(const int4*)((const int32_t*)start + i0), ve = *(const int4*)((const int32_t*)stop + i0);
+      c[0] = vc.x; c[1] = vc.y; c[2] = vc.z; c[3] = vc.w;
+      s[0] = vs.x; s[1] = vs.y; s[2] = vs.z; s[3] = vs.w;
+      e[0] = ve.x; e[1] = ve.y; e[2] = ve.z; e[3] = ve.w;
+      if (sample) { int4 vb = *(const int4*)(sample + i0); sm[0] = vb.x; sm[1] = vb.y; sm[2] = vb.z; sm[3] = vb.w; }
+      else { sm[0] = sm[1] = sm[2] = sm[3] = 0; }
+      if (strand) { uint32_t w = *(const uint32_t*)(strand + i0); st[0] = (int)(int8_t)(w & 0xff); st[1] = (int)(int8_t)((w >> 8) & 0xff); st[2] = (int)(int8_t)((w >> 16) & 0xff); st[3] = (int)(int8_t)(w >> 24); }
+      else { st[0] = st[1] = st[2] = st[3] = 0; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int64_t i = i0 + j;
+        bool ok = i < n;
+        c[j] = ok ? chrom[i] : -2;                         // -2: padding lane
+        s[j] = ok ? ld_coord(start, bits, i) : 0;
+        e[j] = ok ? ld_coord(stop, bits, i) : 1;
+        st[j] = ok && strand ? (int)strand[i] : (ok ? 0 : 1);
+        sm[j] = ok && sample ? sample[i] : 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c[j] == -2) continue;
+      if (st[j] == 0) has_star = 1;
+      if (s[j] == e[j]) zero = 1;
+      if (e[j] - s[j] > maxlen) maxlen = e[j] - s[j];
+      if (c[j] < 0 || c[j] >= n_chrom || s[j] < 0 || s[j] > e[j] || st[j] < 0 || st[j] > 2 || sm[j] < 0 || sm[j] >= n_samples) { bad = 1; continue; }
+      if (sh32) atomicMax(&sspan32[c[j]], (uint32_t)e[j]);
+      else if (use_sh) atomicMax(&sspan[c[j]], (unsigned long long)e[j]);
+      else atomicMax(&span[c[j]], (unsigned long long)e[j]);
+    }
   }
   if (__any_sync(0xffffffffu, has_star) && (threadIdx.x & 31) == 0) flags[0] = 1;
   if (__any_sync(0xffffffffu, zero) && (threadIdx.x & 31) == 0) flags[1] = 1;
@@ -89,8 +119,10 @@ __global__ void k_cover_prepass(const int32_t* __restrict__ chrom, const void* _
   }
   if (use_sh) {
     __syncthreads();
-    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x)
-      if (sspan[c]) atomicMax(&span[c], sspan[c]);
+    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) {
+      unsigned long long v = sh32 ? (unsigned long long)sspan32[c] : sspan[c];
+      if (v) atomicMax(&span[c], v);
+    }
   }
 }
 
@@ -898,9 +930,11 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, hist.p, offS.p, nT, offS.p + nT);
     LAUNCH(ctx, tiled::k_init_cursors, grid_for(ctx, nT, 256), 256, 0, offS.p, (int)nT, cur_tile.p, cur_coarse.p, n_coarse);
     const unsigned mg = (unsigned)std::min<int64_t>(ceil_div64(n, tiled::MSP_TILE), (int64_t)ctx->num_sms * 16);
-    LAUNCH(ctx, tiled::k_multisplit<true>, mg, tiled::MSP_THREADS, 0, (const uint64_t*)nullptr, in.chrom, in.start, in.stop, in.coord_bits, cls, lm, cfg.B, n, 32 + logw + 8, cur_coarse.p, pk_a.p);
+    auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
+    const int vec_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(cls) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
+    LAUNCH(ctx, tiled::k_multisplit<true>, mg, tiled::MSP_THREADS, 0, (const uint64_t*)nullptr, in.chrom, in.start, in.stop, in.coord_bits, cls, lm, cfg.B, n, 32 + logw + 8, cur_coarse.p, pk_a.p, vec_ok);
     LAUNCH(ctx, tiled::k_multisplit<false>, mg, tiled::MSP_THREADS, 0, (const uint64_t*)pk_a.p, (const int32_t*)nullptr, (const void*)nullptr, (const void*)nullptr, 0, (const uint32_t*)nullptr, lm, cfg.B, n,
-           32 + logw, cur_tile.p, pk_b.p);
+           32 + logw, cur_tile.p, pk_b.p, 0);
     P = pk_b.p;
   } else {
     LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, pk_a.p);
@@ -1171,9 +1205,11 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     DevBuf<int> flags(ctx, 4);
     flags.zero();
     if (d.n) {
-      int nb = (int)std::min<int64_t>(ceil_div64(d.n, 256 * 8), (int64_t)ctx->num_sms * 8);
+      int nb = (int)std::min<int64_t>(ceil_div64(d.n, 256 * 16), (int64_t)ctx->num_sms * 8);
       size_t sh = d.n_chrom <= 4096 ? sizeof(unsigned long long) * (size_t)d.n_chrom : 0;
-      LAUNCH(ctx, k_cover_prepass, nb, 256, sh, d.chrom, d.start, d.stop, d.coord_bits, d.strand, d.sample, d.n, d.n_chrom, d.n_samples, spans.span.p, flags.p);
+      auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
+      int vec_ok = al16(d.chrom) && al16(d.start) && al16(d.stop) && al16(d.sample) && ((uintptr_t)d.strand & 3u) == 0;
+      LAUNCH(ctx, k_cover_prepass, nb, 256, sh, d.chrom, d.start, d.stop, d.coord_bits, d.strand, d.sample, d.n, d.n_chrom, d.n_samples, spans.span.p, flags.p, vec_ok);
     }
     LAUNCH(ctx, k_chrom_offsets, 1, 32, 0, spans.span.p, d.n_chrom, spans.coff.p, (unsigned long long)bin_size + 2ull);
     int hf[4];
