@@ -31,7 +31,31 @@ struct gmql_ctx {
   bool profiling = false;
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
+  // pinned host scratch for small host->device tables (truly asynchronous copies); slots are reused from the start of
+  // every API call, when the stream is idle
+  std::vector<std::pair<void*, size_t>> pins;
+  size_t pin_next = 0;
 };
+
+// pinned host memory valid until the next API call on this context
+static inline void* ctx_pinned(gmql_ctx* c, size_t bytes) {
+  if (bytes < 4096) bytes = 4096;
+  if (c->pin_next < c->pins.size()) {
+    auto& slot = c->pins[c->pin_next];
+    if (slot.second < bytes) {
+      cudaFreeHost(slot.first);
+      slot.first = nullptr; slot.second = 0;
+      if (cudaHostAlloc(&slot.first, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); throw gmql_error(GMQL_ERR_NOMEM, "pinned host allocation failed"); }
+      slot.second = bytes;
+    }
+    return c->pins[c->pin_next++].first;
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); throw gmql_error(GMQL_ERR_NOMEM, "pinned host allocation failed"); }
+  c->pins.push_back(std::make_pair(p, bytes));
+  c->pin_next = c->pins.size();
+  return p;
+}
 
 static inline void gmql_prof_begin(gmql_ctx* c, const char* name) {
   gmql_ctx::ProfRec r; r.name = name;
@@ -121,6 +145,7 @@ struct DevRegions {
   std::vector<const uint8_t*> valid;
   std::vector<DevBuf<uint8_t>> owned;  // uploaded copies
   int64_t h2d_bytes = 0;
+  const int64_t* span_hint = nullptr;  // host [n_chrom] upper bounds of stop, or null
 };
 
 // upload (or adopt) a gmql_regions; only the value columns listed in need_cols are moved
@@ -142,6 +167,7 @@ struct gmql_result {
   std::vector<const double*> view_cols;
   std::vector<const uint8_t*> view_valid;
   void* view_acc_double = nullptr;
+  std::vector<int64_t> span_hint;    // cover results: upper bound of stop per chromosome (host)
 };
 template <typename T>
 static inline void result_add(gmql_result* r, int id, DevBuf<T>& b) {

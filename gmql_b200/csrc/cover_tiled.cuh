@@ -652,9 +652,11 @@ static __global__ void k_piece_merge(const uint32_t* __restrict__ order, Pieces 
 }
 
 // runs -> the arrays the common output stage (k_cover_compact) consumes
-static __global__ void k_runs_finalize(Runs r, int64_t nr, LinMap lm, int flat, uint32_t* __restrict__ ocls, int32_t* __restrict__ ochrom, int64_t* __restrict__ fstart, int64_t* __restrict__ fstop,
+static __global__ void k_runs_finalize(Runs r, int64_t nr, const int64_t* __restrict__ n_runs, LinMap lm, int flat, uint32_t* __restrict__ ocls, int32_t* __restrict__ ochrom, int64_t* __restrict__ fstart, int64_t* __restrict__ fstop,
                                        int32_t* __restrict__ oacc, int32_t* __restrict__ keep, double* __restrict__ j1, double* __restrict__ j2) {
+  const int64_t live = *n_runs;                  // entries [live, nr) are unused capacity
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nr; k += (int64_t)gridDim.x * blockDim.x) {
+    if (k >= live) { keep[k] = 0; ocls[k] = 0; ochrom[k] = 0; oacc[k] = 0; fstart[k] = 0; fstop[k] = 0; j1[k] = 0.0; j2[k] = 0.0; continue; }
     uint64_t x = r.rstart[k];
     uint64_t cls = x / lm.G, rem = x - cls * lm.G;
     int lo = 0, hi = lm.n_chrom;

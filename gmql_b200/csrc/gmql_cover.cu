@@ -741,7 +741,7 @@ struct FinalCols {
 };
 __global__ void k_cover_compact(int64_t nc, const int32_t* __restrict__ keep, const int64_t* __restrict__ keep_excl, const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom,
                                 const int64_t* __restrict__ fstart, const int64_t* __restrict__ fstop, const int32_t* __restrict__ cacc, const double* __restrict__ j1, const double* __restrict__ j2,
-                                CovOut in, int n_aggs, int n_classes, int unified, FinalCols f) {
+                                CovOut in, int n_aggs, int n_classes, int unified, FinalCols f, double* __restrict__ acc_d) {
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
     if (!keep[c]) continue;
     int64_t o = keep_excl[c];
@@ -752,6 +752,7 @@ __global__ void k_cover_compact(int64_t nc, const int32_t* __restrict__ keep, co
     f.start[o] = fstart[c];
     f.stop[o] = fstop[c];
     f.acc[o] = cacc[c];
+    acc_d[o] = (double)cacc[c];       // the view of the result as a region dataset exposes AccIndex as a value column
     f.j1[o] = j1[c];
     f.j2[o] = j2[c];
     for (int a = 0; a < n_aggs; ++a) { f.value[a][o] = in.value[a][c]; f.valid[a][o] = in.valid[a][c]; }
@@ -984,7 +985,9 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   DevBuf<int64_t> head_excl(ctx, np + 1);
   if (np) LAUNCH(ctx, tiled::k_piece_heads, grid_for(ctx, np, 256), 256, 0, order, pstart.p, pend.p, pflags.p, np, head.p);
   device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, head.p, head_excl.p, np, head_excl.p + np);
-  const int64_t nr = read_back<int64_t>(ctx, head_excl.p + np);
+  // the number of runs (<= np) stays on the device: the run tables are sized for np and the tail entries are dropped
+  // by the keep flags, which saves a host round trip
+  const int64_t nr = np;
   DevBuf<uint32_t> rstart(ctx, nr), rend(ctx, nr), rsmin(ctx, nr), remax(ctx, nr), rsmax(ctx, nr), remin(ctx, nr);
   DevBuf<int32_t> racc(ctx, nr), rcnt(ctx, nr);
   racc.zero(); rcnt.zero(); remax.zero(); rsmax.zero(); rsmin.fill_byte(0xff); remin.fill_byte(0xff);
@@ -994,7 +997,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   p1->n = nr;
   p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->acc.alloc(ctx, nr);
   keep.alloc(ctx, nr); fstart.alloc(ctx, nr); fstop.alloc(ctx, nr); j1.alloc(ctx, nr); j2.alloc(ctx, nr);
-  if (nr) LAUNCH(ctx, tiled::k_runs_finalize, grid_for(ctx, nr, 256), 256, 0, rr, nr, lm, flag == GMQL_FLAT ? 1 : 0, p1->cls.p, p1->chrom.p, fstart.p, fstop.p, p1->acc.p, keep.p, j1.p, j2.p);
+  if (nr) LAUNCH(ctx, tiled::k_runs_finalize, grid_for(ctx, nr, 256), 256, 0, rr, nr, (const int64_t*)(head_excl.p + np), lm, flag == GMQL_FLAT ? 1 : 0, p1->cls.p, p1->chrom.p, fstart.p, fstop.p, p1->acc.p, keep.p, j1.p, j2.p);
   *nc_out = nr;
   return true;
 }
@@ -1102,7 +1105,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   DevBuf<int32_t> o_group(ctx, n_out), o_chrom(ctx, n_out), o_acc(ctx, n_out);
   DevBuf<int64_t> o_start(ctx, n_out), o_stop(ctx, n_out);
   DevBuf<int8_t> o_strand(ctx, n_out);
-  DevBuf<double> o_j1(ctx, n_out), o_j2(ctx, n_out);
+  DevBuf<double> o_j1(ctx, n_out), o_j2(ctx, n_out), o_accd(ctx, n_out > 0 ? n_out : 1);
   std::vector<DevBuf<double>> ov((size_t)plan.n_aggs);
   std::vector<DevBuf<uint8_t>> ok((size_t)plan.n_aggs);
   FinalCols f;
@@ -1110,8 +1113,11 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   f.group = o_group.p; f.chrom = o_chrom.p; f.start = o_start.p; f.stop = o_stop.p; f.strand = o_strand.p; f.acc = o_acc.p; f.j1 = o_j1.p; f.j2 = o_j2.p;
   for (int a = 0; a < plan.n_aggs; ++a) { ov[a].alloc(ctx, n_out); ok[a].alloc(ctx, n_out); f.value[a] = ov[a].p; f.valid[a] = ok[a].p; }
   if (nc && n_out) LAUNCH(ctx, k_cover_compact, grid_for(ctx, nc, 256), 256, 0, nc, keep.p, keep_excl.p, p1.cls.p, p1.chrom.p, fstart.p, fstop.p, p1.acc.p, j1.p, j2.p,
-                          tmp, plan.n_aggs, cfg.n_classes, cfg.unified, f);
+                          tmp, plan.n_aggs, cfg.n_classes, cfg.unified, f, o_accd.p);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
+  res->view_acc_double = (void*)o_accd.detach();
+  res->view_cols.assign(1, (const double*)res->view_acc_double);
+  res->view_valid.assign(1, nullptr);
 
   res->rows = n_out;
   res->kind = 2;
@@ -1178,6 +1184,7 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->pin_next = 0;
     GMQL_REQUIRE(in != nullptr, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_groups >= 1 && min_acc && max_acc, GMQL_ERR_INVALID, "n_groups >= 1 and per-group thresholds are required");
     const bool force_unified = (flag & GMQL_COVER_FORCE_UNIFIED) != 0;
@@ -1216,6 +1223,8 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     uint64_t G = 0;
     CUDA_TRY(cudaMemcpyAsync(hf, flags.p, sizeof hf, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(&G, spans.coff.p + d.n_chrom, sizeof G, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long* h_span = (unsigned long long*)ctx_pinned(ctx, 8 * (size_t)d.n_chrom);
+    CUDA_TRY(cudaMemcpyAsync(h_span, spans.span.p, 8 * (size_t)d.n_chrom, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     GMQL_REQUIRE(!hf[2], GMQL_ERR_INVALID, "region with chromosome/sample index out of range, start > stop, negative start or bad strand code");
     spans.G = G;
@@ -1225,6 +1234,8 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     bool unified = force_unified || ins.has_star != 0 || d.strand == nullptr || d.n == 0;   // assignGroups (:328-341)
     uint64_t total = (uint64_t)n_groups * (unified ? 1ull : 2ull) * spans.G;
     res = new gmql_result();
+    res->span_hint.resize((size_t)d.n_chrom);
+    for (int c = 0; c < d.n_chrom; ++c) res->span_hint[c] = (int64_t)h_span[c] + 1;   // results may carry the one-base extension
     if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
     else run_cover<uint64_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1277,6 +1288,7 @@ extern "C" int gmql_result_as_regions(gmql_ctx* ctx, gmql_result* r, gmql_region
     view->cols = r->view_cols.data();
     view->valid = r->view_valid.data();
     view->dup_of = nullptr;
+    view->chrom_span_hint = r->span_hint.empty() ? nullptr : r->span_hint.data();
     return GMQL_OK;
   } catch (const gmql_error& ex) {
     ctx->err = ex.what();

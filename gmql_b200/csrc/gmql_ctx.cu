@@ -46,6 +46,7 @@ extern "C" void gmql_ctx_destroy(gmql_ctx* c) {
   if (c->ev_h0) cudaEventDestroy(c->ev_h0);
   if (c->ev_h1) cudaEventDestroy(c->ev_h1);
   if (c->own_stream) cudaStreamDestroy(c->stream);
+  for (auto& pin : c->pins) if (pin.first) cudaFreeHost(pin.first);
   delete c;
 }
 
@@ -119,6 +120,7 @@ void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector
   out->n_chrom = r->n_chrom;
   out->n_samples = r->n_samples;
   out->n_cols = r->n_cols;
+  out->span_hint = r->chrom_span_hint;
   size_t cb = (size_t)(r->coord_bits / 8);
   size_t n = (size_t)r->n;
   GMQL_REQUIRE(r->chrom_bits == 0 || r->chrom_bits == 8 || r->chrom_bits == 16 || r->chrom_bits == 32, GMQL_ERR_INVALID, "chrom_bits must be 0, 8, 16 or 32");
@@ -245,6 +247,7 @@ extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql
     view->cols = d->cols.empty() ? nullptr : d->cols.data();
     view->valid = d->valid.empty() ? nullptr : d->valid.data();
     view->dup_of = d->dev.dup_of;
+    view->chrom_span_hint = host->chrom_span_hint;
     *out = d;
     return GMQL_OK;
   } catch (const gmql_error& ex) {

@@ -499,6 +499,7 @@ extern "C" int gmql_join(gmql_ctx* ctx, const gmql_regions* left, const gmql_reg
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->pin_next = 0;
     GMQL_REQUIRE(left && right, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_pairs >= 0 && (n_pairs == 0 || pairs), GMQL_ERR_INVALID, "bad pair list");
     GMQL_REQUIRE(left->n_chrom == right->n_chrom, GMQL_ERR_INVALID, "left and right must share one chromosome dictionary (n_chrom differs)");

@@ -65,6 +65,10 @@ __global__ void k_sample_keys(const int32_t* __restrict__ sample, int64_t n, int
   }
 }
 
+__global__ void k_iota_rows(uint32_t* __restrict__ p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (uint32_t)i;
+}
+
 // rank of each ref row inside its sample (ascending original row index), for canonical rows of dup groups
 __global__ void k_ref_rank(const uint32_t* __restrict__ rows_by_sample, const uint32_t* __restrict__ keys_sorted, const int64_t* __restrict__ sample_off, int64_t n, uint32_t* __restrict__ rank_of_row) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
@@ -102,15 +106,18 @@ struct alignas(16) RefEntry {
 
 template <typename K>
 __global__ void k_index_entries(const uint32_t* __restrict__ rows, int64_t n, const K* __restrict__ stop, const K* __restrict__ pmax, const int32_t* __restrict__ sample,
-                                const int8_t* __restrict__ strand, const int32_t* __restrict__ dup_of, const uint32_t* __restrict__ rank_of_row, RefEntry<K>* __restrict__ out) {
+                                const int8_t* __restrict__ strand, const int32_t* __restrict__ dup_of, const uint32_t* __restrict__ rank_of_row, int n_samples, int* __restrict__ bad,
+                                RefEntry<K>* __restrict__ out) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     uint32_t row = rows[k];
     uint32_t canon = dup_of ? (uint32_t)dup_of[row] : row;
     RefEntry<K> e;
     e.stop = stop[k];
     e.pmax_prev = k > 0 ? pmax[k - 1] : (K)0;
-    e.rank = rank_of_row[canon];
-    e.meta = ((uint32_t)(sample ? sample[row] : 0) << 2) | (uint32_t)(strand ? strand[row] : (int8_t)0);
+    e.rank = rank_of_row ? rank_of_row[canon] : canon;     // single ref sample: the rank inside the sample is the row itself
+    int sm = sample ? sample[row] : 0;
+    if (sm < 0 || sm >= n_samples) { *bad = 1; sm = 0; }
+    e.meta = ((uint32_t)sm << 2) | (uint32_t)(strand ? strand[row] : (int8_t)0);
     out[k] = e;
   }
 }
@@ -324,53 +331,81 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   const int64_t n_ref = ref.n, n_exp = exp.n;
   const int n_ls = ref.n_samples, n_rs = exp.n_samples;
 
-  // pairs -> device
-  std::vector<int32_t> h_pl((size_t)n_pairs), h_pr((size_t)n_pairs);
+  // pairs -> device (through pinned scratch: truly asynchronous); the single-ref-sample path needs them only for dup marking
+  int32_t* h_pl = (int32_t*)ctx_pinned(ctx, 4 * (size_t)n_pairs);
+  int32_t* h_pr = (int32_t*)ctx_pinned(ctx, 4 * (size_t)n_pairs);
   for (int64_t p = 0; p < n_pairs; ++p) { h_pl[p] = pairs[p].left_sample; h_pr[p] = pairs[p].right_sample; }
   DevBuf<int32_t> d_pl(ctx, n_pairs), d_pr(ctx, n_pairs);
-  if (n_pairs) {
-    CUDA_TRY(cudaMemcpyAsync(d_pl.p, h_pl.data(), 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_pr.p, h_pr.data(), 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_pairs && (n_ls != 1 || ref.dup_of)) {
+    CUDA_TRY(cudaMemcpyAsync(d_pl.p, h_pl, 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_pr.p, h_pr, 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
   }
   cudaEventRecord(ctx->ev_h1, ctx->stream);
 
   DevBuf<int> bad(ctx, 1);
   bad.zero();
 
-  // reference rows grouped by sample (stable: ascending row index inside a sample)
-  DevBuf<uint32_t> sk_a(ctx, n_ref), sk_b(ctx, n_ref), sr_a(ctx, n_ref), sr_b(ctx, n_ref);
-  DevBuf<unsigned int> sample_cnt(ctx, n_ls);
-  sample_cnt.zero();
+  // reference rows grouped by sample (stable: ascending row index inside a sample); rows per pair, row offsets, dense
+  // (ref sample x exp sample) -> first row table
+  DevBuf<uint32_t> sk_a, sk_b, sr_a, sr_b, rank_of_row;
+  DevBuf<unsigned int> sample_cnt;
   DevBuf<int64_t> sample_off(ctx, (int64_t)n_ls + 1);
-  if (n_ref) LAUNCH(ctx, k_sample_keys, grid_for(ctx, n_ref, 256), 256, 0, ref.sample, n_ref, n_ls, sk_a.p, sr_a.p, sample_cnt.p, bad.p);
-  uint32_t* keys_sorted = sk_a.p; uint32_t* rows_by_sample = sr_a.p;
-  radix_sort<uint32_t>(ctx, sk_a.p, sk_b.p, sr_a.p, sr_b.p, n_ref, bits_for((uint64_t)(n_ls - 1)), &keys_sorted, &rows_by_sample);
-  device_scan<unsigned int, int64_t, OpSum<int64_t>, false>(ctx, sample_cnt.p, sample_off.p, n_ls, sample_off.p + n_ls);
-  DevBuf<uint32_t> rank_of_row(ctx, n_ref);
-  if (n_ref) LAUNCH(ctx, k_ref_rank, grid_for(ctx, n_ref, 256), 256, 0, rows_by_sample, keys_sorted, sample_off.p, n_ref, rank_of_row.p);
-
-  // rows per pair, row offsets, dense (ref sample x exp sample) -> first row table
   DevBuf<int64_t> row_off(ctx, n_pairs + 1);
   DevBuf<long long> pair_base(ctx, (int64_t)n_ls * n_rs);
-  pair_base.fill_byte(0xff);
-  if (n_pairs) {
-    LAUNCH(ctx, k_pair_rows, grid_for(ctx, n_pairs, 256), 256, 0, d_pl.p, d_pr.p, n_pairs, n_ls, n_rs, sample_cnt.p, row_off.p, bad.p);
-    device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, row_off.p, row_off.p, n_pairs, row_off.p + n_pairs);
-  } else {
-    row_off.zero();
-  }
+  uint32_t* keys_sorted = nullptr; uint32_t* rows_by_sample = nullptr;
   int64_t n_rows = 0;
   int h_bad = 0;
-  CUDA_TRY(cudaMemcpyAsync(&n_rows, row_off.p + n_pairs, sizeof n_rows, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "sample index out of range (regions or pair list)");
-  if (n_pairs) LAUNCH(ctx, k_pair_base, grid_for(ctx, n_pairs, 256), 256, 0, d_pl.p, d_pr.p, n_pairs, n_rs, row_off.p, pair_base.p, bad.p);
+  const bool single = n_ls == 1;
+  if (single) {
+    // one reference sample (MAP onto a COVER result, an annotation, ...): every table is known on the host; nothing to
+    // sort, no host round trip.  Sample indices of the rows are validated by k_index_entries.
+    sr_a.alloc(ctx, n_ref);
+    rows_by_sample = sr_a.p;
+    if (n_ref) LAUNCH(ctx, k_iota_rows, grid_for(ctx, n_ref, 256), 256, 0, sr_a.p, n_ref);
+    int64_t* h_so = (int64_t*)ctx_pinned(ctx, 16);
+    h_so[0] = 0; h_so[1] = n_ref;
+    CUDA_TRY(cudaMemcpyAsync(sample_off.p, h_so, 16, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t* h_ro = (int64_t*)ctx_pinned(ctx, 8 * ((size_t)n_pairs + 1));
+    long long* h_pb = (long long*)ctx_pinned(ctx, 8 * (size_t)n_rs);
+    for (int b = 0; b < n_rs; ++b) h_pb[b] = -1ll;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+      GMQL_REQUIRE(h_pl[p] == 0 && h_pr[p] >= 0 && h_pr[p] < n_rs, GMQL_ERR_INVALID, "sample index out of range (regions or pair list)");
+      GMQL_REQUIRE(h_pb[h_pr[p]] < 0, GMQL_ERR_INVALID, "the same (ref sample, exp sample) pair is listed twice");
+      h_ro[p] = p * n_ref;
+      h_pb[h_pr[p]] = (long long)(p * n_ref);
+    }
+    h_ro[n_pairs] = n_pairs * n_ref;
+    CUDA_TRY(cudaMemcpyAsync(row_off.p, h_ro, 8 * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(pair_base.p, h_pb, 8 * (size_t)n_rs, cudaMemcpyHostToDevice, ctx->stream));
+    n_rows = n_pairs * n_ref;
+  } else {
+    sk_a.alloc(ctx, n_ref); sk_b.alloc(ctx, n_ref); sr_a.alloc(ctx, n_ref); sr_b.alloc(ctx, n_ref);
+    sample_cnt.alloc(ctx, n_ls);
+    sample_cnt.zero();
+    if (n_ref) LAUNCH(ctx, k_sample_keys, grid_for(ctx, n_ref, 256), 256, 0, ref.sample, n_ref, n_ls, sk_a.p, sr_a.p, sample_cnt.p, bad.p);
+    keys_sorted = sk_a.p; rows_by_sample = sr_a.p;
+    radix_sort<uint32_t>(ctx, sk_a.p, sk_b.p, sr_a.p, sr_b.p, n_ref, bits_for((uint64_t)(n_ls - 1)), &keys_sorted, &rows_by_sample);
+    device_scan<unsigned int, int64_t, OpSum<int64_t>, false>(ctx, sample_cnt.p, sample_off.p, n_ls, sample_off.p + n_ls);
+    rank_of_row.alloc(ctx, n_ref);
+    if (n_ref) LAUNCH(ctx, k_ref_rank, grid_for(ctx, n_ref, 256), 256, 0, rows_by_sample, keys_sorted, sample_off.p, n_ref, rank_of_row.p);
+    pair_base.fill_byte(0xff);
+    if (n_pairs) {
+      LAUNCH(ctx, k_pair_rows, grid_for(ctx, n_pairs, 256), 256, 0, d_pl.p, d_pr.p, n_pairs, n_ls, n_rs, sample_cnt.p, row_off.p, bad.p);
+      device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, row_off.p, row_off.p, n_pairs, row_off.p + n_pairs);
+    } else {
+      row_off.zero();
+    }
+    CUDA_TRY(cudaMemcpyAsync(&n_rows, row_off.p + n_pairs, sizeof n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "sample index out of range (regions or pair list)");
+    if (n_pairs) LAUNCH(ctx, k_pair_base, grid_for(ctx, n_pairs, 256), 256, 0, d_pl.p, d_pr.p, n_pairs, n_rs, row_off.p, pair_base.p, bad.p);
+  }
 
   // interval index over the reference
   LinMap lm = spans.map();
   IntervalIndex<K> ix;
-  build_index<K>(ctx, ref, nullptr, 1, lm, &ix);
+  build_index<K>(ctx, ref, nullptr, 1, lm, &ix, false, ref.span_hint ? bad.p : (int*)nullptr);
   // bucket table, resident in the streaming kernel's shared memory: as fine as fits (most buckets then hold no start
   // and a query needs no search at all), at least 2^10 buckets
   int tbl_shift = 0;
@@ -382,7 +417,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   DevBuf<uint32_t> tbl(ctx, n_buckets + 2);
   LAUNCH(ctx, (k_bucket_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, n_ref, tbl_shift, n_buckets, tbl.p);
   DevBuf<RefEntry<K>> entries(ctx, n_ref);
-  if (n_ref) LAUNCH(ctx, (k_index_entries<K>), grid_for(ctx, n_ref, 256), 256, 0, ix.row, n_ref, ix.stop.p, ix.pmax.p, ref.sample, ref.strand, ref.dup_of, rank_of_row.p, entries.p);
+  if (n_ref) LAUNCH(ctx, (k_index_entries<K>), grid_for(ctx, n_ref, 256), 256, 0, ix.row, n_ref, ix.stop.p, ix.pmax.p, ref.sample, ref.strand, ref.dup_of, single ? (const uint32_t*)nullptr : rank_of_row.p, n_ls, bad.p, entries.p);
 
   // accumulators
   MapAcc acc;
@@ -436,7 +471,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   GMQL_REQUIRE(h_bad != 2, GMQL_ERR_INVALID, "the same (ref sample, exp sample) pair is listed twice");
-  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "experiment region with chromosome/sample index out of range or negative start");
+  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "region with chromosome/sample index out of range, negative start, or reference region beyond its chrom_span_hint");
 
   res->rows = n_rows;
   res->kind = 1;
@@ -464,6 +499,7 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->pin_next = 0;
     GMQL_REQUIRE(ref && exp, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_pairs >= 0 && (n_pairs == 0 || pairs), GMQL_ERR_INVALID, "bad pair list");
     GMQL_REQUIRE(ref->n_chrom == exp->n_chrom, GMQL_ERR_INVALID, "ref and exp must share one chromosome dictionary (n_chrom differs)");
@@ -476,7 +512,8 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
     gmql_upload_regions(ctx, exp, need_cols, &dexp);
     SpanTable spans;
     cudaEventRecord(ctx->ev_k0, ctx->stream);
-    build_span_table(ctx, &dref, nullptr, &spans);
+    if (dref.span_hint) span_table_from_hint(ctx, dref.span_hint, dref.n_chrom, &spans);
+    else build_span_table(ctx, &dref, nullptr, &spans);
     res = new gmql_result();
     if (spans.G < 0xffffffffull) run_map<uint32_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
     else run_map<uint64_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);

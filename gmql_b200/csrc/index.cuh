@@ -86,6 +86,27 @@ static void build_span_table(gmql_ctx* ctx, const DevRegions* a, const DevRegion
   t->G = G;
 }
 
+// span table from a caller-supplied upper bound per chromosome: no pass over the data, no host round trip.  Regions beyond
+// their bound must be detected by the consumer (k_index_stops' `bad`).
+static void span_table_from_hint(gmql_ctx* ctx, const int64_t* hint, int n_chrom, SpanTable* t, unsigned long long pad = 2ull) {
+  t->n_chrom = n_chrom;
+  t->span.alloc(ctx, n_chrom);
+  t->coff.alloc(ctx, n_chrom + 1);
+  t->bad.alloc(ctx, 1);
+  t->bad.zero();
+  unsigned long long* hs = (unsigned long long*)ctx_pinned(ctx, sizeof(unsigned long long) * (size_t)n_chrom);
+  uint64_t* hc = (uint64_t*)ctx_pinned(ctx, sizeof(uint64_t) * ((size_t)n_chrom + 1));
+  uint64_t run = 0;
+  for (int c = 0; c < n_chrom; ++c) {
+    GMQL_REQUIRE(hint[c] >= 0, GMQL_ERR_INVALID, "negative chrom_span_hint");
+    hs[c] = (unsigned long long)hint[c]; hc[c] = run; run += hs[c] + pad;
+  }
+  hc[n_chrom] = run;
+  CUDA_TRY(cudaMemcpyAsync(t->span.p, hs, sizeof(unsigned long long) * (size_t)n_chrom, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(t->coff.p, hc, sizeof(uint64_t) * ((size_t)n_chrom + 1), cudaMemcpyHostToDevice, ctx->stream));
+  t->G = run;
+}
+
 template <typename K>
 struct IntervalIndex {
   int64_t n = 0;
@@ -116,13 +137,17 @@ __global__ void k_index_stops_from_len(const K* __restrict__ starts, const uint3
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) out[k] = starts[k] + (K)lens[k];
 }
 
+// bad (optional): set when a region lies outside its chromosome's span (span tables built from a caller's hint)
 template <typename K>
 __global__ void k_index_stops(const int32_t* __restrict__ chrom, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ blocks,
-                              int64_t n, LinMap lm, const uint32_t* __restrict__ rows, K* __restrict__ out) {
+                              int64_t n, LinMap lm, const uint32_t* __restrict__ rows, K* __restrict__ out, int* __restrict__ bad) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     uint32_t i = rows[k];
     uint64_t blk = blocks ? blocks[i] : 0u;
-    out[k] = (K)(blk * lm.G + lm.coff[chrom[i]] + (uint64_t)ld_coord(stop, bits, i));
+    int c = chrom[i];
+    int64_t e = ld_coord(stop, bits, i);
+    if (bad && (c < 0 || c >= lm.n_chrom || e < 0 || e > lm.span[c])) { *bad = 1; c = 0; e = 0; }
+    out[k] = (K)(blk * lm.G + lm.coff[c] + (uint64_t)e);
   }
 }
 
@@ -145,22 +170,22 @@ static void alloc_index(gmql_ctx* ctx, int64_t n, IntervalIndex<K>* ix) {
 
 // start_a / row_a hold the unsorted keys and payloads (row, or length when payload_len): sort, derive stops, running max
 template <typename K>
-static void finish_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix, bool payload_len) {
+static void finish_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix, bool payload_len, int* bad = nullptr) {
   int64_t n = ix->n;
   if (n == 0) return;
   int g = grid_for(ctx, n, 256);
   uint64_t max_lin = n_blocks * lm.G;
   radix_sort<K>(ctx, ix->start_a.p, ix->start_b.p, ix->row_a.p, ix->row_b.p, n, bits_for(max_lin), &ix->start, &ix->row);
   if (payload_len) LAUNCH(ctx, (k_index_stops_from_len<K>), g, 256, 0, ix->start, ix->row, n, ix->stop.p);
-  else LAUNCH(ctx, (k_index_stops<K>), g, 256, 0, r.chrom, r.stop, r.coord_bits, blocks, n, lm, ix->row, ix->stop.p);
+  else LAUNCH(ctx, (k_index_stops<K>), g, 256, 0, r.chrom, r.stop, r.coord_bits, blocks, n, lm, ix->row, ix->stop.p, bad);
   device_scan<K, K, OpMax<K>, true>(ctx, ix->stop.p, ix->pmax.p, n, (K*)nullptr);
 }
 
 template <typename K>
-static void build_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix, bool payload_len = false) {
+static void build_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blocks, uint64_t n_blocks, const LinMap& lm, IntervalIndex<K>* ix, bool payload_len = false, int* bad = nullptr) {
   alloc_index<K>(ctx, r.n, ix);
   if (r.n == 0) return;
   // payload_len requires region lengths < 2^32 (checked by the caller through the span table)
   LAUNCH(ctx, (k_index_keys<K>), grid_for(ctx, r.n, 256), 256, 0, r.chrom, r.start, payload_len ? r.stop : (const void*)nullptr, r.coord_bits, blocks, r.n, lm, ix->start_a.p, ix->row_a.p);
-  finish_index<K>(ctx, r, blocks, n_blocks, lm, ix, payload_len);
+  finish_index<K>(ctx, r, blocks, n_blocks, lm, ix, payload_len, bad);
 }

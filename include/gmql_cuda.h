@@ -85,6 +85,11 @@ typedef struct {
   const int64_t* sample_offsets;/* HOST array [n_samples+1], used when sample == NULL: rows [off[s], off[s+1]) belong to
                                    sample s (regions arrive one sample file after the other, Loaders.scala:203-208);
                                    off[0] = 0, off[n_samples] = n, non-decreasing */
+  const int64_t* chrom_span_hint;/* HOST array [n_chrom] or NULL: an upper bound of `stop` per chromosome (e.g. the
+                                   assembly's chromosome sizes).  Lets gmql_map / gmql_join lay out the linear coordinate
+                                   without a pass over the data and a host round trip; a region beyond its bound is an
+                                   error (GMQL_ERR_INVALID), never a wrong result.  Views made by gmql_result_as_regions
+                                   carry it. */
 } gmql_regions;
 
 /* aggregates: DefaultRegionsToRegionFactory (GMQL-Server/.../DefaultRegionsToRegionFactory.scala:13-31),
