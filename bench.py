@@ -280,6 +280,12 @@ def run_ours(args):
         alg_launch = 9.0 * n_in
         achieved = alg_launch / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
         step_bytes = c5_algorithmic_bytes(tot_in, tot_cover, n_samples)
+        traffic = None
+        try:   # DRAM bytes per launch of that kernel from the committed ncu capture of this workload (N = 1 only)
+            if world == 1 and n_samples == 2000 and n_regions == 50000:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernel_traffic.json"))).get(top[0])
+        except (OSError, ValueError):
+            traffic = None
         out = {
             "metric": "MAP/COVER/JOIN input regions/s at 1/2/4/8 B200 vs GMQL-Spark local[N] on host",
             "value": tot_in / (ms_dev_max * 1e-3),
@@ -296,7 +302,7 @@ def run_ours(args):
             "gpu_launches": int(tot_launch),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "launches_per_step": top[1], "ms_per_launch": top_ms,
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_launch},
             "roofline_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_dev_max * 1e-3) / 1e9 / world,
                               "frac_per_gpu": step_bytes / (ms_dev_max * 1e-3) / 1e9 / world / peak},

@@ -151,6 +151,7 @@ struct MapStreamArgs {
   const long long* pair_base; int* bad;
   const uint32_t* tbl; int tbl_shift; int n_tbl;   // n_tbl = entries of tbl (buckets + 2)
   int vec_ok;                                        // column pointers are 16-byte aligned
+  uint8_t* hit; int exact;                           // DIFFERENCE: per reference row "some paired experiment region overlaps it"
 };
 
 template <typename K>
@@ -170,7 +171,8 @@ __device__ __forceinline__ void map_hit(const MapStreamArgs<K>& a, const MapAggP
   }
 }
 
-template <typename K>
+// DIFF: instead of accumulating, mark the reference row (GenometricDifference.scala:58-69; `exact`: identical coordinates)
+template <typename K, bool DIFF>
 __global__ void __launch_bounds__(MS_THREADS, 1) k_map_stream(MapStreamArgs<K> a, MapAggPlan plan, ExpCols ec, MapAcc acc) {
   extern __shared__ uint32_t s_tbl[];                   // [n_tbl] bucket table, then chromosome offsets / spans
   const bool chrom_sh = a.lm.n_chrom <= MS_MAX_CHROM;
@@ -208,21 +210,23 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_stream(MapStreamArgs<K> a
       }
     }
     // ---- candidate range of every region: hi = number of reference entries with start < region.stop
-    K ls[MS_PER];
+    K ls[MS_PER], lee[MS_PER];
     int hi[MS_PER];
 #pragma unroll
     for (int j = 0; j < MS_PER; ++j) {
-      hi[j] = 0; ls[j] = 0;
+      hi[j] = 0; ls[j] = 0; lee[j] = 0;
       if (c[j] == -2) continue;
       if (c[j] < 0 || c[j] >= a.lm.n_chrom) { *a.bad = 1; continue; }
       int64_t sp = span[c[j]];
       if (s[j] >= sp || e[j] <= 0) continue;            // no reference region can satisfy r.start < e.stop && e.start < r.stop
       if (s[j] < 0) { *a.bad = 1; continue; }
-      if (e[j] > sp + 1) e[j] = sp + 1;
+      const bool clamped = e[j] > sp + 1;
+      if (clamped) e[j] = sp + 1;
       if (smp[j] < 0 || smp[j] >= a.n_exp_samples) { *a.bad = 1; continue; }
       uint64_t co = coff[c[j]];
       ls[j] = (K)(co + (uint64_t)s[j]);
       K le = (K)(co + (uint64_t)e[j]);
+      lee[j] = clamped ? (K)0 : le;                     // a clamped stop equals no reference stop
       uint64_t b = (uint64_t)le >> a.tbl_shift;
       int lo2 = (int)s_tbl[b], hi2 = (int)s_tbl[b + 1];
       while (lo2 < hi2) { int mid = (lo2 + hi2) >> 1; if (a.r_start[mid] < le) lo2 = mid + 1; else hi2 = mid; }
@@ -238,7 +242,12 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_stream(MapStreamArgs<K> a
       int k = hi[j] - 1;
       RefEntry<K> en = ent[j];
       while (true) {
-        if (en.stop > ls[j]) map_hit<K>(a, plan, ec, acc, en, smp[j], st[j], i0 + j);
+        if (en.stop > ls[j]) {
+          if (!DIFF) map_hit<K>(a, plan, ec, acc, en, smp[j], st[j], i0 + j);
+          else if (strand_ok((int)(en.meta & 3u), st[j]) && a.pair_base[(int64_t)(en.meta >> 2) * a.n_exp_samples + smp[j]] >= 0 &&
+                   (!a.exact || (en.stop == lee[j] && a.r_start[k] == ls[j])))
+            a.hit[en.rank] = 1;
+        }
         if (k == 0 || en.pmax_prev <= ls[j]) break;
         --k;
         en = a.entries[k];
@@ -449,9 +458,10 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
     ma.vec_ok = al16(exp.chrom) && al16(exp.start) && al16(exp.stop) && al16(exp.sample) && ((uintptr_t)exp.strand & 3u) == 0;
     size_t sh = sizeof(uint32_t) * (size_t)((ma.n_tbl + 3) & ~3) + (lm.n_chrom <= MS_MAX_CHROM ? 16 * (size_t)lm.n_chrom : 0);
-    CUDA_TRY(cudaFuncSetAttribute(k_map_stream<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    CUDA_TRY(cudaFuncSetAttribute((k_map_stream<K, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     int g = (int)std::min<int64_t>(ceil_div64(n_exp, (int64_t)MS_THREADS * MS_PER), (int64_t)ctx->num_sms);
-    LAUNCH(ctx, (k_map_stream<K>), g, MS_THREADS, sh, ma, plan, ec, acc);
+    ma.hit = nullptr; ma.exact = 0;
+    LAUNCH(ctx, (k_map_stream<K, false>), g, MS_THREADS, sh, ma, plan, ec, acc);
   }
   if (ref.dup_of && n_pairs && n_rows)
     LAUNCH(ctx, k_mark_dups, (int)std::min<int64_t>(n_pairs, (int64_t)ctx->num_sms * 8), 128, 0, d_pl.p, row_off.p, n_pairs, sample_off.p, rows_by_sample, ref.dup_of, count.p);
@@ -490,6 +500,98 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   }
 }
 
+// ---- DIFFERENCE ------------------------------------------------------------------------------------
+__global__ void k_diff_keep(const int32_t* __restrict__ sample, const int32_t* __restrict__ dup_of, const uint8_t* __restrict__ has_group, const uint8_t* __restrict__ hit,
+                            int64_t n, int n_samples, int32_t* __restrict__ keep, int* __restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int sm = sample ? sample[i] : 0;
+    if (sm < 0 || sm >= n_samples) { *bad = 1; keep[i] = 0; continue; }
+    // identical records of one sample collapse into one output record (the reduce key is the record's content,
+    // GenometricDifference.scala:54,79-81): only the canonical row can be emitted, and it carries every duplicate's hits
+    bool canon = !dup_of || dup_of[i] == (int32_t)i;
+    keep[i] = (canon && has_group[sm] && !hit[i]) ? 1 : 0;
+  }
+}
+
+__global__ void k_diff_compact(const int32_t* __restrict__ keep, const int64_t* __restrict__ excl, int64_t n, int32_t* __restrict__ rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (keep[i]) rows[excl[i]] = (int32_t)i;
+}
+
+template <typename K>
+static void run_difference(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp, const gmql_pair* pairs, int64_t n_pairs, int exact,
+                           const SpanTable& spans, gmql_result* res) {
+  const int64_t n_ref = ref.n, n_exp = exp.n;
+  const int n_ls = ref.n_samples, n_rs = exp.n_samples;
+  DevBuf<int> bad(ctx, 1);
+  bad.zero();
+  // pair table and "sample has a group" flags, built on the host
+  long long* h_pb = (long long*)ctx_pinned(ctx, 8 * (size_t)n_ls * (size_t)n_rs);
+  uint8_t* h_hg = (uint8_t*)ctx_pinned(ctx, (size_t)n_ls);
+  for (int64_t q = 0; q < (int64_t)n_ls * n_rs; ++q) h_pb[q] = -1ll;
+  memset(h_hg, 0, (size_t)n_ls);
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    int a = pairs[p].left_sample, b = pairs[p].right_sample;
+    GMQL_REQUIRE(a >= 0 && a < n_ls && b >= 0 && b < n_rs, GMQL_ERR_INVALID, "sample index out of range in the pair list");
+    h_pb[(int64_t)a * n_rs + b] = 0;
+    h_hg[a] = 1;
+  }
+  DevBuf<long long> pair_base(ctx, (int64_t)n_ls * n_rs);
+  DevBuf<uint8_t> has_group(ctx, n_ls), hit(ctx, n_ref);
+  CUDA_TRY(cudaMemcpyAsync(pair_base.p, h_pb, 8 * (size_t)n_ls * (size_t)n_rs, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(has_group.p, h_hg, (size_t)n_ls, cudaMemcpyHostToDevice, ctx->stream));
+  hit.zero();
+  cudaEventRecord(ctx->ev_h1, ctx->stream);
+
+  LinMap lm = spans.map();
+  IntervalIndex<K> ix;
+  build_index<K>(ctx, ref, nullptr, 1, lm, &ix, false, ref.span_hint ? bad.p : (int*)nullptr);
+  int tbl_shift = 0;
+  {
+    int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)MS_MAX_TBL - 2, 16 * std::max<int64_t>(n_ref, 1)));
+    while (tbl_shift < 62 && (int64_t)(lm.G >> tbl_shift) + 2 > want) ++tbl_shift;
+  }
+  int64_t n_buckets = (int64_t)(lm.G >> tbl_shift) + 1;
+  DevBuf<uint32_t> tbl(ctx, n_buckets + 2);
+  LAUNCH(ctx, (k_bucket_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, n_ref, tbl_shift, n_buckets, tbl.p);
+  DevBuf<RefEntry<K>> entries(ctx, n_ref);
+  if (n_ref) LAUNCH(ctx, (k_index_entries<K>), grid_for(ctx, n_ref, 256), 256, 0, ix.row, n_ref, ix.stop.p, ix.pmax.p, ref.sample, ref.strand, ref.dup_of, (const uint32_t*)nullptr, n_ls, bad.p, entries.p);
+  if (n_exp && n_ref && n_pairs) {
+    MapStreamArgs<K> ma;
+    ma.e_chrom = exp.chrom; ma.e_start = exp.start; ma.e_stop = exp.stop; ma.e_bits = exp.coord_bits;
+    ma.e_strand = exp.strand; ma.e_sample = exp.sample; ma.n_exp = n_exp; ma.n_exp_samples = n_rs;
+    ma.lm = lm; ma.r_start = ix.start; ma.entries = entries.p; ma.n_ref = n_ref;
+    ma.pair_base = pair_base.p; ma.bad = bad.p;
+    ma.tbl = tbl.p; ma.tbl_shift = tbl_shift; ma.n_tbl = (int)(n_buckets + 2);
+    auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
+    ma.vec_ok = al16(exp.chrom) && al16(exp.start) && al16(exp.stop) && al16(exp.sample) && ((uintptr_t)exp.strand & 3u) == 0;
+    ma.hit = hit.p; ma.exact = exact;
+    size_t sh = sizeof(uint32_t) * (size_t)((ma.n_tbl + 3) & ~3) + (lm.n_chrom <= MS_MAX_CHROM ? 16 * (size_t)lm.n_chrom : 0);
+    CUDA_TRY(cudaFuncSetAttribute((k_map_stream<K, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    int g = (int)std::min<int64_t>(ceil_div64(n_exp, (int64_t)MS_THREADS * MS_PER), (int64_t)ctx->num_sms);
+    MapAggPlan plan = MapAggPlan();
+    ExpCols ec; memset(&ec, 0, sizeof ec);
+    MapAcc acc; memset(&acc, 0, sizeof acc);
+    LAUNCH(ctx, (k_map_stream<K, true>), g, MS_THREADS, sh, ma, plan, ec, acc);
+  }
+  DevBuf<int32_t> keep(ctx, n_ref);
+  DevBuf<int64_t> excl(ctx, n_ref + 1);
+  if (n_ref) LAUNCH(ctx, k_diff_keep, grid_for(ctx, n_ref, 256), 256, 0, ref.sample, ref.dup_of, has_group.p, hit.p, n_ref, n_ls, keep.p, bad.p);
+  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, keep.p, excl.p, n_ref, excl.p + n_ref);
+  int64_t n_out = 0;
+  int h_bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n_out, excl.p + n_ref, sizeof n_out, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "region with chromosome/sample index out of range, negative start, or reference region beyond its chrom_span_hint");
+  DevBuf<int32_t> rows(ctx, n_out);
+  if (n_ref && n_out) LAUNCH(ctx, k_diff_compact, grid_for(ctx, n_ref, 256), 256, 0, keep.p, excl.p, n_ref, rows.p);
+  cudaEventRecord(ctx->ev_k1, ctx->stream);
+  res->rows = n_out;
+  res->kind = 4;
+  result_add(res, GMQL_COL_DIFF_REF_ROW, rows);
+}
+
 }  // namespace
 
 extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp, const gmql_pair* pairs, int64_t n_pairs,
@@ -517,6 +619,43 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
     res = new gmql_result();
     if (spans.G < 0xffffffffull) run_map<uint32_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
     else run_map<uint64_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = res;
+    return GMQL_OK;
+  } catch (const gmql_error& ex) {
+    ctx->err = ex.what();
+    if (res) gmql_result_free(ctx, res);
+    cudaStreamSynchronize(ctx->stream);
+    return ex.code;
+  } catch (const std::exception& ex) {
+    ctx->err = ex.what();
+    if (res) gmql_result_free(ctx, res);
+    return GMQL_ERR_INVALID;
+  }
+}
+
+extern "C" int gmql_difference(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp, const gmql_pair* pairs, int64_t n_pairs,
+                               int32_t exact, gmql_result** out) {
+  if (!ctx || !out) return GMQL_ERR_INVALID;
+  *out = nullptr;
+  gmql_result* res = nullptr;
+  try {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->pin_next = 0;
+    GMQL_REQUIRE(ref && exp, GMQL_ERR_INVALID, "null dataset");
+    GMQL_REQUIRE(n_pairs >= 0 && (n_pairs == 0 || pairs), GMQL_ERR_INVALID, "bad pair list");
+    GMQL_REQUIRE(ref->n_chrom == exp->n_chrom, GMQL_ERR_INVALID, "ref and exp must share one chromosome dictionary (n_chrom differs)");
+    cudaEventRecord(ctx->ev_h0, ctx->stream);
+    DevRegions dref, dexp;
+    gmql_upload_regions(ctx, ref, std::vector<int>(), &dref);
+    gmql_upload_regions(ctx, exp, std::vector<int>(), &dexp);
+    SpanTable spans;
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    if (dref.span_hint) span_table_from_hint(ctx, dref.span_hint, dref.n_chrom, &spans);
+    else build_span_table(ctx, &dref, nullptr, &spans);
+    res = new gmql_result();
+    if (spans.G < 0xffffffffull) run_difference<uint32_t>(ctx, dref, dexp, pairs, n_pairs, exact != 0, spans, res);
+    else run_difference<uint64_t>(ctx, dref, dexp, pairs, n_pairs, exact != 0, spans, res);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     *out = res;
     return GMQL_OK;

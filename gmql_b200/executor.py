@@ -168,6 +168,29 @@ class GMQLCudaExecutor:
                 out.append((new_id, rec[1], rec[2], rec[3], rec[4], tuple(rec[5]) + (float(c),) + aggs))
         return out
 
+    # ---- DIFFERENCE ---------------------------------------------------------------------------------------------------------
+    def GenometricDifference(self, grouping, leftDataset, rightDataset, exact=False):
+        """DIFFERENCE (GenometricDifference.apply, RegionsOperators/GenometricDifference.scala:23).  grouping: list of
+        (left_sample_id, right_sample_id) pairs (implement_mjd flattened) or None for all pairs.  Returns the surviving
+        left records as (md5(left sample id), chrom, start, stop, strand, values)."""
+        from .ids import long_id
+        if grouping is None:
+            grouping = [(int(a), int(b)) for a in leftDataset.sample_ids for b in rightDataset.sample_ids]
+        names = sorted(set(leftDataset.chrom_names) | set(rightDataset.chrom_names))
+        ref = leftDataset.with_chrom_names(names)
+        exp = rightDataset.with_chrom_names(names)
+        c_ref, k1 = ref.as_c(dup_of=ref.dup_of(), narrow=self.narrow)
+        c_exp, k2 = exp.as_c(narrow=self.narrow)
+        c_pairs, used = self._c_pairs(grouping, ref, exp)
+        out = C.c_void_p()
+        self._check(self.lib.gmql_difference(self.ctx, C.byref(c_ref), C.byref(c_exp), c_pairs, len(used), 1 if exact else 0, C.byref(out)))
+        del k1, k2
+        res = _Result(self, out)
+        rows = res.column(L.COL_DIFF_REF_ROW, np.int32)
+        res.free()
+        recs = ref.to_records()
+        return [(long_id(recs[i][0]), recs[i][1], recs[i][2], recs[i][3], recs[i][4], tuple(recs[i][5])) for i in rows]
+
     # ---- COVER ------------------------------------------------------------------------------------------------------------
     def cover_raw(self, coverFlag, min, max, aggregators, groups, ds, force_unified=False):
         c_ds, keep = ds.as_c(narrow=self.narrow)

@@ -9,6 +9,11 @@ def pair_id(left_id: int, right_id: int) -> int:
     return int.from_bytes(hashlib.md5(struct.pack("<qq", left_id, right_id)).digest()[:8], "little", signed=True)
 
 
+def long_id(v: int) -> int:
+    """md5.putLong(v).asLong — GenometricDifference.scala:53 (output sample id of DIFFERENCE)."""
+    return int.from_bytes(hashlib.md5(struct.pack("<q", v)).digest()[:8], "little", signed=True)
+
+
 def string_id(s: str) -> int:
     return int.from_bytes(hashlib.md5(s.encode("utf-8")).digest()[:8], "little", signed=True)
 

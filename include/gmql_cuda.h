@@ -207,6 +207,21 @@ int gmql_join(gmql_ctx* ctx, const gmql_regions* left, const gmql_regions* right
               const int64_t* left_eq, const int64_t* right_eq,
               gmql_result** out);
 
+/* ---- DIFFERENCE ------------------------------------------------------------------------
+ * Replaces GenometricDifference.apply (RegionsOperators/GenometricDifference.scala:23-100; dispatch
+ * GMQLSparkExecutor.scala:278, IRDifferenceRD(meta_join, left, right, exact)).  A reference region survives when
+ * no region of ANY experiment sample paired with its sample overlaps it (r.start < e.stop, e.start < r.stop, strands
+ * compatible; exact != 0: with identical coordinates as well, :67).  Regions of reference samples that appear in no
+ * pair produce nothing (:104-114); identical records of one reference sample collapse into one output record (the
+ * reduce key is the record's content, :54) — pass dup_of as for gmql_map.  The fixed 50 000-base binning (:19) is not
+ * observable in the result.
+ *
+ * Result: GMQL_COL_DIFF_REF_ROW int32 [rows] — surviving rows of `ref`, ascending.  Output sample id =
+ * md5(ref sample id) (:53), derived on the host.
+ */
+int gmql_difference(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp,
+                    const gmql_pair* pairs, int64_t n_pairs, int32_t exact, gmql_result** out);
+
 /* ---- results --------------------------------------------------------------------------- */
 enum {
   GMQL_COL_MAP_ROW_OFFSETS = 1, GMQL_COL_MAP_REF_ROW = 2, GMQL_COL_MAP_REF_SAMPLE_OFFSETS = 3, GMQL_COL_MAP_COUNT = 4,
@@ -215,6 +230,7 @@ enum {
   GMQL_COL_COV_STRAND = 20, GMQL_COL_COV_ACC = 21, GMQL_COL_COV_JACC_INTERSECT = 22, GMQL_COL_COV_JACC_RESULT = 23,
   GMQL_COL_JOIN_LEFT_ROW = 32, GMQL_COL_JOIN_RIGHT_ROW = 33, GMQL_COL_JOIN_PAIR = 34, GMQL_COL_JOIN_START = 35,
   GMQL_COL_JOIN_STOP = 36, GMQL_COL_JOIN_STRAND = 37, GMQL_COL_JOIN_CHROM = 38,
+  GMQL_COL_DIFF_REF_ROW = 48,
   GMQL_COL_AGG_VALUE = 256, /* + aggregate index */
   GMQL_COL_AGG_VALID = 512  /* + aggregate index */
 };

@@ -320,6 +320,67 @@ def map_direct(ref, exp, pairs, aggs):
 INT_MAX = 2 ** 31 - 1
 
 
+def md5_long_id(v: int) -> int:
+    """Hashing.md5().newHasher().putLong(v).hash().asLong() (GenometricDifference.scala:53)."""
+    return int.from_bytes(hashlib.md5(struct.pack("<q", v)).digest()[:8], "little", signed=True)
+
+
+def difference_reference(ref, exp, groups, exact=False, bin_size=50000):
+    """GenometricDifference.apply (RegionsOperators/GenometricDifference.scala:23-100), restated line by line.
+    `groups`: dict ref_sample_id -> list of exp sample ids (implement_mjd, :33-34).  A reference region survives when no
+    region of ANY of its paired experiment samples overlaps it (strictly, strand-compatible; `exact`: with identical
+    coordinates, :67).  Reference regions of a sample without a group entry (or with an empty one) produce nothing
+    (binRefDS :104-114); identical reference records of one sample collapse into one output record (the reduce key
+    :54 is built from the record's content; here the tuple itself stands for the md5 of the unseparated string
+    concatenation, whose accidental aliasing is not reproduced).  Output id = md5(ref sample id) (:53)."""
+    ref_binned = defaultdict(list)                       # binRefDS (:102-114); the .distinct (:37) cannot collapse
+    for (sid, chrom, start, stop, strand, vals) in ref:   # records: Array[GValue] has reference equality
+        grp = groups.get(sid)
+        if grp is None:
+            continue
+        for b in range(start // bin_size, stop // bin_size + 1):
+            for exp_id in grp:
+                ref_binned[(exp_id, chrom, b)].append((sid, start, stop, strand, tuple(vals)))
+    exp_binned = defaultdict(list)                       # binExpDS (:116-122)
+    for (sid, chrom, start, stop, strand, vals) in exp:
+        for b in range(start // bin_size, stop // bin_size + 1):
+            exp_binned[(sid, chrom, b)].append((start, stop, strand))
+    reduced = {}                                         # cogroup (:44-72) + reduceByKey (:79-81)
+    for key, refs in ref_binned.items():
+        exps = exp_binned.get(key, ())
+        for (sid, rstart, rstop, rstrand, rvals) in refs:
+            count = 0
+            for (estart, estop, estrand) in exps:
+                if ((rstart < estop and estart < rstop) and _strand_ok(rstrand, estrand)
+                        and ((rstart // bin_size) == key[2] or (estart // bin_size) == key[2])):
+                    if (not exact) or (rstart == estart and rstop == estop):
+                        count += 1
+            agg_key = (md5_long_id(sid), key[1], rstart, rstop, rstrand, rvals)
+            reduced[agg_key] = reduced.get(agg_key, 0) + count
+    return [(k[0], k[1], k[2], k[3], k[4], k[5]) for k, c in reduced.items() if c == 0]     # :83-88
+
+
+def difference_direct(ref, exp, groups, exact=False):
+    """Bin-free form of DIFFERENCE: the set of distinct reference records (of samples with a non-empty group) that no
+    region of a paired experiment sample overlaps."""
+    exp_by = defaultdict(list)
+    for e in exp:
+        exp_by[(e[0], e[1])].append(e)
+    out = {}
+    for (sid, chrom, start, stop, strand, vals) in ref:
+        grp = groups.get(sid)
+        if not grp:
+            continue
+        hit = False
+        for exp_id in grp:
+            for (_s, _c, estart, estop, estrand, _v) in exp_by.get((exp_id, chrom), ()):
+                if start < estop and estart < stop and _strand_ok(strand, estrand) and ((not exact) or (start == estart and stop == estop)):
+                    hit = True
+        key = (md5_long_id(sid), chrom, start, stop, strand, tuple(vals))
+        out[key] = out.get(key, False) or hit
+    return [k for k, h in out.items() if not h]
+
+
 class CoverParam:
     """CoverParam ADT (core/DataStructures/CoverParameters/CoverParam.scala:6-16) and the parser's
     ALL / ALL/k / (ALL+m)/k closures (Compiler GmqlParsers.scala:543-562)."""

@@ -123,3 +123,26 @@ def test_join_distance_and_builders():
     assert O.join_regions(l, r, "CONTIG")[2:5] == (10, 40, "+")
     assert O.join_regions(l, r, "INTERSECTION")[2:5] == (15, 20, "*")
     assert O.join_regions(l, r, "RIGHT")[:5] == (5, "chr1", 15, 40, "-")
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_difference_bins_equal_direct(seed):
+    """GenometricDifference's 50 000-base binning (first-bin rule) is not observable: the literal restatement equals the
+    bin-free set difference, for plain and exact matching."""
+    rng = random.Random(7000 + seed)
+    ref = rand_regions(rng, 80, [1, 2, 3], n_vals=1, span=160000, max_len=(70000 if seed % 2 else 3000), min_len=0)
+    exp = rand_regions(rng, 60, [10, 11], n_vals=0, span=160000, max_len=(3000 if seed % 4 < 2 else 70000), min_len=0)
+    for k in range(0, 30, 3):
+        r = ref[k]
+        exp.append((10, r[1], r[2], r[3], r[4], ()))
+    groups = {1: [10, 11], 2: [11]}
+    for exact in (False, True):
+        a = canon(O.difference_reference(ref, exp, groups, exact))
+        d = canon(O.difference_direct(ref, exp, groups, exact))
+        assert a == d and (len(a) > 0 or seed % 4 >= 2)
+
+
+def test_difference_id_and_ungrouped_samples():
+    ref = [(5, "chr1", 10, 20, "*", (1.0,)), (6, "chr1", 10, 20, "*", (1.0,))]
+    out = O.difference_reference(ref, [], {5: [9]})
+    assert out == [(O.md5_long_id(5), "chr1", 10, 20, "*", (1.0,))]
