@@ -42,7 +42,7 @@ EXPORTS = [
     "gmql_result_column_elem_size", "gmql_result_column_device", "gmql_result_column_copy",
     "gmql_result_as_regions", "gmql_result_free", "gmql_last_device_ms", "gmql_last_h2d_ms",
     "gmql_dataset_upload", "gmql_dataset_free", "gmql_ctx_set_profiling", "gmql_ctx_profile_report",
-    "gmql_difference",
+    "gmql_difference", "gmql_profile",
 ]
 
 _lib = None
@@ -72,6 +72,7 @@ def load_library(path=None):
     lib.gmql_host_free.restype = None
     lib.gmql_map.argtypes = [vp, C.POINTER(Regions), C.POINTER(Regions), C.POINTER(Pair), i64, C.POINTER(Agg), i32, C.POINTER(vp)]
     lib.gmql_difference.argtypes = [vp, C.POINTER(Regions), C.POINTER(Regions), C.POINTER(Pair), i64, i32, C.POINTER(vp)]
+    lib.gmql_profile.argtypes = [vp, C.POINTER(Regions), C.POINTER(vp)]
     lib.gmql_cover.argtypes = [vp, C.POINTER(Regions), vp, i32, i32, vp, vp, i64, C.POINTER(Agg), i32, C.POINTER(vp)]
     lib.gmql_cover_count_samples.argtypes = [vp, C.POINTER(Regions), C.POINTER(i32)]
     lib.gmql_join.argtypes = [vp, C.POINTER(Regions), C.POINTER(Regions), C.POINTER(Pair), i64, C.POINTER(Atom), i32, i32, i64, i64, vp, vp, C.POINTER(vp)]
@@ -107,4 +108,5 @@ COL_BAG_OFFSETS, COL_BAG_ROWS = 5, 6
 COL_COV_GROUP, COL_COV_CHROM, COL_COV_START, COL_COV_STOP, COL_COV_STRAND, COL_COV_ACC, COL_COV_J1, COL_COV_J2 = 16, 17, 18, 19, 20, 21, 22, 23
 COL_JOIN_LEFT_ROW, COL_JOIN_RIGHT_ROW, COL_JOIN_PAIR, COL_JOIN_START, COL_JOIN_STOP, COL_JOIN_STRAND, COL_JOIN_CHROM = 32, 33, 34, 35, 36, 37, 38
 COL_DIFF_REF_ROW = 48
+COL_PROF_LEFTMOST, COL_PROF_RIGHTMOST, COL_PROF_MIN_LENGTH, COL_PROF_MAX_LENGTH, COL_PROF_SUM_LENGTH, COL_PROF_SUM_LENGTH_SQ, COL_PROF_COUNT = 64, 65, 66, 67, 68, 69, 70
 COL_AGG_VALUE, COL_AGG_VALID = 256, 512

@@ -191,6 +191,31 @@ class GMQLCudaExecutor:
         recs = ref.to_records()
         return [(long_id(recs[i][0]), recs[i][1], recs[i][2], recs[i][3], recs[i][4], tuple(recs[i][5])) for i in rows]
 
+    # ---- PROFILE ----------------------------------------------------------------------------------------------------------
+    def profile(self, ds):
+        """Per-sample statistics of Profiler.profile (GMQL-Profiler/.../Profilers/Profiler.scala:124-153): returns
+        {sample_id: {leftMost, rightMost, minLength, maxLength, count, avgLength, varianceLength}} (calculateResult :84-92)."""
+        c_ds, keep = ds.as_c(narrow=self.narrow)
+        out = C.c_void_p()
+        self._check(self.lib.gmql_profile(self.ctx, C.byref(c_ds), C.byref(out)))
+        del keep
+        res = _Result(self, out)
+        cols = {k: res.column(c, np.int64) for k, c in (("l", L.COL_PROF_LEFTMOST), ("r", L.COL_PROF_RIGHTMOST), ("mn", L.COL_PROF_MIN_LENGTH),
+                                                        ("mx", L.COL_PROF_MAX_LENGTH), ("sl", L.COL_PROF_SUM_LENGTH), ("sq", L.COL_PROF_SUM_LENGTH_SQ),
+                                                        ("c", L.COL_PROF_COUNT))}
+        res.free()
+        prof = {}
+        for i, sid in enumerate(ds.sample_ids):
+            c = int(cols["c"][i])
+            if c > 0:
+                mean = float(int(cols["sl"][i])) / c
+                var = float(int(cols["sq"][i])) / c - mean * mean
+                prof[int(sid)] = dict(leftMost=int(cols["l"][i]), rightMost=int(cols["r"][i]), minLength=int(cols["mn"][i]), maxLength=int(cols["mx"][i]),
+                                      count=c, avgLength=mean, varianceLength=var)
+            else:
+                prof[int(sid)] = dict(leftMost=0, rightMost=0, minLength=0, maxLength=0, count=0, avgLength=0.0, varianceLength=0.0)
+        return prof
+
     # ---- COVER ------------------------------------------------------------------------------------------------------------
     def cover_raw(self, coverFlag, min, max, aggregators, groups, ds, force_unified=False):
         c_ds, keep = ds.as_c(narrow=self.narrow)

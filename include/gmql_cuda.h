@@ -222,6 +222,16 @@ int gmql_join(gmql_ctx* ctx, const gmql_regions* left, const gmql_regions* right
 int gmql_difference(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp,
                     const gmql_pair* pairs, int64_t n_pairs, int32_t exact, gmql_result** out);
 
+/* ---- PROFILE ---------------------------------------------------------------------------
+ * The reference profiles every materialised result with two foldByKey passes (Profiler.profile,
+ * GMQL-Profiler/.../Profilers/Profiler.scala:124-153; call site GMQLSparkExecutor.scala:158-173).  gmql_profile
+ * computes the per-sample ProfilerValue (:65) in one read of the coordinate columns: one row per sample index,
+ * columns GMQL_COL_PROF_* (all int64; the two sums wrap like Java longs).  Samples without regions keep the fold's
+ * zero value (leftMost = minLength = Long.MaxValue, rightMost = maxLength = Long.MinValue, count 0, :69); the
+ * per-dataset fold and calculateResult (:84-92) are a few operations on these rows and stay on the host.
+ */
+int gmql_profile(gmql_ctx* ctx, const gmql_regions* in, gmql_result** out);
+
 /* ---- results --------------------------------------------------------------------------- */
 enum {
   GMQL_COL_MAP_ROW_OFFSETS = 1, GMQL_COL_MAP_REF_ROW = 2, GMQL_COL_MAP_REF_SAMPLE_OFFSETS = 3, GMQL_COL_MAP_COUNT = 4,
@@ -231,6 +241,8 @@ enum {
   GMQL_COL_JOIN_LEFT_ROW = 32, GMQL_COL_JOIN_RIGHT_ROW = 33, GMQL_COL_JOIN_PAIR = 34, GMQL_COL_JOIN_START = 35,
   GMQL_COL_JOIN_STOP = 36, GMQL_COL_JOIN_STRAND = 37, GMQL_COL_JOIN_CHROM = 38,
   GMQL_COL_DIFF_REF_ROW = 48,
+  GMQL_COL_PROF_LEFTMOST = 64, GMQL_COL_PROF_RIGHTMOST = 65, GMQL_COL_PROF_MIN_LENGTH = 66, GMQL_COL_PROF_MAX_LENGTH = 67,
+  GMQL_COL_PROF_SUM_LENGTH = 68, GMQL_COL_PROF_SUM_LENGTH_SQ = 69, GMQL_COL_PROF_COUNT = 70,
   GMQL_COL_AGG_VALUE = 256, /* + aggregate index */
   GMQL_COL_AGG_VALID = 512  /* + aggregate index */
 };

@@ -381,6 +381,35 @@ def difference_direct(ref, exp, groups, exact=False):
     return [k for k, h in out.items() if not h]
 
 
+def _wrap64(v: int) -> int:
+    """Java long arithmetic wraps."""
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def profile_reference(records, sample_ids=None):
+    """Profiler.profile's per-sample fold (GMQL-Profiler/.../Profilers/Profiler.scala:124-153): ProfilerValue(leftMost,
+    rightMost, minLength, maxLength, sumLength, sumLengthOfSquares, count) per sample, folded from zeroProfilerValue
+    (:69) with reduceFunc (:71-82), then calculateResult (:84-92).  Returns {sample_id: dict}; samples listed in
+    sample_ids without regions keep count 0."""
+    LMAX, LMIN = 2 ** 63 - 1, -(2 ** 63)
+    acc = {}
+    for (sid, _chrom, start, stop, _strand, _vals) in records:
+        d = stop - start
+        l, r, mn, mx, sl, sq, c = acc.get(sid, (LMAX, LMIN, LMAX, LMIN, 0, 0, 0))
+        acc[sid] = (min(l, start), max(r, stop), min(mn, d), max(mx, d), _wrap64(sl + d), _wrap64(sq + d * d), c + 1)
+    out = {}
+    for sid in (sample_ids if sample_ids is not None else acc.keys()):
+        l, r, mn, mx, sl, sq, c = acc.get(sid, (LMAX, LMIN, LMAX, LMIN, 0, 0, 0))
+        if c > 0:
+            mean = float(sl) / c
+            var = float(sq) / c - mean * mean
+            out[sid] = dict(leftMost=l, rightMost=r, minLength=mn, maxLength=mx, count=c, avgLength=mean, varianceLength=var)
+        else:
+            out[sid] = dict(leftMost=0, rightMost=0, minLength=0, maxLength=0, count=0, avgLength=0.0, varianceLength=0.0)
+    return out
+
+
 class CoverParam:
     """CoverParam ADT (core/DataStructures/CoverParameters/CoverParam.scala:6-16) and the parser's
     ALL / ALL/k / (ALL+m)/k closures (Compiler GmqlParsers.scala:543-562)."""
