@@ -647,7 +647,8 @@ __global__ void __launch_bounds__(256) k_gmap4(const uint32_t* __restrict__ ccls
                                                LinMap lm, const K* __restrict__ xs, const K* __restrict__ xe, const K* __restrict__ xpmax, const uint32_t* __restrict__ xrow, int64_t nx,
                                                CovAggPlan plan, CovCols cc, int flat,
                                                int32_t* __restrict__ keep, int64_t* __restrict__ fstart, int64_t* __restrict__ fstop, double* __restrict__ j1, double* __restrict__ j2,
-                                               int32_t* __restrict__ ocount, CovOut out) {
+                                               int32_t* __restrict__ ocount, CovOut out, const int* __restrict__ only_if /* null, or run only when *only_if != 0 */) {
+  if (only_if && !*only_if) return;
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -731,6 +732,118 @@ __global__ void __launch_bounds__(256) k_gmap4(const uint32_t* __restrict__ ccls
         out.value[a][c] = v;
         out.valid[a][c] = ok;
       }
+    }
+  }
+}
+
+// ---- GMAP4, region-driven: for many small phase-1 regions (HISTOGRAM segments, SUMMIT plateaus) ------------------------
+// The phase-1 regions of every flag are sorted by linear start and pairwise disjoint, so their stops are sorted too.  Instead
+// of one warp searching the input index per phase-1 region, every INPUT region finds the phase-1 regions it overlaps (bucket
+// table over their starts, then a backward walk that ends at the first non-overlap) and accumulates with REDs.
+__device__ __forceinline__ void amin_k(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+__device__ __forceinline__ void amax_k(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+__device__ __forceinline__ void amin_k(uint64_t* p, uint64_t v) { atomicMin((unsigned long long*)p, (unsigned long long)v); }
+__device__ __forceinline__ void amax_k(uint64_t* p, uint64_t v) { atomicMax((unsigned long long*)p, (unsigned long long)v); }
+
+template <typename K>
+struct ScatterAcc {
+  int32_t* cnt; K* smin; K* emax; K* smax; K* emin;
+  int32_t* nn[8]; double* sum[8]; unsigned long long* vmin[8]; unsigned long long* vmax[8];
+};
+
+template <typename K>
+__global__ void k_p1_linear(const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom, const int64_t* __restrict__ cstart, const int64_t* __restrict__ cstop, int64_t nc,
+                            LinMap lm, K* __restrict__ cs, K* __restrict__ ce, int* __restrict__ unsorted) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t base = (uint64_t)ccls[c] * lm.G + lm.coff[cchrom[c]];
+    K s = (K)(base + (uint64_t)cstart[c]), e = (K)(base + (uint64_t)cstop[c]);
+    cs[c] = s; ce[c] = e;
+    if (c > 0) {   // sorted and disjoint: the previous region ends at or before this start
+      uint64_t pb = (uint64_t)ccls[c - 1] * lm.G + lm.coff[cchrom[c - 1]];
+      if ((K)(pb + (uint64_t)cstop[c - 1]) > s) *unsorted = 1;
+    }
+  }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(256) k_gmap4_scatter(const K* __restrict__ xs, const K* __restrict__ xe, const uint32_t* __restrict__ xrow, int64_t nx,
+                                                       const K* __restrict__ cs, const K* __restrict__ ce, int64_t nc, const uint32_t* __restrict__ tbl, int tbl_shift, int64_t n_buckets,
+                                                       CovAggPlan plan, CovCols cc, ScatterAcc<K> acc, const int* __restrict__ unsorted) {
+  if (*unsorted) return;                                   // the warp-per-region kernel takes over
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nx; k += (int64_t)gridDim.x * blockDim.x) {
+    const K s = xs[k], e = xe[k];
+    // last = number of phase-1 regions with start < e
+    int64_t lo, hi;
+    {
+      uint64_t b = (uint64_t)e >> tbl_shift;
+      if (b >= (uint64_t)n_buckets) { lo = hi = nc; }
+      else { lo = tbl[b]; hi = tbl[b + 1]; }
+      while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (cs[mid] < e) lo = mid + 1; else hi = mid; }
+    }
+    uint32_t row = 0;
+    if (plan.n_cols) row = xrow[k];
+    for (int64_t j = lo - 1; j >= 0 && ce[j] > s; --j) {     // strict overlap (GMAP4.scala:41); stops are sorted
+      atomicAdd(&acc.cnt[j], 1);
+      amin_k(&acc.smin[j], s); amax_k(&acc.emax[j], e);
+      amax_k(&acc.smax[j], s); amin_k(&acc.emin[j], e);
+      for (int q = 0; q < plan.n_cols; ++q) {
+        if (cc.ok[q] && !cc.ok[q][row]) continue;
+        double v = cc.v[q][row];
+        atomicAdd(&acc.nn[q][j], 1);
+        atomicAdd(&acc.sum[q][j], v);
+        atomicMin(&acc.vmin[q][j], cov_key_min(v));
+        atomicMax(&acc.vmax[q][j], cov_key_max(v));
+      }
+    }
+  }
+}
+
+template <typename K>
+__global__ void k_p1_table(const K* __restrict__ cs, int64_t nc, int shift, int64_t n_buckets, uint32_t* __restrict__ tbl) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t x = (uint64_t)b << shift;
+    K kx = (x > (uint64_t)(~(K)0)) ? ~(K)0 : (K)x;
+    tbl[b] = (uint32_t)lower_bound_dev<K>(cs, nc, kx);
+  }
+}
+
+template <typename K>
+__global__ void k_gmap4_finish(const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom, const int64_t* __restrict__ cstart, const int64_t* __restrict__ cstop, int64_t nc,
+                               LinMap lm, CovAggPlan plan, ScatterAcc<K> acc, int flat, int32_t* __restrict__ keep, int64_t* __restrict__ fstart, int64_t* __restrict__ fstop,
+                               double* __restrict__ j1, double* __restrict__ j2, int32_t* __restrict__ ocount, CovOut out, const int* __restrict__ unsorted) {
+  if (*unsorted) return;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t base = (uint64_t)ccls[c] * lm.G + lm.coff[cchrom[c]];
+    long long cnt = acc.cnt[c];
+    keep[c] = cnt > 0 ? 1 : 0;
+    ocount[c] = (int32_t)cnt;
+    if (cnt > 0) {
+      unsigned long long smin = acc.smin[c], emax = acc.emax[c], smax = acc.smax[c], emin = acc.emin[c];
+      int64_t start_min = (int64_t)(smin - base), end_max = (int64_t)(emax - base);
+      int64_t os = flat ? start_min : cstart[c], oe = flat ? end_max : cstop[c];   // GMAP4.scala:83-84
+      fstart[c] = os; fstop[c] = oe;
+      long long den = (long long)(emax - smin);
+      double num2;
+      if (cnt == 1) num2 = (double)(long long)(emin - smax);
+      else num2 = smax < emin ? (double)(long long)(emin - smax) : 0.0;            // :74
+      j1[c] = den != 0 ? fabs(((double)oe - (double)os) / (double)den) : 0.0;      // :91
+      j2[c] = den != 0 ? fabs(num2 / (double)den) : 0.0;                           // :93
+    } else { fstart[c] = cstart[c]; fstop[c] = cstop[c]; j1[c] = 0.0; j2[c] = 0.0; }
+    for (int a = 0; a < plan.n_aggs; ++a) {
+      int kind = plan.kind[a], q = plan.slot[a];
+      double v = 0.0; uint8_t ok = 0;
+      if (kind == GMQL_AGG_COUNT) { v = (double)cnt; ok = 1; }
+      else if (acc.nn[q][c] > 0) {
+        ok = 1;
+        int nn = acc.nn[q][c];
+        if (kind == GMQL_AGG_SUM) v = acc.sum[q][c];
+        else if (kind == GMQL_AGG_AVG) v = acc.sum[q][c] / (double)nn;
+        else if (kind == GMQL_AGG_MIN) v = cov_from_key(acc.vmin[q][c]);
+        else if (kind == GMQL_AGG_MAX) v = cov_from_key(acc.vmax[q][c]);
+        else if (kind == GMQL_AGG_MEDIAN) { double m = cov_from_key(acc.vmin[q][c]); v = nn >= 2 ? (m + m) / 2 : m; }
+      }
+      out.value[a][c] = v;
+      out.valid[a][c] = ok;
     }
   }
 }
@@ -1094,8 +1207,43 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   if (nc) {
     int64_t warps_needed = nc;
     int blocks = (int)std::min<int64_t>(ceil_div64(warps_needed, 8), (int64_t)ctx->num_sms * 16);
-    LAUNCH(ctx, (k_gmap4<K>), blocks, 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, ix.start, ix.stop.p, ix.pmax.p, ix.row, n,
-           plan, cc, flag == GMQL_FLAT ? 1 : 0, keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp);
+    if (nc >= n / 8 && nc < (int64_t)0xfffffff0LL) {
+      // many small phase-1 regions: region-driven accumulation; the warp-per-region kernel only runs if the phase-1 list
+      // turns out not to be sorted and disjoint (decided on the device, no host round trip)
+      DevBuf<K> cs(ctx, nc), ce(ctx, nc);
+      DevBuf<int> unsorted(ctx, 1);
+      unsorted.zero();
+      LAUNCH(ctx, (k_p1_linear<K>), grid_for(ctx, nc, 256), 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, cs.p, ce.p, unsorted.p);
+      const uint64_t max_key = n_classes_total * lm.G;
+      int tshift = 0;
+      { int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)1 << 22, nc / 2 + 1)); while (tshift < 62 && (int64_t)(max_key >> tshift) + 2 > want) ++tshift; }
+      const int64_t nb = (int64_t)(max_key >> tshift) + 1;
+      DevBuf<uint32_t> tbl(ctx, nb + 2);
+      LAUNCH(ctx, (k_p1_table<K>), grid_for(ctx, nb + 1, 256), 256, 0, cs.p, nc, tshift, nb, tbl.p);
+      ScatterAcc<K> sa;
+      memset(&sa, 0, sizeof sa);
+      DevBuf<int32_t> a_cnt(ctx, nc);
+      DevBuf<K> a_smin(ctx, nc), a_emax(ctx, nc), a_smax(ctx, nc), a_emin(ctx, nc);
+      a_cnt.zero(); a_emax.zero(); a_smax.zero(); a_smin.fill_byte(0xff); a_emin.fill_byte(0xff);
+      sa.cnt = a_cnt.p; sa.smin = a_smin.p; sa.emax = a_emax.p; sa.smax = a_smax.p; sa.emin = a_emin.p;
+      std::vector<DevBuf<int32_t>> a_nn((size_t)plan.n_cols);
+      std::vector<DevBuf<double>> a_sum((size_t)plan.n_cols);
+      std::vector<DevBuf<unsigned long long>> a_vmin((size_t)plan.n_cols), a_vmax((size_t)plan.n_cols);
+      for (int q = 0; q < plan.n_cols; ++q) {
+        a_nn[q].alloc(ctx, nc); a_nn[q].zero(); a_sum[q].alloc(ctx, nc); a_sum[q].zero();
+        a_vmin[q].alloc(ctx, nc); a_vmin[q].fill_byte(0xff); a_vmax[q].alloc(ctx, nc); a_vmax[q].zero();
+        sa.nn[q] = a_nn[q].p; sa.sum[q] = a_sum[q].p; sa.vmin[q] = a_vmin[q].p; sa.vmax[q] = a_vmax[q].p;
+      }
+      LAUNCH(ctx, (k_gmap4_scatter<K>), grid_for(ctx, n, 256), 256, 0, (const K*)ix.start, (const K*)ix.stop.p, (const uint32_t*)ix.row, n, (const K*)cs.p, (const K*)ce.p, nc,
+             (const uint32_t*)tbl.p, tshift, nb, plan, cc, sa, (const int*)unsorted.p);
+      LAUNCH(ctx, (k_gmap4_finish<K>), grid_for(ctx, nc, 256), 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, plan, sa, flag == GMQL_FLAT ? 1 : 0,
+             keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp, (const int*)unsorted.p);
+      LAUNCH(ctx, (k_gmap4<K>), blocks, 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, ix.start, ix.stop.p, ix.pmax.p, ix.row, n,
+             plan, cc, flag == GMQL_FLAT ? 1 : 0, keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp, (const int*)unsorted.p);
+    } else {
+      LAUNCH(ctx, (k_gmap4<K>), blocks, 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, ix.start, ix.stop.p, ix.pmax.p, ix.row, n,
+             plan, cc, flag == GMQL_FLAT ? 1 : 0, keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp, (const int*)nullptr);
+    }
   }
   }  // !done
   keep_excl.alloc(ctx, nc + 1);

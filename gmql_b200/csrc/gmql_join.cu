@@ -78,10 +78,22 @@ struct LeftSide {
 template <typename K>
 struct RightIndex {
   const K* start; const K* stop; const K* pmax; const uint32_t* row; int64_t n;
+  const uint32_t* tbl; int tbl_shift; int64_t n_buckets;   // tbl[b] = lower_bound(start, b << tbl_shift), b = 0..n_buckets
   const int8_t* strand;    // per sorted entry
   const int32_t* sample;   // per sorted entry
   const int64_t* eq;       // per ORIGINAL row (or null)
 };
+
+// lower_bound over the sorted starts through the bucket table: two table reads and a search inside one bucket
+// (a few entries) instead of ~log2(n) dependent loads across the whole index
+template <typename K>
+__device__ __forceinline__ int64_t start_lower_bound(const RightIndex<K>& R, uint64_t x) {
+  uint64_t b = x >> R.tbl_shift;
+  if (b >= (uint64_t)R.n_buckets) return R.n;            // beyond the last bucket boundary: every start is smaller
+  int64_t lo = R.tbl[b], hi = R.tbl[b + 1];
+  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (R.start[mid] < (K)x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
 
 // window of the index a left region must scan: [lo, hi)
 template <typename K>
@@ -92,8 +104,27 @@ __device__ __forceinline__ void window(const RightIndex<K>& R, const LinMap& lm,
   int64_t wbeg = b0 * B;                                  // r.stop / B >= binStart
   if (wbeg > span + 1) wbeg = span + 1;
   uint64_t base = block_base + lm.coff[c];
-  *hi = lower_bound_dev<K>(R.start, R.n, (K)(base + (uint64_t)wend));
-  *lo = lower_bound_dev<K>(R.pmax, *hi, (K)(base + (uint64_t)wbeg));
+  const int64_t h = start_lower_bound<K>(R, base + (uint64_t)wend);
+  // first entry whose running max stop reaches wbeg: entries starting at or after wbeg qualify (stop >= start), so the
+  // answer is at or before lower_bound(start, wbeg); gallop back over the non-decreasing pmax from there
+  const K y = (K)(base + (uint64_t)wbeg);
+  int64_t r = start_lower_bound<K>(R, base + (uint64_t)wbeg);
+  if (r > h) r = h;
+  int64_t step = 1, l = r;
+  while (l > 0 && R.pmax[l - 1] >= y) { r = l; l = l > step ? l - step : 0; step <<= 1; }
+  // invariant: pmax[r] >= y (or r == h) and (l == 0 or pmax[l-1] < y): the first qualifying entry lies in [l, r]
+  while (l < r) { int64_t mid = (l + r) >> 1; if (R.pmax[mid] < y) l = mid + 1; else r = mid; }
+  *hi = h;
+  *lo = l;
+}
+
+template <typename K>
+__global__ void k_start_table(const K* __restrict__ start, int64_t n, int shift, int64_t n_buckets, uint32_t* __restrict__ tbl) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t x = (uint64_t)b << shift;
+    K kx = (x > (uint64_t)(~(K)0)) ? ~(K)0 : (K)x;
+    tbl[b] = (uint32_t)lower_bound_dev<K>(start, n, kx);
+  }
 }
 
 // ---- no MD: warp per left region over the pooled right index -------------------------------------------------------------
@@ -418,7 +449,18 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
 
   LeftSide L;
   L.chrom = left.chrom; L.start = left.start; L.stop = left.stop; L.bits = left.coord_bits; L.strand = left.strand; L.sample = left.sample; L.eq = d_left_eq; L.n = nl;
+  // bucket table over the linear start key (about two entries per bucket, at most 2^22 buckets)
+  const uint64_t max_key = n_blocks * lm.G;
+  int tbl_shift = 0;
+  {
+    int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)1 << 22, nr / 2 + 1));
+    while (tbl_shift < 62 && (int64_t)(max_key >> tbl_shift) + 2 > want) ++tbl_shift;
+  }
+  const int64_t n_buckets = (int64_t)(max_key >> tbl_shift) + 1;
+  DevBuf<uint32_t> tbl(ctx, n_buckets + 2);
+  LAUNCH(ctx, (k_start_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, nr, tbl_shift, n_buckets, tbl.p);
   RightIndex<K> R;
+  R.tbl = tbl.p; R.tbl_shift = tbl_shift; R.n_buckets = n_buckets;
   R.start = ix.start; R.stop = ix.stop.p; R.pmax = ix.pmax.p; R.row = ix.row; R.n = nr; R.strand = s_strand.p; R.sample = s_sample.p; R.eq = d_right_eq;
 
   // multiplicity of identical left records (MapKey pooling in the MD round)
