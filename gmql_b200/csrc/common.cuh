@@ -80,15 +80,28 @@ static inline void gmql_prof_end(gmql_ctx* c) { cudaEventRecord(c->prof.back().b
     if (!(cond)) throw gmql_error((code), std::string(msg));                                  \
   } while (0)
 
+// host-side trace (GMQL_TRACE=1): wall-clock microseconds of every launch / synchronisation, to stderr
+#include <chrono>
+#include <cstdlib>
+inline bool gmql_trace_on() { static int on = -1; if (on < 0) { const char* e = getenv("GMQL_TRACE"); on = (e && *e == '1') ? 1 : 0; } return on == 1; }
+inline void gmql_trace(const char* what) {
+  if (!gmql_trace_on()) return;
+  static auto t0 = std::chrono::steady_clock::now();
+  fprintf(stderr, "[trace] %10.1f us  %s\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(), what);
+}
+
 // kernel launch on the context stream; counts launches for bench.py's gpu_launches
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                           \
   do {                                                                                        \
+    gmql_trace(#kernel);                                                                      \
     if ((ctx)->profiling) gmql_prof_begin((ctx), #kernel);                                    \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
     if ((ctx)->profiling) gmql_prof_end((ctx));                                               \
     (ctx)->launches++;                                                                        \
     CUDA_TRY(cudaGetLastError());                                                             \
   } while (0)
+
+#define GMQL_SYNC(ctx) ([&]() { gmql_trace("sync>"); cudaError_t _e = cudaStreamSynchronize((ctx)->stream); gmql_trace("<sync"); return _e; }())
 
 // stream-ordered device buffer (cudaMallocAsync pool: frees do not synchronise)
 template <typename T>
@@ -146,6 +159,7 @@ struct DevRegions {
   std::vector<DevBuf<uint8_t>> owned;  // uploaded copies
   int64_t h2d_bytes = 0;
   const int64_t* span_hint = nullptr;  // host [n_chrom] upper bounds of stop, or null
+  bool sorted_hint = false;            // rows ordered by (chrom, start) according to the caller (verified on the device)
 };
 
 // upload (or adopt) a gmql_regions; only the value columns listed in need_cols are moved
@@ -168,6 +182,7 @@ struct gmql_result {
   std::vector<const uint8_t*> view_valid;
   void* view_acc_double = nullptr;
   std::vector<int64_t> span_hint;    // cover results: upper bound of stop per chromosome (host)
+  bool sorted = false;               // cover results: rows ordered by (chrom, start) (single class)
 };
 template <typename T>
 static inline void result_add(gmql_result* r, int id, DevBuf<T>& b) {

@@ -48,8 +48,8 @@ struct Cfg {
 struct Pieces {
   uint32_t* pstart; uint32_t* pend; int32_t* acc; int32_t* cnt;
   uint32_t* smin; uint32_t* emax; uint32_t* smax; uint32_t* emin; uint8_t* flags;   // bit0: continues from the previous tile, bit1: reaches the tile end
-  unsigned long long* cursor;
-  int64_t cap;
+  uint32_t* blk_cnt;   // [gridDim.x] pieces written by every block: block b owns the slots [b * seg, (b + 1) * seg)
+  int64_t seg;         // so that the pieces come out in genome order without sorting (block ranges and tiles ascend)
   int* fail;   // 1: output capacity, 2: distinct positions, 3: pieces, 4: halo regions of one tile
 };
 
@@ -338,7 +338,6 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
   uint32_t* pemin = psmax + MAXP;
   __shared__ int32_t scratch[NWARPS];
   __shared__ int s_nh, s_nout;
-  __shared__ long long s_base;
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t W = 1u << logw;
   const int nW = (int)(W >> 5) > 0 ? (int)(W >> 5) : 1;
@@ -364,6 +363,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
     t_begin = bounds[0]; t_end = bounds[1];
   }
   int nh_carry = -1;                                       // -1: the open regions must be found by scanning the previous tile
+  int64_t my_cnt = 0;                                      // pieces this block has published (block-uniform)
 
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
     const uint32_t s0 = offS[tile], s1 = offS[tile + 1];
@@ -598,19 +598,16 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
     }
     if (np > 0) {
       __syncthreads();
-      // ---- publish the tile's pieces
-      if (tid == 0) {
-        unsigned long long b = atomicAdd(out.cursor, (unsigned long long)np);
-        if ((int64_t)(b + np) > out.cap) { *out.fail = 1; s_base = -1; } else s_base = (long long)b;
-      }
-      __syncthreads();
-      const long long gb = s_base;
-      if (gb >= 0) {
+      // ---- publish the tile's pieces in this block's segment
+      if (my_cnt + np > out.seg) { if (tid == 0) *out.fail = 1; }
+      else {
+        const int64_t gb = (int64_t)blockIdx.x * out.seg + my_cnt;
         for (int k = tid; k < np; k += THREADS) {
           out.pstart[gb + k] = pst[k]; out.pend[gb + k] = pen[k]; out.acc[gb + k] = pacc[k]; out.cnt[gb + k] = pcnt[k];
           out.smin[gb + k] = psmin[k]; out.emax[gb + k] = pemax[k]; out.smax[gb + k] = psmax[k]; out.emin[gb + k] = pemin[k];
           out.flags[gb + k] = (uint8_t)(((k == 0 && cont0) ? 1 : 0) | ((k == np - 1 && reach_end) ? 2 : 0));
         }
+        my_cnt += np;
       }
     }
     __syncthreads();
@@ -618,7 +615,35 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
     { uint32_t* t = hinS; hinS = houtS; houtS = t; t = hinL; hinL = houtL; houtL = t; }
     nh_carry = nout;
   }
+  if (tid == 0) out.blk_cnt[blockIdx.x] = (uint32_t)my_cnt;
 }
+
+// per-block piece counts -> first global index of every block's pieces, and their total (one block)
+static __global__ void __launch_bounds__(1024) k_seg_offsets(const uint32_t* __restrict__ blk_cnt, int nb, uint32_t* __restrict__ blk_off, unsigned long long* __restrict__ total) {
+  __shared__ uint32_t wt[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < nb; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < nb ? blk_cnt[i] : 0u, x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wt[w] = x;
+    __syncthreads();
+    uint32_t b = carry;
+    for (int q = 0; q < w; ++q) b += wt[q];
+    if (i < nb) blk_off[i] = b + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = b + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { blk_off[nb] = carry; *total = carry; }
+}
+
+// global piece index -> slot (pieces in genome order), and the run tables' initial values
+struct Runs;
 
 // ---- stitch: pieces sorted by start -> runs ------------------------------------------------------------------------
 static __global__ void k_piece_heads(const uint32_t* __restrict__ order, const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ pend, const uint8_t* __restrict__ flags, int64_t np, int32_t* __restrict__ head) {
@@ -635,6 +660,15 @@ static __global__ void k_piece_heads(const uint32_t* __restrict__ order, const u
 struct Runs {
   uint32_t* rstart; uint32_t* rend; int32_t* acc; int32_t* cnt; uint32_t* smin; uint32_t* emax; uint32_t* smax; uint32_t* emin;
 };
+
+static __global__ void k_piece_order(const uint32_t* __restrict__ blk_off, int nb, int64_t seg, int64_t np, uint32_t* __restrict__ order, Runs r) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < np; g += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nb;                                   // last block whose first index is <= g
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int64_t)blk_off[mid] <= g) lo = mid; else hi = mid; }
+    order[g] = (uint32_t)((int64_t)lo * seg + (g - (int64_t)blk_off[lo]));
+    r.acc[g] = 0; r.cnt[g] = 0; r.emax[g] = 0; r.smax[g] = 0; r.smin[g] = 0xffffffffu; r.emin[g] = 0xffffffffu;
+  }
+}
 
 static __global__ void k_piece_merge(const uint32_t* __restrict__ order, Pieces p, int64_t np, const int32_t* __restrict__ head, const int64_t* __restrict__ head_excl, Runs r) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {

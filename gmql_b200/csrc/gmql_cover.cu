@@ -907,7 +907,7 @@ template <typename T>
 static int64_t read_back(gmql_ctx* ctx, const T* dev) {
   T v;
   CUDA_TRY(cudaMemcpyAsync(&v, dev, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
   return (int64_t)v;
 }
 
@@ -980,7 +980,7 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
   int64_t ne = 0;
   CUDA_TRY(cudaMemcpyAsync(&G2, coff2.p + spans.n_chrom, sizeof G2, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(&ne, ecnt.p + n, sizeof ne, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(ne < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "SUMMIT: more than 2^32 per-bin events");
   GMQL_REQUIRE(bits_for(n_classes_total * G2) < 63, GMQL_ERR_UNSUPPORTED, "SUMMIT: coordinate space too large");
   DevBuf<uint64_t> ka(ctx, ne), kb(ctx, ne);
@@ -1056,20 +1056,24 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, P, n, nT, logw, offS.p);
   }
 
-  int64_t cap = std::max<int64_t>((int64_t)1 << 20, n / 16 + 2 * nT);
+  // two resident blocks per SM; four ranges per resident block even out the tail.  Every block publishes its pieces in
+  // its own segment of the piece tables, so they come out in genome order and nothing has to be sorted.
+  const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nT, (int64_t)ctx->num_sms * 8));
+  const int64_t seg = std::max<int64_t>(4096, (n / 16 + 2 * nT) / tgrid + 1);
+  const int64_t cap = seg * tgrid;
+  GMQL_REQUIRE(cap < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "piece table too large");
   DevBuf<uint32_t> pstart(ctx, cap), pend(ctx, cap), smin(ctx, cap), emax(ctx, cap), smax(ctx, cap), emin(ctx, cap);
   DevBuf<int32_t> acc(ctx, cap), cnt(ctx, cap);
   DevBuf<uint8_t> pflags(ctx, cap);
-  DevBuf<unsigned long long> cursor(ctx, 1);
+  DevBuf<uint32_t> blk_cnt(ctx, tgrid), blk_off(ctx, (int64_t)tgrid + 1);
+  DevBuf<unsigned long long> np_dev(ctx, 1);
   DevBuf<int> fail(ctx, 1);
-  cursor.zero(); fail.zero();
+  fail.zero();
   tiled::Cfg tc;
   tc.n_groups = cfg.n_groups; tc.n_classes = cfg.n_classes; tc.mn = cfg.mn; tc.mx = cfg.mx; tc.mn0 = h_mn[0]; tc.mx0 = h_mx[0]; tc.G = lm.G;
   tiled::Pieces pc;
   pc.pstart = pstart.p; pc.pend = pend.p; pc.acc = acc.p; pc.cnt = cnt.p; pc.smin = smin.p; pc.emax = emax.p; pc.smax = smax.p; pc.emin = emin.p;
-  pc.flags = pflags.p; pc.cursor = cursor.p; pc.cap = cap; pc.fail = fail.p;
-  // two resident blocks per SM; four ranges per resident block even out the tail
-  const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nT, (int64_t)ctx->num_sms * 8));
+  pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
   if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
     LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, nT, n, logw, tc, pc);
@@ -1077,35 +1081,30 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
     LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, nT, n, logw, tc, pc);
   }
+  LAUNCH(ctx, tiled::k_seg_offsets, 1, 1024, 0, blk_cnt.p, (int)tgrid, blk_off.p, np_dev.p);
   unsigned long long h_np = 0;
   int h_fail = 0;
-  CUDA_TRY(cudaMemcpyAsync(&h_np, cursor.p, sizeof h_np, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&h_np, np_dev.p, sizeof h_np, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(&h_fail, fail.p, sizeof h_fail, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
   if (h_fail) return false;
   const int64_t np = (int64_t)h_np;
   pk_a.release(); pk_b.release();
 
-  // order the pieces by start, fuse the ones that touch at a tile edge
-  DevBuf<uint32_t> ok_a(ctx, np), ok_b(ctx, np), oi_a(ctx, np), oi_b(ctx, np);
-  if (np) {
-    CUDA_TRY(cudaMemcpyAsync(ok_a.p, pstart.p, 4 * (size_t)np, cudaMemcpyDeviceToDevice, ctx->stream));
-    LAUNCH(ctx, k_iota_u32, grid_for(ctx, np, 256), 256, 0, oi_a.p, np);
-  }
-  uint32_t *okeys = ok_a.p, *order = oi_a.p;
-  radix_sort<uint32_t>(ctx, ok_a.p, ok_b.p, oi_a.p, oi_b.p, np, key_bits, &okeys, &order);
+  // pieces in genome order -> runs: fuse the ones that touch at a tile edge.  The number of runs (<= np) stays on the
+  // device: the run tables are sized for np and the tail entries are dropped by the keep flags.
+  const int64_t nr = np;
+  DevBuf<uint32_t> order_buf(ctx, np);
+  DevBuf<uint32_t> rstart(ctx, nr), rend(ctx, nr), rsmin(ctx, nr), remax(ctx, nr), rsmax(ctx, nr), remin(ctx, nr);
+  DevBuf<int32_t> racc(ctx, nr), rcnt(ctx, nr);
+  tiled::Runs rr;
+  rr.rstart = rstart.p; rr.rend = rend.p; rr.acc = racc.p; rr.cnt = rcnt.p; rr.smin = rsmin.p; rr.emax = remax.p; rr.smax = rsmax.p; rr.emin = remin.p;
+  if (np) LAUNCH(ctx, tiled::k_piece_order, grid_for(ctx, np, 256), 256, 0, blk_off.p, (int)tgrid, seg, np, order_buf.p, rr);
+  const uint32_t* order = order_buf.p;
   DevBuf<int32_t> head(ctx, np);
   DevBuf<int64_t> head_excl(ctx, np + 1);
   if (np) LAUNCH(ctx, tiled::k_piece_heads, grid_for(ctx, np, 256), 256, 0, order, pstart.p, pend.p, pflags.p, np, head.p);
   device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, head.p, head_excl.p, np, head_excl.p + np);
-  // the number of runs (<= np) stays on the device: the run tables are sized for np and the tail entries are dropped
-  // by the keep flags, which saves a host round trip
-  const int64_t nr = np;
-  DevBuf<uint32_t> rstart(ctx, nr), rend(ctx, nr), rsmin(ctx, nr), remax(ctx, nr), rsmax(ctx, nr), remin(ctx, nr);
-  DevBuf<int32_t> racc(ctx, nr), rcnt(ctx, nr);
-  racc.zero(); rcnt.zero(); remax.zero(); rsmax.zero(); rsmin.fill_byte(0xff); remin.fill_byte(0xff);
-  tiled::Runs rr;
-  rr.rstart = rstart.p; rr.rend = rend.p; rr.acc = racc.p; rr.cnt = rcnt.p; rr.smin = rsmin.p; rr.emax = remax.p; rr.smax = rsmax.p; rr.emin = remin.p;
   if (np) LAUNCH(ctx, tiled::k_piece_merge, grid_for(ctx, np, 256), 256, 0, order, pc, np, head.p, head_excl.p, rr);
   p1->n = nr;
   p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->acc.alloc(ctx, nr);
@@ -1269,6 +1268,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
 
   res->rows = n_out;
   res->kind = 2;
+  res->sorted = n_classes_total == 1;     // one (group, strand) class: the rows are in (chrom, start) order
   res->n_chrom = in.n_chrom;
   res->group_ids.resize((size_t)n_groups);
   for (int gi = 0; gi < n_groups; ++gi) res->group_ids[gi] = gi;
@@ -1298,7 +1298,7 @@ static void inspect_input(gmql_ctx* ctx, const DevRegions& in, Inspect* out) {
   }
   int h[4];
   CUDA_TRY(cudaMemcpyAsync(h, flags.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(!h[2], GMQL_ERR_INVALID, "region with start > stop, negative start, bad strand code or sample index out of range");
   out->has_star = h[0];
   out->has_zero = h[1];
@@ -1333,6 +1333,7 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
     ctx->pin_next = 0;
+    gmql_trace("ENTER gmql_cover");
     GMQL_REQUIRE(in != nullptr, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_groups >= 1 && min_acc && max_acc, GMQL_ERR_INVALID, "n_groups >= 1 and per-group thresholds are required");
     const bool force_unified = (flag & GMQL_COVER_FORCE_UNIFIED) != 0;
@@ -1373,7 +1374,7 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     CUDA_TRY(cudaMemcpyAsync(&G, spans.coff.p + d.n_chrom, sizeof G, cudaMemcpyDeviceToHost, ctx->stream));
     unsigned long long* h_span = (unsigned long long*)ctx_pinned(ctx, 8 * (size_t)d.n_chrom);
     CUDA_TRY(cudaMemcpyAsync(h_span, spans.span.p, 8 * (size_t)d.n_chrom, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
     GMQL_REQUIRE(!hf[2], GMQL_ERR_INVALID, "region with chromosome/sample index out of range, start > stop, negative start or bad strand code");
     spans.G = G;
     Inspect ins;
@@ -1386,8 +1387,9 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     for (int c = 0; c < d.n_chrom; ++c) res->span_hint[c] = (int64_t)h_span[c] + 1;   // results may carry the one-base extension
     if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
     else run_cover<uint64_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
     *out = res;
+    gmql_trace("EXIT");
     return GMQL_OK;
   } catch (const gmql_error& ex) {
     ctx->err = ex.what();
@@ -1416,7 +1418,7 @@ extern "C" int gmql_result_as_regions(gmql_ctx* ctx, gmql_result* r, gmql_region
       CUDA_TRY(cudaMallocAsync(&p, sizeof(double) * (size_t)(n > 0 ? n : 1), ctx->stream));
       r->view_acc_double = p;
       if (n) LAUNCH(ctx, k_i32_to_f64, grid_for(ctx, n, 256), 256, 0, (const int32_t*)r->cols[GMQL_COL_COV_ACC].p, n, (double*)p);
-      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      CUDA_TRY(GMQL_SYNC(ctx));
       r->view_cols.assign(1, (const double*)p);
       r->view_valid.assign(1, nullptr);
     }
@@ -1437,6 +1439,7 @@ extern "C" int gmql_result_as_regions(gmql_ctx* ctx, gmql_result* r, gmql_region
     view->valid = r->view_valid.data();
     view->dup_of = nullptr;
     view->chrom_span_hint = r->span_hint.empty() ? nullptr : r->span_hint.data();
+    view->sorted_by_position = r->sorted ? 1 : 0;
     return GMQL_OK;
   } catch (const gmql_error& ex) {
     ctx->err = ex.what();

@@ -121,6 +121,7 @@ void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector
   out->n_samples = r->n_samples;
   out->n_cols = r->n_cols;
   out->span_hint = r->chrom_span_hint;
+  out->sorted_hint = r->sorted_by_position != 0;
   size_t cb = (size_t)(r->coord_bits / 8);
   size_t n = (size_t)r->n;
   GMQL_REQUIRE(r->chrom_bits == 0 || r->chrom_bits == 8 || r->chrom_bits == 16 || r->chrom_bits == 32, GMQL_ERR_INVALID, "chrom_bits must be 0, 8, 16 or 32");
@@ -202,6 +203,7 @@ extern "C" int gmql_result_column_copy(gmql_ctx* ctx, const gmql_result* r, int3
 
 extern "C" void gmql_result_free(gmql_ctx* ctx, gmql_result* r) {
   if (!r) return;
+  gmql_trace("result_free");
   for (auto& kv : r->cols)
     if (kv.second.p) { if (ctx) cudaFreeAsync(kv.second.p, ctx->stream); else cudaFree(kv.second.p); }
   if (r->view_acc_double) { if (ctx) cudaFreeAsync(r->view_acc_double, ctx->stream); else cudaFree(r->view_acc_double); }
@@ -248,6 +250,7 @@ extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql
     view->valid = d->valid.empty() ? nullptr : d->valid.data();
     view->dup_of = d->dev.dup_of;
     view->chrom_span_hint = host->chrom_span_hint;
+    view->sorted_by_position = host->sorted_by_position;
     *out = d;
     return GMQL_OK;
   } catch (const gmql_error& ex) {

@@ -420,7 +420,7 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
     CUDA_TRY(cudaMemcpyAsync(d_ars.p, h_ars.data(), 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d_apair.p, h_apair.data(), 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, ctx->stream));
   }
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope below
+  CUDA_TRY(GMQL_SYNC(ctx));   // host vectors go out of scope below
   cudaEventRecord(ctx->ev_h1, ctx->stream);
   cudaEventRecord(ctx->ev_k0, ctx->stream);
 
@@ -444,7 +444,7 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
 
   int h_bad = 0;
   CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "sample index out of range in a region dataset");
 
   LeftSide L;
@@ -482,7 +482,7 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, cnt.p, cnt.p, nl, cnt.p + nl);
   int64_t n_out = 0;
   CUDA_TRY(cudaMemcpyAsync(&n_out, cnt.p + nl, sizeof n_out, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(n_out < (int64_t)0x7fffffff * 8, GMQL_ERR_UNSUPPORTED, "join output too large for this version");
   DevBuf<int32_t> ol(ctx, n_out), orr(ctx, n_out), op(ctx, n_out);
   if (nl && n_out) {
@@ -505,7 +505,7 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
     device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, flag.p, excl.p, n_out, excl.p + n_out);
     int64_t n_u = 0;
     CUDA_TRY(cudaMemcpyAsync(&n_u, excl.p + n_out, sizeof n_u, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
     DevBuf<int32_t> ul(ctx, n_u), ur(ctx, n_u), up(ctx, n_u);
     if (n_out) LAUNCH(ctx, k_unique_write, g, 256, 0, keys, n_out, flag.p, excl.p, ls ? 1 : 0, ul.p, ur.p, up.p);
     ol = std::move(ul); orr = std::move(ur); op = std::move(up);
@@ -571,7 +571,7 @@ extern "C" int gmql_join(gmql_ctx* ctx, const gmql_regions* left, const gmql_reg
     build_span_table(ctx, &dr, nullptr, &spans);
     res = new gmql_result();
     run_join<uint64_t>(ctx, dl, dr, pairs, n_pairs, cfg, rows_only, p_leq, p_req, spans, res);
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
     *out = res;
     return GMQL_OK;
   } catch (const gmql_error& ex) {

@@ -406,7 +406,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     }
     CUDA_TRY(cudaMemcpyAsync(&n_rows, row_off.p + n_pairs, sizeof n_rows, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
     GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "sample index out of range (regions or pair list)");
     if (n_pairs) LAUNCH(ctx, k_pair_base, grid_for(ctx, n_pairs, 256), 256, 0, d_pl.p, d_pr.p, n_pairs, n_rs, row_off.p, pair_base.p, bad.p);
   }
@@ -414,7 +414,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   // interval index over the reference
   LinMap lm = spans.map();
   IntervalIndex<K> ix;
-  build_index<K>(ctx, ref, nullptr, 1, lm, &ix, false, ref.span_hint ? bad.p : (int*)nullptr);
+  build_index<K>(ctx, ref, nullptr, 1, lm, &ix, false, (ref.span_hint || ref.sorted_hint) ? bad.p : (int*)nullptr);
   // bucket table, resident in the streaming kernel's shared memory: as fine as fits (most buckets then hold no start
   // and a query needs no search at all), at least 2^10 buckets
   int tbl_shift = 0;
@@ -479,9 +479,9 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   cudaEventRecord(ctx->ev_k1, ctx->stream);
 
   CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(h_bad != 2, GMQL_ERR_INVALID, "the same (ref sample, exp sample) pair is listed twice");
-  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "region with chromosome/sample index out of range, negative start, or reference region beyond its chrom_span_hint");
+  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "region with chromosome/sample index out of range, negative start, reference region beyond its chrom_span_hint, or reference rows not in the promised (chrom, start) order");
 
   res->rows = n_rows;
   res->kind = 1;
@@ -545,7 +545,7 @@ static void run_difference(gmql_ctx* ctx, const DevRegions& ref, const DevRegion
 
   LinMap lm = spans.map();
   IntervalIndex<K> ix;
-  build_index<K>(ctx, ref, nullptr, 1, lm, &ix, false, ref.span_hint ? bad.p : (int*)nullptr);
+  build_index<K>(ctx, ref, nullptr, 1, lm, &ix, false, (ref.span_hint || ref.sorted_hint) ? bad.p : (int*)nullptr);
   int tbl_shift = 0;
   {
     int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)MS_MAX_TBL - 2, 16 * std::max<int64_t>(n_ref, 1)));
@@ -582,8 +582,8 @@ static void run_difference(gmql_ctx* ctx, const DevRegions& ref, const DevRegion
   int h_bad = 0;
   CUDA_TRY(cudaMemcpyAsync(&n_out, excl.p + n_ref, sizeof n_out, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "region with chromosome/sample index out of range, negative start, or reference region beyond its chrom_span_hint");
+  CUDA_TRY(GMQL_SYNC(ctx));
+  GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "region with chromosome/sample index out of range, negative start, reference region beyond its chrom_span_hint, or reference rows not in the promised (chrom, start) order");
   DevBuf<int32_t> rows(ctx, n_out);
   if (n_ref && n_out) LAUNCH(ctx, k_diff_compact, grid_for(ctx, n_ref, 256), 256, 0, keep.p, excl.p, n_ref, rows.p);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
@@ -602,6 +602,7 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
     ctx->pin_next = 0;
+    gmql_trace("ENTER gmql_map");
     GMQL_REQUIRE(ref && exp, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_pairs >= 0 && (n_pairs == 0 || pairs), GMQL_ERR_INVALID, "bad pair list");
     GMQL_REQUIRE(ref->n_chrom == exp->n_chrom, GMQL_ERR_INVALID, "ref and exp must share one chromosome dictionary (n_chrom differs)");
@@ -619,8 +620,9 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
     res = new gmql_result();
     if (spans.G < 0xffffffffull) run_map<uint32_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
     else run_map<uint64_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
     *out = res;
+    gmql_trace("EXIT");
     return GMQL_OK;
   } catch (const gmql_error& ex) {
     ctx->err = ex.what();
@@ -656,8 +658,9 @@ extern "C" int gmql_difference(gmql_ctx* ctx, const gmql_regions* ref, const gmq
     res = new gmql_result();
     if (spans.G < 0xffffffffull) run_difference<uint32_t>(ctx, dref, dexp, pairs, n_pairs, exact != 0, spans, res);
     else run_difference<uint64_t>(ctx, dref, dexp, pairs, n_pairs, exact != 0, spans, res);
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
     *out = res;
+    gmql_trace("EXIT");
     return GMQL_OK;
   } catch (const gmql_error& ex) {
     ctx->err = ex.what();

@@ -92,7 +92,7 @@ extern "C" int gmql_profile(gmql_ctx* ctx, const gmql_regions* in, gmql_result**
     cudaEventRecord(ctx->ev_k1, ctx->stream);
     int h_bad = 0;
     CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
     GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "sample index out of range");
     res = new gmql_result();
     res->rows = ns;

@@ -81,7 +81,7 @@ static void build_span_table(gmql_ctx* ctx, const DevRegions* a, const DevRegion
   int bad = 0;
   CUDA_TRY(cudaMemcpyAsync(&G, t->coff.p + n_chrom, sizeof G, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(&bad, t->bad.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(!bad, GMQL_ERR_INVALID, "region with chromosome index out of range or negative coordinate");
   t->G = G;
 }
@@ -140,8 +140,9 @@ __global__ void k_index_stops_from_len(const K* __restrict__ starts, const uint3
 // bad (optional): set when a region lies outside its chromosome's span (span tables built from a caller's hint)
 template <typename K>
 __global__ void k_index_stops(const int32_t* __restrict__ chrom, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ blocks,
-                              int64_t n, LinMap lm, const uint32_t* __restrict__ rows, K* __restrict__ out, int* __restrict__ bad) {
+                              int64_t n, LinMap lm, const uint32_t* __restrict__ rows, K* __restrict__ out, int* __restrict__ bad, const K* __restrict__ check_sorted) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    if (check_sorted && k > 0 && check_sorted[k - 1] > check_sorted[k]) *bad = 1;   // caller promised sorted rows
     uint32_t i = rows[k];
     uint64_t blk = blocks ? blocks[i] : 0u;
     int c = chrom[i];
@@ -175,9 +176,12 @@ static void finish_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* blo
   if (n == 0) return;
   int g = grid_for(ctx, n, 256);
   uint64_t max_lin = n_blocks * lm.G;
-  radix_sort<K>(ctx, ix->start_a.p, ix->start_b.p, ix->row_a.p, ix->row_b.p, n, bits_for(max_lin), &ix->start, &ix->row);
+  // rows promised to be in (chrom, start) order need no sort (single block of the linear coordinate only); the promise is
+  // checked by k_index_stops
+  const bool presorted = r.sorted_hint && blocks == nullptr && !payload_len && bad != nullptr;
+  if (!presorted) radix_sort<K>(ctx, ix->start_a.p, ix->start_b.p, ix->row_a.p, ix->row_b.p, n, bits_for(max_lin), &ix->start, &ix->row);
   if (payload_len) LAUNCH(ctx, (k_index_stops_from_len<K>), g, 256, 0, ix->start, ix->row, n, ix->stop.p);
-  else LAUNCH(ctx, (k_index_stops<K>), g, 256, 0, r.chrom, r.stop, r.coord_bits, blocks, n, lm, ix->row, ix->stop.p, bad);
+  else LAUNCH(ctx, (k_index_stops<K>), g, 256, 0, r.chrom, r.stop, r.coord_bits, blocks, n, lm, ix->row, ix->stop.p, bad, presorted ? (const K*)ix->start : (const K*)nullptr);
   device_scan<K, K, OpMax<K>, true>(ctx, ix->stop.p, ix->pmax.p, n, (K*)nullptr);
 }
 

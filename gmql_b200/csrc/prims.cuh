@@ -144,11 +144,53 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin* __restri
   }
 }
 
+// small inputs: ONE block scans everything, 4 096 elements per iteration (one launch instead of three; for a few thousand
+// elements the launches, not the work, are what costs)
+constexpr int64_t SCAN_SMALL_MAX = 1 << 15;
+template <typename Tin, typename T, typename Op, bool INCLUSIVE>
+__global__ void __launch_bounds__(1024) k_scan_small(const Tin* in, T* out, int64_t n, T* total_out) {
+  Op op;
+  __shared__ T wt[32];
+  __shared__ T s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = Op::identity();
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 4096) {
+    const int64_t i0 = base + (int64_t)tid * 4;
+    T v[4];
+    T acc = Op::identity();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[j] = i0 + j < n ? (T)in[i0 + j] : Op::identity(); acc = op(acc, v[j]); }
+    T x = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { T y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x = op(y, x); }
+    if (lane == 31) wt[w] = x;
+    __syncthreads();
+    T b = s_carry;
+    for (int q = 0; q < w; ++q) b = op(b, wt[q]);
+    T prev = __shfl_up_sync(0xffffffffu, x, 1);
+    T run = lane == 0 ? b : op(b, prev);                    // exclusive prefix of this thread's four elements
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (INCLUSIVE) { run = op(run, v[j]); if (i0 + j < n) out[i0 + j] = run; }
+      else { if (i0 + j < n) out[i0 + j] = run; run = op(run, v[j]); }
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry = run;
+    __syncthreads();
+  }
+  if (total_out && tid == 0) *total_out = s_carry;
+}
+
 // out may alias in when Tin == T.  total (device pointer, optional) receives the reduction of all inputs.
 template <typename Tin, typename T, typename Op, bool INCLUSIVE>
 static void device_scan(gmql_ctx* ctx, const Tin* in, T* out, int64_t n, T* total_dev) {
   if (n <= 0) {
     if (total_dev) CUDA_TRY(cudaMemsetAsync(total_dev, 0, sizeof(T), ctx->stream));
+    return;
+  }
+  if (n <= SCAN_SMALL_MAX) {
+    LAUNCH(ctx, (k_scan_small<Tin, T, Op, INCLUSIVE>), 1, 1024, 0, in, out, n, total_dev);
     return;
   }
   int64_t tiles = ceil_div64(n, SCAN_TILE);

@@ -155,7 +155,7 @@ class RegionDataset:
                 k += 1
         return m
 
-    def as_c(self, dup_of=None, coord32=None, narrow=False):
+    def as_c(self, dup_of=None, coord32=None, narrow=False, sorted_by_position=False, chrom_span_hint=None):
         """Builds the gmql_regions struct over this dataset's numpy buffers.  Returns (struct, keepalive).
         narrow=True uses the ABI's compact encodings where they apply: 8/16-bit chromosome indices and, when the rows are
         ordered by sample, sample_offsets instead of a per-row sample column."""
@@ -215,4 +215,11 @@ class RegionDataset:
             d = np.ascontiguousarray(dup_of, dtype=np.int32)
             keep.append(d)
             r.dup_of = d.ctypes.data
+        if sorted_by_position:
+            r.sorted_by_position = 1
+        if chrom_span_hint is not None:
+            h = np.ascontiguousarray(chrom_span_hint, dtype=np.int64)
+            assert h.shape[0] == r.n_chrom
+            keep.append(h)
+            r.chrom_span_hint = h.ctypes.data
         return r, keep

@@ -1,0 +1,87 @@
+"""Optional input promises of the ABI (include/gmql_cuda.h): chrom_span_hint and sorted_by_position.  Honoured promises
+give the same result as the plain call; broken ones are errors, never wrong results."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from tests.randgen import rand_regions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ex():
+    from gmql_b200 import GMQLCudaExecutor
+    e = GMQLCudaExecutor()
+    yield e
+    e.close()
+
+
+def _map_counts(ex, c_ref, c_exp, n_pairs_samples):
+    from gmql_b200 import _lib as L
+    pairs = (L.Pair * n_pairs_samples)()
+    for b in range(n_pairs_samples):
+        pairs[b].left_sample, pairs[b].right_sample = 0, b
+    out = C.c_void_p()
+    rc = ex.lib.gmql_map(ex.ctx, C.byref(c_ref), C.byref(c_exp), pairs, n_pairs_samples, (L.Agg * 1)(), 0, C.byref(out))
+    if rc != 0:
+        return rc, ex.lib.gmql_last_error(ex.ctx)
+    n = int(ex.lib.gmql_result_column_len(out, L.COL_MAP_COUNT))
+    a = np.empty(n, np.int32)
+    ex._check(ex.lib.gmql_result_column_copy(ex.ctx, out, L.COL_MAP_COUNT, a.ctypes.data))
+    ex.lib.gmql_result_free(ex.ctx, out)
+    return 0, a
+
+
+def test_hints_honoured_and_violations_rejected(ex):
+    from gmql_b200 import RegionDataset
+    rng = random.Random(9)
+    ref = sorted(rand_regions(rng, 300, [1], chroms=("chr1", "chr2", "chr3"), n_vals=0, span=200000, max_len=3000), key=lambda r: (r[1], r[2]))
+    exp = rand_regions(rng, 3000, [10, 11], chroms=("chr1", "chr2", "chr3"), n_vals=0, span=200000, max_len=3000)
+    dr, de = RegionDataset.from_records(ref, [1]), RegionDataset.from_records(exp, [10, 11])
+    c_exp, k2 = de.as_c()
+    c_plain, k1 = dr.as_c()
+    rc, want = _map_counts(ex, c_plain, c_exp, 2)
+    assert rc == 0 and want.sum() > 0
+    spans = [int(dr.stop[dr.chrom == c].max()) for c in range(3)]
+    for kw in (dict(sorted_by_position=True), dict(chrom_span_hint=[s + 5 for s in spans]), dict(sorted_by_position=True, chrom_span_hint=[250000] * 3)):
+        c_ref, k = dr.as_c(**kw)
+        rc, got = _map_counts(ex, c_ref, c_exp, 2)
+        assert rc == 0 and np.array_equal(got, want), kw
+    # a reference region beyond its bound
+    c_ref, k = dr.as_c(chrom_span_hint=[spans[0] - 1, spans[1], spans[2]])
+    rc, msg = _map_counts(ex, c_ref, c_exp, 2)
+    assert rc < 0 and b"chrom_span_hint" in msg
+    # rows not in the promised order
+    shuffled = RegionDataset.from_records(ref[::-1], [1])
+    c_ref, k = shuffled.as_c(sorted_by_position=True)
+    rc, msg = _map_counts(ex, c_ref, c_exp, 2)
+    assert rc < 0 and b"order" in msg
+    # the same data without the promise is fine
+    c_ref, k = shuffled.as_c()
+    rc, got = _map_counts(ex, c_ref, c_exp, 2)
+    assert rc == 0 and int(got.sum()) == int(want.sum())
+
+
+def test_cover_result_view_carries_the_hints(ex):
+    """C = COVER(2,ANY) E; M = MAP() C E on the device-resident view equals MAP on the downloaded COVER rows."""
+    import gmql_b200 as G
+    from gmql_b200 import RegionDataset, _lib as L
+    rng = random.Random(10)
+    exp = rand_regions(rng, 2500, [10, 11, 12], chroms=("chr1", "chr2"), strands="*", n_vals=0, span=60000, max_len=900)
+    de = RegionDataset.from_records(exp, [10, 11, 12])
+    res, _ = ex.cover_raw("COVER", G.N(2), G.ANY(), [], None, de)
+    view = L.Regions()
+    ex._check(ex.lib.gmql_result_as_regions(ex.ctx, res.h, C.byref(view)))
+    assert view.sorted_by_position == 1 and view.chrom_span_hint
+    c_exp, k2 = de.as_c()
+    rc, got = _map_counts(ex, view, c_exp, 3)
+    assert rc == 0
+    cov = RegionDataset(de.chrom_names, res.column(L.COL_COV_CHROM, np.int32), res.column(L.COL_COV_START, np.int64), res.column(L.COL_COV_STOP, np.int64),
+                        np.zeros(res.rows(), np.int8), np.zeros(res.rows(), np.int32), np.array([0], np.int64))
+    c_cov, k3 = cov.as_c()
+    rc, want = _map_counts(ex, c_cov, c_exp, 3)
+    res.free()
+    assert rc == 0 and len(want) > 0 and np.array_equal(got, want)
