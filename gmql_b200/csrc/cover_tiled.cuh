@@ -31,11 +31,11 @@ constexpr int MAX_LOGW = 16;
 constexpr int THREADS = 512;
 constexpr int NWARPS = THREADS / 32;
 constexpr int MAXWORDS = (1 << MAX_LOGW) / 32;
-constexpr int CAP_EV = 12288;           // distinct event positions per tile
+constexpr int CAP_EV = 16384;           // distinct event positions per tile
 constexpr int MAXP = 512;               // pieces per tile
 constexpr int HCAP = 512;               // regions of the previous tile still open at the tile start
 constexpr uint32_t EXT = 0x80000000u;   // length payload bit: stop' = stop + 1
-constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 4 * CAP_EV + 2 * CAP_EV + 16 * HCAP + 32 * MAXP;
+constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 4 * CAP_EV + 16 * HCAP + 32 * MAXP;
 
 struct Cfg {
   int n_groups, n_classes;
@@ -277,6 +277,27 @@ __device__ __forceinline__ bool in_rng(const Cfg& c, int32_t mn0, int32_t mx0, i
   return d >= c.mn[g] && d <= c.mx[g];
 }
 
+// Positions of the tile's distinct events in rank order, read off the occupancy bitmap (no per-rank position array):
+// seek(k) finds the word holding rank k through the popcount prefix, next() walks the set bits upward.
+struct RankPos {
+  const uint32_t* bitmap; int w; uint32_t word;
+  __device__ __forceinline__ void seek(const uint32_t* bm, const uint16_t* wpre, int nW, int k) {
+    bitmap = bm;
+    int lo = 0, hi = nW;                                   // last word whose prefix is <= k: it holds rank k
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)wpre[mid] <= k) lo = mid; else hi = mid; }
+    w = lo;
+    word = bm[lo];
+    const int r = k - (int)wpre[lo];                       // drop the r lower set bits of the word
+    if (r > 0) word &= ~((2u << __fns(word, 0, r)) - 1u);
+  }
+  __device__ __forceinline__ uint32_t next() {             // tile-local position of the current rank; advances
+    while (word == 0) { ++w; word = bitmap[w]; }
+    const uint32_t pos = ((uint32_t)w << 5) + (uint32_t)__ffs(word) - 1u;
+    word &= word - 1u;
+    return pos;
+  }
+};
+
 constexpr int RC = 6;   // regions of the tile each thread keeps in registers (the rest are re-read from L1/L2)
 
 // GMAP4 contribution of one region per thread (block-uniform call): find the pieces it overlaps, accumulate with
@@ -323,8 +344,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
   uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
   uint16_t* wpre = (uint16_t*)(bitmap + MAXWORDS);         // [MAXWORDS] set bits before each word
   int32_t* delta = (int32_t*)(wpre + MAXWORDS);            // [CAP_EV] net +1/-1 per distinct position (by rank)
-  uint16_t* epos = (uint16_t*)(delta + CAP_EV);            // [CAP_EV] tile-local position of each rank
-  uint32_t* hinS = (uint32_t*)(epos + CAP_EV);             // [HCAP] regions still open at the tile start: start, length payload
+  uint32_t* hinS = (uint32_t*)(delta + CAP_EV);            // [HCAP] regions still open at the tile start: start, length payload
   uint32_t* hinL = hinS + HCAP;
   uint32_t* houtS = hinL + HCAP;                           // [HCAP] regions still open at the tile end (next tile's hin)
   uint32_t* houtL = houtS + HCAP;
@@ -449,7 +469,6 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
       uint32_t q = hinS[k] + (lp & ~EXT) + (lp >> 31) - tile_lo;
       int r = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
       atomicAdd(&delta[r], -1);
-      epos[r] = (uint16_t)q;
     }
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
@@ -457,12 +476,10 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
         uint32_t q = rsr[r] - tile_lo;
         int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
         atomicAdd(&delta[rk], 1);
-        epos[rk] = (uint16_t)q;
         uint32_t qe = q + (lpr[r] & ~EXT) + (lpr[r] >> 31);
         if (qe < W) {
           int r2 = wpre[qe >> 5] + __popc(bitmap[qe >> 5] & ((1u << (qe & 31)) - 1u));
           atomicAdd(&delta[r2], -1);
-          epos[r2] = (uint16_t)qe;
         }
       }
     }
@@ -471,12 +488,10 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
       uint32_t q = rs - tile_lo;
       int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
       atomicAdd(&delta[rk], 1);
-      epos[rk] = (uint16_t)q;
       uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
       if (qe < W) {
         int r2 = wpre[qe >> 5] + __popc(bitmap[qe >> 5] & ((1u << (qe & 31)) - 1u));
         atomicAdd(&delta[r2], -1);
-        epos[r2] = (uint16_t)qe;
       }
     }
     __syncthreads();
@@ -485,26 +500,41 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
     const int IT = ((total + THREADS - 1) / THREADS) | 1;  // ranks per thread; odd stride: conflict-free shared-memory access
     const int k0 = tid * IT < total ? tid * IT : total;
     const int k1 = k0 + IT < total ? k0 + IT : total;
-    int32_t csum = 0;
-    for (int k = k0; k < k1; ++k) csum += delta[k];
+    // per-thread chunk: net change and the range of the running depth relative to the chunk start
+    int32_t csum = 0, rmin = 0x7fffffff, rmax = -0x7fffffff;
+    for (int k = k0; k < k1; ++k) { csum += delta[k]; rmin = min(rmin, csum); rmax = max(rmax, csum); }
     int32_t tile_net;
     const int32_t d_start = depth_in + block_excl_scan(csum, &tile_net, scratch);
     // the state just before my first rank: in range iff the depth there is (the previous position belongs to the same
     // class unless the depth is 0, which is never in range)
-    const bool in0 = k0 < total ? in_rng<MULTI>(cfg, mn0, mx0, d_start, (uint64_t)tile_lo + epos[k0]) : false;
+    RankPos rp;                                            // positions are needed at transitions (and, with groups, everywhere)
+    uint32_t pos_k0 = 0;
+    if (MULTI && k0 < total) { rp.seek(bitmap, wpre, nW, k0); RankPos peek = rp; pos_k0 = peek.next(); }
+    const bool in0 = k0 < total ? in_rng<MULTI>(cfg, mn0, mx0, d_start, (uint64_t)tile_lo + pos_k0) : false;
+    const bool prev0 = k0 == 0 ? cont0 : in0;
+    // A chunk whose whole depth range stays inside [min, max] (and was inside before), or stays outside, has no
+    // transition: no walk needed.  With groups the thresholds depend on the position's class: always walk.
+    const bool has = k0 < k1;
+    bool quiet = !has;
+    if (!MULTI && has) {
+      const int32_t dlo = d_start + rmin, dhi = d_start + rmax;
+      const bool all_in = dlo >= mn0 && dhi <= mx0, all_out = dhi < mn0 || dlo > mx0;
+      quiet = (all_in && prev0) || (all_out && !prev0);
+    }
     int nopen = 0;
-    {
+    if (!quiet) {
       int32_t d = d_start;
-      bool prev_in = k0 == 0 ? cont0 : in0;
+      bool prev_in = prev0;
+      RankPos it = rp;
       for (int k = k0; k < k1; ++k) {
         d += delta[k];
-        bool cur = in_rng<MULTI>(cfg, mn0, mx0, d, (uint64_t)tile_lo + epos[k]);
+        bool cur = in_rng<MULTI>(cfg, mn0, mx0, d, (uint64_t)tile_lo + (MULTI ? it.next() : 0u));
         nopen += (cur && !prev_in) ? 1 : 0;
         prev_in = cur;
       }
     }
-    int32_t open_total;
-    const int32_t open_pre = block_excl_scan(nopen, &open_total, scratch);
+    int32_t open_total = 0, open_pre = 0;
+    if (__syncthreads_or(quiet ? 0 : 1)) open_pre = block_excl_scan(nopen, &open_total, scratch);   // block-uniform
     const int np = (cont0 ? 1 : 0) + open_total;
     if (np > MAXP) {
       if (tid == 0) *out.fail = 3;
@@ -517,28 +547,44 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
     __syncthreads();
     if (tid == 0 && cont0) atomicMax(&pacc[0], depth_in);
     {
-      int32_t d = d_start;
-      bool prev_in = k0 == 0 ? cont0 : in0;
-      int cur = (cont0 ? 1 : 0) + open_pre - 1;             // piece open at my first rank (when prev_in)
-      int32_t run_max = 0;
-      for (int k = k0; k < k1; ++k) {
-        d += delta[k];
-        uint32_t pos = tile_lo + epos[k];
-        bool cin = in_rng<MULTI>(cfg, mn0, mx0, d, pos);
-        if (cin) {
-          if (!prev_in) { ++cur; pst[cur] = pos; run_max = d; }
-          else if (d > run_max) run_max = d;
-        } else if (prev_in) {
-          pen[cur] = pos;
-          if (run_max > 0) atomicMax(&pacc[cur], run_max);
-          run_max = 0;
+      const int cur0 = (cont0 ? 1 : 0) + open_pre - 1;     // piece open at my first rank (when prev0)
+      if (!quiet) {
+        int32_t d = d_start;
+        bool prev_in = prev0;
+        int cur = cur0;
+        int32_t run_max = 0;
+        if (!MULTI) rp.seek(bitmap, wpre, nW, k0);
+        for (int k = k0; k < k1; ++k) {
+          d += delta[k];
+          uint32_t pos = tile_lo + rp.next();
+          bool cin = in_rng<MULTI>(cfg, mn0, mx0, d, pos);
+          if (cin) {
+            if (!prev_in) { ++cur; pst[cur] = pos; run_max = d; }
+            else if (d > run_max) run_max = d;
+          } else if (prev_in) {
+            pen[cur] = pos;
+            if (run_max > 0) atomicMax(&pacc[cur], run_max);
+            run_max = 0;
+          }
+          prev_in = cin;
         }
-        prev_in = cin;
+        if (prev_in && run_max > 0 && cur >= 0) atomicMax(&pacc[cur], run_max);
       }
-      if (prev_in && run_max > 0 && cur >= 0) atomicMax(&pacc[cur], run_max);
+      // quiet chunks inside a run only raise the run's maximum depth: one atomic per warp when all lanes agree on the run
+      const int32_t qmax = (quiet && has && prev0) ? d_start + rmax : 0;
+      const unsigned qm = __ballot_sync(0xffffffffu, qmax > 0);
+      if (qm) {
+        const int c0 = __shfl_sync(0xffffffffu, cur0, __ffs(qm) - 1);
+        if (__all_sync(0xffffffffu, qmax <= 0 || cur0 == c0)) {
+          const int32_t wmax = __reduce_max_sync(0xffffffffu, qmax);
+          if (lane == 0) atomicMax(&pacc[c0], wmax);
+        } else if (qmax > 0) atomicMax(&pacc[cur0], qmax);
+      }
     }
+    uint32_t last_pos = 0;
+    if (MULTI && total > 0) { RankPos lp; lp.seek(bitmap, wpre, nW, total - 1); last_pos = lp.next(); }
     // depth after the tile's last event, judged with that event's group (tile_lo + W - 1 may lie beyond the last class)
-    const bool reach_end = np > 0 && in_rng<MULTI>(cfg, mn0, mx0, depth_in + tile_net, (uint64_t)tile_lo + (total > 0 ? epos[total - 1] : 0));
+    const bool reach_end = np > 0 && in_rng<MULTI>(cfg, mn0, mx0, depth_in + tile_net, (uint64_t)tile_lo + last_pos);
     __syncthreads();
     if (tid == 0 && reach_end) pen[np - 1] = tile_lo + W;
     __syncthreads();
