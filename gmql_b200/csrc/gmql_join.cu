@@ -55,7 +55,7 @@ __device__ __forceinline__ void left_bins(const JoinCfg& c, int lstrand, int64_t
 }
 
 __device__ __forceinline__ bool first_round_ok(const JoinCfg& c, int lstrand, int64_t ls, int64_t le, int rstrand, int64_t rs, int64_t re, int64_t b0, int64_t* dist) {
-  if (re / c.B < b0) return false;                       // right bins must reach the left's first bin
+  if (re < b0 * c.B) return false;                       // right bins must reach the left's first bin: re / B < b0 (re, b0 >= 0)
   if (!strand_ok(lstrand, rstrand)) return false;        // :123
   int64_t d = join_distance(ls, le, rs, re);
   *dist = d;
@@ -74,6 +74,7 @@ __device__ __forceinline__ bool second_round_ok(const JoinCfg& c, int lstrand, i
 
 struct LeftSide {
   const int32_t* chrom; const void* start; const void* stop; int bits; const int8_t* strand; const int32_t* sample; const int64_t* eq; int64_t n;
+  const uint32_t* perm;   // optional: left rows in genome order (slot w handles row perm[w]); counts / offsets are per slot
 };
 template <typename K>
 struct RightIndex {
@@ -82,6 +83,7 @@ struct RightIndex {
   const int8_t* strand;    // per sorted entry
   const int32_t* sample;   // per sorted entry
   const int64_t* eq;       // per ORIGINAL row (or null)
+  const int4* packed;      // per sorted entry {local start, local stop, original row, strand} when the right coordinates are 32-bit, else null
 };
 
 // lower_bound over the sorted starts through the bucket table: two table reads and a search inside one bucket
@@ -134,7 +136,8 @@ __global__ void __launch_bounds__(256) k_join_scan(LeftSide L, RightIndex<K> R, 
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp; i < L.n; i += nwarps) {
+  for (int64_t slot = warp; slot < L.n; slot += nwarps) {
+    const int64_t i = L.perm ? (int64_t)L.perm[slot] : slot;
     int c = L.chrom[i];
     int64_t ls = ld_coord(L.start, L.bits, i), le = ld_coord(L.stop, L.bits, i);
     int lst = L.strand ? (int)L.strand[i] : 0;
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(256) k_join_scan(LeftSide L, RightIndex<K> R, 
     int64_t b0, b1;
     left_bins(cfg, lst, ls, le, &b0, &b1);
     int64_t total = 0;
-    int64_t wbase = WRITE ? off[i] : 0;
+    int64_t wbase = WRITE ? off[slot] : 0;
     if (b0 <= b1 && c >= 0 && c < lm.n_chrom) {
       int64_t lo, hi;
       window<K>(R, lm, 0ull, c, b0, b1, cfg.B, &lo, &hi);
@@ -171,19 +174,25 @@ __global__ void __launch_bounds__(256) k_join_scan(LeftSide L, RightIndex<K> R, 
         total += __popc(m);
       }
     }
-    if (!WRITE && lane == 0) cnt[i] = total;
+    if (!WRITE && lane == 0) cnt[slot] = total;
   }
 }
+
+constexpr int MD_WCAP = 8;   // candidates of one (left region, right sample) group kept in registers
 
 // ---- MD(k): warp per left region, one lane per allowed right sample, index keyed by sample -----------------------------
 template <typename K, bool WRITE>
 __global__ void __launch_bounds__(256) k_join_md(LeftSide L, RightIndex<K> R, LinMap lm, JoinCfg cfg, const int64_t* __restrict__ allow_off, const int32_t* __restrict__ allow_rs,
                                                  const int32_t* __restrict__ allow_pair, const int32_t* __restrict__ mult,
-                                                 int64_t* __restrict__ cnt, const int64_t* __restrict__ off, int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p) {
+                                                 int64_t* __restrict__ cnt, const int64_t* __restrict__ off, int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p,
+                                                 uint32_t* __restrict__ memo_lo, uint16_t* __restrict__ memo_ok, int64_t memo_stride) {
+  // memo (optional): the count pass records, per (slot, allowed sample) group handled in registers, the window start and the
+  // mask of emitted candidates; the write pass then only reads the rows back instead of repeating search and selection
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp; i < L.n; i += nwarps) {
+  for (int64_t slot = warp; slot < L.n; slot += nwarps) {
+    const int64_t i = L.perm ? (int64_t)L.perm[slot] : slot;
     int c = L.chrom[i];
     int64_t ls = ld_coord(L.start, L.bits, i), le = ld_coord(L.stop, L.bits, i);
     int lst = L.strand ? (int)L.strand[i] : 0;
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(256) k_join_md(LeftSide L, RightIndex<K> R, Li
     int64_t b0, b1;
     left_bins(cfg, lst, ls, le, &b0, &b1);
     int64_t total = 0;
-    int64_t wbase = WRITE ? off[i] : 0;
+    int64_t wbase = WRITE ? off[slot] : 0;
     if (b0 <= b1 && c >= 0 && c < lm.n_chrom) {
       int64_t a0 = allow_off[la], a1 = allow_off[la + 1];
       int64_t m_dup = mult ? mult[i] : 1;
@@ -203,11 +212,68 @@ __global__ void __launch_bounds__(256) k_join_md(LeftSide L, RightIndex<K> R, Li
         int64_t lo = 0, hi = 0, thr = 0;
         int p = -1;
         uint64_t bbase = 0;
-        if (q < a1) {
+        int64_t dreg[MD_WCAP];
+        int rreg[MD_WCAP];
+        unsigned ok2 = 0;
+        int nreg = 0;
+        bool in_regs = false;
+        bool use_memo = false;
+        if (WRITE && memo_ok && q < a1) {
+          const uint16_t m = memo_ok[slot * memo_stride + (q - a0)];
+          if (!(m & 0x8000u)) {
+            use_memo = true; in_regs = true; nreg = MD_WCAP;
+            ok2 = m & 0xffu; mine = __popc(ok2);
+            lo = memo_lo[slot * memo_stride + (q - a0)];
+            p = allow_pair[q];
+          }
+        }
+        if (q < a1 && !use_memo) {
           int b = allow_rs[q];
           p = allow_pair[q];
           bbase = (uint64_t)b * lm.G;
           window<K>(R, lm, bbase, c, b0, b1, cfg.B, &lo, &hi);
+          if (R.packed && hi - lo <= MD_WCAP) {
+            // the usual case: a handful of candidates.  Load each ONCE (one 16-byte record), keep distance and flags in
+            // registers, select the k-th distance there
+            nreg = (int)(hi - lo);
+            int len = 0;
+#pragma unroll
+            for (int j = 0; j < MD_WCAP; ++j) {
+              dreg[j] = 0x7fffffffffffffffLL;
+              if (j < nreg) {
+                const int4 en = R.packed[lo + j];
+                int64_t d;
+                if (first_round_ok(cfg, lst, ls, le, en.w, (int64_t)en.x, (int64_t)en.y, b0, &d) && (!cfg.has_eq || R.eq[(uint32_t)en.z] == leq)) {
+                  dreg[j] = d; ++len;
+                  if (second_round_ok(cfg, lst, ls, le, (int64_t)en.x, (int64_t)en.y, d)) ok2 |= 1u << j;
+                }
+                rreg[j] = en.z;
+              }
+            }
+            if (len > 0) {
+              int64_t want = m_dup * len < cfg.k ? m_dup * len : cfg.k;   // count = min(len, k), identical left records pool their lists (:134)
+              int64_t idx = (want - 1) / m_dup;                           // position in the de-duplicated sorted list
+              // thr = the distance at sorted position idx = the smallest d_j with #{i : d_i <= d_j} > idx
+              thr = 0x7fffffffffffffffLL;
+              if (idx == 0) {                                             // MD(1): the minimum
+#pragma unroll
+                for (int j = 0; j < MD_WCAP; ++j) thr = dreg[j] < thr ? dreg[j] : thr;
+              } else
+#pragma unroll
+              for (int j = 0; j < MD_WCAP; ++j) {
+                if (dreg[j] == 0x7fffffffffffffffLL) continue;
+                int le_cnt = 0;
+#pragma unroll
+                for (int i2 = 0; i2 < MD_WCAP; ++i2) le_cnt += (dreg[i2] <= dreg[j]) ? 1 : 0;
+                if (le_cnt > idx && dreg[j] < thr) thr = dreg[j];
+              }
+#pragma unroll
+              for (int j = 0; j < MD_WCAP; ++j) if (dreg[j] <= thr && ((ok2 >> j) & 1u)) ++mine; else ok2 &= ~(1u << j);
+            } else ok2 = 0;
+            in_regs = true;
+            if (!WRITE && memo_ok) { memo_ok[slot * memo_stride + (q - a0)] = (uint16_t)ok2; memo_lo[slot * memo_stride + (q - a0)] = (uint32_t)lo; }
+          } else {
+          if (!WRITE && memo_ok) memo_ok[slot * memo_stride + (q - a0)] = 0x8000u;   // handled by the streaming path in both passes
           // first-round survivors of this (left region, right sample) group and their k-th smallest distance (:136-146)
           int64_t len = 0;
           for (int64_t k = lo; k < hi; ++k) {
@@ -248,12 +314,19 @@ __global__ void __launch_bounds__(256) k_join_md(LeftSide L, RightIndex<K> R, Li
             }
           }
         }
+          }
         // exclusive scan of `mine` across the warp
         int64_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int64_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
         int64_t chunk_total = __shfl_sync(0xffffffffu, incl, 31);
-        if (WRITE && mine > 0) {
+        if (WRITE && mine > 0 && in_regs) {
+          int64_t o = wbase + total + incl - mine;
+#pragma unroll
+          for (int j = 0; j < MD_WCAP; ++j) {
+            if (j < nreg && ((ok2 >> j) & 1u)) { out_l[o] = (int32_t)i; out_r[o] = use_memo ? R.packed[lo + j].z : rreg[j]; out_p[o] = p; ++o; }
+          }
+        } else if (WRITE && mine > 0) {
           int64_t o = wbase + total + incl - mine;
           for (int64_t k = lo; k < hi; ++k) {
             int64_t rs = (int64_t)((uint64_t)R.start[k] - bbase - cbase), re = (int64_t)((uint64_t)R.stop[k] - bbase - cbase);
@@ -268,7 +341,7 @@ __global__ void __launch_bounds__(256) k_join_md(LeftSide L, RightIndex<K> R, Li
         total += chunk_total;
       }
     }
-    if (!WRITE && lane == 0) cnt[i] = total;
+    if (!WRITE && lane == 0) cnt[slot] = total;
   }
 }
 
@@ -278,6 +351,14 @@ __global__ void k_join_payload(const uint32_t* __restrict__ rows, int64_t n, con
     uint32_t r = rows[k];
     s_strand[k] = strand ? strand[r] : (int8_t)0;
     s_sample[k] = sample ? sample[r] : 0;
+  }
+}
+
+// one 16-byte record per sorted entry: everything the MD round needs about a candidate in one load
+__global__ void k_join_packed(const uint32_t* __restrict__ rows, int64_t n, const int32_t* __restrict__ start, const int32_t* __restrict__ stop, const int8_t* __restrict__ strand, int4* __restrict__ out) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t r = rows[k];
+    out[k] = make_int4(start[r], stop[r], (int)r, strand ? (int)strand[r] : 0);
   }
 }
 
@@ -447,7 +528,12 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "sample index out of range in a region dataset");
 
+  // MD: visit the left regions in genome order, so that successive warps walk every right sample's index block forward and the
+  // few cache lines a (left region, right sample) group touches are still in L2 (the order of the output rows is free)
+  IntervalIndex<K> lix;
+  if (cfg.has_md && nl > 1) build_index<K>(ctx, left, nullptr, 1, lm, &lix);
   LeftSide L;
+  L.perm = (cfg.has_md && nl > 1) ? lix.row : nullptr;
   L.chrom = left.chrom; L.start = left.start; L.stop = left.stop; L.bits = left.coord_bits; L.strand = left.strand; L.sample = left.sample; L.eq = d_left_eq; L.n = nl;
   // bucket table over the linear start key (about two entries per bucket, at most 2^22 buckets)
   const uint64_t max_key = n_blocks * lm.G;
@@ -459,7 +545,13 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   const int64_t n_buckets = (int64_t)(max_key >> tbl_shift) + 1;
   DevBuf<uint32_t> tbl(ctx, n_buckets + 2);
   LAUNCH(ctx, (k_start_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, nr, tbl_shift, n_buckets, tbl.p);
+  DevBuf<int4> packed;
+  if (cfg.has_md && right.coord_bits == 32 && nr) {
+    packed.alloc(ctx, nr);
+    LAUNCH(ctx, k_join_packed, grid_for(ctx, nr, 256), 256, 0, ix.row, nr, (const int32_t*)right.start, (const int32_t*)right.stop, right.strand, packed.p);
+  }
   RightIndex<K> R;
+  R.packed = packed.p;
   R.tbl = tbl.p; R.tbl_shift = tbl_shift; R.n_buckets = n_buckets;
   R.start = ix.start; R.stop = ix.stop.p; R.pmax = ix.pmax.p; R.row = ix.row; R.n = nr; R.strand = s_strand.p; R.sample = s_sample.p; R.eq = d_right_eq;
 
@@ -473,10 +565,19 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
     LAUNCH(ctx, k_dup_mult, grid_for(ctx, nl, 256), 256, 0, left.dup_of, nl, dc.p, mult.p);
   }
 
+  // memo of the count pass for the write pass (6 bytes per (left region, allowed right sample) group), when it fits
+  DevBuf<uint32_t> memo_lo;
+  DevBuf<uint16_t> memo_ok;
+  int64_t memo_stride = 0;
+  if (cfg.has_md && R.packed && nl) {
+    for (int a = 0; a < n_ls; ++a) memo_stride = std::max<int64_t>(memo_stride, h_aoff[a + 1] - h_aoff[a]);
+    if (memo_stride > 0 && nl * memo_stride <= (int64_t)700000000) { memo_lo.alloc(ctx, nl * memo_stride); memo_ok.alloc(ctx, nl * memo_stride); }
+  }
   DevBuf<int64_t> cnt(ctx, nl + 1);
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nl, 8), (int64_t)ctx->num_sms * 16));
   if (nl) {
-    if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, false>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr);
+    if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, false>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
+                           memo_lo.p, memo_ok.p, memo_stride);
     else LAUNCH(ctx, (k_join_scan<K, false>), blocks, 256, 0, L, R, lm, cfg, d_pair.p, n_rs, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr);
   }
   device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, cnt.p, cnt.p, nl, cnt.p + nl);
@@ -486,7 +587,8 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   GMQL_REQUIRE(n_out < (int64_t)0x7fffffff * 8, GMQL_ERR_UNSUPPORTED, "join output too large for this version");
   DevBuf<int32_t> ol(ctx, n_out), orr(ctx, n_out), op(ctx, n_out);
   if (nl && n_out) {
-    if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, true>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p);
+    if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, true>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p,
+                           memo_lo.p, memo_ok.p, memo_stride);
     else LAUNCH(ctx, (k_join_scan<K, true>), blocks, 256, 0, L, R, lm, cfg, d_pair.p, n_rs, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p);
   }
 
