@@ -544,20 +544,33 @@ __global__ void k_summit_points(const uint64_t* __restrict__ keys, int64_t ne, c
   }
 }
 
-// one thread per bin: summitHelper (:269-316).  A piece is stored at the index of the point that emits it.
-__global__ void k_summit_bins(const uint64_t* __restrict__ pkey, const int32_t* __restrict__ pdelta, int64_t np, int64_t B, uint64_t G2, CoverCfg cfg,
-                              int32_t* __restrict__ emit, int64_t* __restrict__ pstart_off, int32_t* __restrict__ pval) {
+// first point of every bin -> compact list (so that the state machines below run with every lane busy)
+__global__ void k_summit_bin_heads(const uint64_t* __restrict__ pkey, int64_t np, int64_t B, int32_t* __restrict__ head) {
   const uint64_t W = (uint64_t)(B + 1);
-  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < np; m += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t bin = pkey[m] / W;
-    if (m > 0 && pkey[m - 1] / W == bin) continue;     // not the first point of its bin
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < np; m += (int64_t)gridDim.x * blockDim.x)
+    head[m] = (m == 0 || pkey[m - 1] / W != pkey[m] / W) ? 1 : 0;
+}
+__global__ void k_summit_bin_list(const int32_t* __restrict__ head, const int64_t* __restrict__ head_excl, int64_t np, uint32_t* __restrict__ bin_first) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < np; m += (int64_t)gridDim.x * blockDim.x)
+    if (head[m]) bin_first[head_excl[m]] = (uint32_t)m;
+}
+
+// one thread per bin: summitHelper (:269-316).  A piece is stored at the index of the point that emits it.
+__global__ void k_summit_bins(const uint64_t* __restrict__ pkey, const int32_t* __restrict__ pdelta, int64_t np, const uint32_t* __restrict__ bin_first, int64_t n_bins,
+                              int64_t B, uint64_t G2, CoverCfg cfg, int32_t* __restrict__ emit, int64_t* __restrict__ pstart_off, int32_t* __restrict__ pval) {
+  const uint64_t W = (uint64_t)(B + 1);
+  for (int64_t bi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bi < n_bins; bi += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = bin_first[bi];
+    const int64_t m_end = bi + 1 < n_bins ? (int64_t)bin_first[bi + 1] : np;
+    const uint64_t bin = pkey[m] / W;
+    const uint64_t bin_base = bin * W;
     int g = (int)((pkey[m] / G2) / (uint64_t)cfg.n_classes);
     int mn = cfg.mn[g], mx = cfg.mx[g];
     int64_t start = 0;
     int count = 0;
     bool valid = false, reentered = false, growing = false;
-    for (int64_t q = m; q < np && pkey[q] / W == bin; ++q) {
-      int64_t off = (int64_t)(pkey[q] % W);
+    for (int64_t q = m; q < m_end; ++q) {
+      int64_t off = (int64_t)(pkey[q] - bin_base);
       int nc = count + pdelta[q];
       bool nvalid = nc >= mn && nc <= mx;
       bool ngrow = nc > count || (growing && nc == count);
@@ -1001,9 +1014,17 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
   // per-bin state machines
   DevBuf<int32_t> emit(ctx, np), pval(ctx, np);
   DevBuf<int64_t> pso(ctx, np), emit_excl(ctx, np + 1);
-  emit.zero();
-  int pg = grid_for(ctx, np, 128, 1);
-  if (np) LAUNCH(ctx, k_summit_bins, pg, 128, 0, pkey.p, pdelta.p, np, B, G2, cfg, emit.p, pso.p, pval.p);
+  {
+    DevBuf<int32_t> bhead(ctx, np);
+    DevBuf<int64_t> bhead_excl(ctx, np + 1);
+    if (np) LAUNCH(ctx, k_summit_bin_heads, grid_for(ctx, np, 256), 256, 0, pkey.p, np, B, bhead.p);
+    device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, bhead.p, bhead_excl.p, np, bhead_excl.p + np);
+    const int64_t n_bins = read_back<int64_t>(ctx, bhead_excl.p + np);
+    DevBuf<uint32_t> bin_first(ctx, n_bins);
+    GMQL_REQUIRE(np < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "SUMMIT: too many event points");
+    if (np) LAUNCH(ctx, k_summit_bin_list, grid_for(ctx, np, 256), 256, 0, bhead.p, bhead_excl.p, np, bin_first.p);
+    if (n_bins) LAUNCH(ctx, k_summit_bins, grid_for(ctx, n_bins, 128, 1), 128, 0, pkey.p, pdelta.p, np, bin_first.p, n_bins, B, G2, cfg, emit.p, pso.p, pval.p);
+  }
   device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, emit.p, emit_excl.p, np, emit_excl.p + np);
   int64_t npieces = read_back<int64_t>(ctx, emit_excl.p + np);
   DevBuf<uint32_t> qcls(ctx, npieces); DevBuf<int32_t> qchrom(ctx, npieces), qval(ctx, npieces); DevBuf<int64_t> qs(ctx, npieces), qe(ctx, npieces);
