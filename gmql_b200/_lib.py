@@ -30,6 +30,11 @@ class Pair(C.Structure):
     _fields_ = [("left_sample", C.c_int32), ("right_sample", C.c_int32)]
 
 
+class TextSchema(C.Structure):
+    _fields_ = [("chr_pos", C.c_int32), ("start_pos", C.c_int32), ("stop_pos", C.c_int32), ("strand_pos", C.c_int32),
+                ("n_values", C.c_int32), ("value_pos", C.c_void_p), ("start_minus_one", C.c_int32)]
+
+
 class Atom(C.Structure):
     _fields_ = [("kind", C.c_int32), ("arg", C.c_int64)]
 
@@ -42,7 +47,7 @@ EXPORTS = [
     "gmql_result_column_elem_size", "gmql_result_column_device", "gmql_result_column_copy",
     "gmql_result_as_regions", "gmql_result_free", "gmql_last_device_ms", "gmql_last_h2d_ms",
     "gmql_dataset_upload", "gmql_dataset_free", "gmql_ctx_set_profiling", "gmql_ctx_profile_report",
-    "gmql_difference", "gmql_profile",
+    "gmql_difference", "gmql_profile", "gmql_parse_text",
 ]
 
 _lib = None
@@ -72,6 +77,7 @@ def load_library(path=None):
     lib.gmql_host_free.restype = None
     lib.gmql_map.argtypes = [vp, C.POINTER(Regions), C.POINTER(Regions), C.POINTER(Pair), i64, C.POINTER(Agg), i32, C.POINTER(vp)]
     lib.gmql_difference.argtypes = [vp, C.POINTER(Regions), C.POINTER(Regions), C.POINTER(Pair), i64, i32, C.POINTER(vp)]
+    lib.gmql_parse_text.argtypes = [vp, C.c_char_p, i64, i32, C.POINTER(TextSchema), C.POINTER(C.c_char_p), i32, C.POINTER(vp)]
     lib.gmql_profile.argtypes = [vp, C.POINTER(Regions), C.POINTER(vp)]
     lib.gmql_cover.argtypes = [vp, C.POINTER(Regions), vp, i32, i32, vp, vp, i64, C.POINTER(Agg), i32, C.POINTER(vp)]
     lib.gmql_cover_count_samples.argtypes = [vp, C.POINTER(Regions), C.POINTER(i32)]
@@ -109,4 +115,5 @@ COL_COV_GROUP, COL_COV_CHROM, COL_COV_START, COL_COV_STOP, COL_COV_STRAND, COL_C
 COL_JOIN_LEFT_ROW, COL_JOIN_RIGHT_ROW, COL_JOIN_PAIR, COL_JOIN_START, COL_JOIN_STOP, COL_JOIN_STRAND, COL_JOIN_CHROM = 32, 33, 34, 35, 36, 37, 38
 COL_DIFF_REF_ROW = 48
 COL_PROF_LEFTMOST, COL_PROF_RIGHTMOST, COL_PROF_MIN_LENGTH, COL_PROF_MAX_LENGTH, COL_PROF_SUM_LENGTH, COL_PROF_SUM_LENGTH_SQ, COL_PROF_COUNT = 64, 65, 66, 67, 68, 69, 70
+COL_TXT_LINE_OFFSET, COL_TXT_STATUS, COL_TXT_CHROM, COL_TXT_START, COL_TXT_STOP, COL_TXT_STRAND = 80, 81, 82, 83, 84, 85
 COL_AGG_VALUE, COL_AGG_VALID = 256, 512

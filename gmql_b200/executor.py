@@ -191,6 +191,37 @@ class GMQLCudaExecutor:
         recs = ref.to_records()
         return [(long_id(recs[i][0]), recs[i][1], recs[i][2], recs[i][3], recs[i][4], tuple(recs[i][5])) for i in rows]
 
+    # ---- TEXT -> columns ---------------------------------------------------------------------------------------------------
+    def parse_text(self, text, parser="NarrowPeakParser", chrom_names=None, start_minus_one=False):
+        """Parses one sample file's tab-separated text on the device (gmql_parse_text; BedParser.region_parser,
+        loaders/BedParser.scala:112-172).  parser: a key of regions.PARSERS or a tuple (chr, start, stop, strand|None,
+        [(pos, "DOUBLE"|"STRING"), ...]).  Returns a dict of numpy columns: line_offset, status, chrom, start, stop, strand,
+        values (list of (float64[n], uint8[n]) for the DOUBLE columns, in schema order) and chrom_names.  String columns
+        stay in the text (line_offset locates them)."""
+        from .regions import PARSERS
+        chr_pos, start_pos, stop_pos, strand_pos, other = PARSERS[parser] if isinstance(parser, str) else parser
+        data = text if isinstance(text, (bytes, bytearray)) else text.encode("utf-8")
+        if chrom_names is None:      # the caller normally knows the assembly; otherwise one cheap host scan of the first column
+            chrom_names = sorted({ln.split(b"\t", 1)[0].strip().decode() for ln in data.split(b"\n") if ln and not ln.startswith(b"#")})
+        vpos = np.array([p for (p, typ) in other if typ != "STRING"], dtype=np.int32)
+        sch = L.TextSchema()
+        sch.chr_pos, sch.start_pos, sch.stop_pos = chr_pos, start_pos, stop_pos
+        sch.strand_pos = -1 if strand_pos is None else strand_pos
+        sch.n_values = len(vpos)
+        sch.value_pos = vpos.ctypes.data if len(vpos) else None
+        sch.start_minus_one = 1 if start_minus_one else 0
+        names = (C.c_char_p * max(1, len(chrom_names)))(*[n.encode() for n in chrom_names])
+        out = C.c_void_p()
+        self._check(self.lib.gmql_parse_text(self.ctx, bytes(data), len(data), 0, C.byref(sch), names, len(chrom_names), C.byref(out)))
+        res = _Result(self, out)
+        cols = dict(line_offset=res.column(L.COL_TXT_LINE_OFFSET, np.int64), status=res.column(L.COL_TXT_STATUS, np.uint8),
+                    chrom=res.column(L.COL_TXT_CHROM, np.int32), start=res.column(L.COL_TXT_START, np.int64),
+                    stop=res.column(L.COL_TXT_STOP, np.int64), strand=res.column(L.COL_TXT_STRAND, np.int8),
+                    values=[(res.column(L.COL_AGG_VALUE + k, np.float64), res.column(L.COL_AGG_VALID + k, np.uint8)) for k in range(len(vpos))],
+                    chrom_names=list(chrom_names))
+        res.free()
+        return cols
+
     # ---- PROFILE ----------------------------------------------------------------------------------------------------------
     def profile(self, ds):
         """Per-sample statistics of Profiler.profile (GMQL-Profiler/.../Profilers/Profiler.scala:124-153): returns

@@ -235,6 +235,35 @@ int gmql_difference(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* 
  */
 int gmql_profile(gmql_ctx* ctx, const gmql_regions* in, gmql_result** out);
 
+/* ---- TEXT -> columns --------------------------------------------------------------------
+ * Replaces the per-line work of BedParser.region_parser (GMQL-Spark/.../loaders/BedParser.scala:112-172; the concrete
+ * parsers are column layouts: NarrowPeakParser :295-303, RnaSeqParser :346-348, BedScoreParser :525-527, custom schemas
+ * :357-507): tab split, trim, strand "+" / "-" else '*', optional start - 1 for 1-based schemas (:164), numeric values
+ * through String.toDouble with "null" / "." -> GNull (:30-48), '#' and empty lines skipped (:173-203).
+ * `text` is one sample file (or several concatenated): n_bytes of tab-separated lines in `location`.  chrom_names is the
+ * caller's chromosome dictionary (HOST strings); a name outside it yields chrom = -1 and status bit 2.
+ *
+ * Result: one row per kept line, in file order:
+ *   GMQL_COL_TXT_LINE_OFFSET int64 (byte offset of the line: string columns stay in the text),
+ *   GMQL_COL_TXT_STATUS uint8: 0 = parsed; bit 0 = a numeric field is left to the host's own parser (more than 19 significant
+ *     digits with an undecidable tail, or a syntax beyond plain decimals: hex floats, NaN, Infinity, type suffixes) — its
+ *     value is 0 / invalid here; bit 1 = malformed line (missing columns, bad integer: the reference throws, :173-203);
+ *     bit 2 = chromosome name not in the dictionary,
+ *   GMQL_COL_TXT_CHROM int32, GMQL_COL_TXT_START int64, GMQL_COL_TXT_STOP int64, GMQL_COL_TXT_STRAND int8,
+ *   GMQL_COL_AGG_VALUE + k double, GMQL_COL_AGG_VALID + k uint8 for the k-th requested value column.
+ * Doubles are correctly rounded (Eisel-Lemire), i.e. bit-identical to Double.parseDouble, whenever status bit 0 is clear.
+ * The device columns can be handed to the operators as a GMQL_LOC_DEVICE gmql_regions (coord_bits = 64).
+ */
+typedef struct {
+  int32_t chr_pos, start_pos, stop_pos;   /* 0-based column of each field */
+  int32_t strand_pos;                     /* < 0: the format has no strand column (every region '*') */
+  int32_t n_values;                       /* numeric value columns to extract (<= 16) */
+  const int32_t* value_pos;               /* HOST [n_values] */
+  int32_t start_minus_one;                /* 1-based schemas */
+} gmql_text_schema;
+int gmql_parse_text(gmql_ctx* ctx, const char* text, int64_t n_bytes, int32_t location, const gmql_text_schema* schema,
+                    const char* const* chrom_names, int32_t n_chrom, gmql_result** out);
+
 /* ---- results --------------------------------------------------------------------------- */
 enum {
   GMQL_COL_MAP_ROW_OFFSETS = 1, GMQL_COL_MAP_REF_ROW = 2, GMQL_COL_MAP_REF_SAMPLE_OFFSETS = 3, GMQL_COL_MAP_COUNT = 4,
@@ -246,6 +275,8 @@ enum {
   GMQL_COL_DIFF_REF_ROW = 48,
   GMQL_COL_PROF_LEFTMOST = 64, GMQL_COL_PROF_RIGHTMOST = 65, GMQL_COL_PROF_MIN_LENGTH = 66, GMQL_COL_PROF_MAX_LENGTH = 67,
   GMQL_COL_PROF_SUM_LENGTH = 68, GMQL_COL_PROF_SUM_LENGTH_SQ = 69, GMQL_COL_PROF_COUNT = 70,
+  GMQL_COL_TXT_LINE_OFFSET = 80, GMQL_COL_TXT_STATUS = 81, GMQL_COL_TXT_CHROM = 82, GMQL_COL_TXT_START = 83, GMQL_COL_TXT_STOP = 84,
+  GMQL_COL_TXT_STRAND = 85,
   GMQL_COL_AGG_VALUE = 256, /* + aggregate index */
   GMQL_COL_AGG_VALID = 512  /* + aggregate index */
 };
