@@ -1,0 +1,113 @@
+"""BASELINE.json's full sizes (C2: 5e7 regions, C5: 1e8 regions) through size-independent properties: the two independent
+device paths of COVER agree row for row, HISTOGRAM's depth-weighted length equals the summed (extended) region lengths
+(linearity), COVER output is sorted, disjoint and never touching, and the MAP counts of the C5 pipeline add up to the number of
+(region, overlapped run) pairs computed by numpy from the runs alone."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ex():
+    from gmql_b200 import GMQLCudaExecutor
+    e = GMQLCudaExecutor()
+    yield e
+    e.close()
+
+
+def _upload(ex, ds):
+    from gmql_b200 import _lib as L
+    host, keep = ds.as_c(narrow=True)
+    dset, view = C.c_void_p(), L.Regions()
+    ex._check(ex.lib.gmql_dataset_upload(ex.ctx, C.byref(host), C.byref(dset), C.byref(view)))
+    return dset, view, keep
+
+
+def _cover(ex, view, flag, mn, mx, path=None):
+    from gmql_b200 import _lib as L
+    a, b = np.array([mn], np.int32), np.array([mx], np.int32)
+    if path:
+        os.environ["GMQL_COVER_PATH"] = path
+    try:
+        out = C.c_void_p()
+        ex._check(ex.lib.gmql_cover(ex.ctx, C.byref(view), None, 1, flag, a.ctypes.data, b.ctypes.data, 2000, (L.Agg * 1)(), 0, C.byref(out)))
+    finally:
+        os.environ.pop("GMQL_COVER_PATH", None)
+    return out
+
+
+def _cols(ex, res, ids_dtypes):
+    outs = []
+    for cid, dt in ids_dtypes:
+        n = int(ex.lib.gmql_result_column_len(res, cid))
+        a = np.empty(n, dtype=dt)
+        if n:
+            ex._check(ex.lib.gmql_result_column_copy(ex.ctx, res, cid, a.ctypes.data))
+        outs.append(a)
+    return outs
+
+
+def test_c2_full_size_properties(ex):
+    from gmql_b200 import synth, _lib as L
+    ds = synth.peak_samples(1000, 50000, 2, with_values=())
+    assert ds.n == 50_000_000
+    dset, view, keep = _upload(ex, ds)
+    ANYV = 2 ** 31 - 1
+    spec = [(L.COL_COV_CHROM, np.int32), (L.COL_COV_START, np.int64), (L.COL_COV_STOP, np.int64), (L.COL_COV_ACC, np.int32), (L.COL_COV_J1, np.float64), (L.COL_COV_J2, np.float64)]
+    # (1) the tile-resident path and the sort-and-merge path are independent algorithms: identical rows
+    rt, rs = _cover(ex, view, 0, 2, ANYV, "tiled"), _cover(ex, view, 0, 2, ANYV, "sort")
+    ct, cs = _cols(ex, rt, spec), _cols(ex, rs, spec)
+    ex.lib.gmql_result_free(ex.ctx, rt); ex.lib.gmql_result_free(ex.ctx, rs)
+    assert len(ct[0]) > 100000
+    for a, b in zip(ct, cs):
+        assert np.array_equal(a, b)
+    chrom, start, stop = ct[0], ct[1], ct[2]
+    key = chrom.astype(np.int64) << 32
+    assert np.all(stop > start) and np.all(np.diff(key + start) > 0)
+    same = chrom[1:] == chrom[:-1]
+    assert np.all(start[1:][same] > stop[:-1][same])                 # maximal runs never touch
+    assert int(ct[3].min()) >= 2
+    # (2) linearity: sum over HISTOGRAM(1,ANY) segments of depth x length == sum of the extended region lengths
+    rh = _cover(ex, view, 3, 1, ANYV)
+    hs, he, hacc = _cols(ex, rh, [(L.COL_COV_START, np.int64), (L.COL_COV_STOP, np.int64), (L.COL_COV_ACC, np.int32)])
+    ex.lib.gmql_result_free(ex.ctx, rh)
+    ext = ds.stop + ((ds.stop % 2000 == 0) & (ds.start // 2000 != ds.stop // 2000))
+    assert int(((he - hs) * hacc.astype(np.int64)).sum()) == int((ext - ds.start).sum())
+    ex.lib.gmql_dataset_free(ex.ctx, dset)
+
+
+def test_c5_full_size_pipeline(ex):
+    from gmql_b200 import synth, _lib as L
+    ds = synth.peak_samples(2000, 50000, 5, with_values=())
+    assert ds.n == 100_000_000
+    dset, view, keep = _upload(ex, ds)
+    cov = _cover(ex, view, 0, 2, 2 ** 31 - 1)
+    cview = L.Regions()
+    ex._check(ex.lib.gmql_result_as_regions(ex.ctx, cov, C.byref(cview)))
+    pairs = (L.Pair * 2000)()
+    for b in range(2000):
+        pairs[b].left_sample, pairs[b].right_sample = 0, b
+    mp = C.c_void_p()
+    ex._check(ex.lib.gmql_map(ex.ctx, C.byref(cview), C.byref(view), pairs, 2000, (L.Agg * 1)(), 0, C.byref(mp)))
+    chrom, start, stop = _cols(ex, cov, [(L.COL_COV_CHROM, np.int32), (L.COL_COV_START, np.int64), (L.COL_COV_STOP, np.int64)])
+    (count,) = _cols(ex, mp, [(L.COL_MAP_COUNT, np.int32)])
+    ex.lib.gmql_result_free(ex.ctx, cov); ex.lib.gmql_result_free(ex.ctx, mp)
+    n_runs = len(start)
+    assert count.shape[0] == 2000 * n_runs and count.min() >= 0
+    # runs are disjoint and sorted: a region overlaps the runs between the first run ending after its start and the last
+    # run starting before its stop
+    rk_s = (chrom.astype(np.int64) << 32) + start
+    rk_e = (chrom.astype(np.int64) << 32) + stop
+    ck = ds.chrom.astype(np.int64) << 32
+    first = np.searchsorted(rk_e, ck + ds.start, side="right")
+    last = np.searchsorted(rk_s, ck + ds.stop, side="left")
+    per_region = np.maximum(last - first, 0)
+    assert int(count.astype(np.int64).sum()) == int(per_region.sum())
+    # per experiment sample as well (rows of pair b are contiguous)
+    per_sample = np.bincount(ds.sample, weights=per_region, minlength=2000).astype(np.int64)
+    assert np.array_equal(count.reshape(2000, n_runs).astype(np.int64).sum(axis=1), per_sample)
+    ex.lib.gmql_dataset_free(ex.ctx, dset)
