@@ -20,6 +20,7 @@ struct MapAggPlan {
   // per aggregate
   int n_aggs = 0;
   int kind[16], slot[16];  // slot = index into the distinct-column tables
+  int need_bag = 0;        // some aggregate is BAG / BAGD: emit the matched experiment rows of every output row
 };
 
 struct MapAcc {
@@ -152,6 +153,7 @@ struct MapStreamArgs {
   const uint32_t* tbl; int tbl_shift; int n_tbl;   // n_tbl = entries of tbl (buckets + 2)
   int vec_ok;                                        // column pointers are 16-byte aligned
   uint8_t* hit; int exact;                           // DIFFERENCE: per reference row "some paired experiment region overlaps it"
+  const int64_t* bag_off; int32_t* bag_cursor; int32_t* bag_rows;   // BAG / BAGD: matched experiment rows of every output row
 };
 
 template <typename K>
@@ -171,8 +173,10 @@ __device__ __forceinline__ void map_hit(const MapStreamArgs<K>& a, const MapAggP
   }
 }
 
-// DIFF: instead of accumulating, mark the reference row (GenometricDifference.scala:58-69; `exact`: identical coordinates)
-template <typename K, bool DIFF>
+// MODE 0: accumulate.  MODE 1 (DIFFERENCE): mark the reference row instead (GenometricDifference.scala:58-69; `exact`: identical
+// coordinates).  MODE 2 (BAG / BAGD): append the experiment row to the output row's list (a second pass, after the counts
+// have been scanned into list offsets); the strings are built on the host from these lists.
+template <typename K, int MODE>
 __global__ void __launch_bounds__(MS_THREADS, 1) k_map_stream(MapStreamArgs<K> a, MapAggPlan plan, ExpCols ec, MapAcc acc) {
   extern __shared__ uint32_t s_tbl[];                   // [n_tbl] bucket table, then chromosome offsets / spans
   const bool chrom_sh = a.lm.n_chrom <= MS_MAX_CHROM;
@@ -243,7 +247,17 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_stream(MapStreamArgs<K> a
       RefEntry<K> en = ent[j];
       while (true) {
         if (en.stop > ls[j]) {
-          if (!DIFF) map_hit<K>(a, plan, ec, acc, en, smp[j], st[j], i0 + j);
+          if (MODE == 0) map_hit<K>(a, plan, ec, acc, en, smp[j], st[j], i0 + j);
+          else if (MODE == 2) {
+            if (strand_ok((int)(en.meta & 3u), st[j])) {
+              long long base = a.pair_base[(int64_t)(en.meta >> 2) * a.n_exp_samples + smp[j]];
+              if (base >= 0) {
+                int64_t row = base + en.rank;
+                int pos = atomicAdd(&a.bag_cursor[row], 1);
+                a.bag_rows[a.bag_off[row] + pos] = (int32_t)(i0 + j);
+              }
+            }
+          }
           else if (strand_ok((int)(en.meta & 3u), st[j]) && a.pair_base[(int64_t)(en.meta >> 2) * a.n_exp_samples + smp[j]] >= 0 &&
                    (!a.exact || (en.stop == lee[j] && a.r_start[k] == ls[j])))
             a.hit[en.rank] = 1;
@@ -283,6 +297,7 @@ __global__ void __launch_bounds__(256) k_map_finalize(int64_t n_rows, MapAggPlan
       double v = 0.0;
       uint8_t ok = 0;
       if (kind == GMQL_AGG_COUNT) { v = (double)(cnt < 0 ? 0 : cnt); ok = 1; }  // funOut = GDouble(count), DefaultRegionsToRegionFactory.scala:62
+      else if (kind == GMQL_AGG_BAG || kind == GMQL_AGG_BAGD) { v = 0.0; ok = 0; }  // host-built string (GMQL_COL_BAG_*)
       else {
         int nn = acc.nn[q][r];
         if (nn > 0) {
@@ -313,8 +328,7 @@ static void plan_aggs(const gmql_agg* aggs, int n_aggs, int n_cols_avail, MapAgg
     plan->kind[a] = kind;
     plan->slot[a] = -1;
     if (kind == GMQL_AGG_COUNT) continue;
-    GMQL_REQUIRE(kind != GMQL_AGG_BAG && kind != GMQL_AGG_BAGD, GMQL_ERR_UNSUPPORTED,
-                 "BAG/BAGD aggregates are built on the host from gmql_join-style match lists; not available in gmql_map yet");
+    if (kind == GMQL_AGG_BAG || kind == GMQL_AGG_BAGD) { plan->need_bag = 1; continue; }   // strings are built on the host from the match lists
     GMQL_REQUIRE(kind >= GMQL_AGG_SUM && kind <= GMQL_AGG_MEDIAN, GMQL_ERR_INVALID,
                  "unknown aggregate kind (user closures have no function_identifier and cannot run on the device)");
     int col = aggs[a].col;
@@ -332,6 +346,13 @@ static void plan_aggs(const gmql_agg* aggs, int n_aggs, int n_cols_avail, MapAgg
     if (kind == GMQL_AGG_MIN || kind == GMQL_AGG_MEDIAN) plan->need_min[q] = 1;
     if (kind == GMQL_AGG_MAX) plan->need_max[q] = 1;
   }
+}
+
+static int64_t read_back_i64(gmql_ctx* ctx, const int64_t* dev) {
+  int64_t v = 0;
+  CUDA_TRY(cudaMemcpyAsync(&v, dev, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(GMQL_SYNC(ctx));
+  return v;
 }
 
 template <typename K>
@@ -448,6 +469,10 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     ec.ok[q] = exp.valid[plan.col_id[q]];
   }
 
+  MapStreamArgs<K> ma_saved;
+  memset(&ma_saved, 0, sizeof ma_saved);
+  size_t sh_saved = 0;
+  int g_saved = 1;
   if (n_exp && n_ref && n_rows) {
     MapStreamArgs<K> ma;
     ma.e_chrom = exp.chrom; ma.e_start = exp.start; ma.e_stop = exp.stop; ma.e_bits = exp.coord_bits;
@@ -458,10 +483,29 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
     ma.vec_ok = al16(exp.chrom) && al16(exp.start) && al16(exp.stop) && al16(exp.sample) && ((uintptr_t)exp.strand & 3u) == 0;
     size_t sh = sizeof(uint32_t) * (size_t)((ma.n_tbl + 3) & ~3) + (lm.n_chrom <= MS_MAX_CHROM ? 16 * (size_t)lm.n_chrom : 0);
-    CUDA_TRY(cudaFuncSetAttribute((k_map_stream<K, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    CUDA_TRY(cudaFuncSetAttribute((k_map_stream<K, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     int g = (int)std::min<int64_t>(ceil_div64(n_exp, (int64_t)MS_THREADS * MS_PER), (int64_t)ctx->num_sms);
     ma.hit = nullptr; ma.exact = 0;
-    LAUNCH(ctx, (k_map_stream<K, false>), g, MS_THREADS, sh, ma, plan, ec, acc);
+    ma.bag_off = nullptr; ma.bag_cursor = nullptr; ma.bag_rows = nullptr;
+    LAUNCH(ctx, (k_map_stream<K, 0>), g, MS_THREADS, sh, ma, plan, ec, acc);
+    ma_saved = ma; sh_saved = sh; g_saved = g;
+  }
+  // BAG / BAGD: count -> scan -> write of the matched experiment rows
+  DevBuf<int64_t> bag_off;
+  DevBuf<int32_t> bag_rows;
+  if (plan.need_bag) {
+    bag_off.alloc(ctx, n_rows + 1);
+    device_scan<int, int64_t, OpSum<int64_t>, false>(ctx, count.p, bag_off.p, n_rows, bag_off.p + n_rows);
+    int64_t n_match = n_rows ? read_back_i64(ctx, bag_off.p + n_rows) : 0;
+    GMQL_REQUIRE(n_match < (int64_t)0x7fffffff * 4, GMQL_ERR_UNSUPPORTED, "BAG: match lists too large for this version");
+    bag_rows.alloc(ctx, n_match);
+    if (n_exp && n_ref && n_rows && n_match) {
+      DevBuf<int32_t> cursor(ctx, n_rows);
+      cursor.zero();
+      ma_saved.bag_off = bag_off.p; ma_saved.bag_cursor = cursor.p; ma_saved.bag_rows = bag_rows.p;
+      CUDA_TRY(cudaFuncSetAttribute((k_map_stream<K, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_saved));
+      LAUNCH(ctx, (k_map_stream<K, 2>), g_saved, MS_THREADS, sh_saved, ma_saved, plan, ec, acc);
+    }
   }
   if (ref.dup_of && n_pairs && n_rows)
     LAUNCH(ctx, k_mark_dups, (int)std::min<int64_t>(n_pairs, (int64_t)ctx->num_sms * 8), 128, 0, d_pl.p, row_off.p, n_pairs, sample_off.p, rows_by_sample, ref.dup_of, count.p);
@@ -494,6 +538,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   }
   result_add(res, GMQL_COL_MAP_REF_SAMPLE_OFFSETS, sample_off);
   result_add(res, GMQL_COL_MAP_COUNT, count);
+  if (plan.need_bag) { result_add(res, GMQL_COL_BAG_OFFSETS, bag_off); result_add(res, GMQL_COL_BAG_ROWS, bag_rows); }
   for (int a = 0; a < plan.n_aggs; ++a) {
     result_add(res, GMQL_COL_AGG_VALUE + a, ov[a]);
     result_add(res, GMQL_COL_AGG_VALID + a, ok[a]);
@@ -566,13 +611,14 @@ static void run_difference(gmql_ctx* ctx, const DevRegions& ref, const DevRegion
     auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
     ma.vec_ok = al16(exp.chrom) && al16(exp.start) && al16(exp.stop) && al16(exp.sample) && ((uintptr_t)exp.strand & 3u) == 0;
     ma.hit = hit.p; ma.exact = exact;
+    ma.bag_off = nullptr; ma.bag_cursor = nullptr; ma.bag_rows = nullptr;
     size_t sh = sizeof(uint32_t) * (size_t)((ma.n_tbl + 3) & ~3) + (lm.n_chrom <= MS_MAX_CHROM ? 16 * (size_t)lm.n_chrom : 0);
-    CUDA_TRY(cudaFuncSetAttribute((k_map_stream<K, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    CUDA_TRY(cudaFuncSetAttribute((k_map_stream<K, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     int g = (int)std::min<int64_t>(ceil_div64(n_exp, (int64_t)MS_THREADS * MS_PER), (int64_t)ctx->num_sms);
     MapAggPlan plan = MapAggPlan();
     ExpCols ec; memset(&ec, 0, sizeof ec);
     MapAcc acc; memset(&acc, 0, sizeof acc);
-    LAUNCH(ctx, (k_map_stream<K, true>), g, MS_THREADS, sh, ma, plan, ec, acc);
+    LAUNCH(ctx, (k_map_stream<K, 1>), g, MS_THREADS, sh, ma, plan, ec, acc);
   }
   DevBuf<int32_t> keep(ctx, n_ref);
   DevBuf<int64_t> excl(ctx, n_ref + 1);

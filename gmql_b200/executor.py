@@ -103,8 +103,8 @@ class GMQLCudaExecutor:
         arr = (L.Agg * max(1, len(aggs)))()
         for i, a in enumerate(aggs):
             arr[i].kind = a.kind
-            if a.function_identifier.upper() == "COUNT":
-                arr[i].col = 0
+            if a.function_identifier.upper() in ("COUNT", "BAG", "BAGD"):
+                arr[i].col = 0      # BAG / BAGD: the device emits match lists, the strings are built here (any column type)
             else:
                 if a.index not in colmap:
                     raise L.GmqlCudaError(-2, "aggregate %s on a non-numeric column (index %d) cannot run on the device" % (a.function_identifier, a.index))
@@ -150,6 +150,12 @@ class GMQLCudaExecutor:
         count = res.column(L.COL_MAP_COUNT, np.int32)
         vals = [res.column(L.COL_AGG_VALUE + k, np.float64) for k in range(len(aggregator))]
         oks = [res.column(L.COL_AGG_VALID + k, np.uint8) for k in range(len(aggregator))]
+        bag_slots = [q for q, a in enumerate(aggregator) if a.function_identifier.upper() in ("BAG", "BAGD")]
+        if bag_slots:
+            from .javafmt import bag_fold
+            bag_off = res.column(L.COL_BAG_OFFSETS, np.int64)
+            bag_rows = res.column(L.COL_BAG_ROWS, np.int32)
+            exp_records = experiments.with_chrom_names(sorted(set(reference.chrom_names) | set(experiments.chrom_names))).to_records()
         res.free()
         ref_records = ref.to_records()
         lidx = {int(s): i for i, s in enumerate(ref.sample_ids)}
@@ -164,7 +170,11 @@ class GMQLCudaExecutor:
                 if c < 0:
                     continue  # collapsed duplicate (MapKey)
                 rec = ref_records[row]
-                aggs = tuple((float(vals[q][base + k]) if oks[q][base + k] else None) for q in range(len(aggregator)))
+                aggs = [(float(vals[q][base + k]) if oks[q][base + k] else None) for q in range(len(aggregator))]
+                for q in bag_slots:      # matched experiment rows in input order, folded pairwise as the operators do
+                    rows_q = np.sort(bag_rows[bag_off[base + k]:bag_off[base + k + 1]])
+                    aggs[q] = bag_fold([exp_records[r][5][aggregator[q].index] for r in rows_q], aggregator[q].function_identifier.upper() == "BAGD") if c > 0 else None
+                aggs = tuple(aggs)
                 out.append((new_id, rec[1], rec[2], rec[3], rec[4], tuple(rec[5]) + (float(c),) + aggs))
         return out
 

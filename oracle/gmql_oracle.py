@@ -113,10 +113,31 @@ def _java_max(a: float, b: float) -> float:
 
 
 def _java_double_to_string(v: float) -> str:
-    """Double.toString for BAG (DefaultRegionsToRegionFactory.scala:139); adequate for test values."""
-    if v == int(v) and abs(v) < 1e7:
-        return "%.1f" % v
-    return repr(v)
+    """java.lang.Double.toString (BAG / BAGD, DefaultRegionsToRegionFactory.scala:139): decimal notation for
+    1e-3 <= |v| < 1e7, else d.dddE[-]n, shortest identifying digits (extreme subnormals, where the JDK prints more digits
+    than necessary, excepted)."""
+    if v != v:
+        return "NaN"
+    if math.isinf(v):
+        return "Infinity" if v > 0 else "-Infinity"
+    if v == 0.0:
+        return "-0.0" if math.copysign(1.0, v) < 0 else "0.0"
+    d = Decimal(repr(abs(v)))
+    sign, digs, exp = d.as_tuple()
+    digs = list(digs)
+    while len(digs) > 1 and digs[-1] == 0:
+        digs.pop()
+        exp += 1
+    ds = "".join(map(str, digs))
+    point = len(ds) + exp                      # position of the decimal point relative to the digit string
+    neg = "-" if v < 0 else ""
+    if 1e-3 <= abs(v) < 1e7:
+        if point <= 0:
+            return neg + "0." + "0" * (-point) + ds
+        if point >= len(ds):
+            return neg + ds + "0" * (point - len(ds)) + ".0"
+        return neg + ds[:point] + "." + ds[point:]
+    return "%s%s.%sE%d" % (neg, ds[0], ds[1:] or "0", point - 1)
 
 
 # --------------------------------------------------------------------------------------

@@ -77,3 +77,23 @@ def test_map_conf_test_map_shape(ex):
     got = ex.GenometricMap71(None, [Agg("MAX", 0), Agg("MIN", 0), Agg("SUM", 0), Agg("AVG", 0)], r, e)
     want = O.map_reference(ref, exp, pairs, [O.Agg("MAX", 0), O.Agg("MIN", 0), O.Agg("SUM", 0), O.Agg("AVG", 0)], 2000)
     assert canon(got, 7) == canon(want, 7)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_map_bag_and_bagd(ex, seed):
+    """BAG / BAGD (DefaultRegionsToRegionFactory.scala:128-168; in the reference's own matrix, conf/test_map.xml:92): the device
+    emits the matched experiment rows of every output row, the host folds them pairwise in experiment order — on numeric
+    columns (Double.toString forms, nulls as '.') and on string columns, next to COUNT and a numeric aggregate."""
+    from gmql_b200 import RegionDataset, Agg
+    rng = random.Random(600 + seed)
+    ref = rand_regions(rng, 60, [1, 2], n_vals=1, span=60000, max_len=4000)
+    ref = list({(r[0], r[1], r[2], r[3], r[4]): r for r in ref}.values())       # no duplicate reference records: their fold order is arbitrary
+    exp = rand_regions(rng, 500, [10, 11], n_vals=1, with_name=True, span=60000, max_len=3000, null_p=0.2)
+    exp = [(e[0], e[1], e[2], e[3], e[4], (e[5][0], e[5][1] if rng.random() > 0.3 else float(rng.choice([1e7, 1e-4, 12345678.5, 0.001, 3.0])))) for e in exp]
+    pairs = {1: [10, 11], 2: [11]}
+    aggs = [("BAG", 1), ("BAGD", 0), ("COUNT", 0), ("MAX", 1), ("BAGD", 1)]
+    got = ex.GenometricMap71([(a, b) for a, bs in pairs.items() for b in bs], [Agg(k, i) for k, i in aggs],
+                             RegionDataset.from_records(ref, [1, 2]), RegionDataset.from_records(exp, [10, 11]))
+    want = O.map_direct(ref, exp, pairs, [O.Agg(k, i) for k, i in aggs])
+    assert canon(got, 9) == canon(want, 9)
+    assert any(isinstance(r[5][-5], str) and "," in r[5][-5] for r in got)        # some multi-element bags were built
