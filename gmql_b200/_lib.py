@@ -18,7 +18,7 @@ class Regions(C.Structure):
         ("chrom", C.c_void_p), ("start", C.c_void_p), ("stop", C.c_void_p), ("strand", C.c_void_p),
         ("sample", C.c_void_p), ("n_chrom", C.c_int32), ("n_samples", C.c_int32), ("sample_ids", C.c_void_p),
         ("n_cols", C.c_int32), ("cols", C.POINTER(C.c_void_p)), ("valid", C.POINTER(C.c_void_p)),
-        ("dup_of", C.c_void_p), ("chrom_bits", C.c_int32), ("sample_offsets", C.c_void_p), ("chrom_span_hint", C.c_void_p), ("sorted_by_position", C.c_int32),
+        ("dup_of", C.c_void_p), ("chrom_bits", C.c_int32), ("sample_offsets", C.c_void_p), ("chrom_span_hint", C.c_void_p), ("stop_is_length", C.c_int32), ("sorted_by_position", C.c_int32),
     ]
 
 

@@ -101,6 +101,12 @@ static __global__ void k_widen_chrom(const T* __restrict__ in, int64_t n, int32_
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)in[i];
 }
 
+// stop = start + length (lengths sent as uint16 / uint32)
+template <typename C, typename LEN>
+static __global__ void k_stop_from_length(const C* __restrict__ start, const LEN* __restrict__ len, int64_t n, C* __restrict__ stop) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) stop[i] = start[i] + (C)len[i];
+}
+
 // sample_offsets (one run of rows per sample) -> per-row sample index; one block per sample, grid-stride
 static __global__ void k_expand_sample_offsets(const int64_t* __restrict__ off, int n_samples, int32_t* __restrict__ sample) {
   for (int s = blockIdx.x; s < n_samples; s += gridDim.x) {
@@ -142,7 +148,24 @@ void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector
     out->chrom = (const int32_t*)upload_array(ctx, r->chrom, n * 4, r->location, out);
   }
   out->start = upload_array(ctx, r->start, n * cb, r->location, out);
-  out->stop = upload_array(ctx, r->stop, n * cb, r->location, out);
+  GMQL_REQUIRE(r->stop_is_length == 0 || r->stop_is_length == 16 || r->stop_is_length == 32, GMQL_ERR_INVALID, "stop_is_length must be 0, 16 or 32");
+  if (r->stop_is_length) {
+    const size_t lw = (size_t)(r->stop_is_length / 8);
+    const void* raw = upload_array(ctx, r->stop, n * lw, r->location, out);
+    DevBuf<uint8_t> full(ctx, (int64_t)(n * cb ? n * cb : 1));
+    if (n) {
+      int g = (int)std::min<int64_t>(ceil_div64((int64_t)n, 256 * 4), (int64_t)ctx->num_sms * 16);
+      if (cb == 4 && lw == 2) LAUNCH(ctx, (k_stop_from_length<int32_t, uint16_t>), g, 256, 0, (const int32_t*)out->start, (const uint16_t*)raw, (int64_t)n, (int32_t*)full.p);
+      else if (cb == 4) LAUNCH(ctx, (k_stop_from_length<int32_t, uint32_t>), g, 256, 0, (const int32_t*)out->start, (const uint32_t*)raw, (int64_t)n, (int32_t*)full.p);
+      else if (lw == 2) LAUNCH(ctx, (k_stop_from_length<int64_t, uint16_t>), g, 256, 0, (const int64_t*)out->start, (const uint16_t*)raw, (int64_t)n, (int64_t*)full.p);
+      else LAUNCH(ctx, (k_stop_from_length<int64_t, uint32_t>), g, 256, 0, (const int64_t*)out->start, (const uint32_t*)raw, (int64_t)n, (int64_t*)full.p);
+    }
+    out->stop = full.p;
+    if (r->location != GMQL_LOC_DEVICE) out->owned.pop_back();   // the length copy is released in stream order
+    out->owned.push_back(std::move(full));
+  } else {
+    out->stop = upload_array(ctx, r->stop, n * cb, r->location, out);
+  }
   out->strand = (const int8_t*)upload_array(ctx, r->strand, n, r->location, out);
   if (!r->sample && r->sample_offsets) {
     const int64_t* off = r->sample_offsets;   // host array by contract

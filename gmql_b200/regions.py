@@ -188,6 +188,12 @@ class RegionDataset:
                 keep.append(cn)
                 r.chrom = cn.ctypes.data
                 r.chrom_bits = 8 if r.n_chrom <= 256 else 16
+            ln = self.stop - self.start
+            if int(ln.min(initial=0)) >= 0 and int(ln.max(initial=0)) < 65536:
+                l16 = ln.astype(np.uint16)
+                keep.append(l16)
+                r.stop = l16.ctypes.data
+                r.stop_is_length = 16
             if np.all(np.diff(self.sample) >= 0):
                 off = np.searchsorted(self.sample, np.arange(r.n_samples + 1), side="left").astype(np.int64)
                 keep.append(off)

@@ -90,6 +90,9 @@ typedef struct {
                                    without a pass over the data and a host round trip; a region beyond its bound is an
                                    error (GMQL_ERR_INVALID), never a wrong result.  Views made by gmql_result_as_regions
                                    carry it. */
+  int32_t stop_is_length;       /* 0: `stop` holds stop coordinates.  16 / 32: `stop` holds region LENGTHS (stop - start) as
+                                   uint16_t[] / uint32_t[] — narrowPeak-like data (lengths below 65 536) then crosses PCIe in
+                                   2 bytes instead of 4 or 8 per region; the stop column is rebuilt on the device. */
   int32_t sorted_by_position;   /* 1: the rows are ordered by (chrom index, start) — e.g. a COVER result or a sorted annotation.
                                    gmql_map / gmql_difference then index the reference side without sorting it; the order is
                                    verified on the device and a violation is an error (GMQL_ERR_INVALID). */
