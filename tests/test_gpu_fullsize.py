@@ -111,3 +111,56 @@ def test_c5_full_size_pipeline(ex):
     per_sample = np.bincount(ds.sample, weights=per_region, minlength=2000).astype(np.int64)
     assert np.array_equal(count.reshape(2000, n_runs).astype(np.int64).sum(axis=1), per_sample)
     ex.lib.gmql_dataset_free(ex.ctx, dset)
+
+
+def test_c4_full_size_join(ex):
+    """C4: 200 x 200 samples (1e6 promoters, 1e7 peaks).  DLE(10000): the number of output pairs equals the count numpy
+    derives from sorted starts / stops per chromosome, and every emitted pair satisfies the predicate; MD(1): every left
+    region keeps, per right sample, only candidates at its minimum distance (checked on the pairs themselves)."""
+    from gmql_b200 import synth, _lib as L
+    left = synth.promoter_samples(200, 5000, 4)
+    right = synth.peak_samples(200, 50000, 4, with_values=())
+    dl, vl, k1 = _upload(ex, left)
+    dr, vr, k2 = _upload(ex, right)
+    pairs = (L.Pair * (200 * 200))()
+    for a in range(200):
+        for b in range(200):
+            pairs[a * 200 + b].left_sample, pairs[a * 200 + b].right_sample = a, b
+
+    def join(atoms, builder, n_pairs=200 * 200):
+        at = (L.Atom * len(atoms))()
+        for i, (kd, arg) in enumerate(atoms):
+            at[i].kind, at[i].arg = kd, arg
+        out = C.c_void_p()
+        ex._check(ex.lib.gmql_join(ex.ctx, C.byref(vl), C.byref(vr), pairs, n_pairs, at, len(atoms), builder | 0x100, 5000, 100000, None, None, C.byref(out)))
+        lrow, rrow = _cols(ex, out, [(L.COL_JOIN_LEFT_ROW, np.int32), (L.COL_JOIN_RIGHT_ROW, np.int32)])
+        ex.lib.gmql_result_free(ex.ctx, out)
+        return lrow, rrow
+
+    def dist(lrow, rrow):
+        ls, le, rs, re_ = left.start[lrow], left.stop[lrow], right.start[rrow], right.stop[rrow]
+        m = np.minimum(np.abs(ls - re_), np.abs(rs - le))
+        return np.where((le < rs) | (re_ < ls), m, -m)
+
+    lrow, rrow = join([(0, 10001)], 4)                       # DLE(10000), CONTIG
+    want = 0
+    for c in range(24):
+        lm, rm = left.chrom == c, right.chrom == c
+        rs, re_ = np.sort(right.start[rm]), np.sort(right.stop[rm])
+        # distance < 10001  <=>  r.start < l.stop + 10001  and  r.stop > l.start - 10001 (strands are compatible: peaks are '*')
+        want += int((np.searchsorted(rs, left.stop[lm] + 10001, side="left") - np.searchsorted(re_, left.start[lm] - 10001, side="right")).sum())
+    assert len(lrow) == want and want > 5 * 10 ** 7
+    assert np.array_equal(left.chrom[lrow], right.chrom[rrow]) and int(dist(lrow, rrow).max()) < 10001
+    key = lrow.astype(np.int64) * right.n + rrow
+    assert len(np.unique(key)) == len(key)                  # no pair twice
+
+    lrow, rrow = join([(2, 1)], 2, 30 * 200)                 # MD(1), RIGHT; the first 30 left samples x every right sample
+    d = dist(lrow, rrow)
+    grp = lrow.astype(np.int64) * 200 + right.sample[rrow]  # (left region, right sample) group
+    o = np.argsort(grp, kind="stable")
+    g, dd = grp[o], d[o]
+    first = np.concatenate([[True], g[1:] != g[:-1]])
+    mins = np.minimum.reduceat(dd, np.nonzero(first)[0])
+    assert np.array_equal(dd, np.repeat(mins, np.diff(np.concatenate([np.nonzero(first)[0], [len(g)]]))))   # only minimum-distance candidates survive
+    assert len(lrow) >= int(first.sum()) > 10 ** 7 and np.array_equal(left.chrom[lrow], right.chrom[rrow])
+    ex.lib.gmql_dataset_free(ex.ctx, dl); ex.lib.gmql_dataset_free(ex.ctx, dr)
