@@ -1189,7 +1189,14 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     bool want = fits && (double)n * (double)(1ull << logw) / total >= 256.0;   // enough regions per tile for the tile pass to pay
     if (force && !strcmp(force, "tiled")) want = fits;
     if (force && !strcmp(force, "sort")) want = false;
-    if (want) done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, logw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc);
+    // A pile-up (many regions on a few kilobases, as real peak data has at promoters) can overflow one tile's tables:
+    // retry with tiles four and sixteen times narrower before giving the input to the sort-and-merge path
+    for (int attempt = 0; want && !done && attempt < 3; ++attempt) {
+      const int lw = logw - 2 * attempt;
+      if (lw < 8 || maxlen >= (int64_t)(1ll << lw) - 2) break;
+      done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc);
+      if (flw) break;                                  // a forced width is not second-guessed
+    }
   }
 
   if (!done) {

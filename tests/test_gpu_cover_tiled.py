@@ -168,3 +168,39 @@ def test_tiled_equals_sort_path_at_scale(ex):
         assert len(out["tiled"][0]) > 1000
         for a, b in zip(out["tiled"], out["sort"]):
             assert np.array_equal(a, b), flag
+
+
+def test_tiled_pile_up_retries_with_narrower_tiles(ex):
+    """A hotspot (40 000 regions inside 30 kb on top of a dense background) overflows a 65 536-wide tile's tables; the path
+    retries with narrower tiles instead of leaving the input to the sort-and-merge path, and the rows still equal that path's."""
+    from gmql_b200 import synth, N, ANY, RegionDataset, _lib as L
+    bg = synth.peak_samples(40, 50000, 7, with_values=())
+    rng = np.random.Generator(np.random.PCG64(3))
+    k = 40000
+    hs = 5_000_000 + rng.integers(0, 30000, k)
+    hot = RegionDataset(bg.chrom_names, np.concatenate([bg.chrom, np.zeros(k, np.int32)]), np.concatenate([bg.start, hs]),
+                        np.concatenate([bg.stop, hs + rng.integers(50, 400, k)]), np.zeros(bg.n + k, np.int8),
+                        np.concatenate([bg.sample, rng.integers(0, 40, k).astype(np.int32)]), bg.sample_ids)
+    out = {}
+    for path in ("tiled", "sort"):
+        os.environ["GMQL_COVER_PATH"] = path
+        ex.lib.gmql_ctx_set_profiling(ex.ctx, 1)
+        try:
+            res, _ = ex.cover_raw("COVER", N(3), ANY(), [], None, hot)
+        finally:
+            os.environ.pop("GMQL_COVER_PATH", None)
+        buf = C.create_string_buffer(1 << 16)
+        ex.lib.gmql_ctx_profile_report(ex.ctx, buf, len(buf))
+        ex.lib.gmql_ctx_set_profiling(ex.ctx, 0)
+        if path == "tiled":
+            rep = buf.value.decode()
+            line = [ln for ln in rep.splitlines() if "k_cover_tile" in ln][0]
+            assert int(line.rsplit(" ", 2)[1]) >= 2, rep          # the first width overflowed, a narrower one succeeded
+            assert "k_cover_runs_fused" not in rep
+        cols = [res.column(c, dt) for c, dt in ((L.COL_COV_CHROM, np.int32), (L.COL_COV_START, np.int64), (L.COL_COV_STOP, np.int64),
+                                                (L.COL_COV_ACC, np.int32), (L.COL_COV_J1, np.float64), (L.COL_COV_J2, np.float64))]
+        res.free()
+        out[path] = cols
+    assert len(out["tiled"][0]) > 100
+    for a, b in zip(out["tiled"], out["sort"]):
+        assert np.array_equal(a, b)
