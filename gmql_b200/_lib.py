@@ -35,6 +35,10 @@ class TextSchema(C.Structure):
                 ("n_values", C.c_int32), ("value_pos", C.c_void_p), ("start_minus_one", C.c_int32)]
 
 
+class CoverShard(C.Structure):
+    _fields_ = [("chrom_span", C.c_void_p), ("first_tile", C.c_int64), ("end_tile", C.c_int64)]
+
+
 class Atom(C.Structure):
     _fields_ = [("kind", C.c_int32), ("arg", C.c_int64)]
 
@@ -47,7 +51,7 @@ EXPORTS = [
     "gmql_result_column_elem_size", "gmql_result_column_device", "gmql_result_column_copy",
     "gmql_result_as_regions", "gmql_result_free", "gmql_last_device_ms", "gmql_last_h2d_ms",
     "gmql_dataset_upload", "gmql_dataset_free", "gmql_ctx_set_profiling", "gmql_ctx_profile_report",
-    "gmql_difference", "gmql_profile", "gmql_parse_text",
+    "gmql_difference", "gmql_profile", "gmql_parse_text", "gmql_cover_shard",
 ]
 
 _lib = None
@@ -80,6 +84,7 @@ def load_library(path=None):
     lib.gmql_parse_text.argtypes = [vp, C.c_char_p, i64, i32, C.POINTER(TextSchema), C.POINTER(C.c_char_p), i32, C.POINTER(vp)]
     lib.gmql_profile.argtypes = [vp, C.POINTER(Regions), C.POINTER(vp)]
     lib.gmql_cover.argtypes = [vp, C.POINTER(Regions), vp, i32, i32, vp, vp, i64, C.POINTER(Agg), i32, C.POINTER(vp)]
+    lib.gmql_cover_shard.argtypes = [vp, C.POINTER(Regions), i32, i32, i32, i64, C.POINTER(CoverShard), C.POINTER(vp)]
     lib.gmql_cover_count_samples.argtypes = [vp, C.POINTER(Regions), C.POINTER(i32)]
     lib.gmql_join.argtypes = [vp, C.POINTER(Regions), C.POINTER(Regions), C.POINTER(Pair), i64, C.POINTER(Atom), i32, i32, i64, i64, vp, vp, C.POINTER(vp)]
     lib.gmql_result_rows.argtypes = [vp]
@@ -112,6 +117,7 @@ def load_library(path=None):
 COL_MAP_ROW_OFFSETS, COL_MAP_REF_ROW, COL_MAP_REF_SAMPLE_OFFSETS, COL_MAP_COUNT = 1, 2, 3, 4
 COL_BAG_OFFSETS, COL_BAG_ROWS = 5, 6
 COL_COV_GROUP, COL_COV_CHROM, COL_COV_START, COL_COV_STOP, COL_COV_STRAND, COL_COV_ACC, COL_COV_J1, COL_COV_J2 = 16, 17, 18, 19, 20, 21, 22, 23
+COL_COV_EDGE, COL_COV_RAW_COUNT, COL_COV_RAW_START, COL_COV_RAW_STOP, COL_COV_RAW_SMIN, COL_COV_RAW_EMAX, COL_COV_RAW_SMAX, COL_COV_RAW_EMIN = 24, 25, 26, 27, 28, 29, 30, 31
 COL_JOIN_LEFT_ROW, COL_JOIN_RIGHT_ROW, COL_JOIN_PAIR, COL_JOIN_START, COL_JOIN_STOP, COL_JOIN_STRAND, COL_JOIN_CHROM = 32, 33, 34, 35, 36, 37, 38
 COL_DIFF_REF_ROW = 48
 COL_PROF_LEFTMOST, COL_PROF_RIGHTMOST, COL_PROF_MIN_LENGTH, COL_PROF_MAX_LENGTH, COL_PROF_SUM_LENGTH, COL_PROF_SUM_LENGTH_SQ, COL_PROF_COUNT = 64, 65, 66, 67, 68, 69, 70

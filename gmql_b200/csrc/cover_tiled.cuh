@@ -339,7 +339,7 @@ __device__ __forceinline__ void gmap4_round(bool valid, uint32_t rs, uint32_t re
 // its predecessor's regions in global memory.
 template <bool MULTI>
 static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* __restrict__ P /* .y = start key, .x = length payload */, const uint32_t* __restrict__ offS,
-                                                                  int64_t nT, int64_t n, int logw, Cfg cfg, Pieces out) {
+                                                                  int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, Pieces out) {
   extern __shared__ uint32_t sm[];
   uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
   uint16_t* wpre = (uint16_t*)(bitmap + MAXWORDS);         // [MAXWORDS] set bits before each word
@@ -364,18 +364,20 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
   const int WPT = (nW + THREADS - 1) / THREADS;            // bitmap words per thread (consecutive)
   const int32_t mn0 = cfg.mn0, mx0 = cfg.mx0;
 
-  // this block's tile range: first tile whose region offset reaches the block's share
+  // this block's tile range inside [t_lo, t_hi) (the whole genome, or the tiles one shard owns): first tile whose region
+  // offset reaches the block's share of the regions that start there
   int64_t t_begin, t_end;
   {
+    const uint32_t o_lo = offS[t_lo], o_hi = offS[t_hi];
     int64_t bounds[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int64_t c = (int64_t)blockIdx.x + q;
-      if (c <= 0) bounds[q] = 0;
-      else if (c >= (int64_t)gridDim.x) bounds[q] = nT;
+      if (c <= 0) bounds[q] = t_lo;
+      else if (c >= (int64_t)gridDim.x) bounds[q] = t_hi;
       else {
-        const uint32_t target = (uint32_t)((n * c) / (int64_t)gridDim.x);
-        int64_t lo = 0, hi = nT;
+        const uint32_t target = o_lo + (uint32_t)(((int64_t)(o_hi - o_lo) * c) / (int64_t)gridDim.x);
+        int64_t lo = t_lo, hi = t_hi;
         while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (offS[mid] < target) lo = mid + 1; else hi = mid; }
         bounds[q] = lo;
       }
@@ -705,6 +707,7 @@ static __global__ void k_piece_heads(const uint32_t* __restrict__ order, const u
 
 struct Runs {
   uint32_t* rstart; uint32_t* rend; int32_t* acc; int32_t* cnt; uint32_t* smin; uint32_t* emax; uint32_t* smax; uint32_t* emin;
+  int32_t* edge;   // bit 0: the run continues a run of the tile before the first piece (another shard's), bit 1: it reaches beyond its last piece's tile
 };
 
 static __global__ void k_piece_order(const uint32_t* __restrict__ blk_off, int nb, int64_t seg, int64_t np, uint32_t* __restrict__ order, Runs r) {
@@ -712,7 +715,7 @@ static __global__ void k_piece_order(const uint32_t* __restrict__ blk_off, int n
     int lo = 0, hi = nb;                                   // last block whose first index is <= g
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int64_t)blk_off[mid] <= g) lo = mid; else hi = mid; }
     order[g] = (uint32_t)((int64_t)lo * seg + (g - (int64_t)blk_off[lo]));
-    r.acc[g] = 0; r.cnt[g] = 0; r.emax[g] = 0; r.smax[g] = 0; r.smin[g] = 0xffffffffu; r.emin[g] = 0xffffffffu;
+    r.acc[g] = 0; r.cnt[g] = 0; r.emax[g] = 0; r.smax[g] = 0; r.smin[g] = 0xffffffffu; r.emin[g] = 0xffffffffu; r.edge[g] = 0;
   }
 }
 
@@ -720,8 +723,8 @@ static __global__ void k_piece_merge(const uint32_t* __restrict__ order, Pieces 
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
     uint32_t a = order[k];
     int64_t o = head[k] ? head_excl[k] : head_excl[k] - 1;
-    if (head[k]) r.rstart[o] = p.pstart[a];
-    if (k + 1 == np || head[k + 1]) r.rend[o] = p.pend[a];
+    if (head[k]) { r.rstart[o] = p.pstart[a]; if (p.flags[a] & 1) atomicOr(&r.edge[o], 1); }        // no piece before it here: the run comes from the previous shard
+    if (k + 1 == np || head[k + 1]) { r.rend[o] = p.pend[a]; if (p.flags[a] & 2) atomicOr(&r.edge[o], 2); }   // ... and goes on in the next one
     atomicMax(&r.acc[o], p.acc[a]);
     if (p.cnt[a]) {
       atomicAdd(&r.cnt[o], p.cnt[a]);
@@ -731,12 +734,20 @@ static __global__ void k_piece_merge(const uint32_t* __restrict__ order, Pieces 
   }
 }
 
+// shard mode: per run, the raw material a cross-shard merge needs (null pointers otherwise).  Coordinates are chromosome-local;
+// smin / emin = -1 and emax / smax = -1 when the run has no contributor on this shard.
+struct ShardRaw { int32_t* edge; int32_t* cnt; int64_t* rstart; int64_t* rstop; int64_t* smin; int64_t* emax; int64_t* smax; int64_t* emin; };
+
 // runs -> the arrays the common output stage (k_cover_compact) consumes
 static __global__ void k_runs_finalize(Runs r, int64_t nr, const int64_t* __restrict__ n_runs, LinMap lm, int flat, uint32_t* __restrict__ ocls, int32_t* __restrict__ ochrom, int64_t* __restrict__ fstart, int64_t* __restrict__ fstop,
-                                       int32_t* __restrict__ oacc, int32_t* __restrict__ keep, double* __restrict__ j1, double* __restrict__ j2) {
+                                       int32_t* __restrict__ oacc, int32_t* __restrict__ keep, double* __restrict__ j1, double* __restrict__ j2, ShardRaw raw) {
   const int64_t live = *n_runs;                  // entries [live, nr) are unused capacity
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nr; k += (int64_t)gridDim.x * blockDim.x) {
-    if (k >= live) { keep[k] = 0; ocls[k] = 0; ochrom[k] = 0; oacc[k] = 0; fstart[k] = 0; fstop[k] = 0; j1[k] = 0.0; j2[k] = 0.0; continue; }
+    if (k >= live) {
+      keep[k] = 0; ocls[k] = 0; ochrom[k] = 0; oacc[k] = 0; fstart[k] = 0; fstop[k] = 0; j1[k] = 0.0; j2[k] = 0.0;
+      if (raw.edge) { raw.edge[k] = 0; raw.cnt[k] = 0; raw.rstart[k] = 0; raw.rstop[k] = 0; raw.smin[k] = -1; raw.emax[k] = -1; raw.smax[k] = -1; raw.emin[k] = -1; }
+      continue;
+    }
     uint64_t x = r.rstart[k];
     uint64_t cls = x / lm.G, rem = x - cls * lm.G;
     int lo = 0, hi = lm.n_chrom;
@@ -746,6 +757,13 @@ static __global__ void k_runs_finalize(Runs r, int64_t nr, const int64_t* __rest
     int32_t cnt = r.cnt[k];
     ocls[k] = (uint32_t)cls; ochrom[k] = lo; oacc[k] = r.acc[k];
     keep[k] = cnt > 0 ? 1 : 0;                                     // GMAP4.scala:33-34,48
+    if (raw.edge) {
+      const int32_t eg = r.edge[k];
+      if (eg) keep[k] = 1;                                         // its contributors may all live on the neighbouring shard
+      raw.edge[k] = eg; raw.cnt[k] = cnt; raw.rstart[k] = cs; raw.rstop[k] = ce;
+      raw.smin[k] = cnt > 0 ? (int64_t)((uint64_t)r.smin[k] - base) : -1; raw.emax[k] = cnt > 0 ? (int64_t)((uint64_t)r.emax[k] - base) : -1;
+      raw.smax[k] = cnt > 0 ? (int64_t)((uint64_t)r.smax[k] - base) : -1; raw.emin[k] = cnt > 0 ? (int64_t)((uint64_t)r.emin[k] - base) : -1;
+    }
     if (cnt > 0) {
       uint64_t smin = r.smin[k], emax = r.emax[k], smax = r.smax[k], emin = r.emin[k];
       int64_t os = flat ? (int64_t)(smin - base) : cs, oe = flat ? (int64_t)(emax - base) : ce;   // :83-84

@@ -867,7 +867,7 @@ struct FinalCols {
 };
 __global__ void k_cover_compact(int64_t nc, const int32_t* __restrict__ keep, const int64_t* __restrict__ keep_excl, const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom,
                                 const int64_t* __restrict__ fstart, const int64_t* __restrict__ fstop, const int32_t* __restrict__ cacc, const double* __restrict__ j1, const double* __restrict__ j2,
-                                CovOut in, int n_aggs, int n_classes, int unified, FinalCols f, double* __restrict__ acc_d) {
+                                CovOut in, int n_aggs, int n_classes, int unified, FinalCols f, double* __restrict__ acc_d, tiled::ShardRaw raw_in, tiled::ShardRaw raw_out) {
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
     if (!keep[c]) continue;
     int64_t o = keep_excl[c];
@@ -881,6 +881,10 @@ __global__ void k_cover_compact(int64_t nc, const int32_t* __restrict__ keep, co
     acc_d[o] = (double)cacc[c];       // the view of the result as a region dataset exposes AccIndex as a value column
     f.j1[o] = j1[c];
     f.j2[o] = j2[c];
+    if (raw_in.edge) {
+      raw_out.edge[o] = raw_in.edge[c]; raw_out.cnt[o] = raw_in.cnt[c]; raw_out.rstart[o] = raw_in.rstart[c]; raw_out.rstop[o] = raw_in.rstop[c];
+      raw_out.smin[o] = raw_in.smin[c]; raw_out.emax[o] = raw_in.emax[c]; raw_out.smax[o] = raw_in.smax[c]; raw_out.emin[o] = raw_in.emin[c];
+    }
     for (int a = 0; a < n_aggs; ++a) { f.value[a][o] = in.value[a][c]; f.valid[a][o] = in.valid[a][c]; }
   }
 }
@@ -1043,14 +1047,20 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
   if (nr) LAUNCH(ctx, k_chain_merge, qg, 256, 0, qcls.p, qchrom.p, qs.p, qe.p, qval.p, npieces, chead.p, chead_excl.p, p1->cls.p, p1->chrom.p, p1->start.p, p1->stop.p, p1->acc.p);
 }
 
+struct ShardSpec { int64_t first_tile, end_tile; };
+struct ShardBufs { DevBuf<int32_t> edge, cnt; DevBuf<int64_t> rstart, rstop, smin, emax, smax, emin; };
+
 // host side of the tile-resident path; returns false (nothing consumed) when a capacity limit was hit and the caller must
 // fall back to the sort-and-merge path
 static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total, int logw,
                             const int32_t* h_mn, const int32_t* h_mx, Phase1Out* p1, DevBuf<int32_t>& keep, DevBuf<int64_t>& fstart, DevBuf<int64_t>& fstop,
-                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out) {
+                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb) {
   const int64_t n = in.n;
   const int key_bits = bits_for(n_classes_total * lm.G);
   const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
+  // the tiles this call owns: all of them, or one shard's range (the tile before the range only lends its open regions)
+  const int64_t t_lo = shard ? shard->first_tile : 0, t_hi = shard ? std::min<int64_t>(shard->end_tile, nT) : nT;
+  GMQL_REQUIRE(t_lo >= 0 && t_lo <= t_hi, GMQL_ERR_INVALID, "bad tile range");
   DevBuf<uint64_t> pk_a(ctx, n), pk_b(ctx, n);
   DevBuf<uint32_t> offS(ctx, nT + 1);
   uint64_t* P;
@@ -1079,7 +1089,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
 
   // two resident blocks per SM; four ranges per resident block even out the tail.  Every block publishes its pieces in
   // its own segment of the piece tables, so they come out in genome order and nothing has to be sorted.
-  const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(nT, (int64_t)ctx->num_sms * 8));
+  const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), (int64_t)ctx->num_sms * 8));
   const int64_t seg = std::max<int64_t>(4096, (n / 16 + 2 * nT) / tgrid + 1);
   const int64_t cap = seg * tgrid;
   GMQL_REQUIRE(cap < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "piece table too large");
@@ -1097,10 +1107,10 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
   if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, nT, n, logw, tc, pc);
+    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, nT, n, logw, tc, pc);
+    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc);
   }
   LAUNCH(ctx, tiled::k_seg_offsets, 1, 1024, 0, blk_cnt.p, (int)tgrid, blk_off.p, np_dev.p);
   unsigned long long h_np = 0;
@@ -1117,8 +1127,9 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   const int64_t nr = np;
   DevBuf<uint32_t> order_buf(ctx, np);
   DevBuf<uint32_t> rstart(ctx, nr), rend(ctx, nr), rsmin(ctx, nr), remax(ctx, nr), rsmax(ctx, nr), remin(ctx, nr);
-  DevBuf<int32_t> racc(ctx, nr), rcnt(ctx, nr);
+  DevBuf<int32_t> racc(ctx, nr), rcnt(ctx, nr), redge(ctx, nr);
   tiled::Runs rr;
+  rr.edge = redge.p;
   rr.rstart = rstart.p; rr.rend = rend.p; rr.acc = racc.p; rr.cnt = rcnt.p; rr.smin = rsmin.p; rr.emax = remax.p; rr.smax = rsmax.p; rr.emin = remin.p;
   if (np) LAUNCH(ctx, tiled::k_piece_order, grid_for(ctx, np, 256), 256, 0, blk_off.p, (int)tgrid, seg, np, order_buf.p, rr);
   const uint32_t* order = order_buf.p;
@@ -1130,14 +1141,22 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   p1->n = nr;
   p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->acc.alloc(ctx, nr);
   keep.alloc(ctx, nr); fstart.alloc(ctx, nr); fstop.alloc(ctx, nr); j1.alloc(ctx, nr); j2.alloc(ctx, nr);
-  if (nr) LAUNCH(ctx, tiled::k_runs_finalize, grid_for(ctx, nr, 256), 256, 0, rr, nr, (const int64_t*)(head_excl.p + np), lm, flag == GMQL_FLAT ? 1 : 0, p1->cls.p, p1->chrom.p, fstart.p, fstop.p, p1->acc.p, keep.p, j1.p, j2.p);
+  tiled::ShardRaw raw;
+  memset(&raw, 0, sizeof raw);
+  if (sb) {
+    sb->edge.alloc(ctx, nr); sb->cnt.alloc(ctx, nr); sb->rstart.alloc(ctx, nr); sb->rstop.alloc(ctx, nr);
+    sb->smin.alloc(ctx, nr); sb->emax.alloc(ctx, nr); sb->smax.alloc(ctx, nr); sb->emin.alloc(ctx, nr);
+    raw.edge = sb->edge.p; raw.cnt = sb->cnt.p; raw.rstart = sb->rstart.p; raw.rstop = sb->rstop.p;
+    raw.smin = sb->smin.p; raw.emax = sb->emax.p; raw.smax = sb->smax.p; raw.emin = sb->emin.p;
+  }
+  if (nr) LAUNCH(ctx, tiled::k_runs_finalize, grid_for(ctx, nr, 256), 256, 0, rr, nr, (const int64_t*)(head_excl.p + np), lm, flag == GMQL_FLAT ? 1 : 0, p1->cls.p, p1->chrom.p, fstart.p, fstop.p, p1->acc.p, keep.p, j1.p, j2.p, raw);
   *nc_out = nr;
   return true;
 }
 
 template <typename K>
 static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_sample_group, int n_groups, int flag, const int32_t* h_mn, const int32_t* h_mx, int64_t B,
-                      const CovAggPlan& plan, const SpanTable& spans, bool unified, bool has_zero, int64_t maxlen, gmql_result* res) {
+                      const CovAggPlan& plan, const SpanTable& spans, bool unified, bool has_zero, int64_t maxlen, gmql_result* res, const ShardSpec* shard = nullptr) {
   const int64_t n = in.n;
   CoverCfg cfg;
   cfg.n_groups = n_groups;
@@ -1176,6 +1195,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
 
   // ---- tile-resident path (cover_tiled.cuh): dense inputs, 32-bit keys, COVER / FLAT without aggregates
   bool done = false;
+  ShardBufs sbufs;
   if (sizeof(K) == 4 && n > 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) && !has_zero && plan.n_aggs == 0 &&
       n_classes_total * lm.G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
     // widest tile whose expected number of events leaves headroom in the kernel's tables
@@ -1185,20 +1205,23 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     const char* force = getenv("GMQL_COVER_PATH");   // "tiled" / "sort": test hook; default = density heuristic
     const char* flw = getenv("GMQL_COVER_LOGW");
     if (flw) logw = atoi(flw);
+    if (shard) logw = tiled::MAX_LOGW;                  // shards are cut on 65 536-position tiles
     bool fits = logw >= 8 && logw <= tiled::MAX_LOGW && maxlen < (int64_t)(1ll << logw) - 2;
     bool want = fits && (double)n * (double)(1ull << logw) / total >= 256.0;   // enough regions per tile for the tile pass to pay
     if (force && !strcmp(force, "tiled")) want = fits;
     if (force && !strcmp(force, "sort")) want = false;
+    if (shard) want = fits;
     // A pile-up (many regions on a few kilobases, as real peak data has at promoters) can overflow one tile's tables:
     // retry with tiles four and sixteen times narrower before giving the input to the sort-and-merge path
     for (int attempt = 0; want && !done && attempt < 3; ++attempt) {
       const int lw = logw - 2 * attempt;
       if (lw < 8 || maxlen >= (int64_t)(1ll << lw) - 2) break;
-      done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc);
-      if (flw) break;                                  // a forced width is not second-guessed
+      done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr);
+      if (flw || shard) break;                         // a forced width is not second-guessed
     }
   }
 
+  GMQL_REQUIRE(done || !shard, GMQL_ERR_UNSUPPORTED, "gmql_cover_shard needs the tile-resident path: COVER or FLAT without aggregates, one (group, strand) class, a linear genome below 2^32, no zero-length regions, regions shorter than 65 534 bases, and no tile denser than the kernel's tables");
   if (!done) {
   // interval index over the ORIGINAL coordinates (phase 2 contributors, GMAP4 uses the un-extended inputs)
   IntervalIndex<K> ix;
@@ -1287,8 +1310,19 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   memset(&f, 0, sizeof f);
   f.group = o_group.p; f.chrom = o_chrom.p; f.start = o_start.p; f.stop = o_stop.p; f.strand = o_strand.p; f.acc = o_acc.p; f.j1 = o_j1.p; f.j2 = o_j2.p;
   for (int a = 0; a < plan.n_aggs; ++a) { ov[a].alloc(ctx, n_out); ok[a].alloc(ctx, n_out); f.value[a] = ov[a].p; f.valid[a] = ok[a].p; }
+  ShardBufs so;
+  tiled::ShardRaw raw_in, raw_out;
+  memset(&raw_in, 0, sizeof raw_in); memset(&raw_out, 0, sizeof raw_out);
+  if (shard) {
+    so.edge.alloc(ctx, n_out); so.cnt.alloc(ctx, n_out); so.rstart.alloc(ctx, n_out); so.rstop.alloc(ctx, n_out);
+    so.smin.alloc(ctx, n_out); so.emax.alloc(ctx, n_out); so.smax.alloc(ctx, n_out); so.emin.alloc(ctx, n_out);
+    raw_in.edge = sbufs.edge.p; raw_in.cnt = sbufs.cnt.p; raw_in.rstart = sbufs.rstart.p; raw_in.rstop = sbufs.rstop.p;
+    raw_in.smin = sbufs.smin.p; raw_in.emax = sbufs.emax.p; raw_in.smax = sbufs.smax.p; raw_in.emin = sbufs.emin.p;
+    raw_out.edge = so.edge.p; raw_out.cnt = so.cnt.p; raw_out.rstart = so.rstart.p; raw_out.rstop = so.rstop.p;
+    raw_out.smin = so.smin.p; raw_out.emax = so.emax.p; raw_out.smax = so.smax.p; raw_out.emin = so.emin.p;
+  }
   if (nc && n_out) LAUNCH(ctx, k_cover_compact, grid_for(ctx, nc, 256), 256, 0, nc, keep.p, keep_excl.p, p1.cls.p, p1.chrom.p, fstart.p, fstop.p, p1.acc.p, j1.p, j2.p,
-                          tmp, plan.n_aggs, cfg.n_classes, cfg.unified, f, o_accd.p);
+                          tmp, plan.n_aggs, cfg.n_classes, cfg.unified, f, o_accd.p, raw_in, raw_out);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   res->view_acc_double = (void*)o_accd.detach();
   res->view_cols.assign(1, (const double*)res->view_acc_double);
@@ -1308,6 +1342,12 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   result_add(res, GMQL_COL_COV_ACC, o_acc);
   result_add(res, GMQL_COL_COV_JACC_INTERSECT, o_j1);
   result_add(res, GMQL_COL_COV_JACC_RESULT, o_j2);
+  if (shard) {
+    result_add(res, GMQL_COL_COV_EDGE, so.edge); result_add(res, GMQL_COL_COV_RAW_COUNT, so.cnt);
+    result_add(res, GMQL_COL_COV_RAW_START, so.rstart); result_add(res, GMQL_COL_COV_RAW_STOP, so.rstop);
+    result_add(res, GMQL_COL_COV_RAW_SMIN, so.smin); result_add(res, GMQL_COL_COV_RAW_EMAX, so.emax);
+    result_add(res, GMQL_COL_COV_RAW_SMAX, so.smax); result_add(res, GMQL_COL_COV_RAW_EMIN, so.emin);
+  }
   for (int a = 0; a < plan.n_aggs; ++a) {
     result_add(res, GMQL_COL_AGG_VALUE + a, ov[a]);
     result_add(res, GMQL_COL_AGG_VALID + a, ok[a]);
@@ -1353,8 +1393,9 @@ extern "C" int gmql_cover_count_samples(gmql_ctx* ctx, const gmql_regions* in, i
   }
 }
 
-extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups, int32_t flag,
-                          const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size, const gmql_agg* aggs, int32_t n_aggs, gmql_result** out) {
+static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups, int32_t flag,
+                      const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size, const gmql_agg* aggs, int32_t n_aggs,
+                      const gmql_cover_shard_t* shard, gmql_result** out) {
   if (!ctx || !out) return GMQL_ERR_INVALID;
   *out = nullptr;
   gmql_result* res = nullptr;
@@ -1405,6 +1446,23 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     CUDA_TRY(GMQL_SYNC(ctx));
     GMQL_REQUIRE(!hf[2], GMQL_ERR_INVALID, "region with chromosome/sample index out of range, start > stop, negative start or bad strand code");
     spans.G = G;
+    ShardSpec sspec;
+    if (shard) {
+      // every shard must lay the genome out identically: the caller's global spans replace the ones seen in this shard's rows
+      GMQL_REQUIRE(shard->chrom_span != nullptr, GMQL_ERR_INVALID, "gmql_cover_shard: chrom_span is required");
+      unsigned long long* gs = (unsigned long long*)ctx_pinned(ctx, 8 * (size_t)d.n_chrom);
+      uint64_t run = 0;
+      for (int c = 0; c < d.n_chrom; ++c) {
+        GMQL_REQUIRE(shard->chrom_span[c] >= 0 && (unsigned long long)shard->chrom_span[c] >= h_span[c], GMQL_ERR_INVALID, "gmql_cover_shard: a region lies beyond its chromosome's chrom_span");
+        gs[c] = (unsigned long long)shard->chrom_span[c];
+        h_span[c] = gs[c];
+        run += gs[c] + (unsigned long long)bin_size + 2ull;
+      }
+      CUDA_TRY(cudaMemcpyAsync(spans.span.p, gs, 8 * (size_t)d.n_chrom, cudaMemcpyHostToDevice, ctx->stream));
+      LAUNCH(ctx, k_chrom_offsets, 1, 32, 0, spans.span.p, d.n_chrom, spans.coff.p, (unsigned long long)bin_size + 2ull);
+      spans.G = run;
+      sspec.first_tile = shard->first_tile; sspec.end_tile = shard->end_tile;
+    }
     Inspect ins;
     ins.has_star = hf[0];
     ins.has_zero = hf[1];
@@ -1413,7 +1471,8 @@ extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* 
     res = new gmql_result();
     res->span_hint.resize((size_t)d.n_chrom);
     for (int c = 0; c < d.n_chrom; ++c) res->span_hint[c] = (int64_t)h_span[c] + 1;   // results may carry the one-base extension
-    if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
+    if (shard) GMQL_REQUIRE(unified && n_groups == 1 && total < 0xffffffffull, GMQL_ERR_UNSUPPORTED, "gmql_cover_shard: one group, unified strands and a linear genome below 2^32 are required");
+    if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res, shard ? &sspec : nullptr);
     else run_cover<uint64_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
     CUDA_TRY(GMQL_SYNC(ctx));
     *out = res;
@@ -1473,4 +1532,15 @@ extern "C" int gmql_result_as_regions(gmql_ctx* ctx, gmql_result* r, gmql_region
     ctx->err = ex.what();
     return ex.code;
   }
+}
+
+extern "C" int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups, int32_t flag,
+                          const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size, const gmql_agg* aggs, int32_t n_aggs, gmql_result** out) {
+  return cover_impl(ctx, in, sample_group, n_groups, flag, min_acc, max_acc, bin_size, aggs, n_aggs, nullptr, out);
+}
+
+extern "C" int gmql_cover_shard(gmql_ctx* ctx, const gmql_regions* in, int32_t flag, int32_t min_acc, int32_t max_acc, int64_t bin_size,
+                                const gmql_cover_shard_t* shard, gmql_result** out) {
+  if (!shard) return GMQL_ERR_INVALID;
+  return cover_impl(ctx, in, nullptr, 1, flag, &min_acc, &max_acc, bin_size, nullptr, 0, shard, out);
 }

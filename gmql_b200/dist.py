@@ -62,6 +62,101 @@ def shard_pairs(pairs, exp_sample_ids, parts, rank):
     return [(a, b) for (a, b) in pairs if b in mine]
 
 
+# ---- coordinate-range sharding of COVER / FLAT (north_star: "by genomic coordinate range with halo handling") -----------------
+TILE_BITS = 16      # gmql_cover_shard cuts the linear coordinate into tiles of 65 536 positions
+
+
+def linear_layout(chrom_span, bin_size=2000):
+    """coff[c] of the library's linear coordinate lin(chrom, pos) = coff[chrom] + pos (include/gmql_cuda.h, gmql_cover_shard):
+    exclusive prefix sum of (chrom_span[c] + bin_size + 2); returns (coff, total)."""
+    w = np.asarray(chrom_span, dtype=np.int64) + bin_size + 2
+    coff = np.concatenate([[0], np.cumsum(w)[:-1]]).astype(np.int64)
+    return coff, int(w.sum())
+
+
+def plan_tile_cuts(ds, chrom_span, world_size, bin_size=2000):
+    """Tile boundaries [t_0 = 0 < t_1 < ... < t_world = n_tiles] that give every rank about the same number of regions
+    (by the tile of the region's start).  Must be computed from the FULL dataset (or an all-reduced tile histogram)."""
+    coff, total = linear_layout(chrom_span, bin_size)
+    n_tiles = (total >> TILE_BITS) + 1
+    tile = (coff[ds.chrom] + ds.start) >> TILE_BITS
+    cum = np.cumsum(np.bincount(tile, minlength=n_tiles))
+    cuts = [0]
+    for r in range(1, world_size):
+        t = int(np.searchsorted(cum, ds.n * r / world_size, side="left")) + 1
+        cuts.append(min(max(t, cuts[-1]), n_tiles))
+    cuts.append(n_tiles)
+    return cuts
+
+
+def shard_by_tiles(ds, chrom_span, first_tile, end_tile, bin_size=2000):
+    """Rows a coordinate-range shard needs: the regions starting in its tiles plus the tile before (the halo: regions are
+    shorter than a tile, so nothing further left can reach in)."""
+    coff, _ = linear_layout(chrom_span, bin_size)
+    tile = (coff[ds.chrom] + ds.start) >> TILE_BITS
+    return _take(ds, (tile >= first_tile - 1) & (tile < end_tile))
+
+
+def merge_cover_shards(shards, flat):
+    """Stitches the per-shard tables of gmql_cover_shard (dicts of numpy columns, in shard order) into the result of the
+    unsharded operator: rows without edge flags are final; runs that touch at a cut are one run — AccIndex = max, contributors
+    = sum, startMin / endMax / startMax / endMin = min / max / max / min — finished with GMAP4's formulas
+    (GMAP4.scala:68-93, the same expressions as the device's k_runs_finalize).  Only the edge rows are touched on the host."""
+    out = {k: [] for k in ("chrom", "start", "stop", "acc", "j1", "j2")}
+    pending = None      # an open run: [chrom, rstart, rstop, acc, cnt, smin, emax, smax, emin]
+
+    def combine(p, q):
+        p[2] = q[2]; p[3] = max(p[3], q[3])
+        if q[4] > 0:
+            if p[4] > 0:
+                p[5] = min(p[5], q[5]); p[6] = max(p[6], q[6]); p[7] = max(p[7], q[7]); p[8] = min(p[8], q[8])
+            else:
+                p[5:9] = q[5:9]
+            p[4] += q[4]
+
+    def finish(p):
+        chrom, cs, ce, acc, cnt, smin, emax, smax, emin = p
+        if cnt <= 0:
+            return                                              # dropped: nothing overlaps it (GMAP4.scala:33-34,48)
+        os_, oe = (smin, emax) if flat else (cs, ce)
+        den = emax - smin
+        num2 = float(emin - smax) if cnt == 1 else (float(emin - smax) if smax < emin else 0.0)
+        out["chrom"].append([chrom]); out["start"].append([os_]); out["stop"].append([oe]); out["acc"].append([acc])
+        out["j1"].append([abs((float(oe) - float(os_)) / float(den)) if den != 0 else 0.0])
+        out["j2"].append([abs(num2 / float(den)) if den != 0 else 0.0])
+
+    for t in shards:
+        edge = t["edge"]
+        idx = np.nonzero(edge)[0]
+        lo = 0
+        for i in idx:                                           # final rows between edge rows pass through untouched
+            if i > lo:
+                if pending is not None:
+                    finish(pending); pending = None
+                for k in out:
+                    out[k].append(t[k][lo:i])
+            row = [int(t["chrom"][i]), int(t["rstart"][i]), int(t["rstop"][i]), int(t["acc"][i]), int(t["cnt"][i]),
+                   int(t["smin"][i]), int(t["emax"][i]), int(t["smax"][i]), int(t["emin"][i])]
+            if pending is not None and (int(edge[i]) & 1) and pending[0] == row[0] and pending[2] == row[1]:
+                combine(pending, row)
+            else:
+                if pending is not None:
+                    finish(pending)
+                pending = row
+            if not (int(edge[i]) & 2):
+                finish(pending); pending = None
+            lo = i + 1
+        if lo < len(edge):
+            if pending is not None:
+                finish(pending); pending = None
+            for k in out:
+                out[k].append(t[k][lo:])
+    if pending is not None:
+        finish(pending)
+    dt = dict(chrom=np.int32, start=np.int64, stop=np.int64, acc=np.int32, j1=np.float64, j2=np.float64)
+    return {k: (np.concatenate([np.asarray(a, dtype=dt[k]) for a in v]) if v else np.zeros(0, dt[k])) for k, v in out.items()}
+
+
 def gather_table(columns, dst=0, group=None):
     """Gathers a dict of equal-length 1-D numpy columns from every rank onto `dst` (concatenated in rank order).
     Uses the default process group: NCCL moves device tensors over NVLink, gloo (CPU tests) host tensors."""

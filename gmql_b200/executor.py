@@ -295,6 +295,26 @@ class GMQLCudaExecutor:
         del keep
         return _Result(self, out), gids
 
+    def cover_shard_raw(self, coverFlag, min_acc, max_acc, ds, chrom_span, first_tile, end_tile):
+        """gmql_cover_shard on the rows of `ds` (which must hold the regions of the tiles [first_tile - 1, end_tile), see
+        dist.shard_by_tiles): COVER / FLAT of one coordinate-range shard.  Returns a dict of numpy columns (the gmql_cover
+        columns plus edge flags and the raw accumulators dist.merge_cover_shards needs)."""
+        c_ds, keep = ds.as_c(narrow=self.narrow)
+        span = np.ascontiguousarray(chrom_span, dtype=np.int64)
+        sh = L.CoverShard()
+        sh.chrom_span, sh.first_tile, sh.end_tile = span.ctypes.data, int(first_tile), int(end_tile)
+        out = C.c_void_p()
+        self._check(self.lib.gmql_cover_shard(self.ctx, C.byref(c_ds), CoverFlag.CODE[coverFlag], int(min_acc), int(max_acc), self.binSize.Cover, C.byref(sh), C.byref(out)))
+        del keep
+        res = _Result(self, out)
+        cols = {k: res.column(c, dt) for k, c, dt in (
+            ("chrom", L.COL_COV_CHROM, np.int32), ("start", L.COL_COV_START, np.int64), ("stop", L.COL_COV_STOP, np.int64), ("acc", L.COL_COV_ACC, np.int32),
+            ("j1", L.COL_COV_J1, np.float64), ("j2", L.COL_COV_J2, np.float64), ("edge", L.COL_COV_EDGE, np.int32), ("cnt", L.COL_COV_RAW_COUNT, np.int32),
+            ("rstart", L.COL_COV_RAW_START, np.int64), ("rstop", L.COL_COV_RAW_STOP, np.int64), ("smin", L.COL_COV_RAW_SMIN, np.int64),
+            ("emax", L.COL_COV_RAW_EMAX, np.int64), ("smax", L.COL_COV_RAW_SMAX, np.int64), ("emin", L.COL_COV_RAW_EMIN, np.int64))}
+        res.free()
+        return cols
+
     def GenometricCover(self, coverFlag, min, max, aggregators, groups, ds, force_unified=False):
         """COVER / FLAT / SUMMIT / HISTOGRAM.  groups: dict sample_id -> group_id (implement_mgd) or None.  Returns records
         (group_id, chrom, start, stop, strand, (AccIndex, JaccardIntersect, JaccardResult, aggregates...)).

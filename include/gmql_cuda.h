@@ -192,6 +192,31 @@ int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp,
 int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups,
                int32_t flag, const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size,
                const gmql_agg* aggs, int32_t n_aggs, gmql_result** out);
+/* ---- COVER / FLAT on one coordinate-range shard (multi-GPU: north_star "by genomic coordinate range with halo handling") ----
+ * The linear coordinate lin(chrom, pos) = coff[chrom] + pos, coff = exclusive prefix sum of (chrom_span[c] + bin_size + 2), is cut
+ * into tiles of 65 536 positions; a shard owns the tiles [first_tile, end_tile).  `in` must hold every region whose start lies in
+ * the tiles [first_tile - 1, end_tile) (the tile before the range only lends the regions still open at the cut: the halo; other
+ * rows are ignored).  chrom_span (HOST [n_chrom], an upper bound of stop per chromosome) must be identical on every shard.
+ * Requirements: COVER or FLAT, one group, unified strands, no aggregates, no zero-length regions, regions shorter than 65 534
+ * bases, the linear genome below 2^32 (otherwise GMQL_ERR_UNSUPPORTED: shard by chromosome instead).
+ *
+ * Result: the columns of gmql_cover for the runs inside the shard, plus what a cross-shard merge needs (all chromosome-local):
+ *   GMQL_COL_COV_EDGE int32 — bit 0: the run continues one that ends at the shard's first position, bit 1: it reaches the shard's
+ *     end (such rows are kept even without a contributor here); rows with EDGE == 0 are final,
+ *   GMQL_COL_COV_RAW_START / _RAW_STOP int64 (the run clipped to the shard), GMQL_COL_COV_RAW_COUNT int32 (contributors accounted
+ *     on this shard: every (run, region) pair is accounted on exactly one shard, the one of max(run start, region start), the
+ *     reference's first-bin rule GMAP4.scala:44-45 at shard granularity), GMQL_COL_COV_RAW_SMIN / _EMAX / _SMAX / _EMIN int64
+ *     (startMin, endMax, startMax, endMin over them, -1 when none).
+ * Runs that touch at a cut (left.RAW_STOP == right.RAW_START, EDGE bits 2 and 1) are one run of the reference (its boundary
+ * merge, GenometricCover.scala:121-152): AccIndex = max, count = sum, min / max of the four bounds, then the GMAP4 formulas
+ * (gmql_b200/dist.py::merge_cover_shards is the host side; NCCL only gathers the few edge rows). */
+typedef struct {
+  const int64_t* chrom_span;
+  int64_t first_tile, end_tile;
+} gmql_cover_shard_t;
+int gmql_cover_shard(gmql_ctx* ctx, const gmql_regions* in, int32_t flag, int32_t min_acc, int32_t max_acc, int64_t bin_size,
+                     const gmql_cover_shard_t* shard, gmql_result** out);
+
 /* number of samples that own at least one region (GenometricCover.scala:64) */
 int gmql_cover_count_samples(gmql_ctx* ctx, const gmql_regions* in, int32_t* out_count);
 
@@ -273,6 +298,8 @@ enum {
   GMQL_COL_BAG_OFFSETS = 5, GMQL_COL_BAG_ROWS = 6,
   GMQL_COL_COV_GROUP = 16, GMQL_COL_COV_CHROM = 17, GMQL_COL_COV_START = 18, GMQL_COL_COV_STOP = 19,
   GMQL_COL_COV_STRAND = 20, GMQL_COL_COV_ACC = 21, GMQL_COL_COV_JACC_INTERSECT = 22, GMQL_COL_COV_JACC_RESULT = 23,
+  GMQL_COL_COV_EDGE = 24, GMQL_COL_COV_RAW_COUNT = 25, GMQL_COL_COV_RAW_START = 26, GMQL_COL_COV_RAW_STOP = 27,
+  GMQL_COL_COV_RAW_SMIN = 28, GMQL_COL_COV_RAW_EMAX = 29, GMQL_COL_COV_RAW_SMAX = 30, GMQL_COL_COV_RAW_EMIN = 31,
   GMQL_COL_JOIN_LEFT_ROW = 32, GMQL_COL_JOIN_RIGHT_ROW = 33, GMQL_COL_JOIN_PAIR = 34, GMQL_COL_JOIN_START = 35,
   GMQL_COL_JOIN_STOP = 36, GMQL_COL_JOIN_STRAND = 37, GMQL_COL_JOIN_CHROM = 38,
   GMQL_COL_DIFF_REF_ROW = 48,

@@ -98,3 +98,50 @@ def test_partition_is_balanced():
         loads = [HG38_SIZES[p].sum() for p in parts]
         assert sorted(sum(parts, [])) == list(range(24))
         assert max(loads) / (HG38_SIZES.sum() / world) < 1.12   # chromosome packing alone keeps the imbalance under 12 %
+
+
+def test_range_shard_planning_and_edge_merge():
+    """Host side of coordinate-range sharding (dist.plan_tile_cuts / shard_by_tiles / merge_cover_shards) on hand-made tables:
+    a run crossing one cut, a run spanning a whole shard, an edge run whose contributors all live on the neighbour, and an
+    edge run nobody overlaps (dropped, GMAP4.scala:33-34,48)."""
+    import numpy as np
+    from gmql_b200 import dist as D
+    from gmql_b200.regions import RegionDataset
+    rng = np.random.Generator(np.random.PCG64(1))
+    n = 20000
+    span = np.array([900000, 500000], dtype=np.int64)
+    chrom = rng.integers(0, 2, n).astype(np.int32)
+    start = (rng.random(n) * (span[chrom] - 1000)).astype(np.int64)
+    ds = RegionDataset(["chr1", "chr2"], chrom, start, start + 500, np.zeros(n, np.int8), np.zeros(n, np.int32), np.array([0], np.int64))
+    coff, total = D.linear_layout(span)
+    assert coff.tolist() == [0, 900000 + 2002] and total == 1400000 + 2 * 2002
+    cuts = D.plan_tile_cuts(ds, span, 4)
+    assert cuts[0] == 0 and cuts[-1] == (total >> 16) + 1 and cuts == sorted(cuts)
+    own = [int((((coff[ds.chrom] + ds.start) >> 16 >= cuts[r]) & ((coff[ds.chrom] + ds.start) >> 16 < cuts[r + 1])).sum()) for r in range(4)]
+    assert sum(own) == n and max(own) < 1.6 * n / 4
+    part = D.shard_by_tiles(ds, span, cuts[1], cuts[2])
+    t = (coff[part.chrom] + part.start) >> 16
+    assert int(t.min()) >= cuts[1] - 1 and int(t.max()) < cuts[2] and part.n >= own[1]
+
+    def table(rows):
+        keys = ("chrom", "start", "stop", "acc", "j1", "j2", "edge", "cnt", "rstart", "rstop", "smin", "emax", "smax", "emin")
+        dt = dict(chrom=np.int32, acc=np.int32, edge=np.int32, cnt=np.int32, j1=np.float64, j2=np.float64)
+        return {k: np.array([r[i] for r in rows], dtype=dt.get(k, np.int64)) for i, k in enumerate(keys)}
+
+    s0 = table([(0, 10, 20, 2, 0.5, 0.25, 0, 3, 10, 20, 5, 30, 12, 18),                 # final row
+                (0, 100, 200, 3, 0, 0, 2, 2, 100, 200, 90, 260, 150, 190)])             # reaches the cut at 200
+    s1 = table([(0, 200, 300, 5, 0, 0, 3, 0, 200, 300, -1, -1, -1, -1)])                # spans the whole shard, no contributor here
+    s2 = table([(0, 300, 350, 4, 0, 0, 1, 4, 300, 350, 280, 400, 340, 310),             # ends inside
+                (0, 500, 600, 2, 0, 0, 2, 0, 500, 600, -1, -1, -1, -1),                 # open to the right, nobody overlaps it at all
+                ])
+    s3 = table([(0, 600, 640, 2, 0, 0, 1, 0, 600, 640, -1, -1, -1, -1),
+                (1, 5, 9, 7, 1.0, 1.0, 0, 1, 5, 9, 5, 9, 5, 9)])
+    for flat in (False, True):
+        m = D.merge_cover_shards([s0, s1, s2, s3], flat)
+        assert m["chrom"].tolist() == [0, 0, 1]
+        # merged run 100..350: acc 5, cnt 6, smin 90, emax 400, smax 340, emin 190 -> (startMax >= endMin: zeroed numerator)
+        assert m["acc"].tolist() == [2, 5, 7]
+        assert (m["start"][1], m["stop"][1]) == ((90, 400) if flat else (100, 350))
+        den = 400 - 90
+        assert m["j1"][1] == abs((float(m["stop"][1]) - float(m["start"][1])) / den) and m["j2"][1] == 0.0
+        assert m["j1"][0] == 0.5 and m["j2"][2] == 1.0
