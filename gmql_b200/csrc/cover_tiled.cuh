@@ -20,7 +20,7 @@
 //   * a small stitch pass fuses pieces that touch at tile edges (the reference's boundary merge, :121-152).
 // Work per tile is proportional to its events (plus W/32 bitmap words), not to W.
 // Preconditions (checked by the caller, which otherwise uses the sort-and-merge path): uint32 keys, COVER or FLAT,
-// no zero-length regions, no aggregates, max region length < W - 2.  Capacity overflows (distinct positions, pieces or
+// no zero-length regions, max region length < W - 2 (value aggregates are a post-pass of the caller over the runs).  Capacity overflows (distinct positions, pieces or
 // halo regions of one tile) raise `fail` and the caller falls back as well.
 #pragma once
 #include "index.cuh"

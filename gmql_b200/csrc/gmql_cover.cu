@@ -861,6 +861,68 @@ __global__ void k_gmap4_finish(const uint32_t* __restrict__ ccls, const int32_t*
   }
 }
 
+// ---- aggregates for the tile-resident path: a region-driven post-pass over the runs ------------------------------------------
+// The tile kernel leaves count / startMin / endMax / startMax / endMin per run; value aggregates are added by one more read of the
+// input columns in their ORIGINAL order (values are fetched by row, no gather): every region finds the runs it overlaps through a
+// bucket table over the sorted, disjoint run starts and accumulates with REDs.
+struct RunAgg { int32_t* nn[8]; double* sum[8]; unsigned long long* vmin[8]; unsigned long long* vmax[8]; };
+
+__global__ void k_run_table(const uint32_t* __restrict__ rstart, const int64_t* __restrict__ n_runs, int shift, int64_t n_buckets, uint32_t* __restrict__ tbl) {
+  const int64_t nr = *n_runs;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t x = (uint64_t)b << shift;
+    uint32_t kx = x > 0xffffffffull ? 0xffffffffu : (uint32_t)x;
+    tbl[b] = (uint32_t)lower_bound_dev<uint32_t>(rstart, nr, kx);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_run_agg_scatter(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls,
+                                                         int64_t n, LinMap lm, const uint32_t* __restrict__ rstart, const uint32_t* __restrict__ rend, const int64_t* __restrict__ n_runs,
+                                                         const uint32_t* __restrict__ tbl, int tbl_shift, int64_t n_buckets, CovAggPlan plan, CovCols cc, RunAgg acc) {
+  const int64_t nr = *n_runs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t base = (cls ? (uint64_t)cls[i] : 0ull) * lm.G + lm.coff[chrom[i]];
+    const uint32_t s = (uint32_t)(base + (uint64_t)ld_coord(start, bits, i)), e = (uint32_t)(base + (uint64_t)ld_coord(stop, bits, i));
+    int64_t lo, hi;                                          // runs with start < e
+    {
+      uint64_t b = (uint64_t)e >> tbl_shift;
+      if (b >= (uint64_t)n_buckets) { lo = hi = nr; } else { lo = tbl[b]; hi = tbl[b + 1]; }
+      while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (rstart[mid] < e) lo = mid + 1; else hi = mid; }
+    }
+    for (int64_t j = lo - 1; j >= 0 && rend[j] > s; --j) {   // strict overlap (GMAP4.scala:41); run ends are sorted
+      for (int q = 0; q < plan.n_cols; ++q) {
+        if (cc.ok[q] && !cc.ok[q][i]) continue;
+        double v = cc.v[q][i];
+        atomicAdd(&acc.nn[q][j], 1);
+        atomicAdd(&acc.sum[q][j], v);
+        atomicMin(&acc.vmin[q][j], cov_key_min(v));
+        atomicMax(&acc.vmax[q][j], cov_key_max(v));
+      }
+    }
+  }
+}
+
+__global__ void k_run_agg_finish(int64_t nr, CovAggPlan plan, RunAgg acc, const int32_t* __restrict__ cnt, CovOut out) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nr; c += (int64_t)gridDim.x * blockDim.x) {
+    for (int a = 0; a < plan.n_aggs; ++a) {
+      int kind = plan.kind[a], q = plan.slot[a];
+      double v = 0.0; uint8_t ok = 0;
+      if (kind == GMQL_AGG_COUNT) { v = (double)cnt[c]; ok = 1; }
+      else if (acc.nn[q][c] > 0) {
+        ok = 1;
+        int nn = acc.nn[q][c];
+        if (kind == GMQL_AGG_SUM) v = acc.sum[q][c];
+        else if (kind == GMQL_AGG_AVG) v = acc.sum[q][c] / (double)nn;
+        else if (kind == GMQL_AGG_MIN) v = cov_from_key(acc.vmin[q][c]);
+        else if (kind == GMQL_AGG_MAX) v = cov_from_key(acc.vmax[q][c]);
+        else if (kind == GMQL_AGG_MEDIAN) { double m = cov_from_key(acc.vmin[q][c]); v = nn >= 2 ? (m + m) / 2 : m; }
+      }
+      out.value[a][c] = v;
+      out.valid[a][c] = ok;
+    }
+  }
+}
+
 struct FinalCols {
   int32_t* group; int32_t* chrom; int64_t* start; int64_t* stop; int8_t* strand; int32_t* acc; double* j1; double* j2;
   double* value[16]; uint8_t* valid[16];
@@ -1048,13 +1110,14 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
 }
 
 struct ShardSpec { int64_t first_tile, end_tile; };
+struct TiledRuns { DevBuf<uint32_t> rstart, rend; DevBuf<int32_t> cnt; DevBuf<int64_t> head_excl; int64_t np = 0; };   // for the aggregate post-pass
 struct ShardBufs { DevBuf<int32_t> edge, cnt; DevBuf<int64_t> rstart, rstop, smin, emax, smax, emin; };
 
 // host side of the tile-resident path; returns false (nothing consumed) when a capacity limit was hit and the caller must
 // fall back to the sort-and-merge path
 static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total, int logw,
                             const int32_t* h_mn, const int32_t* h_mx, Phase1Out* p1, DevBuf<int32_t>& keep, DevBuf<int64_t>& fstart, DevBuf<int64_t>& fstop,
-                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb) {
+                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs) {
   const int64_t n = in.n;
   const int key_bits = bits_for(n_classes_total * lm.G);
   const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
@@ -1151,6 +1214,10 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   }
   if (nr) LAUNCH(ctx, tiled::k_runs_finalize, grid_for(ctx, nr, 256), 256, 0, rr, nr, (const int64_t*)(head_excl.p + np), lm, flag == GMQL_FLAT ? 1 : 0, p1->cls.p, p1->chrom.p, fstart.p, fstop.p, p1->acc.p, keep.p, j1.p, j2.p, raw);
   *nc_out = nr;
+  if (keep_runs) {
+    keep_runs->rstart = std::move(rstart); keep_runs->rend = std::move(rend); keep_runs->cnt = std::move(rcnt);
+    keep_runs->head_excl = std::move(head_excl); keep_runs->np = np;
+  }
   return true;
 }
 
@@ -1196,7 +1263,8 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   // ---- tile-resident path (cover_tiled.cuh): dense inputs, 32-bit keys, COVER / FLAT without aggregates
   bool done = false;
   ShardBufs sbufs;
-  if (sizeof(K) == 4 && n > 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) && !has_zero && plan.n_aggs == 0 &&
+  TiledRuns truns;
+  if (sizeof(K) == 4 && n > 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) && !has_zero && (plan.n_aggs == 0 || !shard) &&
       n_classes_total * lm.G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
     // widest tile whose expected number of events leaves headroom in the kernel's tables
     const double total = (double)(n_classes_total * lm.G);
@@ -1216,11 +1284,41 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     for (int attempt = 0; want && !done && attempt < 3; ++attempt) {
       const int lw = logw - 2 * attempt;
       if (lw < 8 || maxlen >= (int64_t)(1ll << lw) - 2) break;
-      done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr);
+      done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr, plan.n_aggs ? &truns : nullptr);
       if (flw || shard) break;                         // a forced width is not second-guessed
     }
   }
 
+  if (done && plan.n_aggs) {
+    // value aggregates of the tile-resident path: region-driven post-pass over the runs
+    const int64_t nr = nc;
+    CovCols cc;
+    memset(&cc, 0, sizeof cc);
+    for (int q = 0; q < plan.n_cols; ++q) { cc.v[q] = in.cols[plan.col_id[q]]; cc.ok[q] = in.valid[plan.col_id[q]]; }
+    for (int a = 0; a < plan.n_aggs; ++a) { tv[a].alloc(ctx, nr); tk[a].alloc(ctx, nr); tmp.value[a] = tv[a].p; tmp.valid[a] = tk[a].p; }
+    RunAgg ra;
+    memset(&ra, 0, sizeof ra);
+    std::vector<DevBuf<int32_t>> a_nn((size_t)plan.n_cols);
+    std::vector<DevBuf<double>> a_sum((size_t)plan.n_cols);
+    std::vector<DevBuf<unsigned long long>> a_vmin((size_t)plan.n_cols), a_vmax((size_t)plan.n_cols);
+    for (int q = 0; q < plan.n_cols; ++q) {
+      a_nn[q].alloc(ctx, nr); a_nn[q].zero(); a_sum[q].alloc(ctx, nr); a_sum[q].zero();
+      a_vmin[q].alloc(ctx, nr); a_vmin[q].fill_byte(0xff); a_vmax[q].alloc(ctx, nr); a_vmax[q].zero();
+      ra.nn[q] = a_nn[q].p; ra.sum[q] = a_sum[q].p; ra.vmin[q] = a_vmin[q].p; ra.vmax[q] = a_vmax[q].p;
+    }
+    if (nr && plan.n_cols) {
+      const uint64_t max_key = n_classes_total * lm.G;
+      int tshift = 0;
+      { int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)1 << 22, 2 * nr + 1)); while (tshift < 62 && (int64_t)(max_key >> tshift) + 2 > want) ++tshift; }
+      const int64_t nb = (int64_t)(max_key >> tshift) + 1;
+      DevBuf<uint32_t> rtbl(ctx, nb + 2);
+      const int64_t* n_runs = truns.head_excl.p + truns.np;
+      LAUNCH(ctx, k_run_table, grid_for(ctx, nb + 1, 256), 256, 0, (const uint32_t*)truns.rstart.p, n_runs, tshift, nb, rtbl.p);
+      LAUNCH(ctx, k_run_agg_scatter, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, (const uint32_t*)cls.p, n, lm, (const uint32_t*)truns.rstart.p, (const uint32_t*)truns.rend.p,
+             n_runs, (const uint32_t*)rtbl.p, tshift, nb, plan, cc, ra);
+    }
+    if (nr) LAUNCH(ctx, k_run_agg_finish, grid_for(ctx, nr, 256), 256, 0, nr, plan, ra, (const int32_t*)truns.cnt.p, tmp);
+  }
   GMQL_REQUIRE(done || !shard, GMQL_ERR_UNSUPPORTED, "gmql_cover_shard needs the tile-resident path: COVER or FLAT without aggregates, one (group, strand) class, a linear genome below 2^32, no zero-length regions, regions shorter than 65 534 bases, and no tile denser than the kernel's tables");
   if (!done) {
   // interval index over the ORIGINAL coordinates (phase 2 contributors, GMAP4 uses the un-extended inputs)

@@ -204,3 +204,46 @@ def test_tiled_pile_up_retries_with_narrower_tiles(ex):
     assert len(out["tiled"][0]) > 100
     for a, b in zip(out["tiled"], out["sort"]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("flag", ["COVER", "FLAT"])
+@pytest.mark.parametrize("logw", [8, 12, 16])
+def test_tiled_with_aggregates(ex, flag, logw):
+    """Value aggregates on the tile-resident path (region-driven post-pass over the runs): SUM / MIN / MAX / AVG / COUNT with
+    nulls, against the literal oracle."""
+    import gmql_b200 as G
+    from gmql_b200 import RegionDataset, Agg
+    rng = random.Random(1200 + logw)
+    ids = [1, 2, 3, 4]
+    max_len = min(3000, (1 << logw) - 3)
+    ds = _clamp(rng, rand_regions(rng, 500, ids, strands="+-*", n_vals=2, max_len=max_len, aligned_p=0.3, null_p=0.15), max_len)
+    aggs = [("SUM", 0), ("MIN", 1), ("COUNT", 0), ("AVG", 1), ("MAX", 0)]
+    d = RegionDataset.from_records(ds, sample_ids=ids)
+    with forced(ex, logw) as f:
+        for gp, op in _params()[:4]:
+            got = ex.GenometricCover(flag, gp[0], gp[1], [Agg(k, i) for (k, i) in aggs], None, d)
+            want = O.cover_reference(flag, op[0], op[1], [O.Agg(k, i) for (k, i) in aggs], ds, None, 2000)
+            assert canon(got, 9) == canon(want, 9), (flag, gp)
+    f.assert_tiled()
+    assert "k_run_agg_scatter" in f.kernels
+
+
+def test_tiled_aggregates_medium_against_c_oracle(ex):
+    from gmql_b200 import synth, Agg, N, ANY, _lib as L
+    from oracle import c_oracle as CO
+    sizes = synth.HG38_SIZES[[18, 19, 20, 21]] // 2
+    ds = synth.peak_samples(60, 20000, 2, with_values=("signalValue",), sizes=sizes)
+    with forced(ex, 16) as f:
+        res, gids = ex.cover_raw("COVER", N(2), ANY(), [Agg("SUM", 0), Agg("MAX", 0), Agg("COUNT", 0)], None, ds)
+    f.assert_tiled()
+    g = {k: res.column(c, dt) for k, c, dt in (("chrom", L.COL_COV_CHROM, np.int32), ("start", L.COL_COV_START, np.int64), ("stop", L.COL_COV_STOP, np.int64))}
+    s, m, c = (res.column(L.COL_AGG_VALUE + k, np.float64) for k in range(3))
+    res.free()
+    w = CO.cover_rows(ds, 0, [2], [2 ** 31 - 1], None, 2000, val=ds.columns[0][1], valid=None)
+    og = np.lexsort((g["stop"], g["start"], g["chrom"]))
+    ow = np.lexsort((w["stop"], w["start"], w["chrom"]))
+    assert len(og) == len(ow) > 50
+    for k in ("chrom", "start", "stop"):
+        assert np.array_equal(g[k][og], w[k][ow])
+    np.testing.assert_allclose(s[og], w["sum"][ow], rtol=1e-9)
+    assert np.array_equal(m[og], w["max"][ow]) and np.array_equal(c[og], w["count"][ow].astype(np.float64))
