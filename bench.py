@@ -90,6 +90,48 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_ALL_CPUS = None
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Pins this process to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function), so that the pinned
+    host buffers of the end-to-end arm are allocated on the GPU's NUMA node; returns a short description.  The CPU arm
+    restores the full CPU set (restore_all_cpus)."""
+    global _ALL_CPUS
+    try:
+        _ALL_CPUS = os.sched_getaffinity(0)
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bus is None:
+            import ctypes
+            rt = ctypes.CDLL("libcudart.so")
+            buf = ctypes.create_string_buffer(32)
+            if rt.cudaDeviceGetPCIBusId(buf, 32, local) != 0:
+                return "unbound"
+            addr = buf.value.decode().lower()
+        else:
+            addr = "0000:%02x:00.0" % int(bus)
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % addr
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= _ALL_CPUS
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%s: %d local CPUs" % (addr, len(cpus))
+    except Exception as e:   # no sysfs / no permission: run unbound
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
+def restore_all_cpus():
+    if _ALL_CPUS:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)
+        except Exception:
+            pass
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def make_c5(n_samples, n_regions, parts):
     from gmql_b200 import synth
@@ -169,6 +211,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gmql_b200 import GMQLCudaExecutor, synth, _lib as L
+    numa = bind_to_gpu_numa_node(torch, local)      # pinned staging buffers on the GPU's own NUMA node (host -> device copies)
 
     n_samples, n_regions = args.samples, args.regions
     parts = synth.chrom_partition(world)[rank] if world > 1 else None
@@ -226,10 +269,14 @@ def run_ours(args):
     out_cnt = torch.empty(max(n_rows, 1), dtype=torch.int32).pin_memory()
     col_of = {"chrom": L.COL_COV_CHROM, "start": L.COL_COV_START, "stop": L.COL_COV_STOP, "acc": L.COL_COV_ACC, "j1": L.COL_COV_J1, "j2": L.COL_COV_J2}
 
+    h2d_ms = []
+
     def e2e_step():
         d = C.c_void_p()
         v = L.Regions()
         ex._check(lib.gmql_dataset_upload(ctx, C.byref(host), C.byref(d), C.byref(v)))
+        lib.gmql_ctx_sync(ctx)
+        h2d_ms.append(float(lib.gmql_last_h2d_ms(ctx)))
         cov, mp = pipe.run_on_view(v)
         assert int(lib.gmql_result_rows(cov)) == n_cover and int(lib.gmql_result_rows(mp)) == n_rows
         for k, t in out_cov.items():
@@ -300,7 +347,8 @@ def run_ours(args):
                        "map_rows": int(tot_rows), "sharding": "by chromosome (LPT packing), no collective on the data path" if world > 1 else "single GPU",
                        "l2": "device-resident inputs (%.2f GB per rank) larger than the 126 MB L2" % (16.0 * n_in / 1e9), "map_count_checksum": int(tot_check)},
             "e2e": {"value": tot_in / (ms_e2e_max * 1e-3), "unit": "input regions/s", "ms_per_step": ms_e2e_max,
-                    "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h), "steps": e2e_steps},
+                    "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h), "steps": e2e_steps,
+                    "h2d_ms_rank0": round(float(np.median(h2d_ms[1:] or h2d_ms)), 3), "host_binding_rank0": numa},
             "gpu_launches": int(tot_launch),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "launches_per_step": top[1], "ms_per_launch": top_ms,
@@ -311,6 +359,7 @@ def run_ours(args):
             "kernels": [{"name": n, "launches": c, "ms": round(m, 4)} for (n, c, m) in prof[:12]],
         }
         if world == 1 and not args.no_cpu:
+            restore_all_cpus()
             out["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     ex.close()

@@ -1152,7 +1152,11 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
 
   // two resident blocks per SM; four ranges per resident block even out the tail.  Every block publishes its pieces in
   // its own segment of the piece tables, so they come out in genome order and nothing has to be sorted.
-  const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), (int64_t)ctx->num_sms * 8));
+  // whole waves of the 2 x num_sms resident blocks, about 16 tiles per block (the first tile of every block range re-reads
+  // its predecessor's regions), at most four waves
+  const int64_t resident = (int64_t)ctx->num_sms * 2;
+  const int64_t waves = std::max<int64_t>(1, std::min<int64_t>(4, (t_hi - t_lo + resident * 8) / (resident * 16)));
+  const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), resident * waves));
   const int64_t seg = std::max<int64_t>(4096, (n / 16 + 2 * nT) / tgrid + 1);
   const int64_t cap = seg * tgrid;
   GMQL_REQUIRE(cap < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "piece table too large");
