@@ -147,3 +147,58 @@ def test_properties_at_scale(ex):
         le = np.sort(ds.chrom[m].astype(np.int64) * (1 << 32) + ds.stop[m])
         want = np.searchsorted(ls, key + stop, side="left") - np.searchsorted(le, key + start, side="right")
         assert np.array_equal(cnt[p * n:(p + 1) * n], want)
+
+
+@pytest.mark.parametrize("flag", ["COVER", "HISTOGRAM", "SUMMIT"])
+def test_cover_64bit_linear_keys(ex, flag):
+    """Stranded input on hg38-sized chromosomes: 2 strand classes x 3.1e9 positions exceed 2^32, so the sort keys, the index and
+    the region-driven GMAP4 run on 64-bit linear coordinates."""
+    from gmql_b200 import synth, RegionDataset, Agg, N, ANY, _lib as L
+    from oracle import c_oracle as CO
+    base = synth.peak_samples(30, 20000, 8, with_values=("signalValue",))
+    rng = np.random.Generator(np.random.PCG64(4))
+    strand = rng.integers(1, 3, base.n).astype(np.int8)                       # '+' / '-' only: the strands stay separate
+    # concentrate the regions so that pile-ups exist
+    start = (base.start // 4000).astype(np.int64) * 40 + (base.chrom == 0) * 200_000_000
+    ds = RegionDataset(base.chrom_names, base.chrom, start, start + (base.stop - base.start), strand, base.sample, base.sample_ids, base.columns)
+    code = {"COVER": 0, "SUMMIT": 2, "HISTOGRAM": 3}[flag]
+    res, gids = ex.cover_raw(flag, N(2), ANY(), [Agg("MAX", 0), Agg("COUNT", 0)], None, ds)
+    g = {k: res.column(c, dt) for k, c, dt in (("chrom", L.COL_COV_CHROM, np.int32), ("start", L.COL_COV_START, np.int64), ("stop", L.COL_COV_STOP, np.int64),
+                                               ("strand", L.COL_COV_STRAND, np.int8), ("acc", L.COL_COV_ACC, np.int32), ("j1", L.COL_COV_J1, np.float64), ("j2", L.COL_COV_J2, np.float64))}
+    m, c = (res.column(L.COL_AGG_VALUE + k, np.float64) for k in range(2))
+    res.free()
+    w = CO.cover_rows(ds, code, [2], [2 ** 31 - 1], None, 2000, val=ds.columns[0][1], valid=None)
+    og = np.lexsort((g["j2"], g["j1"], g["acc"], g["stop"], g["start"], g["strand"], g["chrom"]))
+    ow = np.lexsort((w["j2"], w["j1"], w["acc"], w["stop"], w["start"], w["strand"], w["chrom"]))
+    assert len(og) == len(ow) > 1000 and set(np.unique(g["strand"])) == {1, 2}
+    for k in ("chrom", "start", "stop", "strand", "acc", "j1", "j2"):
+        assert np.array_equal(g[k][og], w[k][ow]), (flag, k)
+    assert np.array_equal(m[og], w["max"][ow]) and np.array_equal(c[og], w["count"][ow].astype(np.float64))
+
+
+def test_map_64bit_linear_keys(ex):
+    """MAP with chromosome coordinates beyond 2^31 (int64 columns, a linear genome above 2^32): counts equal the numpy
+    two-search count."""
+    from gmql_b200 import RegionDataset, _lib as L
+    rng = np.random.Generator(np.random.PCG64(9))
+    big = 3_000_000_000
+    nr, ne = 3000, 200000
+    rs = np.sort(rng.integers(0, big, nr) // 1000 * 1000 + rng.integers(0, 2, nr) * big // 2) % big
+    ref = RegionDataset(["chrA", "chrB"], rng.integers(0, 2, nr).astype(np.int32), rs, rs + rng.integers(100, 3_000_000, nr), np.zeros(nr, np.int8), np.zeros(nr, np.int32),
+                        np.array([0], np.int64))
+    es = rng.integers(0, big, ne)
+    exp = RegionDataset(["chrA", "chrB"], rng.integers(0, 2, ne).astype(np.int32), es, es + rng.integers(1, 500_000, ne), np.zeros(ne, np.int8),
+                        np.sort(rng.integers(0, 3, ne)).astype(np.int32), np.arange(3, dtype=np.int64))
+    res, used, ref2 = ex.map_raw([(0, 0), (0, 1), (0, 2)], [], ref, exp)
+    cnt = res.column(L.COL_MAP_COUNT, np.int32)
+    res.free()
+    assert int(cnt.max()) > 0
+    for p, (_a, b) in enumerate(used):
+        for c in (0, 1):
+            m = (exp.sample == b) & (exp.chrom == c)
+            ls, le = np.sort(exp.start[m]), np.sort(exp.stop[m])
+            rmask = ref.chrom == c
+            want = np.searchsorted(ls, ref.stop[rmask], side="left") - np.searchsorted(le, ref.start[rmask], side="right")
+            got = cnt[p * nr:(p + 1) * nr][rmask]
+            sel = got >= 0                                   # rows collapsed into a duplicate carry -1
+            assert np.array_equal(got[sel], want[sel])
