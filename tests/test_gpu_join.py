@@ -127,3 +127,15 @@ def test_join_conf_test_join_shape(ex):
     _check(ex, left, right, lids, rids, pairs, [("MD", 1)], "RIGHT")
     _check(ex, left, right, lids, rids, pairs, [("DISTGREATER", 250), ("MD", 1)], "LEFT")
     _check(ex, left, right, lids, rids, pairs, [("DISTLESS", 1000), ("DISTGREATER", 100)], "LEFT")
+
+
+def test_join_md_int64_coordinates(ex):
+    """Coordinates beyond 2^31 (int64 columns): the MD round then runs on the unpacked index instead of the 16-byte packed
+    candidate records; same results as the oracle."""
+    rng = random.Random(77)
+    off = 3_000_000_000
+    left = [(r[0], r[1], r[2] + off, r[3] + off, r[4], r[5]) for r in rand_regions(rng, 60, [1, 2], n_vals=1, span=400000, max_len=3000)]
+    right = [(r[0], r[1], r[2] + off, r[3] + off, r[4], r[5]) for r in rand_regions(rng, 400, [10, 11, 12], n_vals=1, span=400000, max_len=3000)]
+    pairs = {(a, b): O.md5_pair_id(a, b) for a in (1, 2) for b in (10, 11, 12)}
+    for spec, builder in (([("MD", 1)], "RIGHT"), ([("MD", 2), ("DOWN", 0)], "LEFT"), ([("DISTLESS", 20001), ("MD", 3)], "CONTIG")):
+        _check(ex, left, right, [1, 2], [10, 11, 12], pairs, spec, builder)
