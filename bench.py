@@ -215,6 +215,9 @@ def run_ours(args):
 
     n_samples, n_regions = args.samples, args.regions
     parts = synth.chrom_partition(world)[rank] if world > 1 else None
+    if world == 1 and args.emulate_shard:                 # one GPU running rank r's shard of a w-GPU job (tuning aid, not a bench line)
+        r, w = (int(x) for x in args.emulate_shard.split("/"))
+        parts = synth.chrom_partition(w)[r]
     ds = make_c5(n_samples, n_regions, parts)
     n_in = ds.n
     assert len(ds.chrom_names) <= 256 and np.all(np.diff(ds.sample) >= 0) and int((ds.stop - ds.start).max()) < 65536
@@ -447,6 +450,7 @@ def main():
     ap.add_argument("--cpu-chroms", type=int, default=4, help="CPU arm: number of smallest chromosomes in the bounded slice")
     ap.add_argument("--cpu-samples", type=int, default=2000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--emulate-shard", default="", help="r/w: run rank r's chromosome shard of a w-GPU job on one GPU (tuning aid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -23,6 +23,7 @@
 // no zero-length regions, max region length < W - 2 (value aggregates are a post-pass of the caller over the runs).  Capacity overflows (distinct positions, pieces or
 // halo regions of one tile) raise `fail` and the caller falls back as well.
 #pragma once
+#include <cooperative_groups.h>
 #include "index.cuh"
 
 namespace tiled {
@@ -253,6 +254,8 @@ static __global__ void k_tile_offsets(const uint64_t* __restrict__ packed, int64
   }
 }
 
+// One barrier: the caller hands every call site of a tile its own scratch array, so a scratch array is only rewritten
+// after the block has passed other barriers.
 __device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t* total, int32_t* scratch /*[NWARPS]*/) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int32_t x = v;
@@ -265,7 +268,6 @@ __device__ __forceinline__ int32_t block_excl_scan(int32_t v, int32_t* total, in
   for (int o = 1; o < NWARPS; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
   const int32_t tot = __shfl_sync(0xffffffffu, t, NWARPS - 1);
   const int32_t below = __shfl_sync(0xffffffffu, t, w > 0 ? w - 1 : 0);
-  __syncthreads();
   *total = tot;
   return (w > 0 ? below : 0) + x - v;
 }
@@ -356,7 +358,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
   uint32_t* pemax = psmin + MAXP;
   uint32_t* psmax = pemax + MAXP;
   uint32_t* pemin = psmax + MAXP;
-  __shared__ int32_t scratch[NWARPS];
+  __shared__ int32_t scratch[3][NWARPS];                   // one per scan of a tile (see block_excl_scan)
   __shared__ int s_nh, s_nout;
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t W = 1u << logw;
@@ -387,17 +389,29 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
   int nh_carry = -1;                                       // -1: the open regions must be found by scanning the previous tile
   int64_t my_cnt = 0;                                      // pieces this block has published (block-uniform)
 
+  // Invariants at the top of every tile iteration (established here, restored by the tile that breaks them, so that no
+  // barrier is spent on clearing): the bitmap and the piece accumulators are clean, s_nout = 0 and s_nh = the number of
+  // regions carried in hin (0 when the previous tile must be scanned).
+  for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;
+  for (int k = tid; k < MAXP; k += THREADS) { pacc[k] = 0; pcnt[k] = 0; psmin[k] = 0xffffffffu; pemax[k] = 0; psmax[k] = 0; pemin[k] = 0xffffffffu; pen[k] = 0; }
+  if (tid == 0) { s_nh = 0; s_nout = 0; }
+  __syncthreads();
+
+  uint32_t s1_next = t_begin < t_end ? offS[t_begin] : 0u, s2_next = t_begin < t_end ? offS[t_begin + 1] : 0u;
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
-    const uint32_t s0 = offS[tile], s1 = offS[tile + 1];
+    const uint32_t s0 = s1_next, s1 = s2_next;
+    s1_next = s1;
+    if (tile + 1 < t_end) s2_next = offS[tile + 2];        // the next tile's range, loaded a whole tile ahead
     const uint32_t nS = s1 - s0;
     const bool scan_prev = nh_carry < 0;
     const uint32_t h0 = (scan_prev && tile > 0) ? offS[tile - 1] : s0;
     const uint32_t tile_lo = (uint32_t)tile << logw;
     if (nS == 0 && (scan_prev ? h0 == s0 : nh_carry == 0)) { nh_carry = 0; continue; }   // depth 0 throughout, nothing left open
-    // ---- phase 0: clear the bitmap
-    for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;
-    if (tid == 0) { s_nh = scan_prev ? 0 : nh_carry; s_nout = 0; }
-    __syncthreads();
+    // the next tile's records: into L2 while this tile is processed
+    if (tile + 1 < t_end) {
+      const uintptr_t a0 = (uintptr_t)(P + s1) & ~(uintptr_t)127, a1 = (uintptr_t)(P + s2_next);
+      for (uintptr_t a = a0 + ((uintptr_t)tid << 7); a < a1; a += (uintptr_t)THREADS << 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
     // ---- phase 1: mark event positions; regions of the previous tile that are still open; own regions into registers
     if (scan_prev) {
       for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
@@ -454,14 +468,16 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
       int32_t c = 0;
       const int w0 = tid * WPT;
       for (int q = 0; q < WPT; ++q) if (w0 + q < nW) c += __popc(bitmap[w0 + q]);
-      int32_t pre = block_excl_scan(c, &total, scratch);
+      int32_t pre = block_excl_scan(c, &total, scratch[0]);
+      if (nh > HCAP || nout > HCAP || total > CAP_EV) {    // uniform across the block
+        if (tid == 0) { *out.fail = total > CAP_EV ? 2 : 4; s_nh = 0; s_nout = 0; }
+        nh_carry = -1;
+        for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;   // every popcount above happened before the scan's barrier
+        __syncthreads();
+        continue;
+      }
+      if (tid == 0) { s_nh = nout; s_nout = 0; }           // every thread has read both (before the scan's barrier)
       for (int q = 0; q < WPT; ++q) if (w0 + q < nW) { wpre[w0 + q] = (uint16_t)pre; pre += __popc(bitmap[w0 + q]); }
-    }
-    if (nh > HCAP || nout > HCAP || total > CAP_EV) {      // uniform across the block
-      if (tid == 0) *out.fail = total > CAP_EV ? 2 : 4;
-      nh_carry = -1;
-      __syncthreads();
-      continue;
     }
     for (int k = tid; k < total; k += THREADS) delta[k] = 0;
     __syncthreads();
@@ -506,7 +522,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
     int32_t csum = 0, rmin = 0x7fffffff, rmax = -0x7fffffff;
     for (int k = k0; k < k1; ++k) { csum += delta[k]; rmin = min(rmin, csum); rmax = max(rmax, csum); }
     int32_t tile_net;
-    const int32_t d_start = depth_in + block_excl_scan(csum, &tile_net, scratch);
+    const int32_t d_start = depth_in + block_excl_scan(csum, &tile_net, scratch[1]);
     // the state just before my first rank: in range iff the depth there is (the previous position belongs to the same
     // class unless the depth is 0, which is never in range)
     RankPos rp;                                            // positions are needed at transitions (and, with groups, everywhere)
@@ -536,18 +552,25 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
       }
     }
     int32_t open_total = 0, open_pre = 0;
-    if (__syncthreads_or(quiet ? 0 : 1)) open_pre = block_excl_scan(nopen, &open_total, scratch);   // block-uniform
+    if (__syncthreads_or(quiet ? 0 : 1)) open_pre = block_excl_scan(nopen, &open_total, scratch[2]);   // block-uniform
     const int np = (cont0 ? 1 : 0) + open_total;
     if (np > MAXP) {
-      if (tid == 0) *out.fail = 3;
+      if (tid == 0) { *out.fail = 3; s_nh = 0; }
       nh_carry = -1;
+      for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;    // the counting walk ended before the barrier above
       __syncthreads();
       continue;
     }
-    for (int k = tid; k < np; k += THREADS) { pacc[k] = 0; pcnt[k] = 0; psmin[k] = 0xffffffffu; pemax[k] = 0; psmax[k] = 0; pemin[k] = 0xffffffffu; pen[k] = 0; }
-    if (tid == 0 && cont0) pst[0] = tile_lo;
-    __syncthreads();
-    if (tid == 0 && cont0) atomicMax(&pacc[0], depth_in);
+    uint32_t last_pos = 0;
+    if (MULTI && total > 0) { RankPos lp; lp.seek(bitmap, wpre, nW, total - 1); last_pos = lp.next(); }
+    // depth after the tile's last event, judged with that event's group (tile_lo + W - 1 may lie beyond the last class)
+    const bool reach_end = np > 0 && in_rng<MULTI>(cfg, mn0, mx0, depth_in + tile_net, (uint64_t)tile_lo + last_pos);
+    // The piece tables are clean (pen = 0, accumulators neutral).  Thread 0 writes the two entries no walking thread
+    // writes: the start of a piece continuing from the previous tile and the end of a piece still open at the tile end.
+    if (tid == 0) {
+      if (cont0) { pst[0] = tile_lo; atomicMax(&pacc[0], depth_in); }
+      if (reach_end) pen[np - 1] = tile_lo + W;
+    }
     {
       const int cur0 = (cont0 ? 1 : 0) + open_pre - 1;     // piece open at my first rank (when prev0)
       if (!quiet) {
@@ -583,13 +606,8 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
         } else if (qmax > 0) atomicMax(&pacc[cur0], qmax);
       }
     }
-    uint32_t last_pos = 0;
-    if (MULTI && total > 0) { RankPos lp; lp.seek(bitmap, wpre, nW, total - 1); last_pos = lp.next(); }
-    // depth after the tile's last event, judged with that event's group (tile_lo + W - 1 may lie beyond the last class)
-    const bool reach_end = np > 0 && in_rng<MULTI>(cfg, mn0, mx0, depth_in + tile_net, (uint64_t)tile_lo + last_pos);
     __syncthreads();
-    if (tid == 0 && reach_end) pen[np - 1] = tile_lo + W;
-    __syncthreads();
+    for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;    // no reader left; the next tile marks after another barrier
     // ---- phase 5: GMAP4, region-driven: the regions open at the tile start, then the tile's own
     if (np == 1) {
       // one piece (the usual case under dense coverage): no search, thread-local accumulation, one reduction per warp
@@ -657,8 +675,8 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
         }
         my_cnt += np;
       }
-    }
-    __syncthreads();
+      for (int k = tid; k < np; k += THREADS) { pacc[k] = 0; pcnt[k] = 0; psmin[k] = 0xffffffffu; pemax[k] = 0; psmax[k] = 0; pemin[k] = 0xffffffffu; pen[k] = 0; }
+    } else __syncthreads();
     // the regions still open at the tile end are the next tile's open regions
     { uint32_t* t = hinS; hinS = houtS; houtS = t; t = hinL; hinL = houtL; houtL = t; }
     nh_carry = nout;
@@ -774,6 +792,201 @@ static __global__ void k_runs_finalize(Runs r, int64_t nr, const int64_t* __rest
       j2[k] = den != 0 ? fabs(num2 / (double)den) : 0.0;                                           // :93
     } else { fstart[k] = cs; fstop[k] = ce; j1[k] = 0.0; j2[k] = 0.0; }
   }
+}
+
+
+// ---- fused stitch: one thread-block cluster from the pieces to the result rows ---------------------------------------
+// Everything that follows the tile kernel when there are at most STITCH_MAX pieces (COVER / FLAT without aggregates,
+// not a shard) runs in ONE launch of one cluster of STITCH_CL blocks: block offsets, genome order, run heads, run
+// indices, the merge of the pieces of a run, the GMAP4 epilogue of k_runs_finalize and the compaction of the kept runs
+// into the result columns.  Every block owns a contiguous range of the pieces (then of the runs); the two prefix sums
+// that cross block ranges (runs before my range, kept runs before my range) exchange one total per block through
+// distributed shared memory, with the hardware cluster barrier in between.  Nothing returns to the host, so the
+// operator needs a single synchronisation after the tile kernel; as separate kernels these steps were launch- and
+// round-trip-bound.
+constexpr int STITCH_T = 1024;
+constexpr int STITCH_CL = 8;            // blocks of the cluster (portable maximum)
+constexpr int STITCH_MAX = 1 << 18;     // pieces
+constexpr int STITCH_MAXB = 2048;       // tile-kernel blocks whose offsets fit the shared table
+
+struct StitchOut {
+  int32_t* group; int8_t* strand; int32_t* chrom; int64_t* start; int64_t* stop; int32_t* acc; double* accd; double* j1; double* j2;
+  unsigned long long* totals;           // [0] pieces, [1] runs, [2] kept runs, [3] 1 = too many pieces for this kernel (nothing else written)
+};
+
+__device__ __forceinline__ int32_t stitch_incl_scan(int32_t v, int32_t* total, int32_t* wt /*[32]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  __syncthreads();                                         // the previous call's readers are done with wt
+  if (lane == 31) wt[w] = x;
+  __syncthreads();
+  int32_t t = wt[lane];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+  *total = __shfl_sync(0xffffffffu, t, 31);
+  const int32_t below = __shfl_sync(0xffffffffu, t, w > 0 ? w - 1 : 0);
+  return (w > 0 ? below : 0) + x;
+}
+
+static __global__ void __cluster_dims__(STITCH_CL, 1, 1) __launch_bounds__(STITCH_T, 1)
+k_stitch_small(const uint32_t* __restrict__ blk_cnt, int nb, uint32_t* __restrict__ blk_off, Pieces p, uint32_t* __restrict__ order, int32_t* __restrict__ ridx, Runs r, LinMap lm,
+               int flat, int n_classes, int unified, StitchOut out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cr = (int)cluster.block_rank();
+  __shared__ uint32_t s_off[STITCH_MAXB + 1];
+  __shared__ int32_t wt[32];
+  __shared__ int32_t x_heads, x_kept;                      // this block's totals, read by the other blocks of the cluster
+  __shared__ int32_t hp[STITCH_CL + 1], kp[STITCH_CL + 1]; // exclusive prefixes over the cluster's blocks
+  const int tid = threadIdx.x, lane = tid & 31;
+  // block offsets of the tile kernel's segments (every block of the cluster computes the small table itself)
+  int32_t carry = 0;
+  for (int base = 0; base < nb; base += STITCH_T) {
+    const int i = base + tid;
+    const int32_t v = i < nb ? (int32_t)blk_cnt[i] : 0;
+    int32_t tot;
+    const int32_t incl = stitch_incl_scan(v, &tot, wt);
+    if (i < nb) s_off[i] = (uint32_t)(carry + incl - v);
+    carry += tot;
+  }
+  const int32_t np = carry;
+  if (tid == 0) s_off[nb] = (uint32_t)np;
+  __syncthreads();
+  if (cr == 0) {
+    for (int i = tid; i <= nb; i += STITCH_T) blk_off[i] = s_off[i];
+    if (tid == 0) { out.totals[0] = (unsigned long long)np; if (np > STITCH_MAX) out.totals[3] = 1ull; }
+  }
+  if (np > STITCH_MAX) return;                             // the whole cluster leaves together
+  auto slot_of = [&](int32_t g) -> uint32_t {              // last block whose first index is <= g holds piece g
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int32_t)s_off[mid] <= g) lo = mid; else hi = mid; }
+    return (uint32_t)((int64_t)lo * p.seg + (int64_t)(g - (int32_t)s_off[lo]));
+  };
+  // genome order, run heads, run index of every piece inside its block's range
+  const int32_t L = max(1, (np + STITCH_CL - 1) / STITCH_CL);
+  const int32_t g_lo = min(np, cr * L), g_hi = min(np, g_lo + L);
+  carry = 0;
+  for (int base = g_lo; base < g_hi; base += STITCH_T) {
+    const int32_t g = base + tid;
+    int32_t head = 0;
+    if (g < g_hi) {
+      const uint32_t a = slot_of(g);
+      order[g] = a;
+      head = 1;
+      if (g > 0 && (p.flags[a] & 1)) {
+        const uint32_t b = slot_of(g - 1);
+        if ((p.flags[b] & 2) && p.pend[b] == p.pstart[a]) head = 0;
+      }
+    }
+    int32_t tot;
+    const int32_t incl = stitch_incl_scan(head, &tot, wt);
+    if (g < g_hi) ridx[g] = carry + incl - 1;
+    carry += tot;
+  }
+  if (tid == 0) x_heads = carry;
+  cluster.sync();
+  if (tid == 0) {
+    int32_t run = 0;
+    for (int c = 0; c < STITCH_CL; ++c) { hp[c] = run; run += *cluster.map_shared_rank(&x_heads, c); }
+    hp[STITCH_CL] = run;
+  }
+  __syncthreads();
+  const int32_t n_runs = hp[STITCH_CL];
+  for (int k = cr * STITCH_T + tid; k < n_runs; k += STITCH_CL * STITCH_T) { r.acc[k] = 0; r.cnt[k] = 0; r.smin[k] = 0xffffffffu; r.emax[k] = 0; r.smax[k] = 0; r.emin[k] = 0xffffffffu; }
+  cluster.sync();
+  // merge the pieces of every run: segmented warp reduction, then one atomic per warp and run
+  for (int base = g_lo; base < g_hi; base += STITCH_T) {
+    const int32_t g = base + tid;
+    const bool valid = g < g_hi;
+    int32_t key = -1 - lane;
+    int32_t v_acc = 0, v_cnt = 0;
+    uint32_t v_smin = 0xffffffffu, v_emax = 0, v_smax = 0, v_emin = 0xffffffffu;
+    if (valid) {
+      const uint32_t a = order[g];
+      key = hp[cr] + ridx[g];
+      const int32_t kp_ = g > 0 ? hp[(g - 1) / L] + ridx[g - 1] : -1, kn_ = g + 1 < np ? hp[(g + 1) / L] + ridx[g + 1] : -1;
+      if (kp_ != key) r.rstart[key] = p.pstart[a];
+      if (kn_ != key) r.rend[key] = p.pend[a];
+      v_acc = p.acc[a]; v_cnt = p.cnt[a];
+      if (v_cnt) { v_smin = p.smin[a]; v_emax = p.emax[a]; v_smax = p.smax[a]; v_emin = p.emin[a]; }
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {                     // equal keys are contiguous: reduce towards the first lane of a run
+      const int32_t k2 = __shfl_down_sync(0xffffffffu, key, d);
+      const int32_t a2 = __shfl_down_sync(0xffffffffu, v_acc, d), c2 = __shfl_down_sync(0xffffffffu, v_cnt, d);
+      const uint32_t s2 = __shfl_down_sync(0xffffffffu, v_smin, d), e2 = __shfl_down_sync(0xffffffffu, v_emax, d);
+      const uint32_t m2 = __shfl_down_sync(0xffffffffu, v_smax, d), n2 = __shfl_down_sync(0xffffffffu, v_emin, d);
+      if (lane + d < 32 && k2 == key) { v_acc = max(v_acc, a2); v_cnt += c2; v_smin = min(v_smin, s2); v_emax = max(v_emax, e2); v_smax = max(v_smax, m2); v_emin = min(v_emin, n2); }
+    }
+    const int32_t kprev = __shfl_up_sync(0xffffffffu, key, 1);
+    if (valid && (lane == 0 || kprev != key)) {
+      atomicMax(&r.acc[key], v_acc);
+      if (v_cnt) {
+        atomicAdd(&r.cnt[key], v_cnt);
+        atomicMin(&r.smin[key], v_smin); atomicMax(&r.emax[key], v_emax);
+        atomicMax(&r.smax[key], v_smax); atomicMin(&r.emin[key], v_emin);
+      }
+    }
+  }
+  cluster.sync();
+  // runs -> result rows (the epilogue of k_runs_finalize; runs without a contributor are dropped, GMAP4.scala:33-34,48)
+  const int32_t R = max(1, (n_runs + STITCH_CL - 1) / STITCH_CL);
+  const int32_t k_lo = min(n_runs, cr * R), k_hi = min(n_runs, k_lo + R);
+  {
+    int32_t mine = 0;
+    for (int k = k_lo + tid; k < k_hi; k += STITCH_T) mine += r.cnt[k] > 0 ? 1 : 0;
+    int32_t tot;
+    stitch_incl_scan(mine, &tot, wt);
+    if (tid == 0) x_kept = tot;
+  }
+  cluster.sync();
+  if (tid == 0) {
+    int32_t run = 0;
+    for (int c = 0; c < STITCH_CL; ++c) { kp[c] = run; run += *cluster.map_shared_rank(&x_kept, c); }
+    kp[STITCH_CL] = run;
+  }
+  __syncthreads();
+  carry = kp[cr];
+  for (int base = k_lo; base < k_hi; base += STITCH_T) {
+    const int32_t k = base + tid;
+    int32_t keep = 0, cnt = 0, chrom = 0;
+    uint64_t cls = 0, basek = 0;
+    int64_t cs = 0, ce = 0;
+    if (k < k_hi) {
+      const uint64_t x = r.rstart[k];
+      cls = x / lm.G;
+      const uint64_t rem = x - cls * lm.G;
+      int lo = 0, hi = lm.n_chrom;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lm.coff[mid] <= rem) lo = mid; else hi = mid; }
+      chrom = lo;
+      basek = cls * lm.G + lm.coff[lo];
+      cs = (int64_t)(x - basek); ce = (int64_t)((uint64_t)r.rend[k] - basek);
+      cnt = r.cnt[k];
+      keep = cnt > 0 ? 1 : 0;
+    }
+    int32_t tot;
+    const int32_t incl = stitch_incl_scan(keep, &tot, wt);
+    if (keep) {
+      const int64_t o = (int64_t)(carry + incl - 1);
+      const uint64_t smin = r.smin[k], emax = r.emax[k], smax = r.smax[k], emin = r.emin[k];
+      const int64_t os = flat ? (int64_t)(smin - basek) : cs, oe = flat ? (int64_t)(emax - basek) : ce;   // :83-84
+      const long long den = (long long)(emax - smin);
+      const double num2 = cnt == 1 ? (double)(long long)(emin - smax) : (smax < emin ? (double)(long long)(emin - smax) : 0.0);   // :74
+      const int32_t acc = r.acc[k];
+      out.group[o] = (int32_t)((uint32_t)cls / (uint32_t)n_classes);
+      out.strand[o] = unified ? (int8_t)0 : (int8_t)((uint32_t)cls % (uint32_t)n_classes + 1);
+      out.chrom[o] = chrom;
+      out.start[o] = os; out.stop[o] = oe;
+      out.acc[o] = acc; out.accd[o] = (double)acc;
+      out.j1[o] = den != 0 ? fabs(((double)oe - (double)os) / (double)den) : 0.0;                      // :91
+      out.j2[o] = den != 0 ? fabs(num2 / (double)den) : 0.0;                                           // :93
+    }
+    carry += tot;
+  }
+  if (cr == 0 && tid == 0) { out.totals[1] = (unsigned long long)n_runs; out.totals[2] = (unsigned long long)kp[STITCH_CL]; }
+  cluster.sync();                                          // no block leaves while its totals may still be read
 }
 
 }  // namespace tiled

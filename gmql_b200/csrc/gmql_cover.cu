@@ -1112,12 +1112,18 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
 struct ShardSpec { int64_t first_tile, end_tile; };
 struct TiledRuns { DevBuf<uint32_t> rstart, rend; DevBuf<int32_t> cnt; DevBuf<int64_t> head_excl; int64_t np = 0; };   // for the aggregate post-pass
 struct ShardBufs { DevBuf<int32_t> edge, cnt; DevBuf<int64_t> rstart, rstop, smin, emax, smax, emin; };
+// result columns written by the fused stitch kernel (capacity STITCH_MAX; n_out rows are valid)
+struct FusedOut {
+  bool ready = false;
+  int64_t n_out = 0;
+  DevBuf<int32_t> group, chrom, acc; DevBuf<int64_t> start, stop; DevBuf<int8_t> strand; DevBuf<double> j1, j2, accd;
+};
 
 // host side of the tile-resident path; returns false (nothing consumed) when a capacity limit was hit and the caller must
 // fall back to the sort-and-merge path
 static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total, int logw,
                             const int32_t* h_mn, const int32_t* h_mx, Phase1Out* p1, DevBuf<int32_t>& keep, DevBuf<int64_t>& fstart, DevBuf<int64_t>& fstop,
-                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs) {
+                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs, FusedOut* fo) {
   const int64_t n = in.n;
   const int key_bits = bits_for(n_classes_total * lm.G);
   const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
@@ -1179,13 +1185,48 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
     LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc);
   }
-  LAUNCH(ctx, tiled::k_seg_offsets, 1, 1024, 0, blk_cnt.p, (int)tgrid, blk_off.p, np_dev.p);
   unsigned long long h_np = 0;
   int h_fail = 0;
-  CUDA_TRY(cudaMemcpyAsync(&h_np, np_dev.p, sizeof h_np, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(&h_fail, fail.p, sizeof h_fail, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(GMQL_SYNC(ctx));
-  if (h_fail) return false;
+  const char* stitch_env = getenv("GMQL_COVER_STITCH");   // "split": test hook, always the separate stitch kernels
+  const bool fused = fo && !sb && !keep_runs && (int64_t)tgrid <= tiled::STITCH_MAXB && !(stitch_env && !strcmp(stitch_env, "split"));
+  if (fused) {
+    // few pieces (the usual case): one kernel from the pieces to the result columns, one synchronisation
+    const int64_t C = tiled::STITCH_MAX;
+    DevBuf<unsigned long long> totals(ctx, 4);
+    totals.zero();
+    DevBuf<uint32_t> order_buf(ctx, C), rstart(ctx, C), rend(ctx, C), rsmin(ctx, C), remax(ctx, C), rsmax(ctx, C), remin(ctx, C);
+    DevBuf<int32_t> ridx(ctx, C), racc(ctx, C), rcnt(ctx, C);
+    tiled::Runs rr;
+    rr.edge = nullptr;
+    rr.rstart = rstart.p; rr.rend = rend.p; rr.acc = racc.p; rr.cnt = rcnt.p; rr.smin = rsmin.p; rr.emax = remax.p; rr.smax = rsmax.p; rr.emin = remin.p;
+    fo->group.alloc(ctx, C); fo->chrom.alloc(ctx, C); fo->acc.alloc(ctx, C); fo->start.alloc(ctx, C); fo->stop.alloc(ctx, C);
+    fo->strand.alloc(ctx, C); fo->j1.alloc(ctx, C); fo->j2.alloc(ctx, C); fo->accd.alloc(ctx, C);
+    tiled::StitchOut so;
+    so.group = fo->group.p; so.strand = fo->strand.p; so.chrom = fo->chrom.p; so.start = fo->start.p; so.stop = fo->stop.p;
+    so.acc = fo->acc.p; so.accd = fo->accd.p; so.j1 = fo->j1.p; so.j2 = fo->j2.p; so.totals = totals.p;
+    LAUNCH(ctx, tiled::k_stitch_small, tiled::STITCH_CL, tiled::STITCH_T, 0, (const uint32_t*)blk_cnt.p, (int)tgrid, blk_off.p, pc, order_buf.p, ridx.p, rr, lm, flag == GMQL_FLAT ? 1 : 0,
+           cfg.n_classes, cfg.unified, so);
+    unsigned long long* h_tot = (unsigned long long*)ctx_pinned(ctx, 64);
+    int* h_f = (int*)(h_tot + 4);
+    CUDA_TRY(cudaMemcpyAsync(h_tot, totals.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h_f, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
+    if (*h_f) return false;
+    if (!h_tot[3]) {
+      fo->ready = true;
+      fo->n_out = (int64_t)h_tot[2];
+      *nc_out = (int64_t)h_tot[1];
+      p1->n = (int64_t)h_tot[1];
+      return true;
+    }
+    h_np = h_tot[0];                                      // too many pieces for one block: the separate kernels below (blk_off is in place)
+  } else {
+    LAUNCH(ctx, tiled::k_seg_offsets, 1, 1024, 0, blk_cnt.p, (int)tgrid, blk_off.p, np_dev.p);
+    CUDA_TRY(cudaMemcpyAsync(&h_np, np_dev.p, sizeof h_np, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&h_fail, fail.p, sizeof h_fail, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
+    if (h_fail) return false;
+  }
   const int64_t np = (int64_t)h_np;
   pk_a.release(); pk_b.release();
 
@@ -1268,6 +1309,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   bool done = false;
   ShardBufs sbufs;
   TiledRuns truns;
+  FusedOut fo;
   if (sizeof(K) == 4 && n > 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) && !has_zero && (plan.n_aggs == 0 || !shard) &&
       n_classes_total * lm.G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
     // widest tile whose expected number of events leaves headroom in the kernel's tables
@@ -1288,7 +1330,8 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     for (int attempt = 0; want && !done && attempt < 3; ++attempt) {
       const int lw = logw - 2 * attempt;
       if (lw < 8 || maxlen >= (int64_t)(1ll << lw) - 2) break;
-      done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr, plan.n_aggs ? &truns : nullptr);
+      done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr, plan.n_aggs ? &truns : nullptr,
+                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr);
       if (flw || shard) break;                         // a forced width is not second-guessed
     }
   }
@@ -1398,14 +1441,24 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     }
   }
   }  // !done
-  keep_excl.alloc(ctx, nc + 1);
-  device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, keep.p, keep_excl.p, nc, keep_excl.p + nc);
-  int64_t n_out = read_back<int64_t>(ctx, keep_excl.p + nc);
-
-  DevBuf<int32_t> o_group(ctx, n_out), o_chrom(ctx, n_out), o_acc(ctx, n_out);
-  DevBuf<int64_t> o_start(ctx, n_out), o_stop(ctx, n_out);
-  DevBuf<int8_t> o_strand(ctx, n_out);
-  DevBuf<double> o_j1(ctx, n_out), o_j2(ctx, n_out), o_accd(ctx, n_out > 0 ? n_out : 1);
+  int64_t n_out;
+  DevBuf<int32_t> o_group, o_chrom, o_acc;
+  DevBuf<int64_t> o_start, o_stop;
+  DevBuf<int8_t> o_strand;
+  DevBuf<double> o_j1, o_j2, o_accd;
+  if (fo.ready) {
+    // the fused stitch kernel has already written the result rows
+    n_out = fo.n_out;
+    o_group = std::move(fo.group); o_chrom = std::move(fo.chrom); o_acc = std::move(fo.acc); o_start = std::move(fo.start); o_stop = std::move(fo.stop);
+    o_strand = std::move(fo.strand); o_j1 = std::move(fo.j1); o_j2 = std::move(fo.j2); o_accd = std::move(fo.accd);
+    o_group.n = o_chrom.n = o_acc.n = o_start.n = o_stop.n = o_strand.n = o_j1.n = o_j2.n = n_out;
+  } else {
+    keep_excl.alloc(ctx, nc + 1);
+    device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, keep.p, keep_excl.p, nc, keep_excl.p + nc);
+    n_out = read_back<int64_t>(ctx, keep_excl.p + nc);
+    o_group.alloc(ctx, n_out); o_chrom.alloc(ctx, n_out); o_acc.alloc(ctx, n_out); o_start.alloc(ctx, n_out); o_stop.alloc(ctx, n_out);
+    o_strand.alloc(ctx, n_out); o_j1.alloc(ctx, n_out); o_j2.alloc(ctx, n_out); o_accd.alloc(ctx, n_out > 0 ? n_out : 1);
+  }
   std::vector<DevBuf<double>> ov((size_t)plan.n_aggs);
   std::vector<DevBuf<uint8_t>> ok((size_t)plan.n_aggs);
   FinalCols f;
@@ -1423,7 +1476,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     raw_out.edge = so.edge.p; raw_out.cnt = so.cnt.p; raw_out.rstart = so.rstart.p; raw_out.rstop = so.rstop.p;
     raw_out.smin = so.smin.p; raw_out.emax = so.emax.p; raw_out.smax = so.smax.p; raw_out.emin = so.emin.p;
   }
-  if (nc && n_out) LAUNCH(ctx, k_cover_compact, grid_for(ctx, nc, 256), 256, 0, nc, keep.p, keep_excl.p, p1.cls.p, p1.chrom.p, fstart.p, fstop.p, p1.acc.p, j1.p, j2.p,
+  if (nc && n_out && !fo.ready) LAUNCH(ctx, k_cover_compact, grid_for(ctx, nc, 256), 256, 0, nc, keep.p, keep_excl.p, p1.cls.p, p1.chrom.p, fstart.p, fstop.p, p1.acc.p, j1.p, j2.p,
                           tmp, plan.n_aggs, cfg.n_classes, cfg.unified, f, o_accd.p, raw_in, raw_out);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   res->view_acc_double = (void*)o_accd.detach();

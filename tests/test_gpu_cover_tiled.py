@@ -247,3 +247,35 @@ def test_tiled_aggregates_medium_against_c_oracle(ex):
         assert np.array_equal(g[k][og], w[k][ow])
     np.testing.assert_allclose(s[og], w["sum"][ow], rtol=1e-9)
     assert np.array_equal(m[og], w["max"][ow]) and np.array_equal(c[og], w["count"][ow].astype(np.float64))
+
+
+@pytest.mark.parametrize("n_samples,expect_fused", [(10, True), (30, True), (800, False)])
+def test_fused_stitch_equals_split_kernels(ex, n_samples, expect_fused):
+    """The one-block stitch kernel (<= 262 144 pieces) and the separate stitch kernels give the same rows in the same order;
+    with more pieces the fused kernel declines and the separate kernels run."""
+    from gmql_b200 import synth, N, ANY, _lib as L
+    ds = synth.peak_samples(n_samples, 5000, 7, with_values=())
+    for flag, gmin, gmax in (("COVER", N(2), ANY()), ("FLAT", N(1), N(3))):
+        out, kern = {}, {}
+        for mode in ("fused", "split"):
+            os.environ["GMQL_COVER_PATH"] = "tiled"
+            if mode == "split":
+                os.environ["GMQL_COVER_STITCH"] = "split"
+            ex.lib.gmql_ctx_set_profiling(ex.ctx, 1)
+            try:
+                res, _ = ex.cover_raw(flag, gmin, gmax, [], None, ds)
+            finally:
+                os.environ.pop("GMQL_COVER_PATH", None)
+                os.environ.pop("GMQL_COVER_STITCH", None)
+            buf = C.create_string_buffer(1 << 16)
+            ex.lib.gmql_ctx_profile_report(ex.ctx, buf, len(buf))
+            ex.lib.gmql_ctx_set_profiling(ex.ctx, 0)
+            kern[mode] = buf.value.decode()
+            out[mode] = [res.column(c, dt) for c, dt in ((L.COL_COV_CHROM, np.int32), (L.COL_COV_START, np.int64), (L.COL_COV_STOP, np.int64), (L.COL_COV_ACC, np.int32),
+                                                         (L.COL_COV_STRAND, np.int8), (L.COL_COV_GROUP, np.int32), (L.COL_COV_J1, np.float64), (L.COL_COV_J2, np.float64))]
+            res.free()
+        assert "k_cover_tile" in kern["fused"] and "k_stitch_small" in kern["fused"] and "k_stitch_small" not in kern["split"]
+        assert ("k_piece_merge" not in kern["fused"]) == expect_fused, kern["fused"]
+        assert len(out["fused"][0]) > 100
+        for a, b in zip(out["fused"], out["split"]):
+            assert np.array_equal(a, b), (flag, n_samples)
