@@ -8,6 +8,7 @@
 // is streamed once from HBM in its original order, each region finds the reference regions it overlaps and
 // accumulates straight into the output row of (pair, ref region).  The output table — one row per (pair, ref region),
 // zero rows included (GenometricMap71.scala:115-116) — is written by a fill kernel and a finalise kernel.
+#include <cooperative_groups.h>
 #include "index.cuh"
 
 namespace {
@@ -132,6 +133,101 @@ __global__ void k_bucket_table(const K* __restrict__ r_start, int64_t n_ref, int
     K kx = (x > (uint64_t)(~(K)0)) ? ~(K)0 : (K)x;
     tbl[b] = (uint32_t)lower_bound_dev<K>(r_start, n_ref, kx);
   }
+}
+
+// ---- small pre-sorted reference: the whole index in one launch ------------------------------------------------------
+// MAP onto a COVER result or an annotation: one reference sample of at most MIX_MAX rows, promised to be in (chrom, start)
+// order.  Linear keys (with the order and span checks of k_index_stops), stops, the running maximum of the stops, the
+// packed entries and the bucket table come from ONE cluster of MIX_CL blocks instead of six launch-bound kernels.  Every
+// block owns a contiguous range of the rows; the running maximum crosses block ranges through one value per block in
+// distributed shared memory.
+constexpr int MIX_T = 1024;
+constexpr int MIX_CL = 8;
+constexpr int64_t MIX_MAX = 1 << 17;
+
+template <typename K>
+__device__ __forceinline__ K mix_incl_max(K v, K* total, K* wt /*[32]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  K x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { K y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o && y > x) x = y; }
+  __syncthreads();
+  if (lane == 31) wt[w] = x;
+  __syncthreads();
+  K t = wt[lane];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { K y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o && y > t) t = y; }
+  *total = __shfl_sync(0xffffffffu, t, 31);
+  const K below = __shfl_sync(0xffffffffu, t, w > 0 ? w - 1 : 0);
+  return (w > 0 && below > x) ? below : x;
+}
+
+template <typename K>
+__global__ void __cluster_dims__(MIX_CL, 1, 1) __launch_bounds__(MIX_T, 1)
+k_map_index_small(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, int n, LinMap lm,
+                  const int32_t* __restrict__ sample, const int8_t* __restrict__ strand, const int32_t* __restrict__ dup_of, int n_samples,
+                  int tbl_shift, int64_t n_buckets, K* __restrict__ keys, uint32_t* __restrict__ rows, uint32_t* __restrict__ rows_by_sample,
+                  K* __restrict__ stops, K* __restrict__ pmax, uint32_t* __restrict__ tbl, RefEntry<K>* __restrict__ entries, int* __restrict__ bad) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cr = (int)cluster.block_rank();
+  __shared__ K wt[32];
+  __shared__ K x_max;
+  const int tid = threadIdx.x;
+  const int L = (n + MIX_CL - 1) / MIX_CL;
+  const int lo = min(n, cr * L), hi = min(n, lo + L);
+  K carry = 0;
+  for (int base = lo; base < hi; base += MIX_T) {
+    const int i = base + tid;
+    K st = 0;
+    if (i < hi) {
+      int c = chrom[i];
+      int64_t s = ld_coord(start, bits, i), e = ld_coord(stop, bits, i);
+      if (c < 0 || c >= lm.n_chrom || s < 0 || e < 0 || e > lm.span[c]) { *bad = 1; c = 0; s = 0; e = 0; }
+      const K key = (K)(lm.coff[c] + (uint64_t)s);
+      if (i > 0) {                                           // the caller promised (chrom, start) order
+        const int cp = chrom[i - 1];
+        const int64_t sp = ld_coord(start, bits, i - 1);
+        if (cp >= 0 && cp < lm.n_chrom && sp >= 0 && (K)(lm.coff[cp] + (uint64_t)sp) > key) *bad = 1;
+      }
+      st = (K)(lm.coff[c] + (uint64_t)e);
+      keys[i] = key; rows[i] = (uint32_t)i; rows_by_sample[i] = (uint32_t)i; stops[i] = st;
+    }
+    K tot;
+    const K incl = mix_incl_max<K>(st, &tot, wt);
+    if (i < hi) pmax[i] = incl > carry ? incl : carry;       // running maximum inside this block's range
+    if (tot > carry) carry = tot;
+  }
+  if (tid == 0) x_max = carry;
+  cluster.sync();                                            // keys and block maxima are visible cluster-wide
+  K before = 0;
+  for (int c = 0; c < cr; ++c) { const K v = *cluster.map_shared_rank(&x_max, c); if (v > before) before = v; }
+  for (int base = lo; base < hi; base += MIX_T) {
+    const int i = base + tid;
+    K pm = 0, pp = 0;
+    if (i < hi) { pm = pmax[i]; pp = i > lo ? pmax[i - 1] : (K)0; }
+    __syncthreads();                                         // all local values of the round are read before any is replaced
+    if (i < hi) {
+      if (before > pm) pm = before;
+      if (before > pp) pp = before;
+      pmax[i] = pm;
+      const uint32_t canon = dup_of ? (uint32_t)dup_of[i] : (uint32_t)i;
+      RefEntry<K> en;
+      en.stop = stops[i];
+      en.pmax_prev = i > 0 ? pp : (K)0;
+      en.rank = canon;
+      int sm = sample ? sample[i] : 0;
+      if (sm < 0 || sm >= n_samples) { *bad = 1; sm = 0; }
+      en.meta = ((uint32_t)sm << 2) | (uint32_t)(strand ? strand[i] : (int8_t)0);
+      entries[i] = en;
+    }
+  }
+  for (int64_t b = (int64_t)cr * MIX_T + tid; b <= n_buckets; b += (int64_t)MIX_CL * MIX_T) {
+    const uint64_t x = (uint64_t)b << tbl_shift;
+    const K kx = (x > (uint64_t)(~(K)0)) ? ~(K)0 : (K)x;
+    tbl[b] = (uint32_t)lower_bound_dev<K>(keys, n, kx);
+  }
+  cluster.sync();                                            // no block leaves while its maximum may still be read
 }
 
 // ---- the streaming kernel ------------------------------------------------------------------------
@@ -386,12 +482,15 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   int64_t n_rows = 0;
   int h_bad = 0;
   const bool single = n_ls == 1;
+  // small pre-sorted single-sample reference: the whole index comes from one cluster launch (k_map_index_small)
+  const char* mix_env = getenv("GMQL_MAP_INDEX");           // "split": test hook, always the separate index kernels
+  const bool small_index = single && ref.sorted_hint && n_ref > 0 && n_ref <= MIX_MAX && !(mix_env && !strcmp(mix_env, "split"));
   if (single) {
     // one reference sample (MAP onto a COVER result, an annotation, ...): every table is known on the host; nothing to
     // sort, no host round trip.  Sample indices of the rows are validated by k_index_entries.
     sr_a.alloc(ctx, n_ref);
     rows_by_sample = sr_a.p;
-    if (n_ref) LAUNCH(ctx, k_iota_rows, grid_for(ctx, n_ref, 256), 256, 0, sr_a.p, n_ref);
+    if (n_ref && !small_index) LAUNCH(ctx, k_iota_rows, grid_for(ctx, n_ref, 256), 256, 0, sr_a.p, n_ref);
     int64_t* h_so = (int64_t*)ctx_pinned(ctx, 16);
     h_so[0] = 0; h_so[1] = n_ref;
     CUDA_TRY(cudaMemcpyAsync(sample_off.p, h_so, 16, cudaMemcpyHostToDevice, ctx->stream));
@@ -435,7 +534,8 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   // interval index over the reference
   LinMap lm = spans.map();
   IntervalIndex<K> ix;
-  build_index<K>(ctx, ref, nullptr, 1, lm, &ix, false, (ref.span_hint || ref.sorted_hint) ? bad.p : (int*)nullptr);
+  if (small_index) alloc_index<K>(ctx, n_ref, &ix);
+  else build_index<K>(ctx, ref, nullptr, 1, lm, &ix, false, (ref.span_hint || ref.sorted_hint) ? bad.p : (int*)nullptr);
   // bucket table, resident in the streaming kernel's shared memory: as fine as fits (most buckets then hold no start
   // and a query needs no search at all), at least 2^10 buckets
   int tbl_shift = 0;
@@ -445,9 +545,14 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   }
   int64_t n_buckets = (int64_t)(lm.G >> tbl_shift) + 1;
   DevBuf<uint32_t> tbl(ctx, n_buckets + 2);
-  LAUNCH(ctx, (k_bucket_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, n_ref, tbl_shift, n_buckets, tbl.p);
   DevBuf<RefEntry<K>> entries(ctx, n_ref);
-  if (n_ref) LAUNCH(ctx, (k_index_entries<K>), grid_for(ctx, n_ref, 256), 256, 0, ix.row, n_ref, ix.stop.p, ix.pmax.p, ref.sample, ref.strand, ref.dup_of, single ? (const uint32_t*)nullptr : rank_of_row.p, n_ls, bad.p, entries.p);
+  if (small_index) {
+    LAUNCH(ctx, (k_map_index_small<K>), MIX_CL, MIX_T, 0, ref.chrom, ref.start, ref.stop, ref.coord_bits, (int)n_ref, lm, ref.sample, ref.strand, ref.dup_of, n_ls,
+           tbl_shift, n_buckets, ix.start_a.p, ix.row_a.p, sr_a.p, ix.stop.p, ix.pmax.p, tbl.p, entries.p, bad.p);
+  } else {
+    LAUNCH(ctx, (k_bucket_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, n_ref, tbl_shift, n_buckets, tbl.p);
+    if (n_ref) LAUNCH(ctx, (k_index_entries<K>), grid_for(ctx, n_ref, 256), 256, 0, ix.row, n_ref, ix.stop.p, ix.pmax.p, ref.sample, ref.strand, ref.dup_of, single ? (const uint32_t*)nullptr : rank_of_row.p, n_ls, bad.p, entries.p);
+  }
 
   // accumulators
   MapAcc acc;

@@ -85,3 +85,46 @@ def test_cover_result_view_carries_the_hints(ex):
     rc, want = _map_counts(ex, c_cov, c_exp, 3)
     res.free()
     assert rc == 0 and len(want) > 0 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n_ref", [1, 7, 1025, 50000])
+def test_one_launch_index_equals_separate_index_kernels(ex, n_ref):
+    """A pre-sorted single-sample reference is indexed by one cluster kernel (k_map_index_small); same counts as the
+    separate index kernels and as the un-hinted call.  Long regions early in a block range make the running maximum
+    cross the cluster's block boundaries."""
+    import os
+    from gmql_b200 import RegionDataset
+    rng = np.random.Generator(np.random.PCG64(n_ref))
+    span = 5_000_000
+    chrom = np.sort(rng.integers(0, 3, n_ref)).astype(np.int32)
+    start = rng.integers(0, span, n_ref)
+    ln = rng.integers(1, 400, n_ref)
+    ln[rng.random(n_ref) < 0.01] = 2_000_000                      # a few regions covering thousands of their successors
+    o = np.lexsort((start, chrom))
+    chrom, start, ln = chrom[o], start[o], ln[o]
+    names = ["chr1", "chr2", "chr3"]
+    dr = RegionDataset(names, chrom, start, start + ln, rng.integers(0, 3, n_ref).astype(np.int8), np.zeros(n_ref, np.int32), np.array([5], np.int64))
+    n_exp = 200000
+    ec = rng.integers(0, 3, n_exp).astype(np.int32)
+    es = rng.integers(0, span + 2_000_000, n_exp)
+    de = RegionDataset(names, ec, es, es + rng.integers(0, 3000, n_exp), rng.integers(0, 3, n_exp).astype(np.int8), rng.integers(0, 2, n_exp).astype(np.int32), np.array([10, 11], np.int64))
+    c_exp, k2 = de.as_c()
+    c_plain, k0 = dr.as_c()
+    rc, want = _map_counts(ex, c_plain, c_exp, 2)
+    assert rc == 0 and want.sum() > 0
+    c_ref, k1 = dr.as_c(sorted_by_position=True)
+    got = {}
+    for mode in ("fused", "split"):
+        if mode == "split":
+            os.environ["GMQL_MAP_INDEX"] = "split"
+        ex.lib.gmql_ctx_set_profiling(ex.ctx, 1)
+        try:
+            rc, got[mode] = _map_counts(ex, c_ref, c_exp, 2)
+        finally:
+            os.environ.pop("GMQL_MAP_INDEX", None)
+        buf = C.create_string_buffer(1 << 16)
+        ex.lib.gmql_ctx_profile_report(ex.ctx, buf, len(buf))
+        ex.lib.gmql_ctx_set_profiling(ex.ctx, 0)
+        assert rc == 0
+        assert ("k_map_index_small" in buf.value.decode()) == (mode == "fused")
+    assert np.array_equal(got["fused"], want) and np.array_equal(got["split"], want)
