@@ -35,6 +35,7 @@ struct gmql_ctx {
   // every API call, when the stream is idle
   std::vector<std::pair<void*, size_t>> pins;
   size_t pin_next = 0;
+  bool pending = false;   // a kernel has been launched since the last stream synchronisation
 };
 
 // pinned host memory valid until the next API call on this context
@@ -98,10 +99,14 @@ inline void gmql_trace(const char* what) {
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
     if ((ctx)->profiling) gmql_prof_end((ctx));                                               \
     (ctx)->launches++;                                                                        \
+    (ctx)->pending = true;                                                                    \
     CUDA_TRY(cudaGetLastError());                                                             \
   } while (0)
 
-#define GMQL_SYNC(ctx) ([&]() { gmql_trace("sync>"); cudaError_t _e = cudaStreamSynchronize((ctx)->stream); gmql_trace("<sync"); return _e; }())
+#define GMQL_SYNC(ctx) ([&]() { gmql_trace("sync>"); cudaError_t _e = cudaStreamSynchronize((ctx)->stream); (ctx)->pending = false; gmql_trace("<sync"); return _e; }())
+// end of an operator: everything the caller can observe is complete unless a kernel was launched after the last synchronisation
+// (stream-ordered frees and event records may still be queued; consumers of the result use the same stream)
+#define GMQL_SYNC_IF_PENDING(ctx) ((ctx)->pending ? GMQL_SYNC(ctx) : cudaSuccess)
 
 // stream-ordered device buffer (cudaMallocAsync pool: frees do not synchronise)
 template <typename T>

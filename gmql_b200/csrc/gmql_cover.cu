@@ -109,16 +109,30 @@ __global__ void __launch_bounds__(256) k_cover_prepass(const int32_t* __restrict
       else atomicMax(&span[c[j]], (unsigned long long)e[j]);
     }
   }
-  if (__any_sync(0xffffffffu, has_star) && (threadIdx.x & 31) == 0) flags[0] = 1;
-  if (__any_sync(0xffffffffu, zero) && (threadIdx.x & 31) == 0) flags[1] = 1;
-  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) flags[2] = 1;
+  // flags and the longest region: collected per block in shared memory, then ONE store / RED per block and flag (no
+  // value is read back: thousands of warps storing to, and reading from, the same 32-byte sector serialise in the L2)
+  __shared__ int s_fl[4];
+  if (threadIdx.x < 4) s_fl[threadIdx.x] = 0;
+  __syncthreads();
   {
     int ml = maxlen > 0x7fffffffLL ? 0x7fffffff : (int)maxlen;
     ml = __reduce_max_sync(0xffffffffu, ml);
-    if ((threadIdx.x & 31) == 0 && ml > 0) atomicMax(&flags[3], ml);
+    const bool a0 = __any_sync(0xffffffffu, has_star), a1 = __any_sync(0xffffffffu, zero), a2 = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      if (a0) s_fl[0] = 1;
+      if (a1) s_fl[1] = 1;
+      if (a2) s_fl[2] = 1;
+      if (ml > 0) atomicMax(&s_fl[3], ml);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_fl[0]) flags[0] = 1;
+    if (s_fl[1]) flags[1] = 1;
+    if (s_fl[2]) flags[2] = 1;
+    if (s_fl[3] > 0) atomicMax(&flags[3], s_fl[3]);
   }
   if (use_sh) {
-    __syncthreads();
     for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) {
       unsigned long long v = sh32 ? (unsigned long long)sspan32[c] : sspan[c];
       if (v) atomicMax(&span[c], v);
@@ -1161,7 +1175,8 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   // whole waves of the 2 x num_sms resident blocks, about 16 tiles per block (the first tile of every block range re-reads
   // its predecessor's regions), at most four waves
   const int64_t resident = (int64_t)ctx->num_sms * 2;
-  const int64_t waves = std::max<int64_t>(1, std::min<int64_t>(4, (t_hi - t_lo + resident * 8) / (resident * 16)));
+  int64_t waves = std::max<int64_t>(1, std::min<int64_t>(4, (t_hi - t_lo + resident * 8) / (resident * 16)));
+  if (const char* we = getenv("GMQL_COVER_WAVES")) waves = std::max(1, atoi(we));   // tuning hook
   const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), resident * waves));
   const int64_t seg = std::max<int64_t>(4096, (n / 16 + 2 * nT) / tgrid + 1);
   const int64_t cap = seg * tgrid;
@@ -1629,7 +1644,7 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
     if (shard) GMQL_REQUIRE(unified && n_groups == 1 && total < 0xffffffffull, GMQL_ERR_UNSUPPORTED, "gmql_cover_shard: one group, unified strands and a linear genome below 2^32 are required");
     if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res, shard ? &sspec : nullptr);
     else run_cover<uint64_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
-    CUDA_TRY(GMQL_SYNC(ctx));
+    CUDA_TRY(GMQL_SYNC_IF_PENDING(ctx));
     *out = res;
     gmql_trace("EXIT");
     return GMQL_OK;

@@ -627,6 +627,9 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   if (plan.n_aggs && n_rows) LAUNCH(ctx, k_map_finalize, grid_for(ctx, n_rows, 256), 256, 0, n_rows, plan, acc, mo);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
 
+  // REF_ROW: copy out of the ping-pong buffer that holds it (before the operator's one synchronisation)
+  DevBuf<int32_t> ref_row(ctx, n_ref);
+  if (n_ref) CUDA_TRY(cudaMemcpyAsync(ref_row.p, rows_by_sample, 4 * (size_t)n_ref, cudaMemcpyDeviceToDevice, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(h_bad != 2, GMQL_ERR_INVALID, "the same (ref sample, exp sample) pair is listed twice");
@@ -635,12 +638,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   res->rows = n_rows;
   res->kind = 1;
   result_add(res, GMQL_COL_MAP_ROW_OFFSETS, row_off);
-  // REF_ROW: copy out of the ping-pong buffer that holds it
-  {
-    DevBuf<int32_t> rr(ctx, n_ref);
-    if (n_ref) CUDA_TRY(cudaMemcpyAsync(rr.p, rows_by_sample, 4 * (size_t)n_ref, cudaMemcpyDeviceToDevice, ctx->stream));
-    result_add(res, GMQL_COL_MAP_REF_ROW, rr);
-  }
+  result_add(res, GMQL_COL_MAP_REF_ROW, ref_row);
   result_add(res, GMQL_COL_MAP_REF_SAMPLE_OFFSETS, sample_off);
   result_add(res, GMQL_COL_MAP_COUNT, count);
   if (plan.need_bag) { result_add(res, GMQL_COL_BAG_OFFSETS, bag_off); result_add(res, GMQL_COL_BAG_ROWS, bag_rows); }
@@ -771,7 +769,7 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
     res = new gmql_result();
     if (spans.G < 0xffffffffull) run_map<uint32_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
     else run_map<uint64_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
-    CUDA_TRY(GMQL_SYNC(ctx));
+    CUDA_TRY(GMQL_SYNC_IF_PENDING(ctx));
     *out = res;
     gmql_trace("EXIT");
     return GMQL_OK;
