@@ -96,77 +96,173 @@ __device__ __forceinline__ uint64_t make_record(const int32_t* __restrict__ chro
   return ((base + (uint64_t)s) << 32) | (uint64_t)((uint32_t)(e - s) | (ext ? EXT : 0u));
 }
 
-// regions per tile: block-private counters in shared memory, merged with one RED per non-empty counter
+// regions per tile: block-private counters in shared memory, merged with one RED per non-empty counter.  Block b counts
+// the 4096-region input tiles b, b + G, b + 2G, ... (G = gridDim.x) — the same tiles the coarse multisplit pass hands to
+// its blocks b, b + G, ... — and also reports its own count per COARSE bin (256 tiles): the coarse pass then reserves
+// output space on a cursor per (coarse bin, group b) instead of one per coarse bin, which every block of the chip would
+// hit once per tile (tens of thousands of same-address atomics with a returned value, serialised in the L2).
 static __global__ void __launch_bounds__(1024, 1) k_tile_hist(const int32_t* __restrict__ chrom, const void* __restrict__ start, int bits, const uint32_t* __restrict__ cls,
-                                                               int64_t n, LinMap lm, int logw, int nT, uint32_t* __restrict__ hist) {
-  extern __shared__ uint32_t sh_hist[];                    // [nT] then chromosome offsets
+                                                               int64_t n, LinMap lm, int logw, int nT, uint32_t* __restrict__ hist, uint32_t* __restrict__ coarse_cnt, int n_coarse,
+                                                               int vec_ok) {
+  extern __shared__ uint32_t sh_hist[];                    // [nT] then chromosome offsets, then the coarse counters
   uint64_t* s_coff = (uint64_t*)(sh_hist + ((nT + 1) & ~1));
   const bool chrom_sh = lm.n_chrom <= 1024;
+  uint32_t* s_coarse = (uint32_t*)(s_coff + (chrom_sh ? lm.n_chrom : 0));
   for (int k = threadIdx.x; k < nT; k += blockDim.x) sh_hist[k] = 0;
+  for (int k = threadIdx.x; k < n_coarse; k += blockDim.x) s_coarse[k] = 0;
   if (chrom_sh) for (int k = threadIdx.x; k < lm.n_chrom; k += blockDim.x) s_coff[k] = lm.coff[k];
   __syncthreads();
   const uint64_t* coff = chrom_sh ? s_coff : lm.coff;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
-    int c[4]; int64_t st[4]; uint32_t cl[4];
+  const int64_t n_tiles = (n + MSP_TILE - 1) / MSP_TILE;
+  const bool vec = vec_ok && bits == 32;
+  for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += 2 * (int64_t)gridDim.x) {
+    int c[8]; uint32_t st[8], cl[8];                       // two tiles in flight: four consecutive regions per thread and tile
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int64_t q = i + j * stride;
-      bool ok = q < n;
-      c[j] = ok ? chrom[q] : -1;
-      st[j] = ok ? ld_coord(start, bits, q) : 0;
-      cl[j] = ok && cls ? cls[q] : 0u;
+    for (int h = 0; h < 2; ++h) {
+      const int64_t t = t0 + h * (int64_t)gridDim.x;
+      const int64_t i0 = t * MSP_TILE + (int64_t)threadIdx.x * 4;
+      if (t < n_tiles && vec && i0 + 4 <= n) {
+        const int4 vc = *(const int4*)(chrom + i0), vs = *(const int4*)((const int32_t*)start + i0);
+        uint4 vk = make_uint4(0u, 0u, 0u, 0u);
+        if (cls) vk = *(const uint4*)(cls + i0);
+        c[4 * h] = vc.x; c[4 * h + 1] = vc.y; c[4 * h + 2] = vc.z; c[4 * h + 3] = vc.w;
+        st[4 * h] = (uint32_t)vs.x; st[4 * h + 1] = (uint32_t)vs.y; st[4 * h + 2] = (uint32_t)vs.z; st[4 * h + 3] = (uint32_t)vs.w;
+        cl[4 * h] = vk.x; cl[4 * h + 1] = vk.y; cl[4 * h + 2] = vk.z; cl[4 * h + 3] = vk.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool ok = t < n_tiles && i0 + q < n;
+          c[4 * h + q] = ok ? chrom[i0 + q] : -1;
+          st[4 * h + q] = ok ? (uint32_t)ld_coord(start, bits, i0 + q) : 0u;   // the tile path runs on 32-bit linear keys only
+          cl[4 * h + q] = ok && cls ? cls[i0 + q] : 0u;
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       if (c[j] < 0) continue;
-      uint64_t key = (uint64_t)cl[j] * lm.G + coff[c[j]] + (uint64_t)st[j];
+      const uint32_t key = (uint32_t)((uint64_t)cl[j] * lm.G + coff[c[j]]) + st[j];
       atomicAdd(&sh_hist[key >> logw], 1u);
     }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < nT; k += blockDim.x) { uint32_t c = sh_hist[k]; if (c) atomicAdd(&hist[k], c); }
+  for (int k = threadIdx.x; k < nT; k += blockDim.x) {
+    const uint32_t c = sh_hist[k];
+    if (c) { atomicAdd(&hist[k], c); atomicAdd(&s_coarse[k >> 8], c); }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_coarse; k += blockDim.x) coarse_cnt[(size_t)k * gridDim.x + blockIdx.x] = s_coarse[k];
 }
 
-// cursors: every tile / coarse bin starts at its final offset
-static __global__ void k_init_cursors(const uint32_t* __restrict__ off, int nT, uint32_t* __restrict__ cur_tile, uint32_t* __restrict__ cur_coarse, int n_coarse) {
+// cursors: every tile starts at its final offset (the coarse cursors are the exclusive scan of k_tile_hist's coarse counts)
+static __global__ void k_init_cursors(const uint32_t* __restrict__ off, int nT, uint32_t* __restrict__ cur_tile) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nT; k += gridDim.x * blockDim.x) cur_tile[k] = off[k];
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_coarse; k += gridDim.x * blockDim.x) cur_coarse[k] = off[min(k << 8, nT)];
 }
+
+// ---- TMA bulk copies (cp.async.bulk, 1-D) completing on a shared-memory mbarrier -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// generic-proxy reads of a staging buffer are ordered before the async proxy overwrites it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // FUSED: records are built from the input columns and split by coarse bin (tile >> 8); otherwise records are read from
 // `in` and split by tile.  bin_shift = 32 + logw (+ 8 for the coarse pass).
+// The input of the NEXT tile of a block (one 32 KB run of records, or three 16 KB column runs) is fetched by TMA bulk
+// copies into a staging buffer while the current tile is ranked, regrouped and written: every thread moves its items
+// from the staging buffer into registers first, so one staging buffer and one mbarrier suffice, and the load latency
+// no longer sits at the head of every tile (registers are at the 64-per-thread limit of two 512-thread blocks per SM,
+// so a register prefetch is not an option).
+constexpr size_t MSP_STAGE_BYTES_FUSED = 3 * 4 * (size_t)MSP_TILE, MSP_STAGE_BYTES_PACKED = 8 * (size_t)MSP_TILE;
+template <bool FUSED>
+constexpr size_t msp_smem_bytes() { return 8 * (size_t)MSP_TILE + (FUSED ? MSP_STAGE_BYTES_FUSED : MSP_STAGE_BYTES_PACKED) + 3 * 4 * (size_t)MSP_BINS + (FUSED ? 8 * 256 : 0); }
+
 template <bool FUSED>
 static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint64_t* __restrict__ in, const int32_t* __restrict__ chrom, const void* __restrict__ start,
                                                                       const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls, LinMap lm, int64_t B,
-                                                                      int64_t n, int bin_shift, uint32_t* __restrict__ cursor, uint64_t* __restrict__ out, int vec_ok) {
-  __shared__ uint64_t sdata[MSP_TILE];
-  __shared__ uint32_t cnt[MSP_BINS], lexcl[MSP_BINS], gbase[MSP_BINS];
-  __shared__ uint64_t s_coff[FUSED ? 256 : 1];
+                                                                      int64_t n, int bin_shift, uint32_t* __restrict__ cursor, uint64_t* __restrict__ out, int vec_ok, int groups) {
+  extern __shared__ __align__(128) unsigned char msp_smem[];
+  uint64_t* sdata = (uint64_t*)msp_smem;                                    // [MSP_TILE] regroup buffer
+  unsigned char* stage = msp_smem + 8 * (size_t)MSP_TILE;                   // TMA landing buffer
+  uint32_t* cnt = (uint32_t*)(stage + (FUSED ? MSP_STAGE_BYTES_FUSED : MSP_STAGE_BYTES_PACKED));
+  uint32_t* lexcl = cnt + MSP_BINS;
+  uint32_t* gbase = lexcl + MSP_BINS;
+  uint64_t* s_coff = (uint64_t*)(gbase + MSP_BINS);                         // [256], FUSED only
   __shared__ uint32_t wtot[MSP_THREADS / 32];
   __shared__ uint32_t s_base_bin;
+  __shared__ uint64_t s_bar;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool chrom_sh = FUSED && lm.n_chrom <= 256;
   if (chrom_sh) for (int k = tid; k < lm.n_chrom; k += MSP_THREADS) s_coff[k] = lm.coff[k];
   const uint64_t* coff = chrom_sh ? s_coff : lm.coff;
   const int64_t n_tiles = (n + MSP_TILE - 1) / MSP_TILE;
+  // full tiles of suitably aligned 32-bit input go through the staging buffer
+  const bool tma_ok = FUSED ? (vec_ok && bits == 32 && cls == nullptr) : (((uintptr_t)in & 15u) == 0);
+  auto issue = [&](int64_t t) {                            // one thread: arm the barrier, start the copies of tile t
+    const int64_t base = t * MSP_TILE;
+    if (FUSED) {
+      mbar_expect_tx(&s_bar, (uint32_t)MSP_STAGE_BYTES_FUSED);
+      tma_load_1d(stage, chrom + base, 4 * MSP_TILE, &s_bar);
+      tma_load_1d(stage + 4 * MSP_TILE, (const int32_t*)start + base, 4 * MSP_TILE, &s_bar);
+      tma_load_1d(stage + 8 * MSP_TILE, (const int32_t*)stop + base, 4 * MSP_TILE, &s_bar);
+    } else {
+      mbar_expect_tx(&s_bar, (uint32_t)MSP_STAGE_BYTES_PACKED);
+      tma_load_1d(stage, in + base, 8 * MSP_TILE, &s_bar);
+    }
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    if (tma_ok && (int64_t)blockIdx.x < n_tiles && n - (int64_t)blockIdx.x * MSP_TILE >= MSP_TILE) issue(blockIdx.x);
+  }
+  uint32_t parity = 0;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t base = t * MSP_TILE;
     const int count = (int)((n - base) < (int64_t)MSP_TILE ? (n - base) : (int64_t)MSP_TILE);
+    const bool staged = tma_ok && count == MSP_TILE;
+    // coarse pass: the cursor of (bin, group of this input tile), see k_tile_hist; fine pass: one cursor per tile
+    const uint32_t cmul = FUSED ? (uint32_t)groups : 1u, cadd = FUSED ? (uint32_t)(t % groups) : 0u;
     for (int k = tid; k < MSP_BINS; k += MSP_THREADS) cnt[k] = 0;
-    __syncthreads();                                       // also orders s_coff and the previous iteration's reads
+    __syncthreads();                                       // also orders s_coff, the barrier's init and the previous iteration's reads
     // item j of a thread is record idx_of(j) of the tile: striped for packed input, four consecutive regions per
     // 128-bit column load when the records are built from the columns
     uint64_t rec[MSP_ITEMS];
+    if (staged) { mbar_wait(&s_bar, parity); parity ^= 1u; }
     if (FUSED) {
 #pragma unroll
       for (int j4 = 0; j4 < MSP_ITEMS / 4; ++j4) {
         const int idx0 = (j4 * MSP_THREADS + tid) * 4;
         const int64_t i0 = base + idx0;
-        if (idx0 + 4 <= count && vec_ok && bits == 32) {
-          const int4 vc = *(const int4*)(chrom + i0), vs = *(const int4*)((const int32_t*)start + i0), ve = *(const int4*)((const int32_t*)stop + i0);
+        if (staged || (idx0 + 4 <= count && vec_ok && bits == 32)) {
+          int4 vc, vs, ve;
           uint4 vk = make_uint4(0u, 0u, 0u, 0u);
-          if (cls) vk = *(const uint4*)(cls + i0);
+          if (staged) {
+            vc = ((const int4*)stage)[j4 * MSP_THREADS + tid];
+            vs = ((const int4*)(stage + 4 * MSP_TILE))[j4 * MSP_THREADS + tid];
+            ve = ((const int4*)(stage + 8 * MSP_TILE))[j4 * MSP_THREADS + tid];
+          } else {
+            vc = *(const int4*)(chrom + i0); vs = *(const int4*)((const int32_t*)start + i0); ve = *(const int4*)((const int32_t*)stop + i0);
+            if (cls) vk = *(const uint4*)(cls + i0);
+          }
           const int cc[4] = {vc.x, vc.y, vc.z, vc.w}, ss[4] = {vs.x, vs.y, vs.z, vs.w}, ee[4] = {ve.x, ve.y, ve.z, ve.w};
           const uint32_t kk[4] = {vk.x, vk.y, vk.z, vk.w};
 #pragma unroll
@@ -184,13 +280,14 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
 #pragma unroll
       for (int j = 0; j < MSP_ITEMS; ++j) {
         const int idx = j * MSP_THREADS + tid;
-        rec[j] = idx < count ? in[base + idx] : 0ull;
+        rec[j] = staged ? ((const uint64_t*)stage)[idx] : (idx < count ? in[base + idx] : 0ull);
       }
     }
-    if (!FUSED) {
-      // local bins are counted from the coarse bin of the tile's first record
-      if (tid == 0) s_base_bin = (uint32_t)(rec[0] >> bin_shift) & ~255u;
-      __syncthreads();
+    if (!FUSED && tid == 0) s_base_bin = (uint32_t)(rec[0] >> bin_shift) & ~255u;   // local bins are counted from the coarse bin of the tile's first record
+    if (!FUSED || tma_ok) __syncthreads();                 // every thread holds its items: the staging buffer is free again
+    if (tma_ok && tid == 0) {
+      const int64_t tn = t + gridDim.x;
+      if (tn < n_tiles && n - tn * MSP_TILE >= MSP_TILE) { fence_proxy_async(); issue(tn); }
     }
     const uint32_t base_bin = FUSED ? 0u : s_base_bin;
     uint32_t rk[MSP_ITEMS];
@@ -202,7 +299,7 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
         uint32_t lb = (uint32_t)(rec[j] >> bin_shift) - base_bin;
         if (lb < (uint32_t)MSP_BINS) rk[j] = atomicAdd(&cnt[lb], 1u);
         else {                                             // far bin (tiny coarse bins only): placed directly
-          uint32_t g = atomicAdd(&cursor[(uint32_t)(rec[j] >> bin_shift)], 1u);
+          uint32_t g = atomicAdd(&cursor[(uint32_t)(rec[j] >> bin_shift) * cmul + cadd], 1u);
           out[g] = rec[j];
         }
       }
@@ -211,8 +308,8 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
     // reserve every bin's output range; exclusive offsets of the bins inside the block
     {
       uint32_t c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
-      if (c0) gbase[2 * tid] = atomicAdd(&cursor[base_bin + 2 * tid], c0);
-      if (c1) gbase[2 * tid + 1] = atomicAdd(&cursor[base_bin + 2 * tid + 1], c1);
+      if (c0) gbase[2 * tid] = atomicAdd(&cursor[(base_bin + 2 * tid) * cmul + cadd], c0);
+      if (c1) gbase[2 * tid + 1] = atomicAdd(&cursor[(base_bin + 2 * tid + 1) * cmul + cadd], c1);
       uint32_t v = c0 + c1, x = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }

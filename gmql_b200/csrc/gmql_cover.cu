@@ -1150,19 +1150,27 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   if (nT <= tiled::HIST_CAP) {
     // counting + two multisplit passes (cover_tiled.cuh): the packed record never exists unpartitioned
     const int n_coarse = (int)((nT + 255) >> 8) + 1;
-    DevBuf<uint32_t> hist(ctx, nT + 1), cur_tile(ctx, nT + 1), cur_coarse(ctx, n_coarse);
+    // groups of input tiles (k_tile_hist): block b of the counting kernel and the blocks b, b + G, ... of the coarse pass
+    const int64_t in_tiles = ceil_div64(n, tiled::MSP_TILE);
+    const int G = (int)std::max<int64_t>(1, std::min<int64_t>(in_tiles, (int64_t)ctx->num_sms));
+    DevBuf<uint32_t> hist(ctx, nT + 1), cur_tile(ctx, nT + 1), coarse_cnt(ctx, (int64_t)n_coarse * G), cur_coarse(ctx, (int64_t)n_coarse * G + 1);
     hist.zero();
-    size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + (lm.n_chrom <= 1024 ? 8 * (size_t)lm.n_chrom : 0);
-    CUDA_TRY(cudaFuncSetAttribute(tiled::k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
-    LAUNCH(ctx, tiled::k_tile_hist, (unsigned)std::min<int64_t>(ceil_div64(n, 1024 * 16), (int64_t)ctx->num_sms), 1024, hsh, in.chrom, in.start, in.coord_bits, cls, n, lm, logw, (int)nT, hist.p);
-    device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, hist.p, offS.p, nT, offS.p + nT);
-    LAUNCH(ctx, tiled::k_init_cursors, grid_for(ctx, nT, 256), 256, 0, offS.p, (int)nT, cur_tile.p, cur_coarse.p, n_coarse);
-    const unsigned mg = (unsigned)std::min<int64_t>(ceil_div64(n, tiled::MSP_TILE), (int64_t)ctx->num_sms * 16);
     auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
     const int vec_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(cls) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
-    LAUNCH(ctx, tiled::k_multisplit<true>, mg, tiled::MSP_THREADS, 0, (const uint64_t*)nullptr, in.chrom, in.start, in.stop, in.coord_bits, cls, lm, cfg.B, n, 32 + logw + 8, cur_coarse.p, pk_a.p, vec_ok);
-    LAUNCH(ctx, tiled::k_multisplit<false>, mg, tiled::MSP_THREADS, 0, (const uint64_t*)pk_a.p, (const int32_t*)nullptr, (const void*)nullptr, (const void*)nullptr, 0, (const uint32_t*)nullptr, lm, cfg.B, n,
-           32 + logw, cur_tile.p, pk_b.p, 0);
+    size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + (lm.n_chrom <= 1024 ? 8 * (size_t)lm.n_chrom : 0) + sizeof(uint32_t) * (size_t)n_coarse;
+    CUDA_TRY(cudaFuncSetAttribute(tiled::k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
+    LAUNCH(ctx, tiled::k_tile_hist, (unsigned)G, 1024, hsh, in.chrom, in.start, in.coord_bits, cls, n, lm, logw, (int)nT, hist.p, coarse_cnt.p, n_coarse, vec_ok);
+    device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, hist.p, offS.p, nT, offS.p + nT);
+    device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, coarse_cnt.p, cur_coarse.p, (int64_t)n_coarse * G, cur_coarse.p + (int64_t)n_coarse * G);
+    LAUNCH(ctx, tiled::k_init_cursors, grid_for(ctx, nT, 256), 256, 0, offS.p, (int)nT, cur_tile.p);
+    // the coarse pass runs whole multiples of G blocks, so that block x only sees input tiles of group x % G
+    const unsigned mg_c = (unsigned)(G * std::max<int64_t>(1, std::min<int64_t>(16, ceil_div64(in_tiles, G))));
+    const unsigned mg = (unsigned)std::min<int64_t>(in_tiles, (int64_t)ctx->num_sms * 16);
+    CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<true>()));
+    CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<false>()));
+    LAUNCH(ctx, tiled::k_multisplit<true>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<true>(), (const uint64_t*)nullptr, in.chrom, in.start, in.stop, in.coord_bits, cls, lm, cfg.B, n, 32 + logw + 8, cur_coarse.p, pk_a.p, vec_ok, G);
+    LAUNCH(ctx, tiled::k_multisplit<false>, mg, tiled::MSP_THREADS, tiled::msp_smem_bytes<false>(), (const uint64_t*)pk_a.p, (const int32_t*)nullptr, (const void*)nullptr, (const void*)nullptr, 0, (const uint32_t*)nullptr, lm, cfg.B, n,
+           32 + logw, cur_tile.p, pk_b.p, 0, 1);
     P = pk_b.p;
   } else {
     LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, pk_a.p);
