@@ -217,6 +217,8 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
   const uint64_t* coff = chrom_sh ? s_coff : lm.coff;
   const int64_t n_tiles = (n + MSP_TILE - 1) / MSP_TILE;
   // full tiles of suitably aligned 32-bit input go through the staging buffer
+  // n % B == 0  <=>  M * n (mod 2^64) <= M - 1 with M = floor((2^64 - 1) / B) + 1, exact for 32-bit n (Lemire, Kaser, Kurz 2019)
+  const uint64_t bmagic = FUSED && B > 1 ? 0xffffffffffffffffull / (uint64_t)B + 1ull : 0ull;
   const bool tma_ok = FUSED ? (vec_ok && bits == 32 && cls == nullptr) : (((uintptr_t)in & 15u) == 0);
   auto issue = [&](int64_t t) {                            // one thread: arm the barrier, start the copies of tile t
     const int64_t base = t * MSP_TILE;
@@ -268,7 +270,7 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t key = (uint32_t)((uint64_t)kk[q] * lm.G + coff[cc[q]]) + (uint32_t)ss[q];
-            const bool ext = ((uint32_t)ee[q] % (uint32_t)B == 0) && ss[q] < ee[q];
+            const bool ext = (bmagic * (uint64_t)(uint32_t)ee[q] <= bmagic - 1ull) && ss[q] < ee[q];   // ee % B == 0 without a division
             rec[j4 * 4 + q] = ((uint64_t)key << 32) | (uint64_t)((uint32_t)(ee[q] - ss[q]) | (ext ? EXT : 0u));
           }
         } else {
@@ -306,10 +308,13 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
     }
     __syncthreads();
     // reserve every bin's output range; exclusive offsets of the bins inside the block
+    uint32_t g0 = 0, g1 = 0;
     {
       uint32_t c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
-      if (c0) gbase[2 * tid] = atomicAdd(&cursor[(base_bin + 2 * tid) * cmul + cadd], c0);
-      if (c1) gbase[2 * tid + 1] = atomicAdd(&cursor[(base_bin + 2 * tid + 1) * cmul + cadd], c1);
+      // the returned offsets are only needed by the final write: they stay in registers until after the regroup, so the
+      // atomics' round trip to the L2 overlaps the scan, the barriers and the regroup
+      if (c0) g0 = atomicAdd(&cursor[(base_bin + 2 * tid) * cmul + cadd], c0);
+      if (c1) g1 = atomicAdd(&cursor[(base_bin + 2 * tid + 1) * cmul + cadd], c1);
       uint32_t v = c0 + c1, x = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -330,6 +335,7 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
         sdata[lexcl[lb] + rk[j]] = rec[j];
       }
     }
+    gbase[2 * tid] = g0; gbase[2 * tid + 1] = g1;
     __syncthreads();
     const int local_total = (int)(lexcl[MSP_BINS - 1] + cnt[MSP_BINS - 1]);
     for (int i = tid; i < local_total; i += MSP_THREADS) {
