@@ -165,6 +165,8 @@ struct DevRegions {
   int64_t h2d_bytes = 0;
   const int64_t* span_hint = nullptr;  // host [n_chrom] upper bounds of stop, or null
   bool sorted_hint = false;            // rows ordered by (chrom, start) according to the caller (verified on the device)
+  const int64_t* sample_off = nullptr; // device [n_samples + 1] when the rows are grouped by sample (sample_offsets given), else null
+  int64_t max_sample_rows = 0;         // largest sample (rows), valid with sample_off
 };
 
 // upload (or adopt) a gmql_regions; only the value columns listed in need_cols are moved

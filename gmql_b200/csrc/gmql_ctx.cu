@@ -167,17 +167,31 @@ void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector
     out->stop = upload_array(ctx, r->stop, n * cb, r->location, out);
   }
   out->strand = (const int8_t*)upload_array(ctx, r->strand, n, r->location, out);
-  if (!r->sample && r->sample_offsets) {
+  if (r->sample_offsets) {
+    // rows grouped by sample.  Without a sample column the offsets define it; with one they are a promise about its
+    // layout, which the kernels that rely on it check against the column.
     const int64_t* off = r->sample_offsets;   // host array by contract
     GMQL_REQUIRE(off[0] == 0 && off[r->n_samples] == r->n, GMQL_ERR_INVALID, "sample_offsets must start at 0 and end at n");
-    for (int s = 0; s < r->n_samples; ++s) GMQL_REQUIRE(off[s] <= off[s + 1], GMQL_ERR_INVALID, "sample_offsets must be non-decreasing");
-    DevBuf<uint8_t> doff(ctx, (int64_t)(8 * ((size_t)r->n_samples + 1)));
-    CUDA_TRY(cudaMemcpyAsync(doff.p, off, 8 * ((size_t)r->n_samples + 1), cudaMemcpyHostToDevice, ctx->stream));
-    out->h2d_bytes += 8 * ((int64_t)r->n_samples + 1);
-    DevBuf<uint8_t> smp(ctx, (int64_t)(n * 4 ? n * 4 : 1));
-    if (n) LAUNCH(ctx, k_expand_sample_offsets, (int)std::min<int64_t>(r->n_samples, (int64_t)ctx->num_sms * 16), 256, 0, (const int64_t*)doff.p, r->n_samples, (int32_t*)smp.p);
-    out->sample = (const int32_t*)smp.p;
-    out->owned.push_back(std::move(smp));
+    int64_t widest = 0;
+    for (int s = 0; s < r->n_samples; ++s) {
+      GMQL_REQUIRE(off[s] <= off[s + 1], GMQL_ERR_INVALID, "sample_offsets must be non-decreasing");
+      widest = std::max<int64_t>(widest, off[s + 1] - off[s]);
+    }
+    const size_t ob = 8 * ((size_t)r->n_samples + 1);
+    DevBuf<uint8_t> doff(ctx, (int64_t)ob);
+    CUDA_TRY(cudaMemcpyAsync(doff.p, off, ob, cudaMemcpyHostToDevice, ctx->stream));   // small pageable source: staged by the driver before the call returns
+    if (r->location != GMQL_LOC_DEVICE) out->h2d_bytes += (int64_t)ob;
+    out->sample_off = (const int64_t*)doff.p;
+    out->max_sample_rows = widest;
+    if (!r->sample) {
+      DevBuf<uint8_t> smp(ctx, (int64_t)(n * 4 ? n * 4 : 1));
+      if (n) LAUNCH(ctx, k_expand_sample_offsets, (int)std::min<int64_t>(r->n_samples, (int64_t)ctx->num_sms * 16), 256, 0, (const int64_t*)doff.p, r->n_samples, (int32_t*)smp.p);
+      out->sample = (const int32_t*)smp.p;
+      out->owned.push_back(std::move(smp));
+    } else {
+      out->sample = (const int32_t*)upload_array(ctx, r->sample, n * 4, r->location, out);
+    }
+    out->owned.push_back(std::move(doff));
   } else {
     out->sample = (const int32_t*)upload_array(ctx, r->sample, n * 4, r->location, out);
   }
@@ -237,6 +251,7 @@ extern "C" void gmql_result_free(gmql_ctx* ctx, gmql_result* r) {
 struct gmql_dataset {
   DevRegions dev;
   std::vector<int64_t> sample_ids;
+  std::vector<int64_t> sample_offsets;   // host copy when the upload declared the rows grouped by sample
   std::vector<const double*> cols;
   std::vector<const uint8_t*> valid;
 };
@@ -265,6 +280,10 @@ extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql
     view->stop = d->dev.stop;
     view->strand = d->dev.strand;
     view->sample = d->dev.sample;
+    if (host->sample_offsets) {
+      d->sample_offsets.assign(host->sample_offsets, host->sample_offsets + host->n_samples + 1);
+      view->sample_offsets = d->sample_offsets.data();   // the view keeps the promise: rows grouped by sample
+    }
     view->n_chrom = d->dev.n_chrom;
     view->n_samples = d->dev.n_samples;
     view->sample_ids = d->sample_ids.data();

@@ -366,6 +366,92 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_stream(MapStreamArgs<K> a
   }
 }
 
+// ---- COUNT onto a small reference, experiment rows grouped by sample --------------------------------------------------
+// The shape of `M = MAP() C E` with C a COVER result (~10^4 regions) and E a few thousand sample files of ~10^5 regions:
+// the streaming kernel above is then bound by its scattered accesses — one 16-byte reference entry load and one RED into a
+// table of n_ref x n_samples counters per experiment region (L2 sector throughput, not DRAM).  Here a block takes one
+// experiment sample at a time and keeps EVERYTHING it touches at random in shared memory: the reference as 16-byte records
+// {start, stop, running max of the earlier stops, rank << 2 | strand}, the bucket table over the linear coordinate, and the
+// sample's n_ref counters (16 bits each: a count cannot exceed the sample's rows, < 65 536).  Global memory sees only the
+// coalesced stream of the sample's regions and the coalesced write of its finished row block (no REDs, no zero-fill).
+// Conditions (else k_map_stream): one reference sample, 32-bit keys, no value aggregates / BAG, rows grouped by sample
+// (sample_offsets), every sample below 65 536 rows, and the reference small enough for shared memory.
+constexpr int64_t MG_SMEM = 224 * 1024;
+
+struct MapGroupedArgs {
+  const int32_t* e_chrom; const void* e_start; const void* e_stop; int e_bits;
+  const int8_t* e_strand; const int32_t* e_sample; const int64_t* sample_off; int n_exp_samples;
+  LinMap lm; const uint32_t* r_start; const RefEntry<uint32_t>* entries; int n_ref;
+  const long long* pair_base; int* bad;
+  const uint32_t* tbl; int tbl_shift; int n_tbl;
+  int* count;
+};
+
+__global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_grouped(MapGroupedArgs a) {
+  extern __shared__ __align__(16) uint32_t g_dyn[];
+  uint4* s_ref = (uint4*)g_dyn;                                   // [n_ref]
+  uint32_t* s_cnt = g_dyn + 4 * (size_t)a.n_ref;                  // [(n_ref + 1) / 2] two 16-bit counters per word
+  const int n_cw = (a.n_ref + 1) >> 1;
+  uint32_t* s_tbl = s_cnt + ((n_cw + 3) & ~3);                    // [n_tbl]
+  uint64_t* s_coff = (uint64_t*)(s_tbl + ((a.n_tbl + 3) & ~3));   // [n_chrom] offsets, then spans
+  int64_t* s_span = (int64_t*)(s_coff + a.lm.n_chrom);
+  for (int k = threadIdx.x; k < a.n_ref; k += MS_THREADS) {
+    const RefEntry<uint32_t> e = a.entries[k];
+    s_ref[k] = make_uint4(a.r_start[k], e.stop, e.pmax_prev, (e.rank << 2) | (e.meta & 3u));
+  }
+  for (int k = threadIdx.x; k < a.n_tbl; k += MS_THREADS) s_tbl[k] = a.tbl[k];
+  for (int k = threadIdx.x; k < a.lm.n_chrom; k += MS_THREADS) { s_coff[k] = a.lm.coff[k]; s_span[k] = a.lm.span[k]; }
+  for (int smp = blockIdx.x; smp < a.n_exp_samples; smp += gridDim.x) {
+    const long long base = a.pair_base[smp];                      // the only reference sample is sample 0
+    if (base < 0) continue;                                       // this experiment sample is in no pair (block-uniform)
+    for (int k = threadIdx.x; k < n_cw; k += MS_THREADS) s_cnt[k] = 0;
+    __syncthreads();                                              // also orders the staging above
+    const int64_t lo = a.sample_off[smp], hi = a.sample_off[smp + 1];
+    for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += (int64_t)MS_THREADS * MS_PER) {
+      int c[MS_PER], st[MS_PER], sm[MS_PER];
+      int64_t s[MS_PER], e[MS_PER];
+#pragma unroll
+      for (int j = 0; j < MS_PER; ++j) {                          // coalesced 32-bit loads, four rows in flight per thread
+        const int64_t i = i0 + (int64_t)j * MS_THREADS;
+        const bool ok = i < hi;
+        c[j] = ok ? a.e_chrom[i] : -2;                            // -2: padding lane
+        s[j] = ok ? ld_coord(a.e_start, a.e_bits, i) : 0;
+        e[j] = ok ? ld_coord(a.e_stop, a.e_bits, i) : 0;
+        st[j] = ok && a.e_strand ? (int)a.e_strand[i] : 0;
+        sm[j] = ok && a.e_sample ? a.e_sample[i] : smp;
+      }
+#pragma unroll
+      for (int j = 0; j < MS_PER; ++j) {
+        if (c[j] == -2) continue;
+        if (sm[j] != smp) { *a.bad = 3; continue; }               // the rows are not grouped as sample_offsets promised
+        if (c[j] < 0 || c[j] >= a.lm.n_chrom) { *a.bad = 1; continue; }
+        const int64_t sp = s_span[c[j]];
+        if (s[j] >= sp || e[j] <= 0) continue;                    // no reference region can satisfy r.start < e.stop && e.start < r.stop
+        if (s[j] < 0) { *a.bad = 1; continue; }
+        if (e[j] > sp + 1) e[j] = sp + 1;
+        const uint64_t co = s_coff[c[j]];
+        const uint32_t ls = (uint32_t)(co + (uint64_t)s[j]), le = (uint32_t)(co + (uint64_t)e[j]);
+        const uint32_t b = le >> a.tbl_shift;
+        int lo2 = (int)s_tbl[b], hi2 = (int)s_tbl[b + 1];
+        while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (s_ref[mid].x < le) lo2 = mid + 1; else hi2 = mid; }
+        int k = lo2 - 1;                                          // last reference region with start < region.stop
+        while (k >= 0) {
+          const uint4 r = s_ref[k];
+          if (r.y > ls && strand_ok((int)(r.w & 3u), st[j])) {
+            const uint32_t rank = r.w >> 2;
+            atomicAdd(&s_cnt[rank >> 1], 1u << ((rank & 1u) << 4));
+          }
+          if (r.z <= ls) break;
+          --k;
+        }
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.n_ref; k += MS_THREADS) a.count[base + k] = (int)((s_cnt[k >> 1] >> ((k & 1) << 4)) & 0xffffu);
+    __syncthreads();
+  }
+}
+
 // rows of non-canonical duplicates are not emitted by the reference (MapKey collapse): flag them with count = -1
 __global__ void k_mark_dups(const int32_t* __restrict__ pl, const int64_t* __restrict__ row_off, int64_t n_pairs, const int64_t* __restrict__ sample_off,
                             const uint32_t* __restrict__ rows_by_sample, const int32_t* __restrict__ dup_of, int* __restrict__ count) {
@@ -539,8 +625,14 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   // bucket table, resident in the streaming kernel's shared memory: as fine as fits (most buckets then hold no start
   // and a query needs no search at all), at least 2^10 buckets
   int tbl_shift = 0;
+  // COUNT onto a small single-sample reference with the experiment rows grouped by sample: k_map_count_grouped
+  const char* mg_env = getenv("GMQL_MAP_GROUPED");         // "0": test hook
+  const int64_t mg_fixed = 16 * n_ref + 4 * (((n_ref + 1) / 2 + 3) & ~(int64_t)3) + 16 * (int64_t)lm.n_chrom;
+  const int64_t mg_tbl = (MG_SMEM - mg_fixed) / 4 - 8;
+  const bool grouped = single && sizeof(K) == 4 && plan.n_cols == 0 && !plan.need_bag && exp.sample_off != nullptr && exp.max_sample_rows <= 65535 &&
+                       n_ref > 0 && n_exp > 0 && n_pairs > 0 && mg_tbl >= 2048 && !(mg_env && mg_env[0] == '0');
   {
-    int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)MS_MAX_TBL - 2, 16 * std::max<int64_t>(n_ref, 1)));
+    int64_t want = std::max<int64_t>(1024, std::min<int64_t>(grouped ? mg_tbl : (int64_t)MS_MAX_TBL - 2, 16 * std::max<int64_t>(n_ref, 1)));
     while (tbl_shift < 62 && (int64_t)(lm.G >> tbl_shift) + 2 > want) ++tbl_shift;
   }
   int64_t n_buckets = (int64_t)(lm.G >> tbl_shift) + 1;
@@ -558,7 +650,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   MapAcc acc;
   memset(&acc, 0, sizeof acc);
   DevBuf<int> count(ctx, n_rows);
-  count.zero();
+  if (!grouped) count.zero();                            // the grouped kernel writes every row
   acc.count = count.p;
   DevBuf<int> nn[8];
   DevBuf<double> sum[8];
@@ -578,7 +670,18 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   memset(&ma_saved, 0, sizeof ma_saved);
   size_t sh_saved = 0;
   int g_saved = 1;
-  if (n_exp && n_ref && n_rows) {
+  if (grouped) {
+    MapGroupedArgs ga;
+    ga.e_chrom = exp.chrom; ga.e_start = exp.start; ga.e_stop = exp.stop; ga.e_bits = exp.coord_bits;
+    ga.e_strand = exp.strand; ga.e_sample = exp.sample; ga.sample_off = exp.sample_off; ga.n_exp_samples = n_rs;
+    ga.lm = lm; ga.r_start = (const uint32_t*)ix.start; ga.entries = (const RefEntry<uint32_t>*)entries.p; ga.n_ref = (int)n_ref;
+    ga.pair_base = pair_base.p; ga.bad = bad.p;
+    ga.tbl = tbl.p; ga.tbl_shift = tbl_shift; ga.n_tbl = (int)(n_buckets + 2);
+    ga.count = count.p;
+    const size_t sh = (size_t)mg_fixed + 4 * (size_t)((ga.n_tbl + 3) & ~3);
+    CUDA_TRY(cudaFuncSetAttribute(k_map_count_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    LAUNCH(ctx, k_map_count_grouped, (int)std::min<int64_t>(n_rs, (int64_t)ctx->num_sms), MS_THREADS, sh, ga);
+  } else if (n_exp && n_ref && n_rows) {
     MapStreamArgs<K> ma;
     ma.e_chrom = exp.chrom; ma.e_start = exp.start; ma.e_stop = exp.stop; ma.e_bits = exp.coord_bits;
     ma.e_strand = exp.strand; ma.e_sample = exp.sample; ma.n_exp = n_exp; ma.n_exp_samples = n_rs;
@@ -633,6 +736,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(h_bad != 2, GMQL_ERR_INVALID, "the same (ref sample, exp sample) pair is listed twice");
+  GMQL_REQUIRE(h_bad != 3, GMQL_ERR_INVALID, "the sample column does not match sample_offsets (rows must be grouped by sample in offset order)");
   GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "region with chromosome/sample index out of range, negative start, reference region beyond its chrom_span_hint, or reference rows not in the promised (chrom, start) order");
 
   res->rows = n_rows;

@@ -82,9 +82,12 @@ typedef struct {
                                    GenometricJoin.scala:134-136) whose value equality only the host can decide. */
   /* optional narrow encodings (fewer bytes over PCIe); zero / NULL = not used */
   int32_t chrom_bits;           /* 0 or 32: chrom is int32_t[]; 8: uint8_t[]; 16: uint16_t[] (n_chrom must fit) */
-  const int64_t* sample_offsets;/* HOST array [n_samples+1], used when sample == NULL: rows [off[s], off[s+1]) belong to
-                                   sample s (regions arrive one sample file after the other, Loaders.scala:203-208);
-                                   off[0] = 0, off[n_samples] = n, non-decreasing */
+  const int64_t* sample_offsets;/* HOST array [n_samples+1] or NULL: rows [off[s], off[s+1]) belong to sample s (regions
+                                   arrive one sample file after the other, Loaders.scala:203-208); off[0] = 0,
+                                   off[n_samples] = n, non-decreasing.  With sample == NULL it defines the sample of
+                                   every row; next to a sample column it is a promise about that column's layout
+                                   (checked on the device where it is relied upon: gmql_map's per-sample COUNT kernel).
+                                   Views returned by gmql_dataset_upload carry it when the upload had it. */
   const int64_t* chrom_span_hint;/* HOST array [n_chrom] or NULL: an upper bound of `stop` per chromosome (e.g. the
                                    assembly's chromosome sizes).  Lets gmql_map / gmql_join lay out the linear coordinate
                                    without a pass over the data and a host round trip; a region beyond its bound is an

@@ -128,3 +128,83 @@ def test_one_launch_index_equals_separate_index_kernels(ex, n_ref):
         assert rc == 0
         assert ("k_map_index_small" in buf.value.decode()) == (mode == "fused")
     assert np.array_equal(got["fused"], want) and np.array_equal(got["split"], want)
+
+
+def _profile(ex, fn):
+    ex.lib.gmql_ctx_set_profiling(ex.ctx, 1)
+    try:
+        out = fn()
+    finally:
+        buf = C.create_string_buffer(1 << 16)
+        ex.lib.gmql_ctx_profile_report(ex.ctx, buf, len(buf))
+        ex.lib.gmql_ctx_set_profiling(ex.ctx, 0)
+    return out, buf.value.decode()
+
+
+@pytest.mark.parametrize("n_ref,presorted", [(1, False), (700, False), (9000, True), (14000, True)])
+def test_grouped_count_kernel_equals_streaming_kernel(ex, n_ref, presorted):
+    """COUNT onto a small single-sample reference with the experiment rows grouped by sample runs in k_map_count_grouped
+    (everything random-access in shared memory); same counts as the streaming kernel.  14 000 reference regions do not
+    fit shared memory: the streaming kernel runs.  Sample 2 is in no pair, sample 3 is empty."""
+    import os
+    from gmql_b200 import RegionDataset, _lib as L
+    rng = np.random.Generator(np.random.PCG64(100 + n_ref))
+    span = 3_000_000
+    names = ["chr1", "chr2", "chrX"]
+    chrom = rng.integers(0, 3, n_ref).astype(np.int32)
+    start = rng.integers(0, span, n_ref)
+    ln = rng.integers(0, 900, n_ref)
+    ln[rng.random(n_ref) < 0.02] = 500_000
+    if presorted:
+        o = np.lexsort((start, chrom))
+        chrom, start, ln = chrom[o], start[o], ln[o]
+    dr = RegionDataset(names, chrom, start, start + ln, rng.integers(0, 3, n_ref).astype(np.int8), np.zeros(n_ref, np.int32), np.array([5], np.int64))
+    sizes = [30000, 1, 20000, 0, 60000]
+    smp = np.repeat(np.arange(5), sizes).astype(np.int32)
+    n_exp = smp.shape[0]
+    ec = rng.integers(0, 3, n_exp).astype(np.int32)
+    es = rng.integers(0, span + 600_000, n_exp)
+    de = RegionDataset(names, ec, es, es + rng.integers(0, 2500, n_exp), rng.integers(0, 3, n_exp).astype(np.int8), smp, np.arange(10, 15, dtype=np.int64))
+    pairs = (L.Pair * 4)()
+    for k, b in enumerate((0, 1, 3, 4)):
+        pairs[k].left_sample, pairs[k].right_sample = 0, b
+
+    def counts(c_ref, c_exp):
+        out = C.c_void_p()
+        rc = ex.lib.gmql_map(ex.ctx, C.byref(c_ref), C.byref(c_exp), pairs, 4, (L.Agg * 1)(), 0, C.byref(out))
+        if rc != 0:
+            return rc, ex.lib.gmql_last_error(ex.ctx)
+        a = np.empty(int(ex.lib.gmql_result_column_len(out, L.COL_MAP_COUNT)), np.int32)
+        ex._check(ex.lib.gmql_result_column_copy(ex.ctx, out, L.COL_MAP_COUNT, a.ctypes.data))
+        ex.lib.gmql_result_free(ex.ctx, out)
+        return 0, a
+
+    c_ref, k0 = dr.as_c(sorted_by_position=presorted)
+    c_plain, k1 = de.as_c()
+    (rc, want), kern = _profile(ex, lambda: counts(c_ref, c_plain))
+    assert rc == 0 and want.shape[0] == 4 * n_ref and "k_map_count_grouped" not in kern
+    if n_ref > 1:
+        assert want.sum() > 0
+    c_grp, k2 = de.as_c(narrow=True)
+    assert c_grp.sample_offsets and not c_grp.sample
+    (rc, got), kern = _profile(ex, lambda: counts(c_ref, c_grp))
+    assert rc == 0 and np.array_equal(got, want)
+    assert ("k_map_count_grouped" in kern) == (n_ref <= 12000), kern
+    os.environ["GMQL_MAP_GROUPED"] = "0"
+    try:
+        (rc, got), kern = _profile(ex, lambda: counts(c_ref, c_grp))
+    finally:
+        os.environ.pop("GMQL_MAP_GROUPED", None)
+    assert rc == 0 and np.array_equal(got, want) and "k_map_count_grouped" not in kern
+    # a sample column that contradicts the offsets is an error, never a wrong result
+    c_bad, k3 = de.as_c()
+    off = np.array([0, 30000, 30001, 50001, 50001, n_exp], np.int64)
+    off_bad = off.copy()
+    off_bad[1] = 29990
+    c_bad.sample_offsets = off_bad.ctypes.data
+    rc, msg = counts(c_ref, c_bad)
+    if n_ref <= 12000:
+        assert rc < 0 and b"sample_offsets" in msg
+    c_bad.sample_offsets = off.ctypes.data                 # consistent offsets next to the column: fine
+    rc, got = counts(c_ref, c_bad)
+    assert rc == 0 and np.array_equal(got, want)
