@@ -36,6 +36,9 @@ struct gmql_ctx {
   std::vector<std::pair<void*, size_t>> pins;
   size_t pin_next = 0;
   bool pending = false;   // a kernel has been launched since the last stream synchronisation
+  // (sample column, sample_offsets) pairs of the views handed out by gmql_dataset_upload: the column was expanded from those
+  // very offsets on the device, so the layout promise needs no re-check when such a view comes back
+  std::vector<std::pair<const void*, const void*>> trusted_groupings;
 };
 
 // pinned host memory valid until the next API call on this context
@@ -167,6 +170,7 @@ struct DevRegions {
   bool sorted_hint = false;            // rows ordered by (chrom, start) according to the caller (verified on the device)
   const int64_t* sample_off = nullptr; // device [n_samples + 1] when the rows are grouped by sample (sample_offsets given), else null
   int64_t max_sample_rows = 0;         // largest sample (rows), valid with sample_off
+  bool sample_trusted = false;         // the sample column is known to match sample_off (expanded from it by this library)
 };
 
 // upload (or adopt) a gmql_regions; only the value columns listed in need_cols are moved

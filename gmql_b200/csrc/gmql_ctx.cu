@@ -183,7 +183,9 @@ void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector
     if (r->location != GMQL_LOC_DEVICE) out->h2d_bytes += (int64_t)ob;
     out->sample_off = (const int64_t*)doff.p;
     out->max_sample_rows = widest;
+    for (const auto& tg : ctx->trusted_groupings) if (tg.first == (const void*)r->sample && tg.second == (const void*)r->sample_offsets && r->sample) out->sample_trusted = true;
     if (!r->sample) {
+      out->sample_trusted = true;
       DevBuf<uint8_t> smp(ctx, (int64_t)(n * 4 ? n * 4 : 1));
       if (n) LAUNCH(ctx, k_expand_sample_offsets, (int)std::min<int64_t>(r->n_samples, (int64_t)ctx->num_sms * 16), 256, 0, (const int64_t*)doff.p, r->n_samples, (int32_t*)smp.p);
       out->sample = (const int32_t*)smp.p;
@@ -252,6 +254,7 @@ struct gmql_dataset {
   DevRegions dev;
   std::vector<int64_t> sample_ids;
   std::vector<int64_t> sample_offsets;   // host copy when the upload declared the rows grouped by sample
+  gmql_ctx* owner = nullptr;             // context holding this dataset's trusted-grouping entry
   std::vector<const double*> cols;
   std::vector<const uint8_t*> valid;
 };
@@ -283,6 +286,7 @@ extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql
     if (host->sample_offsets) {
       d->sample_offsets.assign(host->sample_offsets, host->sample_offsets + host->n_samples + 1);
       view->sample_offsets = d->sample_offsets.data();   // the view keeps the promise: rows grouped by sample
+      if (d->dev.sample_trusted) { ctx->trusted_groupings.push_back(std::make_pair((const void*)d->dev.sample, (const void*)d->sample_offsets.data())); d->owner = ctx; }
     }
     view->n_chrom = d->dev.n_chrom;
     view->n_samples = d->dev.n_samples;
@@ -304,6 +308,11 @@ extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql
 
 extern "C" void gmql_dataset_free(gmql_ctx* ctx, gmql_dataset* d) {
   (void)ctx;
+  if (d && d->owner) {
+    auto& tg = d->owner->trusted_groupings;
+    for (size_t k = 0; k < tg.size(); ++k)
+      if (tg[k].first == (const void*)d->dev.sample && tg[k].second == (const void*)d->sample_offsets.data()) { tg.erase(tg.begin() + (long)k); break; }
+  }
   delete d;  // DevBuf destructors release on the owning context's stream
 }
 

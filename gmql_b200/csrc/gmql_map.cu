@@ -387,62 +387,95 @@ struct MapGroupedArgs {
   int* count;
 };
 
+
+// B32: 32-bit experiment coordinates (the usual case): the whole row pipeline runs on 32-bit registers, the chromosome's
+// {offset, span} pair is one 8-byte shared-memory load, and the rows of the NEXT iteration are already in flight while
+// the current ones are matched.
+template <bool B32>
 __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_grouped(MapGroupedArgs a) {
   extern __shared__ __align__(16) uint32_t g_dyn[];
   uint4* s_ref = (uint4*)g_dyn;                                   // [n_ref]
   uint32_t* s_cnt = g_dyn + 4 * (size_t)a.n_ref;                  // [(n_ref + 1) / 2] two 16-bit counters per word
   const int n_cw = (a.n_ref + 1) >> 1;
   uint32_t* s_tbl = s_cnt + ((n_cw + 3) & ~3);                    // [n_tbl]
-  uint64_t* s_coff = (uint64_t*)(s_tbl + ((a.n_tbl + 3) & ~3));   // [n_chrom] offsets, then spans
-  int64_t* s_span = (int64_t*)(s_coff + a.lm.n_chrom);
+  uint2* s_cs = (uint2*)(s_tbl + ((a.n_tbl + 3) & ~3));           // [n_chrom] {linear offset, span} (32-bit keys: both < 2^32)
   for (int k = threadIdx.x; k < a.n_ref; k += MS_THREADS) {
     const RefEntry<uint32_t> e = a.entries[k];
     s_ref[k] = make_uint4(a.r_start[k], e.stop, e.pmax_prev, (e.rank << 2) | (e.meta & 3u));
   }
   for (int k = threadIdx.x; k < a.n_tbl; k += MS_THREADS) s_tbl[k] = a.tbl[k];
-  for (int k = threadIdx.x; k < a.lm.n_chrom; k += MS_THREADS) { s_coff[k] = a.lm.coff[k]; s_span[k] = a.lm.span[k]; }
+  for (int k = threadIdx.x; k < a.lm.n_chrom; k += MS_THREADS) s_cs[k] = make_uint2((uint32_t)a.lm.coff[k], (uint32_t)a.lm.span[k]);
+  const int32_t* e_start32 = (const int32_t*)a.e_start; const int32_t* e_stop32 = (const int32_t*)a.e_stop;
+
+  // one experiment row against the staged reference; coordinates already validated against 32-bit overflow by the caller
+  auto match = [&](int c, int64_t s, int64_t e, int st) {
+    if (c < 0 || c >= a.lm.n_chrom) { *a.bad = 1; return; }
+    const uint2 cs = s_cs[c];
+    const int64_t sp = (int64_t)cs.y;
+    if (s >= sp || e <= 0) return;                                // no reference region can satisfy r.start < e.stop && e.start < r.stop
+    if (s < 0) { *a.bad = 1; return; }
+    if (e > sp + 1) e = sp + 1;
+    const uint32_t ls = cs.x + (uint32_t)s, le = cs.x + (uint32_t)e;
+    const uint32_t b = le >> a.tbl_shift;
+    int k = (int)s_tbl[b];
+    const int hi2 = (int)s_tbl[b + 1];
+    if (hi2 - k > 4) { int lo2 = k, h2 = hi2; while (lo2 < h2) { const int mid = (lo2 + h2) >> 1; if (s_ref[mid].x < le) lo2 = mid + 1; else h2 = mid; } k = lo2; }
+    else while (k < hi2 && s_ref[k].x < le) ++k;                  // buckets usually hold no or one reference start
+    --k;                                                          // last reference region with start < row.stop
+    while (k >= 0) {
+      const uint4 r = s_ref[k];
+      if (r.y > ls && strand_ok((int)(r.w & 3u), st)) {
+        const uint32_t rank = r.w >> 2;
+        atomicAdd(&s_cnt[rank >> 1], 1u << ((rank & 1u) << 4));
+      }
+      if (r.z <= ls) break;
+      --k;
+    }
+  };
+
   for (int smp = blockIdx.x; smp < a.n_exp_samples; smp += gridDim.x) {
     const long long base = a.pair_base[smp];                      // the only reference sample is sample 0
     if (base < 0) continue;                                       // this experiment sample is in no pair (block-uniform)
     for (int k = threadIdx.x; k < n_cw; k += MS_THREADS) s_cnt[k] = 0;
     __syncthreads();                                              // also orders the staging above
     const int64_t lo = a.sample_off[smp], hi = a.sample_off[smp + 1];
-    for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += (int64_t)MS_THREADS * MS_PER) {
-      int c[MS_PER], st[MS_PER], sm[MS_PER];
-      int64_t s[MS_PER], e[MS_PER];
+    if (B32) {
+      int c[MS_PER], s[MS_PER], e[MS_PER], sm[MS_PER];            // the rows of the iteration being matched
+      int nc[MS_PER], ns[MS_PER], ne[MS_PER], nsm[MS_PER];        // ... and of the next one, in flight
+      auto fetch = [&](int64_t i0, int* fc, int* fs, int* fe, int* fsm) {
 #pragma unroll
-      for (int j = 0; j < MS_PER; ++j) {                          // coalesced 32-bit loads, four rows in flight per thread
-        const int64_t i = i0 + (int64_t)j * MS_THREADS;
-        const bool ok = i < hi;
-        c[j] = ok ? a.e_chrom[i] : -2;                            // -2: padding lane
-        s[j] = ok ? ld_coord(a.e_start, a.e_bits, i) : 0;
-        e[j] = ok ? ld_coord(a.e_stop, a.e_bits, i) : 0;
-        st[j] = ok && a.e_strand ? (int)a.e_strand[i] : 0;
-        sm[j] = ok && a.e_sample ? a.e_sample[i] : smp;
+        for (int j = 0; j < MS_PER; ++j) {                        // coalesced 32-bit loads; nothing here waits for them
+          const int64_t i = i0 + (int64_t)j * MS_THREADS;
+          const bool ok = i < hi;
+          fc[j] = ok ? a.e_chrom[i] : -2;                         // -2: padding lane
+          fs[j] = ok ? e_start32[i] : 0;
+          fe[j] = ok ? e_stop32[i] : 0;
+          fsm[j] = ok && a.e_sample ? a.e_sample[i] : smp;
+        }
+      };
+      int64_t i0 = lo + threadIdx.x;
+      if (i0 < hi) fetch(i0, nc, ns, ne, nsm);
+      for (; i0 < hi; i0 += (int64_t)MS_THREADS * MS_PER) {
+#pragma unroll
+        for (int j = 0; j < MS_PER; ++j) { c[j] = nc[j]; s[j] = ns[j]; e[j] = ne[j]; sm[j] = nsm[j]; }
+        const int64_t i1 = i0 + (int64_t)MS_THREADS * MS_PER;
+        if (i1 < hi) fetch(i1, nc, ns, ne, nsm);
+#pragma unroll
+        for (int j = 0; j < MS_PER; ++j) {
+          if (c[j] == -2) continue;
+          if (sm[j] != smp) { *a.bad = 3; continue; }             // the rows are not grouped as sample_offsets promised
+          const int st = a.e_strand ? (int)a.e_strand[i0 + (int64_t)j * MS_THREADS] : 0;
+          match(c[j], (int64_t)s[j], (int64_t)e[j], st);
+        }
       }
+    } else {
+      for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += (int64_t)MS_THREADS * MS_PER) {
 #pragma unroll
-      for (int j = 0; j < MS_PER; ++j) {
-        if (c[j] == -2) continue;
-        if (sm[j] != smp) { *a.bad = 3; continue; }               // the rows are not grouped as sample_offsets promised
-        if (c[j] < 0 || c[j] >= a.lm.n_chrom) { *a.bad = 1; continue; }
-        const int64_t sp = s_span[c[j]];
-        if (s[j] >= sp || e[j] <= 0) continue;                    // no reference region can satisfy r.start < e.stop && e.start < r.stop
-        if (s[j] < 0) { *a.bad = 1; continue; }
-        if (e[j] > sp + 1) e[j] = sp + 1;
-        const uint64_t co = s_coff[c[j]];
-        const uint32_t ls = (uint32_t)(co + (uint64_t)s[j]), le = (uint32_t)(co + (uint64_t)e[j]);
-        const uint32_t b = le >> a.tbl_shift;
-        int lo2 = (int)s_tbl[b], hi2 = (int)s_tbl[b + 1];
-        while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (s_ref[mid].x < le) lo2 = mid + 1; else hi2 = mid; }
-        int k = lo2 - 1;                                          // last reference region with start < region.stop
-        while (k >= 0) {
-          const uint4 r = s_ref[k];
-          if (r.y > ls && strand_ok((int)(r.w & 3u), st[j])) {
-            const uint32_t rank = r.w >> 2;
-            atomicAdd(&s_cnt[rank >> 1], 1u << ((rank & 1u) << 4));
-          }
-          if (r.z <= ls) break;
-          --k;
+        for (int j = 0; j < MS_PER; ++j) {
+          const int64_t i = i0 + (int64_t)j * MS_THREADS;
+          if (i >= hi) continue;
+          if (a.e_sample && a.e_sample[i] != smp) { *a.bad = 3; continue; }
+          match(a.e_chrom[i], ((const int64_t*)a.e_start)[i], ((const int64_t*)a.e_stop)[i], a.e_strand ? (int)a.e_strand[i] : 0);
         }
       }
     }
@@ -627,7 +660,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   int tbl_shift = 0;
   // COUNT onto a small single-sample reference with the experiment rows grouped by sample: k_map_count_grouped
   const char* mg_env = getenv("GMQL_MAP_GROUPED");         // "0": test hook
-  const int64_t mg_fixed = 16 * n_ref + 4 * (((n_ref + 1) / 2 + 3) & ~(int64_t)3) + 16 * (int64_t)lm.n_chrom;
+  const int64_t mg_fixed = 16 * n_ref + 4 * (((n_ref + 1) / 2 + 3) & ~(int64_t)3) + 8 * (int64_t)lm.n_chrom;
   const int64_t mg_tbl = (MG_SMEM - mg_fixed) / 4 - 8;
   const bool grouped = single && sizeof(K) == 4 && plan.n_cols == 0 && !plan.need_bag && exp.sample_off != nullptr && exp.max_sample_rows <= 65535 &&
                        n_ref > 0 && n_exp > 0 && n_pairs > 0 && mg_tbl >= 2048 && !(mg_env && mg_env[0] == '0');
@@ -673,14 +706,20 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   if (grouped) {
     MapGroupedArgs ga;
     ga.e_chrom = exp.chrom; ga.e_start = exp.start; ga.e_stop = exp.stop; ga.e_bits = exp.coord_bits;
-    ga.e_strand = exp.strand; ga.e_sample = exp.sample; ga.sample_off = exp.sample_off; ga.n_exp_samples = n_rs;
+    ga.e_strand = exp.strand; ga.e_sample = exp.sample_trusted ? (const int32_t*)nullptr : exp.sample; ga.sample_off = exp.sample_off; ga.n_exp_samples = n_rs;
     ga.lm = lm; ga.r_start = (const uint32_t*)ix.start; ga.entries = (const RefEntry<uint32_t>*)entries.p; ga.n_ref = (int)n_ref;
     ga.pair_base = pair_base.p; ga.bad = bad.p;
     ga.tbl = tbl.p; ga.tbl_shift = tbl_shift; ga.n_tbl = (int)(n_buckets + 2);
     ga.count = count.p;
     const size_t sh = (size_t)mg_fixed + 4 * (size_t)((ga.n_tbl + 3) & ~3);
-    CUDA_TRY(cudaFuncSetAttribute(k_map_count_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    LAUNCH(ctx, k_map_count_grouped, (int)std::min<int64_t>(n_rs, (int64_t)ctx->num_sms), MS_THREADS, sh, ga);
+    const int mg_grid = (int)std::min<int64_t>(n_rs, (int64_t)ctx->num_sms);
+    if (exp.coord_bits == 32) {
+      CUDA_TRY(cudaFuncSetAttribute(k_map_count_grouped<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      LAUNCH(ctx, k_map_count_grouped<true>, mg_grid, MS_THREADS, sh, ga);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(k_map_count_grouped<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      LAUNCH(ctx, k_map_count_grouped<false>, mg_grid, MS_THREADS, sh, ga);
+    }
   } else if (n_exp && n_ref && n_rows) {
     MapStreamArgs<K> ma;
     ma.e_chrom = exp.chrom; ma.e_start = exp.start; ma.e_stop = exp.stop; ma.e_bits = exp.coord_bits;
