@@ -663,7 +663,8 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   const int64_t mg_fixed = 16 * n_ref + 4 * (((n_ref + 1) / 2 + 3) & ~(int64_t)3) + 8 * (int64_t)lm.n_chrom;
   const int64_t mg_tbl = (MG_SMEM - mg_fixed) / 4 - 8;
   const bool grouped = single && sizeof(K) == 4 && plan.n_cols == 0 && !plan.need_bag && exp.sample_off != nullptr && exp.max_sample_rows <= 65535 &&
-                       n_ref > 0 && n_exp > 0 && n_pairs > 0 && mg_tbl >= 2048 && !(mg_env && mg_env[0] == '0');
+                       n_ref > 0 && n_exp > 0 && n_pairs > 0 && mg_tbl >= 2048 && !(mg_env && mg_env[0] == '0') &&
+                       (n_rs >= 4 * ctx->num_sms || (mg_env && mg_env[0] == '1'));   // one block per sample at a time: needs many samples to fill the GPU evenly
   {
     int64_t want = std::max<int64_t>(1024, std::min<int64_t>(grouped ? mg_tbl : (int64_t)MS_MAX_TBL - 2, 16 * std::max<int64_t>(n_ref, 1)));
     while (tbl_shift < 62 && (int64_t)(lm.G >> tbl_shift) + 2 > want) ++tbl_shift;

@@ -187,24 +187,25 @@ def test_grouped_count_kernel_equals_streaming_kernel(ex, n_ref, presorted):
         assert want.sum() > 0
     c_grp, k2 = de.as_c(narrow=True)
     assert c_grp.sample_offsets and not c_grp.sample
+    # five samples would not fill the GPU: the kernel is chosen from 4 x SMs samples on; "1" forces it
     (rc, got), kern = _profile(ex, lambda: counts(c_ref, c_grp))
-    assert rc == 0 and np.array_equal(got, want)
-    assert ("k_map_count_grouped" in kern) == (n_ref <= 12000), kern
-    os.environ["GMQL_MAP_GROUPED"] = "0"
+    assert rc == 0 and np.array_equal(got, want) and "k_map_count_grouped" not in kern
+    os.environ["GMQL_MAP_GROUPED"] = "1"
     try:
         (rc, got), kern = _profile(ex, lambda: counts(c_ref, c_grp))
+        assert rc == 0 and np.array_equal(got, want)
+        assert ("k_map_count_grouped" in kern) == (n_ref <= 12000), kern
+        # a sample column that contradicts the offsets is an error, never a wrong result
+        c_bad, k3 = de.as_c()
+        off = np.array([0, 30000, 30001, 50001, 50001, n_exp], np.int64)
+        off_bad = off.copy()
+        off_bad[1] = 29990
+        c_bad.sample_offsets = off_bad.ctypes.data
+        rc, msg = counts(c_ref, c_bad)
+        if n_ref <= 12000:
+            assert rc < 0 and b"sample_offsets" in msg
+        c_bad.sample_offsets = off.ctypes.data             # consistent offsets next to the column: fine
+        rc, got = counts(c_ref, c_bad)
+        assert rc == 0 and np.array_equal(got, want)
     finally:
         os.environ.pop("GMQL_MAP_GROUPED", None)
-    assert rc == 0 and np.array_equal(got, want) and "k_map_count_grouped" not in kern
-    # a sample column that contradicts the offsets is an error, never a wrong result
-    c_bad, k3 = de.as_c()
-    off = np.array([0, 30000, 30001, 50001, 50001, n_exp], np.int64)
-    off_bad = off.copy()
-    off_bad[1] = 29990
-    c_bad.sample_offsets = off_bad.ctypes.data
-    rc, msg = counts(c_ref, c_bad)
-    if n_ref <= 12000:
-        assert rc < 0 and b"sample_offsets" in msg
-    c_bad.sample_offsets = off.ctypes.data                 # consistent offsets next to the column: fine
-    rc, got = counts(c_ref, c_bad)
-    assert rc == 0 and np.array_equal(got, want)
