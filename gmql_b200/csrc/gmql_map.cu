@@ -397,13 +397,13 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_grouped(MapGroupedA
   uint4* s_ref = (uint4*)g_dyn;                                   // [n_ref]
   uint32_t* s_cnt = g_dyn + 4 * (size_t)a.n_ref;                  // [(n_ref + 1) / 2] two 16-bit counters per word
   const int n_cw = (a.n_ref + 1) >> 1;
-  uint32_t* s_tbl = s_cnt + ((n_cw + 3) & ~3);                    // [n_tbl]
-  uint2* s_cs = (uint2*)(s_tbl + ((a.n_tbl + 3) & ~3));           // [n_chrom] {linear offset, span} (32-bit keys: both < 2^32)
+  uint16_t* s_tbl = (uint16_t*)(s_cnt + ((n_cw + 3) & ~3));       // [n_tbl] 16-bit entries (n_ref < 65 536): twice the buckets per byte
+  uint2* s_cs = (uint2*)(s_tbl + ((a.n_tbl + 7) & ~7));           // [n_chrom] {linear offset, span} (32-bit keys: both < 2^32)
   for (int k = threadIdx.x; k < a.n_ref; k += MS_THREADS) {
     const RefEntry<uint32_t> e = a.entries[k];
     s_ref[k] = make_uint4(a.r_start[k], e.stop, e.pmax_prev, (e.rank << 2) | (e.meta & 3u));
   }
-  for (int k = threadIdx.x; k < a.n_tbl; k += MS_THREADS) s_tbl[k] = a.tbl[k];
+  for (int k = threadIdx.x; k < a.n_tbl; k += MS_THREADS) s_tbl[k] = (uint16_t)a.tbl[k];
   for (int k = threadIdx.x; k < a.lm.n_chrom; k += MS_THREADS) s_cs[k] = make_uint2((uint32_t)a.lm.coff[k], (uint32_t)a.lm.span[k]);
   const int32_t* e_start32 = (const int32_t*)a.e_start; const int32_t* e_stop32 = (const int32_t*)a.e_stop;
 
@@ -661,12 +661,12 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   // COUNT onto a small single-sample reference with the experiment rows grouped by sample: k_map_count_grouped
   const char* mg_env = getenv("GMQL_MAP_GROUPED");         // "0": test hook
   const int64_t mg_fixed = 16 * n_ref + 4 * (((n_ref + 1) / 2 + 3) & ~(int64_t)3) + 8 * (int64_t)lm.n_chrom;
-  const int64_t mg_tbl = (MG_SMEM - mg_fixed) / 4 - 8;
+  const int64_t mg_tbl = (MG_SMEM - mg_fixed) / 2 - 16;   // 16-bit table entries
   const bool grouped = single && sizeof(K) == 4 && plan.n_cols == 0 && !plan.need_bag && exp.sample_off != nullptr && exp.max_sample_rows <= 65535 &&
-                       n_ref > 0 && n_exp > 0 && n_pairs > 0 && mg_tbl >= 2048 && !(mg_env && mg_env[0] == '0') &&
+                       n_ref > 0 && n_ref < 65536 && n_exp > 0 && n_pairs > 0 && mg_tbl >= 2048 && !(mg_env && mg_env[0] == '0') &&
                        (n_rs >= 4 * ctx->num_sms || (mg_env && mg_env[0] == '1'));   // one block per sample at a time: needs many samples to fill the GPU evenly
   {
-    int64_t want = std::max<int64_t>(1024, std::min<int64_t>(grouped ? mg_tbl : (int64_t)MS_MAX_TBL - 2, 16 * std::max<int64_t>(n_ref, 1)));
+    int64_t want = std::max<int64_t>(1024, std::min<int64_t>(grouped ? mg_tbl : (int64_t)MS_MAX_TBL - 2, (grouped ? 64 : 16) * std::max<int64_t>(n_ref, 1)));
     while (tbl_shift < 62 && (int64_t)(lm.G >> tbl_shift) + 2 > want) ++tbl_shift;
   }
   int64_t n_buckets = (int64_t)(lm.G >> tbl_shift) + 1;
@@ -712,7 +712,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     ga.pair_base = pair_base.p; ga.bad = bad.p;
     ga.tbl = tbl.p; ga.tbl_shift = tbl_shift; ga.n_tbl = (int)(n_buckets + 2);
     ga.count = count.p;
-    const size_t sh = (size_t)mg_fixed + 4 * (size_t)((ga.n_tbl + 3) & ~3);
+    const size_t sh = (size_t)mg_fixed + 2 * (size_t)((ga.n_tbl + 7) & ~7);
     const int mg_grid = (int)std::min<int64_t>(n_rs, (int64_t)ctx->num_sms);
     if (exp.coord_bits == 32) {
       CUDA_TRY(cudaFuncSetAttribute(k_map_count_grouped<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
