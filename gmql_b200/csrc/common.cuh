@@ -194,6 +194,7 @@ struct gmql_result {
   void* view_acc_double = nullptr;
   std::vector<int64_t> span_hint;    // cover results: upper bound of stop per chromosome (host)
   bool sorted = false;               // cover results: rows ordered by (chrom, start) (single class)
+  bool unified = false;              // cover results: strands unified, every row '*'
 };
 template <typename T>
 static inline void result_add(gmql_result* r, int id, DevBuf<T>& b) {

@@ -1509,6 +1509,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   res->rows = n_out;
   res->kind = 2;
   res->sorted = n_classes_total == 1;     // one (group, strand) class: the rows are in (chrom, start) order
+  res->unified = cfg.unified != 0;
   res->n_chrom = in.n_chrom;
   res->group_ids.resize((size_t)n_groups);
   for (int gi = 0; gi < n_groups; ++gi) res->group_ids[gi] = gi;
@@ -1694,7 +1695,7 @@ extern "C" int gmql_result_as_regions(gmql_ctx* ctx, gmql_result* r, gmql_region
     view->chrom = (const int32_t*)r->cols[GMQL_COL_COV_CHROM].p;
     view->start = r->cols[GMQL_COL_COV_START].p;
     view->stop = r->cols[GMQL_COL_COV_STOP].p;
-    view->strand = (const int8_t*)r->cols[GMQL_COL_COV_STRAND].p;
+    view->strand = r->unified ? (const int8_t*)nullptr : (const int8_t*)r->cols[GMQL_COL_COV_STRAND].p;   // every row '*': same as no strand column
     view->sample = (const int32_t*)r->cols[GMQL_COL_COV_GROUP].p;
     view->n_chrom = r->n_chrom;
     view->n_samples = (int32_t)r->group_ids.size();

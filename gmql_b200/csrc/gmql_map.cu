@@ -385,6 +385,7 @@ struct MapGroupedArgs {
   const long long* pair_base; int* bad;
   const uint32_t* tbl; int tbl_shift; int n_tbl;
   int* count;
+  int compact;   // every entry's rank is its index and the reference has no strand column: no rank|strand array in shared memory
 };
 
 
@@ -394,14 +395,19 @@ struct MapGroupedArgs {
 template <bool B32>
 __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_grouped(MapGroupedArgs a) {
   extern __shared__ __align__(16) uint32_t g_dyn[];
-  uint4* s_ref = (uint4*)g_dyn;                                   // [n_ref]
-  uint32_t* s_cnt = g_dyn + 4 * (size_t)a.n_ref;                  // [(n_ref + 1) / 2] two 16-bit counters per word
+  // the reference as a structure of arrays: the in-bucket scan walks consecutive 4-byte starts
+  uint32_t* s_start = g_dyn;                                      // [n_ref]
+  uint32_t* s_stop = s_start + a.n_ref;                           // [n_ref]
+  uint32_t* s_pmax = s_stop + a.n_ref;                            // [n_ref] running max of the EARLIER stops
+  uint32_t* s_rs = s_pmax + a.n_ref;                              // [n_ref] rank << 2 | strand, absent when a.compact
+  uint32_t* s_cnt = s_rs + (a.compact ? 0 : a.n_ref);             // [(n_ref + 1) / 2] two 16-bit counters per word
   const int n_cw = (a.n_ref + 1) >> 1;
-  uint16_t* s_tbl = (uint16_t*)(s_cnt + ((n_cw + 3) & ~3));       // [n_tbl] 16-bit entries (n_ref < 65 536): twice the buckets per byte
-  uint2* s_cs = (uint2*)(s_tbl + ((a.n_tbl + 7) & ~7));           // [n_chrom] {linear offset, span} (32-bit keys: both < 2^32)
+  uint16_t* s_tbl = (uint16_t*)(s_cnt + n_cw);                    // [n_tbl] 16-bit entries (n_ref < 65 536): twice the buckets per byte
+  uint2* s_cs = (uint2*)(g_dyn + (((a.compact ? 3 : 4) * (size_t)a.n_ref + n_cw + (((size_t)a.n_tbl + 1) >> 1) + 1) & ~(size_t)1));   // [n_chrom] {linear offset, span}
   for (int k = threadIdx.x; k < a.n_ref; k += MS_THREADS) {
     const RefEntry<uint32_t> e = a.entries[k];
-    s_ref[k] = make_uint4(a.r_start[k], e.stop, e.pmax_prev, (e.rank << 2) | (e.meta & 3u));
+    s_start[k] = a.r_start[k]; s_stop[k] = e.stop; s_pmax[k] = e.pmax_prev;
+    if (!a.compact) s_rs[k] = (e.rank << 2) | (e.meta & 3u);
   }
   for (int k = threadIdx.x; k < a.n_tbl; k += MS_THREADS) s_tbl[k] = (uint16_t)a.tbl[k];
   for (int k = threadIdx.x; k < a.lm.n_chrom; k += MS_THREADS) s_cs[k] = make_uint2((uint32_t)a.lm.coff[k], (uint32_t)a.lm.span[k]);
@@ -419,16 +425,18 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_grouped(MapGroupedA
     const uint32_t b = le >> a.tbl_shift;
     int k = (int)s_tbl[b];
     const int hi2 = (int)s_tbl[b + 1];
-    if (hi2 - k > 4) { int lo2 = k, h2 = hi2; while (lo2 < h2) { const int mid = (lo2 + h2) >> 1; if (s_ref[mid].x < le) lo2 = mid + 1; else h2 = mid; } k = lo2; }
-    else while (k < hi2 && s_ref[k].x < le) ++k;                  // buckets usually hold no or one reference start
+    if (hi2 - k > 4) { int lo2 = k, h2 = hi2; while (lo2 < h2) { const int mid = (lo2 + h2) >> 1; if (s_start[mid] < le) lo2 = mid + 1; else h2 = mid; } k = lo2; }
+    else while (k < hi2 && s_start[k] < le) ++k;                  // buckets usually hold no or one reference start
     --k;                                                          // last reference region with start < row.stop
     while (k >= 0) {
-      const uint4 r = s_ref[k];
-      if (r.y > ls && strand_ok((int)(r.w & 3u), st)) {
-        const uint32_t rank = r.w >> 2;
-        atomicAdd(&s_cnt[rank >> 1], 1u << ((rank & 1u) << 4));
+      if (s_stop[k] > ls) {
+        const uint32_t rs = a.compact ? ((uint32_t)k << 2) : s_rs[k];
+        if (strand_ok((int)(rs & 3u), st)) {
+          const uint32_t rank = rs >> 2;
+          atomicAdd(&s_cnt[rank >> 1], 1u << ((rank & 1u) << 4));
+        }
       }
-      if (r.z <= ls) break;
+      if (s_pmax[k] <= ls) break;
       --k;
     }
   };
@@ -660,7 +668,8 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   int tbl_shift = 0;
   // COUNT onto a small single-sample reference with the experiment rows grouped by sample: k_map_count_grouped
   const char* mg_env = getenv("GMQL_MAP_GROUPED");         // "0": test hook
-  const int64_t mg_fixed = 16 * n_ref + 4 * (((n_ref + 1) / 2 + 3) & ~(int64_t)3) + 8 * (int64_t)lm.n_chrom;
+  const bool mg_compact = small_index && !ref.dup_of && !ref.strand;   // rank == index, no strand: 12 bytes per reference region
+  const int64_t mg_fixed = (mg_compact ? 12 : 16) * n_ref + 4 * ((n_ref + 1) / 2) + 8 * (int64_t)lm.n_chrom + 16;
   const int64_t mg_tbl = (MG_SMEM - mg_fixed) / 2 - 16;   // 16-bit table entries
   const bool grouped = single && sizeof(K) == 4 && plan.n_cols == 0 && !plan.need_bag && exp.sample_off != nullptr && exp.max_sample_rows <= 65535 &&
                        n_ref > 0 && n_ref < 65536 && n_exp > 0 && n_pairs > 0 && mg_tbl >= 2048 && !(mg_env && mg_env[0] == '0') &&
@@ -712,6 +721,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     ga.pair_base = pair_base.p; ga.bad = bad.p;
     ga.tbl = tbl.p; ga.tbl_shift = tbl_shift; ga.n_tbl = (int)(n_buckets + 2);
     ga.count = count.p;
+    ga.compact = mg_compact ? 1 : 0;
     const size_t sh = (size_t)mg_fixed + 2 * (size_t)((ga.n_tbl + 7) & ~7);
     const int mg_grid = (int)std::min<int64_t>(n_rs, (int64_t)ctx->num_sms);
     if (exp.coord_bits == 32) {
