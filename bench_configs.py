@@ -24,12 +24,15 @@ PROFILE = False
 
 def timed(ex, fn, reps):
     best, out = None, None
+    each = []
     for _ in range(reps):
         if out is not None:
             ex.lib.gmql_result_free(ex.ctx, out)
         out = fn()
         ms = ex.last_device_ms()
+        each.append(round(ms, 2))
         best = ms if best is None else min(best, ms)
+    sys.stderr.write("reps (device ms): %s\n" % each)
     if PROFILE:      # one more run with CUDA events around every launch: per-kernel totals on stderr
         ex.lib.gmql_result_free(ex.ctx, out)
         ex.lib.gmql_ctx_set_profiling(ex.ctx, 1)
