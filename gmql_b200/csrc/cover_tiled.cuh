@@ -29,14 +29,28 @@
 namespace tiled {
 
 constexpr int MAX_LOGW = 16;
-constexpr int THREADS = 512;
+// Four 256-thread blocks per SM (64 registers per thread, 54 KB of shared memory each): a tile costs a fixed number of block-wide
+// scans and barriers, so fewer threads per tile and more independent tiles in flight per SM beat two 512-thread blocks.
+constexpr int THREADS = 256;
+constexpr int CTAS_PER_SM = 4;
 constexpr int NWARPS = THREADS / 32;
 constexpr int MAXWORDS = (1 << MAX_LOGW) / 32;
-constexpr int CAP_EV = 16384;           // distinct event positions per tile
-constexpr int MAXP = 512;               // pieces per tile
+constexpr int CAP_EV = 13312;           // distinct event positions per tile
+constexpr int MAXP = 256;               // pieces per tile
 constexpr int HCAP = 512;               // regions of the previous tile still open at the tile start
+constexpr int MAX_TILE_REGIONS = 32000; // own + open regions of one tile: keeps every 16-bit net change exact
 constexpr uint32_t EXT = 0x80000000u;   // length payload bit: stop' = stop + 1
-constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 4 * CAP_EV + 16 * HCAP + 32 * MAXP;
+constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 2 * CAP_EV + 16 * HCAP + 32 * MAXP;
+
+// net +1 / -1 per distinct position, two 16-bit signed counters per shared-memory word.  Adding +-1 to the low half may borrow
+// from / carry into the high half; the word is always high * 65536 + low (mod 2^32), so decoding the low half as signed and
+// removing it first recovers both exactly as long as every net change fits 16 bits (MAX_TILE_REGIONS).
+__device__ __forceinline__ void delta_add(uint32_t* d, int r, int v) { atomicAdd(&d[r >> 1], (r & 1) ? ((uint32_t)v << 16) : (uint32_t)v); }
+__device__ __forceinline__ int32_t delta_get(const uint32_t* d, int k) {
+  const uint32_t w = d[k >> 1];
+  const int32_t lo = (int32_t)(int16_t)(w & 0xffffu);
+  return (k & 1) ? (int32_t)(int16_t)((w - (uint32_t)lo) >> 16) : lo;
+}
 
 struct Cfg {
   int n_groups, n_classes;
@@ -403,7 +417,7 @@ struct RankPos {
   }
 };
 
-constexpr int RC = 6;   // regions of the tile each thread keeps in registers (the rest are re-read from L1/L2)
+constexpr int RC = 8;   // regions of the tile each thread keeps in registers (the rest are re-read from L1/L2)
 
 // GMAP4 contribution of one region per thread (block-uniform call): find the pieces it overlaps, accumulate with
 // warp-aggregated shared-memory atomics
@@ -443,13 +457,13 @@ __device__ __forceinline__ void gmap4_round(bool valid, uint32_t rs, uint32_t re
 // still open at a tile's end are handed to the next tile through shared memory; only the first tile of a range scans
 // its predecessor's regions in global memory.
 template <bool MULTI>
-static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* __restrict__ P /* .y = start key, .x = length payload */, const uint32_t* __restrict__ offS,
+static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(const uint2* __restrict__ P /* .y = start key, .x = length payload */, const uint32_t* __restrict__ offS,
                                                                   int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, Pieces out) {
   extern __shared__ uint32_t sm[];
   uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
   uint16_t* wpre = (uint16_t*)(bitmap + MAXWORDS);         // [MAXWORDS] set bits before each word
-  int32_t* delta = (int32_t*)(wpre + MAXWORDS);            // [CAP_EV] net +1/-1 per distinct position (by rank)
-  uint32_t* hinS = (uint32_t*)(delta + CAP_EV);            // [HCAP] regions still open at the tile start: start, length payload
+  uint32_t* delta = (uint32_t*)(wpre + MAXWORDS);          // [CAP_EV / 2] net +1/-1 per distinct position (by rank), 16 bits each
+  uint32_t* hinS = delta + CAP_EV / 2;                     // [HCAP] regions still open at the tile start: start, length payload
   uint32_t* hinL = hinS + HCAP;
   uint32_t* houtS = hinL + HCAP;                           // [HCAP] regions still open at the tile end (next tile's hin)
   uint32_t* houtL = houtS + HCAP;
@@ -572,8 +586,8 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
       const int w0 = tid * WPT;
       for (int q = 0; q < WPT; ++q) if (w0 + q < nW) c += __popc(bitmap[w0 + q]);
       int32_t pre = block_excl_scan(c, &total, scratch[0]);
-      if (nh > HCAP || nout > HCAP || total > CAP_EV) {    // uniform across the block
-        if (tid == 0) { *out.fail = total > CAP_EV ? 2 : 4; s_nh = 0; s_nout = 0; }
+      if (nh > HCAP || nout > HCAP || total > CAP_EV || nS > (uint32_t)MAX_TILE_REGIONS) {    // uniform across the block
+        if (tid == 0) { *out.fail = (total > CAP_EV || nS > (uint32_t)MAX_TILE_REGIONS) ? 2 : 4; s_nh = 0; s_nout = 0; }
         nh_carry = -1;
         for (int k = tid; k < nW; k += THREADS) bitmap[k] = 0;   // every popcount above happened before the scan's barrier
         __syncthreads();
@@ -582,25 +596,25 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
       if (tid == 0) { s_nh = nout; s_nout = 0; }           // every thread has read both (before the scan's barrier)
       for (int q = 0; q < WPT; ++q) if (w0 + q < nW) { wpre[w0 + q] = (uint16_t)pre; pre += __popc(bitmap[w0 + q]); }
     }
-    for (int k = tid; k < total; k += THREADS) delta[k] = 0;
+    for (int k = tid; k < ((total + 1) >> 1); k += THREADS) delta[k] = 0;
     __syncthreads();
     // ---- phase 3: sum +1 / -1 per distinct position
     for (int k = tid; k < nh; k += THREADS) {
       uint32_t lp = hinL[k];
       uint32_t q = hinS[k] + (lp & ~EXT) + (lp >> 31) - tile_lo;
       int r = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
-      atomicAdd(&delta[r], -1);
+      delta_add(delta, r, -1);
     }
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
       if (s0 + tid + r * THREADS < s1) {
         uint32_t q = rsr[r] - tile_lo;
         int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
-        atomicAdd(&delta[rk], 1);
+        delta_add(delta, rk, 1);
         uint32_t qe = q + (lpr[r] & ~EXT) + (lpr[r] >> 31);
         if (qe < W) {
           int r2 = wpre[qe >> 5] + __popc(bitmap[qe >> 5] & ((1u << (qe & 31)) - 1u));
-          atomicAdd(&delta[r2], -1);
+          delta_add(delta, r2, -1);
         }
       }
     }
@@ -608,11 +622,11 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
       const uint2 pr = P[i]; uint32_t rs = pr.y, lp = pr.x;
       uint32_t q = rs - tile_lo;
       int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
-      atomicAdd(&delta[rk], 1);
+      delta_add(delta, rk, 1);
       uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
       if (qe < W) {
         int r2 = wpre[qe >> 5] + __popc(bitmap[qe >> 5] & ((1u << (qe & 31)) - 1u));
-        atomicAdd(&delta[r2], -1);
+        delta_add(delta, r2, -1);
       }
     }
     __syncthreads();
@@ -623,7 +637,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
     const int k1 = k0 + IT < total ? k0 + IT : total;
     // per-thread chunk: net change and the range of the running depth relative to the chunk start
     int32_t csum = 0, rmin = 0x7fffffff, rmax = -0x7fffffff;
-    for (int k = k0; k < k1; ++k) { csum += delta[k]; rmin = min(rmin, csum); rmax = max(rmax, csum); }
+    for (int k = k0; k < k1; ++k) { csum += delta_get(delta, k); rmin = min(rmin, csum); rmax = max(rmax, csum); }
     int32_t tile_net;
     const int32_t d_start = depth_in + block_excl_scan(csum, &tile_net, scratch[1]);
     // the state just before my first rank: in range iff the depth there is (the previous position belongs to the same
@@ -648,7 +662,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
       bool prev_in = prev0;
       RankPos it = rp;
       for (int k = k0; k < k1; ++k) {
-        d += delta[k];
+        d += delta_get(delta, k);
         bool cur = in_rng<MULTI>(cfg, mn0, mx0, d, (uint64_t)tile_lo + (MULTI ? it.next() : 0u));
         nopen += (cur && !prev_in) ? 1 : 0;
         prev_in = cur;
@@ -683,7 +697,7 @@ static __global__ void __launch_bounds__(THREADS, 2) k_cover_tile(const uint2* _
         int32_t run_max = 0;
         if (!MULTI) rp.seek(bitmap, wpre, nW, k0);
         for (int k = k0; k < k1; ++k) {
-          d += delta[k];
+          d += delta_get(delta, k);
           uint32_t pos = tile_lo + rp.next();
           bool cin = in_rng<MULTI>(cfg, mn0, mx0, d, pos);
           if (cin) {
@@ -910,7 +924,7 @@ static __global__ void k_runs_finalize(Runs r, int64_t nr, const int64_t* __rest
 constexpr int STITCH_T = 1024;
 constexpr int STITCH_CL = 8;            // blocks of the cluster (portable maximum)
 constexpr int STITCH_MAX = 1 << 18;     // pieces
-constexpr int STITCH_MAXB = 2048;       // tile-kernel blocks whose offsets fit the shared table
+constexpr int STITCH_MAXB = 4096;       // tile-kernel blocks whose offsets fit the shared table
 
 struct StitchOut {
   int32_t* group; int8_t* strand; int32_t* chrom; int64_t* start; int64_t* stop; int32_t* acc; double* accd; double* j1; double* j2;

@@ -1182,7 +1182,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   // its own segment of the piece tables, so they come out in genome order and nothing has to be sorted.
   // whole waves of the 2 x num_sms resident blocks, about 16 tiles per block (the first tile of every block range re-reads
   // its predecessor's regions), at most four waves
-  const int64_t resident = (int64_t)ctx->num_sms * 2;
+  const int64_t resident = (int64_t)ctx->num_sms * tiled::CTAS_PER_SM;
   int64_t waves = std::max<int64_t>(1, std::min<int64_t>(4, (t_hi - t_lo + resident * 8) / (resident * 16)));
   if (const char* we = getenv("GMQL_COVER_WAVES")) waves = std::max(1, atoi(we));   // tuning hook
   const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), resident * waves));

@@ -171,12 +171,12 @@ def test_tiled_equals_sort_path_at_scale(ex):
 
 
 def test_tiled_pile_up_retries_with_narrower_tiles(ex):
-    """A hotspot (40 000 regions inside 30 kb on top of a dense background) overflows a 65 536-wide tile's tables; the path
+    """A hotspot (15 000 regions inside 30 kb on top of a dense background) overflows a 65 536-wide tile's tables; the path
     retries with narrower tiles instead of leaving the input to the sort-and-merge path, and the rows still equal that path's."""
     from gmql_b200 import synth, N, ANY, RegionDataset, _lib as L
     bg = synth.peak_samples(40, 50000, 7, with_values=())
     rng = np.random.Generator(np.random.PCG64(3))
-    k = 40000
+    k = 15000
     hs = 5_000_000 + rng.integers(0, 30000, k)
     hot = RegionDataset(bg.chrom_names, np.concatenate([bg.chrom, np.zeros(k, np.int32)]), np.concatenate([bg.start, hs]),
                         np.concatenate([bg.stop, hs + rng.integers(50, 400, k)]), np.zeros(bg.n + k, np.int8),
