@@ -18,7 +18,7 @@
 //     tile max(tile(run.start), tile(region.start)) — the reference's own first-bin rule (GMAP4.scala:44-45) at tile
 //     granularity;
 //   * a small stitch pass fuses pieces that touch at tile edges (the reference's boundary merge, :121-152).
-// Work per tile is proportional to its events (plus W/32 bitmap words), not to W.
+// Work per tile is proportional to its events (plus W/32 bitmap words), not to W.  Four 256-thread blocks per SM (54 KB of shared memory each).
 // Preconditions (checked by the caller, which otherwise uses the sort-and-merge path): uint32 keys, COVER or FLAT,
 // no zero-length regions, max region length < W - 2 (value aggregates are a post-pass of the caller over the runs).  Capacity overflows (distinct positions, pieces or
 // halo regions of one tile) raise `fail` and the caller falls back as well.
