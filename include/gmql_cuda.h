@@ -324,7 +324,9 @@ int  gmql_result_column_copy(gmql_ctx* ctx, const gmql_result* r, int32_t col, v
 /* COVER results only: a device-located gmql_regions view (sample = group index, one value column = AccIndex)
  * so that `C = COVER(..) E; M = MAP() C E` chains without a host round trip (the analogue of the reference's
  * per-node memo, GMQLSparkExecutor.scala:252-253).  The small host arrays the view points at (sample_ids, cols)
- * are owned by the result and live until gmql_result_free. */
+ * are owned by the result and live until gmql_result_free.  The view carries chrom_span_hint and, for a single
+ * (group, strand) class, sorted_by_position; when the strands were unified (every row '*') it has no strand column
+ * (strand = NULL means exactly that). */
 int  gmql_result_as_regions(gmql_ctx* ctx, gmql_result* r, gmql_regions* view);
 void gmql_result_free(gmql_ctx* ctx, gmql_result* r);
 
