@@ -168,6 +168,100 @@ static __global__ void __launch_bounds__(1024, 1) k_tile_hist(const int32_t* __r
   for (int k = threadIdx.x; k < n_coarse; k += blockDim.x) coarse_cnt[(size_t)k * gridDim.x + blockIdx.x] = s_coarse[k];
 }
 
+// ---- speculative launch (caller knows the chromosome spans up front: chrom_span_hint) ----------------------------------
+// With the layout of the linear coordinate known before any data is read, gmql_cover does not wait for its prepass: ONE
+// kernel reads the columns once and produces both what the prepass reports (validity / zero-length flags, longest region,
+// observed spans — and "beyond its hint" as a validity error) and the tile histogram, and the rest of the tile pipeline is
+// queued behind it at once.  The kernels that would misbehave on an ineligible input (zero-length regions, a region as
+// long as a tile, invalid rows) look at the flags first and return; the host reads the flags with the pipeline's single
+// synchronisation and, in that rare case, runs the operator again the ordinary way.
+struct Guard { const int* flags; int max_len; };   // flags: [1] zero-length seen, [2] invalid row, [3] longest region; null = no guard
+__device__ __forceinline__ bool guard_trips(const Guard& g) {
+  return g.flags != nullptr && (g.flags[1] != 0 || g.flags[2] != 0 || g.flags[3] >= g.max_len);
+}
+
+static __global__ void __launch_bounds__(1024, 1) k_prepass_hist(const int32_t* __restrict__ chrom, const int32_t* __restrict__ start, const int32_t* __restrict__ stop,
+                                                                  const int32_t* __restrict__ sample, int64_t n, int n_samples, LinMap lm, int logw, int nT,
+                                                                  uint32_t* __restrict__ hist, uint32_t* __restrict__ coarse_cnt, int n_coarse, int vec_ok,
+                                                                  unsigned long long* __restrict__ act_span, int* __restrict__ flags) {
+  extern __shared__ uint32_t sh_hist[];                    // [nT], chromosome offsets, coarse counters, hint spans, observed spans
+  uint64_t* s_coff = (uint64_t*)(sh_hist + ((nT + 1) & ~1));
+  uint32_t* s_coarse = (uint32_t*)(s_coff + lm.n_chrom);
+  uint32_t* s_hint = s_coarse + n_coarse;                  // [n_chrom] upper bound of stop (32-bit coordinates)
+  uint32_t* s_seen = s_hint + lm.n_chrom;                  // [n_chrom] largest stop seen
+  __shared__ int s_fl[4];
+  for (int k = threadIdx.x; k < nT; k += blockDim.x) sh_hist[k] = 0;
+  for (int k = threadIdx.x; k < n_coarse; k += blockDim.x) s_coarse[k] = 0;
+  for (int k = threadIdx.x; k < lm.n_chrom; k += blockDim.x) {
+    s_coff[k] = lm.coff[k]; s_seen[k] = 0;
+    const int64_t h = lm.span[k];
+    s_hint[k] = h > 0x7fffffffLL ? 0x7fffffffu : (uint32_t)h;
+  }
+  if (threadIdx.x < 4) s_fl[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t n_tiles = (n + MSP_TILE - 1) / MSP_TILE;
+  int zero = 0, bad = 0, maxlen = 0;
+  for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += 2 * (int64_t)gridDim.x) {
+    int c[8], st[8], en[8], sm[8];                         // two input tiles in flight, four consecutive regions per thread and tile
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t t = t0 + h * (int64_t)gridDim.x;
+      const int64_t i0 = t * MSP_TILE + (int64_t)threadIdx.x * 4;
+      if (t < n_tiles && vec_ok && i0 + 4 <= n) {
+        const int4 vc = *(const int4*)(chrom + i0), vs = *(const int4*)(start + i0), ve = *(const int4*)(stop + i0);
+        int4 vb = make_int4(0, 0, 0, 0);
+        if (sample) vb = *(const int4*)(sample + i0);
+        c[4 * h] = vc.x; c[4 * h + 1] = vc.y; c[4 * h + 2] = vc.z; c[4 * h + 3] = vc.w;
+        st[4 * h] = vs.x; st[4 * h + 1] = vs.y; st[4 * h + 2] = vs.z; st[4 * h + 3] = vs.w;
+        en[4 * h] = ve.x; en[4 * h + 1] = ve.y; en[4 * h + 2] = ve.z; en[4 * h + 3] = ve.w;
+        sm[4 * h] = vb.x; sm[4 * h + 1] = vb.y; sm[4 * h + 2] = vb.z; sm[4 * h + 3] = vb.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool ok = t < n_tiles && i0 + q < n;
+          c[4 * h + q] = ok ? chrom[i0 + q] : -2;          // -2: padding lane
+          st[4 * h + q] = ok ? start[i0 + q] : 0;
+          en[4 * h + q] = ok ? stop[i0 + q] : 1;
+          sm[4 * h + q] = ok && sample ? sample[i0 + q] : 0;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c[j] == -2) continue;
+      if (st[j] == en[j]) zero = 1;
+      if (c[j] < 0 || c[j] >= lm.n_chrom || st[j] < 0 || st[j] > en[j] || sm[j] < 0 || sm[j] >= n_samples || (uint32_t)en[j] > s_hint[c[j]]) { bad = 1; continue; }
+      maxlen = max(maxlen, en[j] - st[j]);
+      atomicMax(&s_seen[c[j]], (uint32_t)en[j]);
+      const uint32_t key = (uint32_t)s_coff[c[j]] + (uint32_t)st[j];
+      atomicAdd(&sh_hist[key >> logw], 1u);
+    }
+  }
+  {
+    maxlen = __reduce_max_sync(0xffffffffu, maxlen);
+    const bool a1 = __any_sync(0xffffffffu, zero), a2 = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      if (a1) s_fl[1] = 1;
+      if (a2) s_fl[2] = 1;
+      if (maxlen > 0) atomicMax(&s_fl[3], maxlen);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                                  // one store / RED per block and flag (see k_cover_prepass)
+    flags[0] = 1;                                          // no strand column: every region counts as '*'
+    if (s_fl[1]) flags[1] = 1;
+    if (s_fl[2]) flags[2] = 1;
+    if (s_fl[3] > 0) atomicMax(&flags[3], s_fl[3]);
+  }
+  for (int k = threadIdx.x; k < lm.n_chrom; k += blockDim.x) { const uint32_t v = s_seen[k]; if (v) atomicMax(&act_span[k], (unsigned long long)v); }
+  for (int k = threadIdx.x; k < nT; k += blockDim.x) {
+    const uint32_t cnt = sh_hist[k];
+    if (cnt) { atomicAdd(&hist[k], cnt); atomicAdd(&s_coarse[k >> 8], cnt); }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_coarse; k += blockDim.x) coarse_cnt[(size_t)k * gridDim.x + blockIdx.x] = s_coarse[k];
+}
+
 // cursors: every tile starts at its final offset (the coarse cursors are the exclusive scan of k_tile_hist's coarse counts)
 static __global__ void k_init_cursors(const uint32_t* __restrict__ off, int nT, uint32_t* __restrict__ cur_tile) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nT; k += gridDim.x * blockDim.x) cur_tile[k] = off[k];
@@ -214,7 +308,8 @@ constexpr size_t msp_smem_bytes() { return 8 * (size_t)MSP_TILE + (FUSED ? MSP_S
 template <bool FUSED>
 static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint64_t* __restrict__ in, const int32_t* __restrict__ chrom, const void* __restrict__ start,
                                                                       const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls, LinMap lm, int64_t B,
-                                                                      int64_t n, int bin_shift, uint32_t* __restrict__ cursor, uint64_t* __restrict__ out, int vec_ok, int groups) {
+                                                                      int64_t n, int bin_shift, uint32_t* __restrict__ cursor, uint64_t* __restrict__ out, int vec_ok, int groups, Guard guard) {
+  if (guard_trips(guard)) return;
   extern __shared__ __align__(128) unsigned char msp_smem[];
   uint64_t* sdata = (uint64_t*)msp_smem;                                    // [MSP_TILE] regroup buffer
   unsigned char* stage = msp_smem + 8 * (size_t)MSP_TILE;                   // TMA landing buffer
@@ -458,7 +553,8 @@ __device__ __forceinline__ void gmap4_round(bool valid, uint32_t rs, uint32_t re
 // its predecessor's regions in global memory.
 template <bool MULTI>
 static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(const uint2* __restrict__ P /* .y = start key, .x = length payload */, const uint32_t* __restrict__ offS,
-                                                                  int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, Pieces out) {
+                                                                  int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, Pieces out, Guard guard) {
+  if (guard_trips(guard)) return;
   extern __shared__ uint32_t sm[];
   uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
   uint16_t* wpre = (uint16_t*)(bitmap + MAXWORDS);         // [MAXWORDS] set bits before each word
@@ -949,7 +1045,8 @@ __device__ __forceinline__ int32_t stitch_incl_scan(int32_t v, int32_t* total, i
 
 static __global__ void __cluster_dims__(STITCH_CL, 1, 1) __launch_bounds__(STITCH_T, 1)
 k_stitch_small(const uint32_t* __restrict__ blk_cnt, int nb, uint32_t* __restrict__ blk_off, Pieces p, uint32_t* __restrict__ order, int32_t* __restrict__ ridx, Runs r, LinMap lm,
-               int flat, int n_classes, int unified, StitchOut out) {
+               int flat, int n_classes, int unified, StitchOut out, Guard guard) {
+  if (guard_trips(guard)) return;                          // uniform over the cluster
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int cr = (int)cluster.block_rank();

@@ -1126,6 +1126,19 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
 struct ShardSpec { int64_t first_tile, end_tile; };
 struct TiledRuns { DevBuf<uint32_t> rstart, rend; DevBuf<int32_t> cnt; DevBuf<int64_t> head_excl; int64_t np = 0; };   // for the aggregate post-pass
 struct ShardBufs { DevBuf<int32_t> edge, cnt; DevBuf<int64_t> rstart, rstop, smin, emax, smax, emin; };
+// speculative launch of the tile pipeline (cover_tiled.cuh, "speculative launch"): the prepass is fused with the tile histogram
+// and nothing waits for its flags; they come back with the pipeline's one synchronisation
+struct SpecCtx {
+  int* flags = nullptr;                    // device [4]: any '*', zero-length seen, invalid row, longest region (zeroed by the caller)
+  unsigned long long* act_span = nullptr;  // device [n_chrom]: largest stop seen per chromosome (zeroed by the caller)
+  int* h_flags = nullptr;                  // pinned host copies, valid once `synced`
+  unsigned long long* h_span = nullptr;
+  int n_chrom = 0;
+  bool synced = false;                     // the flags have reached the host
+  bool tripped = false;                    // the input was not eligible after all (or invalid): the caller starts over without speculation
+  bool declined = false;                   // the tile path was not chosen at all: nothing has run
+};
+
 // result columns written by the fused stitch kernel (capacity STITCH_MAX; n_out rows are valid)
 struct FusedOut {
   bool ready = false;
@@ -1137,8 +1150,11 @@ struct FusedOut {
 // fall back to the sort-and-merge path
 static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total, int logw,
                             const int32_t* h_mn, const int32_t* h_mx, Phase1Out* p1, DevBuf<int32_t>& keep, DevBuf<int64_t>& fstart, DevBuf<int64_t>& fstop,
-                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs, FusedOut* fo) {
+                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs, FusedOut* fo, SpecCtx* spec) {
   const int64_t n = in.n;
+  tiled::Guard guard;
+  guard.flags = (spec && !spec->synced) ? spec->flags : nullptr;
+  guard.max_len = (int)((1ll << logw) - 2);
   const int key_bits = bits_for(n_classes_total * lm.G);
   const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
   // the tiles this call owns: all of them, or one shard's range (the tile before the range only lends its open regions)
@@ -1157,9 +1173,18 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     hist.zero();
     auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
     const int vec_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(cls) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
-    size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + (lm.n_chrom <= 1024 ? 8 * (size_t)lm.n_chrom : 0) + sizeof(uint32_t) * (size_t)n_coarse;
-    CUDA_TRY(cudaFuncSetAttribute(tiled::k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
-    LAUNCH(ctx, tiled::k_tile_hist, (unsigned)G, 1024, hsh, in.chrom, in.start, in.coord_bits, cls, n, lm, logw, (int)nT, hist.p, coarse_cnt.p, n_coarse, vec_ok);
+    if (guard.flags) {
+      // speculative: the prepass and the histogram in one read of the columns
+      size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + 16 * (size_t)lm.n_chrom + sizeof(uint32_t) * (size_t)n_coarse;
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_prepass_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
+      const int pv_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(in.sample);
+      LAUNCH(ctx, tiled::k_prepass_hist, (unsigned)G, 1024, hsh, in.chrom, (const int32_t*)in.start, (const int32_t*)in.stop, in.sample, n, in.n_samples, lm, logw, (int)nT,
+             hist.p, coarse_cnt.p, n_coarse, pv_ok, spec->act_span, spec->flags);
+    } else {
+      size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + (lm.n_chrom <= 1024 ? 8 * (size_t)lm.n_chrom : 0) + sizeof(uint32_t) * (size_t)n_coarse;
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
+      LAUNCH(ctx, tiled::k_tile_hist, (unsigned)G, 1024, hsh, in.chrom, in.start, in.coord_bits, cls, n, lm, logw, (int)nT, hist.p, coarse_cnt.p, n_coarse, vec_ok);
+    }
     device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, hist.p, offS.p, nT, offS.p + nT);
     device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, coarse_cnt.p, cur_coarse.p, (int64_t)n_coarse * G, cur_coarse.p + (int64_t)n_coarse * G);
     LAUNCH(ctx, tiled::k_init_cursors, grid_for(ctx, nT, 256), 256, 0, offS.p, (int)nT, cur_tile.p);
@@ -1168,9 +1193,9 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     const unsigned mg = (unsigned)std::min<int64_t>(in_tiles, (int64_t)ctx->num_sms * 16);
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<true>()));
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<false>()));
-    LAUNCH(ctx, tiled::k_multisplit<true>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<true>(), (const uint64_t*)nullptr, in.chrom, in.start, in.stop, in.coord_bits, cls, lm, cfg.B, n, 32 + logw + 8, cur_coarse.p, pk_a.p, vec_ok, G);
+    LAUNCH(ctx, tiled::k_multisplit<true>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<true>(), (const uint64_t*)nullptr, in.chrom, in.start, in.stop, in.coord_bits, cls, lm, cfg.B, n, 32 + logw + 8, cur_coarse.p, pk_a.p, vec_ok, G, guard);
     LAUNCH(ctx, tiled::k_multisplit<false>, mg, tiled::MSP_THREADS, tiled::msp_smem_bytes<false>(), (const uint64_t*)pk_a.p, (const int32_t*)nullptr, (const void*)nullptr, (const void*)nullptr, 0, (const uint32_t*)nullptr, lm, cfg.B, n,
-           32 + logw, cur_tile.p, pk_b.p, 0, 1);
+           32 + logw, cur_tile.p, pk_b.p, 0, 1, guard);
     P = pk_b.p;
   } else {
     LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, pk_a.p);
@@ -1203,10 +1228,10 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
   if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc);
+    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc, guard);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc);
+    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc, guard);
   }
   unsigned long long h_np = 0;
   int h_fail = 0;
@@ -1228,12 +1253,20 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     so.group = fo->group.p; so.strand = fo->strand.p; so.chrom = fo->chrom.p; so.start = fo->start.p; so.stop = fo->stop.p;
     so.acc = fo->acc.p; so.accd = fo->accd.p; so.j1 = fo->j1.p; so.j2 = fo->j2.p; so.totals = totals.p;
     LAUNCH(ctx, tiled::k_stitch_small, tiled::STITCH_CL, tiled::STITCH_T, 0, (const uint32_t*)blk_cnt.p, (int)tgrid, blk_off.p, pc, order_buf.p, ridx.p, rr, lm, flag == GMQL_FLAT ? 1 : 0,
-           cfg.n_classes, cfg.unified, so);
+           cfg.n_classes, cfg.unified, so, guard);
     unsigned long long* h_tot = (unsigned long long*)ctx_pinned(ctx, 64);
     int* h_f = (int*)(h_tot + 4);
     CUDA_TRY(cudaMemcpyAsync(h_tot, totals.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(h_f, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (guard.flags) {
+      CUDA_TRY(cudaMemcpyAsync(spec->h_flags, spec->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(spec->h_span, spec->act_span, 8 * (size_t)spec->n_chrom, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CUDA_TRY(GMQL_SYNC(ctx));
+    if (guard.flags) {
+      spec->synced = true;
+      if (spec->h_flags[1] || spec->h_flags[2] || spec->h_flags[3] >= guard.max_len) { spec->tripped = true; return false; }
+    }
     if (*h_f) return false;
     if (!h_tot[3]) {
       fo->ready = true;
@@ -1247,7 +1280,15 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     LAUNCH(ctx, tiled::k_seg_offsets, 1, 1024, 0, blk_cnt.p, (int)tgrid, blk_off.p, np_dev.p);
     CUDA_TRY(cudaMemcpyAsync(&h_np, np_dev.p, sizeof h_np, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(&h_fail, fail.p, sizeof h_fail, cudaMemcpyDeviceToHost, ctx->stream));
+    if (guard.flags) {
+      CUDA_TRY(cudaMemcpyAsync(spec->h_flags, spec->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(spec->h_span, spec->act_span, 8 * (size_t)spec->n_chrom, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CUDA_TRY(GMQL_SYNC(ctx));
+    if (guard.flags) {
+      spec->synced = true;
+      if (spec->h_flags[1] || spec->h_flags[2] || spec->h_flags[3] >= guard.max_len) { spec->tripped = true; return false; }
+    }
     if (h_fail) return false;
   }
   const int64_t np = (int64_t)h_np;
@@ -1291,7 +1332,8 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
 
 template <typename K>
 static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_sample_group, int n_groups, int flag, const int32_t* h_mn, const int32_t* h_mx, int64_t B,
-                      const CovAggPlan& plan, const SpanTable& spans, bool unified, bool has_zero, int64_t maxlen, gmql_result* res, const ShardSpec* shard = nullptr) {
+                      const CovAggPlan& plan, const SpanTable& spans, bool unified, bool has_zero, int64_t maxlen, gmql_result* res, const ShardSpec* shard = nullptr,
+                      SpecCtx* spec = nullptr) {
   const int64_t n = in.n;
   CoverCfg cfg;
   cfg.n_groups = n_groups;
@@ -1348,16 +1390,21 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     if (force && !strcmp(force, "tiled")) want = fits;
     if (force && !strcmp(force, "sort")) want = false;
     if (shard) want = fits;
+    if (spec && (!want || (int64_t)((n_classes_total * lm.G) >> logw) + 1 > tiled::HIST_CAP || lm.n_chrom > 1024)) { spec->declined = true; return; }
     // A pile-up (many regions on a few kilobases, as real peak data has at promoters) can overflow one tile's tables:
     // retry with tiles four and sixteen times narrower before giving the input to the sort-and-merge path
     for (int attempt = 0; want && !done && attempt < 3; ++attempt) {
       const int lw = logw - 2 * attempt;
       if (lw < 8 || maxlen >= (int64_t)(1ll << lw) - 2) break;
       done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr, plan.n_aggs ? &truns : nullptr,
-                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr);
+                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr, spec);
+      if (spec) {
+        if (spec->tripped) return;                     // not eligible after all: the caller starts over with a blocking prepass
+        maxlen = spec->h_flags[3];                     // the flags are on the host now: later attempts (and the sort path) are ordinary
+      }
       if (flw || shard) break;                         // a forced width is not second-guessed
     }
-  }
+  } else if (spec) { spec->declined = true; return; }
 
   if (done && plan.n_aggs) {
     // value aggregates of the tile-resident path: region-driven post-pass over the runs
@@ -1601,6 +1648,38 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
     gmql_upload_regions(ctx, in, need_cols, &d);
     cudaEventRecord(ctx->ev_h1, ctx->stream);
     cudaEventRecord(ctx->ev_k0, ctx->stream);
+    // Speculative launch: the caller knows an upper bound of every chromosome's span (chrom_span_hint), so the linear layout is
+    // fixed before any data is read and the tile pipeline is queued at once behind a fused prepass + histogram kernel; the
+    // prepass flags come back with the pipeline's one synchronisation.  One (group, strand) class, 32-bit coordinates, no
+    // strand column, COVER / FLAT without aggregates; anything else, and any input that turns out not to be eligible, takes
+    // the ordinary route below.
+    const char* spec_env = getenv("GMQL_COVER_SPECULATE");   // "0": test hook
+    if (in->chrom_span_hint && !shard && d.n > 0 && d.coord_bits == 32 && d.strand == nullptr && n_groups == 1 && plan.n_aggs == 0 &&
+        (flag == GMQL_COVER || flag == GMQL_FLAT) && !(spec_env && spec_env[0] == '0')) {
+      SpanTable hs;
+      span_table_from_hint(ctx, in->chrom_span_hint, d.n_chrom, &hs, (unsigned long long)bin_size + 2ull);
+      if (hs.G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
+        DevBuf<int> sflags(ctx, 4);
+        DevBuf<unsigned long long> act(ctx, d.n_chrom);
+        sflags.zero(); act.zero();
+        SpecCtx sc;
+        sc.flags = sflags.p; sc.act_span = act.p; sc.n_chrom = d.n_chrom;
+        sc.h_flags = (int*)ctx_pinned(ctx, 4 * sizeof(int));
+        sc.h_span = (unsigned long long*)ctx_pinned(ctx, 8 * (size_t)d.n_chrom);
+        res = new gmql_result();
+        run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, hs, /*unified=*/true, /*has_zero=*/false, /*maxlen=*/0, res, nullptr, &sc);
+        if (!sc.declined && !sc.tripped) {
+          res->span_hint.resize((size_t)d.n_chrom);
+          for (int c = 0; c < d.n_chrom; ++c) res->span_hint[c] = (int64_t)sc.h_span[c] + 1;   // results may carry the one-base extension
+          CUDA_TRY(GMQL_SYNC_IF_PENDING(ctx));
+          *out = res;
+          gmql_trace("EXIT");
+          return GMQL_OK;
+        }
+        gmql_result_free(ctx, res);                       // nothing (declined) or a guarded, empty pipeline (tripped) has run
+        res = nullptr;
+      }
+    }
     // one read of the columns: chromosome spans + input flags
     SpanTable spans;
     spans.n_chrom = d.n_chrom;

@@ -1,5 +1,5 @@
 // gmql_ctx.cu — context, dataset upload, result accessors of the C ABI (include/gmql_cuda.h).
-#include "common.cuh"
+#include "index.cuh"
 #include <algorithm>
 
 extern "C" int gmql_abi_version(void) { return GMQL_ABI_VERSION; }
@@ -255,6 +255,7 @@ struct gmql_dataset {
   std::vector<int64_t> sample_ids;
   std::vector<int64_t> sample_offsets;   // host copy when the upload declared the rows grouped by sample
   gmql_ctx* owner = nullptr;             // context holding this dataset's trusted-grouping entry
+  std::vector<int64_t> span_hint;        // largest stop per chromosome, computed at upload when the caller gave no hint
   std::vector<const double*> cols;
   std::vector<const uint8_t*> valid;
 };
@@ -296,6 +297,23 @@ extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql
     view->valid = d->valid.empty() ? nullptr : d->valid.data();
     view->dup_of = d->dev.dup_of;
     view->chrom_span_hint = host->chrom_span_hint;
+    if (!host->chrom_span_hint && d->dev.n > 0) {
+      // dataset statistics at load time (what GMQL's own profiler keeps per dataset): the largest stop of every chromosome.
+      // The view hands them on as chrom_span_hint, so operators on the resident dataset know the genome's layout up front.
+      DevBuf<unsigned long long> span(ctx, d->dev.n_chrom);
+      DevBuf<int> bad(ctx, 1);
+      span.zero(); bad.zero();
+      accumulate_spans(ctx, d->dev, span.p, bad.p);
+      std::vector<unsigned long long> hs((size_t)d->dev.n_chrom);
+      int h_bad = 0;
+      CUDA_TRY(cudaMemcpyAsync(hs.data(), span.p, 8 * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(GMQL_SYNC(ctx));
+      if (!h_bad) {                                     // invalid rows: no hint; the operators report them
+        d->span_hint.assign(hs.begin(), hs.end());
+        view->chrom_span_hint = d->span_hint.data();
+      }
+    }
     view->sorted_by_position = host->sorted_by_position;
     *out = d;
     return GMQL_OK;

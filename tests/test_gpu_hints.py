@@ -209,3 +209,70 @@ def test_grouped_count_kernel_equals_streaming_kernel(ex, n_ref, presorted):
         assert rc == 0 and np.array_equal(got, want)
     finally:
         os.environ.pop("GMQL_MAP_GROUPED", None)
+
+
+def _cover_cols(ex, c_ds, flag, mn, mx):
+    from gmql_b200 import _lib as L
+    mn_a, mx_a = np.array([mn], np.int32), np.array([mx], np.int32)
+    out = C.c_void_p()
+    rc = ex.lib.gmql_cover(ex.ctx, C.byref(c_ds), None, 1, flag, mn_a.ctypes.data, mx_a.ctypes.data, 2000, (L.Agg * 1)(), 0, C.byref(out))
+    if rc != 0:
+        return rc, ex.lib.gmql_last_error(ex.ctx)
+    cols = []
+    for col, dt in ((L.COL_COV_CHROM, np.int32), (L.COL_COV_START, np.int64), (L.COL_COV_STOP, np.int64), (L.COL_COV_ACC, np.int32),
+                    (L.COL_COV_STRAND, np.int8), (L.COL_COV_J1, np.float64), (L.COL_COV_J2, np.float64)):
+        a = np.empty(int(ex.lib.gmql_result_column_len(out, col)), dt)
+        if a.shape[0]:
+            ex._check(ex.lib.gmql_result_column_copy(ex.ctx, out, col, a.ctypes.data))
+        cols.append(a)
+    ex.lib.gmql_result_free(ex.ctx, out)
+    return 0, cols
+
+
+@pytest.mark.parametrize("case", ["eligible", "zero_length", "long_region", "beyond_hint", "bad_row"])
+def test_speculative_cover_with_span_hint(ex, case):
+    """With chrom_span_hint (and no strand column) gmql_cover queues the whole tile pipeline behind a fused prepass + histogram
+    kernel without waiting for the prepass flags.  Eligible input: same rows as the ordinary call, and k_prepass_hist ran.
+    Inputs that turn out not to be eligible (a zero-length region, a region as long as a tile, a region beyond its hint) are
+    caught by the device-side guard and recomputed the ordinary way: same rows as without the hint.  Invalid rows are errors."""
+    import os
+    from gmql_b200 import synth, _lib as L
+    ds = synth.peak_samples(60, 20000, 9, with_values=())
+    spans = [int(ds.stop[ds.chrom == c].max(initial=0)) for c in range(len(ds.chrom_names))]
+    if case == "zero_length":
+        ds.stop[1234] = ds.start[1234]
+    elif case == "long_region":
+        ds.stop[777] = ds.start[777] + 70000
+        spans = [int(ds.stop[ds.chrom == c].max(initial=0)) for c in range(len(ds.chrom_names))]
+    elif case == "bad_row":
+        ds.start[55] = ds.stop[55] + 10
+    hint = list(spans)
+    if case == "beyond_hint":
+        hint[0] -= 5
+    os.environ["GMQL_COVER_PATH"] = "tiled"
+    try:
+        for flag, (mn, mx) in ((0, (2, 2 ** 31 - 1)), (1, (1, 3))):
+            c_plain, k0 = ds.as_c()
+            c_plain.strand = None
+            rc0, want = _cover_cols(ex, c_plain, flag, mn, mx)
+            c_hint, k1 = ds.as_c(chrom_span_hint=hint)
+            c_hint.strand = None
+            (rc, got), kern = _profile(ex, lambda: _cover_cols(ex, c_hint, flag, mn, mx))
+            if case == "bad_row":
+                assert rc0 < 0 and rc < 0
+                continue
+            assert rc0 == 0 and rc == 0 and "k_prepass_hist" in kern
+            assert ("k_cover_prepass" in kern) == (case != "eligible"), kern      # the ordinary prepass only runs after a tripped guard
+            assert len(want[0]) > 100
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (case, flag)
+            os.environ["GMQL_COVER_SPECULATE"] = "0"
+            try:
+                (rc, got), kern = _profile(ex, lambda: _cover_cols(ex, c_hint, flag, mn, mx))
+            finally:
+                os.environ.pop("GMQL_COVER_SPECULATE", None)
+            assert rc == 0 and "k_prepass_hist" not in kern
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (case, flag)
+    finally:
+        os.environ.pop("GMQL_COVER_PATH", None)
