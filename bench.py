@@ -354,7 +354,7 @@ def run_ours(args):
                        "l2": "device-resident inputs (%.2f GB per rank) larger than the 126 MB L2" % (16.0 * n_in / 1e9), "map_count_checksum": int(tot_check)},
             "e2e": {"value": tot_in / (ms_e2e_max * 1e-3), "unit": "input regions/s", "ms_per_step": ms_e2e_max,
                     "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h), "steps": e2e_steps,
-                    "h2d_ms_rank0": round(float(np.median(h2d_ms[1:] or h2d_ms)), 3), "step_ms_rank0": e2e_each, "host_binding_rank0": numa},
+                    "h2d_ms_rank0": round(float(np.median(h2d_ms[1:] or h2d_ms)), 3), "step_ms_rank0": e2e_each, "h2d_each_ms_rank0": [round(float(x), 2) for x in h2d_ms[1:]], "host_binding_rank0": numa},
             "gpu_launches": int(tot_launch),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "launches_per_step": top[1], "ms_per_launch": top_ms,

@@ -91,8 +91,11 @@ typedef struct {
   const int64_t* chrom_span_hint;/* HOST array [n_chrom] or NULL: an upper bound of `stop` per chromosome (e.g. the
                                    assembly's chromosome sizes).  Lets gmql_map / gmql_join lay out the linear coordinate
                                    without a pass over the data and a host round trip; a region beyond its bound is an
-                                   error (GMQL_ERR_INVALID), never a wrong result.  Views made by gmql_result_as_regions
-                                   carry it. */
+                                   error (GMQL_ERR_INVALID), never a wrong result.  gmql_cover uses it to queue its tile
+                                   pipeline without waiting for its own prepass (a region beyond its bound there only
+                                   makes the call take the ordinary route).  Views made by gmql_result_as_regions carry
+                                   it, and so do views made by gmql_dataset_upload (the largest stop seen per
+                                   chromosome, computed once at upload, when the caller gave none). */
   int32_t stop_is_length;       /* 0: `stop` holds stop coordinates.  16 / 32: `stop` holds region LENGTHS (stop - start) as
                                    uint16_t[] / uint32_t[] — narrowPeak-like data (lengths below 65 536) then crosses PCIe in
                                    2 bytes instead of 4 or 8 per region; the stop column is rebuilt on the device. */
