@@ -32,7 +32,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r01k_bench_c5_*gpu.json"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r01[kl]_bench_c5_*gpu.json"))))
 def test_committed_gpu_lines_follow_the_contract(path):
     d = json.load(open(path))
     for k in BASE_KEYS:
