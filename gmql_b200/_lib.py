@@ -51,7 +51,7 @@ EXPORTS = [
     "gmql_result_column_elem_size", "gmql_result_column_device", "gmql_result_column_copy",
     "gmql_result_as_regions", "gmql_result_free", "gmql_last_device_ms", "gmql_last_h2d_ms",
     "gmql_dataset_upload", "gmql_dataset_free", "gmql_ctx_set_profiling", "gmql_ctx_profile_report",
-    "gmql_difference", "gmql_profile", "gmql_parse_text", "gmql_cover_shard",
+    "gmql_difference", "gmql_profile", "gmql_parse_text", "gmql_cover_shard", "gmql_ctx_set_option",
 ]
 
 _lib = None
@@ -74,6 +74,7 @@ def load_library(path=None):
     lib.gmql_last_error.argtypes = [vp]
     lib.gmql_last_error.restype = C.c_char_p
     lib.gmql_ctx_sync.argtypes = [vp]
+    lib.gmql_ctx_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     lib.gmql_ctx_launch_count.argtypes = [vp]
     lib.gmql_ctx_launch_count.restype = i64
     lib.gmql_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]

@@ -40,6 +40,11 @@ constexpr int MAXP = 256;               // pieces per tile
 constexpr int HCAP = 512;               // regions of the previous tile still open at the tile start
 constexpr int MAX_TILE_REGIONS = 32000; // own + open regions of one tile: keeps every 16-bit net change exact
 constexpr uint32_t EXT = 0x80000000u;   // length payload bit: stop' = stop + 1
+// Partitioned records are 4 bytes: tile-local start (16 bits) | one-base extension (bit 15) | length (15 bits).  Regions of
+// 32 768 bases and more do not take the tile path.
+constexpr int MAX_REGION_LEN = 32767;
+constexpr uint32_t LEN_EXT16 = 0x8000u; // the extension bit inside the 16-bit length word
+__device__ __forceinline__ uint32_t rec_len_payload(uint32_t rec) { return (rec & 0x7fffu) | ((rec & LEN_EXT16) << 16); }   // length | EXT
 constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 2 * CAP_EV + 16 * HCAP + 32 * MAXP;
 
 // net +1 / -1 per distinct position, two 16-bit signed counters per shared-memory word.  Adding +-1 to the low half may borrow
@@ -163,6 +168,51 @@ static __global__ void __launch_bounds__(1024, 1) k_tile_hist(const int32_t* __r
   for (int k = threadIdx.x; k < nT; k += blockDim.x) {
     const uint32_t c = sh_hist[k];
     if (c) { atomicAdd(&hist[k], c); atomicAdd(&s_coarse[k >> 8], c); }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_coarse; k += blockDim.x) coarse_cnt[(size_t)k * gridDim.x + blockIdx.x] = s_coarse[k];
+}
+
+// the same counts from the ABI's narrow encodings (uint8 chromosome, int32 start): what gmql_dataset_upload keeps resident
+static __global__ void __launch_bounds__(1024, 1) k_tile_hist_narrow(const uint8_t* __restrict__ chrom8, const int32_t* __restrict__ start, int64_t n, LinMap lm, int logw, int nT,
+                                                                      uint32_t* __restrict__ hist, uint32_t* __restrict__ coarse_cnt, int n_coarse, int vec_ok) {
+  extern __shared__ uint32_t sh_hist[];                    // [nT], chromosome offsets (<= 256), coarse counters
+  uint32_t* s_coff = sh_hist + nT;
+  uint32_t* s_coarse = s_coff + 256;
+  for (int k = threadIdx.x; k < nT; k += blockDim.x) sh_hist[k] = 0;
+  for (int k = threadIdx.x; k < n_coarse; k += blockDim.x) s_coarse[k] = 0;
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) s_coff[k] = k < lm.n_chrom ? (uint32_t)lm.coff[k] : 0u;
+  __syncthreads();
+  const int64_t n_tiles = (n + MSP_TILE - 1) / MSP_TILE;
+  for (int64_t t0 = blockIdx.x; t0 < n_tiles; t0 += 2 * (int64_t)gridDim.x) {
+    uint32_t c[8], st[8]; bool ok[8];                      // two input tiles in flight: four consecutive regions per thread and tile
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t t = t0 + h * (int64_t)gridDim.x;
+      const int64_t i0 = t * MSP_TILE + (int64_t)threadIdx.x * 4;
+      if (t < n_tiles && vec_ok && i0 + 4 <= n) {
+        const uint32_t vc = *(const uint32_t*)(chrom8 + i0);
+        const int4 vs = *(const int4*)(start + i0);
+        c[4 * h] = vc & 0xffu; c[4 * h + 1] = (vc >> 8) & 0xffu; c[4 * h + 2] = (vc >> 16) & 0xffu; c[4 * h + 3] = vc >> 24;
+        st[4 * h] = (uint32_t)vs.x; st[4 * h + 1] = (uint32_t)vs.y; st[4 * h + 2] = (uint32_t)vs.z; st[4 * h + 3] = (uint32_t)vs.w;
+        ok[4 * h] = ok[4 * h + 1] = ok[4 * h + 2] = ok[4 * h + 3] = true;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool v = t < n_tiles && i0 + q < n;
+          ok[4 * h + q] = v;
+          c[4 * h + q] = v ? (uint32_t)chrom8[i0 + q] : 0u;
+          st[4 * h + q] = v ? (uint32_t)start[i0 + q] : 0u;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (ok[j]) atomicAdd(&sh_hist[(s_coff[c[j]] + st[j]) >> logw], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nT; k += blockDim.x) {
+    const uint32_t cnt = sh_hist[k];
+    if (cnt) { atomicAdd(&hist[k], cnt); atomicAdd(&s_coarse[k >> 8], cnt); }
   }
   __syncthreads();
   for (int k = threadIdx.x; k < n_coarse; k += blockDim.x) coarse_cnt[(size_t)k * gridDim.x + blockIdx.x] = s_coarse[k];
@@ -294,29 +344,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // generic-proxy reads of a staging buffer are ordered before the async proxy overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// FUSED: records are built from the input columns and split by coarse bin (tile >> 8); otherwise records are read from
-// `in` and split by tile.  bin_shift = 32 + logw (+ 8 for the coarse pass).
-// The input of the NEXT tile of a block (one 32 KB run of records, or three 16 KB column runs) is fetched by TMA bulk
-// copies into a staging buffer while the current tile is ranked, regrouped and written: every thread moves its items
-// from the staging buffer into registers first, so one staging buffer and one mbarrier suffice, and the load latency
-// no longer sits at the head of every tile (registers are at the 64-per-thread limit of two 512-thread blocks per SM,
-// so a register prefetch is not an option).
-constexpr size_t MSP_STAGE_BYTES_FUSED = 3 * 4 * (size_t)MSP_TILE, MSP_STAGE_BYTES_PACKED = 8 * (size_t)MSP_TILE;
-template <bool FUSED>
-constexpr size_t msp_smem_bytes() { return 8 * (size_t)MSP_TILE + (FUSED ? MSP_STAGE_BYTES_FUSED : MSP_STAGE_BYTES_PACKED) + 3 * 4 * (size_t)MSP_BINS + (FUSED ? 8 * 256 : 0); }
+// Three variants of one kernel:
+//   MSP_WIDE / MSP_NARROW  coarse pass: records are built from the input columns — int32 (or int64) chrom / start / stop, or the
+//                          ABI's narrow encodings uint8 chrom, int32 start, uint16 length (7 bytes per region) — and split by
+//                          coarse bin (tile >> 8); written as two arrays, linear start key (uint32) and length word (uint16:
+//                          length | extension bit 15), 6 bytes per region;
+//   MSP_FINE               fine pass: reads those two arrays and splits every coarse bin into its tiles; written as ONE 4-byte
+//                          record per region (tile-local start << 16 | length word), which is all the tile kernel reads.
+// bin_shift = 32 + logw (+ 8 for the coarse pass) applies to the 64-bit register form (key << 32 | length word).
+// The input of the NEXT tile of a block is fetched by TMA bulk copies into a staging buffer while the current tile is ranked,
+// regrouped and written: every thread moves its items from the staging buffer into registers first, so one staging buffer
+// and one mbarrier suffice, and the load latency no longer sits at the head of every tile (registers are at the
+// 64-per-thread limit of two 512-thread blocks per SM, so a register prefetch is not an option).
+enum { MSP_FINE = 0, MSP_WIDE = 1, MSP_NARROW = 2 };
+struct MspIn {
+  const uint32_t* key; const uint16_t* len;                                                         // MSP_FINE
+  const int32_t* chrom; const void* start; const void* stop; int bits; const uint32_t* cls;       // MSP_WIDE
+  const uint8_t* chrom8; const uint16_t* len16;                                                     // MSP_NARROW (start: int32 in `start`)
+};
+struct MspOut { uint32_t* key; uint16_t* len; uint32_t* rec; };
+template <int MODE>
+__host__ __device__ constexpr size_t msp_stage_bytes() { return (MODE == MSP_FINE ? 6 : (MODE == MSP_WIDE ? 12 : 7)) * (size_t)MSP_TILE; }
+template <int MODE>
+constexpr size_t msp_smem_bytes() { return 8 * (size_t)MSP_TILE + msp_stage_bytes<MODE>() + 3 * 4 * (size_t)MSP_BINS + (MODE != MSP_FINE ? 8 * 256 : 0); }
 
-template <bool FUSED>
-static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint64_t* __restrict__ in, const int32_t* __restrict__ chrom, const void* __restrict__ start,
-                                                                      const void* __restrict__ stop, int bits, const uint32_t* __restrict__ cls, LinMap lm, int64_t B,
-                                                                      int64_t n, int bin_shift, uint32_t* __restrict__ cursor, uint64_t* __restrict__ out, int vec_ok, int groups, Guard guard) {
+template <int MODE>
+static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, LinMap lm, int64_t B, int64_t n, int bin_shift, int logw, uint32_t* __restrict__ cursor, MspOut out,
+                                                                      int vec_ok, int groups, Guard guard) {
   if (guard_trips(guard)) return;
+  constexpr bool FUSED = MODE != MSP_FINE;
   extern __shared__ __align__(128) unsigned char msp_smem[];
   uint64_t* sdata = (uint64_t*)msp_smem;                                    // [MSP_TILE] regroup buffer
   unsigned char* stage = msp_smem + 8 * (size_t)MSP_TILE;                   // TMA landing buffer
-  uint32_t* cnt = (uint32_t*)(stage + (FUSED ? MSP_STAGE_BYTES_FUSED : MSP_STAGE_BYTES_PACKED));
+  uint32_t* cnt = (uint32_t*)(stage + msp_stage_bytes<MODE>());
   uint32_t* lexcl = cnt + MSP_BINS;
   uint32_t* gbase = lexcl + MSP_BINS;
-  uint64_t* s_coff = (uint64_t*)(gbase + MSP_BINS);                         // [256], FUSED only
+  uint64_t* s_coff = (uint64_t*)(gbase + MSP_BINS);                         // [256], coarse passes only
   __shared__ uint32_t wtot[MSP_THREADS / 32];
   __shared__ uint32_t s_base_bin;
   __shared__ uint64_t s_bar;
@@ -325,20 +388,25 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
   if (chrom_sh) for (int k = tid; k < lm.n_chrom; k += MSP_THREADS) s_coff[k] = lm.coff[k];
   const uint64_t* coff = chrom_sh ? s_coff : lm.coff;
   const int64_t n_tiles = (n + MSP_TILE - 1) / MSP_TILE;
-  // full tiles of suitably aligned 32-bit input go through the staging buffer
   // n % B == 0  <=>  M * n (mod 2^64) <= M - 1 with M = floor((2^64 - 1) / B) + 1, exact for 32-bit n (Lemire, Kaser, Kurz 2019)
   const uint64_t bmagic = FUSED && B > 1 ? 0xffffffffffffffffull / (uint64_t)B + 1ull : 0ull;
-  const bool tma_ok = FUSED ? (vec_ok && bits == 32 && cls == nullptr) : (((uintptr_t)in & 15u) == 0);
+  // full tiles of suitably aligned input go through the staging buffer
+  const bool tma_ok = MODE == MSP_FINE ? ((((uintptr_t)in.key | (uintptr_t)in.len) & 15u) == 0)
+                    : (MODE == MSP_WIDE ? (vec_ok && in.bits == 32 && in.cls == nullptr) : (vec_ok != 0));
   auto issue = [&](int64_t t) {                            // one thread: arm the barrier, start the copies of tile t
     const int64_t base = t * MSP_TILE;
-    if (FUSED) {
-      mbar_expect_tx(&s_bar, (uint32_t)MSP_STAGE_BYTES_FUSED);
-      tma_load_1d(stage, chrom + base, 4 * MSP_TILE, &s_bar);
-      tma_load_1d(stage + 4 * MSP_TILE, (const int32_t*)start + base, 4 * MSP_TILE, &s_bar);
-      tma_load_1d(stage + 8 * MSP_TILE, (const int32_t*)stop + base, 4 * MSP_TILE, &s_bar);
+    mbar_expect_tx(&s_bar, (uint32_t)msp_stage_bytes<MODE>());
+    if (MODE == MSP_WIDE) {
+      tma_load_1d(stage, in.chrom + base, 4 * MSP_TILE, &s_bar);
+      tma_load_1d(stage + 4 * MSP_TILE, (const int32_t*)in.start + base, 4 * MSP_TILE, &s_bar);
+      tma_load_1d(stage + 8 * MSP_TILE, (const int32_t*)in.stop + base, 4 * MSP_TILE, &s_bar);
+    } else if (MODE == MSP_NARROW) {
+      tma_load_1d(stage, (const int32_t*)in.start + base, 4 * MSP_TILE, &s_bar);
+      tma_load_1d(stage + 4 * MSP_TILE, in.len16 + base, 2 * MSP_TILE, &s_bar);
+      tma_load_1d(stage + 6 * MSP_TILE, in.chrom8 + base, MSP_TILE, &s_bar);
     } else {
-      mbar_expect_tx(&s_bar, (uint32_t)MSP_STAGE_BYTES_PACKED);
-      tma_load_1d(stage, in + base, 8 * MSP_TILE, &s_bar);
+      tma_load_1d(stage, in.key + base, 4 * MSP_TILE, &s_bar);
+      tma_load_1d(stage + 4 * MSP_TILE, in.len + base, 2 * MSP_TILE, &s_bar);
     }
   };
   if (tid == 0) {
@@ -354,16 +422,16 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
     const uint32_t cmul = FUSED ? (uint32_t)groups : 1u, cadd = FUSED ? (uint32_t)(t % groups) : 0u;
     for (int k = tid; k < MSP_BINS; k += MSP_THREADS) cnt[k] = 0;
     __syncthreads();                                       // also orders s_coff, the barrier's init and the previous iteration's reads
-    // item j of a thread is record idx_of(j) of the tile: striped for packed input, four consecutive regions per
-    // 128-bit column load when the records are built from the columns
+    // item j of a thread is record idx_of(j) of the tile: striped for the fine pass, four consecutive regions per
+    // vector load when the records are built from the columns
     uint64_t rec[MSP_ITEMS];
     if (staged) { mbar_wait(&s_bar, parity); parity ^= 1u; }
-    if (FUSED) {
+    if (MODE == MSP_WIDE) {
 #pragma unroll
       for (int j4 = 0; j4 < MSP_ITEMS / 4; ++j4) {
         const int idx0 = (j4 * MSP_THREADS + tid) * 4;
         const int64_t i0 = base + idx0;
-        if (staged || (idx0 + 4 <= count && vec_ok && bits == 32)) {
+        if (staged || (idx0 + 4 <= count && vec_ok && in.bits == 32)) {
           int4 vc, vs, ve;
           uint4 vk = make_uint4(0u, 0u, 0u, 0u);
           if (staged) {
@@ -371,8 +439,8 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
             vs = ((const int4*)(stage + 4 * MSP_TILE))[j4 * MSP_THREADS + tid];
             ve = ((const int4*)(stage + 8 * MSP_TILE))[j4 * MSP_THREADS + tid];
           } else {
-            vc = *(const int4*)(chrom + i0); vs = *(const int4*)((const int32_t*)start + i0); ve = *(const int4*)((const int32_t*)stop + i0);
-            if (cls) vk = *(const uint4*)(cls + i0);
+            vc = *(const int4*)(in.chrom + i0); vs = *(const int4*)((const int32_t*)in.start + i0); ve = *(const int4*)((const int32_t*)in.stop + i0);
+            if (in.cls) vk = *(const uint4*)(in.cls + i0);
           }
           const int cc[4] = {vc.x, vc.y, vc.z, vc.w}, ss[4] = {vs.x, vs.y, vs.z, vs.w}, ee[4] = {ve.x, ve.y, ve.z, ve.w};
           const uint32_t kk[4] = {vk.x, vk.y, vk.z, vk.w};
@@ -380,18 +448,63 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
           for (int q = 0; q < 4; ++q) {
             const uint32_t key = (uint32_t)((uint64_t)kk[q] * lm.G + coff[cc[q]]) + (uint32_t)ss[q];
             const bool ext = (bmagic * (uint64_t)(uint32_t)ee[q] <= bmagic - 1ull) && ss[q] < ee[q];   // ee % B == 0 without a division
-            rec[j4 * 4 + q] = ((uint64_t)key << 32) | (uint64_t)((uint32_t)(ee[q] - ss[q]) | (ext ? EXT : 0u));
+            rec[j4 * 4 + q] = ((uint64_t)key << 32) | (uint64_t)(((uint32_t)(ee[q] - ss[q]) & 0x7fffu) | (ext ? LEN_EXT16 : 0u));
           }
         } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rec[j4 * 4 + q] = idx0 + q < count ? make_record(chrom, start, stop, bits, cls, coff, lm.G, B, i0 + q) : 0ull;
+          for (int q = 0; q < 4; ++q) {
+            uint64_t r = 0ull;
+            if (idx0 + q < count) {
+              const uint64_t r64 = make_record(in.chrom, in.start, in.stop, in.bits, in.cls, coff, lm.G, B, i0 + q);   // key << 32 | length | EXT (bit 31)
+              r = (r64 & 0xffffffff00000000ull) | (r64 & 0x7fffull) | ((r64 & (uint64_t)EXT) ? (uint64_t)LEN_EXT16 : 0ull);
+            }
+            rec[j4 * 4 + q] = r;
+          }
+        }
+      }
+    } else if (MODE == MSP_NARROW) {
+#pragma unroll
+      for (int j4 = 0; j4 < MSP_ITEMS / 4; ++j4) {
+        const int idx0 = (j4 * MSP_THREADS + tid) * 4;
+        const int64_t i0 = base + idx0;
+        int ss[4]; uint32_t ll[4], cc[4];
+        if (staged || (idx0 + 4 <= count && vec_ok)) {
+          int4 vs; uint2 vl; uint32_t vc;
+          if (staged) {
+            vs = ((const int4*)stage)[j4 * MSP_THREADS + tid];
+            vl = ((const uint2*)(stage + 4 * MSP_TILE))[j4 * MSP_THREADS + tid];
+            vc = ((const uint32_t*)(stage + 6 * MSP_TILE))[j4 * MSP_THREADS + tid];
+          } else {
+            vs = *(const int4*)((const int32_t*)in.start + i0); vl = *(const uint2*)(in.len16 + i0); vc = *(const uint32_t*)(in.chrom8 + i0);
+          }
+          ss[0] = vs.x; ss[1] = vs.y; ss[2] = vs.z; ss[3] = vs.w;
+          ll[0] = vl.x & 0xffffu; ll[1] = vl.x >> 16; ll[2] = vl.y & 0xffffu; ll[3] = vl.y >> 16;
+          cc[0] = vc & 0xffu; cc[1] = (vc >> 8) & 0xffu; cc[2] = (vc >> 16) & 0xffu; cc[3] = vc >> 24;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool ok = idx0 + q < count;
+            ss[q] = ok ? ((const int32_t*)in.start)[i0 + q] : 0;
+            ll[q] = ok ? (uint32_t)in.len16[i0 + q] : 0u;
+            cc[q] = ok ? (uint32_t)in.chrom8[i0 + q] : 0u;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t key = (uint32_t)coff[cc[q]] + (uint32_t)ss[q];
+          const uint32_t e = (uint32_t)ss[q] + ll[q];
+          const bool ext = (bmagic * (uint64_t)e <= bmagic - 1ull) && ll[q] != 0u;
+          rec[j4 * 4 + q] = idx0 + q < count ? (((uint64_t)key << 32) | (uint64_t)((ll[q] & 0x7fffu) | (ext ? LEN_EXT16 : 0u))) : 0ull;
         }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < MSP_ITEMS; ++j) {
         const int idx = j * MSP_THREADS + tid;
-        rec[j] = staged ? ((const uint64_t*)stage)[idx] : (idx < count ? in[base + idx] : 0ull);
+        uint32_t k32 = 0u, l16 = 0u;
+        if (staged) { k32 = ((const uint32_t*)stage)[idx]; l16 = ((const uint16_t*)(stage + 4 * MSP_TILE))[idx]; }
+        else if (idx < count) { k32 = in.key[base + idx]; l16 = in.len[base + idx]; }
+        rec[j] = ((uint64_t)k32 << 32) | (uint64_t)l16;
       }
     }
     if (!FUSED && tid == 0) s_base_bin = (uint32_t)(rec[0] >> bin_shift) & ~255u;   // local bins are counted from the coarse bin of the tile's first record
@@ -401,6 +514,11 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
       if (tn < n_tiles && n - tn * MSP_TILE >= MSP_TILE) { fence_proxy_async(); issue(tn); }
     }
     const uint32_t base_bin = FUSED ? 0u : s_base_bin;
+    const uint32_t wmask = (1u << logw) - 1u;
+    auto emit = [&](uint32_t g, uint64_t r) {              // one record at its final place
+      if (FUSED) { out.key[g] = (uint32_t)(r >> 32); out.len[g] = (uint16_t)r; }
+      else out.rec[g] = ((((uint32_t)(r >> 32)) & wmask) << 16) | ((uint32_t)r & 0xffffu);
+    };
     uint32_t rk[MSP_ITEMS];
 #pragma unroll
     for (int j = 0; j < MSP_ITEMS; ++j) {
@@ -411,7 +529,7 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
         if (lb < (uint32_t)MSP_BINS) rk[j] = atomicAdd(&cnt[lb], 1u);
         else {                                             // far bin (tiny coarse bins only): placed directly
           uint32_t g = atomicAdd(&cursor[(uint32_t)(rec[j] >> bin_shift) * cmul + cadd], 1u);
-          out[g] = rec[j];
+          emit(g, rec[j]);
         }
       }
     }
@@ -450,9 +568,18 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(const uint
     for (int i = tid; i < local_total; i += MSP_THREADS) {
       uint64_t r = sdata[i];
       uint32_t lb = (uint32_t)(r >> bin_shift) - base_bin;
-      out[gbase[lb] + ((uint32_t)i - lexcl[lb])] = r;
+      emit(gbase[lb] + ((uint32_t)i - lexcl[lb]), r);
     }
     __syncthreads();
+  }
+}
+
+// the radix-sort route (more tiles than the counting kernel's shared memory holds): sorted 64-bit records -> 4-byte records
+static __global__ void k_pack_rec32(const uint64_t* __restrict__ packed, int64_t n, int logw, uint32_t* __restrict__ rec) {
+  const uint32_t wmask = (1u << logw) - 1u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = packed[i];
+    rec[i] = ((((uint32_t)(r >> 32)) & wmask) << 16) | ((uint32_t)r & 0x7fffu) | ((r & (uint64_t)EXT) ? LEN_EXT16 : 0u);
   }
 }
 
@@ -552,7 +679,7 @@ __device__ __forceinline__ void gmap4_round(bool valid, uint32_t rs, uint32_t re
 // still open at a tile's end are handed to the next tile through shared memory; only the first tile of a range scans
 // its predecessor's regions in global memory.
 template <bool MULTI>
-static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(const uint2* __restrict__ P /* .y = start key, .x = length payload */, const uint32_t* __restrict__ offS,
+static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(const uint32_t* __restrict__ P /* tile-local start << 16 | length word */, const uint32_t* __restrict__ offS,
                                                                   int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, Pieces out, Guard guard) {
   if (guard_trips(guard)) return;
   extern __shared__ uint32_t sm[];
@@ -630,7 +757,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
         uint32_t i = i0 + tid;
         if (i < s0) {
-          const uint2 pr = P[i]; uint32_t rs = pr.y, lp = pr.x;
+          const uint32_t pr = P[i]; uint32_t rs = tile_lo - W + (pr >> 16), lp = rec_len_payload(pr);
           uint32_t ee = rs + (lp & ~EXT) + (lp >> 31);
           if (ee >= tile_lo) {
             int slot = atomicAdd(&s_nh, 1);
@@ -652,7 +779,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
     for (int r = 0; r < RC; ++r) {
       uint32_t i = s0 + tid + r * THREADS;
       rsr[r] = 0; lpr[r] = 0;
-      if (i < s1) { const uint2 pr = P[i]; rsr[r] = pr.y; lpr[r] = pr.x; }
+      if (i < s1) { const uint32_t pr = P[i]; rsr[r] = tile_lo + (pr >> 16); lpr[r] = rec_len_payload(pr); }
     }
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
@@ -665,7 +792,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       }
     }
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      const uint2 pr = P[i]; uint32_t rs = pr.y, lp = pr.x;
+      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr);
       uint32_t q = rs - tile_lo;
       atomicOr(&bitmap[q >> 5], 1u << (q & 31));
       uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
@@ -715,7 +842,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       }
     }
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      const uint2 pr = P[i]; uint32_t rs = pr.y, lp = pr.x;
+      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr);
       uint32_t q = rs - tile_lo;
       int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
       delta_add(delta, rk, 1);
@@ -841,7 +968,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
         }
       }
       for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-        const uint2 pr = P[i]; uint32_t rs = pr.y, re = rs + (pr.x & ~EXT);
+        const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), re = rs + (pr & 0x7fffu);
         if (p1 > rs && p0 < re) { ++cnt; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
       }
       cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -871,7 +998,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
         uint32_t i = i0 + tid;
         bool valid = i < s1;
         uint32_t rs = 0, re = 0;
-        if (valid) { const uint2 pr = P[i]; rs = pr.y; re = rs + (pr.x & ~EXT); }
+        if (valid) { const uint32_t pr = P[i]; rs = tile_lo + (pr >> 16); re = rs + (pr & 0x7fffu); }
         gmap4_round(valid, rs, re, true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
     }

@@ -20,6 +20,7 @@
 #include "index.cuh"
 #include "cover_tiled.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 namespace {
 
@@ -1148,60 +1149,122 @@ struct FusedOut {
 
 // host side of the tile-resident path; returns false (nothing consumed) when a capacity limit was hit and the caller must
 // fall back to the sort-and-merge path
+// what a resident dataset contributes to the tile path (cover_impl's fast route): its narrow arrays are read as they are and
+// the tile / coarse offsets computed at upload are reused when they were made for this layout
+struct TileSource { bool narrow = false; gmql_dataset* ds = nullptr; };
+
+static bool dataset_offsets_match(const gmql_dataset* ds, const LinMap& lm, uint64_t pad, int logw, int64_t nT, int groups, int n_coarse) {
+  return ds && ds->tile_off.p && ds->lay_pad == pad && ds->lay_G == lm.G && logw == tiled::MAX_LOGW && ds->hist_nT == nT && ds->hist_groups == groups && ds->hist_n_coarse == n_coarse;
+}
+
+// counts + scans of the tile partition for a dataset's narrow arrays (at upload, or when an operator uses another layout)
+static void tile_offsets_narrow(gmql_ctx* ctx, const DevRegions& in, const LinMap& lm, int logw, int64_t nT, int G, int n_coarse, uint32_t* tile_off /*[nT + 1]*/, uint32_t* coarse_off /*[n_coarse * G + 1]*/) {
+  const int64_t n = in.n;
+  DevBuf<uint32_t> hist(ctx, nT + 1), coarse_cnt(ctx, (int64_t)n_coarse * G);
+  hist.zero();
+  auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
+  const int vec_ok = al16(in.chrom_narrow) && al16(in.start);
+  const size_t hsh = sizeof(uint32_t) * ((size_t)nT + 256 + (size_t)n_coarse);
+  CUDA_TRY(cudaFuncSetAttribute(tiled::k_tile_hist_narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
+  LAUNCH(ctx, tiled::k_tile_hist_narrow, (unsigned)G, 1024, hsh, (const uint8_t*)in.chrom_narrow, (const int32_t*)in.start, n, lm, logw, (int)nT, hist.p, coarse_cnt.p, n_coarse, vec_ok);
+  device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, hist.p, tile_off, nT, tile_off + nT);
+  device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, coarse_cnt.p, coarse_off, (int64_t)n_coarse * G, coarse_off + (int64_t)n_coarse * G);
+}
+
+// host side of the tile-resident path; returns false (nothing consumed) when a capacity limit was hit and the caller must
+// fall back to the sort-and-merge path
 static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total, int logw,
                             const int32_t* h_mn, const int32_t* h_mx, Phase1Out* p1, DevBuf<int32_t>& keep, DevBuf<int64_t>& fstart, DevBuf<int64_t>& fstop,
-                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs, FusedOut* fo, SpecCtx* spec) {
+                            DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs, FusedOut* fo, SpecCtx* spec,
+                            const TileSource& src) {
   const int64_t n = in.n;
   tiled::Guard guard;
   guard.flags = (spec && !spec->synced) ? spec->flags : nullptr;
-  guard.max_len = (int)((1ll << logw) - 2);
+  guard.max_len = (int)std::min<int64_t>((1ll << logw) - 2, (int64_t)tiled::MAX_REGION_LEN + 1);
   const int key_bits = bits_for(n_classes_total * lm.G);
   const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
   // the tiles this call owns: all of them, or one shard's range (the tile before the range only lends its open regions)
   const int64_t t_lo = shard ? shard->first_tile : 0, t_hi = shard ? std::min<int64_t>(shard->end_tile, nT) : nT;
   GMQL_REQUIRE(t_lo >= 0 && t_lo <= t_hi, GMQL_ERR_INVALID, "bad tile range");
-  DevBuf<uint64_t> pk_a(ctx, n), pk_b(ctx, n);
-  DevBuf<uint32_t> offS(ctx, nT + 1);
-  uint64_t* P;
+  DevBuf<uint32_t> rec(ctx, n);                           // the partitioned 4-byte records
+  DevBuf<uint32_t> offS_own;
+  const uint32_t* offS = nullptr;
   if (nT <= tiled::HIST_CAP) {
-    // counting + two multisplit passes (cover_tiled.cuh): the packed record never exists unpartitioned
+    // counting + two multisplit passes (cover_tiled.cuh): the records never exist unpartitioned
     const int n_coarse = (int)((nT + 255) >> 8) + 1;
     // groups of input tiles (k_tile_hist): block b of the counting kernel and the blocks b, b + G, ... of the coarse pass
     const int64_t in_tiles = ceil_div64(n, tiled::MSP_TILE);
     const int G = (int)std::max<int64_t>(1, std::min<int64_t>(in_tiles, (int64_t)ctx->num_sms));
-    DevBuf<uint32_t> hist(ctx, nT + 1), cur_tile(ctx, nT + 1), coarse_cnt(ctx, (int64_t)n_coarse * G), cur_coarse(ctx, (int64_t)n_coarse * G + 1);
-    hist.zero();
+    DevBuf<uint32_t> key_a(ctx, n);
+    DevBuf<uint16_t> len_a(ctx, n);
+    DevBuf<uint32_t> cur_tile(ctx, nT + 1), cur_coarse(ctx, (int64_t)n_coarse * G + 1);
     auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15u) == 0; };
-    const int vec_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(cls) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
-    if (guard.flags) {
-      // speculative: the prepass and the histogram in one read of the columns
-      size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + 16 * (size_t)lm.n_chrom + sizeof(uint32_t) * (size_t)n_coarse;
-      CUDA_TRY(cudaFuncSetAttribute(tiled::k_prepass_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
-      const int pv_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(in.sample);
-      LAUNCH(ctx, tiled::k_prepass_hist, (unsigned)G, 1024, hsh, in.chrom, (const int32_t*)in.start, (const int32_t*)in.stop, in.sample, n, in.n_samples, lm, logw, (int)nT,
-             hist.p, coarse_cnt.p, n_coarse, pv_ok, spec->act_span, spec->flags);
+    if (src.narrow && dataset_offsets_match(src.ds, lm, src.ds ? src.ds->lay_pad : 0, logw, nT, G, n_coarse)) {
+      // everything up to the partition was done when the dataset was uploaded: the cursors start from its offsets
+      offS = src.ds->tile_off.p;
+      CUDA_TRY(cudaMemcpyAsync(cur_tile.p, src.ds->tile_off.p, 4 * (size_t)(nT + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(cur_coarse.p, src.ds->coarse_off.p, 4 * ((size_t)n_coarse * G + 1), cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-      size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + (lm.n_chrom <= 1024 ? 8 * (size_t)lm.n_chrom : 0) + sizeof(uint32_t) * (size_t)n_coarse;
-      CUDA_TRY(cudaFuncSetAttribute(tiled::k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
-      LAUNCH(ctx, tiled::k_tile_hist, (unsigned)G, 1024, hsh, in.chrom, in.start, in.coord_bits, cls, n, lm, logw, (int)nT, hist.p, coarse_cnt.p, n_coarse, vec_ok);
+      offS_own.alloc(ctx, nT + 1);
+      offS = offS_own.p;
+      if (src.narrow) {
+        tile_offsets_narrow(ctx, in, lm, logw, nT, G, n_coarse, offS_own.p, cur_coarse.p);
+      } else {
+        DevBuf<uint32_t> hist(ctx, nT + 1), coarse_cnt(ctx, (int64_t)n_coarse * G);
+        hist.zero();
+        const int vec_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(cls) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
+        if (guard.flags) {
+          // speculative: the prepass and the histogram in one read of the columns
+          size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + 16 * (size_t)lm.n_chrom + sizeof(uint32_t) * (size_t)n_coarse;
+          CUDA_TRY(cudaFuncSetAttribute(tiled::k_prepass_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
+          const int pv_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(in.sample);
+          LAUNCH(ctx, tiled::k_prepass_hist, (unsigned)G, 1024, hsh, in.chrom, (const int32_t*)in.start, (const int32_t*)in.stop, in.sample, n, in.n_samples, lm, logw, (int)nT,
+                 hist.p, coarse_cnt.p, n_coarse, pv_ok, spec->act_span, spec->flags);
+        } else {
+          size_t hsh = sizeof(uint32_t) * (size_t)((nT + 1) & ~1) + (lm.n_chrom <= 1024 ? 8 * (size_t)lm.n_chrom : 0) + sizeof(uint32_t) * (size_t)n_coarse;
+          CUDA_TRY(cudaFuncSetAttribute(tiled::k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsh));
+          LAUNCH(ctx, tiled::k_tile_hist, (unsigned)G, 1024, hsh, in.chrom, in.start, in.coord_bits, cls, n, lm, logw, (int)nT, hist.p, coarse_cnt.p, n_coarse, vec_ok);
+        }
+        device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, hist.p, offS_own.p, nT, offS_own.p + nT);
+        device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, coarse_cnt.p, cur_coarse.p, (int64_t)n_coarse * G, cur_coarse.p + (int64_t)n_coarse * G);
+      }
+      LAUNCH(ctx, tiled::k_init_cursors, grid_for(ctx, nT, 256), 256, 0, offS, (int)nT, cur_tile.p);
     }
-    device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, hist.p, offS.p, nT, offS.p + nT);
-    device_scan<uint32_t, uint32_t, OpSum<uint32_t>, false>(ctx, coarse_cnt.p, cur_coarse.p, (int64_t)n_coarse * G, cur_coarse.p + (int64_t)n_coarse * G);
-    LAUNCH(ctx, tiled::k_init_cursors, grid_for(ctx, nT, 256), 256, 0, offS.p, (int)nT, cur_tile.p);
     // the coarse pass runs whole multiples of G blocks, so that block x only sees input tiles of group x % G
     const unsigned mg_c = (unsigned)(G * std::max<int64_t>(1, std::min<int64_t>(16, ceil_div64(in_tiles, G))));
     const unsigned mg = (unsigned)std::min<int64_t>(in_tiles, (int64_t)ctx->num_sms * 16);
-    CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<true>()));
-    CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<false>()));
-    LAUNCH(ctx, tiled::k_multisplit<true>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<true>(), (const uint64_t*)nullptr, in.chrom, in.start, in.stop, in.coord_bits, cls, lm, cfg.B, n, 32 + logw + 8, cur_coarse.p, pk_a.p, vec_ok, G, guard);
-    LAUNCH(ctx, tiled::k_multisplit<false>, mg, tiled::MSP_THREADS, tiled::msp_smem_bytes<false>(), (const uint64_t*)pk_a.p, (const int32_t*)nullptr, (const void*)nullptr, (const void*)nullptr, 0, (const uint32_t*)nullptr, lm, cfg.B, n,
-           32 + logw, cur_tile.p, pk_b.p, 0, 1, guard);
-    P = pk_b.p;
+    tiled::MspIn mi;
+    memset(&mi, 0, sizeof mi);
+    tiled::MspOut mo;
+    mo.key = key_a.p; mo.len = len_a.p; mo.rec = nullptr;
+    if (src.narrow) {
+      mi.chrom8 = (const uint8_t*)in.chrom_narrow; mi.start = in.start; mi.len16 = (const uint16_t*)in.len_narrow; mi.bits = 32;
+      const int vec_ok = al16(in.chrom_narrow) && al16(in.start) && al16(in.len_narrow) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_NARROW>()));
+      LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_NARROW>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_NARROW>(), mi, lm, cfg.B, n, 32 + logw + 8, logw, cur_coarse.p, mo, vec_ok, G, guard);
+    } else {
+      mi.chrom = in.chrom; mi.start = in.start; mi.stop = in.stop; mi.bits = in.coord_bits; mi.cls = cls;
+      const int vec_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(cls) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_WIDE>()));
+      LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_WIDE>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_WIDE>(), mi, lm, cfg.B, n, 32 + logw + 8, logw, cur_coarse.p, mo, vec_ok, G, guard);
+    }
+    memset(&mi, 0, sizeof mi);
+    mi.key = key_a.p; mi.len = len_a.p;
+    mo.key = nullptr; mo.len = nullptr; mo.rec = rec.p;
+    CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_FINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_FINE>()));
+    LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_FINE>, mg, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_FINE>(), mi, lm, cfg.B, n, 32 + logw, logw, cur_tile.p, mo, 0, 1, guard);
   } else {
+    GMQL_REQUIRE(!src.narrow, GMQL_ERR_INVALID, "internal: the radix route of the tile path needs the wide columns");
+    DevBuf<uint64_t> pk_a(ctx, n), pk_b(ctx, n);
+    uint64_t* P64;
+    offS_own.alloc(ctx, nT + 1);
+    offS = offS_own.p;
     LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, pk_a.p);
-    radix_sort<uint64_t>(ctx, pk_a.p, pk_b.p, nullptr, nullptr, n, 32 + key_bits, &P, nullptr, 32 + logw);   // partition by tile only
-    LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, P, n, nT, logw, offS.p);
+    radix_sort<uint64_t>(ctx, pk_a.p, pk_b.p, nullptr, nullptr, n, 32 + key_bits, &P64, nullptr, 32 + logw);   // partition by tile only
+    LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, P64, n, nT, logw, offS_own.p);
+    LAUNCH(ctx, tiled::k_pack_rec32, grid_for(ctx, n, 256), 256, 0, (const uint64_t*)P64, n, logw, rec.p);
   }
+  const uint32_t* P = rec.p;
 
   // two resident blocks per SM; four ranges per resident block even out the tail.  Every block publishes its pieces in
   // its own segment of the piece tables, so they come out in genome order and nothing has to be sorted.
@@ -1209,7 +1272,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   // its predecessor's regions), at most four waves
   const int64_t resident = (int64_t)ctx->num_sms * tiled::CTAS_PER_SM;
   int64_t waves = std::max<int64_t>(1, std::min<int64_t>(4, (t_hi - t_lo + resident * 8) / (resident * 16)));
-  if (const char* we = getenv("GMQL_COVER_WAVES")) waves = std::max(1, atoi(we));   // tuning hook
+  if (const char* we = ctx_opt(ctx, "cover.waves")) waves = std::max(1, atoi(we));   // tuning hook
   const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), resident * waves));
   const int64_t seg = std::max<int64_t>(4096, (n / 16 + 2 * nT) / tgrid + 1);
   const int64_t cap = seg * tgrid;
@@ -1228,14 +1291,14 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
   if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc, guard);
+    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, pc, guard);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, (const uint2*)P, offS.p, t_lo, t_hi, logw, tc, pc, guard);
+    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, pc, guard);
   }
   unsigned long long h_np = 0;
   int h_fail = 0;
-  const char* stitch_env = getenv("GMQL_COVER_STITCH");   // "split": test hook, always the separate stitch kernels
+  const char* stitch_env = ctx_opt(ctx, "cover.stitch");   // "split": test hook, always the separate stitch kernels
   const bool fused = fo && !sb && !keep_runs && (int64_t)tgrid <= tiled::STITCH_MAXB && !(stitch_env && !strcmp(stitch_env, "split"));
   if (fused) {
     // few pieces (the usual case): one kernel from the pieces to the result columns, one synchronisation
@@ -1292,7 +1355,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     if (h_fail) return false;
   }
   const int64_t np = (int64_t)h_np;
-  pk_a.release(); pk_b.release();
+  rec.release();
 
   // pieces in genome order -> runs: fuse the ones that touch at a tile edge.  The number of runs (<= np) stays on the
   // device: the run tables are sized for np and the tail entries are dropped by the keep flags.
@@ -1331,9 +1394,9 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
 }
 
 template <typename K>
-static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_sample_group, int n_groups, int flag, const int32_t* h_mn, const int32_t* h_mx, int64_t B,
+static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_group, int n_groups, int flag, const int32_t* h_mn, const int32_t* h_mx, int64_t B,
                       const CovAggPlan& plan, const SpanTable& spans, bool unified, bool has_zero, int64_t maxlen, gmql_result* res, const ShardSpec* shard = nullptr,
-                      SpecCtx* spec = nullptr) {
+                      SpecCtx* spec = nullptr, TileSource src = TileSource()) {
   const int64_t n = in.n;
   CoverCfg cfg;
   cfg.n_groups = n_groups;
@@ -1356,6 +1419,8 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
   // class of every region (only materialised when there is more than one class)
   DevBuf<uint32_t> cls;
   if (n_classes_total > 1) {
+    gmql_ensure_wide(ctx, &in);
+    src.narrow = false;
     cls.alloc(ctx, n);
     if (n) LAUNCH(ctx, k_cover_classes, grid_for(ctx, n, 256), 256, 0, in.strand, in.sample, n, cfg, cls.p);
   }
@@ -1381,11 +1446,12 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     const double total = (double)(n_classes_total * lm.G);
     int logw = tiled::MAX_LOGW;
     while (logw > 8 && 2.0 * (double)n * (double)(1ull << logw) / total > tiled::CAP_EV / 2.5) --logw;
-    const char* force = getenv("GMQL_COVER_PATH");   // "tiled" / "sort": test hook; default = density heuristic
-    const char* flw = getenv("GMQL_COVER_LOGW");
+    const char* force = ctx_opt(ctx, "cover.path");   // "tiled" / "sort": test hook; default = density heuristic
+    const char* flw = ctx_opt(ctx, "cover.logw");
     if (flw) logw = atoi(flw);
     if (shard) logw = tiled::MAX_LOGW;                  // shards are cut on 65 536-position tiles
-    bool fits = logw >= 8 && logw <= tiled::MAX_LOGW && maxlen < (int64_t)(1ll << logw) - 2;
+    bool fits = logw >= 8 && logw <= tiled::MAX_LOGW && maxlen < (int64_t)(1ll << logw) - 2 && maxlen <= tiled::MAX_REGION_LEN;
+    if (src.narrow && (int64_t)((n_classes_total * lm.G) >> logw) + 1 > tiled::HIST_CAP) { gmql_ensure_wide(ctx, &in); src.narrow = false; }   // radix route reads the wide columns
     bool want = fits && (double)n * (double)(1ull << logw) / total >= 256.0;   // enough regions per tile for the tile pass to pay
     if (force && !strcmp(force, "tiled")) want = fits;
     if (force && !strcmp(force, "sort")) want = false;
@@ -1397,7 +1463,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
       const int lw = logw - 2 * attempt;
       if (lw < 8 || maxlen >= (int64_t)(1ll << lw) - 2) break;
       done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr, plan.n_aggs ? &truns : nullptr,
-                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr, spec);
+                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr, spec, src);
       if (spec) {
         if (spec->tripped) return;                     // not eligible after all: the caller starts over with a blocking prepass
         maxlen = spec->h_flags[3];                     // the flags are on the host now: later attempts (and the sort path) are ordinary
@@ -1406,6 +1472,7 @@ static void run_cover(gmql_ctx* ctx, const DevRegions& in, const int32_t* h_samp
     }
   } else if (spec) { spec->declined = true; return; }
 
+  if (!done || plan.n_aggs) gmql_ensure_wide(ctx, &in);   // everything below reads the int32 / int64 columns
   if (done && plan.n_aggs) {
     // value aggregates of the tile-resident path: region-driven post-pass over the runs
     const int64_t nr = nc;
@@ -1619,6 +1686,47 @@ extern "C" int gmql_cover_count_samples(gmql_ctx* ctx, const gmql_regions* in, i
   }
 }
 
+// a SpanTable whose device arrays belong to somebody else (a resident dataset's layout): the DevBufs are pointed at them for the
+// duration of the call and detached again, so nothing is freed twice
+struct LinMapBorrow {
+  SpanTable* t;
+  LinMapBorrow(SpanTable* tab, uint64_t* coff, unsigned long long* span) : t(tab) { t->coff.p = coff; t->span.p = span; }
+  ~LinMapBorrow() { t->coff.detach(); t->span.detach(); }
+};
+
+// The linear layout of a resident dataset for BinSize.Cover = bin_size and what the tile path's partition needs before it can
+// start: tile_off (first record of every 65 536-position tile) and coarse_off (start of every (coarse bin, input-tile group) range).
+// Called by gmql_dataset_upload, and again by gmql_cover when an operator uses another bin size.
+void gmql_cover_prepare_dataset(gmql_ctx* ctx, gmql_dataset* ds, int64_t bin_size) {
+  const DevRegions& dv = ds->dev;
+  ds->tile_off.release(); ds->coarse_off.release(); ds->lay_coff.release(); ds->lay_span.release();
+  ds->lay_pad = 0; ds->lay_G = 0; ds->hist_nT = 0;
+  if (!ds->stats_ok || ds->span_hint.empty() || dv.n <= 0) return;
+  const int nc = dv.n_chrom;
+  const uint64_t pad = (uint64_t)bin_size + 2ull;
+  unsigned long long* hs = (unsigned long long*)ctx_pinned(ctx, 8 * (size_t)nc);
+  uint64_t* hc = (uint64_t*)ctx_pinned(ctx, 8 * ((size_t)nc + 1));
+  uint64_t run = 0;
+  for (int c = 0; c < nc; ++c) { hs[c] = (unsigned long long)ds->span_hint[c]; hc[c] = run; run += hs[c] + pad; }
+  hc[nc] = run;
+  ds->lay_coff.alloc(ctx, nc + 1); ds->lay_span.alloc(ctx, nc);
+  CUDA_TRY(cudaMemcpyAsync(ds->lay_span.p, hs, 8 * (size_t)nc, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ds->lay_coff.p, hc, 8 * ((size_t)nc + 1), cudaMemcpyHostToDevice, ctx->stream));
+  ds->lay_pad = pad; ds->lay_G = run;
+  // the partition offsets only for what the tile path's fast route accepts
+  const int logw = tiled::MAX_LOGW;
+  const int64_t nT = (int64_t)(run >> logw) + 1;
+  if (!(dv.coord_bits == 32 && dv.chrom_narrow && dv.chrom_bits == 8 && dv.len_narrow && dv.len_bits == 16 && ds->has_star && !ds->has_zero &&
+        ds->maxlen <= tiled::MAX_REGION_LEN && run + 2ull * (1ull << logw) < 0xffffffffull && nT <= tiled::HIST_CAP)) return;
+  const int n_coarse = (int)((nT + 255) >> 8) + 1;
+  const int64_t in_tiles = ceil_div64(dv.n, tiled::MSP_TILE);
+  const int G = (int)std::max<int64_t>(1, std::min<int64_t>(in_tiles, (int64_t)ctx->num_sms));
+  ds->tile_off.alloc(ctx, nT + 1); ds->coarse_off.alloc(ctx, (int64_t)n_coarse * G + 1);
+  LinMap lm; lm.coff = ds->lay_coff.p; lm.span = (const int64_t*)ds->lay_span.p; lm.G = run; lm.n_chrom = nc;
+  tile_offsets_narrow(ctx, dv, lm, logw, nT, G, n_coarse, ds->tile_off.p, ds->coarse_off.p);
+  ds->hist_nT = nT; ds->hist_groups = G; ds->hist_n_coarse = n_coarse;
+}
+
 static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups, int32_t flag,
                       const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size, const gmql_agg* aggs, int32_t n_aggs,
                       const gmql_cover_shard_t* shard, gmql_result** out) {
@@ -1627,7 +1735,7 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
-    ctx->pin_next = 0;
+    ctx_begin_call(ctx);
     gmql_trace("ENTER gmql_cover");
     GMQL_REQUIRE(in != nullptr, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_groups >= 1 && min_acc && max_acc, GMQL_ERR_INVALID, "n_groups >= 1 and per-group thresholds are required");
@@ -1645,15 +1753,44 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
     plan_cov_aggs(aggs, n_aggs, in->n_cols, &plan, &need_cols);
     cudaEventRecord(ctx->ev_h0, ctx->stream);
     DevRegions d;
-    gmql_upload_regions(ctx, in, need_cols, &d);
+    gmql_upload_regions(ctx, in, need_cols, &d, /*keep_narrow=*/true);
     cudaEventRecord(ctx->ev_h1, ctx->stream);
     cudaEventRecord(ctx->ev_k0, ctx->stream);
+    // Resident dataset in the narrow encodings (uint8 chromosome, int32 start, uint16 length; strands unified) whose upload-time
+    // statistics say it is eligible for the tile path: no pass over the data is needed to decide anything, the linear layout and
+    // the partition offsets come from the dataset, and the operator starts at the partition itself, reading 7 bytes per region.
+    {
+      gmql_dataset* ds = d.dataset;
+      const char* spec_opt = ctx_opt(ctx, "cover.speculate");   // "0": test hook (the generic route)
+      if (ds && ds->stats_ok && !ds->span_hint.empty() && in->chrom_span_hint == ds->span_hint.data() && !shard && d.n > 0 && d.coord_bits == 32 && d.chrom_narrow &&
+          d.chrom_bits == 8 && d.len_narrow && d.len_bits == 16 && ds->has_star /* strands unify to '*': the column, if any, is not read */ && n_groups == 1 && plan.n_aggs == 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) &&
+          !ds->has_zero && ds->maxlen <= tiled::MAX_REGION_LEN && !(spec_opt && spec_opt[0] == '0')) {
+        if (ds->lay_pad != (uint64_t)bin_size + 2ull) gmql_cover_prepare_dataset(ctx, ds, bin_size);   // another BinSize.Cover than the upload assumed
+        if (ds->lay_coff.p && ds->lay_G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
+          SpanTable hs;                                       // borrowed views of the dataset's layout
+          hs.n_chrom = d.n_chrom; hs.G = ds->lay_G;
+          LinMapBorrow lb(&hs, ds->lay_coff.p, ds->lay_span.p);
+          res = new gmql_result();
+          res->owner = ctx;
+          TileSource src;
+          src.narrow = true; src.ds = ds;
+          run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, hs, /*unified=*/true, /*has_zero=*/false, ds->maxlen, res, nullptr, nullptr, src);
+          res->span_hint.resize((size_t)d.n_chrom);
+          for (int c = 0; c < d.n_chrom; ++c) res->span_hint[c] = ds->span_hint[c] + 1;   // results may carry the one-base extension
+          CUDA_TRY(GMQL_SYNC_IF_PENDING(ctx));
+          *out = res;
+          gmql_trace("EXIT");
+          return GMQL_OK;
+        }
+      }
+    }
+    gmql_ensure_wide(ctx, &d);
     // Speculative launch: the caller knows an upper bound of every chromosome's span (chrom_span_hint), so the linear layout is
     // fixed before any data is read and the tile pipeline is queued at once behind a fused prepass + histogram kernel; the
     // prepass flags come back with the pipeline's one synchronisation.  One (group, strand) class, 32-bit coordinates, no
     // strand column, COVER / FLAT without aggregates; anything else, and any input that turns out not to be eligible, takes
     // the ordinary route below.
-    const char* spec_env = getenv("GMQL_COVER_SPECULATE");   // "0": test hook
+    const char* spec_env = ctx_opt(ctx, "cover.speculate");   // "0": test hook
     if (in->chrom_span_hint && !shard && d.n > 0 && d.coord_bits == 32 && d.strand == nullptr && n_groups == 1 && plan.n_aggs == 0 &&
         (flag == GMQL_COVER || flag == GMQL_FLAT) && !(spec_env && spec_env[0] == '0')) {
       SpanTable hs;
@@ -1667,6 +1804,7 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
         sc.h_flags = (int*)ctx_pinned(ctx, 4 * sizeof(int));
         sc.h_span = (unsigned long long*)ctx_pinned(ctx, 8 * (size_t)d.n_chrom);
         res = new gmql_result();
+    res->owner = ctx;
         run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, hs, /*unified=*/true, /*has_zero=*/false, /*maxlen=*/0, res, nullptr, &sc);
         if (!sc.declined && !sc.tripped) {
           res->span_hint.resize((size_t)d.n_chrom);
@@ -1727,6 +1865,7 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
     bool unified = force_unified || ins.has_star != 0 || d.strand == nullptr || d.n == 0;   // assignGroups (:328-341)
     uint64_t total = (uint64_t)n_groups * (unified ? 1ull : 2ull) * spans.G;
     res = new gmql_result();
+    res->owner = ctx;
     res->span_hint.resize((size_t)d.n_chrom);
     for (int c = 0; c < d.n_chrom; ++c) res->span_hint[c] = (int64_t)h_span[c] + 1;   // results may carry the one-base extension
     if (shard) GMQL_REQUIRE(unified && n_groups == 1 && total < 0xffffffffull, GMQL_ERR_UNSUPPORTED, "gmql_cover_shard: one group, unified strands and a linear genome below 2^32 are required");

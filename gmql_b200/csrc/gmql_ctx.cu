@@ -24,11 +24,20 @@ extern "C" int gmql_ctx_create(int device, void* stream, gmql_ctx** out) {
     CUDA_TRY(cudaEventCreate(&c->ev_k1));
     CUDA_TRY(cudaEventCreate(&c->ev_h0));
     CUDA_TRY(cudaEventCreate(&c->ev_h1));
-    // keep freed blocks cached in the stream-ordered pool (operators allocate scratch every call)
-    cudaMemPool_t pool;
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    // a private stream-ordered pool (the process's default pool is left alone: other allocators of the host process are not
+    // starved by what this library keeps cached); released blocks stay in it until gmql_ctx_destroy
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CUDA_TRY(cudaMemPoolCreate(&c->pool, &props));
     uint64_t thr = ~0ull;
-    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    CUDA_TRY(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    c->arena_limit = total_b / 4;
   } catch (const gmql_error& ex) {
     delete c;
     return ex.code;
@@ -41,22 +50,48 @@ extern "C" void gmql_ctx_destroy(gmql_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (auto* d : c->datasets) if (d) d->owner = nullptr;   // datasets / results must be freed before their context (header)
+  arena_trim(c);
+  cudaStreamSynchronize(c->stream);
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   if (c->ev_k0) cudaEventDestroy(c->ev_k0);
   if (c->ev_k1) cudaEventDestroy(c->ev_k1);
   if (c->ev_h0) cudaEventDestroy(c->ev_h0);
   if (c->ev_h1) cudaEventDestroy(c->ev_h1);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (auto& pin : c->pins) if (pin.first) cudaFreeHost(pin.first);
+  if (c->h_defer) cudaFreeHost(c->h_defer);
   delete c;
 }
 
 extern "C" const char* gmql_last_error(const gmql_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
+extern "C" int gmql_ctx_set_option(gmql_ctx* c, const char* name, const char* value) {
+  if (!c || !name) return GMQL_ERR_INVALID;
+  static const char* known[] = {"cover.path", "cover.logw", "cover.waves", "cover.stitch", "cover.speculate", "cover.kernel", "map.index", "map.grouped",
+                                "defer_check", nullptr};
+  bool ok = false;
+  for (int k = 0; known[k]; ++k) if (!strcmp(known[k], name)) ok = true;
+  if (!ok) { c->err = std::string("unknown option: ") + name; return GMQL_ERR_INVALID; }
+  if (value && *value) c->options[name] = value; else c->options.erase(name);
+  return GMQL_OK;
+}
+
+// flags of operators that returned without their last synchronisation (option "defer_check"); call with the stream idle
+int gmql_check_deferred(gmql_ctx* c) {
+  int rc = GMQL_OK;
+  for (auto& d : c->deferred)
+    if (*d.h_flag) { c->err = std::string("deferred check of an earlier call failed: ") + d.what; rc = GMQL_ERR_INVALID; }
+  c->deferred.clear();
+  return rc;
+}
+
 extern "C" int gmql_ctx_sync(gmql_ctx* c) {
   if (!c) return GMQL_ERR_INVALID;
   cudaError_t e = cudaStreamSynchronize(c->stream);
+  c->pending = false;
   if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return GMQL_ERR_CUDA; }
-  return GMQL_OK;
+  return gmql_check_deferred(c);
 }
 
 extern "C" int64_t gmql_ctx_launch_count(const gmql_ctx* c) { return c ? c->launches : 0; }
@@ -115,7 +150,15 @@ static __global__ void k_expand_sample_offsets(const int64_t* __restrict__ off, 
   }
 }
 
-void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector<int>& need_cols, DevRegions* out) {
+// the dataset whose resident arrays a device-located gmql_regions points at (views made by gmql_dataset_upload), or null
+static gmql_dataset* find_dataset(gmql_ctx* ctx, const gmql_regions* r) {
+  if (r->location != GMQL_LOC_DEVICE || !r->start) return nullptr;
+  for (auto* d : ctx->datasets)
+    if (d && d->dev.start == r->start && d->dev.n == r->n && d->dev.coord_bits == r->coord_bits) return d;
+  return nullptr;
+}
+
+void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector<int>& need_cols, DevRegions* out, bool keep_narrow) {
   GMQL_REQUIRE(r != nullptr, GMQL_ERR_INVALID, "null gmql_regions");
   GMQL_REQUIRE(r->n >= 0 && r->n < (int64_t)0x7fffffff, GMQL_ERR_UNSUPPORTED, "datasets of >= 2^31 regions are not supported in this version");
   GMQL_REQUIRE(r->coord_bits == 32 || r->coord_bits == 64, GMQL_ERR_INVALID, "coord_bits must be 32 or 64");
@@ -128,72 +171,65 @@ void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector
   out->n_cols = r->n_cols;
   out->span_hint = r->chrom_span_hint;
   out->sorted_hint = r->sorted_by_position != 0;
+  gmql_dataset* ds = find_dataset(ctx, r);
+  out->dataset = ds;
   size_t cb = (size_t)(r->coord_bits / 8);
   size_t n = (size_t)r->n;
   GMQL_REQUIRE(r->chrom_bits == 0 || r->chrom_bits == 8 || r->chrom_bits == 16 || r->chrom_bits == 32, GMQL_ERR_INVALID, "chrom_bits must be 0, 8, 16 or 32");
+  out->wide_ready = true;
   if (r->chrom_bits == 8 || r->chrom_bits == 16) {
     GMQL_REQUIRE(r->n_chrom <= (r->chrom_bits == 8 ? 256 : 65536), GMQL_ERR_INVALID, "n_chrom does not fit chrom_bits");
-    const size_t cw = (size_t)(r->chrom_bits / 8);
-    const void* raw = upload_array(ctx, r->chrom, n * cw, r->location, out);
-    DevBuf<uint8_t> wide(ctx, (int64_t)(n * 4 ? n * 4 : 1));
-    if (n) {
-      int g = (int)std::min<int64_t>(ceil_div64((int64_t)n, 256 * 4), (int64_t)ctx->num_sms * 16);
-      if (r->chrom_bits == 8) LAUNCH(ctx, (k_widen_chrom<uint8_t>), g, 256, 0, (const uint8_t*)raw, (int64_t)n, (int32_t*)wide.p);
-      else LAUNCH(ctx, (k_widen_chrom<uint16_t>), g, 256, 0, (const uint16_t*)raw, (int64_t)n, (int32_t*)wide.p);
-    }
-    out->chrom = (const int32_t*)wide.p;
-    if (r->location != GMQL_LOC_DEVICE) out->owned.pop_back();   // the narrow copy is released in stream order
-    out->owned.push_back(std::move(wide));
+    out->chrom_narrow = upload_array(ctx, r->chrom, n * (size_t)(r->chrom_bits / 8), r->location, out);
+    out->chrom_bits = r->chrom_bits;
+    out->chrom = nullptr;
+    out->wide_ready = false;
   } else {
     out->chrom = (const int32_t*)upload_array(ctx, r->chrom, n * 4, r->location, out);
   }
   out->start = upload_array(ctx, r->start, n * cb, r->location, out);
   GMQL_REQUIRE(r->stop_is_length == 0 || r->stop_is_length == 16 || r->stop_is_length == 32, GMQL_ERR_INVALID, "stop_is_length must be 0, 16 or 32");
   if (r->stop_is_length) {
-    const size_t lw = (size_t)(r->stop_is_length / 8);
-    const void* raw = upload_array(ctx, r->stop, n * lw, r->location, out);
-    DevBuf<uint8_t> full(ctx, (int64_t)(n * cb ? n * cb : 1));
-    if (n) {
-      int g = (int)std::min<int64_t>(ceil_div64((int64_t)n, 256 * 4), (int64_t)ctx->num_sms * 16);
-      if (cb == 4 && lw == 2) LAUNCH(ctx, (k_stop_from_length<int32_t, uint16_t>), g, 256, 0, (const int32_t*)out->start, (const uint16_t*)raw, (int64_t)n, (int32_t*)full.p);
-      else if (cb == 4) LAUNCH(ctx, (k_stop_from_length<int32_t, uint32_t>), g, 256, 0, (const int32_t*)out->start, (const uint32_t*)raw, (int64_t)n, (int32_t*)full.p);
-      else if (lw == 2) LAUNCH(ctx, (k_stop_from_length<int64_t, uint16_t>), g, 256, 0, (const int64_t*)out->start, (const uint16_t*)raw, (int64_t)n, (int64_t*)full.p);
-      else LAUNCH(ctx, (k_stop_from_length<int64_t, uint32_t>), g, 256, 0, (const int64_t*)out->start, (const uint32_t*)raw, (int64_t)n, (int64_t*)full.p);
-    }
-    out->stop = full.p;
-    if (r->location != GMQL_LOC_DEVICE) out->owned.pop_back();   // the length copy is released in stream order
-    out->owned.push_back(std::move(full));
+    out->len_narrow = upload_array(ctx, r->stop, n * (size_t)(r->stop_is_length / 8), r->location, out);
+    out->len_bits = r->stop_is_length;
+    out->stop = nullptr;
+    out->wide_ready = false;
   } else {
     out->stop = upload_array(ctx, r->stop, n * cb, r->location, out);
   }
   out->strand = (const int8_t*)upload_array(ctx, r->strand, n, r->location, out);
+  out->host_sample_col = r->sample != nullptr;
   if (r->sample_offsets) {
     // rows grouped by sample.  Without a sample column the offsets define it; with one they are a promise about its
     // layout, which the kernels that rely on it check against the column.
     const int64_t* off = r->sample_offsets;   // host array by contract
-    GMQL_REQUIRE(off[0] == 0 && off[r->n_samples] == r->n, GMQL_ERR_INVALID, "sample_offsets must start at 0 and end at n");
-    int64_t widest = 0;
-    for (int s = 0; s < r->n_samples; ++s) {
-      GMQL_REQUIRE(off[s] <= off[s + 1], GMQL_ERR_INVALID, "sample_offsets must be non-decreasing");
-      widest = std::max<int64_t>(widest, off[s + 1] - off[s]);
+    if (ds && !ds->sample_offsets.empty() && off == ds->sample_offsets.data()) {
+      out->sample_off = ds->dev.sample_off;    // validated and uploaded once, with the dataset
+      out->max_sample_rows = ds->dev.max_sample_rows;
+    } else {
+      GMQL_REQUIRE(off[0] == 0 && off[r->n_samples] == r->n, GMQL_ERR_INVALID, "sample_offsets must start at 0 and end at n");
+      int64_t widest = 0;
+      for (int s = 0; s < r->n_samples; ++s) {
+        GMQL_REQUIRE(off[s] <= off[s + 1], GMQL_ERR_INVALID, "sample_offsets must be non-decreasing");
+        widest = std::max<int64_t>(widest, off[s + 1] - off[s]);
+      }
+      const size_t ob = 8 * ((size_t)r->n_samples + 1);
+      DevBuf<uint8_t> doff(ctx, (int64_t)ob);
+      int64_t* h_off = (int64_t*)ctx_pinned(ctx, ob);
+      memcpy(h_off, off, ob);
+      CUDA_TRY(cudaMemcpyAsync(doff.p, h_off, ob, cudaMemcpyHostToDevice, ctx->stream));
+      if (r->location != GMQL_LOC_DEVICE) out->h2d_bytes += (int64_t)ob;
+      out->sample_off = (const int64_t*)doff.p;
+      out->max_sample_rows = widest;
+      out->owned.push_back(std::move(doff));
     }
-    const size_t ob = 8 * ((size_t)r->n_samples + 1);
-    DevBuf<uint8_t> doff(ctx, (int64_t)ob);
-    CUDA_TRY(cudaMemcpyAsync(doff.p, off, ob, cudaMemcpyHostToDevice, ctx->stream));   // small pageable source: staged by the driver before the call returns
-    if (r->location != GMQL_LOC_DEVICE) out->h2d_bytes += (int64_t)ob;
-    out->sample_off = (const int64_t*)doff.p;
-    out->max_sample_rows = widest;
     for (const auto& tg : ctx->trusted_groupings) if (tg.first == (const void*)r->sample && tg.second == (const void*)r->sample_offsets && r->sample) out->sample_trusted = true;
     if (!r->sample) {
       out->sample_trusted = true;
-      DevBuf<uint8_t> smp(ctx, (int64_t)(n * 4 ? n * 4 : 1));
-      if (n) LAUNCH(ctx, k_expand_sample_offsets, (int)std::min<int64_t>(r->n_samples, (int64_t)ctx->num_sms * 16), 256, 0, (const int64_t*)doff.p, r->n_samples, (int32_t*)smp.p);
-      out->sample = (const int32_t*)smp.p;
-      out->owned.push_back(std::move(smp));
+      out->sample = nullptr;
+      out->wide_ready = false;
     } else {
       out->sample = (const int32_t*)upload_array(ctx, r->sample, n * 4, r->location, out);
     }
-    out->owned.push_back(std::move(doff));
   } else {
     out->sample = (const int32_t*)upload_array(ctx, r->sample, n * 4, r->location, out);
   }
@@ -206,6 +242,57 @@ void gmql_upload_regions(gmql_ctx* ctx, const gmql_regions* r, const std::vector
     out->cols[c] = (const double*)upload_array(ctx, r->cols[c], n * 8, r->location, out);
     if (r->valid && r->valid[c]) out->valid[c] = (const uint8_t*)upload_array(ctx, r->valid[c], n, r->location, out);
   }
+  if (!keep_narrow) gmql_ensure_wide(ctx, out);
+}
+
+// int32 chromosome indices, stop coordinates and the per-row sample column of a dataset that arrived in the narrow encodings.
+// For a resident dataset they are materialised once and kept with it; otherwise they live as long as `d`.
+void gmql_ensure_wide(gmql_ctx* ctx, DevRegions* d) {
+  if (d->wide_ready) return;
+  const int64_t n = d->n;
+  gmql_dataset* ds = d->dataset;
+  if (ds && ds->wide_done) {
+    if (!d->chrom) d->chrom = (const int32_t*)ds->wide_chrom.p;
+    if (!d->stop) d->stop = ds->wide_stop.p;
+    if (!d->sample && d->sample_off) d->sample = (const int32_t*)ds->wide_sample.p;
+    d->wide_ready = true;
+    return;
+  }
+  const size_t cb = (size_t)(d->coord_bits / 8);
+  const int g = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, 256 * 4), (int64_t)ctx->num_sms * 16));
+  DevBuf<uint8_t> wc, ws, wm;
+  if (!d->chrom && d->chrom_narrow) {
+    wc.alloc(ctx, (int64_t)(n * 4 ? n * 4 : 1));
+    if (n) {
+      if (d->chrom_bits == 8) LAUNCH(ctx, (k_widen_chrom<uint8_t>), g, 256, 0, (const uint8_t*)d->chrom_narrow, n, (int32_t*)wc.p);
+      else LAUNCH(ctx, (k_widen_chrom<uint16_t>), g, 256, 0, (const uint16_t*)d->chrom_narrow, n, (int32_t*)wc.p);
+    }
+    d->chrom = (const int32_t*)wc.p;
+  }
+  if (!d->stop && d->len_narrow) {
+    ws.alloc(ctx, (int64_t)((size_t)n * cb ? (size_t)n * cb : 1));
+    if (n) {
+      if (cb == 4 && d->len_bits == 16) LAUNCH(ctx, (k_stop_from_length<int32_t, uint16_t>), g, 256, 0, (const int32_t*)d->start, (const uint16_t*)d->len_narrow, n, (int32_t*)ws.p);
+      else if (cb == 4) LAUNCH(ctx, (k_stop_from_length<int32_t, uint32_t>), g, 256, 0, (const int32_t*)d->start, (const uint32_t*)d->len_narrow, n, (int32_t*)ws.p);
+      else if (d->len_bits == 16) LAUNCH(ctx, (k_stop_from_length<int64_t, uint16_t>), g, 256, 0, (const int64_t*)d->start, (const uint16_t*)d->len_narrow, n, (int64_t*)ws.p);
+      else LAUNCH(ctx, (k_stop_from_length<int64_t, uint32_t>), g, 256, 0, (const int64_t*)d->start, (const uint32_t*)d->len_narrow, n, (int64_t*)ws.p);
+    }
+    d->stop = ws.p;
+  }
+  if (!d->sample && d->sample_off) {
+    wm.alloc(ctx, (int64_t)(n * 4 ? n * 4 : 1));
+    if (n) LAUNCH(ctx, k_expand_sample_offsets, (int)std::min<int64_t>(d->n_samples, (int64_t)ctx->num_sms * 16), 256, 0, d->sample_off, d->n_samples, (int32_t*)wm.p);
+    d->sample = (const int32_t*)wm.p;
+  }
+  if (ds) {
+    ds->wide_chrom = std::move(wc); ds->wide_stop = std::move(ws); ds->wide_sample = std::move(wm);
+    ds->wide_done = true;
+  } else {
+    if (wc.p) d->owned.push_back(std::move(wc));
+    if (ws.p) d->owned.push_back(std::move(ws));
+    if (wm.p) d->owned.push_back(std::move(wm));
+  }
+  d->wide_ready = true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -235,7 +322,9 @@ extern "C" int gmql_result_column_copy(gmql_ctx* ctx, const gmql_result* r, int3
     if (!dst) { ctx->err = "null destination"; return GMQL_ERR_INVALID; }
     cudaError_t e = cudaMemcpyAsync(dst, it->second.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    ctx->pending = false;
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return GMQL_ERR_CUDA; }
+    if (!ctx->deferred.empty()) return gmql_check_deferred(ctx);
   }
   return GMQL_OK;
 }
@@ -243,22 +332,67 @@ extern "C" int gmql_result_column_copy(gmql_ctx* ctx, const gmql_result* r, int3
 extern "C" void gmql_result_free(gmql_ctx* ctx, gmql_result* r) {
   if (!r) return;
   gmql_trace("result_free");
+  gmql_ctx* owner = r->owner ? r->owner : ctx;
   for (auto& kv : r->cols)
-    if (kv.second.p) { if (ctx) cudaFreeAsync(kv.second.p, ctx->stream); else cudaFree(kv.second.p); }
-  if (r->view_acc_double) { if (ctx) cudaFreeAsync(r->view_acc_double, ctx->stream); else cudaFree(r->view_acc_double); }
+    if (kv.second.p) { if (owner) ctx_free(owner, kv.second.p); else cudaFree(kv.second.p); }
+  if (r->view_acc_double) { if (owner) ctx_free(owner, r->view_acc_double); else cudaFree(r->view_acc_double); }
   delete r;
 }
 
 // ------------------------------------------------------------------------------------------------
-struct gmql_dataset {
-  DevRegions dev;
-  std::vector<int64_t> sample_ids;
-  std::vector<int64_t> sample_offsets;   // host copy when the upload declared the rows grouped by sample
-  gmql_ctx* owner = nullptr;             // context holding this dataset's trusted-grouping entry
-  std::vector<int64_t> span_hint;        // largest stop per chromosome, computed at upload when the caller gave no hint
-  std::vector<const double*> cols;
-  std::vector<const uint8_t*> valid;
-};
+// Upload-time statistics of a dataset, in ONE read of its arrays in whatever encoding they arrived: largest stop per chromosome
+// (the linear layout every operator derives), longest region, "a zero-length region exists", "a '*' strand exists", and row
+// validity (chromosome / sample index in range, 0 <= start <= stop, strand code, no 32-bit overflow of start + length).
+static __global__ void __launch_bounds__(256) k_dataset_stats(const void* __restrict__ chrom, int chrom_bits, const void* __restrict__ start, int bits, const void* __restrict__ stop_or_len,
+                                                              int len_bits, const int8_t* __restrict__ strand, const int32_t* __restrict__ sample, int64_t n, int n_chrom, int n_samples,
+                                                              unsigned long long* __restrict__ span, int* __restrict__ flags /* [0] '*' seen, [1] zero-length, [2] bad row, [3] longest (clamped) */) {
+  extern __shared__ unsigned long long sspan[];
+  const bool use_sh = n_chrom <= 4096;
+  if (use_sh) {
+    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) sspan[c] = 0ull;
+    __syncthreads();
+  }
+  int has_star = 0, zero = 0, bad = 0;
+  long long maxlen = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = chrom_bits == 8 ? (int)((const uint8_t*)chrom)[i] : (chrom_bits == 16 ? (int)((const uint16_t*)chrom)[i] : ((const int32_t*)chrom)[i]);
+    const int64_t s = ld_coord(start, bits, i);
+    int64_t e;
+    if (len_bits == 16) e = s + (int64_t)((const uint16_t*)stop_or_len)[i];
+    else if (len_bits == 32) e = s + (int64_t)((const uint32_t*)stop_or_len)[i];
+    else e = ld_coord(stop_or_len, bits, i);
+    const int st = strand ? (int)strand[i] : 0;
+    const int sm = sample ? sample[i] : 0;
+    if (st == 0) has_star = 1;
+    if (c < 0 || c >= n_chrom || s < 0 || s > e || st < 0 || st > 2 || sm < 0 || sm >= n_samples || (bits == 32 && e > 0x7fffffffLL)) { bad = 1; continue; }
+    if (s == e) zero = 1;
+    if (e - s > maxlen) maxlen = e - s;
+    if (use_sh) atomicMax(&sspan[c], (unsigned long long)e); else atomicMax(&span[c], (unsigned long long)e);
+  }
+  __shared__ int s_fl[4];
+  if (threadIdx.x < 4) s_fl[threadIdx.x] = 0;
+  __syncthreads();
+  {
+    int ml = maxlen > 0x7fffffffLL ? 0x7fffffff : (int)maxlen;
+    ml = __reduce_max_sync(0xffffffffu, ml);
+    const bool a0 = __any_sync(0xffffffffu, has_star), a1 = __any_sync(0xffffffffu, zero), a2 = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      if (a0) s_fl[0] = 1;
+      if (a1) s_fl[1] = 1;
+      if (a2) s_fl[2] = 1;
+      if (ml > 0) atomicMax(&s_fl[3], ml);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                                  // one store / RED per block and flag
+    if (s_fl[0]) flags[0] = 1;
+    if (s_fl[1]) flags[1] = 1;
+    if (s_fl[2]) flags[2] = 1;
+    if (s_fl[3] > 0) atomicMax(&flags[3], s_fl[3]);
+  }
+  if (use_sh)
+    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) if (sspan[c]) atomicMax(&span[c], sspan[c]);
+}
 
 extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql_dataset** out, gmql_regions* view) {
   if (!ctx || !host || !out || !view) return GMQL_ERR_INVALID;
@@ -266,55 +400,75 @@ extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql
   gmql_dataset* d = new gmql_dataset();
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx_begin_call(ctx);
     std::vector<int> all;
     for (int c = 0; c < host->n_cols; ++c) all.push_back(c);
     cudaEventRecord(ctx->ev_h0, ctx->stream);
-    gmql_upload_regions(ctx, host, all, &d->dev);
+    gmql_upload_regions(ctx, host, all, &d->dev, /*keep_narrow=*/true);   // the narrow encodings stay resident as they arrived
     cudaEventRecord(ctx->ev_h1, ctx->stream);
+    d->owner = ctx;
     if (host->sample_ids) d->sample_ids.assign(host->sample_ids, host->sample_ids + host->n_samples);
     else d->sample_ids.assign((size_t)host->n_samples, 0);
     d->cols = d->dev.cols;
     d->valid = d->dev.valid;
+    const DevRegions& dv = d->dev;
     memset(view, 0, sizeof *view);
-    view->n = d->dev.n;
+    view->n = dv.n;
     view->location = GMQL_LOC_DEVICE;
-    view->coord_bits = d->dev.coord_bits;
-    view->chrom = d->dev.chrom;
-    view->start = d->dev.start;
-    view->stop = d->dev.stop;
-    view->strand = d->dev.strand;
-    view->sample = d->dev.sample;
+    view->coord_bits = dv.coord_bits;
+    view->chrom = dv.chrom_narrow ? (const int32_t*)dv.chrom_narrow : dv.chrom;
+    view->chrom_bits = dv.chrom_narrow ? dv.chrom_bits : 0;
+    view->start = dv.start;
+    view->stop = dv.len_narrow ? dv.len_narrow : dv.stop;
+    view->stop_is_length = dv.len_narrow ? dv.len_bits : 0;
+    view->strand = dv.strand;
+    view->sample = dv.sample;             // null when the upload had sample_offsets only
     if (host->sample_offsets) {
       d->sample_offsets.assign(host->sample_offsets, host->sample_offsets + host->n_samples + 1);
       view->sample_offsets = d->sample_offsets.data();   // the view keeps the promise: rows grouped by sample
-      if (d->dev.sample_trusted) { ctx->trusted_groupings.push_back(std::make_pair((const void*)d->dev.sample, (const void*)d->sample_offsets.data())); d->owner = ctx; }
+      if (dv.sample && dv.sample_trusted) ctx->trusted_groupings.push_back(std::make_pair((const void*)dv.sample, (const void*)d->sample_offsets.data()));
     }
-    view->n_chrom = d->dev.n_chrom;
-    view->n_samples = d->dev.n_samples;
+    view->n_chrom = dv.n_chrom;
+    view->n_samples = dv.n_samples;
     view->sample_ids = d->sample_ids.data();
-    view->n_cols = d->dev.n_cols;
+    view->n_cols = dv.n_cols;
     view->cols = d->cols.empty() ? nullptr : d->cols.data();
     view->valid = d->valid.empty() ? nullptr : d->valid.data();
-    view->dup_of = d->dev.dup_of;
+    view->dup_of = dv.dup_of;
     view->chrom_span_hint = host->chrom_span_hint;
-    if (!host->chrom_span_hint && d->dev.n > 0) {
-      // dataset statistics at load time (what GMQL's own profiler keeps per dataset): the largest stop of every chromosome.
-      // The view hands them on as chrom_span_hint, so operators on the resident dataset know the genome's layout up front.
-      DevBuf<unsigned long long> span(ctx, d->dev.n_chrom);
-      DevBuf<int> bad(ctx, 1);
-      span.zero(); bad.zero();
-      accumulate_spans(ctx, d->dev, span.p, bad.p);
-      std::vector<unsigned long long> hs((size_t)d->dev.n_chrom);
-      int h_bad = 0;
-      CUDA_TRY(cudaMemcpyAsync(hs.data(), span.p, 8 * hs.size(), cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+    view->sorted_by_position = host->sorted_by_position;
+    if (dv.n > 0) {
+      // dataset statistics at load time (what GMQL's own profiler keeps per dataset).  The view hands the spans on as
+      // chrom_span_hint, so operators on the resident dataset know the genome's layout up front; the flags let them choose
+      // their path without a pass over the data.
+      DevBuf<unsigned long long> span(ctx, dv.n_chrom);
+      DevBuf<int> fl(ctx, 4);
+      span.zero(); fl.zero();
+      const int nb = (int)std::min<int64_t>(ceil_div64(dv.n, 256 * 8), (int64_t)ctx->num_sms * 8);
+      const size_t sh = dv.n_chrom <= 4096 ? sizeof(unsigned long long) * (size_t)dv.n_chrom : 0;
+      LAUNCH(ctx, k_dataset_stats, nb, 256, sh, dv.chrom_narrow ? dv.chrom_narrow : (const void*)dv.chrom, dv.chrom_narrow ? dv.chrom_bits : 32, dv.start, dv.coord_bits,
+             dv.len_narrow ? dv.len_narrow : dv.stop, dv.len_narrow ? dv.len_bits : 0, dv.strand, dv.sample, dv.n, dv.n_chrom, dv.n_samples, span.p, fl.p);
+      unsigned long long* hs = (unsigned long long*)ctx_pinned(ctx, 8 * (size_t)dv.n_chrom);
+      int* hf = (int*)ctx_pinned(ctx, 4 * sizeof(int));
+      CUDA_TRY(cudaMemcpyAsync(hs, span.p, 8 * (size_t)dv.n_chrom, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaMemcpyAsync(hf, fl.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(GMQL_SYNC(ctx));
-      if (!h_bad) {                                     // invalid rows: no hint; the operators report them
-        d->span_hint.assign(hs.begin(), hs.end());
-        view->chrom_span_hint = d->span_hint.data();
+      if (!hf[2]) {                                       // invalid rows: no statistics, no hint; the operators report them
+        d->stats_ok = true;
+        d->has_star = hf[0] != 0 || dv.strand == nullptr;
+        d->has_zero = hf[1] != 0;
+        d->maxlen = hf[3];
+        bool hint_ok = host->chrom_span_hint != nullptr;
+        if (hint_ok) for (int c = 0; c < dv.n_chrom; ++c) if (host->chrom_span_hint[c] < (int64_t)hs[c]) hint_ok = false;
+        if (hint_ok) d->span_hint.assign(host->chrom_span_hint, host->chrom_span_hint + dv.n_chrom);   // the caller's bounds hold: keep its layout
+        else if (!host->chrom_span_hint) d->span_hint.assign(hs, hs + dv.n_chrom);
+        if (!d->span_hint.empty()) {
+          view->chrom_span_hint = d->span_hint.data();
+          gmql_cover_prepare_dataset(ctx, d, 2000);       // BinSize.Cover's default (core/BinSize.scala:14); other bin sizes recount
+        }
       }
     }
-    view->sorted_by_position = host->sorted_by_position;
+    ctx->datasets.push_back(d);
     *out = d;
     return GMQL_OK;
   } catch (const gmql_error& ex) {
@@ -326,12 +480,15 @@ extern "C" int gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql
 
 extern "C" void gmql_dataset_free(gmql_ctx* ctx, gmql_dataset* d) {
   (void)ctx;
-  if (d && d->owner) {
+  if (!d) return;
+  if (d->owner) {
     auto& tg = d->owner->trusted_groupings;
     for (size_t k = 0; k < tg.size(); ++k)
       if (tg[k].first == (const void*)d->dev.sample && tg[k].second == (const void*)d->sample_offsets.data()) { tg.erase(tg.begin() + (long)k); break; }
+    auto& ds = d->owner->datasets;
+    for (size_t k = 0; k < ds.size(); ++k) if (ds[k] == d) { ds.erase(ds.begin() + (long)k); break; }
   }
-  delete d;  // DevBuf destructors release on the owning context's stream
+  delete d;  // DevBuf destructors hand the buffers back to the owning context's arena
 }
 
 extern "C" int gmql_ctx_set_profiling(gmql_ctx* c, int enabled) {

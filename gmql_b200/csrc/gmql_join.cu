@@ -643,7 +643,7 @@ extern "C" int gmql_join(gmql_ctx* ctx, const gmql_regions* left, const gmql_reg
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
-    ctx->pin_next = 0;
+    ctx_begin_call(ctx);
     GMQL_REQUIRE(left && right, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_pairs >= 0 && (n_pairs == 0 || pairs), GMQL_ERR_INVALID, "bad pair list");
     GMQL_REQUIRE(left->n_chrom == right->n_chrom, GMQL_ERR_INVALID, "left and right must share one chromosome dictionary (n_chrom differs)");
@@ -672,6 +672,7 @@ extern "C" int gmql_join(gmql_ctx* ctx, const gmql_regions* left, const gmql_reg
     SpanTable spans;
     build_span_table(ctx, &dr, nullptr, &spans);
     res = new gmql_result();
+    res->owner = ctx;
     run_join<uint64_t>(ctx, dl, dr, pairs, n_pairs, cfg, rows_only, p_leq, p_req, spans, res);
     CUDA_TRY(GMQL_SYNC(ctx));
     *out = res;

@@ -380,6 +380,7 @@ constexpr int64_t MG_SMEM = 224 * 1024;
 
 struct MapGroupedArgs {
   const int32_t* e_chrom; const void* e_start; const void* e_stop; int e_bits;
+  const uint8_t* e_chrom8; const uint16_t* e_len16;   // NARROW: the ABI's narrow encodings, read as they are (7 bytes per row)
   const int8_t* e_strand; const int32_t* e_sample; const int64_t* sample_off; int n_exp_samples;
   LinMap lm; const uint32_t* r_start; const RefEntry<uint32_t>* entries; int n_ref;
   const long long* pair_base; int* bad;
@@ -392,7 +393,7 @@ struct MapGroupedArgs {
 // B32: 32-bit experiment coordinates (the usual case): the whole row pipeline runs on 32-bit registers, the chromosome's
 // {offset, span} pair is one 8-byte shared-memory load, and the rows of the NEXT iteration are already in flight while
 // the current ones are matched.
-template <bool B32>
+template <bool B32, bool NARROW>
 __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_grouped(MapGroupedArgs a) {
   extern __shared__ __align__(16) uint32_t g_dyn[];
   // the reference as a structure of arrays: the in-bucket scan walks consecutive 4-byte starts
@@ -455,9 +456,9 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_grouped(MapGroupedA
         for (int j = 0; j < MS_PER; ++j) {                        // coalesced 32-bit loads; nothing here waits for them
           const int64_t i = i0 + (int64_t)j * MS_THREADS;
           const bool ok = i < hi;
-          fc[j] = ok ? a.e_chrom[i] : -2;                         // -2: padding lane
+          fc[j] = ok ? (NARROW ? (int)a.e_chrom8[i] : a.e_chrom[i]) : -2;   // -2: padding lane
           fs[j] = ok ? e_start32[i] : 0;
-          fe[j] = ok ? e_stop32[i] : 0;
+          fe[j] = ok ? (NARROW ? fs[j] + (int)a.e_len16[i] : e_stop32[i]) : 0;
           fsm[j] = ok && a.e_sample ? a.e_sample[i] : smp;
         }
       };
@@ -579,7 +580,7 @@ static int64_t read_back_i64(gmql_ctx* ctx, const int64_t* dev) {
 }
 
 template <typename K>
-static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp, const gmql_pair* pairs, int64_t n_pairs,
+static void run_map(gmql_ctx* ctx, const DevRegions& ref, DevRegions& exp, const gmql_pair* pairs, int64_t n_pairs,
                     const MapAggPlan& plan, const SpanTable& spans, gmql_result* res) {
   const int64_t n_ref = ref.n, n_exp = exp.n;
   const int n_ls = ref.n_samples, n_rs = exp.n_samples;
@@ -610,7 +611,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   int h_bad = 0;
   const bool single = n_ls == 1;
   // small pre-sorted single-sample reference: the whole index comes from one cluster launch (k_map_index_small)
-  const char* mix_env = getenv("GMQL_MAP_INDEX");           // "split": test hook, always the separate index kernels
+  const char* mix_env = ctx_opt(ctx, "map.index");           // "split": test hook, always the separate index kernels
   const bool small_index = single && ref.sorted_hint && n_ref > 0 && n_ref <= MIX_MAX && !(mix_env && !strcmp(mix_env, "split"));
   if (single) {
     // one reference sample (MAP onto a COVER result, an annotation, ...): every table is known on the host; nothing to
@@ -667,11 +668,13 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   // and a query needs no search at all), at least 2^10 buckets
   int tbl_shift = 0;
   // COUNT onto a small single-sample reference with the experiment rows grouped by sample: k_map_count_grouped
-  const char* mg_env = getenv("GMQL_MAP_GROUPED");         // "0": test hook
+  const char* mg_env = ctx_opt(ctx, "map.grouped");         // "0" / "1": test hook
   const bool mg_compact = small_index && !ref.dup_of && !ref.strand;   // rank == index, no strand: 12 bytes per reference region
   const int64_t mg_fixed = (mg_compact ? 12 : 16) * n_ref + 4 * ((n_ref + 1) / 2) + 8 * (int64_t)lm.n_chrom + 16;
   const int64_t mg_tbl = (MG_SMEM - mg_fixed) / 2 - 16;   // 16-bit table entries
-  const bool grouped = single && sizeof(K) == 4 && plan.n_cols == 0 && !plan.need_bag && exp.sample_off != nullptr && exp.max_sample_rows <= 65535 &&
+  // (16-bit counters: a count cannot exceed the sample's rows — unless duplicate reference records pool their counts on one row,
+  // GenometricMap71.scala:186-203, so a reference with dup_of takes the streaming kernel)
+  const bool grouped = single && sizeof(K) == 4 && plan.n_cols == 0 && !plan.need_bag && exp.sample_off != nullptr && exp.max_sample_rows <= 65535 && !ref.dup_of &&
                        n_ref > 0 && n_ref < 65536 && n_exp > 0 && n_pairs > 0 && mg_tbl >= 2048 && !(mg_env && mg_env[0] == '0') &&
                        (n_rs >= 4 * ctx->num_sms || (mg_env && mg_env[0] == '1'));   // one block per sample at a time: needs many samples to fill the GPU evenly
   {
@@ -709,6 +712,10 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     ec.ok[q] = exp.valid[plan.col_id[q]];
   }
 
+  // the per-sample COUNT kernel reads the narrow encodings as they are; everything else wants the int32 / int64 columns
+  const bool exp_narrow = grouped && !exp.wide_ready && exp.coord_bits == 32 && exp.chrom_narrow && exp.chrom_bits == 8 && exp.len_narrow && exp.len_bits == 16 &&
+                          exp.sample_trusted;
+  if (!exp_narrow) gmql_ensure_wide(ctx, &exp);
   MapStreamArgs<K> ma_saved;
   memset(&ma_saved, 0, sizeof ma_saved);
   size_t sh_saved = 0;
@@ -716,6 +723,7 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   if (grouped) {
     MapGroupedArgs ga;
     ga.e_chrom = exp.chrom; ga.e_start = exp.start; ga.e_stop = exp.stop; ga.e_bits = exp.coord_bits;
+    ga.e_chrom8 = (const uint8_t*)exp.chrom_narrow; ga.e_len16 = (const uint16_t*)exp.len_narrow;
     ga.e_strand = exp.strand; ga.e_sample = exp.sample_trusted ? (const int32_t*)nullptr : exp.sample; ga.sample_off = exp.sample_off; ga.n_exp_samples = n_rs;
     ga.lm = lm; ga.r_start = (const uint32_t*)ix.start; ga.entries = (const RefEntry<uint32_t>*)entries.p; ga.n_ref = (int)n_ref;
     ga.pair_base = pair_base.p; ga.bad = bad.p;
@@ -724,12 +732,15 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
     ga.compact = mg_compact ? 1 : 0;
     const size_t sh = (size_t)mg_fixed + 2 * (size_t)((ga.n_tbl + 7) & ~7);
     const int mg_grid = (int)std::min<int64_t>(n_rs, (int64_t)ctx->num_sms);
-    if (exp.coord_bits == 32) {
-      CUDA_TRY(cudaFuncSetAttribute(k_map_count_grouped<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      LAUNCH(ctx, k_map_count_grouped<true>, mg_grid, MS_THREADS, sh, ga);
+    if (exp_narrow) {
+      CUDA_TRY(cudaFuncSetAttribute((k_map_count_grouped<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      LAUNCH(ctx, (k_map_count_grouped<true, true>), mg_grid, MS_THREADS, sh, ga);
+    } else if (exp.coord_bits == 32) {
+      CUDA_TRY(cudaFuncSetAttribute((k_map_count_grouped<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      LAUNCH(ctx, (k_map_count_grouped<true, false>), mg_grid, MS_THREADS, sh, ga);
     } else {
-      CUDA_TRY(cudaFuncSetAttribute(k_map_count_grouped<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      LAUNCH(ctx, k_map_count_grouped<false>, mg_grid, MS_THREADS, sh, ga);
+      CUDA_TRY(cudaFuncSetAttribute((k_map_count_grouped<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      LAUNCH(ctx, (k_map_count_grouped<false, false>), mg_grid, MS_THREADS, sh, ga);
     }
   } else if (n_exp && n_ref && n_rows) {
     MapStreamArgs<K> ma;
@@ -783,8 +794,23 @@ static void run_map(gmql_ctx* ctx, const DevRegions& ref, const DevRegions& exp,
   // REF_ROW: copy out of the ping-pong buffer that holds it (before the operator's one synchronisation)
   DevBuf<int32_t> ref_row(ctx, n_ref);
   if (n_ref) CUDA_TRY(cudaMemcpyAsync(ref_row.p, rows_by_sample, 4 * (size_t)n_ref, cudaMemcpyDeviceToDevice, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(GMQL_SYNC(ctx));
+  const char* defer = ctx_opt(ctx, "defer_check");
+  if (defer && defer[0] == '1' && single) {
+    // the caller asked not to wait: the flag travels to a pinned word and is looked at by the next call that finds the stream
+    // idle (gmql_result_column_copy, gmql_ctx_sync, the start of the next operator); row counts and offsets are host-known
+    if (!ctx->h_defer) { if (cudaHostAlloc((void**)&ctx->h_defer, 256 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); throw gmql_error(GMQL_ERR_NOMEM, "pinned host allocation failed"); } }
+    if (ctx->deferred.size() >= 200) { CUDA_TRY(GMQL_SYNC(ctx)); GMQL_REQUIRE(gmql_check_deferred(ctx) == GMQL_OK, GMQL_ERR_INVALID, ctx->err); }
+    int* slot = ctx->h_defer + (ctx->h_defer_next++ & 255);
+    *slot = 0;
+    CUDA_TRY(cudaMemcpyAsync(slot, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    gmql_ctx::Deferred df; df.h_flag = slot; df.what = "gmql_map: invalid region / sample index, reference region beyond its chrom_span_hint, reference rows out of the promised order, or a sample column that contradicts sample_offsets";
+    ctx->deferred.push_back(df);
+    ctx->last_deferred = true;
+    h_bad = 0;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
+  }
   GMQL_REQUIRE(h_bad != 2, GMQL_ERR_INVALID, "the same (ref sample, exp sample) pair is listed twice");
   GMQL_REQUIRE(h_bad != 3, GMQL_ERR_INVALID, "the sample column does not match sample_offsets (rows must be grouped by sample in offset order)");
   GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "region with chromosome/sample index out of range, negative start, reference region beyond its chrom_span_hint, or reference rows not in the promised (chrom, start) order");
@@ -904,7 +930,7 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
-    ctx->pin_next = 0;
+    ctx_begin_call(ctx);
     gmql_trace("ENTER gmql_map");
     GMQL_REQUIRE(ref && exp, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_pairs >= 0 && (n_pairs == 0 || pairs), GMQL_ERR_INVALID, "bad pair list");
@@ -915,15 +941,17 @@ extern "C" int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regio
     cudaEventRecord(ctx->ev_h0, ctx->stream);
     DevRegions dref, dexp;
     gmql_upload_regions(ctx, ref, std::vector<int>(), &dref);
-    gmql_upload_regions(ctx, exp, need_cols, &dexp);
+    gmql_upload_regions(ctx, exp, need_cols, &dexp, /*keep_narrow=*/true);   // run_map widens unless its per-sample COUNT kernel takes the rows as they are
     SpanTable spans;
     cudaEventRecord(ctx->ev_k0, ctx->stream);
     if (dref.span_hint) span_table_from_hint(ctx, dref.span_hint, dref.n_chrom, &spans);
     else build_span_table(ctx, &dref, nullptr, &spans);
     res = new gmql_result();
+    res->owner = ctx;
+    ctx->last_deferred = false;
     if (spans.G < 0xffffffffull) run_map<uint32_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
     else run_map<uint64_t>(ctx, dref, dexp, pairs, n_pairs, plan, spans, res);
-    CUDA_TRY(GMQL_SYNC_IF_PENDING(ctx));
+    if (!ctx->last_deferred) CUDA_TRY(GMQL_SYNC_IF_PENDING(ctx));
     *out = res;
     gmql_trace("EXIT");
     return GMQL_OK;
@@ -946,7 +974,7 @@ extern "C" int gmql_difference(gmql_ctx* ctx, const gmql_regions* ref, const gmq
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
-    ctx->pin_next = 0;
+    ctx_begin_call(ctx);
     GMQL_REQUIRE(ref && exp, GMQL_ERR_INVALID, "null dataset");
     GMQL_REQUIRE(n_pairs >= 0 && (n_pairs == 0 || pairs), GMQL_ERR_INVALID, "bad pair list");
     GMQL_REQUIRE(ref->n_chrom == exp->n_chrom, GMQL_ERR_INVALID, "ref and exp must share one chromosome dictionary (n_chrom differs)");
@@ -959,6 +987,7 @@ extern "C" int gmql_difference(gmql_ctx* ctx, const gmql_regions* ref, const gmq
     if (dref.span_hint) span_table_from_hint(ctx, dref.span_hint, dref.n_chrom, &spans);
     else build_span_table(ctx, &dref, nullptr, &spans);
     res = new gmql_result();
+    res->owner = ctx;
     if (spans.G < 0xffffffffull) run_difference<uint32_t>(ctx, dref, dexp, pairs, n_pairs, exact != 0, spans, res);
     else run_difference<uint64_t>(ctx, dref, dexp, pairs, n_pairs, exact != 0, spans, res);
     CUDA_TRY(GMQL_SYNC(ctx));

@@ -297,7 +297,7 @@ extern "C" int gmql_parse_text(gmql_ctx* ctx, const char* text, int64_t n_bytes,
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
-    ctx->pin_next = 0;
+    ctx_begin_call(ctx);
     GMQL_REQUIRE(schema && (n_bytes == 0 || text) && n_bytes >= 0, GMQL_ERR_INVALID, "null text or schema");
     GMQL_REQUIRE(schema->n_values >= 0 && schema->n_values <= TXT_MAX_VALUES, GMQL_ERR_UNSUPPORTED, "at most 16 numeric value columns per parse");
     GMQL_REQUIRE(schema->chr_pos >= 0 && schema->start_pos >= 0 && schema->stop_pos >= 0, GMQL_ERR_INVALID, "chr/start/stop positions are required");
@@ -352,6 +352,7 @@ extern "C" int gmql_parse_text(gmql_ctx* ctx, const char* text, int64_t n_bytes,
     cudaEventRecord(ctx->ev_k0, ctx->stream);
 
     res = new gmql_result();
+    res->owner = ctx;
     res->kind = 6;
     int64_t n_rows = 0;
     if (n_bytes > 0) {

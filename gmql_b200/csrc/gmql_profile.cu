@@ -70,7 +70,7 @@ extern "C" int gmql_profile(gmql_ctx* ctx, const gmql_regions* in, gmql_result**
   gmql_result* res = nullptr;
   try {
     CUDA_TRY(cudaSetDevice(ctx->device));
-    ctx->pin_next = 0;
+    ctx_begin_call(ctx);
     GMQL_REQUIRE(in != nullptr, GMQL_ERR_INVALID, "null dataset");
     cudaEventRecord(ctx->ev_h0, ctx->stream);
     DevRegions d;
@@ -95,6 +95,7 @@ extern "C" int gmql_profile(gmql_ctx* ctx, const gmql_regions* in, gmql_result**
     CUDA_TRY(GMQL_SYNC(ctx));
     GMQL_REQUIRE(!h_bad, GMQL_ERR_INVALID, "sample index out of range");
     res = new gmql_result();
+    res->owner = ctx;
     res->rows = ns;
     res->kind = 5;
     result_add(res, GMQL_COL_PROF_LEFTMOST, left);

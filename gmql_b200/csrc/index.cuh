@@ -122,11 +122,15 @@ struct IntervalIndex {
 // payload = original row, or (stop - start) when `stop` is given (no later gather needed; rows are then unavailable)
 template <typename K>
 __global__ void k_index_keys(const int32_t* __restrict__ chrom, const void* __restrict__ start, const void* __restrict__ stop, int bits, const uint32_t* __restrict__ blocks,
-                             int64_t n, LinMap lm, K* __restrict__ keys, uint32_t* __restrict__ rows) {
+                             int64_t n, LinMap lm, K* __restrict__ keys, uint32_t* __restrict__ rows, int* __restrict__ bad = nullptr) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint64_t blk = blocks ? blocks[i] : 0u;
     int64_t s = ld_coord(start, bits, i);
-    uint64_t lin = blk * lm.G + lm.coff[chrom[i]] + (uint64_t)s;
+    int c = chrom[i];
+    // span tables built from a caller's hint have seen no row yet: an out-of-range chromosome or a negative start is
+    // reported (and the row parked at the origin), never dereferenced
+    if (bad && (c < 0 || c >= lm.n_chrom || s < 0)) { *bad = 1; c = 0; s = 0; }
+    uint64_t lin = blk * lm.G + lm.coff[c] + (uint64_t)s;
     keys[i] = (K)lin;
     rows[i] = stop ? (uint32_t)(ld_coord(stop, bits, i) - s) : (uint32_t)i;
   }
@@ -190,6 +194,6 @@ static void build_index(gmql_ctx* ctx, const DevRegions& r, const uint32_t* bloc
   alloc_index<K>(ctx, r.n, ix);
   if (r.n == 0) return;
   // payload_len requires region lengths < 2^32 (checked by the caller through the span table)
-  LAUNCH(ctx, (k_index_keys<K>), grid_for(ctx, r.n, 256), 256, 0, r.chrom, r.start, payload_len ? r.stop : (const void*)nullptr, r.coord_bits, blocks, r.n, lm, ix->start_a.p, ix->row_a.p);
+  LAUNCH(ctx, (k_index_keys<K>), grid_for(ctx, r.n, 256), 256, 0, r.chrom, r.start, payload_len ? r.stop : (const void*)nullptr, r.coord_bits, blocks, r.n, lm, ix->start_a.p, ix->row_a.p, bad);
   finish_index<K>(ctx, r, blocks, n_blocks, lm, ix, payload_len, bad);
 }

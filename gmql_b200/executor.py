@@ -90,6 +90,10 @@ class GMQLCudaExecutor:
         if rc != 0:
             raise L.GmqlCudaError(rc, self.lib.gmql_last_error(self.ctx).decode("utf-8", "replace"))
 
+    def set_option(self, name, value):
+        """gmql_ctx_set_option: per-context test / tuning hooks and "defer_check" (include/gmql_cuda.h)."""
+        self._check(self.lib.gmql_ctx_set_option(self.ctx, name.encode(), None if value is None else str(value).encode()))
+
     def last_device_ms(self):
         return float(self.lib.gmql_last_device_ms(self.ctx))
 

@@ -1,0 +1,48 @@
+"""Test / tuning helper: environment variables -> per-context options.
+
+The library itself never reads the environment (include/gmql_cuda.h: gmql_ctx_set_option).  Tests and tuning runs find it
+convenient to flip a device path with `GMQL_COVER_PATH=tiled pytest ...` or os.environ inside a test; install_env_hooks()
+wraps the operator entry points of the ctypes binding so that, before every call, the GMQL_* variables below are copied into
+the options of the context the call is made on.  Product code (gmql_b200.executor) does not depend on this module.
+"""
+import os
+
+ENV_OPTIONS = {
+    "GMQL_COVER_PATH": b"cover.path", "GMQL_COVER_LOGW": b"cover.logw", "GMQL_COVER_WAVES": b"cover.waves",
+    "GMQL_COVER_STITCH": b"cover.stitch", "GMQL_COVER_SPECULATE": b"cover.speculate", "GMQL_COVER_KERNEL": b"cover.kernel",
+    "GMQL_MAP_INDEX": b"map.index", "GMQL_MAP_GROUPED": b"map.grouped", "GMQL_DEFER_CHECK": b"defer_check",
+}
+_OPERATORS = ("gmql_cover", "gmql_cover_shard", "gmql_map", "gmql_difference", "gmql_join")
+
+
+def install_env_hooks(lib):
+    """Idempotent.  Returns lib."""
+    if getattr(lib, "_gmql_env_hooks", False):
+        return lib
+    seen = {}
+
+    def sync(ctx):
+        key = ctx.value if hasattr(ctx, "value") else ctx
+        vals = tuple(os.environ.get(e) for e in ENV_OPTIONS)
+        if seen.get(key) == vals:
+            return
+        for (env, name), v in zip(ENV_OPTIONS.items(), vals):
+            lib.gmql_ctx_set_option(ctx, name, v.encode() if v else None)
+        seen[key] = vals
+
+    def wrap(raw):
+        def call(ctx, *args):
+            sync(ctx)
+            return raw(ctx, *args)
+        return call
+
+    for name in _OPERATORS:
+        setattr(lib, name, wrap(getattr(lib, name)))
+    raw_destroy = lib.gmql_ctx_destroy
+
+    def destroy(ctx):
+        seen.pop(ctx.value if hasattr(ctx, "value") else ctx, None)
+        return raw_destroy(ctx)
+    lib.gmql_ctx_destroy = destroy
+    lib._gmql_env_hooks = True
+    return lib

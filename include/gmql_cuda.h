@@ -22,7 +22,9 @@
  *  - a context is used by one thread at a time; distinct contexts are independent
  *    (no global mutable state), matching GMQLExecute's 5-job pool (GMQLExecute.scala:29-30);
  *  - inputs are owned by the caller and must stay alive for the duration of the call;
- *    results are owned by the library until gmql_result_free;
+ *    results are owned by the library until gmql_result_free; results and datasets live in their context's memory pool and
+ *    must be freed (with that context) before gmql_ctx_destroy;
+ *  - device memory comes from a pool private to the context (cudaMemPoolCreate): the process's default pool is untouched;
  *  - there is NO CPU fallback: without a CUDA device every compute call fails.
  */
 #ifndef GMQL_CUDA_H
@@ -89,7 +91,7 @@ typedef struct {
                                    (checked on the device where it is relied upon: gmql_map's per-sample COUNT kernel).
                                    Views returned by gmql_dataset_upload carry it when the upload had it. */
   const int64_t* chrom_span_hint;/* HOST array [n_chrom] or NULL: an upper bound of `stop` per chromosome (e.g. the
-                                   assembly's chromosome sizes).  Lets gmql_map / gmql_join lay out the linear coordinate
+                                   assembly's chromosome sizes).  Lets gmql_map / gmql_difference lay out the linear coordinate
                                    without a pass over the data and a host round trip; a region beyond its bound is an
                                    error (GMQL_ERR_INVALID), never a wrong result.  gmql_cover uses it to queue its tile
                                    pipeline without waiting for its own prepass (a region beyond its bound there only
@@ -142,7 +144,20 @@ int  gmql_abi_version(void);
 int  gmql_ctx_create(int device, void* stream, gmql_ctx** out);
 void gmql_ctx_destroy(gmql_ctx* ctx);
 const char* gmql_last_error(const gmql_ctx* ctx);
-int  gmql_ctx_sync(gmql_ctx* ctx);                      /* cudaStreamSynchronize on the context stream */
+int  gmql_ctx_sync(gmql_ctx* ctx);                      /* cudaStreamSynchronize on the context stream; reports deferred checks */
+/* Per-context options (strings; value NULL or "" clears).  They never change results, only which device path computes them
+ * (test hooks, tuning) or when an error is reported:
+ *   "cover.path"      "tiled" | "sort"   force the tile-resident or the sort-and-merge path of COVER / FLAT
+ *   "cover.logw"      "8".."16"          tile width of the tile-resident path
+ *   "cover.kernel"    "rank" | "count"   tile kernel: bitmap-rank (round 1) or word-count (default where it applies)
+ *   "cover.waves", "cover.stitch" ("split"), "cover.speculate" ("0"), "map.index" ("split"), "map.grouped" ("0" | "1")
+ *   "defer_check"     "1"                gmql_map (one reference sample) returns without waiting for the device: an invalid
+ *                                        input (bad index, broken layout promise) is then reported by the next call on this
+ *                                        context that finds the stream idle — gmql_result_column_copy, gmql_ctx_sync or the next
+ *                                        operator — as GMQL_ERR_INVALID.  For pipelines that want one host synchronisation per
+ *                                        COVER -> MAP step.  Default: every operator reports its own errors.
+ * Options are per context: nothing in this library reads process-global state (environment variables). */
+int  gmql_ctx_set_option(gmql_ctx* ctx, const char* name, const char* value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t gmql_ctx_launch_count(const gmql_ctx* ctx);
 /* pinned host memory for the SoA columns (JNI: wrap with NewDirectByteBuffer) */
@@ -152,8 +167,14 @@ void gmql_host_free(void* p);
 /* Device-resident copy of a host dataset: the analogue of the per-IR-node memo (IROperator.intermediateResult,
  * GMQLSparkExecutor.scala:252-253,282) so that a dataset consumed by several operators (`C = COVER(..) E; M = MAP() C E`)
  * crosses PCIe once.  `view` is filled with device pointers (location = GMQL_LOC_DEVICE) that stay valid until
- * gmql_dataset_free; the small host arrays of the view (sample_ids, cols, valid) are owned by the dataset too.
- * All n_cols value columns are uploaded.  The copy is asynchronous on the context stream. */
+ * gmql_dataset_free; the small host arrays of the view (sample_ids, cols, valid, sample_offsets, chrom_span_hint) are owned by
+ * the dataset too.  All n_cols value columns are uploaded.  The arrays stay resident in the encodings they arrived in: a
+ * dataset sent with chrom_bits = 8, stop_is_length = 16 and sample_offsets costs 7 bytes per region of device memory, and the
+ * view says so (chrom_bits / stop_is_length / sample == NULL); operators without a path for the narrow encodings widen them once
+ * per dataset.  The upload also gathers the dataset's statistics in one read (largest stop per chromosome — handed on as the
+ * view's chrom_span_hint — longest region, zero-length / '*' flags, row validity) and, for datasets the tile-resident COVER
+ * path accepts, the partition offsets of that path: the per-node memo of GMQLSparkExecutor.scala:252-253 extended to what every
+ * operator on the dataset would otherwise recompute. */
 typedef struct gmql_dataset gmql_dataset;
 int  gmql_dataset_upload(gmql_ctx* ctx, const gmql_regions* host, gmql_dataset** out, gmql_regions* view);
 void gmql_dataset_free(gmql_ctx* ctx, gmql_dataset* d);
@@ -203,7 +224,7 @@ int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_grou
  * into tiles of 65 536 positions; a shard owns the tiles [first_tile, end_tile).  `in` must hold every region whose start lies in
  * the tiles [first_tile - 1, end_tile) (the tile before the range only lends the regions still open at the cut: the halo; other
  * rows are ignored).  chrom_span (HOST [n_chrom], an upper bound of stop per chromosome) must be identical on every shard.
- * Requirements: COVER or FLAT, one group, unified strands, no aggregates, no zero-length regions, regions shorter than 65 534
+ * Requirements: COVER or FLAT, one group, unified strands, no aggregates, no zero-length regions, regions shorter than 32 768
  * bases, the linear genome below 2^32 (otherwise GMQL_ERR_UNSUPPORTED: shard by chromosome instead).
  *
  * Result: the columns of gmql_cover for the runs inside the shard, plus what a cross-shard merge needs (all chromosome-local):

@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _env_options():
+    """GMQL_* environment variables act as per-context options in the tests (gmql_b200/testing.py); the library itself never
+    reads the environment."""
+    try:
+        from gmql_b200 import _lib as L
+        from gmql_b200.testing import install_env_hooks
+        install_env_hooks(L.load_library())
+    except Exception:
+        pass            # library not built: the tests that need it fail on their own
+    yield
+
+
 def _has_gpu():
     try:
         import torch
