@@ -40,11 +40,40 @@ constexpr int MAXP = 256;               // pieces per tile
 constexpr int HCAP = 512;               // regions of the previous tile still open at the tile start
 constexpr int MAX_TILE_REGIONS = 32000; // own + open regions of one tile: keeps every 16-bit net change exact
 constexpr uint32_t EXT = 0x80000000u;   // length payload bit: stop' = stop + 1
-// Partitioned records are 4 bytes: tile-local start (16 bits) | one-base extension (bit 15) | length (15 bits).  Regions of
-// 32 768 bases and more do not take the tile path.
-constexpr int MAX_REGION_LEN = 32767;
-constexpr uint32_t LEN_EXT16 = 0x8000u; // the extension bit inside the 16-bit length word
-__device__ __forceinline__ uint32_t rec_len_payload(uint32_t rec) { return (rec & 0x7fffu) | ((rec & LEN_EXT16) << 16); }   // length | EXT
+// Partitioned records are 4 bytes: tile-local start (16 bits) | length (16 bits); regions are shorter than a tile, so both fit.
+// The extractor's one-base extension (stop on a bin multiple, GenometricCover.scala:353-354) is a property of the chromosome-local
+// stop: the tile kernel recomputes it from the tile's chromosome offset (TileChrom) instead of carrying a bit.
+struct TileChrom {                       // chromosome layout around one tile (block-uniform)
+  uint32_t lo, next, base;               // linear positions [lo, next) belong to one chromosome of one class, whose position 0 is `base`
+};
+__device__ __forceinline__ uint32_t lin_base_slow(const LinMap& lm, uint32_t x) {      // linear position of the chromosome start at or before x
+  const uint64_t cls = (uint64_t)x / lm.G, rem = (uint64_t)x - cls * lm.G;
+  int lo = 0, hi = lm.n_chrom;           // last chromosome with coff <= rem
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lm.coff[mid] <= rem) lo = mid; else hi = mid; }
+  return (uint32_t)(cls * lm.G + lm.coff[lo]);
+}
+__device__ __forceinline__ TileChrom tile_chrom(const LinMap& lm, uint32_t tile_lo) {
+  const uint64_t cls = (uint64_t)tile_lo / lm.G, rem = (uint64_t)tile_lo - cls * lm.G;
+  int lo = 0, hi = lm.n_chrom;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lm.coff[mid] <= rem) lo = mid; else hi = mid; }
+  TileChrom t;
+  t.base = (uint32_t)(cls * lm.G + lm.coff[lo]);
+  t.lo = t.base;
+  const uint64_t nx = cls * lm.G + (lo + 1 < lm.n_chrom ? lm.coff[lo + 1] : lm.G);
+  t.next = nx > 0xffffffffull ? 0xffffffffu : (uint32_t)nx;
+  return t;
+}
+struct BinMod { uint64_t magic; int64_t B; };   // x % B == 0 without a division (Lemire, Kaser, Kurz 2019), exact for 32-bit x and B < 2^31
+__device__ __forceinline__ BinMod make_binmod(int64_t B) { BinMod m; m.B = B; m.magic = B > 1 ? 0xffffffffffffffffull / (uint64_t)B + 1ull : 0ull; return m; }
+__device__ __forceinline__ bool is_bin_multiple(const BinMod& m, uint32_t x) {
+  return m.B < 0x7fffffffLL ? (m.magic * (uint64_t)x <= m.magic - 1ull) : ((uint64_t)x % (uint64_t)m.B == 0ull);
+}
+// length payload of a record that starts at linear position rs: length | EXT when stop' = stop + 1
+__device__ __forceinline__ uint32_t rec_len_payload(uint32_t rec, uint32_t rs, const TileChrom& tc, const LinMap& lm, const BinMod& bm) {
+  const uint32_t len = rec & 0xffffu;
+  const uint32_t base = (rs >= tc.lo && rs < tc.next) ? tc.base : lin_base_slow(lm, rs);
+  return len | ((len != 0u && is_bin_multiple(bm, rs + len - base)) ? EXT : 0u);
+}
 constexpr size_t SMEM_BYTES = 4 * MAXWORDS + 2 * MAXWORDS + 2 * CAP_EV + 16 * HCAP + 32 * MAXP;
 
 // net +1 / -1 per distinct position, two 16-bit signed counters per shared-memory word.  Adding +-1 to the low half may borrow
@@ -347,11 +376,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // Three variants of one kernel:
 //   MSP_WIDE / MSP_NARROW  coarse pass: records are built from the input columns — int32 (or int64) chrom / start / stop, or the
 //                          ABI's narrow encodings uint8 chrom, int32 start, uint16 length (7 bytes per region) — and split by
-//                          coarse bin (tile >> 8); written as two arrays, linear start key (uint32) and length word (uint16:
-//                          length | extension bit 15), 6 bytes per region;
+//                          coarse bin (tile >> 8); written as two arrays, linear start key (uint32) and length (uint16),
+//                          6 bytes per region;
 //   MSP_FINE               fine pass: reads those two arrays and splits every coarse bin into its tiles; written as ONE 4-byte
-//                          record per region (tile-local start << 16 | length word), which is all the tile kernel reads.
-// bin_shift = 32 + logw (+ 8 for the coarse pass) applies to the 64-bit register form (key << 32 | length word).
+//                          record per region (tile-local start << 16 | length), which is all the tile kernel reads.
+// bin_shift = 32 + logw (+ 8 for the coarse pass) applies to the 64-bit register form (key << 32 | length).
 // The input of the NEXT tile of a block is fetched by TMA bulk copies into a staging buffer while the current tile is ranked,
 // regrouped and written: every thread moves its items from the staging buffer into registers first, so one staging buffer
 // and one mbarrier suffice, and the load latency no longer sits at the head of every tile (registers are at the
@@ -388,8 +417,6 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, 
   if (chrom_sh) for (int k = tid; k < lm.n_chrom; k += MSP_THREADS) s_coff[k] = lm.coff[k];
   const uint64_t* coff = chrom_sh ? s_coff : lm.coff;
   const int64_t n_tiles = (n + MSP_TILE - 1) / MSP_TILE;
-  // n % B == 0  <=>  M * n (mod 2^64) <= M - 1 with M = floor((2^64 - 1) / B) + 1, exact for 32-bit n (Lemire, Kaser, Kurz 2019)
-  const uint64_t bmagic = FUSED && B > 1 ? 0xffffffffffffffffull / (uint64_t)B + 1ull : 0ull;
   // full tiles of suitably aligned input go through the staging buffer
   const bool tma_ok = MODE == MSP_FINE ? ((((uintptr_t)in.key | (uintptr_t)in.len) & 15u) == 0)
                     : (MODE == MSP_WIDE ? (vec_ok && in.bits == 32 && in.cls == nullptr) : (vec_ok != 0));
@@ -447,17 +474,13 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, 
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t key = (uint32_t)((uint64_t)kk[q] * lm.G + coff[cc[q]]) + (uint32_t)ss[q];
-            const bool ext = (bmagic * (uint64_t)(uint32_t)ee[q] <= bmagic - 1ull) && ss[q] < ee[q];   // ee % B == 0 without a division
-            rec[j4 * 4 + q] = ((uint64_t)key << 32) | (uint64_t)(((uint32_t)(ee[q] - ss[q]) & 0x7fffu) | (ext ? LEN_EXT16 : 0u));
+            rec[j4 * 4 + q] = ((uint64_t)key << 32) | (uint64_t)((uint32_t)(ee[q] - ss[q]) & 0xffffu);
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint64_t r = 0ull;
-            if (idx0 + q < count) {
-              const uint64_t r64 = make_record(in.chrom, in.start, in.stop, in.bits, in.cls, coff, lm.G, B, i0 + q);   // key << 32 | length | EXT (bit 31)
-              r = (r64 & 0xffffffff00000000ull) | (r64 & 0x7fffull) | ((r64 & (uint64_t)EXT) ? (uint64_t)LEN_EXT16 : 0ull);
-            }
+            if (idx0 + q < count) r = make_record(in.chrom, in.start, in.stop, in.bits, in.cls, coff, lm.G, B, i0 + q) & 0xffffffff0000ffffull;   // key << 32 | length
             rec[j4 * 4 + q] = r;
           }
         }
@@ -492,9 +515,7 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t key = (uint32_t)coff[cc[q]] + (uint32_t)ss[q];
-          const uint32_t e = (uint32_t)ss[q] + ll[q];
-          const bool ext = (bmagic * (uint64_t)e <= bmagic - 1ull) && ll[q] != 0u;
-          rec[j4 * 4 + q] = idx0 + q < count ? (((uint64_t)key << 32) | (uint64_t)((ll[q] & 0x7fffu) | (ext ? LEN_EXT16 : 0u))) : 0ull;
+          rec[j4 * 4 + q] = idx0 + q < count ? (((uint64_t)key << 32) | (uint64_t)ll[q]) : 0ull;
         }
       }
     } else {
@@ -579,7 +600,7 @@ static __global__ void k_pack_rec32(const uint64_t* __restrict__ packed, int64_t
   const uint32_t wmask = (1u << logw) - 1u;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t r = packed[i];
-    rec[i] = ((((uint32_t)(r >> 32)) & wmask) << 16) | ((uint32_t)r & 0x7fffu) | ((r & (uint64_t)EXT) ? LEN_EXT16 : 0u);
+    rec[i] = ((((uint32_t)(r >> 32)) & wmask) << 16) | ((uint32_t)r & 0xffffu);
   }
 }
 
@@ -679,9 +700,10 @@ __device__ __forceinline__ void gmap4_round(bool valid, uint32_t rs, uint32_t re
 // still open at a tile's end are handed to the next tile through shared memory; only the first tile of a range scans
 // its predecessor's regions in global memory.
 template <bool MULTI>
-static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(const uint32_t* __restrict__ P /* tile-local start << 16 | length word */, const uint32_t* __restrict__ offS,
-                                                                  int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, Pieces out, Guard guard) {
+static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(const uint32_t* __restrict__ P /* tile-local start << 16 | length */, const uint32_t* __restrict__ offS,
+                                                                  int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, LinMap lm, int64_t B, Pieces out, Guard guard) {
   if (guard_trips(guard)) return;
+  const BinMod bm = make_binmod(B);
   extern __shared__ uint32_t sm[];
   uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
   uint16_t* wpre = (uint16_t*)(bitmap + MAXWORDS);         // [MAXWORDS] set bits before each word
@@ -747,6 +769,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
     const uint32_t h0 = (scan_prev && tile > 0) ? offS[tile - 1] : s0;
     const uint32_t tile_lo = (uint32_t)tile << logw;
     if (nS == 0 && (scan_prev ? h0 == s0 : nh_carry == 0)) { nh_carry = 0; continue; }   // depth 0 throughout, nothing left open
+    const TileChrom tch = tile_chrom(lm, tile_lo);
     // the next tile's records: into L2 while this tile is processed
     if (tile + 1 < t_end) {
       const uintptr_t a0 = (uintptr_t)(P + s1) & ~(uintptr_t)127, a1 = (uintptr_t)(P + s2_next);
@@ -757,7 +780,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
         uint32_t i = i0 + tid;
         if (i < s0) {
-          const uint32_t pr = P[i]; uint32_t rs = tile_lo - W + (pr >> 16), lp = rec_len_payload(pr);
+          const uint32_t pr = P[i]; uint32_t rs = tile_lo - W + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm);
           uint32_t ee = rs + (lp & ~EXT) + (lp >> 31);
           if (ee >= tile_lo) {
             int slot = atomicAdd(&s_nh, 1);
@@ -779,7 +802,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
     for (int r = 0; r < RC; ++r) {
       uint32_t i = s0 + tid + r * THREADS;
       rsr[r] = 0; lpr[r] = 0;
-      if (i < s1) { const uint32_t pr = P[i]; rsr[r] = tile_lo + (pr >> 16); lpr[r] = rec_len_payload(pr); }
+      if (i < s1) { const uint32_t pr = P[i]; rsr[r] = tile_lo + (pr >> 16); lpr[r] = rec_len_payload(pr, rsr[r], tch, lm, bm); }
     }
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
@@ -792,7 +815,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       }
     }
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr);
+      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm);
       uint32_t q = rs - tile_lo;
       atomicOr(&bitmap[q >> 5], 1u << (q & 31));
       uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
@@ -842,7 +865,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       }
     }
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr);
+      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm);
       uint32_t q = rs - tile_lo;
       int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
       delta_add(delta, rk, 1);
@@ -968,7 +991,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
         }
       }
       for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-        const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), re = rs + (pr & 0x7fffu);
+        const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), re = rs + (pr & 0xffffu);
         if (p1 > rs && p0 < re) { ++cnt; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
       }
       cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -998,7 +1021,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
         uint32_t i = i0 + tid;
         bool valid = i < s1;
         uint32_t rs = 0, re = 0;
-        if (valid) { const uint32_t pr = P[i]; rs = tile_lo + (pr >> 16); re = rs + (pr & 0x7fffu); }
+        if (valid) { const uint32_t pr = P[i]; rs = tile_lo + (pr >> 16); re = rs + (pr & 0xffffu); }
         gmap4_round(valid, rs, re, true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
     }

@@ -1180,7 +1180,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   const int64_t n = in.n;
   tiled::Guard guard;
   guard.flags = (spec && !spec->synced) ? spec->flags : nullptr;
-  guard.max_len = (int)std::min<int64_t>((1ll << logw) - 2, (int64_t)tiled::MAX_REGION_LEN + 1);
+  guard.max_len = (int)((1ll << logw) - 2);
   const int key_bits = bits_for(n_classes_total * lm.G);
   const int64_t nT = (int64_t)((n_classes_total * lm.G) >> logw) + 1;
   // the tiles this call owns: all of them, or one shard's range (the tile before the range only lends its open regions)
@@ -1291,10 +1291,10 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
   if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, pc, guard);
+    LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, cfg.B, pc, guard);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, pc, guard);
+    LAUNCH(ctx, tiled::k_cover_tile<false>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, cfg.B, pc, guard);
   }
   unsigned long long h_np = 0;
   int h_fail = 0;
@@ -1450,7 +1450,7 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
     const char* flw = ctx_opt(ctx, "cover.logw");
     if (flw) logw = atoi(flw);
     if (shard) logw = tiled::MAX_LOGW;                  // shards are cut on 65 536-position tiles
-    bool fits = logw >= 8 && logw <= tiled::MAX_LOGW && maxlen < (int64_t)(1ll << logw) - 2 && maxlen <= tiled::MAX_REGION_LEN;
+    bool fits = logw >= 8 && logw <= tiled::MAX_LOGW && maxlen < (int64_t)(1ll << logw) - 2;
     if (src.narrow && (int64_t)((n_classes_total * lm.G) >> logw) + 1 > tiled::HIST_CAP) { gmql_ensure_wide(ctx, &in); src.narrow = false; }   // radix route reads the wide columns
     bool want = fits && (double)n * (double)(1ull << logw) / total >= 256.0;   // enough regions per tile for the tile pass to pay
     if (force && !strcmp(force, "tiled")) want = fits;
@@ -1717,7 +1717,7 @@ void gmql_cover_prepare_dataset(gmql_ctx* ctx, gmql_dataset* ds, int64_t bin_siz
   const int logw = tiled::MAX_LOGW;
   const int64_t nT = (int64_t)(run >> logw) + 1;
   if (!(dv.coord_bits == 32 && dv.chrom_narrow && dv.chrom_bits == 8 && dv.len_narrow && dv.len_bits == 16 && ds->has_star && !ds->has_zero &&
-        ds->maxlen <= tiled::MAX_REGION_LEN && run + 2ull * (1ull << logw) < 0xffffffffull && nT <= tiled::HIST_CAP)) return;
+        ds->maxlen < (1ll << tiled::MAX_LOGW) - 2 && run + 2ull * (1ull << logw) < 0xffffffffull && nT <= tiled::HIST_CAP)) return;
   const int n_coarse = (int)((nT + 255) >> 8) + 1;
   const int64_t in_tiles = ceil_div64(dv.n, tiled::MSP_TILE);
   const int G = (int)std::max<int64_t>(1, std::min<int64_t>(in_tiles, (int64_t)ctx->num_sms));
@@ -1764,7 +1764,7 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
       const char* spec_opt = ctx_opt(ctx, "cover.speculate");   // "0": test hook (the generic route)
       if (ds && ds->stats_ok && !ds->span_hint.empty() && in->chrom_span_hint == ds->span_hint.data() && !shard && d.n > 0 && d.coord_bits == 32 && d.chrom_narrow &&
           d.chrom_bits == 8 && d.len_narrow && d.len_bits == 16 && ds->has_star /* strands unify to '*': the column, if any, is not read */ && n_groups == 1 && plan.n_aggs == 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) &&
-          !ds->has_zero && ds->maxlen <= tiled::MAX_REGION_LEN && !(spec_opt && spec_opt[0] == '0')) {
+          !ds->has_zero && ds->maxlen < (1ll << tiled::MAX_LOGW) - 2 && !(spec_opt && spec_opt[0] == '0')) {
         if (ds->lay_pad != (uint64_t)bin_size + 2ull) gmql_cover_prepare_dataset(ctx, ds, bin_size);   // another BinSize.Cover than the upload assumed
         if (ds->lay_coff.p && ds->lay_G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
           SpanTable hs;                                       // borrowed views of the dataset's layout

@@ -224,7 +224,7 @@ int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_grou
  * into tiles of 65 536 positions; a shard owns the tiles [first_tile, end_tile).  `in` must hold every region whose start lies in
  * the tiles [first_tile - 1, end_tile) (the tile before the range only lends the regions still open at the cut: the halo; other
  * rows are ignored).  chrom_span (HOST [n_chrom], an upper bound of stop per chromosome) must be identical on every shard.
- * Requirements: COVER or FLAT, one group, unified strands, no aggregates, no zero-length regions, regions shorter than 32 768
+ * Requirements: COVER or FLAT, one group, unified strands, no aggregates, no zero-length regions, regions shorter than 65 534
  * bases, the linear genome below 2^32 (otherwise GMQL_ERR_UNSUPPORTED: shard by chromosome instead).
  *
  * Result: the columns of gmql_cover for the runs inside the shard, plus what a cross-shard merge needs (all chromosome-local):

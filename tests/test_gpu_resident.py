@@ -94,6 +94,8 @@ def _oracle_pipeline(ds, n_samples):
     from oracle import c_oracle as CO
     from gmql_b200.regions import RegionDataset
     r = CO.cover_rows(ds, 0, [2], [ANYV], None, 2000)
+    o = np.lexsort((r["start"], r["chrom"]))              # the oracle emits a chromosome's bin-edge pieces after the others
+    r = {k: v[o] for k, v in r.items()}
     nc = len(r["start"])
     ref = RegionDataset(ds.chrom_names, r["chrom"], r["start"], r["stop"], r["strand"], np.zeros(nc, np.int32), np.array([0], np.int64))
     pidx = np.stack([np.zeros(n_samples, np.int32), np.arange(n_samples, dtype=np.int32)], axis=1)
@@ -102,12 +104,12 @@ def _oracle_pipeline(ds, n_samples):
 
 
 def test_c5_production_route_against_the_oracle(ex):
-    """640 samples x 3 000 peaks on hg38 shrunk twenty-fold (the same depth and tile density as C5): the exact kernels the bench
+    """640 samples x 8 000 peaks on hg38 shrunk twenty-fold (the same depth and tile density as C5): the exact kernels the bench
     times, row for row against the C oracle, with no path override."""
     from gmql_b200 import synth
     for k in ("GMQL_COVER_PATH", "GMQL_COVER_LOGW", "GMQL_MAP_GROUPED", "GMQL_COVER_KERNEL", "GMQL_COVER_SPECULATE"):
         assert k not in os.environ
-    ds = synth.peak_samples(640, 3000, 5, with_values=(), sizes=synth.HG38_SIZES // 20)
+    ds = synth.peak_samples(640, 8000, 5, with_values=(), sizes=synth.HG38_SIZES // 20)
     # the natural incidence of bin-aligned stops is kept, and a few are forced (extractor's one-base extension, :353-354)
     ds.stop[::977] = np.maximum((ds.stop[::977] // 2000) * 2000, ds.start[::977] + 1)
     dset, view, keep = _upload(ex, ds)
@@ -118,7 +120,7 @@ def test_c5_production_route_against_the_oracle(ex):
     for name in ("k_prepass_hist", "k_cover_prepass", "k_tile_hist", "k_widen_chrom", "k_stop_from_length", "k_expand_sample_offsets", "k_map_stream", "onesweep"):
         assert name not in kern, (name, kern)
     want_c, want_m = _oracle_pipeline(ds, 640)
-    assert len(want_c["start"]) > 500
+    assert 100 < len(want_c["start"]) < 12000
     for a, k in zip(got_c, ("chrom", "start", "stop", "acc", "j1", "j2")):
         assert np.array_equal(a, want_c[k]), k
     assert np.array_equal(got_m, want_m)
@@ -137,7 +139,7 @@ def test_c5_production_route_against_the_oracle(ex):
 
 @pytest.mark.parametrize("case", ["zero_length", "long_region", "strand_column", "other_bin"])
 def test_upload_statistics_choose_the_route(ex, case):
-    """What the upload learns decides the route without a pass over the data: a zero-length region, a region of 32 768 bases or a
+    """What the upload learns decides the route without a pass over the data: a zero-length region, a region as long as a tile or a
     strand column keep a narrow dataset off the fast route (same rows as the oracle through the generic one); another
     BinSize.Cover only recounts the partition offsets."""
     from gmql_b200 import synth, _lib as L
@@ -147,7 +149,7 @@ def test_upload_statistics_choose_the_route(ex, case):
     if case == "zero_length":
         ds.stop[4321] = ds.start[4321]
     elif case == "long_region":
-        ds.stop[99] = ds.start[99] + 40000
+        ds.stop[99] = ds.start[99] + 65534
     elif case == "other_bin":
         bin_size = 1000
     if case == "strand_column":
@@ -166,6 +168,8 @@ def test_upload_statistics_choose_the_route(ex, case):
     got, kern = _profile(ex, run)
     assert ("k_multisplit<tiled::MSP_NARROW>" in kern) == (case == "other_bin"), kern
     want = CO.cover_rows(ds, 0, [2], [ANYV], None, bin_size)
+    o = np.lexsort((want["start"], want["chrom"], want["strand"]))
+    want = {k: v[o] for k, v in want.items()}
     assert len(want["start"]) > 100
     for a, k in zip(got, ("chrom", "start", "stop", "acc", "j1", "j2")):
         assert np.array_equal(a, want[k]), (case, k)
