@@ -27,6 +27,12 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def set_threads(n):
+    """All host cores for the CPU arm of bench.py, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)."""
+    lib().oracle_set_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 

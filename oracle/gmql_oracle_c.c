@@ -19,8 +19,9 @@
  *          (chrom, bin, group, strand) (:98-108), sorted per bin (:111), coverHelper / histogramHelper / summitHelper
  *          state machines per bin, split + boundary merge (:121-152), then
  *          RO/GenometricMap/GMAP4.scala:20-100 — binned join of the cover regions against the inputs, reduce per region.
- * Parallelism: OpenMP over independent keys (exp samples for MAP, (group,strand,chrom) segments for COVER), the
- * analogue of Spark's partitions in local[N].
+ * Parallelism: OpenMP over independent keys — experiment samples for MAP; for COVER chunks of 1024 consecutive 2000-bp bins of a
+ * (group, strand, chrom) segment in phase 1 (Spark keys that plan by (chrom, bin, group, strand), :51,98-108) and phase-1
+ * regions in GMAP4 — the analogue of Spark's partitions in local[N].
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -41,6 +42,15 @@ static double java_max(double a, double b) {
   if (a != a) return a;
   if (a == 0.0 && b == 0.0 && signbit(a)) return b;
   return a >= b ? a : b;
+}
+
+/* bench.py: use every host core whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers) */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 
 int oracle_num_threads(void) {
@@ -208,37 +218,65 @@ typedef struct {
 
 typedef struct { CoverRow* p; int64_t n, cap; } RowVec;
 
-/* runs one (group, strand, chrom) segment: regions idx[0..m) */
-static int cover_segment(int flag, int64_t B, int32_t mn, int32_t mx, int32_t group, int32_t chrom, int8_t strand,
-                         const int32_t* idx, int64_t m, const int64_t* start, const int64_t* stop, const double* val, const uint8_t* valid, RowVec* out) {
-  /* extractor (:345-360) */
-  int64_t ne = 0;
-  for (int64_t q = 0; q < m; ++q) { int64_t s = start[idx[q]], e = stop[idx[q]]; ne += (s / B == e / B) ? 2 : 2 * (e / B - s / B + 1); }
-  Pt* ev = (Pt*)malloc(sizeof(Pt) * (size_t)(ne ? ne : 1));
-  if (!ev) return -1;
-  int64_t w = 0;
+/* ---- phase 1 of one chunk of consecutive bins [b_lo, b_hi) of one (group, strand, chrom) segment ------------------------------
+ * Spark keys the COVER plan by (chrom, bin, group, strand) (GenometricCover.scala:51,98-108): every bin is an independent unit
+ * of work until the boundary merge.  The port keeps that granularity for its parallelism: a segment is cut into chunks of
+ * CHUNK_BINS bins, a region is handed to every chunk it touches, and a chunk generates, sorts and sweeps only the events of its
+ * own bins.  It also builds the chunk's share of GMAP4's binned input (GMAP4.scala:102-139). */
+#define CHUNK_BINS 1024
+
+typedef struct {
+  int64_t b_lo, b_hi;                /* bins of this chunk */
+  PieceVec pieces;                   /* phase-1 pieces, in bin order */
+  BinRec* eb; int64_t nb;            /* GMAP4: (bin, region) records of the chunk's bins, sorted by bin */
+  int rc;
+} Chunk;
+
+static void cover_chunk(int flag, int64_t B, int32_t mn, int32_t mx, const int32_t* idx, int64_t m, const int64_t* start, const int64_t* stop, Chunk* ck) {
+  const int64_t b_lo = ck->b_lo, b_hi = ck->b_hi;
+  /* extractor (:345-360), restricted to the bins of this chunk */
+  int64_t ne = 0, nb = 0;
   for (int64_t q = 0; q < m; ++q) {
     int64_t s = start[idx[q]], e = stop[idx[q]];
     int64_t sb = s / B, eb = e / B;
+    int64_t lo = sb > b_lo ? sb : b_lo, hi = eb < b_hi - 1 ? eb : b_hi - 1;
+    if (hi >= lo) { ne += 2 * (hi - lo + 1); nb += hi - lo + 1; }
+  }
+  Pt* ev = (Pt*)malloc(sizeof(Pt) * (size_t)(ne ? ne : 1));
+  ck->eb = (BinRec*)malloc(sizeof(BinRec) * (size_t)(nb ? nb : 1));
+  if (!ev || !ck->eb) { free(ev); ck->rc = -1; return; }
+  int64_t w = 0, v = 0;
+  for (int64_t q = 0; q < m; ++q) {
+    int64_t s = start[idx[q]], e = stop[idx[q]];
+    int64_t sb = s / B, eb = e / B;
+    int64_t lo = sb > b_lo ? sb : b_lo, hi = eb < b_hi - 1 ? eb : b_hi - 1;
+    for (int64_t k = lo; k <= hi; ++k) { ck->eb[v].chrom = 0; ck->eb[v].bin = k; ck->eb[v].idx = idx[q]; ++v; }
     if (sb == eb) {
-      if (s == e) { ev[w].bin = sb; ev[w].off = (int32_t)(s - sb * B); ev[w].delta = -1; ++w; }   /* duplicate HashMap key keeps the -1 */
+      if (sb < b_lo || sb >= b_hi) continue;
+      if (s == e) { ev[w].bin = sb; ev[w].off = (int32_t)(s - sb * B); ev[w].delta = -1; ++w; }   /* duplicate HashMap key keeps the -1 (:351) */
       else {
         ev[w].bin = sb; ev[w].off = (int32_t)(s - sb * B); ev[w].delta = 1; ++w;
         ev[w].bin = sb; ev[w].off = (int32_t)(e - sb * B); ev[w].delta = -1; ++w;
       }
     } else {
-      ev[w].bin = sb; ev[w].off = (int32_t)(s - sb * B); ev[w].delta = 1; ++w;
-      ev[w].bin = sb; ev[w].off = (int32_t)B; ev[w].delta = -1; ++w;
-      int64_t eo = e - eb * B;
-      ev[w].bin = eb; ev[w].off = (int32_t)(eo != 0 ? eo : 1); ev[w].delta = -1; ++w;
-      ev[w].bin = eb; ev[w].off = 0; ev[w].delta = 1; ++w;
-      for (int64_t k = sb + 1; k < eb; ++k) {
+      if (sb >= b_lo && sb < b_hi) {                                                              /* map_start (:353) */
+        ev[w].bin = sb; ev[w].off = (int32_t)(s - sb * B); ev[w].delta = 1; ++w;
+        ev[w].bin = sb; ev[w].off = (int32_t)B; ev[w].delta = -1; ++w;
+      }
+      if (eb >= b_lo && eb < b_hi) {                                                              /* map_stop (:354) */
+        int64_t eo = e - eb * B;
+        ev[w].bin = eb; ev[w].off = (int32_t)(eo != 0 ? eo : 1); ev[w].delta = -1; ++w;
+        ev[w].bin = eb; ev[w].off = 0; ev[w].delta = 1; ++w;
+      }
+      int64_t klo = sb + 1 > b_lo ? sb + 1 : b_lo, khi = eb - 1 < b_hi - 1 ? eb - 1 : b_hi - 1;
+      for (int64_t k = klo; k <= khi; ++k) {                                                      /* map_int (:355) */
         ev[w].bin = k; ev[w].off = 0; ev[w].delta = 1; ++w;
         ev[w].bin = k; ev[w].off = (int32_t)B; ev[w].delta = -1; ++w;
       }
     }
   }
-  ne = w;
+  ne = w; ck->nb = v;
+  qsort(ck->eb, (size_t)ck->nb, sizeof(BinRec), cmp_binrec);
   qsort(ev, (size_t)ne, sizeof(Pt), cmp_pt);
   /* reduceByKey: coincident points are summed, zero-net points stay (:98-108) */
   int64_t np = 0;
@@ -248,7 +286,7 @@ static int cover_segment(int flag, int64_t B, int32_t mn, int32_t mx, int32_t gr
     ev[np].bin = ev[q].bin; ev[np].off = ev[q].off; ev[np].delta = d; ++np;
     q = r;
   }
-  PieceVec pv = {0, 0, 0};
+  PieceVec* pv = &ck->pieces;
   int rc = 0;
   for (int64_t q = 0; q < np && rc == 0;) {
     int64_t r = q;
@@ -263,7 +301,7 @@ static int cover_segment(int flag, int64_t B, int32_t mn, int32_t mx, int32_t gr
         int nrec = inr && has_next;
         int32_t ncmax = (!nrec && rec) ? 0 : ((nrec && nc > cmax) ? nc : cmax);
         int64_t nst = (inr && !rec) ? ev[t].off : st;
-        if (!nrec && rec) rc |= pv_push(&pv, nst + bin * B, (ev[t].off > B ? B : ev[t].off) + bin * B, cmax);
+        if (!nrec && rec) rc |= pv_push(pv, nst + bin * B, (ev[t].off > B ? B : ev[t].off) + bin * B, cmax);
         count = nc; st = nst; cmax = ncmax; rec = nrec;
       }
     } else if (flag == 3) {                             /* histogramHelper (:229-258) */
@@ -271,7 +309,7 @@ static int cover_segment(int flag, int64_t B, int32_t mn, int32_t mx, int32_t gr
       for (int64_t t = q; t < r; ++t) {
         int32_t nc = count + ev[t].delta;
         int64_t nst = (nc >= mn && nc <= mx && nc != count) ? ev[t].off : st;
-        if (count >= mn && count <= mx && nc != count && count != 0) rc |= pv_push(&pv, st + bin * B, ev[t].off + bin * B, count);
+        if (count >= mn && count <= mx && nc != count && count != 0) rc |= pv_push(pv, st + bin * B, ev[t].off + bin * B, count);
         st = nst; count = nc;
       }
     } else {                                            /* summitHelper (:269-316) */
@@ -283,95 +321,79 @@ static int cover_segment(int flag, int64_t B, int32_t mn, int32_t mx, int32_t gr
         int nre = !valid_ && nvalid;
         int64_t nst = (nvalid && nc != count) ? ev[t].off : st;
         if (((valid_ && grow && (!ngrow || !nvalid)) || (re && !ngrow)) && count != 0)
-          rc |= pv_push(&pv, st + bin * B, (ev[t].off > B ? B : ev[t].off) + bin * B, count);
+          rc |= pv_push(pv, st + bin * B, (ev[t].off > B ? B : ev[t].off) + bin * B, count);
         st = nst; count = nc; valid_ = nvalid; re = nre; grow = ngrow;
       }
     }
     q = r;
   }
   free(ev);
-  if (rc) { free(pv.p); return -1; }
-  /* split + boundary merge (:121-152) */
-  PieceVec fin = {0, 0, 0}, nv = {0, 0, 0};
-  for (int64_t q = 0; q < pv.n; ++q) {
-    if (pv.p[q].start % B != 0 && pv.p[q].stop % B != 0) rc |= pv_push(&fin, pv.p[q].start, pv.p[q].stop, pv.p[q].acc);
-    else rc |= pv_push(&nv, pv.p[q].start, pv.p[q].stop, pv.p[q].acc);
-  }
-  free(pv.p);
+  ck->rc = rc;
+}
+
+/* split + boundary merge of one segment's pieces (:121-152); pieces arrive in bin order */
+static int merge_segment(int flag, int64_t B, const Chunk* chunks, int64_t n_chunks, PieceVec* fin) {
+  PieceVec nv = {0, 0, 0};
+  int rc = 0;
+  for (int64_t c = 0; c < n_chunks; ++c)
+    for (int64_t q = 0; q < chunks[c].pieces.n; ++q) {
+      const Piece* p = &chunks[c].pieces.p[q];
+      if (p->start % B != 0 && p->stop % B != 0) rc |= pv_push(fin, p->start, p->stop, p->acc);
+      else rc |= pv_push(&nv, p->start, p->stop, p->acc);
+    }
   if (nv.n) {
     qsort(nv.p, (size_t)nv.n, sizeof(Piece), cmp_piece);
     Piece old = nv.p[0];
     for (int64_t q = 1; q < nv.n; ++q) {
       Piece cur = nv.p[q];
       if (old.stop == cur.start && (flag != 3 || old.acc == cur.acc)) { old.stop = cur.stop; if (cur.acc > old.acc) old.acc = cur.acc; }
-      else { rc |= pv_push(&fin, old.start, old.stop, old.acc); old = cur; }
+      else { rc |= pv_push(fin, old.start, old.stop, old.acc); old = cur; }
     }
-    rc |= pv_push(&fin, old.start, old.stop, old.acc);
+    rc |= pv_push(fin, old.start, old.stop, old.acc);
   }
   free(nv.p);
-  if (rc) { free(fin.p); return -1; }
-  /* GMAP4 (GMAP4.scala:20-100): binned join of cover regions with the segment's inputs */
-  int64_t nb = 0;
-  for (int64_t q = 0; q < m; ++q) nb += stop[idx[q]] / B - start[idx[q]] / B + 1;
-  BinRec* eb = (BinRec*)malloc(sizeof(BinRec) * (size_t)(nb ? nb : 1));
-  if (!eb) { free(fin.p); return -1; }
-  w = 0;
-  for (int64_t q = 0; q < m; ++q)
-    for (int64_t k = start[idx[q]] / B; k <= stop[idx[q]] / B; ++k) { eb[w].chrom = 0; eb[w].bin = k; eb[w].idx = idx[q]; ++w; }
-  qsort(eb, (size_t)nb, sizeof(BinRec), cmp_binrec);
-  for (int64_t c = 0; c < fin.n; ++c) {
-    int64_t cs = fin.p[c].start, ce = fin.p[c].stop;
-    int64_t cnt = 0, smin = 0, emax = 0, smax = 0, emin = 0;
-    int32_t nn = 0; double sum = 0, vmin = 0, vmax = 0;
-    for (int64_t k = cs / B; k <= ce / B; ++k) {
-      /* records of bin k */
-      int64_t lo = 0, hi = nb;
-      while (lo < hi) { int64_t mid = (lo + hi) / 2; if (eb[mid].bin < k) lo = mid + 1; else hi = mid; }
-      for (int64_t y = lo; y < nb && eb[y].bin == k; ++y) {
-        int32_t e = eb[y].idx;
-        if (cs < stop[e] && start[e] < ce && ((cs / B) == k || (start[e] / B) == k)) {   /* :39-46 */
-          if (cnt == 0) { smin = start[e]; emax = stop[e]; smax = start[e]; emin = stop[e]; }
-          else {                                                                         /* reduce (:68-74) */
-            if (start[e] < smin) smin = start[e];
-            if (stop[e] > emax) emax = stop[e];
-            int64_t a = smax > start[e] ? smax : start[e], b2 = emin < stop[e] ? emin : stop[e];
-            if (a < b2) { smax = a; emin = b2; } else { smax = 0; emin = 0; }
-          }
-          ++cnt;
-          if (val && (!valid || valid[e])) {
-            double x = val[e];
-            if (nn == 0) { sum = x; vmin = x; vmax = x; } else { sum += x; vmin = java_min(vmin, x); vmax = java_max(vmax, x); }
-            ++nn;
-          }
+  return rc;
+}
+
+/* GMAP4 (GMAP4.scala:20-100) for one phase-1 region against the chunks' binned inputs; returns 1 when a row was produced */
+static int gmap4_region(int flag, int64_t B, int32_t group, int32_t chrom, int8_t strand, const Piece* pc, const Chunk* chunks, int64_t n_chunks, int64_t first_bin,
+                        const int64_t* start, const int64_t* stop, const double* val, const uint8_t* valid, CoverRow* o) {
+  int64_t cs = pc->start, ce = pc->stop;
+  int64_t cnt = 0, smin = 0, emax = 0, smax = 0, emin = 0;
+  int32_t nn = 0; double sum = 0, vmin = 0, vmax = 0;
+  for (int64_t k = cs / B; k <= ce / B; ++k) {
+    int64_t ci = (k - first_bin) / CHUNK_BINS;
+    if (ci < 0 || ci >= n_chunks) continue;
+    const Chunk* ck = &chunks[ci];
+    int64_t lo = 0, hi = ck->nb;
+    while (lo < hi) { int64_t mid = (lo + hi) / 2; if (ck->eb[mid].bin < k) lo = mid + 1; else hi = mid; }
+    for (int64_t y = lo; y < ck->nb && ck->eb[y].bin == k; ++y) {
+      int32_t e = ck->eb[y].idx;
+      if (cs < stop[e] && start[e] < ce && ((cs / B) == k || (start[e] / B) == k)) {   /* :39-46 */
+        if (cnt == 0) { smin = start[e]; emax = stop[e]; smax = start[e]; emin = stop[e]; }
+        else {                                                                         /* reduce (:68-74) */
+          if (start[e] < smin) smin = start[e];
+          if (stop[e] > emax) emax = stop[e];
+          int64_t a = smax > start[e] ? smax : start[e], b2 = emin < stop[e] ? emin : stop[e];
+          if (a < b2) { smax = a; emin = b2; } else { smax = 0; emin = 0; }
+        }
+        ++cnt;
+        if (val && (!valid || valid[e])) {
+          double x = val[e];
+          if (nn == 0) { sum = x; vmin = x; vmax = x; } else { sum += x; vmin = java_min(vmin, x); vmax = java_max(vmax, x); }
+          ++nn;
         }
       }
     }
-    if (cnt == 0) continue;                                                              /* :33-34,48 */
-    if (out->n == out->cap) {
-      int64_t ncap = out->cap ? out->cap * 2 : 1024;
-      CoverRow* q2 = (CoverRow*)realloc(out->p, sizeof(CoverRow) * (size_t)ncap);
-      if (!q2) { free(eb); free(fin.p); return -1; }
-      out->p = q2; out->cap = ncap;
-    }
-    CoverRow* o = &out->p[out->n++];
-    double os = flag == 1 ? (double)smin : (double)cs, oe = flag == 1 ? (double)emax : (double)ce;   /* :83-84 */
-    o->group = group; o->chrom = chrom; o->strand = strand; o->start = (int64_t)os; o->stop = (int64_t)oe; o->acc = fin.p[c].acc;
-    int64_t den = emax - smin;
-    o->j1 = den != 0 ? fabs((oe - os) / (double)den) : 0.0;
-    o->j2 = den != 0 ? fabs(((double)emin - (double)smax) / (double)den) : 0.0;
-    o->count = (int32_t)cnt; o->nn = nn; o->sum = sum; o->vmin = vmin; o->vmax = vmax;
   }
-  free(eb); free(fin.p);
-  return 0;
-}
-
-typedef struct { int32_t g; int8_t st; int32_t chrom; int32_t idx; } SegRec;
-static int cmp_seg(const void* a, const void* b) {
-  const SegRec* x = (const SegRec*)a; const SegRec* y = (const SegRec*)b;
-  if (x->g != y->g) return x->g < y->g ? -1 : 1;
-  if (x->st != y->st) return x->st < y->st ? -1 : 1;
-  if (x->chrom != y->chrom) return x->chrom < y->chrom ? -1 : 1;
-  return x->idx < y->idx ? -1 : (x->idx > y->idx);
+  if (cnt == 0) return 0;                                                              /* :33-34,48 */
+  double os = flag == 1 ? (double)smin : (double)cs, oe = flag == 1 ? (double)emax : (double)ce;   /* :83-84 */
+  o->group = group; o->chrom = chrom; o->strand = strand; o->start = (int64_t)os; o->stop = (int64_t)oe; o->acc = pc->acc;
+  int64_t den = emax - smin;
+  o->j1 = den != 0 ? fabs((oe - os) / (double)den) : 0.0;
+  o->j2 = den != 0 ? fabs(((double)emin - (double)smax) / (double)den) : 0.0;
+  o->count = (int32_t)cnt; o->nn = nn; o->sum = sum; o->vmin = vmin; o->vmax = vmax;
+  return 1;
 }
 
 static CoverRow* g_rows = 0;
@@ -385,47 +407,104 @@ int64_t oracle_cover(int64_t n, const int32_t* chrom, const int64_t* start, cons
   free(g_rows); g_rows = 0; g_nrows = 0;
   int unknown = strand == 0;                                                             /* assignGroups (:328) */
   for (int64_t i = 0; i < n && !unknown; ++i) if (strand[i] == 0) unknown = 1;
-  SegRec* sr = (SegRec*)malloc(sizeof(SegRec) * (size_t)(n ? n : 1));
-  int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
-  if (!sr || !idx) return -1;
+  /* segments (group, strand, chrom), in that order; regions of a segment in ascending row order (a counting sort) */
+  int32_t n_chrom = 0;
+  for (int64_t i = 0; i < n; ++i) if (chrom[i] + 1 > n_chrom) n_chrom = chrom[i] + 1;
+  if (n_groups < 1) n_groups = 1;
+  const int64_t n_seg_keys = (int64_t)n_groups * 3 * (n_chrom > 0 ? n_chrom : 1);
+  int64_t* seg_cnt = (int64_t*)calloc((size_t)n_seg_keys + 1, sizeof(int64_t));
+  int64_t* seg_maxbin = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_seg_keys ? n_seg_keys : 1));
+  int64_t* seg_minbin = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_seg_keys ? n_seg_keys : 1));
+  if (!seg_cnt || !seg_maxbin || !seg_minbin) return -1;
+  for (int64_t k = 0; k < n_seg_keys; ++k) { seg_maxbin[k] = -1; seg_minbin[k] = INT64_MAX; }
+#define SEGKEY(i) (((int64_t)(sample_group ? sample_group[sample ? sample[i] : 0] : 0) * 3 + (unknown ? 0 : strand[i])) * n_chrom + chrom[i])
   for (int64_t i = 0; i < n; ++i) {
-    sr[i].g = sample_group ? sample_group[sample ? sample[i] : 0] : 0;
-    sr[i].st = unknown ? 0 : strand[i];
-    sr[i].chrom = chrom[i];
-    sr[i].idx = (int32_t)i;
+    int64_t k = SEGKEY(i);
+    int64_t sb = start[i] / B, eb = stop[i] / B;
+    if (eb > seg_maxbin[k]) seg_maxbin[k] = eb;
+    if (sb < seg_minbin[k]) seg_minbin[k] = sb;
   }
-  qsort(sr, (size_t)n, sizeof(SegRec), cmp_seg);
-  int64_t nseg = 0;
-  int64_t* seg_off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 2));
-  if (!seg_off) return -1;
+  /* chunks of every non-empty segment */
+  int64_t* seg_chunk0 = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_seg_keys + 1));
+  if (!seg_chunk0) return -1;
+  int64_t n_chunks = 0;
+  for (int64_t k = 0; k < n_seg_keys; ++k) {
+    seg_chunk0[k] = n_chunks;
+    if (seg_maxbin[k] >= 0) n_chunks += (seg_maxbin[k] - seg_minbin[k]) / CHUNK_BINS + 1;
+  }
+  seg_chunk0[n_seg_keys] = n_chunks;
+  Chunk* chunks = (Chunk*)calloc((size_t)(n_chunks ? n_chunks : 1), sizeof(Chunk));
+  int64_t* ck_off = (int64_t*)calloc((size_t)n_chunks + 2, sizeof(int64_t));
+  if (!chunks || !ck_off) return -1;
+  /* a region goes to every chunk its bins touch (counting sort by chunk, ascending row order inside a chunk) */
   for (int64_t i = 0; i < n; ++i) {
-    idx[i] = sr[i].idx;
-    if (i == 0 || sr[i].g != sr[i - 1].g || sr[i].st != sr[i - 1].st || sr[i].chrom != sr[i - 1].chrom) seg_off[nseg++] = i;
+    int64_t k = SEGKEY(i);
+    int64_t c0 = seg_chunk0[k] + (start[i] / B - seg_minbin[k]) / CHUNK_BINS, c1 = seg_chunk0[k] + (stop[i] / B - seg_minbin[k]) / CHUNK_BINS;
+    for (int64_t c = c0; c <= c1; ++c) ck_off[c + 1]++;
   }
-  seg_off[nseg] = n;
-  RowVec* per = (RowVec*)calloc((size_t)(nseg ? nseg : 1), sizeof(RowVec));
-  if (!per) return -1;
+  for (int64_t c = 0; c < n_chunks; ++c) ck_off[c + 1] += ck_off[c];
+  int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)(ck_off[n_chunks] ? ck_off[n_chunks] : 1));
+  int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_chunks + 1));
+  if (!idx || !fill) return -1;
+  memcpy(fill, ck_off, sizeof(int64_t) * (size_t)(n_chunks + 1));
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t k = SEGKEY(i);
+    int64_t c0 = seg_chunk0[k] + (start[i] / B - seg_minbin[k]) / CHUNK_BINS, c1 = seg_chunk0[k] + (stop[i] / B - seg_minbin[k]) / CHUNK_BINS;
+    for (int64_t c = c0; c <= c1; ++c) idx[fill[c]++] = (int32_t)i;
+  }
+  free(fill);
+  for (int64_t k = 0; k < n_seg_keys; ++k)
+    for (int64_t c = seg_chunk0[k]; c < seg_chunk0[k + 1]; ++c) {
+      chunks[c].b_lo = seg_minbin[k] + (c - seg_chunk0[k]) * CHUNK_BINS;
+      chunks[c].b_hi = chunks[c].b_lo + CHUNK_BINS;
+    }
   int failed = 0;
-  (void)n_groups;
+  /* phase 1: every chunk on its own (the analogue of Spark's per-(chrom, bin, group, strand) partitions in local[N]) */
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int64_t s = 0; s < nseg; ++s) {
-    int64_t a = seg_off[s];
-    int rc = cover_segment(flag, B, mn[sr[a].g], mx[sr[a].g], sr[a].g, sr[a].chrom, sr[a].st, idx + a, seg_off[s + 1] - a, start, stop, val, valid, &per[s]);
-    if (rc) failed = 1;
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    int64_t k = 0;
+    { int64_t lo = 0, hi = n_seg_keys; while (hi - lo > 1) { int64_t mid = (lo + hi) / 2; if (seg_chunk0[mid] <= c) lo = mid; else hi = mid; } k = lo; while (seg_chunk0[k + 1] <= c) ++k; }
+    int32_t g = (int32_t)(k / ((int64_t)3 * n_chrom));
+    cover_chunk(flag, B, mn[g], mx[g], idx + ck_off[c], ck_off[c + 1] - ck_off[c], start, stop, &chunks[c]);
+    if (chunks[c].rc) failed = 1;
+  }
+  /* boundary merge per segment, GMAP4 per phase-1 region */
+  RowVec* per = (RowVec*)calloc((size_t)(n_seg_keys ? n_seg_keys : 1), sizeof(RowVec));
+  if (!per) return -1;
+  for (int64_t k = 0; k < n_seg_keys && !failed; ++k) {
+    int64_t nck = seg_chunk0[k + 1] - seg_chunk0[k];
+    if (nck == 0) continue;
+    PieceVec fin = {0, 0, 0};
+    if (merge_segment(flag, B, chunks + seg_chunk0[k], nck, &fin)) { failed = 1; free(fin.p); break; }
+    CoverRow* rows = (CoverRow*)malloc(sizeof(CoverRow) * (size_t)(fin.n ? fin.n : 1));
+    uint8_t* keep = (uint8_t*)calloc((size_t)(fin.n ? fin.n : 1), 1);
+    if (!rows || !keep) { failed = 1; free(fin.p); free(rows); free(keep); break; }
+    int32_t g = (int32_t)(k / ((int64_t)3 * n_chrom));
+    int8_t st = (int8_t)((k / n_chrom) % 3);
+    int32_t ch = (int32_t)(k % n_chrom);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t c = 0; c < fin.n; ++c)
+      keep[c] = (uint8_t)gmap4_region(flag, B, g, ch, st, &fin.p[c], chunks + seg_chunk0[k], nck, seg_minbin[k], start, stop, val, valid, &rows[c]);
+    int64_t w = 0;
+    for (int64_t c = 0; c < fin.n; ++c) if (keep[c]) rows[w++] = rows[c];
+    per[k].p = rows; per[k].n = w; per[k].cap = fin.n;
+    free(keep); free(fin.p);
   }
   int64_t tot = 0;
-  for (int64_t s = 0; s < nseg; ++s) tot += per[s].n;
+  for (int64_t k = 0; k < n_seg_keys; ++k) tot += per[k].n;
   if (!failed) {
     g_rows = (CoverRow*)malloc(sizeof(CoverRow) * (size_t)(tot ? tot : 1));
     if (!g_rows) failed = 1;
   }
   if (!failed) {
     int64_t w = 0;
-    for (int64_t s = 0; s < nseg; ++s) { memcpy(g_rows + w, per[s].p, sizeof(CoverRow) * (size_t)per[s].n); w += per[s].n; }
+    for (int64_t k = 0; k < n_seg_keys; ++k) { if (per[k].n) memcpy(g_rows + w, per[k].p, sizeof(CoverRow) * (size_t)per[k].n); w += per[k].n; }
     g_nrows = tot;
   }
-  for (int64_t s = 0; s < nseg; ++s) free(per[s].p);
-  free(per); free(seg_off); free(sr); free(idx);
+  for (int64_t k = 0; k < n_seg_keys; ++k) free(per[k].p);
+  for (int64_t c = 0; c < n_chunks; ++c) { free(chunks[c].pieces.p); free(chunks[c].eb); }
+  free(per); free(chunks); free(ck_off); free(idx); free(seg_cnt); free(seg_maxbin); free(seg_minbin); free(seg_chunk0);
+#undef SEGKEY
   return failed ? -1 : tot;
 }
 

@@ -30,6 +30,23 @@ def test_reference_arm_prints_one_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # both arms word the workload identically (the driver compares `config`), and the probe for a real GMQL-Spark is recorded
+    import bench
+    import argparse
+    a = argparse.Namespace(samples=40, regions=2000)
+    assert d["config"] == bench.c5_config(a, 1) and d["warmup"] == 0
+    assert d["gmql_spark_probe"]["conclusion"]
+
+
+def test_reference_arm_uses_every_core_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not drop to one core because of it."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--samples", "20", "--regions", "1000", "--cpu-samples", "20", "--cpu-chroms", "2"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([ln for ln in p.stdout.splitlines() if ln.strip()][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r01[kl]_bench_c5_*gpu.json"))))
