@@ -47,13 +47,15 @@ struct TileChrom {                       // chromosome layout around one tile (b
   uint32_t lo, next, base;               // linear positions [lo, next) belong to one chromosome of one class, whose position 0 is `base`
 };
 __device__ __forceinline__ uint32_t lin_base_slow(const LinMap& lm, uint32_t x) {      // linear position of the chromosome start at or before x
-  const uint64_t cls = (uint64_t)x / lm.G, rem = (uint64_t)x - cls * lm.G;
+  uint64_t cls = 0, rem = x;
+  if (rem >= lm.G) { cls = rem / lm.G; rem -= cls * lm.G; }   // one class (the usual case): no division
   int lo = 0, hi = lm.n_chrom;           // last chromosome with coff <= rem
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lm.coff[mid] <= rem) lo = mid; else hi = mid; }
   return (uint32_t)(cls * lm.G + lm.coff[lo]);
 }
 __device__ __forceinline__ TileChrom tile_chrom(const LinMap& lm, uint32_t tile_lo) {
-  const uint64_t cls = (uint64_t)tile_lo / lm.G, rem = (uint64_t)tile_lo - cls * lm.G;
+  uint64_t cls = 0, rem = tile_lo;
+  if (rem >= lm.G) { cls = rem / lm.G; rem -= cls * lm.G; }
   int lo = 0, hi = lm.n_chrom;
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lm.coff[mid] <= rem) lo = mid; else hi = mid; }
   TileChrom t;
@@ -1046,6 +1048,8 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
   }
   if (tid == 0) out.blk_cnt[blockIdx.x] = (uint32_t)my_cnt;
 }
+
+#include "cover_tile_wc.cuh"
 
 // per-block piece counts -> first global index of every block's pieces, and their total (one block)
 static __global__ void __launch_bounds__(1024) k_seg_offsets(const uint32_t* __restrict__ blk_cnt, int nb, uint32_t* __restrict__ blk_off, unsigned long long* __restrict__ total) {

@@ -1176,7 +1176,8 @@ static void tile_offsets_narrow(gmql_ctx* ctx, const DevRegions& in, const LinMa
 static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total, int logw,
                             const int32_t* h_mn, const int32_t* h_mx, Phase1Out* p1, DevBuf<int32_t>& keep, DevBuf<int64_t>& fstart, DevBuf<int64_t>& fstop,
                             DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs, FusedOut* fo, SpecCtx* spec,
-                            const TileSource& src) {
+                            const TileSource& src, bool use_wc, int* fail_code) {
+  *fail_code = 0;
   const int64_t n = in.n;
   tiled::Guard guard;
   guard.flags = (spec && !spec->synced) ? spec->flags : nullptr;
@@ -1289,7 +1290,11 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   tiled::Pieces pc;
   pc.pstart = pstart.p; pc.pend = pend.p; pc.acc = acc.p; pc.cnt = cnt.p; pc.smin = smin.p; pc.emax = emax.p; pc.smax = smax.p; pc.emin = emin.p;
   pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
-  if (cfg.n_groups > 1) {
+  if (cfg.n_groups == 1 && use_wc) {
+    // the word-count kernel (cover_tile_wc.cuh); a tile with too many words to resolve sends the operator to the rank kernel
+    CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile_wc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::WC_SMEM_BYTES));
+    LAUNCH(ctx, tiled::k_cover_tile_wc, tgrid, tiled::THREADS, tiled::WC_SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, cfg.B, pc, guard);
+  } else if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
     LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, cfg.B, pc, guard);
   } else {
@@ -1330,7 +1335,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
       spec->synced = true;
       if (spec->h_flags[1] || spec->h_flags[2] || spec->h_flags[3] >= guard.max_len) { spec->tripped = true; return false; }
     }
-    if (*h_f) return false;
+    if (*h_f) { *fail_code = *h_f; return false; }
     if (!h_tot[3]) {
       fo->ready = true;
       fo->n_out = (int64_t)h_tot[2];
@@ -1352,7 +1357,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
       spec->synced = true;
       if (spec->h_flags[1] || spec->h_flags[2] || spec->h_flags[3] >= guard.max_len) { spec->tripped = true; return false; }
     }
-    if (h_fail) return false;
+    if (h_fail) { *fail_code = h_fail; return false; }
   }
   const int64_t np = (int64_t)h_np;
   rec.release();
@@ -1459,11 +1464,20 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
     if (spec && (!want || (int64_t)((n_classes_total * lm.G) >> logw) + 1 > tiled::HIST_CAP || lm.n_chrom > 1024)) { spec->declined = true; return; }
     // A pile-up (many regions on a few kilobases, as real peak data has at promoters) can overflow one tile's tables:
     // retry with tiles four and sixteen times narrower before giving the input to the sort-and-merge path
+    const char* kopt = ctx_opt(ctx, "cover.kernel");      // "rank" / "count": test hook; default = the word-count kernel where it applies
+    bool use_wc = !(kopt && !strcmp(kopt, "rank"));
     for (int attempt = 0; want && !done && attempt < 3; ++attempt) {
       const int lw = logw - 2 * attempt;
       if (lw < 8 || maxlen >= (int64_t)(1ll << lw) - 2) break;
+      int fail_code = 0;
       done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr, plan.n_aggs ? &truns : nullptr,
-                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr, spec, src);
+                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr, spec, src, use_wc, &fail_code);
+      if (!done && fail_code == 5 && use_wc && !(spec && spec->tripped)) {      // only the word-count kernel's own table overflowed: same tiles, rank kernel
+        use_wc = false;
+        --attempt;
+        if (spec) maxlen = spec->h_flags[3];
+        continue;
+      }
       if (spec) {
         if (spec->tripped) return;                     // not eligible after all: the caller starts over with a blocking prepass
         maxlen = spec->h_flags[3];                     // the flags are on the host now: later attempts (and the sort path) are ordinary

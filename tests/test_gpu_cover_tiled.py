@@ -26,6 +26,15 @@ def ex():
     e.close()
 
 
+@pytest.fixture(autouse=True, params=["count", "rank"])
+def tile_kernel(request):
+    """Every test of this module runs with both tile kernels: the word-count kernel (cover_tile_wc.cuh, the default where there
+    is one group) and the bitmap-rank kernel (its fall-back, and the only one for several groups)."""
+    os.environ["GMQL_COVER_KERNEL"] = request.param
+    yield request.param
+    os.environ.pop("GMQL_COVER_KERNEL", None)
+
+
 class forced:
     """Force the tiled path at a given tile width and record which kernels ran."""
 
@@ -105,6 +114,27 @@ def test_tiled_random(ex, flag, logw, seed):
         for gp, op in _params():
             _check(ex, flag, ds, ids, groups, gp, op)
     f.assert_tiled()
+    if groups is None:
+        assert ("k_cover_tile_wc" in f.kernels) == (os.environ["GMQL_COVER_KERNEL"] == "count"), f.kernels
+
+
+def test_word_count_kernel_hands_over_when_a_tile_has_too_many_words_to_resolve(ex):
+    """Two long regions give depth 2 over most of a tile; a chain of short regions, each ending five bases into a 32-position word
+    and the next one starting five bases later, adds a third layer that is open at every word boundary.  Every word then holds a
+    stop and a start at the plateau's maximum: its upper depth bound (4) exceeds every boundary depth (3), so the word-count kernel
+    must resolve ~1 800 words of one tile — more than WC_NCAP = 384.  It raises its flag and the operator is recomputed by the
+    bitmap-rank kernel on the same tiles: same rows as the oracle (one run, AccIndex 3), both kernels ran."""
+    import gmql_b200 as G
+    if os.environ["GMQL_COVER_KERNEL"] != "count":
+        pytest.skip("word-count kernel only")
+    ds = [(1, "chr1", 100, 60100, "*", ()), (2, "chr1", 100, 60100, "*", ())]
+    for k in range(5, 1800):
+        ds.append((3, "chr1", 32 * k + 10, 32 * k + 37, "*", ()))
+    with forced(ex, 16) as f:
+        _check(ex, "COVER", ds, [1, 2, 3], None, (G.N(2), G.ANY()), (O.CoverParam.N(2), O.CoverParam.ANY()))
+        _check(ex, "FLAT", ds, [1, 2, 3], None, (G.N(3), G.N(3)), (O.CoverParam.N(3), O.CoverParam.N(3)))
+    f.assert_tiled()
+    assert "k_cover_tile_wc" in f.kernels and "k_cover_tile<false>" in f.kernels, f.kernels
 
 
 @pytest.mark.parametrize("flag", ["COVER", "FLAT"])

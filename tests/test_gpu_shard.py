@@ -18,6 +18,14 @@ def ex():
     e.close()
 
 
+@pytest.fixture(autouse=True, params=["count", "rank"])
+def tile_kernel(request):
+    import os
+    os.environ["GMQL_COVER_KERNEL"] = request.param
+    yield request.param
+    os.environ.pop("GMQL_COVER_KERNEL", None)
+
+
 def _unsharded(ex, flag, mn, mx, ds):
     import gmql_b200 as G
     from gmql_b200 import _lib as L
