@@ -26,14 +26,15 @@
 
 constexpr int WC_NCAP = 384;                    // words of one tile resolved position by position
 constexpr int WC_SEGCAP = MAXWORDS / 2 + 2;     // stretches of consecutive IN words of one tile
-constexpr uint32_t WC_NONE = 0xffffffffu;
+constexpr int WC_MASKW = MAXWORDS / 32;         // words of the "to be resolved" bit mask
 constexpr size_t WC_SMEM_BYTES = 4 * (size_t)MAXWORDS + 64 * (size_t)WC_NCAP + 2 * 4 * (size_t)HCAP + 32 * (size_t)MAXP + 4 * (size_t)WC_SEGCAP +
-                                 2 * (size_t)WC_SEGCAP + 2 * 3 * (size_t)(WC_NCAP + 2) + 4 * (size_t)WC_NCAP + 16;
+                                 2 * (size_t)WC_SEGCAP + 2 * 3 * (size_t)(WC_NCAP + 2) + 4 * (size_t)WC_NCAP + 2 * 4 * (size_t)WC_MASKW + 16;
 static_assert(WC_SMEM_BYTES <= 56 * 1024, "four blocks per SM");
 
-// x % B == 0 with one multiply-high (x < 2^32): q = floor(x * floor((2^32 - 1) / B) / 2^32) underestimates x / B by at most 2
+// x % B == 0 with one multiply-high (x < 2^32): q = floor(x * floor((2^32 - 1) / B) / 2^32) underestimates x / B by at most 2.
+// Built on the host, passed by value.
 struct BinMod32 { uint32_t B, inv; int big; };
-__device__ __forceinline__ BinMod32 make_binmod32(int64_t B) {
+static inline BinMod32 make_binmod32(int64_t B) {
   BinMod32 m;
   m.big = B >= 0x7fffffffLL ? 1 : 0;
   m.B = B > 0xffffffffLL ? 0u : (uint32_t)B;    // a bin wider than any 32-bit coordinate: only 0 is a multiple
@@ -45,18 +46,20 @@ __device__ __forceinline__ bool is_bin_multiple32(const BinMod32& m, uint32_t x)
   const uint32_t r = x - __umulhi(x, m.inv) * m.B;
   return r == 0u || r == m.B || r == 2u * m.B;
 }
-__device__ __forceinline__ uint32_t lin_base_far(const LinMap& lm, uint32_t x) { return lin_base_slow(lm, x); }
 // the extractor's one-base extension of a region that starts at linear position rs (GenometricCover.scala:353-354)
 __device__ __forceinline__ uint32_t wc_ext(uint32_t rs, uint32_t len, const TileChrom& tc, const LinMap& lm, const BinMod32& bm) {
-  const uint32_t base = (rs >= tc.lo && rs < tc.next) ? tc.base : lin_base_far(lm, rs);
+  const uint32_t base = (rs >= tc.lo && rs < tc.next) ? tc.base : lin_base_slow(lm, rs);
   return (len != 0u && is_bin_multiple32(bm, rs + len - base)) ? 1u : 0u;
 }
 
+// FULL: tiles of 65 536 positions (the production width): 2 048 words, eight per thread, every word valid — the per-word loops then
+// carry no bounds predicates.
+template <bool FULL>
 static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(const uint32_t* __restrict__ P /* tile-local start << 16 | length */, const uint32_t* __restrict__ offS,
-                                                                               int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, LinMap lm, int64_t B, Pieces out, Guard guard) {
+                                                                               int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, LinMap lm, BinMod32 bm, Pieces out, Guard guard) {
   if (guard_trips(guard)) return;
-  extern __shared__ uint32_t sm[];
-  uint32_t* cnt = sm;                                      // [MAXWORDS] starts | stops' << 16 per word; later: slot of the word or WC_NONE
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t* cnt = sm;                                      // [MAXWORDS] starts | stops' << 16 per word
   uint32_t* npos = cnt + MAXWORDS;                         // [WC_NCAP * 16] net change per position of the resolved words (16 bits each)
   uint32_t* hin = npos + WC_NCAP * 16;                     // [HCAP] records of the regions still open at the tile start (they start one tile earlier)
   uint32_t* hout = hin + HCAP;                             // [HCAP] records of this tile's regions still open at its end
@@ -70,25 +73,28 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
   uint32_t* pemin = psmax + MAXP;
   int32_t* segmax = (int32_t*)(pemin + MAXP);              // [WC_SEGCAP] largest boundary depth of every stretch of IN words
   int32_t* slotd0 = segmax + WC_SEGCAP;                    // [WC_NCAP] depth before the resolved word
-  uint16_t* segslot = (uint16_t*)(slotd0 + WC_NCAP);       // [WC_SEGCAP] resolved words before the stretch
+  uint32_t* nmask = (uint32_t*)(slotd0 + WC_NCAP);         // [WC_MASKW] bit w: word w is resolved position by position
+  uint32_t* sbase = nmask + WC_MASKW;                      // [WC_MASKW] resolved words before the mask word
+  uint16_t* segslot = (uint16_t*)(sbase + WC_MASKW);       // [WC_SEGCAP] resolved words before the stretch
   uint16_t* slotw = segslot + WC_SEGCAP;                   // [WC_NCAP + 2] word of every resolved slot (ascending)
   uint16_t* sopen = slotw + (WC_NCAP + 2);                 // [WC_NCAP + 2] run opens inside the slot
   uint16_t* sopre = sopen + (WC_NCAP + 2);                 // [WC_NCAP + 2] opens in the slots before
   __shared__ int32_t scratch[4][NWARPS];                   // one per scan of a tile (see block_excl_scan)
   __shared__ int s_nh, s_nout;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t W = 1u << logw;
-  const int nW = (int)(W >> 5);
-  const int WPT = (nW + THREADS - 1) / THREADS;            // words per thread (consecutive), <= 8
+  const uint32_t W = FULL ? 65536u : (1u << logw);
+  const int nW = FULL ? MAXWORDS : (int)(W >> 5);
+  const int WPT = FULL ? 8 : (nW + THREADS - 1) / THREADS; // words per thread (consecutive), <= 8
+  const int w0 = tid * WPT;
+  const uint32_t vmask = FULL ? 0xffu : (w0 < nW ? ((1u << min(WPT, nW - w0)) - 1u) : 0u);   // this thread's valid words
   const int32_t mn0 = cfg.mn0, mx0 = cfg.mx0;
-  const BinMod32 bm = make_binmod32(B);
 
   // this block's tile range inside [t_lo, t_hi): first tile whose region offset reaches the block's share of the regions
   int64_t t_begin, t_end;
   {
     const uint32_t o_lo = offS[t_lo], o_hi = offS[t_hi];
     int64_t bounds[2];
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < 2; ++q) {
       const int64_t c = (int64_t)blockIdx.x + q;
       if (c <= 0) bounds[q] = t_lo;
@@ -105,16 +111,20 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
   int nh_carry = -1;                                       // -1: the open regions must be found by scanning the previous tile
   int64_t my_cnt = 0;                                      // pieces this block has published (block-uniform)
 
-  // Invariants at the top of every tile iteration (restored by the tile that breaks them): cnt, npos, segmax and the piece
+  // Invariants at the top of every tile iteration (restored by the tile that breaks them): cnt, npos, nmask, segmax and the piece
   // accumulators are clean, s_nout = 0 and s_nh = the number of regions carried in hin (0 when the previous tile must be scanned).
   for (int k = tid; k < MAXWORDS; k += THREADS) cnt[k] = 0;
   for (int k = tid; k < WC_NCAP * 16; k += THREADS) npos[k] = 0;
   for (int k = tid; k < WC_SEGCAP; k += THREADS) segmax[k] = 0;
+  for (int k = tid; k < WC_MASKW; k += THREADS) nmask[k] = 0;
   for (int k = tid; k < MAXP; k += THREADS) { pacc[k] = 0; pcnt[k] = 0; psmin[k] = 0xffffffffu; pemax[k] = 0; psmax[k] = 0; pemin[k] = 0xffffffffu; pen[k] = 0; }
   if (tid == 0) { s_nh = 0; s_nout = 0; }
   __syncthreads();
 
+  TileChrom tch;
+  tch.lo = 1u; tch.next = 0u; tch.base = 0u;               // empty range: recomputed at the first tile and whenever a tile leaves it
   uint32_t s1_next = t_begin < t_end ? offS[t_begin] : 0u, s2_next = t_begin < t_end ? offS[t_begin + 1] : 0u;
+#pragma unroll 1
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
     const uint32_t s0 = s1_next, s1 = s2_next;
     s1_next = s1;
@@ -124,13 +134,14 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     const uint32_t h0 = (scan_prev && tile > 0) ? offS[tile - 1] : s0;
     const uint32_t tile_lo = (uint32_t)tile << logw;
     if (nS_tile == 0 && (scan_prev ? h0 == s0 : nh_carry == 0)) { nh_carry = 0; continue; }   // depth 0 throughout, nothing left open
-    const TileChrom tch = tile_chrom(lm, tile_lo);
+    if (tile_lo < tch.lo || tile_lo >= tch.next) tch = tile_chrom(lm, tile_lo);                // a handful of times per chromosome
     if (tile + 1 < t_end) {                                // the next tile's records: into L2 while this tile is processed
       const uintptr_t a0 = (uintptr_t)(P + s1) & ~(uintptr_t)127, a1 = (uintptr_t)(P + s2_next);
       for (uintptr_t a = a0 + ((uintptr_t)tid << 7); a < a1; a += (uintptr_t)THREADS << 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     }
     // ---- phase A: counts of starts and stops' per word; the tile's own regions stay in registers
     if (scan_prev) {
+#pragma unroll 1
       for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
         const uint32_t i = i0 + tid;
         if (i < s0) {
@@ -144,6 +155,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         }
       }
     } else {
+#pragma unroll 1
       for (int k = tid; k < nh_carry; k += THREADS) {
         const uint32_t pr = hin[k], rs = tile_lo - W + (pr >> 16), len = pr & 0xffffu;
         const uint32_t q = rs + len + wc_ext(rs, len, tch, lm, bm) - tile_lo;
@@ -170,6 +182,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         else { const int slot = atomicAdd(&s_nout, 1); if (slot < HCAP) hout[slot] = rcr[r]; }
       }
     }
+#pragma unroll 1
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
       const uint32_t pr = P[i], q = pr >> 16, len = pr & 0xffffu;
       const uint32_t qe = q + len + wc_ext(tile_lo + q, len, tch, lm, bm);
@@ -181,61 +194,76 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     const int nh = s_nh, nout = s_nout;
     const int32_t depth_in = nh;                           // regions still open when the tile begins
     // ---- phase B: exact depth at every word boundary, classes of the words
-    const int w0 = tid * WPT;
-    uint32_t cw[8];                                        // this thread's words (WPT <= 8) ...
+    uint32_t cw[8];                                        // this thread's words ...
     uint32_t cprev = 0;                                    // ... and the word before them (its class decides whether a stretch starts here)
+    if (FULL) {
+      const uint4 a = ((const uint4*)cnt)[2 * tid], b = ((const uint4*)cnt)[2 * tid + 1];
+      cw[0] = a.x; cw[1] = a.y; cw[2] = a.z; cw[3] = a.w; cw[4] = b.x; cw[5] = b.y; cw[6] = b.z; cw[7] = b.w;
+      cprev = __shfl_up_sync(0xffffffffu, cw[7], 1);
+      if (lane == 0) cprev = tid > 0 ? cnt[w0 - 1] : 0u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cw[j] = ((vmask >> j) & 1u) ? cnt[w0 + j] : 0u;
+      if (w0 > 0 && w0 < nW) cprev = cnt[w0 - 1];
+    }
     int32_t lsum = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      cw[j] = (j < WPT && w0 + j < nW) ? cnt[w0 + j] : 0u;
-      lsum += (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
-    }
-    if (w0 > 0 && w0 < nW) cprev = cnt[w0 - 1];
+    for (int j = 0; j < 8; ++j) lsum += (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
     int32_t tile_net;
-    int32_t d0 = depth_in + block_excl_scan(lsum, &tile_net, scratch[0]);
+    const int32_t d0 = depth_in + block_excl_scan(lsum, &tile_net, scratch[0]);
+    // the counts are in registers: the table is clean again (every read of it happened before the scan's barrier)
+    if (FULL) { ((uint4*)cnt)[2 * tid] = make_uint4(0u, 0u, 0u, 0u); ((uint4*)cnt)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u); }
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if ((vmask >> j) & 1u) cnt[w0 + j] = 0u;
+    }
     // failures (uniform across the block): this tile is skipped and left clean
     if (nh > HCAP || nout > HCAP || nS_tile > (uint32_t)MAX_TILE_REGIONS) {
       if (tid == 0) { *out.fail = nS_tile > (uint32_t)MAX_TILE_REGIONS ? 2 : 4; s_nh = 0; s_nout = 0; }
       nh_carry = -1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < WPT && w0 + j < nW) cnt[w0 + j] = 0;
       __syncthreads();
       continue;
     }
     if (tid == 0) { s_nh = nout; s_nout = 0; }             // every thread has read both (before the scan's barrier)
-    // classes: bit j of m_in / m_thr; a word is IN when its depth bounds lie inside [min, max], THR when they straddle a threshold
+    // classes: bit j of m_in / m_thr; a word is IN when its depth bounds lie inside [min, max], THR when they straddle a threshold.
+    // bmax: largest boundary depth around this thread's IN words; hmax: largest upper bound d + starts of its IN words
     uint32_t m_in = 0, m_thr = 0;
-    bool prev_in;
-    {
-      const int32_t pnet = (int32_t)(cprev & 0xffffu) - (int32_t)(cprev >> 16);
-      const int32_t pd0 = d0 - pnet;
-      prev_in = w0 > 0 && w0 < nW && (pd0 - (int32_t)(cprev >> 16) >= mn0) && (pd0 + (int32_t)(cprev & 0xffffu) <= mx0);
-    }
+    int32_t bmax = -1, hmax = -1;
     {
       int32_t d = d0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (j < WPT && w0 + j < nW) {
-          const int32_t ns = (int32_t)(cw[j] & 0xffffu), ne = (int32_t)(cw[j] >> 16);
-          const int32_t lo = d - ne, hi = d + ns;
-          const bool in = lo >= mn0 && hi <= mx0, outside = hi < mn0 || lo > mx0;
-          if (in) m_in |= 1u << j;
-          else if (!outside) m_thr |= 1u << j;
-          d += ns - ne;
-        }
+        const int32_t ns = (int32_t)(cw[j] & 0xffffu), ne = (int32_t)(cw[j] >> 16);
+        const int32_t lo = d - ne, hi = d + ns, de = d + ns - ne;
+        const bool ok = FULL || ((vmask >> j) & 1u);
+        const bool in = ok && lo >= mn0 && hi <= mx0, outside = hi < mn0 || lo > mx0;
+        if (in) { m_in |= 1u << j; bmax = max(bmax, max(d, de)); hmax = max(hmax, hi); }
+        else if (ok && !outside) m_thr |= 1u << j;
+        d = de;
       }
+    }
+    bool prev_in;
+    {
+      const int32_t pns = (int32_t)(cprev & 0xffffu), pne = (int32_t)(cprev >> 16);
+      const int32_t pd0 = d0 - (pns - pne);
+      prev_in = w0 > 0 && w0 < nW && (pd0 - pne >= mn0) && (pd0 + pns <= mx0);
     }
     // stretches of consecutive IN words: index, largest boundary depth
     const uint32_t m_start = m_in & ~((m_in << 1) | (prev_in ? 1u : 0u));
-    int32_t seg_total;
-    int32_t seg_id = block_excl_scan(__popc(m_start), &seg_total, scratch[1]) - 1;   // stretch open before this thread's first word
-    if (seg_total > WC_SEGCAP) seg_total = WC_SEGCAP;      // cannot happen: a stretch start needs a non-IN word before it
-    {
+    const bool all_in = m_in == vmask;                     // (threads without words: vmask == 0, m_in == 0)
+    int32_t seg_total, seg_id;                             // seg_id: stretch open before this thread's first word (-1: none)
+    if (__syncthreads_or(all_in ? 0 : 1)) {
+      seg_id = block_excl_scan(__popc(m_start), &seg_total, scratch[1]) - 1;
+      if (seg_total > WC_SEGCAP) seg_total = WC_SEGCAP;    // cannot happen: a stretch start needs a non-IN word before it
+    } else { seg_total = 1; seg_id = tid == 0 ? -1 : 0; }  // every word of the tile is IN: one stretch, started by the tile's first word
+    if (all_in) {
+      if (vmask) atomicMax(&segmax[seg_id + (int32_t)(m_start & 1u)], bmax);     // one stretch covers all my words
+    } else if (m_in) {
       int32_t s = seg_id, m = -1, d = d0;                  // d: depth before word j
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 8; ++j) {
         const int32_t de = d + (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
-        if (j < WPT && (m_in >> j) & 1u) {
+        if ((m_in >> j) & 1u) {
           if ((m_start >> j) & 1u) { if (m >= 0) atomicMax(&segmax[s], m); ++s; m = -1; }
           m = max(m, max(d, de));
         } else if (m >= 0) { atomicMax(&segmax[s], m); m = -1; }
@@ -246,105 +274,103 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     __syncthreads();
     // words to resolve: THR, and IN words whose upper bound exceeds what the stretch's boundaries already prove
     uint32_t m_noisy = m_thr;
-    {
+    if (m_in && !(all_in && hmax <= segmax[seg_id + (int32_t)(m_start & 1u)])) {
       int32_t s = seg_id, d = d0;
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 8; ++j) {
-        if (j < WPT && (m_in >> j) & 1u) {
+        if ((m_in >> j) & 1u) {
           if ((m_start >> j) & 1u) ++s;
           if (d + (int32_t)(cw[j] & 0xffffu) > segmax[s]) m_noisy |= 1u << j;
         }
         d += (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
       }
     }
-    int32_t nn_total;
-    int32_t slot0 = block_excl_scan(__popc(m_noisy), &nn_total, scratch[2]);
+    int32_t nn_total = 0, slot0 = 0;
+    if (__syncthreads_or(m_noisy ? 1 : 0)) slot0 = block_excl_scan(__popc(m_noisy), &nn_total, scratch[2]);
     if (nn_total > WC_NCAP) {                              // too many words to resolve: the rank kernel takes the operator
       if (tid == 0) { *out.fail = 5; s_nh = 0; }
       nh_carry = -1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < WPT && w0 + j < nW) cnt[w0 + j] = 0;
       for (int k = tid; k < seg_total; k += THREADS) segmax[k] = 0;
       __syncthreads();
       continue;
     }
-    {
-      int32_t s = seg_id, sl = slot0, d = d0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < WPT && w0 + j < nW) {
-          if ((m_start >> j) & 1u) { ++s; segslot[s] = (uint16_t)sl; }
-          if ((m_noisy >> j) & 1u) { cnt[w0 + j] = (uint32_t)sl; slotw[sl] = (uint16_t)(w0 + j); slotd0[sl] = d; ++sl; }
-          else cnt[w0 + j] = WC_NONE;
-        }
-        d += (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
-      }
-    }
-    __syncthreads();
-    // ---- phase C: per-position net change of the words to resolve
+    const bool cont0 = depth_in >= mn0 && depth_in <= mx0;
+    int32_t open_total = 0;
     if (nn_total > 0) {
+      if (m_noisy) atomicOr(&nmask[w0 >> 5], m_noisy << (w0 & 31));
+      if (vmask && (w0 & 31) == 0) sbase[w0 >> 5] = (uint32_t)slot0;
+      if (m_noisy | m_start) {
+        int32_t s = seg_id, sl = slot0, d = d0;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          if ((m_start >> j) & 1u) { ++s; segslot[s] = (uint16_t)sl; }
+          if ((m_noisy >> j) & 1u) { slotw[sl] = (uint16_t)(w0 + j); slotd0[sl] = d; ++sl; }
+          d += (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
+        }
+      }
+      __syncthreads();
+      // ---- phase C: per-position net change of the words to resolve
+      auto hit = [&](uint32_t q, int v) {                  // event at tile-local position q: counted when its word is resolved
+        const uint32_t wd = q >> 5, mk = nmask[wd >> 5];
+        if ((mk >> (wd & 31u)) & 1u) {
+          const uint32_t sl = sbase[wd >> 5] + (uint32_t)__popc(mk & ((1u << (wd & 31u)) - 1u));
+          delta_add(npos, (int)(sl * 32u + (q & 31u)), v);
+        }
+      };
+#pragma unroll 1
       for (int k = tid; k < nh; k += THREADS) {
         const uint32_t pr = hin[k], rs = tile_lo - W + (pr >> 16), len = pr & 0xffffu;
-        const uint32_t q = rs + len + wc_ext(rs, len, tch, lm, bm) - tile_lo;
-        const uint32_t sl = cnt[q >> 5];
-        if (sl != WC_NONE) delta_add(npos, (int)(sl * 32u + (q & 31u)), -1);
+        hit(rs + len + wc_ext(rs, len, tch, lm, bm) - tile_lo, -1);
       }
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
         if (s0 + tid + r * THREADS < s1) {
           const uint32_t q = rcr[r] >> 16, qe = q + (rcr[r] & 0xffffu) + ((rce >> r) & 1u);
-          const uint32_t sl = cnt[q >> 5];
-          if (sl != WC_NONE) delta_add(npos, (int)(sl * 32u + (q & 31u)), 1);
-          if (qe < W) { const uint32_t s2 = cnt[qe >> 5]; if (s2 != WC_NONE) delta_add(npos, (int)(s2 * 32u + (qe & 31u)), -1); }
+          hit(q, 1);
+          if (qe < W) hit(qe, -1);
         }
       }
+#pragma unroll 1
       for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
         const uint32_t pr = P[i], q = pr >> 16, len = pr & 0xffffu;
-        const uint32_t sl = cnt[q >> 5];
-        if (sl != WC_NONE) delta_add(npos, (int)(sl * 32u + (q & 31u)), 1);
-        const uint32_t qw = (q + len) >> 5;                // the extension moves a stop by one base: its word, or the next one
-        if ((qw < (uint32_t)nW && cnt[qw] != WC_NONE) || (qw + 1 < (uint32_t)nW && cnt[qw + 1] != WC_NONE)) {
-          const uint32_t qe = q + len + wc_ext(tile_lo + q, len, tch, lm, bm);
-          if (qe < W) { const uint32_t s2 = cnt[qe >> 5]; if (s2 != WC_NONE) delta_add(npos, (int)(s2 * 32u + (qe & 31u)), -1); }
-        }
+        hit(q, 1);
+        const uint32_t qe = q + len + wc_ext(tile_lo + q, len, tch, lm, bm);
+        if (qe < W) hit(qe, -1);
       }
-    }
-    __syncthreads();
-    // ---- phase D1: run opens inside every resolved word (one warp per word, lane = position)
-    const bool cont0 = depth_in >= mn0 && depth_in <= mx0;
-    for (int sl = warp; sl < nn_total; sl += NWARPS) {
-      int32_t x = delta_get(npos, sl * 32 + lane);
+      __syncthreads();
+      if (tid < WC_MASKW) nmask[tid] = 0;                  // clean for the next tile (its next writer is several barriers away)
+      // ---- phase D1: run opens inside every resolved word (one warp per word, lane = position)
+#pragma unroll 1
+      for (int sl = warp; sl < nn_total; sl += NWARPS) {
+        int32_t x = delta_get(npos, sl * 32 + lane);
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-      const int32_t d = slotd0[sl] + x;
-      const bool in = d >= mn0 && d <= mx0;
-      const unsigned inm = __ballot_sync(0xffffffffu, in);
-      const int32_t dd = slotd0[sl];
-      const unsigned prevm = (inm << 1) | ((dd >= mn0 && dd <= mx0) ? 1u : 0u);
-      if (lane == 0) sopen[sl] = (uint16_t)__popc(inm & ~prevm);
-    }
-    __syncthreads();
-    int32_t open_total;
-    {
-      // two slots per thread: WC_NCAP <= 2 * THREADS
-      const int a = 2 * tid, b = 2 * tid + 1;
-      const int32_t va = a < nn_total ? (int32_t)sopen[a] : 0, vb = b < nn_total ? (int32_t)sopen[b] : 0;
-      const int32_t pre = block_excl_scan(va + vb, &open_total, scratch[3]);
-      if (a <= nn_total && a < WC_NCAP + 2) sopre[a] = (uint16_t)pre;
-      if (b <= nn_total && b < WC_NCAP + 2) sopre[b] = (uint16_t)(pre + va);
+        for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        const int32_t dd = slotd0[sl];
+        const int32_t d = dd + x;
+        const unsigned inm = __ballot_sync(0xffffffffu, d >= mn0 && d <= mx0);
+        const unsigned prevm = (inm << 1) | ((dd >= mn0 && dd <= mx0) ? 1u : 0u);
+        if (lane == 0) sopen[sl] = (uint16_t)__popc(inm & ~prevm);
+      }
+      __syncthreads();
+      {
+        // two slots per thread: WC_NCAP <= 2 * THREADS
+        const int a = 2 * tid, b = 2 * tid + 1;
+        const int32_t va = a < nn_total ? (int32_t)sopen[a] : 0, vb = b < nn_total ? (int32_t)sopen[b] : 0;
+        const int32_t pre = block_excl_scan(va + vb, &open_total, scratch[3]);
+        if (a <= nn_total) sopre[a] = (uint16_t)pre;
+        if (b <= nn_total) sopre[b] = (uint16_t)(pre + va);
+      }
     }
     const int np = (cont0 ? 1 : 0) + open_total;
     if (np > MAXP) {
       if (tid == 0) { *out.fail = 3; s_nh = 0; }
       nh_carry = -1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (j < WPT && w0 + j < nW) cnt[w0 + j] = 0;
       for (int k = tid; k < seg_total; k += THREADS) segmax[k] = 0;
       for (int k = tid; k < nn_total * 16; k += THREADS) npos[k] = 0;
       __syncthreads();
       continue;
     }
-    __syncthreads();
+    if (nn_total > 0) __syncthreads();                     // sopre is complete
     // ---- phase D2: pieces.  Resolved words: exact opens, closes and maxima; stretches of IN words: their boundary maximum
     const int32_t d_end = depth_in + tile_net;
     const bool reach_end = np > 0 && d_end >= mn0 && d_end <= mx0;
@@ -352,13 +378,12 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       if (cont0) { pst[0] = tile_lo; atomicMax(&pacc[0], depth_in); }
       if (reach_end) pen[np - 1] = tile_lo + W;
     }
+#pragma unroll 1
     for (int sl = warp; sl < nn_total; sl += NWARPS) {
-      const int32_t raw = delta_get(npos, sl * 32 + lane);
-      int32_t x = raw;
+      int32_t x = delta_get(npos, sl * 32 + lane);
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-      __syncwarp();
-      if (lane < 16) npos[sl * 16 + lane] = 0;             // clean for the next tile
+      if (lane < 16) npos[sl * 16 + lane] = 0;             // clean for the next tile (every lane's value went through the shuffles above)
       const int32_t dd = slotd0[sl];
       const int32_t d = dd + x;
       const bool in = d >= mn0 && d <= mx0;
@@ -370,8 +395,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       const int mine = base + __popc(openm & (0xffffffffu >> (31 - lane)));      // piece this position belongs to when in range
       if ((openm >> lane) & 1u) pst[mine] = pos;
       if ((closem >> lane) & 1u) pen[base + __popc(openm & ((1u << lane) - 1u))] = pos;
-      // maximum depth of every in-range stretch of the word
-      unsigned todo = inm;
+      unsigned todo = inm;                                 // maximum depth of every in-range stretch of the word
       while (todo) {
         const int first = __ffs(todo) - 1;
         const int pc = __shfl_sync(0xffffffffu, mine, first);
@@ -381,54 +405,58 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         todo &= ~__ballot_sync(0xffffffffu, sel);
       }
     }
-    {
+    if (m_start) {
       int32_t s = seg_id;
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 8; ++j) {
-        if (j < WPT && (m_start >> j) & 1u) {
+        if ((m_start >> j) & 1u) {
           ++s;
-          const int pc = (cont0 ? 1 : 0) + (int)sopre[segslot[s]] - 1;           // the run this stretch lies in
+          const int pc = (cont0 ? 1 : 0) + (nn_total > 0 ? (int)sopre[segslot[s]] : 0) - 1;   // the run this stretch lies in
           if (pc >= 0) atomicMax(&pacc[pc], segmax[s]);
         }
       }
     }
-    // words before the first stretch start of a thread continue the stretch of an earlier thread: nothing to add
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) if (j < WPT && w0 + j < nW) cnt[w0 + j] = 0;       // no reader left
-    for (int k = tid; k < seg_total; k += THREADS) segmax[k] = 0;
+    for (int k = tid; k < seg_total; k += THREADS) segmax[k] = 0;                 // no reader left
     // ---- phase E: GMAP4, region-driven: the regions open at the tile start, then the tile's own
-    if (np == 1) {
-      // one piece (the usual case under dense coverage): no search, thread-local accumulation, one reduction per warp
-      const uint32_t p0 = pst[0], p1 = pen[0];
-      int32_t c = 0;
-      uint32_t a_smin = 0xffffffffu, a_emax = 0, a_smax = 0, a_emin = 0xffffffffu;
-      if (!cont0) {                                         // the open regions only feed a run that STARTS in this tile
-        for (int k = tid; k < nh; k += THREADS) {
-          const uint32_t rs = tile_lo - W + (hin[k] >> 16), re = rs + (hin[k] & 0xffffu);
-          if (re > tile_lo && p1 > rs && p0 < re) { ++c; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
+    if (np == 1 || np == 2) {
+      // one or two pieces (the usual cases under dense coverage): no search, thread-local accumulation, one reduction per warp and piece
+#pragma unroll 1
+      for (int pi = 0; pi < np; ++pi) {
+        const uint32_t p0 = pst[pi], p1 = pen[pi];
+        const bool from_prev = pi == 0 && cont0;           // the open regions only feed a run that STARTS in this tile
+        int32_t c = 0;
+        uint32_t a_smin = 0xffffffffu, a_emax = 0, a_smax = 0, a_emin = 0xffffffffu;
+        if (!from_prev) {
+#pragma unroll 1
+          for (int k = tid; k < nh; k += THREADS) {
+            const uint32_t rs = tile_lo - W + (hin[k] >> 16), re = rs + (hin[k] & 0xffffu);
+            if (re > tile_lo && p1 > rs && p0 < re) { ++c; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
+          }
         }
-      }
 #pragma unroll
-      for (int r = 0; r < RC; ++r) {
-        if (s0 + tid + r * THREADS < s1) {
-          const uint32_t rs = tile_lo + (rcr[r] >> 16), re = rs + (rcr[r] & 0xffffu);
+        for (int r = 0; r < RC; ++r) {
+          if (s0 + tid + r * THREADS < s1) {
+            const uint32_t rs = tile_lo + (rcr[r] >> 16), re = rs + (rcr[r] & 0xffffu);
+            if (p1 > rs && p0 < re) { ++c; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
+          }
+        }
+#pragma unroll 1
+        for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
+          const uint32_t pr = P[i], rs = tile_lo + (pr >> 16), re = rs + (pr & 0xffffu);
           if (p1 > rs && p0 < re) { ++c; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
         }
+        c = __reduce_add_sync(0xffffffffu, c);
+        a_smin = __reduce_min_sync(0xffffffffu, a_smin); a_emax = __reduce_max_sync(0xffffffffu, a_emax);
+        a_smax = __reduce_max_sync(0xffffffffu, a_smax); a_emin = __reduce_min_sync(0xffffffffu, a_emin);
+        if (lane == 0 && c > 0) {
+          atomicAdd(&pcnt[pi], c);
+          atomicMin(&psmin[pi], a_smin); atomicMax(&pemax[pi], a_emax);
+          atomicMax(&psmax[pi], a_smax); atomicMin(&pemin[pi], a_emin);
+        }
       }
-      for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-        const uint32_t pr = P[i], rs = tile_lo + (pr >> 16), re = rs + (pr & 0xffffu);
-        if (p1 > rs && p0 < re) { ++c; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
-      }
-      c = __reduce_add_sync(0xffffffffu, c);
-      a_smin = __reduce_min_sync(0xffffffffu, a_smin); a_emax = __reduce_max_sync(0xffffffffu, a_emax);
-      a_smax = __reduce_max_sync(0xffffffffu, a_smax); a_emin = __reduce_min_sync(0xffffffffu, a_emin);
-      if (lane == 0 && c > 0) {
-        atomicAdd(&pcnt[0], c);
-        atomicMin(&psmin[0], a_smin); atomicMax(&pemax[0], a_emax);
-        atomicMax(&psmax[0], a_smax); atomicMin(&pemin[0], a_emin);
-      }
-    } else if (np > 1) {
+    } else if (np > 2) {
+#pragma unroll 1
       for (int k0h = 0; k0h < nh; k0h += THREADS) {
         const int k = k0h + tid;
         bool valid = k < nh;
@@ -436,14 +464,16 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         if (valid) { rs = tile_lo - W + (hin[k] >> 16); re = rs + (hin[k] & 0xffffu); valid = re > tile_lo; }
         gmap4_round(valid, rs, re, false, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
-#pragma unroll
+#pragma unroll 1
       for (int r = 0; r < RC; ++r) {
         if ((uint32_t)(r * THREADS) < nS_tile) {            // block-uniform
           const bool valid = s0 + tid + r * THREADS < s1;
-          const uint32_t rs = tile_lo + (rcr[r] >> 16);
-          gmap4_round(valid, rs, rs + (rcr[r] & 0xffffu), true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
+          const uint32_t pr = valid ? P[s0 + tid + r * THREADS] : 0u;
+          const uint32_t rs = tile_lo + (pr >> 16);
+          gmap4_round(valid, rs, rs + (pr & 0xffffu), true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
         }
       }
+#pragma unroll 1
       for (uint32_t i0 = s0 + RC * THREADS; i0 < s1; i0 += THREADS) {
         const uint32_t i = i0 + tid;
         const bool valid = i < s1;

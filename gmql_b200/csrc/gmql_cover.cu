@@ -1292,8 +1292,14 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
   if (cfg.n_groups == 1 && use_wc) {
     // the word-count kernel (cover_tile_wc.cuh); a tile with too many words to resolve sends the operator to the rank kernel
-    CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile_wc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::WC_SMEM_BYTES));
-    LAUNCH(ctx, tiled::k_cover_tile_wc, tgrid, tiled::THREADS, tiled::WC_SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, cfg.B, pc, guard);
+    const tiled::BinMod32 bm = tiled::make_binmod32(cfg.B);
+    if (logw == tiled::MAX_LOGW) {
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile_wc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::WC_SMEM_BYTES));
+      LAUNCH(ctx, tiled::k_cover_tile_wc<true>, tgrid, tiled::THREADS, tiled::WC_SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, bm, pc, guard);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile_wc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::WC_SMEM_BYTES));
+      LAUNCH(ctx, tiled::k_cover_tile_wc<false>, tgrid, tiled::THREADS, tiled::WC_SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, bm, pc, guard);
+    }
   } else if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
     LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, cfg.B, pc, guard);
