@@ -110,6 +110,10 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
   }
   int nh_carry = -1;                                       // -1: the open regions must be found by scanning the previous tile
   int64_t my_cnt = 0;                                      // pieces this block has published (block-uniform)
+  // A run that crosses tile edges only needs its OVERALL maximum to be exact (the stitch kernel takes the maximum over its pieces).
+  // acc_carry = what the earlier tiles of this block already proved about the run still open at the previous tile's end (0: none):
+  // words whose depth bound stays below it need no resolution even when they hold this tile's own maximum.
+  int32_t acc_carry = 0;
 
   // Invariants at the top of every tile iteration (restored by the tile that breaks them): cnt, npos, nmask, segmax and the piece
   // accumulators are clean, s_nout = 0 and s_nh = the number of regions carried in hin (0 when the previous tile must be scanned).
@@ -133,7 +137,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     const bool scan_prev = nh_carry < 0;
     const uint32_t h0 = (scan_prev && tile > 0) ? offS[tile - 1] : s0;
     const uint32_t tile_lo = (uint32_t)tile << logw;
-    if (nS_tile == 0 && (scan_prev ? h0 == s0 : nh_carry == 0)) { nh_carry = 0; continue; }   // depth 0 throughout, nothing left open
+    if (nS_tile == 0 && (scan_prev ? h0 == s0 : nh_carry == 0)) { nh_carry = 0; acc_carry = 0; continue; }   // depth 0 throughout, nothing left open
     if (tile_lo < tch.lo || tile_lo >= tch.next) tch = tile_chrom(lm, tile_lo);                // a handful of times per chromosome
     if (tile + 1 < t_end) {                                // the next tile's records: into L2 while this tile is processed
       const uintptr_t a0 = (uintptr_t)(P + s1) & ~(uintptr_t)127, a1 = (uintptr_t)(P + s2_next);
@@ -220,7 +224,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     // failures (uniform across the block): this tile is skipped and left clean
     if (nh > HCAP || nout > HCAP || nS_tile > (uint32_t)MAX_TILE_REGIONS) {
       if (tid == 0) { *out.fail = nS_tile > (uint32_t)MAX_TILE_REGIONS ? 2 : 4; s_nh = 0; s_nout = 0; }
-      nh_carry = -1;
+      nh_carry = -1; acc_carry = 0;
       __syncthreads();
       continue;
     }
@@ -271,6 +275,8 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       }
       if (m >= 0) atomicMax(&segmax[s], m);
     }
+    // the run entering the tile: its first stretch (index 0, when the tile's first word is IN) inherits what earlier tiles proved
+    if (tid == 0 && acc_carry > 0 && (m_in & 1u)) atomicMax(&segmax[0], acc_carry);
     __syncthreads();
     // words to resolve: THR, and IN words whose upper bound exceeds what the stretch's boundaries already prove
     uint32_t m_noisy = m_thr;
@@ -289,7 +295,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     if (__syncthreads_or(m_noisy ? 1 : 0)) slot0 = block_excl_scan(__popc(m_noisy), &nn_total, scratch[2]);
     if (nn_total > WC_NCAP) {                              // too many words to resolve: the rank kernel takes the operator
       if (tid == 0) { *out.fail = 5; s_nh = 0; }
-      nh_carry = -1;
+      nh_carry = -1; acc_carry = 0;
       for (int k = tid; k < seg_total; k += THREADS) segmax[k] = 0;
       __syncthreads();
       continue;
@@ -310,8 +316,12 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       }
       __syncthreads();
       // ---- phase C: per-position net change of the words to resolve
+      // (which of the 64 mask words hold anything at all: two registers, so that most events never touch shared memory)
+      const unsigned nm_lo = __ballot_sync(0xffffffffu, nmask[lane] != 0u), nm_hi = __ballot_sync(0xffffffffu, nmask[32 + lane] != 0u);
       auto hit = [&](uint32_t q, int v) {                  // event at tile-local position q: counted when its word is resolved
-        const uint32_t wd = q >> 5, mk = nmask[wd >> 5];
+        const uint32_t wd = q >> 5;
+        if (!(((wd & 1024u) ? nm_hi : nm_lo) >> ((wd >> 5) & 31u) & 1u)) return;
+        const uint32_t mk = nmask[wd >> 5];
         if ((mk >> (wd & 31u)) & 1u) {
           const uint32_t sl = sbase[wd >> 5] + (uint32_t)__popc(mk & ((1u << (wd & 31u)) - 1u));
           delta_add(npos, (int)(sl * 32u + (q & 31u)), v);
@@ -352,7 +362,15 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         if (lane == 0) sopen[sl] = (uint16_t)__popc(inm & ~prevm);
       }
       __syncthreads();
-      {
+      if (nn_total <= 32) {
+        // few resolved words (the usual case): every warp sums the open counts itself, no block-wide scan
+        const int32_t v = lane < nn_total ? (int32_t)sopen[lane] : 0;
+        int32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        open_total = __shfl_sync(0xffffffffu, x, 31);
+        if (warp == 0) { sopre[lane] = (uint16_t)(x - v); if (lane == 31) sopre[32] = (uint16_t)x; }
+      } else {
         // two slots per thread: WC_NCAP <= 2 * THREADS
         const int a = 2 * tid, b = 2 * tid + 1;
         const int32_t va = a < nn_total ? (int32_t)sopen[a] : 0, vb = b < nn_total ? (int32_t)sopen[b] : 0;
@@ -364,7 +382,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     const int np = (cont0 ? 1 : 0) + open_total;
     if (np > MAXP) {
       if (tid == 0) { *out.fail = 3; s_nh = 0; }
-      nh_carry = -1;
+      nh_carry = -1; acc_carry = 0;
       for (int k = tid; k < seg_total; k += THREADS) segmax[k] = 0;
       for (int k = tid; k < nn_total * 16; k += THREADS) npos[k] = 0;
       __syncthreads();
@@ -418,6 +436,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     }
     __syncthreads();
     for (int k = tid; k < seg_total; k += THREADS) segmax[k] = 0;                 // no reader left
+    acc_carry = reach_end ? pacc[np - 1] : 0;              // block-uniform: read after the barrier, before the tables are cleaned
     // ---- phase E: GMAP4, region-driven: the regions open at the tile start, then the tile's own
     if (np == 1 || np == 2) {
       // one or two pieces (the usual cases under dense coverage): no search, thread-local accumulation, one reduction per warp and piece

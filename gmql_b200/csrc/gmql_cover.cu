@@ -1273,6 +1273,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   // its predecessor's regions), at most four waves
   const int64_t resident = (int64_t)ctx->num_sms * tiled::CTAS_PER_SM;
   int64_t waves = std::max<int64_t>(1, std::min<int64_t>(4, (t_hi - t_lo + resident * 8) / (resident * 16)));
+  if (cfg.n_groups == 1 && use_wc) waves = 1;             // the word-count kernel's blocks cost more to set up; their ranges hold equal shares of the regions anyway
   if (const char* we = ctx_opt(ctx, "cover.waves")) waves = std::max(1, atoi(we));   // tuning hook
   const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), resident * waves));
   const int64_t seg = std::max<int64_t>(4096, (n / 16 + 2 * nT) / tgrid + 1);
