@@ -1276,7 +1276,12 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   if (cfg.n_groups == 1 && use_wc) waves = 1;             // the word-count kernel's blocks cost more to set up; their ranges hold equal shares of the regions anyway
   if (const char* we = ctx_opt(ctx, "cover.waves")) waves = std::max(1, atoi(we));   // tuning hook
   const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), resident * waves));
-  const int64_t seg = std::max<int64_t>(4096, (n / 16 + 2 * nT) / tgrid + 1);
+  // piece capacity of a block's segment.  Dense inputs (the tile path's home ground) make few pieces: about two per tile.  With few
+  // regions per tile nearly every region can be a piece of its own (at most MAXP per tile); the blocks hold equal shares of the
+  // regions, so the pieces spread about evenly — half as much again covers the difference
+  const int64_t n_own_tiles = std::max<int64_t>(t_hi - t_lo, 1);
+  const int64_t est_pieces = n >= 1024 * n_own_tiles ? n / 16 + 2 * nT : std::min<int64_t>(n + n_own_tiles, n_own_tiles * (int64_t)tiled::MAXP) * 3 / 2;
+  const int64_t seg = std::max<int64_t>(4096, est_pieces / tgrid + 1);
   const int64_t cap = seg * tgrid;
   GMQL_REQUIRE(cap < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "piece table too large");
   DevBuf<uint32_t> pstart(ctx, cap), pend(ctx, cap), smin(ctx, cap), emax(ctx, cap), smax(ctx, cap), emin(ctx, cap);

@@ -115,7 +115,7 @@ def test_c5_production_route_against_the_oracle(ex):
     dset, view, keep = _upload(ex, ds)
     assert view.chrom_bits == 8 and view.stop_is_length == 16 and not view.sample and view.sample_offsets and view.chrom_span_hint
     (got_c, got_m), kern = _profile(ex, lambda: _pipeline(ex, view, 640))
-    for name in ("k_multisplit<tiled::MSP_NARROW>", "k_multisplit<tiled::MSP_FINE>", "k_cover_tile", "k_stitch_small", "k_map_index_small", "k_map_count_grouped<true, true>"):
+    for name in ("k_multisplit<tiled::MSP_NARROW>", "k_multisplit<tiled::MSP_FINE>", "k_cover_tile", "k_stitch_small", "k_map_index_small", "k_map_count_lean"):
         assert name in kern, (name, kern)
     for name in ("k_prepass_hist", "k_cover_prepass", "k_tile_hist", "k_widen_chrom", "k_stop_from_length", "k_expand_sample_offsets", "k_map_stream", "onesweep"):
         assert name not in kern, (name, kern)
@@ -134,6 +134,14 @@ def test_c5_production_route_against_the_oracle(ex):
     for a, b in zip(gen_c, got_c):
         assert np.array_equal(a, b)
     assert np.array_equal(gen_m, got_m)
+    # ... and MAP through the general per-sample kernel (the lean kernel's fall-back for references with strands or duplicates)
+    os.environ["GMQL_MAP_LEAN"] = "0"
+    try:
+        (_, grp_m), kern3 = _profile(ex, lambda: _pipeline(ex, view, 640))
+    finally:
+        os.environ.pop("GMQL_MAP_LEAN", None)
+    assert "k_map_count_grouped<true, true>" in kern3 and "k_map_count_lean" not in kern3
+    assert np.array_equal(grp_m, want_m)
     ex.lib.gmql_dataset_free(ex.ctx, dset)
 
 
@@ -247,6 +255,65 @@ class RegionDatasetFromRuns:
         chrom, start, stop = (a[sl] for a in self.cols)
         n = len(chrom)
         return self.cls(self.names, chrom, start, stop, np.zeros(n, np.int8), np.zeros(n, np.int32), np.array([0], np.int64))
+
+
+@pytest.mark.parametrize("n_ref", [1, 900, 9000])
+def test_lean_count_kernel_against_the_oracle(ex, n_ref):
+    """k_map_count_lean directly against the C oracle (GenometricMap71.scala:81-147) on what its vector loads and 32-bit pipeline
+    could get wrong: samples whose first / last rows share an aligned group of four with their neighbours (sizes 1, 2, 3, 5, empty
+    samples, a last group cut by the end of the dataset), a sorted annotation whose regions OVERLAP (running-maximum walk), long
+    reference regions, experiment rows beyond the last reference region of their chromosome and zero-length rows."""
+    from gmql_b200 import _lib as L
+    from gmql_b200.regions import RegionDataset
+    from oracle import c_oracle as CO
+    rng = np.random.Generator(np.random.PCG64(700 + n_ref))
+    span = 2_000_000
+    names = ["chr1", "chr2", "chrX", "chrY"]
+    chrom = rng.integers(0, 3, n_ref).astype(np.int32)        # chrY holds no reference region
+    start = rng.integers(0, span, n_ref)
+    ln = rng.integers(1, 1200, n_ref)
+    ln[rng.random(n_ref) < 0.03] = 300_000
+    o = np.lexsort((start, chrom))
+    chrom, start, ln = chrom[o], start[o], ln[o]
+    ref = RegionDataset(names, chrom, start, start + ln, np.zeros(n_ref, np.int8), np.zeros(n_ref, np.int32), np.array([5], np.int64))
+    sizes = [30001, 1, 20002, 0, 60003, 3, 5, 2, 0, 41]
+    smp = np.repeat(np.arange(len(sizes)), sizes).astype(np.int32)
+    n_exp = smp.shape[0]
+    assert n_exp % 4 != 0
+    ec = rng.integers(0, 4, n_exp).astype(np.int32)
+    es = rng.integers(0, span + 500_000, n_exp)
+    el = rng.integers(0, 3000, n_exp)
+    el[::53] = 0
+    exp = RegionDataset(names, ec, es, es + el, np.zeros(n_exp, np.int8), smp, np.arange(10, 10 + len(sizes), dtype=np.int64))
+    dset, view, keep = _upload(ex, exp)
+    c_ref, k1 = ref.as_c(sorted_by_position=True)
+    c_ref.strand = None                                       # no strand column: every reference region is '*'
+    n_pairs = len(sizes) - 1                                  # sample 8 (empty) is in no pair
+    order = [b for b in range(len(sizes)) if b != 8]
+    pairs = (L.Pair * n_pairs)()
+    for k, b in enumerate(order):
+        pairs[k].left_sample, pairs[k].right_sample = 0, b
+
+    def run():
+        out = C.c_void_p()
+        ex._check(ex.lib.gmql_map(ex.ctx, C.byref(c_ref), C.byref(view), pairs, n_pairs, (L.Agg * 1)(), 0, C.byref(out)))
+        (cnt,) = _cols(ex, out, [(L.COL_MAP_COUNT, np.int32)])
+        ex.lib.gmql_result_free(ex.ctx, out)
+        return cnt
+    os.environ["GMQL_MAP_GROUPED"] = "1"
+    try:
+        got, kern = _profile(ex, run)
+        os.environ["GMQL_MAP_LEAN"] = "0"
+        got_g, kern_g = _profile(ex, run)
+    finally:
+        os.environ.pop("GMQL_MAP_GROUPED", None)
+        os.environ.pop("GMQL_MAP_LEAN", None)
+    assert "k_map_count_lean" in kern and "k_map_count_grouped" in kern_g and "k_map_count_lean" not in kern_g, (kern, kern_g)
+    pidx = np.stack([np.zeros(n_pairs, np.int32), np.array(order, np.int32)], axis=1)
+    want = CO.map_rows(ref, exp, pidx, None, None, 50000)["count"]
+    assert want.sum() > 0
+    assert np.array_equal(got, want) and np.array_equal(got_g, want)
+    ex.lib.gmql_dataset_free(ex.ctx, dset)
 
 
 def test_grouped_kernel_is_not_used_with_duplicate_reference_records(ex):
