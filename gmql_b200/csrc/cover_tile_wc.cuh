@@ -31,21 +31,6 @@ constexpr size_t WC_SMEM_BYTES = 4 * (size_t)MAXWORDS + 64 * (size_t)WC_NCAP + 2
                                  2 * (size_t)WC_SEGCAP + 2 * 3 * (size_t)(WC_NCAP + 2) + 4 * (size_t)WC_NCAP + 2 * 4 * (size_t)WC_MASKW + 16;
 static_assert(WC_SMEM_BYTES <= 56 * 1024, "four blocks per SM");
 
-// x % B == 0 with one multiply-high (x < 2^32): q = floor(x * floor((2^32 - 1) / B) / 2^32) underestimates x / B by at most 2.
-// Built on the host, passed by value.
-struct BinMod32 { uint32_t B, inv; int big; };
-static inline BinMod32 make_binmod32(int64_t B) {
-  BinMod32 m;
-  m.big = B >= 0x7fffffffLL ? 1 : 0;
-  m.B = B > 0xffffffffLL ? 0u : (uint32_t)B;    // a bin wider than any 32-bit coordinate: only 0 is a multiple
-  m.inv = m.big ? 0u : 0xffffffffu / m.B;
-  return m;
-}
-__device__ __forceinline__ bool is_bin_multiple32(const BinMod32& m, uint32_t x) {
-  if (m.big) return x == 0u || (m.B != 0u && x == m.B);
-  const uint32_t r = x - __umulhi(x, m.inv) * m.B;
-  return r == 0u || r == m.B || r == 2u * m.B;
-}
 // the extractor's one-base extension of a region that starts at linear position rs (GenometricCover.scala:353-354)
 __device__ __forceinline__ uint32_t wc_ext(uint32_t rs, uint32_t len, const TileChrom& tc, const LinMap& lm, const BinMod32& bm) {
   const uint32_t base = (rs >= tc.lo && rs < tc.next) ? tc.base : lin_base_slow(lm, rs);
@@ -54,10 +39,14 @@ __device__ __forceinline__ uint32_t wc_ext(uint32_t rs, uint32_t len, const Tile
 
 // FULL: tiles of 65 536 positions (the production width): 2 048 words, eight per thread, every word valid — the per-word loops then
 // carry no bounds predicates.
-template <bool FULL>
+// XB: the partition already decided the one-base extension and left it in bit 15 of the record (lengths below 32 768, the host
+// knows the longest region): the tile kernel then never looks at chromosome offsets or the bin size.
+template <bool FULL, bool XB>
 static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(const uint32_t* __restrict__ P /* tile-local start << 16 | length */, const uint32_t* __restrict__ offS,
                                                                                int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, LinMap lm, BinMod32 bm, Pieces out, Guard guard) {
   if (guard_trips(guard)) return;
+#define RLEN(pr) (XB ? ((pr) & 0x7fffu) : ((pr) & 0xffffu))
+#define REXT(pr, rs, len) (XB ? (((pr) >> 15) & 1u) : wc_ext((rs), (len), tch, lm, bm))
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* cnt = sm;                                      // [MAXWORDS] starts | stops' << 16 per word
   uint32_t* npos = cnt + MAXWORDS;                         // [WC_NCAP * 16] net change per position of the resolved words (16 bits each)
@@ -138,7 +127,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     const uint32_t h0 = (scan_prev && tile > 0) ? offS[tile - 1] : s0;
     const uint32_t tile_lo = (uint32_t)tile << logw;
     if (nS_tile == 0 && (scan_prev ? h0 == s0 : nh_carry == 0)) { nh_carry = 0; acc_carry = 0; continue; }   // depth 0 throughout, nothing left open
-    if (tile_lo < tch.lo || tile_lo >= tch.next) tch = tile_chrom(lm, tile_lo);                // a handful of times per chromosome
+    if (!XB && (tile_lo < tch.lo || tile_lo >= tch.next)) tch = tile_chrom(lm, tile_lo);                // a handful of times per chromosome
     if (tile + 1 < t_end) {                                // the next tile's records: into L2 while this tile is processed
       const uintptr_t a0 = (uintptr_t)(P + s1) & ~(uintptr_t)127, a1 = (uintptr_t)(P + s2_next);
       for (uintptr_t a = a0 + ((uintptr_t)tid << 7); a < a1; a += (uintptr_t)THREADS << 7) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
@@ -149,8 +138,8 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
         const uint32_t i = i0 + tid;
         if (i < s0) {
-          const uint32_t pr = P[i], rs = tile_lo - W + (pr >> 16), len = pr & 0xffffu;
-          const uint32_t ee = rs + len + wc_ext(rs, len, tch, lm, bm);
+          const uint32_t pr = P[i], rs = tile_lo - W + (pr >> 16), len = RLEN(pr);
+          const uint32_t ee = rs + len + REXT(pr, rs, len);
           if (ee >= tile_lo) {
             const int slot = atomicAdd(&s_nh, 1);
             if (slot < HCAP) hin[slot] = pr;
@@ -161,8 +150,8 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     } else {
 #pragma unroll 1
       for (int k = tid; k < nh_carry; k += THREADS) {
-        const uint32_t pr = hin[k], rs = tile_lo - W + (pr >> 16), len = pr & 0xffffu;
-        const uint32_t q = rs + len + wc_ext(rs, len, tch, lm, bm) - tile_lo;
+        const uint32_t pr = hin[k], rs = tile_lo - W + (pr >> 16), len = RLEN(pr);
+        const uint32_t q = rs + len + REXT(pr, rs, len) - tile_lo;
         atomicAdd(&cnt[q >> 5], 0x10000u);
       }
     }
@@ -177,8 +166,8 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
       if (s0 + tid + r * THREADS < s1) {
-        const uint32_t q = rcr[r] >> 16, len = rcr[r] & 0xffffu;
-        const uint32_t ex = wc_ext(tile_lo + q, len, tch, lm, bm);
+        const uint32_t q = rcr[r] >> 16, len = RLEN(rcr[r]);
+        const uint32_t ex = REXT(rcr[r], tile_lo + q, len);
         rce |= ex << r;
         atomicAdd(&cnt[q >> 5], 1u);
         const uint32_t qe = q + len + ex;
@@ -188,8 +177,8 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     }
 #pragma unroll 1
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      const uint32_t pr = P[i], q = pr >> 16, len = pr & 0xffffu;
-      const uint32_t qe = q + len + wc_ext(tile_lo + q, len, tch, lm, bm);
+      const uint32_t pr = P[i], q = pr >> 16, len = RLEN(pr);
+      const uint32_t qe = q + len + REXT(pr, tile_lo + q, len);
       atomicAdd(&cnt[q >> 5], 1u);
       if (qe < W) atomicAdd(&cnt[qe >> 5], 0x10000u);
       else { const int slot = atomicAdd(&s_nout, 1); if (slot < HCAP) hout[slot] = pr; }
@@ -329,22 +318,22 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       };
 #pragma unroll 1
       for (int k = tid; k < nh; k += THREADS) {
-        const uint32_t pr = hin[k], rs = tile_lo - W + (pr >> 16), len = pr & 0xffffu;
-        hit(rs + len + wc_ext(rs, len, tch, lm, bm) - tile_lo, -1);
+        const uint32_t pr = hin[k], rs = tile_lo - W + (pr >> 16), len = RLEN(pr);
+        hit(rs + len + REXT(pr, rs, len) - tile_lo, -1);
       }
 #pragma unroll
       for (int r = 0; r < RC; ++r) {
         if (s0 + tid + r * THREADS < s1) {
-          const uint32_t q = rcr[r] >> 16, qe = q + (rcr[r] & 0xffffu) + ((rce >> r) & 1u);
+          const uint32_t q = rcr[r] >> 16, qe = q + RLEN(rcr[r]) + ((XB ? (rcr[r] >> 15) : (rce >> r)) & 1u);
           hit(q, 1);
           if (qe < W) hit(qe, -1);
         }
       }
 #pragma unroll 1
       for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-        const uint32_t pr = P[i], q = pr >> 16, len = pr & 0xffffu;
+        const uint32_t pr = P[i], q = pr >> 16, len = RLEN(pr);
         hit(q, 1);
-        const uint32_t qe = q + len + wc_ext(tile_lo + q, len, tch, lm, bm);
+        const uint32_t qe = q + len + REXT(pr, tile_lo + q, len);
         if (qe < W) hit(qe, -1);
       }
       __syncthreads();
@@ -449,20 +438,20 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         if (!from_prev) {
 #pragma unroll 1
           for (int k = tid; k < nh; k += THREADS) {
-            const uint32_t rs = tile_lo - W + (hin[k] >> 16), re = rs + (hin[k] & 0xffffu);
+            const uint32_t rs = tile_lo - W + (hin[k] >> 16), re = rs + RLEN(hin[k]);
             if (re > tile_lo && p1 > rs && p0 < re) { ++c; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
           }
         }
 #pragma unroll
         for (int r = 0; r < RC; ++r) {
           if (s0 + tid + r * THREADS < s1) {
-            const uint32_t rs = tile_lo + (rcr[r] >> 16), re = rs + (rcr[r] & 0xffffu);
+            const uint32_t rs = tile_lo + (rcr[r] >> 16), re = rs + RLEN(rcr[r]);
             if (p1 > rs && p0 < re) { ++c; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
           }
         }
 #pragma unroll 1
         for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-          const uint32_t pr = P[i], rs = tile_lo + (pr >> 16), re = rs + (pr & 0xffffu);
+          const uint32_t pr = P[i], rs = tile_lo + (pr >> 16), re = rs + RLEN(pr);
           if (p1 > rs && p0 < re) { ++c; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
         }
         c = __reduce_add_sync(0xffffffffu, c);
@@ -480,7 +469,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         const int k = k0h + tid;
         bool valid = k < nh;
         uint32_t rs = 0, re = 0;
-        if (valid) { rs = tile_lo - W + (hin[k] >> 16); re = rs + (hin[k] & 0xffffu); valid = re > tile_lo; }
+        if (valid) { rs = tile_lo - W + (hin[k] >> 16); re = rs + RLEN(hin[k]); valid = re > tile_lo; }
         gmap4_round(valid, rs, re, false, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
 #pragma unroll 1
@@ -489,7 +478,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
           const bool valid = s0 + tid + r * THREADS < s1;
           const uint32_t pr = valid ? P[s0 + tid + r * THREADS] : 0u;
           const uint32_t rs = tile_lo + (pr >> 16);
-          gmap4_round(valid, rs, rs + (pr & 0xffffu), true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
+          gmap4_round(valid, rs, rs + RLEN(pr), true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
         }
       }
 #pragma unroll 1
@@ -497,7 +486,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         const uint32_t i = i0 + tid;
         const bool valid = i < s1;
         uint32_t rs = 0, re = 0;
-        if (valid) { const uint32_t pr = P[i]; rs = tile_lo + (pr >> 16); re = rs + (pr & 0xffffu); }
+        if (valid) { const uint32_t pr = P[i]; rs = tile_lo + (pr >> 16); re = rs + RLEN(pr); }
         gmap4_round(valid, rs, re, true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
     }
@@ -521,4 +510,6 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     nh_carry = nout;
   }
   if (tid == 0) out.blk_cnt[blockIdx.x] = (uint32_t)my_cnt;
+#undef RLEN
+#undef REXT
 }

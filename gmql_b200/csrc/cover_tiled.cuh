@@ -70,8 +70,24 @@ __device__ __forceinline__ BinMod make_binmod(int64_t B) { BinMod m; m.B = B; m.
 __device__ __forceinline__ bool is_bin_multiple(const BinMod& m, uint32_t x) {
   return m.B < 0x7fffffffLL ? (m.magic * (uint64_t)x <= m.magic - 1ull) : ((uint64_t)x % (uint64_t)m.B == 0ull);
 }
+// x % B == 0 with one multiply-high (x < 2^32): q = floor(x * floor((2^32 - 1) / B) / 2^32) underestimates x / B by at most 2.
+// Built on the host, passed by value.
+struct BinMod32 { uint32_t B, inv; int big; };
+static inline BinMod32 make_binmod32(int64_t B) {
+  BinMod32 m;
+  m.big = B >= 0x7fffffffLL ? 1 : 0;
+  m.B = B > 0xffffffffLL ? 0u : (uint32_t)B;    // a bin wider than any 32-bit coordinate: only 0 is a multiple
+  m.inv = m.big ? 0u : 0xffffffffu / m.B;
+  return m;
+}
+__device__ __forceinline__ bool is_bin_multiple32(const BinMod32& m, uint32_t x) {
+  if (m.big) return x == 0u || (m.B != 0u && x == m.B);
+  const uint32_t r = x - __umulhi(x, m.inv) * m.B;
+  return r == 0u || r == m.B || r == 2u * m.B;
+}
 // length payload of a record that starts at linear position rs: length | EXT when stop' = stop + 1
-__device__ __forceinline__ uint32_t rec_len_payload(uint32_t rec, uint32_t rs, const TileChrom& tc, const LinMap& lm, const BinMod& bm) {
+__device__ __forceinline__ uint32_t rec_len_payload(uint32_t rec, uint32_t rs, const TileChrom& tc, const LinMap& lm, const BinMod& bm, bool xb) {
+  if (xb) return (rec & 0x7fffu) | ((rec & 0x8000u) << 16);   // the partition left the extension in bit 15 of the record
   const uint32_t len = rec & 0xffffu;
   const uint32_t base = (rs >= tc.lo && rs < tc.next) ? tc.base : lin_base_slow(lm, rs);
   return len | ((len != 0u && is_bin_multiple(bm, rs + len - base)) ? EXT : 0u);
@@ -94,6 +110,7 @@ struct Cfg {
   const int32_t* mx;
   int32_t mn0, mx0;    // thresholds of group 0 (fast path when n_groups == 1)
   uint64_t G;
+  int xb;              // 1: partitioned records carry the one-base extension in bit 15 (lengths below 32 768)
 };
 
 struct Pieces {
@@ -401,7 +418,7 @@ constexpr size_t msp_smem_bytes() { return 8 * (size_t)MSP_TILE + msp_stage_byte
 
 template <int MODE>
 static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, LinMap lm, int64_t B, int64_t n, int bin_shift, int logw, uint32_t* __restrict__ cursor, MspOut out,
-                                                                      int vec_ok, int groups, Guard guard) {
+                                                                      int vec_ok, int groups, Guard guard, int xb, BinMod32 bm32) {
   if (guard_trips(guard)) return;
   constexpr bool FUSED = MODE != MSP_FINE;
   extern __shared__ __align__(128) unsigned char msp_smem[];
@@ -476,13 +493,18 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, 
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t key = (uint32_t)((uint64_t)kk[q] * lm.G + coff[cc[q]]) + (uint32_t)ss[q];
-            rec[j4 * 4 + q] = ((uint64_t)key << 32) | (uint64_t)((uint32_t)(ee[q] - ss[q]) & 0xffffu);
+            uint32_t lq = (uint32_t)(ee[q] - ss[q]) & 0xffffu;
+            if (xb && lq != 0u && is_bin_multiple32(bm32, (uint32_t)ee[q])) lq |= 0x8000u;   // the extractor's one-base extension (GenometricCover.scala:353-354)
+            rec[j4 * 4 + q] = ((uint64_t)key << 32) | (uint64_t)lq;
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint64_t r = 0ull;
-            if (idx0 + q < count) r = make_record(in.chrom, in.start, in.stop, in.bits, in.cls, coff, lm.G, B, i0 + q) & 0xffffffff0000ffffull;   // key << 32 | length
+            if (idx0 + q < count) {
+              r = make_record(in.chrom, in.start, in.stop, in.bits, in.cls, coff, lm.G, B, i0 + q);
+              r = xb ? ((r & 0xffffffff00007fffull) | ((r >> 16) & 0x8000ull)) : (r & 0xffffffff0000ffffull);   // key << 32 | length (| extension in bit 15)
+            }
             rec[j4 * 4 + q] = r;
           }
         }
@@ -517,7 +539,9 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t key = (uint32_t)coff[cc[q]] + (uint32_t)ss[q];
-          rec[j4 * 4 + q] = idx0 + q < count ? (((uint64_t)key << 32) | (uint64_t)ll[q]) : 0ull;
+          uint32_t lq = ll[q];
+          if (xb && lq != 0u && is_bin_multiple32(bm32, (uint32_t)ss[q] + lq)) lq |= 0x8000u;   // the extractor's one-base extension (GenometricCover.scala:353-354)
+          rec[j4 * 4 + q] = idx0 + q < count ? (((uint64_t)key << 32) | (uint64_t)lq) : 0ull;
         }
       }
     } else {
@@ -598,11 +622,11 @@ static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, 
 }
 
 // the radix-sort route (more tiles than the counting kernel's shared memory holds): sorted 64-bit records -> 4-byte records
-static __global__ void k_pack_rec32(const uint64_t* __restrict__ packed, int64_t n, int logw, uint32_t* __restrict__ rec) {
+static __global__ void k_pack_rec32(const uint64_t* __restrict__ packed, int64_t n, int logw, uint32_t* __restrict__ rec, int xb) {
   const uint32_t wmask = (1u << logw) - 1u;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t r = packed[i];
-    rec[i] = ((((uint32_t)(r >> 32)) & wmask) << 16) | ((uint32_t)r & 0xffffu);
+    rec[i] = ((((uint32_t)(r >> 32)) & wmask) << 16) | (xb ? (((uint32_t)r & 0x7fffu) | (((uint32_t)r >> 16) & 0x8000u)) : ((uint32_t)r & 0xffffu));
   }
 }
 
@@ -706,6 +730,8 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
                                                                   int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, LinMap lm, int64_t B, Pieces out, Guard guard) {
   if (guard_trips(guard)) return;
   const BinMod bm = make_binmod(B);
+  const bool xb = cfg.xb != 0;
+  const uint32_t lmask = xb ? 0x7fffu : 0xffffu;
   extern __shared__ uint32_t sm[];
   uint32_t* bitmap = sm;                                   // [MAXWORDS] occupancy of the tile's positions
   uint16_t* wpre = (uint16_t*)(bitmap + MAXWORDS);         // [MAXWORDS] set bits before each word
@@ -782,7 +808,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       for (uint32_t i0 = h0; i0 < s0; i0 += THREADS) {
         uint32_t i = i0 + tid;
         if (i < s0) {
-          const uint32_t pr = P[i]; uint32_t rs = tile_lo - W + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm);
+          const uint32_t pr = P[i]; uint32_t rs = tile_lo - W + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm, xb);
           uint32_t ee = rs + (lp & ~EXT) + (lp >> 31);
           if (ee >= tile_lo) {
             int slot = atomicAdd(&s_nh, 1);
@@ -804,7 +830,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
     for (int r = 0; r < RC; ++r) {
       uint32_t i = s0 + tid + r * THREADS;
       rsr[r] = 0; lpr[r] = 0;
-      if (i < s1) { const uint32_t pr = P[i]; rsr[r] = tile_lo + (pr >> 16); lpr[r] = rec_len_payload(pr, rsr[r], tch, lm, bm); }
+      if (i < s1) { const uint32_t pr = P[i]; rsr[r] = tile_lo + (pr >> 16); lpr[r] = rec_len_payload(pr, rsr[r], tch, lm, bm, xb); }
     }
 #pragma unroll
     for (int r = 0; r < RC; ++r) {
@@ -817,7 +843,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       }
     }
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm);
+      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm, xb);
       uint32_t q = rs - tile_lo;
       atomicOr(&bitmap[q >> 5], 1u << (q & 31));
       uint32_t qe = q + (lp & ~EXT) + (lp >> 31);
@@ -867,7 +893,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
       }
     }
     for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm);
+      const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), lp = rec_len_payload(pr, rs, tch, lm, bm, xb);
       uint32_t q = rs - tile_lo;
       int rk = wpre[q >> 5] + __popc(bitmap[q >> 5] & ((1u << (q & 31)) - 1u));
       delta_add(delta, rk, 1);
@@ -993,7 +1019,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
         }
       }
       for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
-        const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), re = rs + (pr & 0xffffu);
+        const uint32_t pr = P[i]; uint32_t rs = tile_lo + (pr >> 16), re = rs + (pr & lmask);
         if (p1 > rs && p0 < re) { ++cnt; a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re); }
       }
       cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -1023,7 +1049,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile(cons
         uint32_t i = i0 + tid;
         bool valid = i < s1;
         uint32_t rs = 0, re = 0;
-        if (valid) { const uint32_t pr = P[i]; rs = tile_lo + (pr >> 16); re = rs + (pr & 0xffffu); }
+        if (valid) { const uint32_t pr = P[i]; rs = tile_lo + (pr >> 16); re = rs + (pr & lmask); }
         gmap4_round(valid, rs, re, true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
     }

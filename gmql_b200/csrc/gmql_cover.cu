@@ -1176,9 +1176,12 @@ static void tile_offsets_narrow(gmql_ctx* ctx, const DevRegions& in, const LinMa
 static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total, int logw,
                             const int32_t* h_mn, const int32_t* h_mx, Phase1Out* p1, DevBuf<int32_t>& keep, DevBuf<int64_t>& fstart, DevBuf<int64_t>& fstop,
                             DevBuf<double>& j1, DevBuf<double>& j2, int64_t* nc_out, const ShardSpec* shard, ShardBufs* sb, TiledRuns* keep_runs, FusedOut* fo, SpecCtx* spec,
-                            const TileSource& src, bool use_wc, int* fail_code) {
+                            const TileSource& src, bool use_wc, int64_t maxlen_known, int* fail_code) {
   *fail_code = 0;
   const int64_t n = in.n;
+  // lengths below 32 768 (known before the launch): the partition decides the one-base extension and leaves it in bit 15 of the record
+  const int xb = (maxlen_known >= 0 && maxlen_known < 32768 && cfg.B > 0) ? 1 : 0;
+  const tiled::BinMod32 bm32 = tiled::make_binmod32(cfg.B);
   tiled::Guard guard;
   guard.flags = (spec && !spec->synced) ? spec->flags : nullptr;
   guard.max_len = (int)((1ll << logw) - 2);
@@ -1242,18 +1245,18 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
       mi.chrom8 = (const uint8_t*)in.chrom_narrow; mi.start = in.start; mi.len16 = (const uint16_t*)in.len_narrow; mi.bits = 32;
       const int vec_ok = al16(in.chrom_narrow) && al16(in.start) && al16(in.len_narrow) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
       CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_NARROW>()));
-      LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_NARROW>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_NARROW>(), mi, lm, cfg.B, n, 32 + logw + 8, logw, cur_coarse.p, mo, vec_ok, G, guard);
+      LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_NARROW>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_NARROW>(), mi, lm, cfg.B, n, 32 + logw + 8, logw, cur_coarse.p, mo, vec_ok, G, guard, xb, bm32);
     } else {
       mi.chrom = in.chrom; mi.start = in.start; mi.stop = in.stop; mi.bits = in.coord_bits; mi.cls = cls;
       const int vec_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(cls) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
       CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_WIDE>()));
-      LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_WIDE>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_WIDE>(), mi, lm, cfg.B, n, 32 + logw + 8, logw, cur_coarse.p, mo, vec_ok, G, guard);
+      LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_WIDE>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_WIDE>(), mi, lm, cfg.B, n, 32 + logw + 8, logw, cur_coarse.p, mo, vec_ok, G, guard, xb, bm32);
     }
     memset(&mi, 0, sizeof mi);
     mi.key = key_a.p; mi.len = len_a.p;
     mo.key = nullptr; mo.len = nullptr; mo.rec = rec.p;
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_FINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_FINE>()));
-    LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_FINE>, mg, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_FINE>(), mi, lm, cfg.B, n, 32 + logw, logw, cur_tile.p, mo, 0, 1, guard);
+    LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_FINE>, mg, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_FINE>(), mi, lm, cfg.B, n, 32 + logw, logw, cur_tile.p, mo, 0, 1, guard, xb, bm32);
   } else {
     GMQL_REQUIRE(!src.narrow, GMQL_ERR_INVALID, "internal: the radix route of the tile path needs the wide columns");
     DevBuf<uint64_t> pk_a(ctx, n), pk_b(ctx, n);
@@ -1263,7 +1266,7 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     LAUNCH(ctx, tiled::k_tile_keys, grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, lm, cfg.B, pk_a.p);
     radix_sort<uint64_t>(ctx, pk_a.p, pk_b.p, nullptr, nullptr, n, 32 + key_bits, &P64, nullptr, 32 + logw);   // partition by tile only
     LAUNCH(ctx, tiled::k_tile_offsets, grid_for(ctx, n, 256), 256, 0, P64, n, nT, logw, offS_own.p);
-    LAUNCH(ctx, tiled::k_pack_rec32, grid_for(ctx, n, 256), 256, 0, (const uint64_t*)P64, n, logw, rec.p);
+    LAUNCH(ctx, tiled::k_pack_rec32, grid_for(ctx, n, 256), 256, 0, (const uint64_t*)P64, n, logw, rec.p, xb);
   }
   const uint32_t* P = rec.p;
 
@@ -1292,20 +1295,21 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   DevBuf<int> fail(ctx, 1);
   fail.zero();
   tiled::Cfg tc;
-  tc.n_groups = cfg.n_groups; tc.n_classes = cfg.n_classes; tc.mn = cfg.mn; tc.mx = cfg.mx; tc.mn0 = h_mn[0]; tc.mx0 = h_mx[0]; tc.G = lm.G;
+  tc.n_groups = cfg.n_groups; tc.n_classes = cfg.n_classes; tc.mn = cfg.mn; tc.mx = cfg.mx; tc.mn0 = h_mn[0]; tc.mx0 = h_mx[0]; tc.G = lm.G; tc.xb = xb;
   tiled::Pieces pc;
   pc.pstart = pstart.p; pc.pend = pend.p; pc.acc = acc.p; pc.cnt = cnt.p; pc.smin = smin.p; pc.emax = emax.p; pc.smax = smax.p; pc.emin = emin.p;
   pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
   if (cfg.n_groups == 1 && use_wc) {
     // the word-count kernel (cover_tile_wc.cuh); a tile with too many words to resolve sends the operator to the rank kernel
-    const tiled::BinMod32 bm = tiled::make_binmod32(cfg.B);
-    if (logw == tiled::MAX_LOGW) {
-      CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile_wc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::WC_SMEM_BYTES));
-      LAUNCH(ctx, tiled::k_cover_tile_wc<true>, tgrid, tiled::THREADS, tiled::WC_SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, bm, pc, guard);
-    } else {
-      CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile_wc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::WC_SMEM_BYTES));
-      LAUNCH(ctx, tiled::k_cover_tile_wc<false>, tgrid, tiled::THREADS, tiled::WC_SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, bm, pc, guard);
-    }
+    const tiled::BinMod32 bm = bm32;
+#define WC_LAUNCH(F, X)                                                                                                                   \
+    do {                                                                                                                                  \
+      CUDA_TRY(cudaFuncSetAttribute((tiled::k_cover_tile_wc<F, X>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::WC_SMEM_BYTES)); \
+      LAUNCH(ctx, (tiled::k_cover_tile_wc<F, X>), tgrid, tiled::THREADS, tiled::WC_SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, bm, pc, guard); \
+    } while (0)
+    if (logw == tiled::MAX_LOGW) { if (xb) WC_LAUNCH(true, true); else WC_LAUNCH(true, false); }
+    else { if (xb) WC_LAUNCH(false, true); else WC_LAUNCH(false, false); }
+#undef WC_LAUNCH
   } else if (cfg.n_groups > 1) {
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_cover_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::SMEM_BYTES));
     LAUNCH(ctx, tiled::k_cover_tile<true>, tgrid, tiled::THREADS, tiled::SMEM_BYTES, P, offS, t_lo, t_hi, logw, tc, lm, cfg.B, pc, guard);
@@ -1483,7 +1487,7 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
       if (lw < 8 || maxlen >= (int64_t)(1ll << lw) - 2) break;
       int fail_code = 0;
       done = run_cover_tiled(ctx, in, cls.p, lm, cfg, flag, n_classes_total, lw, h_mn, h_mx, &p1, keep, fstart, fstop, j1, j2, &nc, shard, shard ? &sbufs : nullptr, plan.n_aggs ? &truns : nullptr,
-                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr, spec, src, use_wc, &fail_code);
+                             (plan.n_aggs == 0 && !shard) ? &fo : nullptr, spec, src, use_wc, (spec && !spec->synced) ? (int64_t)-1 : maxlen, &fail_code);
       if (!done && fail_code == 5 && use_wc && !(spec && spec->tripped)) {      // only the word-count kernel's own table overflowed: same tiles, rank kernel
         use_wc = false;
         --attempt;

@@ -502,18 +502,19 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_grouped(MapGroupedA
 // strand / sample / padding-lane bookkeeping is left: ~4.5 -> ~2 warp instructions per row (ncu, profiles/).
 __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_lean(MapGroupedArgs a, int64_t n_exp_rows) {
   extern __shared__ __align__(16) uint32_t g_dyn[];
-  const int n_ref = a.n_ref, n_ref2 = (n_ref + 1) & ~1;
+  const int n_ref = a.n_ref, n_ref2 = (n_ref + 2) & ~1;
   uint2* s_sp = (uint2*)g_dyn;                                    // [n_ref] {stop, running max of the EARLIER stops}
-  uint32_t* s_start = g_dyn + 2 * (size_t)n_ref;                  // [n_ref] (+ pad)
+  uint32_t* s_start = g_dyn + 2 * (size_t)n_ref;                  // [n_ref] + a sentinel that ends every forward scan
   uint32_t* s_cnt = s_start + n_ref2;                             // [(n_ref + 1) / 2] two 16-bit counters per word
   const int n_cw = (n_ref + 1) >> 1;
   uint16_t* s_tbl = (uint16_t*)(s_cnt + n_cw);                    // [n_tbl]
-  uint2* s_cs = (uint2*)(g_dyn + ((3 * (size_t)n_ref + 1 + n_cw + (((size_t)a.n_tbl + 1) >> 1) + 1) & ~(size_t)1));   // [n_chrom] {linear offset, span}
+  uint2* s_cs = (uint2*)(g_dyn + ((3 * (size_t)n_ref + 2 + n_cw + (((size_t)a.n_tbl + 1) >> 1) + 1) & ~(size_t)1));   // [n_chrom] {linear offset, span}
   for (int k = threadIdx.x; k < n_ref; k += MS_THREADS) {
     const RefEntry<uint32_t> e = a.entries[k];
     s_start[k] = a.r_start[k];
     s_sp[k] = make_uint2(e.stop, e.pmax_prev);
   }
+  if (threadIdx.x == 0) s_start[n_ref] = 0xffffffffu;
   for (int k = threadIdx.x; k < a.n_tbl; k += MS_THREADS) s_tbl[k] = (uint16_t)a.tbl[k];
   for (int k = threadIdx.x; k < a.lm.n_chrom; k += MS_THREADS) s_cs[k] = make_uint2((uint32_t)a.lm.coff[k], (uint32_t)a.lm.span[k]);
   const int4* st4 = (const int4*)a.e_start;
@@ -531,10 +532,20 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_map_count_lean(MapGroupedArgs
     if (e > cs.y + 1u) e = cs.y + 1u;
     const uint32_t ls = cs.x + (uint32_t)s, le = cs.x + e;
     const uint32_t b = le >> shift;
-    int k = (int)s_tbl[b];
-    const int hi2 = (int)s_tbl[b + 1];
-    if (hi2 - k > 4) { int lo2 = k, h2 = hi2; while (lo2 < h2) { const int mid = (lo2 + h2) >> 1; if (s_start[mid] < le) lo2 = mid + 1; else h2 = mid; } k = lo2; }
-    else while (k < hi2 && s_start[k] < le) ++k;                  // buckets usually hold no or one reference start
+    int k = (int)s_tbl[b];                                        // first reference start at or after the bucket's first position
+    // forward to the first start >= row.stop: buckets usually hold no or one reference start, and the sentinel ends the scan
+    // without a look at the next bucket's entry; a crowded bucket is finished by bisection
+    if (s_start[k] < le) {
+      ++k;
+      if (s_start[k] < le) {
+        ++k;
+        if (s_start[k] < le) {
+          int lo2 = k + 1, h2 = (int)s_tbl[b + 1];
+          while (lo2 < h2) { const int mid = (lo2 + h2) >> 1; if (s_start[mid] < le) lo2 = mid + 1; else h2 = mid; }
+          k = lo2;
+        }
+      }
+    }
     --k;                                                          // last reference region with start < row.stop
     while (k >= 0) {
       const uint2 sp = s_sp[k];

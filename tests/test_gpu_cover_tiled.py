@@ -118,6 +118,26 @@ def test_tiled_random(ex, flag, logw, seed):
         assert ("k_cover_tile_wc" in f.kernels) == (os.environ["GMQL_COVER_KERNEL"] == "count"), f.kernels
 
 
+@pytest.mark.parametrize("flag", ["COVER", "FLAT"])
+def test_tiled_long_regions_keep_full_16_bit_lengths(ex, flag):
+    """With every region shorter than 32 768 bases the partition stores the extractor's one-base extension in bit 15 of the 4-byte
+    record (test_tiled_random runs that format); a longer region needs all 16 length bits and the tile kernels derive the extension
+    from the chromosome offsets themselves.  Same rows as the oracle either way, including bin-aligned stops of the long regions."""
+    rng = random.Random(4242)
+    ids = [1, 2, 3, 4]
+    ds = _clamp(rng, rand_regions(rng, 500, ids, strands="*", n_vals=0, max_len=3000, aligned_p=0.4, bin_mults=(2000, 5000, 50000)), 3000)
+    chroms = sorted({r[1] for r in ds})
+    for k in range(12):
+        st = rng.randrange(0, 200000)
+        ln = rng.randrange(33000, 65000)
+        stop = st + ln if k % 3 else ((st + ln) // 2000) * 2000
+        ds.append((ids[k % 4], chroms[k % len(chroms)], st, stop, "*", ()))
+    with forced(ex, 16) as f:
+        for gp, op in _params()[:5]:
+            _check(ex, flag, ds, ids, None, gp, op)
+    f.assert_tiled()
+
+
 def test_word_count_kernel_hands_over_when_a_tile_has_too_many_words_to_resolve(ex):
     """Two long regions give depth 2 over most of a tile; a chain of short regions, each ending five bases into a 32-position word
     and the next one starting five bases later, adds a third layer that is open at every word boundary.  Every word then holds a
