@@ -45,6 +45,12 @@ template <bool FULL, bool XB>
 static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(const uint32_t* __restrict__ P /* tile-local start << 16 | length */, const uint32_t* __restrict__ offS,
                                                                                int64_t t_lo, int64_t t_hi, int logw, Cfg cfg, LinMap lm, BinMod32 bm, Pieces out, Guard guard) {
   if (guard_trips(guard)) return;
+#ifdef GMQL_TILE_TICKS   // profiling build (make NVFLAGS+=-DGMQL_TILE_TICKS; option cover.dbg = 9): cycles per phase, thread 0 of every block
+#define TICK(p) do { if (cfg.dbg == 9 && tid == 0) { const long long now_ = clock64(); atomicAdd((unsigned long long*)out.ticks + (p), (unsigned long long)(now_ - tick_last)); tick_last = now_; } } while (0)
+  long long tick_last = 0;
+#else
+#define TICK(p) do { } while (0)
+#endif
 #define RLEN(pr) (XB ? ((pr) & 0x7fffu) : ((pr) & 0xffffu))
 #define REXT(pr, rs, len) (XB ? (((pr) >> 15) & 1u) : wc_ext((rs), (len), tch, lm, bm))
   extern __shared__ __align__(16) uint32_t sm[];
@@ -69,6 +75,8 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
   uint16_t* sopen = slotw + (WC_NCAP + 2);                 // [WC_NCAP + 2] run opens inside the slot
   uint16_t* sopre = sopen + (WC_NCAP + 2);                 // [WC_NCAP + 2] opens in the slots before
   __shared__ int32_t scratch[4][NWARPS];                   // one per scan of a tile (see block_excl_scan)
+  __shared__ int32_t red[NWARPS][4];                       // per-warp {all words IN, largest boundary depth, largest upper bound}
+  __shared__ uint32_t red2[NWARPS][5];                     // per-warp GMAP4 bounds and resolved maximum of the one-run tiles
   __shared__ int s_nh, s_nout;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t W = FULL ? 65536u : (1u << logw);
@@ -123,6 +131,9 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     s1_next = s1;
     if (tile + 1 < t_end) s2_next = offS[tile + 2];        // the next tile's range, loaded a whole tile ahead
     const uint32_t nS_tile = s1 - s0;
+#ifdef GMQL_TILE_TICKS
+    if (cfg.dbg == 9 && tid == 0) tick_last = clock64();
+#endif
     const bool scan_prev = nh_carry < 0;
     const uint32_t h0 = (scan_prev && tile > 0) ? offS[tile - 1] : s0;
     const uint32_t tile_lo = (uint32_t)tile << logw;
@@ -184,6 +195,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       else { const int slot = atomicAdd(&s_nout, 1); if (slot < HCAP) hout[slot] = pr; }
     }
     __syncthreads();
+    TICK(0);
     const int nh = s_nh, nout = s_nout;
     const int32_t depth_in = nh;                           // regions still open when the tile begins
     // ---- phase B: exact depth at every word boundary, classes of the words
@@ -244,44 +256,80 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
     // stretches of consecutive IN words: index, largest boundary depth
     const uint32_t m_start = m_in & ~((m_in << 1) | (prev_in ? 1u : 0u));
     const bool all_in = m_in == vmask;                     // (threads without words: vmask == 0, m_in == 0)
-    int32_t seg_total, seg_id;                             // seg_id: stretch open before this thread's first word (-1: none)
-    if (__syncthreads_or(all_in ? 0 : 1)) {
-      seg_id = block_excl_scan(__popc(m_start), &seg_total, scratch[1]) - 1;
-      if (seg_total > WC_SEGCAP) seg_total = WC_SEGCAP;    // cannot happen: a stretch start needs a non-IN word before it
-    } else { seg_total = 1; seg_id = tid == 0 ? -1 : 0; }  // every word of the tile is IN: one stretch, started by the tile's first word
-    if (all_in) {
-      if (vmask) atomicMax(&segmax[seg_id + (int32_t)(m_start & 1u)], bmax);     // one stretch covers all my words
-    } else if (m_in) {
-      int32_t s = seg_id, m = -1, d = d0;                  // d: depth before word j
-#pragma unroll 1
-      for (int j = 0; j < 8; ++j) {
-        const int32_t de = d + (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
-        if ((m_in >> j) & 1u) {
-          if ((m_start >> j) & 1u) { if (m >= 0) atomicMax(&segmax[s], m); ++s; m = -1; }
-          m = max(m, max(d, de));
-        } else if (m >= 0) { atomicMax(&segmax[s], m); m = -1; }
-        d = de;
-      }
-      if (m >= 0) atomicMax(&segmax[s], m);
+    // block-wide in ONE barrier: is every word of the tile IN, the largest boundary depth, the largest upper bound of a word
+    {
+      const bool w_all = __all_sync(0xffffffffu, all_in);
+      const int32_t w_b = __reduce_max_sync(0xffffffffu, bmax), w_h = __reduce_max_sync(0xffffffffu, hmax);
+      if (lane == 0) { red[warp][0] = w_all ? 1 : 0; red[warp][1] = w_b; red[warp][2] = w_h; }
     }
-    // the run entering the tile: its first stretch (index 0, when the tile's first word is IN) inherits what earlier tiles proved
-    if (tid == 0 && acc_carry > 0 && (m_in & 1u)) atomicMax(&segmax[0], acc_carry);
     __syncthreads();
-    // words to resolve: THR, and IN words whose upper bound exceeds what the stretch's boundaries already prove
-    uint32_t m_noisy = m_thr;
-    if (m_in && !(all_in && hmax <= segmax[seg_id + (int32_t)(m_start & 1u)])) {
-      int32_t s = seg_id, d = d0;
-#pragma unroll 1
-      for (int j = 0; j < 8; ++j) {
-        if ((m_in >> j) & 1u) {
-          if ((m_start >> j) & 1u) ++s;
-          if (d + (int32_t)(cw[j] & 0xffffu) > segmax[s]) m_noisy |= 1u << j;
+    TICK(1);
+    const bool blk_all = __all_sync(0xffffffffu, lane < NWARPS ? red[lane][0] != 0 : true);
+    const int32_t blk_b = __reduce_max_sync(0xffffffffu, lane < NWARPS ? red[lane][1] : -1);
+    const int32_t blk_h = __reduce_max_sync(0xffffffffu, lane < NWARPS ? red[lane][2] : -1);
+    // ---- one-run tiles (three in four under dense coverage): every word is IN, so the whole tile is ONE piece [tile_lo, tile_lo + W)
+    // of a run that began earlier; every region that starts here overlaps it (the open regions were accounted by the run's earlier
+    // tiles, GMAP4.scala:44-45).  Only the run's maximum depth may still hide inside a word: M is what the word boundaries and the
+    // run's earlier tiles prove; a word whose upper bound stays at or below M needs no look.  Half of these tiles resolve nothing
+    // (four barriers, no second pass over the events); the others resolve a few words for their maximum only — no stretches, no
+    // piece tables, no opens / closes.  (cover.dbg = 4, a test hook, sends them through the general path below instead.)
+    const bool lite = blk_all && cfg.dbg != 4;
+    const int32_t M = max(blk_b, acc_carry);
+    int32_t seg_total = 0, seg_id = 0;                     // seg_id: stretch open before this thread's first word (-1: none)
+    uint32_t m_noisy = 0;
+    bool resolve = true;                                   // block-uniform
+    if (lite) {
+      resolve = blk_h > M;
+      if (resolve) {
+        int32_t d = d0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int32_t ns = (int32_t)(cw[j] & 0xffffu), ne = (int32_t)(cw[j] >> 16);
+          if ((FULL || ((vmask >> j) & 1u)) && d + ns > M) m_noisy |= 1u << j;
+          d += ns - ne;
         }
-        d += (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
+      }
+    } else {
+      if (!blk_all) {
+        seg_id = block_excl_scan(__popc(m_start), &seg_total, scratch[1]) - 1;
+        if (seg_total > WC_SEGCAP) seg_total = WC_SEGCAP;  // cannot happen: a stretch start needs a non-IN word before it
+      } else { seg_total = 1; seg_id = tid == 0 ? -1 : 0; }  // every word of the tile is IN: one stretch, started by the tile's first word
+      if (all_in) {
+        if (vmask) atomicMax(&segmax[seg_id + (int32_t)(m_start & 1u)], bmax);     // one stretch covers all my words
+      } else if (m_in) {
+        int32_t s = seg_id, m = -1, d = d0;                // d: depth before word j
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          const int32_t de = d + (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
+          if ((m_in >> j) & 1u) {
+            if ((m_start >> j) & 1u) { if (m >= 0) atomicMax(&segmax[s], m); ++s; m = -1; }
+            m = max(m, max(d, de));
+          } else if (m >= 0) { atomicMax(&segmax[s], m); m = -1; }
+          d = de;
+        }
+        if (m >= 0) atomicMax(&segmax[s], m);
+      }
+      // the run entering the tile: its first stretch (index 0, when the tile's first word is IN) inherits what earlier tiles proved
+      if (tid == 0 && acc_carry > 0 && (m_in & 1u)) atomicMax(&segmax[0], acc_carry);
+      __syncthreads();
+      TICK(2);
+      // words to resolve: THR, and IN words whose upper bound exceeds what the stretch's boundaries already prove
+      m_noisy = m_thr;
+      if (m_in && !(all_in && hmax <= segmax[seg_id + (int32_t)(m_start & 1u)])) {
+        int32_t s = seg_id, d = d0;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          if ((m_in >> j) & 1u) {
+            if ((m_start >> j) & 1u) ++s;
+            if (d + (int32_t)(cw[j] & 0xffffu) > segmax[s]) m_noisy |= 1u << j;
+          }
+          d += (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
+        }
       }
     }
     int32_t nn_total = 0, slot0 = 0;
-    if (__syncthreads_or(m_noisy ? 1 : 0)) slot0 = block_excl_scan(__popc(m_noisy), &nn_total, scratch[2]);
+    if (resolve && (lite || __syncthreads_or(m_noisy ? 1 : 0))) slot0 = block_excl_scan(__popc(m_noisy), &nn_total, scratch[2]);
+    TICK(3);
     if (nn_total > WC_NCAP) {                              // too many words to resolve: the rank kernel takes the operator
       if (tid == 0) { *out.fail = 5; s_nh = 0; }
       nh_carry = -1; acc_carry = 0;
@@ -289,21 +337,21 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       __syncthreads();
       continue;
     }
-    const bool cont0 = depth_in >= mn0 && depth_in <= mx0;
-    int32_t open_total = 0;
+    if (cfg.dbg == 8 && tid == 0) { atomicAdd(out.fail + (lite ? 1 : 2), 1); atomicAdd(out.fail + 3, nn_total); }
     if (nn_total > 0) {
       if (m_noisy) atomicOr(&nmask[w0 >> 5], m_noisy << (w0 & 31));
       if (vmask && (w0 & 31) == 0) sbase[w0 >> 5] = (uint32_t)slot0;
-      if (m_noisy | m_start) {
+      if (m_noisy | (lite ? 0u : m_start)) {
         int32_t s = seg_id, sl = slot0, d = d0;
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
-          if ((m_start >> j) & 1u) { ++s; segslot[s] = (uint16_t)sl; }
-          if ((m_noisy >> j) & 1u) { slotw[sl] = (uint16_t)(w0 + j); slotd0[sl] = d; ++sl; }
+          if (!lite && ((m_start >> j) & 1u)) { ++s; segslot[s] = (uint16_t)sl; }
+          if ((m_noisy >> j) & 1u) { if (!lite) slotw[sl] = (uint16_t)(w0 + j); slotd0[sl] = d; ++sl; }
           d += (int32_t)(cw[j] & 0xffffu) - (int32_t)(cw[j] >> 16);
         }
       }
       __syncthreads();
+      TICK(4);
       // ---- phase C: per-position net change of the words to resolve
       // (which of the 64 mask words hold anything at all: two registers, so that most events never touch shared memory)
       const unsigned nm_lo = __ballot_sync(0xffffffffu, nmask[lane] != 0u), nm_hi = __ballot_sync(0xffffffffu, nmask[32 + lane] != 0u);
@@ -337,7 +385,64 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         if (qe < W) hit(qe, -1);
       }
       __syncthreads();
+      TICK(5);
       if (tid < WC_MASKW) nmask[tid] = 0;                  // clean for the next tile (its next writer is several barriers away)
+    }
+    if (lite) {
+      // the exact maximum inside every resolved word (one warp per word, lane = position)
+      int32_t wmax = 0;
+#pragma unroll 1
+      for (int sl = warp; sl < nn_total; sl += NWARPS) {
+        int32_t x = delta_get(npos, sl * 32 + lane);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane < 16) npos[sl * 16 + lane] = 0;           // clean for the next tile (every lane's value went through the shuffles above)
+        wmax = max(wmax, __reduce_max_sync(0xffffffffu, slotd0[sl] + x));
+      }
+      uint32_t a_smin = 0xffffffffu, a_emax = 0u, a_smax = 0u, a_emin = 0xffffffffu;
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        if (s0 + tid + r * THREADS < s1) {
+          const uint32_t rs = tile_lo + (rcr[r] >> 16), re = rs + RLEN(rcr[r]);
+          a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re);
+        }
+      }
+#pragma unroll 1
+      for (uint32_t i = s0 + RC * THREADS + tid; i < s1; i += THREADS) {
+        const uint32_t pr = P[i], rs = tile_lo + (pr >> 16), re = rs + RLEN(pr);
+        a_smin = min(a_smin, rs); a_emax = max(a_emax, re); a_smax = max(a_smax, rs); a_emin = min(a_emin, re);
+      }
+      a_smin = __reduce_min_sync(0xffffffffu, a_smin); a_emax = __reduce_max_sync(0xffffffffu, a_emax);
+      a_smax = __reduce_max_sync(0xffffffffu, a_smax); a_emin = __reduce_min_sync(0xffffffffu, a_emin);
+      if (lane == 0) { red2[warp][0] = a_smin; red2[warp][1] = a_emax; red2[warp][2] = a_smax; red2[warp][3] = a_emin; red2[warp][4] = (uint32_t)wmax; }
+      __syncthreads();
+      const int32_t acc = max(M, (int32_t)__reduce_max_sync(0xffffffffu, lane < NWARPS ? red2[lane][4] : 0u));
+      const bool fits = my_cnt + 1 <= out.seg;
+      if (warp == 0) {
+        a_smin = __reduce_min_sync(0xffffffffu, lane < NWARPS ? red2[lane][0] : 0xffffffffu);
+        a_emax = __reduce_max_sync(0xffffffffu, lane < NWARPS ? red2[lane][1] : 0u);
+        a_smax = __reduce_max_sync(0xffffffffu, lane < NWARPS ? red2[lane][2] : 0u);
+        a_emin = __reduce_min_sync(0xffffffffu, lane < NWARPS ? red2[lane][3] : 0xffffffffu);
+        if (lane == 0) {
+          if (!fits) *out.fail = 1;
+          else {
+            const int64_t gb = (int64_t)blockIdx.x * out.seg + my_cnt;
+            out.pstart[gb] = tile_lo; out.pend[gb] = tile_lo + W; out.acc[gb] = acc; out.cnt[gb] = (int32_t)nS_tile;
+            out.smin[gb] = a_smin; out.emax[gb] = a_emax; out.smax[gb] = a_smax; out.emin[gb] = a_emin;
+            out.flags[gb] = (uint8_t)3;
+          }
+        }
+      }
+      TICK(11);
+      if (fits) my_cnt += 1;
+      acc_carry = acc;
+      { uint32_t* t = hin; hin = hout; hout = t; }
+      nh_carry = nout;
+      continue;
+    }
+    const bool cont0 = depth_in >= mn0 && depth_in <= mx0;
+    int32_t open_total = 0;
+    if (nn_total > 0) {
       // ---- phase D1: run opens inside every resolved word (one warp per word, lane = position)
 #pragma unroll 1
       for (int sl = warp; sl < nn_total; sl += NWARPS) {
@@ -351,6 +456,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         if (lane == 0) sopen[sl] = (uint16_t)__popc(inm & ~prevm);
       }
       __syncthreads();
+      TICK(6);
       if (nn_total <= 32) {
         // few resolved words (the usual case): every warp sums the open counts itself, no block-wide scan
         const int32_t v = lane < nn_total ? (int32_t)sopen[lane] : 0;
@@ -378,6 +484,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       continue;
     }
     if (nn_total > 0) __syncthreads();                     // sopre is complete
+    TICK(7);
     // ---- phase D2: pieces.  Resolved words: exact opens, closes and maxima; stretches of IN words: their boundary maximum
     const int32_t d_end = depth_in + tile_net;
     const bool reach_end = np > 0 && d_end >= mn0 && d_end <= mx0;
@@ -424,6 +531,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       }
     }
     __syncthreads();
+    TICK(8);
     for (int k = tid; k < seg_total; k += THREADS) segmax[k] = 0;                 // no reader left
     acc_carry = reach_end ? pacc[np - 1] : 0;              // block-uniform: read after the barrier, before the tables are cleaned
     // ---- phase E: GMAP4, region-driven: the regions open at the tile start, then the tile's own
@@ -490,6 +598,7 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
         gmap4_round(valid, rs, re, true, cont0, np, pst, pen, pcnt, psmin, pemax, psmax, pemin);
       }
     }
+    TICK(9);
     if (np > 0) {
       __syncthreads();
       // ---- publish the tile's pieces in this block's segment
@@ -505,11 +614,13 @@ static __global__ void __launch_bounds__(THREADS, CTAS_PER_SM) k_cover_tile_wc(c
       }
       for (int k = tid; k < np; k += THREADS) { pacc[k] = 0; pcnt[k] = 0; psmin[k] = 0xffffffffu; pemax[k] = 0; psmax[k] = 0; pemin[k] = 0xffffffffu; pen[k] = 0; }
     } else __syncthreads();                                // (the clean-up above and the reads of hin are over before the next tile writes)
+    TICK(10);
     // the regions still open at the tile end are the next tile's open regions
     { uint32_t* t = hin; hin = hout; hout = t; }
     nh_carry = nout;
   }
   if (tid == 0) out.blk_cnt[blockIdx.x] = (uint32_t)my_cnt;
+#undef TICK
 #undef RLEN
 #undef REXT
 }

@@ -111,6 +111,7 @@ struct Cfg {
   int32_t mn0, mx0;    // thresholds of group 0 (fast path when n_groups == 1)
   uint64_t G;
   int xb;              // 1: partitioned records carry the one-base extension in bit 15 (lengths below 32 768)
+  int dbg;             // profiling hook (option "cover.dbg"): 1 / 2 / 3 cut the word-count tile kernel short after a phase; results are then WRONG
 };
 
 struct Pieces {
@@ -118,6 +119,7 @@ struct Pieces {
   uint32_t* smin; uint32_t* emax; uint32_t* smax; uint32_t* emin; uint8_t* flags;   // bit0: continues from the previous tile, bit1: reaches the tile end
   uint32_t* blk_cnt;   // [gridDim.x] pieces written by every block: block b owns the slots [b * seg, (b + 1) * seg)
   int64_t seg;         // so that the pieces come out in genome order without sorting (block ranges and tiles ascend)
+  unsigned long long* ticks;   // profiling hook (cover.dbg = 9): clock cycles per phase of the word-count kernel, summed over the tiles (thread 0 of every block)
   int* fail;   // 1: output capacity, 2: distinct positions, 3: pieces, 4: halo regions of one tile
 };
 

@@ -1292,13 +1292,16 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   DevBuf<uint8_t> pflags(ctx, cap);
   DevBuf<uint32_t> blk_cnt(ctx, tgrid), blk_off(ctx, (int64_t)tgrid + 1);
   DevBuf<unsigned long long> np_dev(ctx, 1);
-  DevBuf<int> fail(ctx, 1);
+  DevBuf<int> fail(ctx, 4);                              // [0] failure code; [1..3] profiling counters of option cover.dbg = 8
   fail.zero();
   tiled::Cfg tc;
-  tc.n_groups = cfg.n_groups; tc.n_classes = cfg.n_classes; tc.mn = cfg.mn; tc.mx = cfg.mx; tc.mn0 = h_mn[0]; tc.mx0 = h_mx[0]; tc.G = lm.G; tc.xb = xb;
+  tc.n_groups = cfg.n_groups; tc.n_classes = cfg.n_classes; tc.mn = cfg.mn; tc.mx = cfg.mx; tc.mn0 = h_mn[0]; tc.mx0 = h_mx[0]; tc.G = lm.G; tc.xb = xb; tc.dbg = ctx_opt(ctx, "cover.dbg") ? atoi(ctx_opt(ctx, "cover.dbg")) : 0;
   tiled::Pieces pc;
   pc.pstart = pstart.p; pc.pend = pend.p; pc.acc = acc.p; pc.cnt = cnt.p; pc.smin = smin.p; pc.emax = emax.p; pc.smax = smax.p; pc.emin = emin.p;
   pc.flags = pflags.p; pc.blk_cnt = blk_cnt.p; pc.seg = seg; pc.fail = fail.p;
+  DevBuf<unsigned long long> ticks(ctx, 16);
+  ticks.zero();
+  pc.ticks = ticks.p;
   if (cfg.n_groups == 1 && use_wc) {
     // the word-count kernel (cover_tile_wc.cuh); a tile with too many words to resolve sends the operator to the rank kernel
     const tiled::BinMod32 bm = bm32;
@@ -1350,6 +1353,18 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
     if (guard.flags) {
       spec->synced = true;
       if (spec->h_flags[1] || spec->h_flags[2] || spec->h_flags[3] >= guard.max_len) { spec->tripped = true; return false; }
+    }
+    if (tc.dbg == 9) {
+      unsigned long long ht[16];
+      CUDA_TRY(cudaMemcpy(ht, ticks.p, sizeof ht, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[cover.dbg] cycles per phase (sum over tiles, thread 0):");
+      for (int k = 0; k < 12; ++k) fprintf(stderr, " %d:%.1fM", k, (double)ht[k] * 1e-6);
+      fprintf(stderr, "\n");
+    }
+    if (tc.dbg == 8) {
+      int h4[4];
+      CUDA_TRY(cudaMemcpy(h4, fail.p, sizeof h4, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[cover.dbg] tile kernel: %d tiles on the fast path, %d on the regular path, %d words resolved\n", h4[1], h4[2], h4[3]);
     }
     if (*h_f) { *fail_code = *h_f; return false; }
     if (!h_tot[3]) {
