@@ -35,6 +35,10 @@ class TextSchema(C.Structure):
                 ("n_values", C.c_int32), ("value_pos", C.c_void_p), ("start_minus_one", C.c_int32)]
 
 
+class TextOutSchema(C.Structure):
+    _fields_ = [("one_based", C.c_int32), ("n_values", C.c_int32), ("value_cols", C.c_void_p)]
+
+
 class CoverShard(C.Structure):
     _fields_ = [("chrom_span", C.c_void_p), ("first_tile", C.c_int64), ("end_tile", C.c_int64)]
 
@@ -51,7 +55,7 @@ EXPORTS = [
     "gmql_result_column_elem_size", "gmql_result_column_device", "gmql_result_column_copy",
     "gmql_result_as_regions", "gmql_result_free", "gmql_last_device_ms", "gmql_last_h2d_ms",
     "gmql_dataset_upload", "gmql_dataset_free", "gmql_ctx_set_profiling", "gmql_ctx_profile_report",
-    "gmql_difference", "gmql_profile", "gmql_parse_text", "gmql_cover_shard", "gmql_ctx_set_option",
+    "gmql_difference", "gmql_profile", "gmql_parse_text", "gmql_cover_shard", "gmql_ctx_set_option", "gmql_format_text",
 ]
 
 _lib = None
@@ -83,6 +87,7 @@ def load_library(path=None):
     lib.gmql_map.argtypes = [vp, C.POINTER(Regions), C.POINTER(Regions), C.POINTER(Pair), i64, C.POINTER(Agg), i32, C.POINTER(vp)]
     lib.gmql_difference.argtypes = [vp, C.POINTER(Regions), C.POINTER(Regions), C.POINTER(Pair), i64, i32, C.POINTER(vp)]
     lib.gmql_parse_text.argtypes = [vp, C.c_char_p, i64, i32, C.POINTER(TextSchema), C.POINTER(C.c_char_p), i32, C.POINTER(vp)]
+    lib.gmql_format_text.argtypes = [vp, C.POINTER(Regions), C.POINTER(TextOutSchema), C.POINTER(C.c_char_p), C.POINTER(vp)]
     lib.gmql_profile.argtypes = [vp, C.POINTER(Regions), C.POINTER(vp)]
     lib.gmql_cover.argtypes = [vp, C.POINTER(Regions), vp, i32, i32, vp, vp, i64, C.POINTER(Agg), i32, C.POINTER(vp)]
     lib.gmql_cover_shard.argtypes = [vp, C.POINTER(Regions), i32, i32, i32, i64, C.POINTER(CoverShard), C.POINTER(vp)]
@@ -123,4 +128,5 @@ COL_JOIN_LEFT_ROW, COL_JOIN_RIGHT_ROW, COL_JOIN_PAIR, COL_JOIN_START, COL_JOIN_S
 COL_DIFF_REF_ROW = 48
 COL_PROF_LEFTMOST, COL_PROF_RIGHTMOST, COL_PROF_MIN_LENGTH, COL_PROF_MAX_LENGTH, COL_PROF_SUM_LENGTH, COL_PROF_SUM_LENGTH_SQ, COL_PROF_COUNT = 64, 65, 66, 67, 68, 69, 70
 COL_TXT_LINE_OFFSET, COL_TXT_STATUS, COL_TXT_CHROM, COL_TXT_START, COL_TXT_STOP, COL_TXT_STRAND = 80, 81, 82, 83, 84, 85
+COL_TXT_BYTES = 86
 COL_AGG_VALUE, COL_AGG_VALID = 256, 512

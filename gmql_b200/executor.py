@@ -236,6 +236,41 @@ class GMQLCudaExecutor:
         res.free()
         return cols
 
+    # ---- columns -> TEXT ---------------------------------------------------------------------------------------------------
+    def format_text(self, ds, value_cols=None, one_based=False, host_format=None):
+        """The region lines StoreTABRD writes for `ds` (SelectRegions/StoreTABRD.scala:62-80), built on the device
+        (gmql_format_text): returns (bytes, line_offsets int64[n + 1], status uint8[n]).  value_cols: indices of the numeric
+        columns to print (default: all).  Fields the device leaves to the host's DecimalFormat (status bit 0; placeholder byte
+        0x1A) are filled in with host_format(value) when given (the JVM side passes GDouble.toString; tests pass the oracle's)."""
+        c_ds, keep = ds.as_c(narrow=False)
+        nums = [c for c in ds.columns if c[0] == "num"]
+        vc = np.arange(len(nums), dtype=np.int32) if value_cols is None else np.asarray(value_cols, dtype=np.int32)
+        sch = L.TextOutSchema()
+        sch.one_based, sch.n_values = (1 if one_based else 0), len(vc)
+        sch.value_cols = vc.ctypes.data if len(vc) else None
+        names = (C.c_char_p * max(1, len(ds.chrom_names)))(*([n.encode() for n in ds.chrom_names] or [b""]))
+        out = C.c_void_p()
+        self._check(self.lib.gmql_format_text(self.ctx, C.byref(c_ds), C.byref(sch), names, C.byref(out)))
+        res = _Result(self, out)
+        text, off, status = res.column(L.COL_TXT_BYTES, np.uint8).tobytes(), res.column(L.COL_TXT_LINE_OFFSET, np.int64), res.column(L.COL_TXT_STATUS, np.uint8)
+        res.free()
+        if host_format is not None and status.any():
+            lines = []
+            pos = 0
+            for i in np.flatnonzero(status & 1):
+                lines.append(text[pos:off[i]])
+                fields = text[off[i]:off[i + 1] - 1].split(b"\t")
+                for k, col in enumerate(vc):
+                    if fields[4 + k] == b"\x1a":
+                        fields[4 + k] = host_format(float(nums[col][1][i])).encode()
+                lines.append(b"\t".join(fields) + b"\n")
+                pos = off[i + 1]
+            lines.append(text[pos:])
+            text = b"".join(lines)
+            ln = np.frombuffer(text, dtype=np.uint8) == 10
+            off = np.concatenate([[0], np.flatnonzero(ln) + 1]).astype(np.int64)
+        return text, off, status
+
     # ---- PROFILE ----------------------------------------------------------------------------------------------------------
     def profile(self, ds):
         """Per-sample statistics of Profiler.profile (GMQL-Profiler/.../Profilers/Profiler.scala:124-153): returns

@@ -24,10 +24,14 @@ def install_env_hooks(lib):
     def sync(ctx):
         key = ctx.value if hasattr(ctx, "value") else ctx
         vals = tuple(os.environ.get(e) for e in ENV_OPTIONS)
-        if seen.get(key) == vals:
+        before = seen.get(key, (None,) * len(vals))
+        if before == vals:
             return
-        for (env, name), v in zip(ENV_OPTIONS.items(), vals):
-            lib.gmql_ctx_set_option(ctx, name, v.encode() if v else None)
+        # only what the environment sets (or has set and dropped again) is touched: options the program chose itself through
+        # gmql_ctx_set_option (bench.py: defer_check) stay as they are
+        for (env, name), v, old in zip(ENV_OPTIONS.items(), vals, before):
+            if v != old:
+                lib.gmql_ctx_set_option(ctx, name, v.encode() if v else None)
         seen[key] = vals
 
     def wrap(raw):

@@ -319,6 +319,28 @@ typedef struct {
 int gmql_parse_text(gmql_ctx* ctx, const char* text, int64_t n_bytes, int32_t location, const gmql_text_schema* schema,
                     const char* const* chrom_names, int32_t n_chrom, gmql_result** out);
 
+/* ---- columns -> TEXT --------------------------------------------------------------------
+ * Replaces the per-region line construction of MATERIALIZE's writer, StoreTABRD
+ * (GMQL-Spark/.../RegionsOperators/SelectRegions/StoreTABRD.scala:62-80): `(recordKey.productIterator.drop(1) ++ values)
+ * .mkString("\t")`, i.e. chrom \t start \t stop \t strand \t value ... \n with the strand as '*' / '+' / '-', start + 1 for one-based
+ * schemas (:62-69), GNull as "null" (DataTypes.scala:185) and GDouble.toString = DecimalFormat("#.########", ENGLISH) with
+ * RoundingMode.FLOOR (GMQL-Core/.../DataTypes.scala:139-150): at most eight fraction digits, floored towards minus infinity on the
+ * double's shortest decimal form, no trailing zeros, "-0" for -0.0.  One line per region of `in`, in row order (StoreTABRD writes one
+ * file per sample id: with rows grouped by sample a file is one contiguous byte range of the result).  String-valued columns stay on
+ * the host, as everywhere in this ABI; value_cols lists the numeric columns of `in` to print, in output order.
+ *
+ * Result: GMQL_COL_TXT_BYTES uint8 [total] (the text), GMQL_COL_TXT_LINE_OFFSET int64 [n + 1] (byte offset of every line; the last
+ * entry is the total), GMQL_COL_TXT_STATUS uint8 [n]: bit 0 = some numeric field of the line is left to the host's own DecimalFormat
+ * and stands in the text as the single byte 0x1A — non-integers from 2^26 on, magnitudes from 2^53 on, NaN and infinities (below
+ * 2^26 the digits are derived exactly, see gmql_text.cu).  Reading the three columns back is the D2H of the MATERIALIZE step.
+ */
+typedef struct {
+  int32_t one_based;          /* GMQLSchemaCoordinateSystem.OneBased: print start + 1 */
+  int32_t n_values;           /* numeric value columns to print (<= 16) */
+  const int32_t* value_cols;  /* HOST [n_values] indices into in->cols */
+} gmql_text_out_schema;
+int gmql_format_text(gmql_ctx* ctx, const gmql_regions* in, const gmql_text_out_schema* schema, const char* const* chrom_names, gmql_result** out);
+
 /* ---- results --------------------------------------------------------------------------- */
 enum {
   GMQL_COL_MAP_ROW_OFFSETS = 1, GMQL_COL_MAP_REF_ROW = 2, GMQL_COL_MAP_REF_SAMPLE_OFFSETS = 3, GMQL_COL_MAP_COUNT = 4,
@@ -333,7 +355,7 @@ enum {
   GMQL_COL_PROF_LEFTMOST = 64, GMQL_COL_PROF_RIGHTMOST = 65, GMQL_COL_PROF_MIN_LENGTH = 66, GMQL_COL_PROF_MAX_LENGTH = 67,
   GMQL_COL_PROF_SUM_LENGTH = 68, GMQL_COL_PROF_SUM_LENGTH_SQ = 69, GMQL_COL_PROF_COUNT = 70,
   GMQL_COL_TXT_LINE_OFFSET = 80, GMQL_COL_TXT_STATUS = 81, GMQL_COL_TXT_CHROM = 82, GMQL_COL_TXT_START = 83, GMQL_COL_TXT_STOP = 84,
-  GMQL_COL_TXT_STRAND = 85,
+  GMQL_COL_TXT_STRAND = 85, GMQL_COL_TXT_BYTES = 86,
   GMQL_COL_AGG_VALUE = 256, /* + aggregate index */
   GMQL_COL_AGG_VALID = 512  /* + aggregate index */
 };

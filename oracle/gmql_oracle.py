@@ -62,6 +62,9 @@ def sample_id_from_filename(name: str) -> int:
 # GValue helpers (core/DataTypes.scala:76-194)
 # --------------------------------------------------------------------------------------
 
+_WIDE_CONTEXT = __import__("decimal").Context(prec=400)
+
+
 def gdouble_to_string(v: float) -> str:
     """GDouble.toString: DecimalFormat("#.########", ENGLISH), RoundingMode.FLOOR
     (core/DataTypes.scala:139-148)."""
@@ -69,7 +72,8 @@ def gdouble_to_string(v: float) -> str:
         return "NaN"  # DecimalFormat prints U+FFFD for NaN; never produced on this path
     if math.isinf(v):
         return "∞" if v > 0 else "-∞"
-    q = Decimal(repr(v)).quantize(Decimal("0.00000001"), rounding=ROUND_FLOOR)
+    # (a context wide enough for the 309 integer digits of the largest double)
+    q = Decimal(repr(v)).quantize(Decimal("0.00000001"), rounding=ROUND_FLOOR, context=_WIDE_CONTEXT)
     s = format(q, "f")
     if "." in s:
         s = s.rstrip("0").rstrip(".")
@@ -84,6 +88,13 @@ def gvalue_to_string(v) -> str:
     if isinstance(v, float):
         return gdouble_to_string(v)
     return str(v)
+
+
+def store_tab_line(rec, one_based=False) -> str:
+    """One region line of StoreTABRD (SelectRegions/StoreTABRD.scala:62-80): `(recordKey.productIterator.drop(1) ++ values)
+    .mkString("\\t")` — chrom, start (+ 1 for one-based schemas, :62-69), stop, strand, then every GValue's toString."""
+    _sid, chrom, start, stop, strand, vals = rec
+    return "\t".join([chrom, str(start + (1 if one_based else 0)), str(stop), strand] + [gvalue_to_string(v) for v in vals])
 
 
 def _gvalue_cmp_key(v):

@@ -164,3 +164,107 @@ def test_c4_full_size_join(ex):
     assert np.array_equal(dd, np.repeat(mins, np.diff(np.concatenate([np.nonzero(first)[0], [len(g)]]))))   # only minimum-distance candidates survive
     assert len(lrow) >= int(first.sum()) > 10 ** 7 and np.array_equal(left.chrom[lrow], right.chrom[rrow])
     ex.lib.gmql_dataset_free(ex.ctx, dl); ex.lib.gmql_dataset_free(ex.ctx, dr)
+
+
+# ---- BASELINE.json's configs at FULL size, row for row against the C oracle (oracle/gmql_oracle_c.c: the bin-based plan of
+# GenometricCover.scala:98-152 + GMAP4.scala:20-100 and GenometricMap71.scala:81-147), not only through properties -------------
+def _sorted_rows(cols, keys=("chrom", "start", "stop")):
+    o = np.lexsort(tuple(cols[k] for k in reversed(keys)))
+    return {k: v[o] for k, v in cols.items()}
+
+
+@pytest.mark.parametrize("flag", [0, 1, 2, 3], ids=["COVER", "FLAT", "SUMMIT", "HISTOGRAM"])
+def test_c2_full_size_against_the_oracle(ex, flag):
+    """C2: (2, ANY) over 1 000 x 50 000 peaks (5e7 regions) — every row of every variant: coordinates, AccIndex and both Jaccard
+    columns, bit for bit."""
+    from gmql_b200 import synth, _lib as L
+    from oracle import c_oracle as CO
+    CO.set_threads(os.cpu_count() or 1)
+    ds = synth.peak_samples(1000, 50000, 2, with_values=())
+    dset, view, keep = _upload(ex, ds)
+    res = _cover(ex, view, flag, 2, 2 ** 31 - 1)
+    spec = [("chrom", L.COL_COV_CHROM, np.int32), ("start", L.COL_COV_START, np.int64), ("stop", L.COL_COV_STOP, np.int64), ("acc", L.COL_COV_ACC, np.int32),
+            ("j1", L.COL_COV_J1, np.float64), ("j2", L.COL_COV_J2, np.float64)]
+    got = dict(zip([s[0] for s in spec], _cols(ex, res, [(s[1], s[2]) for s in spec])))
+    ex.lib.gmql_result_free(ex.ctx, res)
+    ex.lib.gmql_dataset_free(ex.ctx, dset)
+    want = CO.cover_rows(ds, flag, [2], [2 ** 31 - 1], None, 2000)
+    want = {k: want[k] for k in got}
+    assert len(got["start"]) == len(want["start"]) > 100000
+    # FLAT rows are the extents of the contributing regions: neighbouring runs under the same long regions give identical
+    # (chrom, start, stop), so the comparison orders the rows by every column
+    allk = ("chrom", "start", "stop", "acc", "j1", "j2")
+    got, want = _sorted_rows(got, allk), _sorted_rows(want, allk)
+    for k in got:
+        assert np.array_equal(got[k], want[k]), k
+
+
+def test_c5_full_size_against_the_oracle(ex):
+    """C5: the bench's own step at its own size (2 000 x 50 000 peaks, 1e8 regions, production route on the resident dataset):
+    the COVER table and all 2 000 x n_runs MAP counts equal the oracle's."""
+    from gmql_b200 import synth, _lib as L
+    from gmql_b200.regions import RegionDataset
+    from oracle import c_oracle as CO
+    CO.set_threads(os.cpu_count() or 1)
+    ds = synth.peak_samples(2000, 50000, 5, with_values=())
+    dset, view, keep = _upload(ex, ds)
+    cov = _cover(ex, view, 0, 2, 2 ** 31 - 1)
+    cview = L.Regions()
+    ex._check(ex.lib.gmql_result_as_regions(ex.ctx, cov, C.byref(cview)))
+    pairs = (L.Pair * 2000)()
+    for b in range(2000):
+        pairs[b].left_sample, pairs[b].right_sample = 0, b
+    mp = C.c_void_p()
+    ex._check(ex.lib.gmql_map(ex.ctx, C.byref(cview), C.byref(view), pairs, 2000, (L.Agg * 1)(), 0, C.byref(mp)))
+    names = ("chrom", "start", "stop", "acc", "j1", "j2")
+    got = dict(zip(names, _cols(ex, cov, [(L.COL_COV_CHROM, np.int32), (L.COL_COV_START, np.int64), (L.COL_COV_STOP, np.int64), (L.COL_COV_ACC, np.int32),
+                                          (L.COL_COV_J1, np.float64), (L.COL_COV_J2, np.float64)])))
+    (count,) = _cols(ex, mp, [(L.COL_MAP_COUNT, np.int32)])
+    ex.lib.gmql_result_free(ex.ctx, cov); ex.lib.gmql_result_free(ex.ctx, mp)
+    ex.lib.gmql_dataset_free(ex.ctx, dset)
+    r = CO.cover_rows(ds, 0, [2], [2 ** 31 - 1], None, 2000)
+    r = _sorted_rows(r, ("chrom", "start"))
+    n_runs = len(r["start"])
+    assert n_runs == len(got["start"]) > 5000
+    for k in names:
+        assert np.array_equal(got[k], r[k]), k                   # the device emits (chrom, start) order
+    ref = RegionDataset(ds.chrom_names, r["chrom"], r["start"], r["stop"], r["strand"], np.zeros(n_runs, np.int32), np.array([0], np.int64))
+    pidx = np.stack([np.zeros(2000, np.int32), np.arange(2000, dtype=np.int32)], axis=1)
+    want = CO.map_rows(ref, ds, pidx, None, None, 50000)["count"]
+    assert np.array_equal(count, want)
+
+
+def test_c3_full_size_against_the_oracle(ex):
+    """C3: MAP with SUM / AVG / MAX of signalValue, 100 reference x 1 000 experiment samples (1e8 output rows): counts and MAX
+    bit-exact, SUM / AVG within 1e-9 relative (the association order of a floating-point sum differs, SURVEY A-M8)."""
+    from gmql_b200 import synth, _lib as L
+    from oracle import c_oracle as CO
+    CO.set_threads(os.cpu_count() or 1)
+    nr, ne = 100, 1000
+    ref = synth.promoter_samples(nr, 1000, 3)
+    exp = synth.peak_samples(ne, 50000, 3, with_values=("signalValue",))
+    dr, vr, k1 = _upload(ex, ref)
+    de, ve, k2 = _upload(ex, exp)
+    pairs = (L.Pair * (nr * ne))()
+    for a in range(nr):
+        for b in range(ne):
+            pairs[a * ne + b].left_sample, pairs[a * ne + b].right_sample = a, b
+    aggs = (L.Agg * 3)()
+    for i, kind in enumerate((1, 4, 3)):                         # SUM, AVG, MAX
+        aggs[i].kind, aggs[i].col = kind, 0
+    out = C.c_void_p()
+    ex._check(ex.lib.gmql_map(ex.ctx, C.byref(vr), C.byref(ve), pairs, nr * ne, aggs, 3, C.byref(out)))
+    count, v_sum, v_avg, v_max, ok_sum, ok_max = _cols(ex, out, [(L.COL_MAP_COUNT, np.int32), (L.COL_AGG_VALUE, np.float64), (L.COL_AGG_VALUE + 1, np.float64),
+                                                               (L.COL_AGG_VALUE + 2, np.float64), (L.COL_AGG_VALID, np.uint8), (L.COL_AGG_VALID + 2, np.uint8)])
+    ex.lib.gmql_result_free(ex.ctx, out)
+    ex.lib.gmql_dataset_free(ex.ctx, dr); ex.lib.gmql_dataset_free(ex.ctx, de)
+    pidx = np.array([(a, b) for a in range(nr) for b in range(ne)], dtype=np.int32)
+    val = [c for c in exp.columns if c[0] == "num"][0][1]
+    want = CO.map_rows(ref, exp, pidx, val=val, valid=None, bin_size=50000)
+    assert count.shape[0] == 100_000_000 == want["count"].shape[0]
+    assert np.array_equal(count, want["count"]) and int(count.astype(np.int64).sum()) > 10 ** 6
+    has = want["nn"] > 0
+    assert np.array_equal(ok_sum.astype(bool), has) and np.array_equal(ok_max.astype(bool), has)
+    assert np.array_equal(v_max[has], want["max"][has])
+    np.testing.assert_allclose(v_sum[has], want["sum"][has], rtol=1e-9)
+    np.testing.assert_allclose(v_avg[has], want["sum"][has] / want["nn"][has], rtol=1e-9)
