@@ -650,6 +650,7 @@ struct CovAggPlan {
   int col_id[8];
   int n_aggs = 0;
   int kind[16], slot[16];
+  int need_bag = 0;      // some aggregate is BAG / BAGD: the contributors of every output region are listed (GMQL_COL_BAG_*)
 };
 struct CovCols { const double* v[8]; const uint8_t* ok[8]; };
 struct CovOut { double* value[16]; uint8_t* valid[16]; };
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(256) k_gmap4(const uint32_t* __restrict__ ccls
         int kind = plan.kind[a], q = plan.slot[a];
         double v = 0.0; uint8_t ok = 0;
         if (kind == GMQL_AGG_COUNT) { v = (double)cnt; ok = 1; }
-        else if (nn[q] > 0) {
+        else if (q >= 0 && nn[q] > 0) {
           ok = 1;
           if (kind == GMQL_AGG_SUM) v = sum[q];
           else if (kind == GMQL_AGG_AVG) v = sum[q] / (double)nn[q];
@@ -861,7 +862,7 @@ __global__ void k_gmap4_finish(const uint32_t* __restrict__ ccls, const int32_t*
       int kind = plan.kind[a], q = plan.slot[a];
       double v = 0.0; uint8_t ok = 0;
       if (kind == GMQL_AGG_COUNT) { v = (double)cnt; ok = 1; }
-      else if (acc.nn[q][c] > 0) {
+      else if (q >= 0 && acc.nn[q][c] > 0) {
         ok = 1;
         int nn = acc.nn[q][c];
         if (kind == GMQL_AGG_SUM) v = acc.sum[q][c];
@@ -923,7 +924,7 @@ __global__ void k_run_agg_finish(int64_t nr, CovAggPlan plan, RunAgg acc, const 
       int kind = plan.kind[a], q = plan.slot[a];
       double v = 0.0; uint8_t ok = 0;
       if (kind == GMQL_AGG_COUNT) { v = (double)cnt[c]; ok = 1; }
-      else if (acc.nn[q][c] > 0) {
+      else if (q >= 0 && acc.nn[q][c] > 0) {
         ok = 1;
         int nn = acc.nn[q][c];
         if (kind == GMQL_AGG_SUM) v = acc.sum[q][c];
@@ -976,7 +977,7 @@ static void plan_cov_aggs(const gmql_agg* aggs, int n_aggs, int n_cols_avail, Co
     plan->kind[a] = kind;
     plan->slot[a] = -1;
     if (kind == GMQL_AGG_COUNT) continue;
-    GMQL_REQUIRE(kind != GMQL_AGG_BAG && kind != GMQL_AGG_BAGD, GMQL_ERR_UNSUPPORTED, "BAG/BAGD aggregates are not available in gmql_cover yet");
+    if (kind == GMQL_AGG_BAG || kind == GMQL_AGG_BAGD) { plan->need_bag = 1; continue; }   // strings are built on the host from the contributor lists
     GMQL_REQUIRE(kind >= GMQL_AGG_SUM && kind <= GMQL_AGG_MEDIAN, GMQL_ERR_INVALID, "unknown aggregate kind");
     int col = aggs[a].col;
     GMQL_REQUIRE(col >= 0 && col < n_cols_avail, GMQL_ERR_INVALID, "aggregate column index out of range");
@@ -1278,7 +1279,8 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
   int64_t waves = std::max<int64_t>(1, std::min<int64_t>(4, (t_hi - t_lo + resident * 8) / (resident * 16)));
   if (cfg.n_groups == 1 && use_wc) waves = 1;             // the word-count kernel's blocks cost more to set up; their ranges hold equal shares of the regions anyway
   if (const char* we = ctx_opt(ctx, "cover.waves")) waves = std::max(1, atoi(we));   // tuning hook
-  const unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), resident * waves));
+  unsigned tgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(t_hi - t_lo, 1), resident * waves));
+  if (const char* be = ctx_opt(ctx, "cover.blocks")) tgrid = (unsigned)std::max(1, atoi(be));   // tuning hook
   // piece capacity of a block's segment.  Dense inputs (the tile path's home ground) make few pieces: about two per tile.  With few
   // regions per tile nearly every region can be a piece of its own (at most MAXP per tile); the blocks hold equal shares of the
   // regions, so the pieces spread about evenly — half as much again covers the difference
@@ -1772,6 +1774,58 @@ void gmql_cover_prepare_dataset(gmql_ctx* ctx, gmql_dataset* ds, int64_t bin_siz
   ds->hist_nT = nT; ds->hist_groups = G; ds->hist_n_coarse = n_coarse;
 }
 
+// BAG / BAGD in COVER (DefaultRegionsToRegionFactory.scala:128-168 through GMAP4.scala:57-66,85): the values of the regions that
+// contribute to an output region, as text — strings are host business, so the device lists the contributing input rows of every
+// output region and the host folds them.  A contributor of an output region is an input region of the same group that overlaps it
+// with a compatible strand (GMAP4.scala:38-45; the first-bin clause only makes every pair count once): exactly MAP of the input,
+// every sample relabelled with its group, onto the COVER result (whose "sample" is the group).  One internal gmql_map call with a
+// BAG aggregate produces the lists; output row r of COVER is row r of that MAP (rows come out by group, then in row order).
+__global__ void k_group_of_row(const int32_t* __restrict__ sample, const int32_t* __restrict__ sample_group, int64_t n, int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = sample_group[sample ? sample[i] : 0];
+}
+
+static void attach_bag_lists(gmql_ctx* ctx, DevRegions& d, const int32_t* h_sample_group, int n_groups, gmql_result* res, gmql_result* runs) {
+  // `runs`: the rows whose coordinates define the contributors — the result itself, except for FLAT, whose rows carry the extent
+  // of their contributors instead of the run they were found with (GMAP4.scala:83-84): there the same call with flag COVER
+  if (res->rows == 0) return;
+  gmql_ensure_wide(ctx, &d);
+  gmql_regions rview;
+  int rc = gmql_result_as_regions(ctx, runs, &rview);
+  GMQL_REQUIRE(rc == GMQL_OK, rc, ctx->err);
+  DevBuf<int32_t> grp, d_sg;
+  if (h_sample_group && n_groups > 1) {
+    grp.alloc(ctx, d.n); d_sg.alloc(ctx, d.n_samples);
+    int32_t* h = (int32_t*)ctx_pinned(ctx, 4 * (size_t)d.n_samples);
+    memcpy(h, h_sample_group, 4 * (size_t)d.n_samples);
+    CUDA_TRY(cudaMemcpyAsync(d_sg.p, h, 4 * (size_t)d.n_samples, cudaMemcpyHostToDevice, ctx->stream));
+    if (d.n) LAUNCH(ctx, k_group_of_row, grid_for(ctx, d.n, 256), 256, 0, d.sample, (const int32_t*)d_sg.p, d.n, grp.p);
+    CUDA_TRY(GMQL_SYNC(ctx));            // the pinned table is recycled by the nested call below
+  }
+  std::vector<int64_t> gids((size_t)n_groups);
+  for (int g = 0; g < n_groups; ++g) gids[g] = g;
+  gmql_regions ev;
+  memset(&ev, 0, sizeof ev);
+  ev.n = d.n; ev.location = GMQL_LOC_DEVICE; ev.coord_bits = d.coord_bits;
+  ev.chrom = d.chrom; ev.start = d.start; ev.stop = d.stop;
+  ev.strand = res->unified ? (const int8_t*)nullptr : d.strand;     // unified strands: every input region counts as '*' (assignGroups, GenometricCover.scala:328-341)
+  ev.sample = grp.p;                                                 // null with one group: every row is sample 0
+  ev.n_chrom = d.n_chrom; ev.n_samples = n_groups; ev.sample_ids = gids.data();
+  std::vector<gmql_pair> pairs((size_t)n_groups);
+  for (int g = 0; g < n_groups; ++g) { pairs[g].left_sample = g; pairs[g].right_sample = g; }
+  gmql_agg bag; bag.kind = GMQL_AGG_BAG; bag.col = 0;
+  gmql_result* mp = nullptr;
+  rc = gmql_map(ctx, &rview, &ev, pairs.data(), n_groups, &bag, 1, &mp);
+  GMQL_REQUIRE(rc == GMQL_OK, rc, ctx->err);
+  GMQL_REQUIRE(gmql_result_rows(mp) == res->rows, GMQL_ERR_INVALID, "internal: contributor lists do not line up with the COVER rows");
+  for (int id : {GMQL_COL_BAG_OFFSETS, GMQL_COL_BAG_ROWS}) {
+    auto it = mp->cols.find(id);
+    GMQL_REQUIRE(it != mp->cols.end(), GMQL_ERR_INVALID, "internal: gmql_map returned no contributor lists");
+    res->cols[id] = it->second;
+    mp->cols.erase(it);
+  }
+  gmql_result_free(ctx, mp);
+}
+
 static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups, int32_t flag,
                       const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size, const gmql_agg* aggs, int32_t n_aggs,
                       const gmql_cover_shard_t* shard, gmql_result** out) {
@@ -1917,6 +1971,19 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
     if (total < 0xffffffffull) run_cover<uint32_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res, shard ? &sspec : nullptr);
     else run_cover<uint64_t>(ctx, d, sample_group, n_groups, flag, min_acc, max_acc, bin_size, plan, spans, unified, ins.has_zero != 0, (int64_t)hf[3], res);
     CUDA_TRY(GMQL_SYNC_IF_PENDING(ctx));
+    if (plan.need_bag) {
+      GMQL_REQUIRE(!shard, GMQL_ERR_UNSUPPORTED, "gmql_cover_shard has no aggregates");
+      gmql_result* runs = res;
+      if (flag == GMQL_FLAT) {
+        // the runs behind the FLAT rows, in the same order (both drop the runs without contributors)
+        int rc2 = cover_impl(ctx, in, sample_group, n_groups, GMQL_COVER | (force_unified ? GMQL_COVER_FORCE_UNIFIED : 0), min_acc, max_acc, bin_size, nullptr, 0, nullptr, &runs);
+        GMQL_REQUIRE(rc2 == GMQL_OK, rc2, ctx->err);
+        if (runs->rows != res->rows) { gmql_result_free(ctx, runs); throw gmql_error(GMQL_ERR_INVALID, "internal: FLAT rows do not line up with their runs"); }
+      }
+      try { attach_bag_lists(ctx, d, sample_group, n_groups, res, runs); }
+      catch (...) { if (runs != res) gmql_result_free(ctx, runs); throw; }
+      if (runs != res) gmql_result_free(ctx, runs);
+    }
     *out = res;
     gmql_trace("EXIT");
     return GMQL_OK;

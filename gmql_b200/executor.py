@@ -369,13 +369,24 @@ class GMQLCudaExecutor:
         j2 = res.column(L.COL_COV_J2, np.float64)
         vals = [res.column(L.COL_AGG_VALUE + k, np.float64) for k in range(len(aggregators))]
         oks = [res.column(L.COL_AGG_VALID + k, np.uint8) for k in range(len(aggregators))]
+        # BAG / BAGD: the device lists the contributing input rows of every output region (GMQL_COL_BAG_*); the strings are folded
+        # here, pairwise in input row order, as in GenometricMap71 (the reference's own order is whatever Spark's shuffle produced)
+        bag_slots = [q for q, a in enumerate(aggregators) if a.function_identifier.upper() in ("BAG", "BAGD")]
+        if bag_slots and len(g):
+            from .javafmt import bag_fold
+            bag_off = res.column(L.COL_BAG_OFFSETS, np.int64)
+            bag_rows = res.column(L.COL_BAG_ROWS, np.int32)
+            recs = ds.to_records()
         res.free()
         sc = "*+-"
         out = []
         for i in range(len(g)):
-            aggs = tuple((float(vals[q][i]) if oks[q][i] else None) for q in range(len(aggregators)))
+            aggs = [(float(vals[q][i]) if oks[q][i] else None) for q in range(len(aggregators))]
+            for q in bag_slots:
+                rows_q = np.sort(bag_rows[bag_off[i]:bag_off[i + 1]])
+                aggs[q] = bag_fold([recs[r][5][aggregators[q].index] for r in rows_q], aggregators[q].function_identifier.upper() == "BAGD")
             out.append((gids[g[i]], ds.chrom_names[chrom[i]], int(start[i]), int(stop[i]), sc[strand[i]],
-                        (float(acc[i]), float(j1[i]), float(j2[i])) + aggs))
+                        (float(acc[i]), float(j1[i]), float(j2[i])) + tuple(aggs)))
         return out
 
     # ---- JOIN -------------------------------------------------------------------------------------------------------------

@@ -215,6 +215,11 @@ int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp,
  *   GMQL_COL_COV_GROUP int32, GMQL_COL_COV_CHROM int32, GMQL_COL_COV_START int64, GMQL_COL_COV_STOP int64,
  *   GMQL_COL_COV_STRAND int8, GMQL_COL_COV_ACC int32 (AccIndex), GMQL_COL_COV_JACC_INTERSECT double,
  *   GMQL_COL_COV_JACC_RESULT double, GMQL_COL_AGG_VALUE/VALID + k.
+ * BAG / BAGD (DefaultRegionsToRegionFactory.scala:128-168, folded by GMAP4.scala:57-66): strings are host business, so the
+ * device lists the CONTRIBUTORS of every output row — the input regions of the row's group that overlap the run with a
+ * compatible strand (GMAP4.scala:38-45) — as GMQL_COL_BAG_OFFSETS int64 [rows + 1] / GMQL_COL_BAG_ROWS int32 (row indices of
+ * `in`, unordered inside a list); the host folds the values' text forms (gmql_b200/executor.py).  For FLAT the
+ * contributors are those of the run behind the row, not of the row's own (wider) coordinates.
  */
 int gmql_cover(gmql_ctx* ctx, const gmql_regions* in, const int32_t* sample_group, int32_t n_groups,
                int32_t flag, const int32_t* min_acc, const int32_t* max_acc, int64_t bin_size,
