@@ -419,7 +419,7 @@ template <int MODE>
 constexpr size_t msp_smem_bytes() { return 8 * (size_t)MSP_TILE + msp_stage_bytes<MODE>() + 3 * 4 * (size_t)MSP_BINS + (MODE != MSP_FINE ? 8 * 256 : 0); }
 
 template <int MODE>
-static __global__ void __launch_bounds__(MSP_THREADS, 2) k_multisplit(MspIn in, LinMap lm, int64_t B, int64_t n, int bin_shift, int logw, uint32_t* __restrict__ cursor, MspOut out,
+static __global__ void __launch_bounds__(MSP_THREADS, MODE == 0 ? 3 : 2) k_multisplit(MspIn in, LinMap lm, int64_t B, int64_t n, int bin_shift, int logw, uint32_t* __restrict__ cursor, MspOut out,
                                                                       int vec_ok, int groups, Guard guard, int xb, BinMod32 bm32) {
   if (guard_trips(guard)) return;
   constexpr bool FUSED = MODE != MSP_FINE;
@@ -700,6 +700,20 @@ __device__ __forceinline__ void gmap4_round(bool valid, uint32_t rs, uint32_t re
     int lo = 0, hi = np;                 // first piece with end > rs
     while (lo < hi) { int mid = (lo + hi) >> 1; if (pen[mid] > rs) hi = mid; else lo = mid + 1; }
     j = lo;
+  }
+  if (np > 6) {
+    // many pieces (sparse coverage, thresholds near the typical depth): the lanes of a warp rarely meet on a piece, and the
+    // warp-aggregated loop below would run once per distinct piece — every lane accumulates on its own instead
+    if (valid) {
+      for (; j < np && pst[j] < re; ++j) {
+        if (own || !(j == 0 && cont0)) {   // halo regions only feed runs that START in this tile
+          atomicAdd(&pcnt[j], 1);
+          atomicMin(&psmin[j], rs); atomicMax(&pemax[j], re);
+          atomicMax(&psmax[j], rs); atomicMin(&pemin[j], re);
+        }
+      }
+    }
+    return;
   }
   while (true) {
     bool ov = valid && j < np && pst[j] < re;

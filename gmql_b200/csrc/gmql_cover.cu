@@ -1246,17 +1246,20 @@ static bool run_cover_tiled(gmql_ctx* ctx, const DevRegions& in, const uint32_t*
       mi.chrom8 = (const uint8_t*)in.chrom_narrow; mi.start = in.start; mi.len16 = (const uint16_t*)in.len_narrow; mi.bits = 32;
       const int vec_ok = al16(in.chrom_narrow) && al16(in.start) && al16(in.len_narrow) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
       CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_NARROW>()));
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_NARROW>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // three blocks per SM
       LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_NARROW>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_NARROW>(), mi, lm, cfg.B, n, 32 + logw + 8, logw, cur_coarse.p, mo, vec_ok, G, guard, xb, bm32);
     } else {
       mi.chrom = in.chrom; mi.start = in.start; mi.stop = in.stop; mi.bits = in.coord_bits; mi.cls = cls;
       const int vec_ok = al16(in.chrom) && al16(in.start) && al16(in.stop) && al16(cls) && cfg.B > 0 && cfg.B < 0x7fffffffLL;
       CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_WIDE>()));
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // three blocks per SM
       LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_WIDE>, mg_c, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_WIDE>(), mi, lm, cfg.B, n, 32 + logw + 8, logw, cur_coarse.p, mo, vec_ok, G, guard, xb, bm32);
     }
     memset(&mi, 0, sizeof mi);
     mi.key = key_a.p; mi.len = len_a.p;
     mo.key = nullptr; mo.len = nullptr; mo.rec = rec.p;
     CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_FINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled::msp_smem_bytes<tiled::MSP_FINE>()));
+      CUDA_TRY(cudaFuncSetAttribute(tiled::k_multisplit<tiled::MSP_FINE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // three blocks per SM
     LAUNCH(ctx, tiled::k_multisplit<tiled::MSP_FINE>, mg, tiled::MSP_THREADS, tiled::msp_smem_bytes<tiled::MSP_FINE>(), mi, lm, cfg.B, n, 32 + logw, logw, cur_tile.p, mo, 0, 1, guard, xb, bm32);
   } else {
     GMQL_REQUIRE(!src.narrow, GMQL_ERR_INVALID, "internal: the radix route of the tile path needs the wide columns");
