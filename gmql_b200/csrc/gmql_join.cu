@@ -345,6 +345,235 @@ __global__ void __launch_bounds__(256) k_join_md(LeftSide L, RightIndex<K> R, Li
   }
 }
 
+// ---- MD(k), team form: a warp owns 32 CONSECUTIVE left regions of the genome order and visits the right samples one by one ----
+// k_join_md gives every (left region, right sample) group to one lane: each lane searches a different sample's index block and
+// loads its own handful of candidates — ~15 dependent, uncoalesced sector reads per group, and the kernel is bound by the L2's
+// sector rate (C4: 2e8 groups, 16 + 10 ms).  Neighbouring left regions of the genome order look at (nearly) the same candidates
+// of a sample.  Here a round takes 32 right samples: lane j searches sample j ONCE for the whole team (the union of the team's
+// bin ranges) and copies its few candidates (16-byte packed records) into the sample's slot in shared memory; then the team
+// walks the 32 slots and every lane selects from a slot with its own window, first-round predicates and k-th distance
+// (:117-151) in 32-bit arithmetic.  Same results group by group; the rows of a left region come out by right sample, then in
+// index order.  Samples with more candidates near the team than a slot holds are staged one at a time (up to MDT_CAP), and
+// beyond that every lane streams its own window as k_join_md does.
+constexpr int MDT_SLOT = 8;   // candidates per (team, right sample) slot
+constexpr int MDT_CAP = 64;   // candidates of one (team, right sample) staged one sample at a time (a 64-bit survivor mask)
+
+struct JoinCfg32 { int f_has_max, f_has_min, f_stream, f_max, f_min, s_has_max, s_has_min, s_stream, s_max, s_min, builder, has_eq; };
+// distances of 32-bit coordinates lie in [-(2^31-1), 2^31-1]: thresholds beyond that range always or never hold
+static JoinCfg32 narrow_cfg(const JoinCfg& c) {
+  auto fit = [](int has, int64_t v, bool is_max, int* has32, int* v32) {
+    *has32 = has; *v32 = 0;
+    if (!has) return;
+    if (is_max) {                                          // max > d
+      if (v > 0x7fffffffLL) *has32 = 0; else *v32 = v < -0x80000000LL ? (int)-0x80000000LL : (int)v;
+    } else {                                               // min < d
+      if (v < -0x80000000LL) *has32 = 0; else *v32 = v > 0x7fffffffLL ? 0x7fffffff : (int)v;
+    }
+  };
+  JoinCfg32 r;
+  fit(c.f_has_max, c.f_max, true, &r.f_has_max, &r.f_max); fit(c.f_has_min, c.f_min, false, &r.f_has_min, &r.f_min);
+  fit(c.s_has_max, c.s_max, true, &r.s_has_max, &r.s_max); fit(c.s_has_min, c.s_min, false, &r.s_has_min, &r.s_min);
+  r.f_stream = c.f_stream; r.s_stream = c.s_stream; r.builder = c.builder; r.has_eq = c.has_eq;
+  return r;
+}
+__device__ __forceinline__ int join_distance32(int as, int ae, int bs, int be) {   // distanceCalculator (:375-386)
+  const int d1 = as - be, d2 = bs - ae;
+  const int a1 = d1 < 0 ? -d1 : d1, a2 = d2 < 0 ? -d2 : d2;
+  const int m = a1 < a2 ? a1 : a2;
+  return (ae < bs || be < as) ? m : -m;
+}
+__device__ __forceinline__ bool stream_ok32(int stream, int lstrand, int ls, int le, int rs, int re) {
+  if (stream == 1) return (lstrand != 2) ? (re <= ls) : (rs >= le);
+  if (stream == 2) return (lstrand != 2) ? (rs >= le) : (re <= ls);
+  return true;
+}
+
+// one lane's (left region, right sample) group over `n` staged candidates (sorted by start): count = min(len, k) with ties
+// (:136-146), second round (:160-198); returns the number of rows (written at o when WRITE)
+template <bool WRITE>
+__device__ __forceinline__ int md_select32(const JoinCfg32& c, const int4* cand, int n, int lst, int ls, int le, int wbeg, int wlast, int64_t k, int64_t m_dup,
+                                           const int64_t* __restrict__ r_eq, int64_t leq, int32_t i, int p, int64_t o,
+                                           int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p) {
+  uint64_t fr = 0, em = 0;                                 // first-round survivors; rows to emit
+  int len = 0, dmin = 0x7fffffff;
+  for (int t = 0; t < n; ++t) {
+    const int4 en = cand[t];
+    if (en.x > wlast) break;                               // r.start / B <= binEnd; sorted by start: nothing further lies in the window
+    if (en.y < wbeg || !strand_ok(lst, en.w)) continue;    // r.stop / B >= binStart (:120-122), strands (:123)
+    const int d = join_distance32(ls, le, en.x, en.y);
+    if (c.f_has_max && !(c.f_max > d)) continue;           // :250
+    if (c.f_has_min && !(c.f_min < d)) continue;           // :251
+    if (!stream_ok32(c.f_stream, lst, ls, le, en.x, en.y)) continue;
+    if (c.has_eq && r_eq[(uint32_t)en.z] != leq) continue; // :102-114
+    fr |= 1ull << t; ++len;
+    bool s2 = !(c.s_has_max && !(c.s_max > d)) && !(c.s_has_min && !(c.s_min < d)) && stream_ok32(c.s_stream, lst, ls, le, en.x, en.y);
+    if (c.builder == GMQL_B_INTERSECTION && !(ls < en.y && en.x < le)) s2 = false;
+    if (d < dmin) { dmin = d; em = 0; }
+    if (d == dmin && s2) em |= 1ull << t;
+  }
+  if (len == 0) return 0;
+  const int64_t want = m_dup * len < k ? m_dup * len : k;   // count = min(len, k); identical left records pool their lists (:134)
+  const int64_t idx = (want - 1) / m_dup;                   // position in the de-duplicated sorted list
+  if (idx > 0) {                                            // beyond the minimum: walk the distinct distances in increasing order
+    int64_t seen = 0;
+    int prev = 0;
+    bool first = true;
+    while (true) {
+      int cur = 0, ncur = 0;
+      bool any = false;
+      for (uint64_t m = fr; m; m &= m - 1) {
+        const int4 en = cand[__ffsll((long long)m) - 1];
+        const int d = join_distance32(ls, le, en.x, en.y);
+        if (!first && d <= prev) continue;
+        if (!any || d < cur) { cur = d; ncur = 1; any = true; }
+        else if (d == cur) ++ncur;
+      }
+      seen += ncur; prev = cur; first = false;
+      if (seen > idx) break;
+    }
+    em = 0;
+    for (uint64_t m = fr; m; m &= m - 1) {
+      const int t = __ffsll((long long)m) - 1;
+      const int4 en = cand[t];
+      const int d = join_distance32(ls, le, en.x, en.y);
+      bool s2 = d <= prev && !(c.s_has_max && !(c.s_max > d)) && !(c.s_has_min && !(c.s_min < d)) && stream_ok32(c.s_stream, lst, ls, le, en.x, en.y);
+      if (c.builder == GMQL_B_INTERSECTION && !(ls < en.y && en.x < le)) s2 = false;
+      if (s2) em |= 1ull << t;
+    }
+  }
+  if (WRITE) {
+    for (uint64_t m = em; m; m &= m - 1) { out_l[o] = i; out_r[o] = cand[__ffsll((long long)m) - 1].z; out_p[o] = p; ++o; }
+  }
+  return __popcll(em);
+}
+
+// one (left region, right sample) group on the unpacked index, no storage: count = min(len, k) with ties (:136-146), second round
+template <typename K, bool WRITE>
+__device__ int64_t md_lane_stream(const RightIndex<K>& R, const JoinCfg& cfg, int lst, int64_t ls, int64_t le, int64_t b0, int64_t leq, int64_t m_dup,
+                                  uint64_t base, int64_t lo, int64_t hi, int32_t i, int p, int64_t o, int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p) {
+  int64_t len = 0;
+  for (int64_t k = lo; k < hi; ++k) {
+    int64_t rs = (int64_t)((uint64_t)R.start[k] - base), re = (int64_t)((uint64_t)R.stop[k] - base), d;
+    if (first_round_ok(cfg, lst, ls, le, (int)R.strand[k], rs, re, b0, &d) && (!cfg.has_eq || R.eq[R.row[k]] == leq)) ++len;
+  }
+  if (len == 0) return 0;
+  const int64_t want = m_dup * len < cfg.k ? m_dup * len : cfg.k;
+  const int64_t idx = (want - 1) / m_dup;
+  int64_t seen = 0, prev = 0;
+  bool first = true;
+  while (true) {                                           // walk the distinct distances in increasing order
+    int64_t cur = 0, ncur = 0;
+    bool any = false;
+    for (int64_t k = lo; k < hi; ++k) {
+      int64_t rs = (int64_t)((uint64_t)R.start[k] - base), re = (int64_t)((uint64_t)R.stop[k] - base), d;
+      if (!(first_round_ok(cfg, lst, ls, le, (int)R.strand[k], rs, re, b0, &d) && (!cfg.has_eq || R.eq[R.row[k]] == leq))) continue;
+      if (!first && d <= prev) continue;
+      if (!any || d < cur) { cur = d; ncur = 1; any = true; }
+      else if (d == cur) ++ncur;
+    }
+    seen += ncur; prev = cur; first = false;
+    if (seen > idx) break;
+  }
+  int64_t mine = 0;
+  for (int64_t k = lo; k < hi; ++k) {
+    int64_t rs = (int64_t)((uint64_t)R.start[k] - base), re = (int64_t)((uint64_t)R.stop[k] - base), d;
+    if (first_round_ok(cfg, lst, ls, le, (int)R.strand[k], rs, re, b0, &d) && (!cfg.has_eq || R.eq[R.row[k]] == leq) && d <= prev &&
+        second_round_ok(cfg, lst, ls, le, rs, re, d)) {
+      if (WRITE) { out_l[o + mine] = i; out_r[o + mine] = (int32_t)R.row[k]; out_p[o + mine] = p; }
+      ++mine;
+    }
+  }
+  return mine;
+}
+
+template <typename K, bool WRITE>
+__global__ void __launch_bounds__(256, 3) k_join_md_team(LeftSide L, RightIndex<K> R, LinMap lm, JoinCfg cfg, JoinCfg32 c32, const int32_t* __restrict__ pair_t /* [right sample][left sample] */, int n_ls, int n_rs,
+                                                         const int32_t* __restrict__ mult, int64_t* __restrict__ cnt, const int64_t* __restrict__ off,
+                                                         int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p) {
+  __shared__ int4 s_slot[8][32 * MDT_SLOT];
+  __shared__ int4 s_big[8][MDT_CAP];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int4* slots = s_slot[threadIdx.x >> 5];
+  int4* big = s_big[threadIdx.x >> 5];
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_teams = (L.n + 31) >> 5;
+  for (int64_t team = warp; team < n_teams; team += nwarps) {
+    const int64_t slot = team * 32 + lane;
+    bool valid = slot < L.n;
+    int64_t i = 0, b0 = 1, b1 = 0, m_dup = 1, leq = 0;
+    int c = -1, lst = 0, la = 0, ls = 0, le = 0;
+    if (valid) {
+      i = L.perm ? (int64_t)L.perm[slot] : slot;
+      c = L.chrom[i];
+      ls = ((const int32_t*)L.start)[i]; le = ((const int32_t*)L.stop)[i];
+      lst = L.strand ? (int)L.strand[i] : 0;
+      la = L.sample ? L.sample[i] : 0;
+      left_bins(cfg, lst, ls, le, &b0, &b1);
+      m_dup = mult ? mult[i] : 1;
+      leq = cfg.has_eq ? L.eq[i] : 0;
+      valid = b0 <= b1 && c >= 0 && c < lm.n_chrom;
+    }
+    // the lane's own window in 32 bits: r.stop >= binStart * B (at most the left stop), r.start <= (binEnd + 1) * B - 1
+    const int wbeg = (int)(b0 * cfg.B);
+    const int64_t wl = (b1 + 1) * cfg.B - 1;
+    const int wlast = wl > 0x7fffffffLL ? 0x7fffffff : (int)wl;
+    const int64_t wbase = (WRITE && slot < L.n) ? off[slot] : 0;
+    int64_t total = 0;
+    unsigned todo = __ballot_sync(FULL, valid);
+    while (todo) {                                         // one pass per chromosome present in the team (nearly always one)
+      const int cs = __shfl_sync(FULL, c, __ffs(todo) - 1);
+      const bool act = valid && c == cs;
+      todo &= ~__ballot_sync(FULL, act);
+      int64_t ub0 = act ? b0 : 0x7fffffffffffffffLL, ub1 = act ? b1 : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int64_t x0 = __shfl_xor_sync(FULL, ub0, o), x1 = __shfl_xor_sync(FULL, ub1, o);
+        ub0 = x0 < ub0 ? x0 : ub0; ub1 = x1 > ub1 ? x1 : ub1;
+      }
+      const uint64_t cbase = lm.coff[cs];
+      for (int s0 = 0; s0 < n_rs; s0 += 32) {
+        // lane j: sample s0 + j's candidates near the team -> its slot
+        int64_t LO = 0, HI = 0;
+        if (s0 + lane < n_rs) window<K>(R, lm, (uint64_t)(s0 + lane) * lm.G, cs, ub0, ub1, cfg.B, &LO, &HI);
+        const int64_t nn = HI - LO;
+        const int nmine = nn > MDT_CAP ? MDT_CAP + 1 : (int)nn;
+        __syncwarp();                                      // the previous round's readers are done with the slots
+        if (nmine <= MDT_SLOT) {
+#pragma unroll
+          for (int t = 0; t < MDT_SLOT; ++t) if (t < nmine) slots[lane * MDT_SLOT + t] = R.packed[LO + t];
+        }
+        __syncwarp();
+        const int ns = n_rs - s0 < 32 ? n_rs - s0 : 32;
+        int p_next = act ? pair_t[(int64_t)s0 * n_ls + la] : -1;
+        for (int jj = 0; jj < ns; ++jj) {
+          const int n = __shfl_sync(FULL, nmine, jj);
+          const int p = p_next;
+          if (jj + 1 < ns) p_next = act ? pair_t[(int64_t)(s0 + jj + 1) * n_ls + la] : -1;
+          if (n == 0) continue;                            // no candidate of this sample near the team
+          const int b = s0 + jj;
+          int mine = 0;
+          if (n <= MDT_SLOT) {
+            if (p >= 0) mine = md_select32<WRITE>(c32, slots + jj * MDT_SLOT, n, lst, ls, le, wbeg, wlast, cfg.k, m_dup, R.eq, leq, (int32_t)i, p, wbase + total, out_l, out_r, out_p);
+          } else if (n <= MDT_CAP) {                       // more than a slot holds: stage this sample alone
+            const int64_t lo = __shfl_sync(FULL, LO, jj);
+            __syncwarp();
+            for (int t = lane; t < n; t += 32) big[t] = R.packed[lo + t];
+            __syncwarp();
+            if (p >= 0) mine = md_select32<WRITE>(c32, big, n, lst, ls, le, wbeg, wlast, cfg.k, m_dup, R.eq, leq, (int32_t)i, p, wbase + total, out_l, out_r, out_p);
+          } else if (p >= 0) {                             // a dense right sample: every lane on its own, as k_join_md's streaming path
+            int64_t l1, h1;
+            window<K>(R, lm, (uint64_t)b * lm.G, cs, b0, b1, cfg.B, &l1, &h1);
+            mine = (int)md_lane_stream<K, WRITE>(R, cfg, lst, ls, le, b0, leq, m_dup, (uint64_t)b * lm.G + cbase, l1, h1, (int32_t)i, p, wbase + total, out_l, out_r, out_p);
+          }
+          total += mine;
+        }
+      }
+    }
+    if (!WRITE && slot < L.n) cnt[slot] = total;
+  }
+}
+
 // per sorted index entry: strand and sample of the right row
 __global__ void k_join_payload(const uint32_t* __restrict__ rows, int64_t n, const int8_t* __restrict__ strand, const int32_t* __restrict__ sample, int8_t* __restrict__ s_strand, int32_t* __restrict__ s_sample) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
@@ -565,18 +794,38 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
     LAUNCH(ctx, k_dup_mult, grid_for(ctx, nl, 256), 256, 0, left.dup_of, nl, dc.p, mult.p);
   }
 
+  // MD: the team kernel when the right coordinates are packed, the left regions are visited in genome order and the pair table is
+  // dense enough that a team meets most samples anyway (it walks all right samples); option "join.md" = "team" | "lane" forces one
+  const bool team_ok = cfg.has_md && R.packed && left.coord_bits == 32;
+  bool md_team = team_ok && L.perm && n_pairs * 4 >= (int64_t)n_ls * n_rs;
+  if (const char* o = ctx_opt(ctx, "join.md")) {
+    if (!strcmp(o, "team")) md_team = team_ok;
+    else if (!strcmp(o, "lane")) md_team = false;
+  }
+  DevBuf<int32_t> d_pair_t;
+  if (md_team) {
+    std::vector<int32_t> h_pair_t((size_t)n_ls * (size_t)n_rs);
+    for (int a = 0; a < n_ls; ++a)
+      for (int b = 0; b < n_rs; ++b) h_pair_t[(size_t)b * n_ls + a] = h_pair[(size_t)a * n_rs + b];
+    d_pair_t.alloc(ctx, (int64_t)n_ls * n_rs);
+    CUDA_TRY(cudaMemcpyAsync(d_pair_t.p, h_pair_t.data(), 4 * h_pair_t.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(GMQL_SYNC(ctx));
+  }
   // memo of the count pass for the write pass (6 bytes per (left region, allowed right sample) group), when it fits
   DevBuf<uint32_t> memo_lo;
   DevBuf<uint16_t> memo_ok;
   int64_t memo_stride = 0;
-  if (cfg.has_md && R.packed && nl) {
+  if (cfg.has_md && R.packed && nl && !md_team) {
     for (int a = 0; a < n_ls; ++a) memo_stride = std::max<int64_t>(memo_stride, h_aoff[a + 1] - h_aoff[a]);
     if (memo_stride > 0 && nl * memo_stride <= (int64_t)700000000) { memo_lo.alloc(ctx, nl * memo_stride); memo_ok.alloc(ctx, nl * memo_stride); }
   }
+  const int team_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nl, 256), (int64_t)ctx->num_sms * 8));
+
   DevBuf<int64_t> cnt(ctx, nl + 1);
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nl, 8), (int64_t)ctx->num_sms * 16));
   if (nl) {
-    if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, false>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
+    if (md_team) LAUNCH(ctx, (k_join_md_team<K, false>), team_blocks, 256, 0, L, R, lm, cfg, narrow_cfg(cfg), d_pair_t.p, n_ls, n_rs, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr);
+    else if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, false>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
                            memo_lo.p, memo_ok.p, memo_stride);
     else LAUNCH(ctx, (k_join_scan<K, false>), blocks, 256, 0, L, R, lm, cfg, d_pair.p, n_rs, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr);
   }
@@ -587,7 +836,8 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   GMQL_REQUIRE(n_out < (int64_t)0x7fffffff * 8, GMQL_ERR_UNSUPPORTED, "join output too large for this version");
   DevBuf<int32_t> ol(ctx, n_out), orr(ctx, n_out), op(ctx, n_out);
   if (nl && n_out) {
-    if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, true>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p,
+    if (md_team) LAUNCH(ctx, (k_join_md_team<K, true>), team_blocks, 256, 0, L, R, lm, cfg, narrow_cfg(cfg), d_pair_t.p, n_ls, n_rs, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p);
+    else if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, true>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p,
                            memo_lo.p, memo_ok.p, memo_stride);
     else LAUNCH(ctx, (k_join_scan<K, true>), blocks, 256, 0, L, R, lm, cfg, d_pair.p, n_rs, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p);
   }

@@ -11,10 +11,14 @@ from tests.randgen import rand_regions, canon
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ex():
+@pytest.fixture(scope="module", params=["auto", "team", "lane"])
+def ex(request):
+    """Every test runs three times: the library's own choice of the MD kernel, the team form (a warp owns 32 consecutive left
+    regions and walks the right samples, candidates staged in shared memory) and the lane form (one lane per group)."""
     from gmql_b200 import GMQLCudaExecutor
     e = GMQLCudaExecutor()
+    if request.param != "auto":
+        e.set_option("join.md", request.param)
     yield e
     e.close()
 
@@ -139,3 +143,21 @@ def test_join_md_int64_coordinates(ex):
     pairs = {(a, b): O.md5_pair_id(a, b) for a in (1, 2) for b in (10, 11, 12)}
     for spec, builder in (([("MD", 1)], "RIGHT"), ([("MD", 2), ("DOWN", 0)], "LEFT"), ([("DISTLESS", 20001), ("MD", 3)], "CONTIG")):
         _check(ex, left, right, [1, 2], [10, 11, 12], pairs, spec, builder)
+
+
+def test_join_md_dense_right_and_many_samples(ex):
+    """More right samples than a warp has lanes (the team kernel searches 32 samples at a time), several chromosomes inside one
+    team of 32 left regions, and right samples dense enough that a team's candidate list overflows its shared-memory stage
+    (every lane then streams its own window)."""
+    rng = random.Random(2024)
+    chroms = ["chr1", "chr2", "chr3"]
+    lids, rids = [1, 2, 3], list(range(10, 10 + 45))
+    left = rand_regions(rng, 90, lids, chroms=chroms, span=300000, max_len=2500, n_vals=0, bin_mults=(5000,))
+    left = left + left[:6]                                     # identical left records pool their candidate lists
+    right = rand_regions(rng, 45 * 12, rids, chroms=chroms, span=300000, max_len=2500, n_vals=0, bin_mults=(5000,))
+    dense = rand_regions(rng, 900, [rids[3], rids[40]], chroms=["chr1"], span=120000, max_len=300, n_vals=0)   # > 64 candidates per team
+    right = right + dense
+    pairs = {(a, b): O.md5_pair_id(a, b) for a in lids for b in rids if (a + b) % 7 != 0}
+    for spec, builder in (([("MD", 1)], "RIGHT"), ([("MD", 3), ("DOWN", 0)], "LEFT"), ([("UP", 0), ("MD", 2)], "CONTIG"),
+                          ([("DISTLESS", 30001), ("MD", 1), ("DISTGREATER", 50)], "LEFT"), ([("DISTGREATER", 1000), ("MD", 2)], "BOTH")):
+        _check(ex, left, right, lids, rids, pairs, spec, builder)
