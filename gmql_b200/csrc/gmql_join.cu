@@ -355,8 +355,9 @@ __global__ void __launch_bounds__(256) k_join_md(LeftSide L, RightIndex<K> R, Li
 // (:117-151) in 32-bit arithmetic.  Same results group by group; the rows of a left region come out by right sample, then in
 // index order.  Samples with more candidates near the team than a slot holds are staged one at a time (up to MDT_CAP), and
 // beyond that every lane streams its own window as k_join_md does.
-constexpr int MDT_SLOT = 8;   // candidates per (team, right sample) slot
-constexpr int MDT_CAP = 64;   // candidates of one (team, right sample) staged one sample at a time (a 64-bit survivor mask)
+constexpr int MDT_SLOT = 16;  // candidates per (team, right sample) slot (a 16-bit memo mask per lane)
+constexpr int MDT_CAP = 32;   // candidates of one (team, right sample) staged one sample at a time (a 32-bit survivor mask)
+constexpr uint32_t MDT_NONE = 0xffffffffu, MDT_REDO = 0xfffffffeu;   // memo: no candidate near the team / not memoised
 
 struct JoinCfg32 { int f_has_max, f_has_min, f_stream, f_max, f_min, s_has_max, s_has_min, s_stream, s_max, s_min, builder, has_eq; };
 // distances of 32-bit coordinates lie in [-(2^31-1), 2^31-1]: thresholds beyond that range always or never hold
@@ -382,38 +383,42 @@ __device__ __forceinline__ int join_distance32(int as, int ae, int bs, int be) {
   const int m = a1 < a2 ? a1 : a2;
   return (ae < bs || be < as) ? m : -m;
 }
-__device__ __forceinline__ bool stream_ok32(int stream, int lstrand, int ls, int le, int rs, int re) {
-  if (stream == 1) return (lstrand != 2) ? (re <= ls) : (rs >= le);
-  if (stream == 2) return (lstrand != 2) ? (rs >= le) : (re <= ls);
-  return true;
+
+// what a lane keeps about its left region for the selection: window, and the stream conditions (:255-279, :171-183; they look at
+// the LEFT strand only) of both rounds as bounds on the candidate's stop / start
+struct LaneQ { int ls, le, lst, wbeg, wlast, f_re_max, f_rs_min, s_re_max, s_rs_min; };
+__device__ __forceinline__ void stream_bounds(int stream, int lst, int ls, int le, int* re_max, int* rs_min) {
+  const bool need_re = (stream == 1 && lst != 2) || (stream == 2 && lst == 2);   // re <= ls
+  const bool need_rs = (stream == 1 && lst == 2) || (stream == 2 && lst != 2);   // rs >= le
+  *re_max = need_re ? ls : 0x7fffffff;
+  *rs_min = need_rs ? le : (int)0x80000000;
 }
 
-// one lane's (left region, right sample) group over `n` staged candidates (sorted by start): count = min(len, k) with ties
-// (:136-146), second round (:160-198); returns the number of rows (written at o when WRITE)
-template <bool WRITE>
-__device__ __forceinline__ int md_select32(const JoinCfg32& c, const int4* cand, int n, int lst, int ls, int le, int wbeg, int wlast, int64_t k, int64_t m_dup,
-                                           const int64_t* __restrict__ r_eq, int64_t leq, int32_t i, int p, int64_t o,
-                                           int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p) {
-  uint64_t fr = 0, em = 0;                                 // first-round survivors; rows to emit
+// one lane's (left region, right sample) group over `n` <= 32 staged candidates (cand[t * stride], sorted by start):
+// count = min(len, k) with ties (:136-146), second round (:160-198); returns the mask of the candidates that become rows.
+// The scan is branch-free: the lanes of a team disagree about nearly every candidate.
+__device__ __forceinline__ uint32_t md_select32(const JoinCfg32& c, const int4* cand, int stride, int n, const LaneQ& q, int64_t k, int64_t m_dup,
+                                                const int64_t* __restrict__ r_eq, int64_t leq) {
+  uint32_t fr = 0, em = 0;                                 // first-round survivors; rows to emit
   int len = 0, dmin = 0x7fffffff;
+  const bool inter = c.builder == GMQL_B_INTERSECTION;
   for (int t = 0; t < n; ++t) {
-    const int4 en = cand[t];
-    if (en.x > wlast) break;                               // r.start / B <= binEnd; sorted by start: nothing further lies in the window
-    if (en.y < wbeg || !strand_ok(lst, en.w)) continue;    // r.stop / B >= binStart (:120-122), strands (:123)
-    const int d = join_distance32(ls, le, en.x, en.y);
-    if (c.f_has_max && !(c.f_max > d)) continue;           // :250
-    if (c.f_has_min && !(c.f_min < d)) continue;           // :251
-    if (!stream_ok32(c.f_stream, lst, ls, le, en.x, en.y)) continue;
-    if (c.has_eq && r_eq[(uint32_t)en.z] != leq) continue; // :102-114
-    fr |= 1ull << t; ++len;
-    bool s2 = !(c.s_has_max && !(c.s_max > d)) && !(c.s_has_min && !(c.s_min < d)) && stream_ok32(c.s_stream, lst, ls, le, en.x, en.y);
-    if (c.builder == GMQL_B_INTERSECTION && !(ls < en.y && en.x < le)) s2 = false;
-    if (d < dmin) { dmin = d; em = 0; }
-    if (d == dmin && s2) em |= 1ull << t;
+    const int4 en = cand[t * stride];
+    const int d = join_distance32(q.ls, q.le, en.x, en.y);
+    // window: r.start / B <= binEnd, r.stop / B >= binStart (:120-122); strands (:123); distance and stream (:250-279)
+    bool ok = (en.x <= q.wlast) & (en.y >= q.wbeg) & strand_ok(q.lst, en.w) & (!c.f_has_max | (c.f_max > d)) & (!c.f_has_min | (c.f_min < d)) &
+              (en.y <= q.f_re_max) & (en.x >= q.f_rs_min);
+    if (c.has_eq) { if (ok) ok = r_eq[(uint32_t)en.z] == leq; }   // :102-114
+    const bool s2 = ok & (!c.s_has_max | (c.s_max > d)) & (!c.s_has_min | (c.s_min < d)) & (en.y <= q.s_re_max) & (en.x >= q.s_rs_min) &
+                    (!inter | ((q.ls < en.y) & (en.x < q.le)));
+    fr |= (uint32_t)ok << t; len += ok;
+    const bool lt = ok & (d < dmin);
+    dmin = lt ? d : dmin; em = lt ? 0u : em;
+    em |= (uint32_t)(s2 & (d == dmin)) << t;
   }
-  if (len == 0) return 0;
+  if (len == 0) return 0u;
   const int64_t want = m_dup * len < k ? m_dup * len : k;   // count = min(len, k); identical left records pool their lists (:134)
-  const int64_t idx = (want - 1) / m_dup;                   // position in the de-duplicated sorted list
+  const int64_t idx = m_dup == 1 ? want - 1 : (want - 1) / m_dup;   // position in the de-duplicated sorted list (no 64-bit division in the usual case)
   if (idx > 0) {                                            // beyond the minimum: walk the distinct distances in increasing order
     int64_t seen = 0;
     int prev = 0;
@@ -421,9 +426,9 @@ __device__ __forceinline__ int md_select32(const JoinCfg32& c, const int4* cand,
     while (true) {
       int cur = 0, ncur = 0;
       bool any = false;
-      for (uint64_t m = fr; m; m &= m - 1) {
-        const int4 en = cand[__ffsll((long long)m) - 1];
-        const int d = join_distance32(ls, le, en.x, en.y);
+      for (uint32_t m = fr; m; m &= m - 1) {
+        const int4 en = cand[(__ffs((int)m) - 1) * stride];
+        const int d = join_distance32(q.ls, q.le, en.x, en.y);
         if (!first && d <= prev) continue;
         if (!any || d < cur) { cur = d; ncur = 1; any = true; }
         else if (d == cur) ++ncur;
@@ -432,19 +437,16 @@ __device__ __forceinline__ int md_select32(const JoinCfg32& c, const int4* cand,
       if (seen > idx) break;
     }
     em = 0;
-    for (uint64_t m = fr; m; m &= m - 1) {
-      const int t = __ffsll((long long)m) - 1;
-      const int4 en = cand[t];
-      const int d = join_distance32(ls, le, en.x, en.y);
-      bool s2 = d <= prev && !(c.s_has_max && !(c.s_max > d)) && !(c.s_has_min && !(c.s_min < d)) && stream_ok32(c.s_stream, lst, ls, le, en.x, en.y);
-      if (c.builder == GMQL_B_INTERSECTION && !(ls < en.y && en.x < le)) s2 = false;
-      if (s2) em |= 1ull << t;
+    for (uint32_t m = fr; m; m &= m - 1) {
+      const int t = __ffs((int)m) - 1;
+      const int4 en = cand[t * stride];
+      const int d = join_distance32(q.ls, q.le, en.x, en.y);
+      const bool s2 = (d <= prev) & (!c.s_has_max | (c.s_max > d)) & (!c.s_has_min | (c.s_min < d)) & (en.y <= q.s_re_max) & (en.x >= q.s_rs_min) &
+                      (!inter | ((q.ls < en.y) & (en.x < q.le)));
+      em |= (uint32_t)s2 << t;
     }
   }
-  if (WRITE) {
-    for (uint64_t m = em; m; m &= m - 1) { out_l[o] = i; out_r[o] = cand[__ffsll((long long)m) - 1].z; out_p[o] = p; ++o; }
-  }
-  return __popcll(em);
+  return em;
 }
 
 // one (left region, right sample) group on the unpacked index, no storage: count = min(len, k) with ties (:136-146), second round
@@ -487,15 +489,18 @@ __device__ int64_t md_lane_stream(const RightIndex<K>& R, const JoinCfg& cfg, in
 }
 
 template <typename K, bool WRITE>
-__global__ void __launch_bounds__(256, 3) k_join_md_team(LeftSide L, RightIndex<K> R, LinMap lm, JoinCfg cfg, JoinCfg32 c32, const int32_t* __restrict__ pair_t /* [right sample][left sample] */, int n_ls, int n_rs,
+__global__ void __launch_bounds__(256, 2) k_join_md_team(LeftSide L, RightIndex<K> R, LinMap lm, JoinCfg cfg, JoinCfg32 c32, const int32_t* __restrict__ pair_t /* [right sample][left sample] */, int n_ls, int n_rs,
                                                          const int32_t* __restrict__ mult, int64_t* __restrict__ cnt, const int64_t* __restrict__ off,
-                                                         int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p) {
-  __shared__ int4 s_slot[8][32 * MDT_SLOT];
-  __shared__ int4 s_big[8][MDT_CAP];
+                                                         int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p,
+                                                         uint32_t* __restrict__ memo_lo, uint16_t* __restrict__ memo_em, int32_t* __restrict__ cnt_ts) {
+  // memo (count pass, optional): per (team, right sample) the first index of the slot's candidates (or MDT_NONE / MDT_REDO), the
+  // number of rows of the whole team with that sample (cnt_ts, instead of the per-region cnt) and per lane the 16-bit mask of the
+  // candidates that become rows — k_join_md_team_write then needs neither searches nor selection and writes contiguous runs
+  extern __shared__ int4 s_team[];                         // per warp: 32 slots [entry][sample], then the one-sample stage
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  int4* slots = s_slot[threadIdx.x >> 5];
-  int4* big = s_big[threadIdx.x >> 5];
+  int4* slots = s_team + (threadIdx.x >> 5) * (32 * MDT_SLOT + MDT_CAP);
+  int4* big = slots + 32 * MDT_SLOT;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n_teams = (L.n + 31) >> 5;
   for (int64_t team = warp; team < n_teams; team += nwarps) {
@@ -518,9 +523,19 @@ __global__ void __launch_bounds__(256, 3) k_join_md_team(LeftSide L, RightIndex<
     const int wbeg = (int)(b0 * cfg.B);
     const int64_t wl = (b1 + 1) * cfg.B - 1;
     const int wlast = wl > 0x7fffffffLL ? 0x7fffffff : (int)wl;
+    LaneQ q;
+    q.ls = ls; q.le = le; q.lst = lst; q.wbeg = wbeg; q.wlast = wlast;
+    stream_bounds(c32.f_stream, lst, ls, le, &q.f_re_max, &q.f_rs_min);
+    stream_bounds(c32.s_stream, lst, ls, le, &q.s_re_max, &q.s_rs_min);
     const int64_t wbase = (WRITE && slot < L.n) ? off[slot] : 0;
     int64_t total = 0;
     unsigned todo = __ballot_sync(FULL, valid);
+    // a team that spans a chromosome boundary visits the samples once per chromosome: nothing to memoise, the write pass redoes it
+    const bool memo_on = !WRITE && memo_lo != nullptr;
+    const int c_first = __shfl_sync(FULL, c, todo ? __ffs(todo) - 1 : 0);   // (not inside a short-circuit: every lane takes part)
+    const unsigned same = __ballot_sync(FULL, valid && c == c_first);
+    const bool memo = memo_on && todo == same;
+    if (memo_on && !memo) for (int b = lane; b < n_rs; b += 32) { memo_lo[team * n_rs + b] = MDT_REDO; cnt_ts[team * n_rs + b] = 0; }
     while (todo) {                                         // one pass per chromosome present in the team (nearly always one)
       const int cs = __shfl_sync(FULL, c, __ffs(todo) - 1);
       const bool act = valid && c == cs;
@@ -541,11 +556,13 @@ __global__ void __launch_bounds__(256, 3) k_join_md_team(LeftSide L, RightIndex<
         __syncwarp();                                      // the previous round's readers are done with the slots
         if (nmine <= MDT_SLOT) {
 #pragma unroll
-          for (int t = 0; t < MDT_SLOT; ++t) if (t < nmine) slots[lane * MDT_SLOT + t] = R.packed[LO + t];
+          for (int t = 0; t < MDT_SLOT; ++t) if (t < nmine) slots[t * 32 + lane] = R.packed[LO + t];   // [entry][sample]: conflict-free both ways
         }
         __syncwarp();
+        if (memo && s0 + lane < n_rs) memo_lo[team * n_rs + s0 + lane] = nmine == 0 ? MDT_NONE : (nmine <= MDT_SLOT ? (uint32_t)LO : MDT_REDO);
         const int ns = n_rs - s0 < 32 ? n_rs - s0 : 32;
         int p_next = act ? pair_t[(int64_t)s0 * n_ls + la] : -1;
+        int round_cnt = 0;                                 // lane j: rows of the whole team with sample s0 + j (memo mode)
         for (int jj = 0; jj < ns; ++jj) {
           const int n = __shfl_sync(FULL, nmine, jj);
           const int p = p_next;
@@ -554,23 +571,119 @@ __global__ void __launch_bounds__(256, 3) k_join_md_team(LeftSide L, RightIndex<
           const int b = s0 + jj;
           int mine = 0;
           if (n <= MDT_SLOT) {
-            if (p >= 0) mine = md_select32<WRITE>(c32, slots + jj * MDT_SLOT, n, lst, ls, le, wbeg, wlast, cfg.k, m_dup, R.eq, leq, (int32_t)i, p, wbase + total, out_l, out_r, out_p);
+            const uint32_t em = p >= 0 ? md_select32(c32, slots + jj, 32, n, q, cfg.k, m_dup, R.eq, leq) : 0u;
+            mine = __popc(em);
+            if (memo) memo_em[((team * n_rs + b) << 5) + lane] = (uint16_t)em;
+            if (WRITE) { int64_t o = wbase + total; for (uint32_t m = em; m; m &= m - 1) { out_l[o] = (int32_t)i; out_r[o] = slots[(__ffs((int)m) - 1) * 32 + jj].z; out_p[o] = p; ++o; } }
           } else if (n <= MDT_CAP) {                       // more than a slot holds: stage this sample alone
             const int64_t lo = __shfl_sync(FULL, LO, jj);
             __syncwarp();
             for (int t = lane; t < n; t += 32) big[t] = R.packed[lo + t];
             __syncwarp();
-            if (p >= 0) mine = md_select32<WRITE>(c32, big, n, lst, ls, le, wbeg, wlast, cfg.k, m_dup, R.eq, leq, (int32_t)i, p, wbase + total, out_l, out_r, out_p);
+            const uint32_t em = p >= 0 ? md_select32(c32, big, 1, n, q, cfg.k, m_dup, R.eq, leq) : 0u;
+            mine = __popc(em);
+            if (WRITE) { int64_t o = wbase + total; for (uint32_t m = em; m; m &= m - 1) { out_l[o] = (int32_t)i; out_r[o] = big[__ffs((int)m) - 1].z; out_p[o] = p; ++o; } }
           } else if (p >= 0) {                             // a dense right sample: every lane on its own, as k_join_md's streaming path
             int64_t l1, h1;
             window<K>(R, lm, (uint64_t)b * lm.G, cs, b0, b1, cfg.B, &l1, &h1);
             mine = (int)md_lane_stream<K, WRITE>(R, cfg, lst, ls, le, b0, leq, m_dup, (uint64_t)b * lm.G + cbase, l1, h1, (int32_t)i, p, wbase + total, out_l, out_r, out_p);
           }
           total += mine;
+          if (memo_on) { const int tot = __reduce_add_sync(FULL, mine); if (lane == jj) round_cnt = tot; }
+        }
+        if (memo_on && s0 + lane < n_rs) {
+          if (memo) cnt_ts[team * n_rs + s0 + lane] = round_cnt; else cnt_ts[team * n_rs + s0 + lane] += round_cnt;
         }
       }
     }
-    if (!WRITE && slot < L.n) cnt[slot] = total;
+    if (!WRITE && !memo_on && slot < L.n) cnt[slot] = total;
+  }
+}
+
+// write pass of the team form from the count pass's memo.  The order of the output rows is free, so the rows of a (team, right
+// sample) entry go out as ONE contiguous run at the entry's offset (exclusive scan of cnt_ts): lanes in order, a lane's rows in
+// index order.  Entries that were not memoised (a sample with more candidates than a slot, a team across a chromosome boundary)
+// are redone lane by lane on the index — the same exact selection, so the same rows as were counted.
+template <typename K>
+__global__ void __launch_bounds__(256, 3) k_join_md_team_write(LeftSide L, RightIndex<K> R, LinMap lm, JoinCfg cfg, const int32_t* __restrict__ pair_t, int n_ls, int n_rs,
+                                                            const int32_t* __restrict__ mult, const int64_t* __restrict__ off_ts, const uint32_t* __restrict__ memo_lo, const uint16_t* __restrict__ memo_em,
+                                                            int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_teams = (L.n + 31) >> 5;
+  for (int64_t team = warp; team < n_teams; team += nwarps) {
+    const int64_t slot = team * 32 + lane;
+    const bool valid = slot < L.n;
+    const int64_t i = valid ? (L.perm ? (int64_t)L.perm[slot] : slot) : 0;
+    const int la = (valid && L.sample) ? L.sample[i] : 0;
+    for (int s0 = 0; s0 < n_rs; s0 += 32) {
+      const int64_t e0 = team * n_rs + s0;
+      const bool has = s0 + lane < n_rs;
+      const uint32_t lo_j = has ? memo_lo[e0 + lane] : MDT_NONE;
+      const int64_t base_j = has ? off_ts[e0 + lane] : 0;
+      const int ns = n_rs - s0 < 32 ? n_rs - s0 : 32;
+      // memoised entries, four at a time: nothing in an entry depends on another, so the four mask loads, then the four pair and
+      // first-row loads are issued back to back and their latencies overlap (a warp meets ~200 dependent global loads per team otherwise)
+      for (int j0 = 0; j0 < ns; j0 += 4) {
+        uint32_t lo4[4], em4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          lo4[u] = __shfl_sync(FULL, lo_j, (j0 + u) & 31);
+          em4[u] = (j0 + u < ns && lo4[u] < MDT_REDO) ? (uint32_t)memo_em[((e0 + j0 + u) << 5) + lane] : 0u;
+        }
+        int64_t o4[4];
+        int p4[4], r4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = __popc(em4[u]);
+          int incl = c;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += y; }
+          o4[u] = __shfl_sync(FULL, base_j, (j0 + u) & 31) + incl - c;
+          p4[u] = 0; r4[u] = 0;
+          if (em4[u]) { p4[u] = pair_t[(int64_t)(s0 + j0 + u) * n_ls + la]; r4[u] = R.packed[lo4[u] + (__ffs((int)em4[u]) - 1)].z; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t em = em4[u];
+          if (em) {
+            int64_t o = o4[u];
+            out_l[o] = (int32_t)i; out_r[o] = r4[u]; out_p[o] = p4[u];
+            for (em &= em - 1; em; em &= em - 1) { ++o; out_l[o] = (int32_t)i; out_r[o] = R.packed[lo4[u] + (__ffs((int)em) - 1)].z; out_p[o] = p4[u]; }
+          }
+        }
+      }
+      // entries that were not memoised: count, place, write — lane by lane on the index
+      unsigned redo = __ballot_sync(FULL, lo_j == MDT_REDO);
+      for (; redo; redo &= redo - 1) {
+        const int jj = __ffs((int)redo) - 1, b = s0 + jj;
+        const int64_t base = __shfl_sync(FULL, base_j, jj);
+        int p = -1, c = -1, lst = 0;
+        int64_t ls = 0, le = 0, b0 = 1, b1 = 0, l1 = 0, h1 = 0, leq = 0, m_dup = 1;
+        if (valid) {
+          p = pair_t[(int64_t)b * n_ls + la];
+          c = L.chrom[i];
+          ls = ld_coord(L.start, L.bits, i); le = ld_coord(L.stop, L.bits, i);
+          lst = L.strand ? (int)L.strand[i] : 0;
+          left_bins(cfg, lst, ls, le, &b0, &b1);
+          leq = cfg.has_eq ? L.eq[i] : 0;
+          m_dup = mult ? mult[i] : 1;
+        }
+        const bool go = valid && p >= 0 && c >= 0 && c < lm.n_chrom && b0 <= b1;
+        int mine = 0;
+        uint64_t gbase = 0;
+        if (go) {
+          gbase = (uint64_t)b * lm.G + lm.coff[c];
+          window<K>(R, lm, (uint64_t)b * lm.G, c, b0, b1, cfg.B, &l1, &h1);
+          mine = (int)md_lane_stream<K, false>(R, cfg, lst, ls, le, b0, leq, m_dup, gbase, l1, h1, (int32_t)i, p, 0, out_l, out_r, out_p);
+        }
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += y; }
+        if (mine) md_lane_stream<K, true>(R, cfg, lst, ls, le, b0, leq, m_dup, gbase, l1, h1, (int32_t)i, p, base + incl - mine, out_l, out_r, out_p);
+      }
+    }
   }
 }
 
@@ -820,23 +933,48 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
     if (memo_stride > 0 && nl * memo_stride <= (int64_t)700000000) { memo_lo.alloc(ctx, nl * memo_stride); memo_ok.alloc(ctx, nl * memo_stride); }
   }
   const int team_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nl, 256), (int64_t)ctx->num_sms * 8));
+  // the team form's memo for its write pass: 80 bytes per (team, right sample) with the offsets, when it fits (option "join.md_memo" = "0": never)
+  const size_t team_smem = 8 * (32 * MDT_SLOT + MDT_CAP) * sizeof(int4);
+  if (md_team) {
+    CUDA_TRY(cudaFuncSetAttribute(k_join_md_team<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_join_md_team<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_smem));
+  }
+  DevBuf<uint32_t> team_lo;
+  DevBuf<uint16_t> team_em;
+  DevBuf<int32_t> team_cnt;
+  {
+    const int64_t n_e = ceil_div64(nl, 32) * n_rs;
+    const char* o = ctx_opt(ctx, "join.md_memo");
+    if (md_team && n_e > 0 && n_e * 80 <= ((int64_t)1 << 30) && !(o && !strcmp(o, "0"))) { team_lo.alloc(ctx, n_e); team_em.alloc(ctx, n_e * 32); team_cnt.alloc(ctx, n_e); }
+  }
 
   DevBuf<int64_t> cnt(ctx, nl + 1);
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nl, 8), (int64_t)ctx->num_sms * 16));
   if (nl) {
-    if (md_team) LAUNCH(ctx, (k_join_md_team<K, false>), team_blocks, 256, 0, L, R, lm, cfg, narrow_cfg(cfg), d_pair_t.p, n_ls, n_rs, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr);
+    if (md_team) LAUNCH(ctx, (k_join_md_team<K, false>), team_blocks, 256, team_smem, L, R, lm, cfg, narrow_cfg(cfg), d_pair_t.p, n_ls, n_rs, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
+                        team_lo.p, team_em.p, team_cnt.p);
     else if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, false>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
                            memo_lo.p, memo_ok.p, memo_stride);
     else LAUNCH(ctx, (k_join_scan<K, false>), blocks, 256, 0, L, R, lm, cfg, d_pair.p, n_rs, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr);
   }
-  device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, cnt.p, cnt.p, nl, cnt.p + nl);
+  // offsets: per left region (slot), or per (team, right sample) entry when the team kernel memoised its count pass
+  DevBuf<int64_t> team_off;
+  const int64_t n_ts = team_lo.p ? ceil_div64(nl, 32) * n_rs : 0;
+  const int64_t* p_total = cnt.p + nl;
+  if (n_ts) {
+    team_off.alloc(ctx, n_ts + 1);
+    device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, team_cnt.p, team_off.p, n_ts, team_off.p + n_ts);
+    p_total = team_off.p + n_ts;
+  } else device_scan<int64_t, int64_t, OpSum<int64_t>, false>(ctx, cnt.p, cnt.p, nl, cnt.p + nl);
   int64_t n_out = 0;
-  CUDA_TRY(cudaMemcpyAsync(&n_out, cnt.p + nl, sizeof n_out, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&n_out, p_total, sizeof n_out, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(GMQL_SYNC(ctx));
   GMQL_REQUIRE(n_out < (int64_t)0x7fffffff * 8, GMQL_ERR_UNSUPPORTED, "join output too large for this version");
   DevBuf<int32_t> ol(ctx, n_out), orr(ctx, n_out), op(ctx, n_out);
   if (nl && n_out) {
-    if (md_team) LAUNCH(ctx, (k_join_md_team<K, true>), team_blocks, 256, 0, L, R, lm, cfg, narrow_cfg(cfg), d_pair_t.p, n_ls, n_rs, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p);
+    if (md_team && team_lo.p) LAUNCH(ctx, (k_join_md_team_write<K>), team_blocks, 256, 0, L, R, lm, cfg, d_pair_t.p, n_ls, n_rs, mult.p, team_off.p, team_lo.p, team_em.p, ol.p, orr.p, op.p);
+    else if (md_team) LAUNCH(ctx, (k_join_md_team<K, true>), team_blocks, 256, team_smem, L, R, lm, cfg, narrow_cfg(cfg), d_pair_t.p, n_ls, n_rs, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p,
+                             (uint32_t*)nullptr, (uint16_t*)nullptr, (int32_t*)nullptr);
     else if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, true>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p,
                            memo_lo.p, memo_ok.p, memo_stride);
     else LAUNCH(ctx, (k_join_scan<K, true>), blocks, 256, 0, L, R, lm, cfg, d_pair.p, n_rs, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p);

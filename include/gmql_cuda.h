@@ -153,6 +153,7 @@ int  gmql_ctx_sync(gmql_ctx* ctx);                      /* cudaStreamSynchronize
  *   "cover.waves", "cover.stitch" ("split"), "cover.speculate" ("0"), "map.index" ("split"), "map.grouped" ("0" | "1"), "map.lean" ("0")
  *   "join.md"         "team" | "lane"    MD(k) kernel: a warp per 32 neighbouring left regions walking the right samples, or a lane per
  *                                        (left region, right sample) group (default: team when the pair table is dense)
+ *   "join.md_memo"    "0"                the team kernel's write pass repeats the selection instead of reading the count pass's memo
  *   "defer_check"     "1"                gmql_map (one reference sample) returns without waiting for the device: an invalid
  *                                        input (bad index, broken layout promise) is then reported by the next call on this
  *                                        context that finds the stream idle — gmql_result_column_copy, gmql_ctx_sync or the next

@@ -11,14 +11,17 @@ from tests.randgen import rand_regions, canon
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["auto", "team", "lane"])
+@pytest.fixture(scope="module", params=["auto", "team", "team-nomemo", "lane"])
 def ex(request):
     """Every test runs three times: the library's own choice of the MD kernel, the team form (a warp owns 32 consecutive left
-    regions and walks the right samples, candidates staged in shared memory) and the lane form (one lane per group)."""
+    regions and walks the right samples, candidates staged in shared memory; its write pass from the count pass's memo or
+    repeating the selection) and the lane form (one lane per group)."""
     from gmql_b200 import GMQLCudaExecutor
     e = GMQLCudaExecutor()
     if request.param != "auto":
-        e.set_option("join.md", request.param)
+        e.set_option("join.md", request.param.split("-")[0])
+    if request.param.endswith("nomemo"):
+        e.set_option("join.md_memo", "0")
     yield e
     e.close()
 
