@@ -357,23 +357,25 @@ __global__ void __launch_bounds__(256) k_join_md(LeftSide L, RightIndex<K> R, Li
 // beyond that every lane streams its own window as k_join_md does.
 constexpr int MDT_SLOT = 16;  // candidates per (team, right sample) slot (a 16-bit memo mask per lane)
 constexpr int MDT_CAP = 32;   // candidates of one (team, right sample) staged one sample at a time (a 32-bit survivor mask)
+constexpr int MDT_WB = 8;     // entries the write pass keeps in flight
 constexpr uint32_t MDT_NONE = 0xffffffffu, MDT_REDO = 0xfffffffeu;   // memo: no candidate near the team / not memoised
 
-struct JoinCfg32 { int f_has_max, f_has_min, f_stream, f_max, f_min, s_has_max, s_has_min, s_stream, s_max, s_min, builder, has_eq; };
-// distances of 32-bit coordinates lie in [-(2^31-1), 2^31-1]: thresholds beyond that range always or never hold
+// the distance thresholds of both rounds as closed intervals lo <= d <= hi on 32-bit distances (d lies in [-(2^31-1), 2^31-1]);
+// never_f / never_s: a round no distance can pass
+struct JoinCfg32 { int f_lo, f_hi, s_lo, s_hi, never_f, never_s, f_stream, s_stream, builder, has_eq; };
 static JoinCfg32 narrow_cfg(const JoinCfg& c) {
-  auto fit = [](int has, int64_t v, bool is_max, int* has32, int* v32) {
-    *has32 = has; *v32 = 0;
-    if (!has) return;
-    if (is_max) {                                          // max > d
-      if (v > 0x7fffffffLL) *has32 = 0; else *v32 = v < -0x80000000LL ? (int)-0x80000000LL : (int)v;
-    } else {                                               // min < d
-      if (v < -0x80000000LL) *has32 = 0; else *v32 = v > 0x7fffffffLL ? 0x7fffffff : (int)v;
+  auto fit = [](int has_max, int64_t mx, int has_min, int64_t mn, int* lo, int* hi, int* never) {
+    *lo = (int)-0x7fffffff; *hi = 0x7fffffff; *never = 0;
+    if (has_max) {                                         // max > d  <=>  d <= max - 1
+      if (mx <= -0x7fffffffLL) *never = 1; else if (mx <= 0x7fffffffLL) *hi = (int)(mx - 1);
+    }
+    if (has_min) {                                         // min < d  <=>  d >= min + 1
+      if (mn >= 0x7fffffffLL) *never = 1; else if (mn >= -0x7fffffffLL) *lo = (int)(mn + 1);
     }
   };
   JoinCfg32 r;
-  fit(c.f_has_max, c.f_max, true, &r.f_has_max, &r.f_max); fit(c.f_has_min, c.f_min, false, &r.f_has_min, &r.f_min);
-  fit(c.s_has_max, c.s_max, true, &r.s_has_max, &r.s_max); fit(c.s_has_min, c.s_min, false, &r.s_has_min, &r.s_min);
+  fit(c.f_has_max, c.f_max, c.f_has_min, c.f_min, &r.f_lo, &r.f_hi, &r.never_f);
+  fit(c.s_has_max, c.s_max, c.s_has_min, c.s_min, &r.s_lo, &r.s_hi, &r.never_s);
   r.f_stream = c.f_stream; r.s_stream = c.s_stream; r.builder = c.builder; r.has_eq = c.has_eq;
   return r;
 }
@@ -406,11 +408,9 @@ __device__ __forceinline__ uint32_t md_select32(const JoinCfg32& c, const int4* 
     const int4 en = cand[t * stride];
     const int d = join_distance32(q.ls, q.le, en.x, en.y);
     // window: r.start / B <= binEnd, r.stop / B >= binStart (:120-122); strands (:123); distance and stream (:250-279)
-    bool ok = (en.x <= q.wlast) & (en.y >= q.wbeg) & strand_ok(q.lst, en.w) & (!c.f_has_max | (c.f_max > d)) & (!c.f_has_min | (c.f_min < d)) &
-              (en.y <= q.f_re_max) & (en.x >= q.f_rs_min);
+    bool ok = (en.x <= q.wlast) & (en.y >= q.wbeg) & strand_ok(q.lst, en.w) & (d <= c.f_hi) & (d >= c.f_lo) & (en.y <= q.f_re_max) & (en.x >= q.f_rs_min);
     if (c.has_eq) { if (ok) ok = r_eq[(uint32_t)en.z] == leq; }   // :102-114
-    const bool s2 = ok & (!c.s_has_max | (c.s_max > d)) & (!c.s_has_min | (c.s_min < d)) & (en.y <= q.s_re_max) & (en.x >= q.s_rs_min) &
-                    (!inter | ((q.ls < en.y) & (en.x < q.le)));
+    const bool s2 = ok & (d <= c.s_hi) & (d >= c.s_lo) & (en.y <= q.s_re_max) & (en.x >= q.s_rs_min) & (!inter | ((q.ls < en.y) & (en.x < q.le)));
     fr |= (uint32_t)ok << t; len += ok;
     const bool lt = ok & (d < dmin);
     dmin = lt ? d : dmin; em = lt ? 0u : em;
@@ -441,8 +441,7 @@ __device__ __forceinline__ uint32_t md_select32(const JoinCfg32& c, const int4* 
       const int t = __ffs((int)m) - 1;
       const int4 en = cand[t * stride];
       const int d = join_distance32(q.ls, q.le, en.x, en.y);
-      const bool s2 = (d <= prev) & (!c.s_has_max | (c.s_max > d)) & (!c.s_has_min | (c.s_min < d)) & (en.y <= q.s_re_max) & (en.x >= q.s_rs_min) &
-                      (!inter | ((q.ls < en.y) & (en.x < q.le)));
+      const bool s2 = (d <= prev) & (d <= c.s_hi) & (d >= c.s_lo) & (en.y <= q.s_re_max) & (en.x >= q.s_rs_min) & (!inter | ((q.ls < en.y) & (en.x < q.le)));
       em |= (uint32_t)s2 << t;
     }
   }
@@ -488,11 +487,39 @@ __device__ int64_t md_lane_stream(const RightIndex<K>& R, const JoinCfg& cfg, in
   return mine;
 }
 
+// teams = runs of up to 32 consecutive left regions of the genome order that lie on ONE chromosome (a team across a chromosome
+// boundary would visit every right sample once per chromosome and could not be memoised): per chromosome the first sorted left
+// slot and the first team, then per team its first slot and size.  At most ceil(n / 32) + n_chrom teams; the rest are empty.
+template <typename K>
+__global__ void k_team_chroms(const K* __restrict__ lstart, int64_t n, LinMap lm, int64_t* __restrict__ lb, int64_t* __restrict__ toff) {
+  for (int c = threadIdx.x; c <= lm.n_chrom; c += blockDim.x)
+    lb[c] = c == lm.n_chrom ? n : (lstart ? lower_bound_dev<K>(lstart, n, (K)lm.coff[c]) : 0);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t t = 0;
+    for (int c = 0; c < lm.n_chrom; ++c) { toff[c] = t; t += (lb[c + 1] - lb[c] + 31) >> 5; }
+    toff[lm.n_chrom] = t;
+  }
+}
+__global__ void k_team_table(const int64_t* __restrict__ lb, const int64_t* __restrict__ toff, int n_chrom, int64_t n_teams, int2* __restrict__ teams) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_teams; t += (int64_t)gridDim.x * blockDim.x) {
+    int2 r = make_int2(0, 0);
+    if (t < toff[n_chrom]) {
+      int lo = 0, hi = n_chrom;                            // the last chromosome whose first team is <= t
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (toff[mid] <= t) lo = mid; else hi = mid; }
+      const int64_t first = lb[lo] + ((t - toff[lo]) << 5), left = lb[lo + 1] - first;
+      r = make_int2((int)first, (int)(left < 32 ? left : 32));
+    }
+    teams[t] = r;
+  }
+}
+
 template <typename K, bool WRITE>
 __global__ void __launch_bounds__(256, 2) k_join_md_team(LeftSide L, RightIndex<K> R, LinMap lm, JoinCfg cfg, JoinCfg32 c32, const int32_t* __restrict__ pair_t /* [right sample][left sample] */, int n_ls, int n_rs,
                                                          const int32_t* __restrict__ mult, int64_t* __restrict__ cnt, const int64_t* __restrict__ off,
                                                          int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p,
-                                                         uint32_t* __restrict__ memo_lo, uint16_t* __restrict__ memo_em, int32_t* __restrict__ cnt_ts) {
+                                                         uint32_t* __restrict__ memo_lo, uint16_t* __restrict__ memo_em, int32_t* __restrict__ cnt_ts,
+                                                         const int2* __restrict__ teams, int64_t n_teams) {
   // memo (count pass, optional): per (team, right sample) the first index of the slot's candidates (or MDT_NONE / MDT_REDO), the
   // number of rows of the whole team with that sample (cnt_ts, instead of the per-region cnt) and per lane the 16-bit mask of the
   // candidates that become rows — k_join_md_team_write then needs neither searches nor selection and writes contiguous runs
@@ -502,10 +529,11 @@ __global__ void __launch_bounds__(256, 2) k_join_md_team(LeftSide L, RightIndex<
   int4* slots = s_team + (threadIdx.x >> 5) * (32 * MDT_SLOT + MDT_CAP);
   int4* big = slots + 32 * MDT_SLOT;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_teams = (L.n + 31) >> 5;
   for (int64_t team = warp; team < n_teams; team += nwarps) {
-    const int64_t slot = team * 32 + lane;
-    bool valid = slot < L.n;
+    const int2 tm = teams[team];
+    const int64_t slot = (int64_t)tm.x + lane;
+    bool valid = lane < tm.y;
+    const bool mine_slot = valid;
     int64_t i = 0, b0 = 1, b1 = 0, m_dup = 1, leq = 0;
     int c = -1, lst = 0, la = 0, ls = 0, le = 0;
     if (valid) {
@@ -527,11 +555,20 @@ __global__ void __launch_bounds__(256, 2) k_join_md_team(LeftSide L, RightIndex<
     q.ls = ls; q.le = le; q.lst = lst; q.wbeg = wbeg; q.wlast = wlast;
     stream_bounds(c32.f_stream, lst, ls, le, &q.f_re_max, &q.f_rs_min);
     stream_bounds(c32.s_stream, lst, ls, le, &q.s_re_max, &q.s_rs_min);
-    const int64_t wbase = (WRITE && slot < L.n) ? off[slot] : 0;
+    if (c32.never_f) q.wlast = (int)0x80000000;            // no candidate start lies at or below it
+    if (c32.never_s) q.s_re_max = (int)0x80000000;         // nor a stop
+    // kept in registers: recomputing these selects for every candidate costs more than the registers
+    asm volatile("" : "+r"(q.wbeg), "+r"(q.wlast), "+r"(q.f_re_max), "+r"(q.f_rs_min), "+r"(q.s_re_max), "+r"(q.s_rs_min));
+    const int64_t wbase = (WRITE && mine_slot) ? off[slot] : 0;
     int64_t total = 0;
     unsigned todo = __ballot_sync(FULL, valid);
     // a team that spans a chromosome boundary visits the samples once per chromosome: nothing to memoise, the write pass redoes it
     const bool memo_on = !WRITE && memo_lo != nullptr;
+    if (todo == 0u) {                                      // an empty team, or no left region with a window: no rows
+      if (memo_on) for (int b = lane; b < n_rs; b += 32) { memo_lo[team * n_rs + b] = MDT_NONE; cnt_ts[team * n_rs + b] = 0; }
+      if (!WRITE && !memo_on && mine_slot) cnt[slot] = 0;
+      continue;
+    }
     const int c_first = __shfl_sync(FULL, c, todo ? __ffs(todo) - 1 : 0);   // (not inside a short-circuit: every lane takes part)
     const unsigned same = __ballot_sync(FULL, valid && c == c_first);
     const bool memo = memo_on && todo == same;
@@ -596,7 +633,7 @@ __global__ void __launch_bounds__(256, 2) k_join_md_team(LeftSide L, RightIndex<
         }
       }
     }
-    if (!WRITE && !memo_on && slot < L.n) cnt[slot] = total;
+    if (!WRITE && !memo_on && mine_slot) cnt[slot] = total;
   }
 }
 
@@ -605,16 +642,20 @@ __global__ void __launch_bounds__(256, 2) k_join_md_team(LeftSide L, RightIndex<
 // index order.  Entries that were not memoised (a sample with more candidates than a slot, a team across a chromosome boundary)
 // are redone lane by lane on the index — the same exact selection, so the same rows as were counted.
 template <typename K>
-__global__ void __launch_bounds__(256, 3) k_join_md_team_write(LeftSide L, RightIndex<K> R, LinMap lm, JoinCfg cfg, const int32_t* __restrict__ pair_t, int n_ls, int n_rs,
+__global__ void __launch_bounds__(256, 2) k_join_md_team_write(LeftSide L, RightIndex<K> R, LinMap lm, JoinCfg cfg, const int32_t* __restrict__ pair_t, int n_ls, int n_rs,
                                                             const int32_t* __restrict__ mult, const int64_t* __restrict__ off_ts, const uint32_t* __restrict__ memo_lo, const uint16_t* __restrict__ memo_em,
-                                                            int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p) {
+                                                            int32_t* __restrict__ out_l, int32_t* __restrict__ out_r, int32_t* __restrict__ out_p,
+                                                            const int2* __restrict__ teams, int64_t n_teams) {
+  __shared__ __align__(16) uint16_t s_em_all[8][32 * 32];  // per warp: the masks of a round of 32 entries
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  uint16_t* s_em = s_em_all[threadIdx.x >> 5];
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_teams = (L.n + 31) >> 5;
   for (int64_t team = warp; team < n_teams; team += nwarps) {
-    const int64_t slot = team * 32 + lane;
-    const bool valid = slot < L.n;
+    const int2 tm = teams[team];
+    if (tm.y == 0) continue;
+    const int64_t slot = (int64_t)tm.x + lane;
+    const bool valid = lane < tm.y;
     const int64_t i = valid ? (L.perm ? (int64_t)L.perm[slot] : slot) : 0;
     const int la = (valid && L.sample) ? L.sample[i] : 0;
     for (int s0 = 0; s0 < n_rs; s0 += 32) {
@@ -623,34 +664,45 @@ __global__ void __launch_bounds__(256, 3) k_join_md_team_write(LeftSide L, Right
       const uint32_t lo_j = has ? memo_lo[e0 + lane] : MDT_NONE;
       const int64_t base_j = has ? off_ts[e0 + lane] : 0;
       const int ns = n_rs - s0 < 32 ? n_rs - s0 : 32;
-      // memoised entries, four at a time: nothing in an entry depends on another, so the four mask loads, then the four pair and
-      // first-row loads are issued back to back and their latencies overlap (a warp meets ~200 dependent global loads per team otherwise)
-      for (int j0 = 0; j0 < ns; j0 += 4) {
-        uint32_t lo4[4], em4[4];
+      // memoised entries.  The round's masks are one contiguous block (64 bytes per entry): four independent 16-byte loads per lane
+      // bring them into shared memory; then eight entries at a time — nothing in an entry depends on another, so their pair and
+      // first-row loads are issued back to back and the latencies overlap (a warp meets ~400 dependent global loads per team otherwise)
+      {
+        const uint4* src = (const uint4*)(memo_em + (e0 << 5));
+        uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          lo4[u] = __shfl_sync(FULL, lo_j, (j0 + u) & 31);
-          em4[u] = (j0 + u < ns && lo4[u] < MDT_REDO) ? (uint32_t)memo_em[((e0 + j0 + u) << 5) + lane] : 0u;
+        for (int k = 0; k < 4; ++k) if (k * 32 + lane < ns * 4) v[k] = src[k * 32 + lane];
+        __syncwarp();                                      // the previous round's readers are done
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (k * 32 + lane < ns * 4) ((uint4*)s_em)[k * 32 + lane] = v[k];
+        __syncwarp();
+      }
+      for (int j0 = 0; j0 < ns; j0 += MDT_WB) {
+        uint32_t lo8[MDT_WB], em8[MDT_WB];
+#pragma unroll
+        for (int u = 0; u < MDT_WB; ++u) {
+          lo8[u] = __shfl_sync(FULL, lo_j, (j0 + u) & 31);
+          em8[u] = (j0 + u < ns && lo8[u] < MDT_REDO) ? (uint32_t)s_em[((j0 + u) << 5) + lane] : 0u;   // (never written for other entries)
         }
-        int64_t o4[4];
-        int p4[4], r4[4];
+        int64_t o8[MDT_WB];
+        int p8[MDT_WB], r8[MDT_WB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = __popc(em4[u]);
+        for (int u = 0; u < MDT_WB; ++u) {
+          const int c = __popc(em8[u]);
           int incl = c;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += y; }
-          o4[u] = __shfl_sync(FULL, base_j, (j0 + u) & 31) + incl - c;
-          p4[u] = 0; r4[u] = 0;
-          if (em4[u]) { p4[u] = pair_t[(int64_t)(s0 + j0 + u) * n_ls + la]; r4[u] = R.packed[lo4[u] + (__ffs((int)em4[u]) - 1)].z; }
+          o8[u] = __shfl_sync(FULL, base_j, (j0 + u) & 31) + incl - c;
+          p8[u] = 0; r8[u] = 0;
+          if (em8[u]) { p8[u] = pair_t[(int64_t)(s0 + j0 + u) * n_ls + la]; r8[u] = R.packed[lo8[u] + (__ffs((int)em8[u]) - 1)].z; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint32_t em = em4[u];
+        for (int u = 0; u < MDT_WB; ++u) {
+          uint32_t em = em8[u];
           if (em) {
-            int64_t o = o4[u];
-            out_l[o] = (int32_t)i; out_r[o] = r4[u]; out_p[o] = p4[u];
-            for (em &= em - 1; em; em &= em - 1) { ++o; out_l[o] = (int32_t)i; out_r[o] = R.packed[lo4[u] + (__ffs((int)em) - 1)].z; out_p[o] = p4[u]; }
+            int64_t o = o8[u];
+            out_l[o] = (int32_t)i; out_r[o] = r8[u]; out_p[o] = p8[u];
+            for (em &= em - 1; em; em &= em - 1) { ++o; out_l[o] = (int32_t)i; out_r[o] = R.packed[lo8[u] + (__ffs((int)em) - 1)].z; out_p[o] = p8[u]; }
           }
         }
       }
@@ -932,7 +984,15 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
     for (int a = 0; a < n_ls; ++a) memo_stride = std::max<int64_t>(memo_stride, h_aoff[a + 1] - h_aoff[a]);
     if (memo_stride > 0 && nl * memo_stride <= (int64_t)700000000) { memo_lo.alloc(ctx, nl * memo_stride); memo_ok.alloc(ctx, nl * memo_stride); }
   }
-  const int team_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nl, 256), (int64_t)ctx->num_sms * 8));
+  const int64_t n_teams = md_team ? ceil_div64(nl, 32) + lm.n_chrom : 0;
+  const int team_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n_teams, 8), (int64_t)ctx->num_sms * 8));
+  DevBuf<int2> teams;
+  if (md_team && nl) {
+    DevBuf<int64_t> lb(ctx, lm.n_chrom + 1), toff(ctx, lm.n_chrom + 1);
+    teams.alloc(ctx, n_teams);
+    LAUNCH(ctx, (k_team_chroms<K>), 1, 256, 0, (const K*)(L.perm ? lix.start : nullptr), nl, lm, lb.p, toff.p);
+    LAUNCH(ctx, k_team_table, grid_for(ctx, n_teams, 256), 256, 0, lb.p, toff.p, lm.n_chrom, n_teams, teams.p);
+  }
   // the team form's memo for its write pass: 80 bytes per (team, right sample) with the offsets, when it fits (option "join.md_memo" = "0": never)
   const size_t team_smem = 8 * (32 * MDT_SLOT + MDT_CAP) * sizeof(int4);
   if (md_team) {
@@ -943,7 +1003,7 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   DevBuf<uint16_t> team_em;
   DevBuf<int32_t> team_cnt;
   {
-    const int64_t n_e = ceil_div64(nl, 32) * n_rs;
+    const int64_t n_e = n_teams * n_rs;
     const char* o = ctx_opt(ctx, "join.md_memo");
     if (md_team && n_e > 0 && n_e * 80 <= ((int64_t)1 << 30) && !(o && !strcmp(o, "0"))) { team_lo.alloc(ctx, n_e); team_em.alloc(ctx, n_e * 32); team_cnt.alloc(ctx, n_e); }
   }
@@ -952,14 +1012,14 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nl, 8), (int64_t)ctx->num_sms * 16));
   if (nl) {
     if (md_team) LAUNCH(ctx, (k_join_md_team<K, false>), team_blocks, 256, team_smem, L, R, lm, cfg, narrow_cfg(cfg), d_pair_t.p, n_ls, n_rs, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
-                        team_lo.p, team_em.p, team_cnt.p);
+                        team_lo.p, team_em.p, team_cnt.p, teams.p, n_teams);
     else if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, false>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr,
                            memo_lo.p, memo_ok.p, memo_stride);
     else LAUNCH(ctx, (k_join_scan<K, false>), blocks, 256, 0, L, R, lm, cfg, d_pair.p, n_rs, cnt.p, (const int64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr);
   }
   // offsets: per left region (slot), or per (team, right sample) entry when the team kernel memoised its count pass
   DevBuf<int64_t> team_off;
-  const int64_t n_ts = team_lo.p ? ceil_div64(nl, 32) * n_rs : 0;
+  const int64_t n_ts = team_lo.p ? n_teams * n_rs : 0;
   const int64_t* p_total = cnt.p + nl;
   if (n_ts) {
     team_off.alloc(ctx, n_ts + 1);
@@ -972,9 +1032,9 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   GMQL_REQUIRE(n_out < (int64_t)0x7fffffff * 8, GMQL_ERR_UNSUPPORTED, "join output too large for this version");
   DevBuf<int32_t> ol(ctx, n_out), orr(ctx, n_out), op(ctx, n_out);
   if (nl && n_out) {
-    if (md_team && team_lo.p) LAUNCH(ctx, (k_join_md_team_write<K>), team_blocks, 256, 0, L, R, lm, cfg, d_pair_t.p, n_ls, n_rs, mult.p, team_off.p, team_lo.p, team_em.p, ol.p, orr.p, op.p);
+    if (md_team && team_lo.p) LAUNCH(ctx, (k_join_md_team_write<K>), team_blocks, 256, 0, L, R, lm, cfg, d_pair_t.p, n_ls, n_rs, mult.p, team_off.p, team_lo.p, team_em.p, ol.p, orr.p, op.p, teams.p, n_teams);
     else if (md_team) LAUNCH(ctx, (k_join_md_team<K, true>), team_blocks, 256, team_smem, L, R, lm, cfg, narrow_cfg(cfg), d_pair_t.p, n_ls, n_rs, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p,
-                             (uint32_t*)nullptr, (uint16_t*)nullptr, (int32_t*)nullptr);
+                             (uint32_t*)nullptr, (uint16_t*)nullptr, (int32_t*)nullptr, teams.p, n_teams);
     else if (cfg.has_md) LAUNCH(ctx, (k_join_md<K, true>), blocks, 256, 0, L, R, lm, cfg, d_aoff.p, d_ars.p, d_apair.p, mult.p, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p,
                            memo_lo.p, memo_ok.p, memo_stride);
     else LAUNCH(ctx, (k_join_scan<K, true>), blocks, 256, 0, L, R, lm, cfg, d_pair.p, n_rs, (int64_t*)nullptr, cnt.p, ol.p, orr.p, op.p);
