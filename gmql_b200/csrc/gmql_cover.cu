@@ -570,9 +570,14 @@ __global__ void k_summit_bin_list(const int32_t* __restrict__ head, const int64_
     if (head[m]) bin_first[head_excl[m]] = (uint32_t)m;
 }
 
-// one thread per bin: summitHelper (:269-316).  A piece is stored at the index of the point that emits it.
+// one thread per bin: the reference's per-bin state machine over the bin's coalesced points — summitHelper (:269-316),
+// coverHelper (:172-218, also FLAT) or histogramHelper (:229-258), literally.  A piece is stored at the index of the point that
+// emits it (its stop is that point's offset, clipped at the bin size by k_summit_pieces).  SUMMIT always runs here (every bin
+// restarts at depth 0); COVER / FLAT / HISTOGRAM only when minAcc < 1 makes depth 0 "in range": the reference's result then
+// depends on which bins hold events at all (:57-79 with the bins of :98-118), which only the bin-wise machine reproduces.
+enum { BINS_SUMMIT = 0, BINS_COVER = 1, BINS_HISTOGRAM = 2 };
 __global__ void k_summit_bins(const uint64_t* __restrict__ pkey, const int32_t* __restrict__ pdelta, int64_t np, const uint32_t* __restrict__ bin_first, int64_t n_bins,
-                              int64_t B, uint64_t G2, CoverCfg cfg, int32_t* __restrict__ emit, int64_t* __restrict__ pstart_off, int32_t* __restrict__ pval) {
+                              int64_t B, uint64_t G2, CoverCfg cfg, int kind, int32_t* __restrict__ emit, int64_t* __restrict__ pstart_off, int32_t* __restrict__ pval) {
   const uint64_t W = (uint64_t)(B + 1);
   for (int64_t bi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bi < n_bins; bi += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = bin_first[bi];
@@ -583,18 +588,45 @@ __global__ void k_summit_bins(const uint64_t* __restrict__ pkey, const int32_t* 
     int mn = cfg.mn[g], mx = cfg.mx[g];
     int64_t start = 0;
     int count = 0;
-    bool valid = false, reentered = false, growing = false;
-    for (int64_t q = m; q < m_end; ++q) {
-      int64_t off = (int64_t)(pkey[q] - bin_base);
-      int nc = count + pdelta[q];
-      bool nvalid = nc >= mn && nc <= mx;
-      bool ngrow = nc > count || (growing && nc == count);
-      bool nre = !valid && nvalid;
-      int64_t nstart = (nvalid && nc != count) ? off : start;
-      bool out = ((valid && growing && (!ngrow || !nvalid)) || (reentered && !ngrow)) && count != 0;
-      emit[q] = out ? 1 : 0;
-      if (out) { pstart_off[q] = start; pval[q] = count; }
-      start = nstart; count = nc; valid = nvalid; reentered = nre; growing = ngrow;
+    if (kind == BINS_SUMMIT) {
+      bool valid = false, reentered = false, growing = false;
+      for (int64_t q = m; q < m_end; ++q) {
+        int64_t off = (int64_t)(pkey[q] - bin_base);
+        int nc = count + pdelta[q];
+        bool nvalid = nc >= mn && nc <= mx;
+        bool ngrow = nc > count || (growing && nc == count);
+        bool nre = !valid && nvalid;
+        int64_t nstart = (nvalid && nc != count) ? off : start;
+        bool out = ((valid && growing && (!ngrow || !nvalid)) || (reentered && !ngrow)) && count != 0;
+        emit[q] = out ? 1 : 0;
+        if (out) { pstart_off[q] = start; pval[q] = count; }
+        start = nstart; count = nc; valid = nvalid; reentered = nre; growing = ngrow;
+      }
+    } else if (kind == BINS_COVER) {
+      int count_max = 0;
+      bool recording = false;
+      for (int64_t q = m; q < m_end; ++q) {
+        const int64_t off = (int64_t)(pkey[q] - bin_base);
+        const int nc = count + pdelta[q];
+        const bool in_range = nc >= mn && nc <= mx;
+        const bool nrec = in_range && q + 1 < m_end;       // `si.hasNext` (:180): the bin's last point never records
+        const int ncmax = (!nrec && recording) ? 0 : ((nrec && nc > count_max) ? nc : count_max);
+        const int64_t nstart = (in_range && !recording) ? off : start;
+        const bool out = !nrec && recording;
+        emit[q] = out ? 1 : 0;
+        if (out) { pstart_off[q] = nstart; pval[q] = count_max; }
+        count = nc; start = nstart; count_max = ncmax; recording = nrec;
+      }
+    } else {
+      for (int64_t q = m; q < m_end; ++q) {
+        const int64_t off = (int64_t)(pkey[q] - bin_base);
+        const int nc = count + pdelta[q];
+        const int64_t nstart = (nc >= mn && nc <= mx && nc != count) ? off : start;
+        const bool out = count >= mn && count <= mx && nc != count && count != 0;
+        emit[q] = out ? 1 : 0;
+        if (out) { pstart_off[q] = start; pval[q] = count; }
+        start = nstart; count = nc;
+      }
     }
   }
 }
@@ -622,13 +654,14 @@ __global__ void k_summit_pieces(const uint64_t* __restrict__ pkey, int64_t np, i
 }
 
 // cross-bin merge (GenometricCover.scala:121-152): pieces touching a bin edge chain when prev.stop == cur.start
-__global__ void k_chain_heads(const uint32_t* __restrict__ cls, const int32_t* __restrict__ chrom, const int64_t* __restrict__ s, const int64_t* __restrict__ e, int64_t n, int64_t B, int32_t* __restrict__ head) {
+__global__ void k_chain_heads(const uint32_t* __restrict__ cls, const int32_t* __restrict__ chrom, const int64_t* __restrict__ s, const int64_t* __restrict__ e, const int32_t* __restrict__ v, int eq_vals,
+                              int64_t n, int64_t B, int32_t* __restrict__ head) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     bool merge = false;
     if (k > 0) {
       bool nv = (s[k] % B == 0) || (e[k] % B == 0);
       bool nvp = (s[k - 1] % B == 0) || (e[k - 1] % B == 0);
-      merge = nv && nvp && cls[k] == cls[k - 1] && chrom[k] == chrom[k - 1] && e[k - 1] == s[k];
+      merge = nv && nvp && cls[k] == cls[k - 1] && chrom[k] == chrom[k - 1] && e[k - 1] == s[k] && (!eq_vals || v[k - 1] == v[k]);   // HISTOGRAM: equal depths only (:139)
     }
     head[k] = merge ? 0 : 1;
   }
@@ -1062,7 +1095,7 @@ static void phase1_sweep(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cl
   if (nr) LAUNCH(ctx, (k_lin_to_regions<K>), grid_for(ctx, nr, 256), 256, 0, rs.p, re.p, nr, lm, p1->cls.p, p1->chrom.p, p1->start.p, p1->stop.p);
 }
 
-static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const SpanTable& spans, const CoverCfg& cfg, uint64_t n_classes_total, Phase1Out* p1) {
+static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const SpanTable& spans, const CoverCfg& cfg, uint64_t n_classes_total, Phase1Out* p1, int kind) {
   const int64_t n = in.n;
   const int64_t B = cfg.B;
   int g = grid_for(ctx, n, 256);
@@ -1105,7 +1138,7 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
     DevBuf<uint32_t> bin_first(ctx, n_bins);
     GMQL_REQUIRE(np < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "SUMMIT: too many event points");
     if (np) LAUNCH(ctx, k_summit_bin_list, grid_for(ctx, np, 256), 256, 0, bhead.p, bhead_excl.p, np, bin_first.p);
-    if (n_bins) LAUNCH(ctx, k_summit_bins, grid_for(ctx, n_bins, 128, 1), 128, 0, pkey.p, pdelta.p, np, bin_first.p, n_bins, B, G2, cfg, emit.p, pso.p, pval.p);
+    if (n_bins) LAUNCH(ctx, k_summit_bins, grid_for(ctx, n_bins, 128, 1), 128, 0, pkey.p, pdelta.p, np, bin_first.p, n_bins, B, G2, cfg, kind, emit.p, pso.p, pval.p);
   }
   device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, emit.p, emit_excl.p, np, emit_excl.p + np);
   int64_t npieces = read_back<int64_t>(ctx, emit_excl.p + np);
@@ -1116,7 +1149,7 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
   DevBuf<int32_t> chead(ctx, npieces);
   DevBuf<int64_t> chead_excl(ctx, npieces + 1);
   int qg = grid_for(ctx, npieces, 256);
-  if (npieces) LAUNCH(ctx, k_chain_heads, qg, 256, 0, qcls.p, qchrom.p, qs.p, qe.p, npieces, B, chead.p);
+  if (npieces) LAUNCH(ctx, k_chain_heads, qg, 256, 0, qcls.p, qchrom.p, qs.p, qe.p, qval.p, kind == BINS_HISTOGRAM ? 1 : 0, npieces, B, chead.p);
   device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, chead.p, chead_excl.p, npieces, chead_excl.p + npieces);
   int64_t nr = read_back<int64_t>(ctx, chead_excl.p + npieces);
   p1->n = nr;
@@ -1456,6 +1489,12 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
   cfg.mx = d_mx.p;
   const uint64_t n_classes_total = (uint64_t)n_groups * (uint64_t)cfg.n_classes;
   LinMap lm = spans.map();
+  // bin-wise phase 1 (k_summit_bins): SUMMIT always; the others when minAcc < 1 (or option "cover.path" = "bins", a cross-check)
+  bool binwise = flag == GMQL_SUMMIT;
+  for (int g = 0; g < n_groups; ++g) if (h_mn[g] < 1) binwise = true;
+  if (const char* f = ctx_opt(ctx, "cover.path")) if (!strcmp(f, "bins")) binwise = true;
+  GMQL_REQUIRE(!(binwise && shard), GMQL_ERR_UNSUPPORTED, "gmql_cover_shard: minAcc < 1 needs the bin-wise path, which is not sharded by coordinate range");
+  if (spec && binwise) { spec->declined = true; return; }
 
   // class of every region (only materialised when there is more than one class)
   DevBuf<uint32_t> cls;
@@ -1481,7 +1520,7 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
   ShardBufs sbufs;
   TiledRuns truns;
   FusedOut fo;
-  if (sizeof(K) == 4 && n > 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) && !has_zero && (plan.n_aggs == 0 || !shard) &&
+  if (sizeof(K) == 4 && n > 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) && !binwise && !has_zero && (plan.n_aggs == 0 || !shard) &&
       n_classes_total * lm.G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
     // widest tile whose expected number of events leaves headroom in the kernel's tables
     const double total = (double)(n_classes_total * lm.G);
@@ -1558,8 +1597,8 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
   // interval index over the ORIGINAL coordinates (phase 2 contributors, GMAP4 uses the un-extended inputs)
   IntervalIndex<K> ix;
   const bool payload_len = plan.n_cols == 0 && spans.G < 0xffffffffull;
-  const bool fused_keys = payload_len && !has_zero && flag != GMQL_SUMMIT && n > 0;
-  DevBuf<K> ek_a(ctx, flag != GMQL_SUMMIT ? n : 0);
+  const bool fused_keys = payload_len && !has_zero && !binwise && n > 0;
+  DevBuf<K> ek_a(ctx, !binwise ? n : 0);
   if (fused_keys) {
     alloc_index<K>(ctx, n, &ix);
     LAUNCH(ctx, (k_cover_all_keys<K>), grid_for(ctx, n, 256), 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls.p, n, lm, cfg.B, ix.start_a.p, ix.row_a.p, ek_a.p);
@@ -1570,8 +1609,8 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
 
   if (n == 0) {
     p1.n = 0;
-  } else if (flag == GMQL_SUMMIT) {
-    phase1_summit(ctx, in, cls.p, spans, cfg, n_classes_total, &p1);
+  } else if (binwise) {
+    phase1_summit(ctx, in, cls.p, spans, cfg, n_classes_total, &p1, flag == GMQL_SUMMIT ? BINS_SUMMIT : (flag == GMQL_HISTOGRAM ? BINS_HISTOGRAM : BINS_COVER));
   } else {
     // without zero-length regions the phase-1 start keys are exactly the index's sorted starts: reuse them
     phase1_sweep<K>(ctx, in, cls.p, lm, cfg, flag, n_classes_total, has_zero ? (const K*)nullptr : ix.start, ek_a, fused_keys, &p1);
@@ -1845,8 +1884,9 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
     flag &= ~GMQL_COVER_FORCE_UNIFIED;
     GMQL_REQUIRE(flag >= GMQL_COVER && flag <= GMQL_HISTOGRAM, GMQL_ERR_INVALID, "unknown cover flag");
     GMQL_REQUIRE(bin_size > 0, GMQL_ERR_INVALID, "bin_size must be positive (BinSize.Cover = 2000)");
-    for (int g = 0; g < n_groups; ++g)
-      GMQL_REQUIRE(min_acc[g] >= 1, GMQL_ERR_UNSUPPORTED, "COVER minAcc < 1 makes the reference's result depend on empty bins; not accelerated");
+    bool low_min = false;                                  // minAcc < 1: depth 0 is "in range" between the events of a bin (bin-wise path only)
+    for (int g = 0; g < n_groups; ++g) if (min_acc[g] < 1) low_min = true;
+    if (const char* f = ctx_opt(ctx, "cover.path")) if (!strcmp(f, "bins")) low_min = true;
     if (sample_group)
       for (int s = 0; s < in->n_samples; ++s)
         GMQL_REQUIRE(sample_group[s] >= 0 && sample_group[s] < n_groups, GMQL_ERR_INVALID, "sample_group entry out of range");
@@ -1866,7 +1906,7 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
       const char* spec_opt = ctx_opt(ctx, "cover.speculate");   // "0": test hook (the generic route)
       if (ds && ds->stats_ok && !ds->span_hint.empty() && in->chrom_span_hint == ds->span_hint.data() && !shard && d.n > 0 && d.coord_bits == 32 && d.chrom_narrow &&
           d.chrom_bits == 8 && d.len_narrow && d.len_bits == 16 && ds->has_star /* strands unify to '*': the column, if any, is not read */ && n_groups == 1 && plan.n_aggs == 0 && (flag == GMQL_COVER || flag == GMQL_FLAT) &&
-          !ds->has_zero && ds->maxlen < (1ll << tiled::MAX_LOGW) - 2 && !(spec_opt && spec_opt[0] == '0')) {
+          !ds->has_zero && ds->maxlen < (1ll << tiled::MAX_LOGW) - 2 && !low_min && !(spec_opt && spec_opt[0] == '0')) {
         if (ds->lay_pad != (uint64_t)bin_size + 2ull) gmql_cover_prepare_dataset(ctx, ds, bin_size);   // another BinSize.Cover than the upload assumed
         if (ds->lay_coff.p && ds->lay_G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {
           SpanTable hs;                                       // borrowed views of the dataset's layout
@@ -1894,7 +1934,7 @@ static int cover_impl(gmql_ctx* ctx, const gmql_regions* in, const int32_t* samp
     // the ordinary route below.
     const char* spec_env = ctx_opt(ctx, "cover.speculate");   // "0": test hook
     if (in->chrom_span_hint && !shard && d.n > 0 && d.coord_bits == 32 && d.strand == nullptr && n_groups == 1 && plan.n_aggs == 0 &&
-        (flag == GMQL_COVER || flag == GMQL_FLAT) && !(spec_env && spec_env[0] == '0')) {
+        (flag == GMQL_COVER || flag == GMQL_FLAT) && !low_min && !(spec_env && spec_env[0] == '0')) {
       SpanTable hs;
       span_table_from_hint(ctx, in->chrom_span_hint, d.n_chrom, &hs, (unsigned long long)bin_size + 2ull);
       if (hs.G + 2ull * (1ull << tiled::MAX_LOGW) < 0xffffffffull) {

@@ -147,7 +147,7 @@ const char* gmql_last_error(const gmql_ctx* ctx);
 int  gmql_ctx_sync(gmql_ctx* ctx);                      /* cudaStreamSynchronize on the context stream; reports deferred checks */
 /* Per-context options (strings; value NULL or "" clears).  They never change results, only which device path computes them
  * (test hooks, tuning) or when an error is reported:
- *   "cover.path"      "tiled" | "sort"   force the tile-resident or the sort-and-merge path of COVER / FLAT
+ *   "cover.path"      "tiled" | "sort" | "bins"   force the tile-resident, the sort-and-merge or the bin-wise path of COVER / FLAT / HISTOGRAM
  *   "cover.logw"      "8".."16"          tile width of the tile-resident path
  *   "cover.kernel"    "rank" | "count"   tile kernel: bitmap-rank (round 1) or word-count (default where it applies)
  *   "cover.waves", "cover.stitch" ("split"), "cover.speculate" ("0"), "map.index" ("split"), "map.grouped" ("0" | "1"), "map.lean" ("0")
@@ -212,7 +212,9 @@ int gmql_map(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* exp,
  * MetaGroupMGD.scala:20-79) or NULL = one group (id 0L).  min_acc/max_acc: HOST [n_groups] thresholds
  * already resolved from N/ANY/ALL (GenometricCover.scala:57-79); use gmql_cover_count_samples for the
  * ungrouped ALL case.  bin_size = BinSize.Cover (2000): observable in results (stop%bin==0 extension,
- * SUMMIT bin cuts; GenometricCover.scala:345-360, 269-316).
+ * SUMMIT bin cuts; GenometricCover.scala:345-360, 269-316).  A threshold min_acc < 1 (N(0), ALL - k) makes depth 0
+ * "in range": coverHelper (:172-218) then records from the first to the last event of every bin that holds events, so
+ * the result depends on the bins; such calls (and SUMMIT always) run the reference's per-bin state machines literally.
  *
  * Result columns: one row per output region, sorted by (group, strand, chrom, start):
  *   GMQL_COL_COV_GROUP int32, GMQL_COL_COV_CHROM int32, GMQL_COL_COV_START int64, GMQL_COL_COV_STOP int64,

@@ -139,3 +139,46 @@ def test_cover_bag_aggregates(ex, flag, grouped):
     # with at most two contributors the fold order cannot matter: those rows agree as plain strings
     plain = lambda rows: sorted((r[:5], r[5][3], r[5][5], r[5][7]) for r in rows if r[5][6] <= 2.0)
     assert plain(got) == plain(want) and len(plain(got)) > 0
+
+
+def _low_params():
+    import gmql_b200 as G
+    return [
+        ((G.N(0), G.ANY()), (O.CoverParam.N(0), O.CoverParam.ANY())),
+        ((G.N(0), G.N(2)), (O.CoverParam.N(0), O.CoverParam.N(2))),
+        ((G.N(0), G.N(1)), (O.CoverParam.N(0), O.CoverParam.N(1))),
+        ((G.ALL(add=-5), G.ANY()), (O.CoverParam.ALL(add=-5), O.CoverParam.ANY())),     # (ALL - 5) <= 0 with five samples
+        ((G.ALL(add=-5), G.ALL()), (O.CoverParam.ALL(add=-5), O.CoverParam.ALL())),
+    ]
+
+
+@pytest.mark.parametrize("flag", FLAGS)
+@pytest.mark.parametrize("seed", range(4))
+def test_cover_min_acc_below_one(ex, flag, seed):
+    """minAcc < 1 (GenometricCover.scala:57-79): depth 0 is then "in range", and coverHelper (:172-218) records from the first to
+    the last event of every 2000-bp bin that holds events at all — the result depends on the bins, so it comes from the bin-wise
+    path (the reference's per-bin state machines, literally), with the boundary merge and GMAP4's drop of empty regions after it."""
+    rng = random.Random(900 + seed)
+    ids = [1, 2, 3, 4, 5]
+    strands = "+-*" if seed % 2 == 0 else "+-"
+    ds = rand_regions(rng, 220, ids, strands=strands, n_vals=1, span=30000, max_len=3500, min_len=(0 if seed == 3 else 1))
+    groups = None if seed < 2 else {1: 50, 2: 50, 3: 90, 4: 90, 5: 90}
+    for gp, op in _low_params():
+        if groups is not None and "ALL" in repr(gp[0]):
+            continue                                        # (ALL - 5) is negative for groups of two or three samples: covered ungrouped
+        _check(ex, flag, ds, ids, groups, gp, op, [("SUM", 0), ("COUNT", 0), ("MAX", 0)])
+
+
+@pytest.mark.parametrize("flag", ["COVER", "FLAT", "HISTOGRAM"])
+def test_cover_binwise_path_equals_oracle_for_ordinary_thresholds(ex, flag):
+    """The bin-wise path (option cover.path = bins) is the reference's algorithm bin by bin; with minAcc >= 1 it must give what the
+    sweep / tile paths give: a cross-check of both against the literal oracle."""
+    rng = random.Random(4242)
+    ids = list(range(6))
+    ds = rand_regions(rng, 500, ids, chroms=("chr1", "chr7"), strands="+-*", span=50000, max_len=9000, n_vals=1, aligned_p=0.4)
+    ex.set_option("cover.path", "bins")
+    try:
+        for gp, op in _params()[:5]:
+            _check(ex, flag, ds, ids, None, gp, op, [("SUM", 0), ("MIN", 0)])
+    finally:
+        ex.set_option("cover.path", None)
