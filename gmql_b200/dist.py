@@ -77,6 +77,11 @@ def linear_layout(chrom_span, bin_size=2000):
 def plan_tile_cuts(ds, chrom_span, world_size, bin_size=2000):
     """Tile boundaries [t_0 = 0 < t_1 < ... < t_world = n_tiles] that give every rank about the same number of regions
     (by the tile of the region's start).  Must be computed from the FULL dataset (or an all-reduced tile histogram)."""
+    # the one-tile halo only holds for regions shorter than a tile (gmql_cover_shard's own bound): say so here, before any rank has
+    # uploaded anything, instead of GMQL_ERR_UNSUPPORTED from whichever shard happens to hold the long region
+    if ds.n and int((np.asarray(ds.stop, dtype=np.int64) - np.asarray(ds.start, dtype=np.int64)).max()) >= (1 << TILE_BITS) - 2:
+        raise ValueError("coordinate-range sharding needs every region shorter than %d bases (one-tile halo); shard this dataset by "
+                         "chromosome instead (dist.shard_by_chromosome)" % ((1 << TILE_BITS) - 2))
     coff, total = linear_layout(chrom_span, bin_size)
     n_tiles = (total >> TILE_BITS) + 1
     tile = (coff[ds.chrom] + ds.start) >> TILE_BITS

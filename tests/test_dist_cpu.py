@@ -145,3 +145,19 @@ def test_range_shard_planning_and_edge_merge():
         den = 400 - 90
         assert m["j1"][1] == abs((float(m["stop"][1]) - float(m["start"][1])) / den) and m["j2"][1] == 0.0
         assert m["j1"][0] == 0.5 and m["j2"][2] == 1.0
+
+
+def test_range_shard_planner_refuses_long_regions():
+    """the one-tile halo of coordinate-range sharding only holds for regions shorter than a tile; the planner says so
+    on the full dataset, before any rank uploads anything, and points at chromosome sharding."""
+    import numpy as np
+    import pytest
+    from gmql_b200 import dist as D
+    from gmql_b200.regions import RegionDataset
+    span = np.array([900000], dtype=np.int64)
+    start = np.array([10, 5000, 200000], dtype=np.int64)
+    ok = RegionDataset(["chr1"], np.zeros(3, np.int32), start, start + np.array([500, 65533, 10]), np.zeros(3, np.int8), np.zeros(3, np.int32), np.array([0], np.int64))
+    assert D.plan_tile_cuts(ok, span, 2)[0] == 0
+    long_ = RegionDataset(["chr1"], np.zeros(3, np.int32), start, start + np.array([500, 65534, 10]), np.zeros(3, np.int8), np.zeros(3, np.int32), np.array([0], np.int64))
+    with pytest.raises(ValueError, match="shard_by_chromosome"):
+        D.plan_tile_cuts(long_, span, 2)
