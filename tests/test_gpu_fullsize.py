@@ -268,3 +268,82 @@ def test_c3_full_size_against_the_oracle(ex):
     assert np.array_equal(v_max[has], want["max"][has])
     np.testing.assert_allclose(v_sum[has], want["sum"][has], rtol=1e-9)
     np.testing.assert_allclose(v_avg[has], want["sum"][has] / want["nn"][has], rtol=1e-9)
+
+
+def _md1_reference(left, right, lrows, first_max, down, B=5000, max_bin_distance=100000):
+    """Bin-free numpy restatement of JOIN [DLE(first_max - 1),] MD(1) [, DOWN] for the left rows `lrows` against EVERY right sample
+    (GenometricJoin.scala:62-81 parameter split, :284-309 bin window, :117-127 first round, :130-151 MD(k) with ties, :160-188 second
+    round).  Returns the sorted keys lrow * right.n + rrow.  Right strands are '*' (compatible with everything)."""
+    n_chrom = 24
+    maxd = first_max if first_max is not None else max_bin_distance          # :75-79
+    key = (right.sample.astype(np.int64) * n_chrom + right.chrom) << 32 | right.start.astype(np.int64)
+    order = np.argsort(key, kind="stable")
+    skey = key[order]
+    maxlen = int((right.stop - right.start).max())
+    n_rs = len(right.sample_ids)
+    out = []
+    for b in range(n_rs):
+        ls, le, lst, lc = left.start[lrows], left.stop[lrows], left.strand[lrows], left.chrom[lrows]
+        b0 = np.maximum(ls - maxd, 0) // B
+        b1 = (le + maxd) // B
+        wbeg, wend = b0 * B, (b1 + 1) * B
+        base = (np.int64(b) * n_chrom + lc) << 32
+        lo = np.searchsorted(skey, base + np.maximum(wbeg - maxlen, 0), side="left")
+        hi = np.searchsorted(skey, base + wend, side="left")                  # r.start / B <= binEnd
+        cnt = hi - lo
+        g = np.repeat(np.arange(len(lrows)), cnt)                             # group = position in lrows
+        r = order[np.repeat(lo, cnt) + (np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt))]
+        rs, re_ = right.start[r], right.stop[r]
+        gls, gle = ls[g], le[g]
+        m = np.minimum(np.abs(gls - re_), np.abs(rs - gle))
+        d = np.where((gle < rs) | (re_ < gls), m, -m)                          # distanceCalculator :375-386
+        ok = re_ >= wbeg[g]                                                   # r.stop / B >= binStart
+        if first_max is not None:
+            ok &= d < first_max                                               # :250
+        g, r, d, rs, re_ = g[ok], r[ok], d[ok], rs[ok], re_[ok]
+        dmin = np.full(len(lrows), np.iinfo(np.int64).max)
+        np.minimum.at(dmin, g, d)
+        keep = d == dmin[g]                                                   # k = 1: the minimum with its ties
+        if down:                                                              # second round, :171-183 (left strand only; '*' as '+')
+            keep &= np.where(lst[g] != 2, rs >= le[g], re_ <= ls[g])
+        out.append(lrows[g[keep]].astype(np.int64) * right.n + r[keep])
+    return np.sort(np.concatenate(out))
+
+
+def test_c4_md_full_size_exact_on_a_sample_of_left_regions(ex):
+    """C4's two MD joins at full size (200 x 200 samples, 2e8 (left region, right sample) groups, the team kernels): for the
+    10 000 left regions of two left samples the emitted (left row, right row) pairs are EXACTLY those of an independent bin-free
+    numpy restatement — complete and exact, not only the minimum-distance property — and the lane kernel gives the same rows for
+    the whole join."""
+    from gmql_b200 import synth, _lib as L
+    left = synth.promoter_samples(200, 5000, 4)
+    right = synth.peak_samples(200, 50000, 4, with_values=())
+    dl, vl, k1 = _upload(ex, left)
+    dr, vr, k2 = _upload(ex, right)
+    pairs = (L.Pair * (200 * 200))()
+    for a in range(200):
+        for b in range(200):
+            pairs[a * 200 + b].left_sample, pairs[a * 200 + b].right_sample = a, b
+
+    def join(atoms, kernel):
+        at = (L.Atom * len(atoms))()
+        for i, (kd, arg) in enumerate(atoms):
+            at[i].kind, at[i].arg = kd, arg
+        ex.set_option("join.md", kernel)
+        try:
+            out = C.c_void_p()
+            ex._check(ex.lib.gmql_join(ex.ctx, C.byref(vl), C.byref(vr), pairs, 200 * 200, at, len(atoms), 2 | 0x100, 5000, 100000, None, None, C.byref(out)))
+        finally:
+            ex.set_option("join.md", None)
+        lrow, rrow = _cols(ex, out, [(L.COL_JOIN_LEFT_ROW, np.int32), (L.COL_JOIN_RIGHT_ROW, np.int32)])
+        ex.lib.gmql_result_free(ex.ctx, out)
+        return np.sort(lrow.astype(np.int64) * right.n + rrow)
+
+    lrows = np.nonzero((left.sample == 3) | (left.sample == 117))[0]
+    for atoms, first_max in (([(2, 1), (4, 0)], None), ([(0, 10001), (2, 1), (4, 0)], 10001)):   # MD(1), DOWN;  DLE(10000), MD(1), DOWN
+        team = join(atoms, "team")
+        want = _md1_reference(left, right, lrows, first_max, down=True)
+        got = team[np.isin(team // right.n, lrows)]
+        assert len(want) > 10 ** 5 and np.array_equal(got, want)
+        assert np.array_equal(team, join(atoms, "lane"))
+    ex.lib.gmql_dataset_free(ex.ctx, dl); ex.lib.gmql_dataset_free(ex.ctx, dr)
