@@ -55,7 +55,7 @@ EXPORTS = [
     "gmql_result_column_elem_size", "gmql_result_column_device", "gmql_result_column_copy",
     "gmql_result_as_regions", "gmql_result_free", "gmql_last_device_ms", "gmql_last_h2d_ms",
     "gmql_dataset_upload", "gmql_dataset_free", "gmql_ctx_set_profiling", "gmql_ctx_profile_report",
-    "gmql_difference", "gmql_profile", "gmql_parse_text", "gmql_cover_shard", "gmql_ctx_set_option", "gmql_format_text",
+    "gmql_difference", "gmql_profile", "gmql_parse_text", "gmql_cover_shard", "gmql_ctx_set_option", "gmql_format_text", "gmql_group",
 ]
 
 _lib = None
@@ -89,6 +89,7 @@ def load_library(path=None):
     lib.gmql_parse_text.argtypes = [vp, C.c_char_p, i64, i32, C.POINTER(TextSchema), C.POINTER(C.c_char_p), i32, C.POINTER(vp)]
     lib.gmql_format_text.argtypes = [vp, C.POINTER(Regions), C.POINTER(TextOutSchema), C.POINTER(C.c_char_p), C.POINTER(vp)]
     lib.gmql_profile.argtypes = [vp, C.POINTER(Regions), C.POINTER(vp)]
+    lib.gmql_group.argtypes = [vp, C.POINTER(Regions), vp, C.POINTER(Agg), i32, C.POINTER(vp)]
     lib.gmql_cover.argtypes = [vp, C.POINTER(Regions), vp, i32, i32, vp, vp, i64, C.POINTER(Agg), i32, C.POINTER(vp)]
     lib.gmql_cover_shard.argtypes = [vp, C.POINTER(Regions), i32, i32, i32, i64, C.POINTER(CoverShard), C.POINTER(vp)]
     lib.gmql_cover_count_samples.argtypes = [vp, C.POINTER(Regions), C.POINTER(i32)]
@@ -129,4 +130,5 @@ COL_DIFF_REF_ROW = 48
 COL_PROF_LEFTMOST, COL_PROF_RIGHTMOST, COL_PROF_MIN_LENGTH, COL_PROF_MAX_LENGTH, COL_PROF_SUM_LENGTH, COL_PROF_SUM_LENGTH_SQ, COL_PROF_COUNT = 64, 65, 66, 67, 68, 69, 70
 COL_TXT_LINE_OFFSET, COL_TXT_STATUS, COL_TXT_CHROM, COL_TXT_START, COL_TXT_STOP, COL_TXT_STRAND = 80, 81, 82, 83, 84, 85
 COL_TXT_BYTES = 86
+COL_GROUP_ROW, COL_GROUP_COUNT = 96, 97
 COL_AGG_VALUE, COL_AGG_VALID = 256, 512

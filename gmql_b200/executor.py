@@ -205,6 +205,60 @@ class GMQLCudaExecutor:
         recs = ref.to_records()
         return [(long_id(recs[i][0]), recs[i][1], recs[i][2], recs[i][3], recs[i][4], tuple(recs[i][5])) for i in rows]
 
+    # ---- GROUP by coordinates, MERGE ------------------------------------------------------------------------------------------
+    def GroupRD(self, groupingParameters, aggregates, regionDataset):
+        """GROUP (GroupRD.apply, RegionsOperators/GroupRD.scala:22-64).  groupingParameters: list of value positions (FIELD(pos))
+        or None; aggregates: list of Agg or None.  Records of one sample with equal (chrom, start, stop, strand) and equal text
+        forms of the grouping fields collapse into one: (id, chrom, start, stop, strand, groupingFields ++ aggregates); every
+        aggregate sees the group's whole value list (MEDIAN is the true lower median here)."""
+        from .javafmt import bag_text, gvalue_text
+        fields = list(groupingParameters or [])
+        aggregates = list(aggregates or [])
+        recs = regionDataset.to_records()
+        code = None
+        if fields and recs:
+            seen = {}
+            code = np.array([seen.setdefault(tuple(gvalue_text(r[5][p]) for p in fields), len(seen)) for r in recs], dtype=np.int64)
+        c_ds, keep = regionDataset.as_c(narrow=self.narrow)
+        c_aggs = self._c_aggs(aggregates, regionDataset)
+        out = C.c_void_p()
+        self._check(self.lib.gmql_group(self.ctx, C.byref(c_ds), code.ctypes.data if code is not None else None, c_aggs, len(aggregates), C.byref(out)))
+        del keep
+        res = _Result(self, out)
+        rows = res.column(L.COL_GROUP_ROW, np.int32)
+        bag_slots = [q for q, a in enumerate(aggregates) if a.function_identifier.upper() in ("BAG", "BAGD")]
+        vals = [None if q in bag_slots else res.column(L.COL_AGG_VALUE + q, np.float64) for q in range(len(aggregates))]
+        oks = [None if q in bag_slots else res.column(L.COL_AGG_VALID + q, np.uint8) for q in range(len(aggregates))]
+        if bag_slots:
+            bag_off = res.column(L.COL_BAG_OFFSETS, np.int64)
+            bag_rows = res.column(L.COL_BAG_ROWS, np.int32)
+        res.free()
+        outp = []
+        for g, row in enumerate(rows):
+            rec = recs[row]
+            aggs = []
+            for q, a in enumerate(aggregates):
+                if q in bag_slots:
+                    members = bag_rows[bag_off[g]:bag_off[g + 1]]
+                    aggs.append(bag_text([recs[m][5][a.index] for m in members], a.function_identifier.upper() == "BAGD"))
+                else:
+                    aggs.append(float(vals[q][g]) if oks[q][g] else None)
+            outp.append((rec[0], rec[1], rec[2], rec[3], rec[4], tuple(rec[5][p] for p in fields) + tuple(aggs)))
+        return outp
+
+    @staticmethod
+    def MergeRD(groups, regionDataset):
+        """MERGE (MergeRD.apply, RegionsOperators/MergeRD.scala:20-45): every record keeps its coordinates and values and takes its
+        sample's group id (samples without a group are dropped by the join, :41-44), or 1L without grouping (:33-36).  Nothing
+        is computed per region, so this stays on the host: a relabelling of the sample ids."""
+        out = []
+        for (sid, chrom, start, stop, strand, vals) in regionDataset.to_records():
+            if groups is None:
+                out.append((1, chrom, start, stop, strand, tuple(vals)))
+            elif sid in groups:
+                out.append((groups[sid], chrom, start, stop, strand, tuple(vals)))
+        return out
+
     # ---- TEXT -> columns ---------------------------------------------------------------------------------------------------
     def parse_text(self, text, parser="NarrowPeakParser", chrom_names=None, start_minus_one=False):
         """Parses one sample file's tab-separated text on the device (gmql_parse_text; BedParser.region_parser,

@@ -2,8 +2,29 @@
 
 java_double_to_string: java.lang.Double.toString — used by the BAG / BAGD aggregates
 (GMQL-Server/.../DefaultRegionsToRegionFactory.scala:139,160: `case GDouble(v) => v.toString`).
-bag_fold: the pairwise fold of BAG / BAGD as the operators apply it (fun on a two-element list, :133-146 / :154-167)."""
+bag_fold: the pairwise fold of BAG / BAGD as the operators apply it (fun on a two-element list, :133-146 / :154-167).
+bag_text: BAG / BAGD applied once to a whole list (GROUP, GroupRD.scala:48-55).
+gvalue_text: GValue.toString (GDouble = DecimalFormat("#.########"), RoundingMode.FLOOR; core/DataTypes.scala:139-150,185) —
+the text GROUP's grouping fields are compared by (GroupRD.scala:40)."""
 import math
+from decimal import Context, Decimal, ROUND_FLOOR
+
+_WIDE = Context(prec=400)
+
+
+def gvalue_text(v) -> str:
+    if v is None:
+        return "null"
+    if not isinstance(v, float):
+        return str(v)
+    if v != v:
+        return "NaN"
+    if math.isinf(v):
+        return "\u221e" if v > 0 else "-\u221e"
+    s = format(Decimal(repr(v)).quantize(Decimal("0.00000001"), rounding=ROUND_FLOOR, context=_WIDE), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    return s if s not in ("", "-") else "0"
 
 
 def java_double_to_string(v: float) -> str:
@@ -76,3 +97,8 @@ def bag_fold(values, distinct=False):
     for v in values[1:]:
         acc = _bag_fun([acc, v], distinct)
     return acc
+
+
+def bag_text(values, distinct=False):
+    """BAG / BAGD on a whole list at once (GROUP applies `fun` to the group's full value list, GroupRD.scala:50)."""
+    return _bag_fun(list(values), distinct)

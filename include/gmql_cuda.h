@@ -300,6 +300,22 @@ int gmql_difference(gmql_ctx* ctx, const gmql_regions* ref, const gmql_regions* 
  */
 int gmql_profile(gmql_ctx* ctx, const gmql_regions* in, gmql_result** out);
 
+/* ---- GROUP by coordinates ----------------------------------------------------------------
+ * GroupRD.apply (RegionsOperators/GroupRD.scala:22-64): the records of one sample that agree on (chrom, start, stop, strand)
+ * and on the text forms of the grouping fields collapse into one record.  field_code: [in->n] (same location as `in`) one code
+ * per row, equal exactly when the rows agree on every grouping field's text (the host knows strings; :34-42), or NULL without
+ * grouping fields.  Every aggregate sees the group's whole value list (:48-55, `fun` is n-ary here): COUNT = members, SUM / AVG /
+ * MIN / MAX over the non-null values (GNull when there is none), GMQL_AGG_MEDIAN = the TRUE lower median (sorted non-null values,
+ * element (m - 1) / 2, DefaultRegionsToRegionFactory.scala:33-56 — unlike MAP / COVER, whose pairwise fold degrades it to MIN),
+ * BAG / BAGD = member lists for the host.
+ * Result: one row per group, ordered by (sample, chrom, start) and, inside that, by first appearance:
+ *   GMQL_COL_GROUP_ROW int32 (the group's first input row: key and grouping-field values come from it),
+ *   GMQL_COL_GROUP_COUNT int32 (members), GMQL_COL_AGG_VALUE / _VALID + k, and with BAG / BAGD GMQL_COL_BAG_OFFSETS int64
+ *   [rows + 1] / GMQL_COL_BAG_ROWS int32 (the members of every group, input order).
+ * MERGE (RegionsOperators/MergeRD.scala:20-45) relabels sample ids with group ids and touches no region: it stays on the host.
+ */
+int gmql_group(gmql_ctx* ctx, const gmql_regions* in, const int64_t* field_code, const gmql_agg* aggs, int32_t n_aggs, gmql_result** out);
+
 /* ---- TEXT -> columns --------------------------------------------------------------------
  * Replaces the per-line work of BedParser.region_parser (GMQL-Spark/.../loaders/BedParser.scala:112-172; the concrete
  * parsers are column layouts: NarrowPeakParser :295-303, RnaSeqParser :346-348, BedScoreParser :525-527, custom schemas
@@ -366,6 +382,7 @@ enum {
   GMQL_COL_PROF_SUM_LENGTH = 68, GMQL_COL_PROF_SUM_LENGTH_SQ = 69, GMQL_COL_PROF_COUNT = 70,
   GMQL_COL_TXT_LINE_OFFSET = 80, GMQL_COL_TXT_STATUS = 81, GMQL_COL_TXT_CHROM = 82, GMQL_COL_TXT_START = 83, GMQL_COL_TXT_STOP = 84,
   GMQL_COL_TXT_STRAND = 85, GMQL_COL_TXT_BYTES = 86,
+  GMQL_COL_GROUP_ROW = 96, GMQL_COL_GROUP_COUNT = 97,
   GMQL_COL_AGG_VALUE = 256, /* + aggregate index */
   GMQL_COL_AGG_VALID = 512  /* + aggregate index */
 };

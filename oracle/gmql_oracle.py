@@ -352,6 +352,41 @@ def map_direct(ref, exp, pairs, aggs):
 INT_MAX = 2 ** 31 - 1
 
 
+def group_reference(ds, grouping_fields, aggs):
+    """GroupRD.apply (RegionsOperators/GroupRD.scala:22-64), literally: every record's values become one-element lists (:31),
+    records are grouped by the md5 of the UNSEPARATED string id + chrom + start + stop + strand (+ "\u00a7" + text of every
+    grouping field, :32-42; grouped here by the string itself), a group's lists are concatenated (:44), every aggregate is
+    applied ONCE to the whole list of its column with (length, non-null count) (:48-52), and the output values are the first
+    record's grouping fields followed by the aggregates (:56-61).  The fold order is Spark's; here: input order."""
+    fields = list(grouping_fields or [])
+    groups = {}
+    for rec in ds:
+        sid, chrom, start, stop, strand, vals = rec
+        k = "%d%s%d%d%s" % (sid, chrom, start, stop, strand)
+        for pos in fields:
+            k += "\u00a7" + gvalue_to_string(vals[pos])
+        if k not in groups:
+            groups[k] = ((sid, chrom, start, stop, strand), [[v] for v in vals])
+        else:
+            for lst, v in zip(groups[k][1], vals):
+                lst.append(v)
+    out = []
+    for key, lists in groups.values():
+        aggregated = []
+        for a in (aggs or []):
+            line = lists[a.index]
+            aggregated.append(a.fun_out(a.fun(line), (len(line), sum(1 for v in line if v is not None))))
+        out.append(key + (tuple(lists[pos][0] for pos in fields) + tuple(aggregated),))
+    return out
+
+
+def merge_reference(ds, groups=None):
+    """MergeRD.apply (RegionsOperators/MergeRD.scala:20-45): id := group of the sample (inner join, :41-44) or 1L (:33-36)."""
+    if groups is None:
+        return [(1, c, s, e, st, tuple(v)) for (_sid, c, s, e, st, v) in ds]
+    return [(groups[sid], c, s, e, st, tuple(v)) for (sid, c, s, e, st, v) in ds if sid in groups]
+
+
 def md5_long_id(v: int) -> int:
     """Hashing.md5().newHasher().putLong(v).hash().asLong() (GenometricDifference.scala:53)."""
     return int.from_bytes(hashlib.md5(struct.pack("<q", v)).digest()[:8], "little", signed=True)

@@ -146,3 +146,18 @@ def test_difference_id_and_ungrouped_samples():
     ref = [(5, "chr1", 10, 20, "*", (1.0,)), (6, "chr1", 10, 20, "*", (1.0,))]
     out = O.difference_reference(ref, [], {5: [9]})
     assert out == [(O.md5_long_id(5), "chr1", 10, 20, "*", (1.0,))]
+
+
+def test_group_reference_hand_case():
+    """GroupRD.scala:22-64 on a hand-made input: one group of three (values 5, null, 1), one singleton with another strand."""
+    from oracle import gmql_oracle as O
+    ds = [(1, "chr1", 100, 200, "+", ("a", 5.0)), (1, "chr1", 100, 200, "+", ("b", None)), (1, "chr1", 100, 200, "-", ("a", 2.0)),
+          (1, "chr1", 100, 200, "+", ("a", 1.0))]
+    aggs = [O.Agg("COUNT"), O.Agg("SUM", 1), O.Agg("AVG", 1), O.Agg("MEDIAN", 1), O.Agg("BAG", 0), O.Agg("BAGD", 0), O.Agg("MIN", 1)]
+    got = {r[:5]: r[5] for r in O.group_reference(ds, None, aggs)}
+    assert got[(1, "chr1", 100, 200, "+")] == (3.0, 6.0, 3.0, 1.0, "a,a,b", "a,b", 1.0)
+    assert got[(1, "chr1", 100, 200, "-")] == (1.0, 2.0, 2.0, 2.0, "a", "a", 2.0)
+    # grouping on the name field splits the first group; the field's value leads the output values
+    got = {r[:5] + (r[5][0],): r[5][1:] for r in O.group_reference(ds, [0], [O.Agg("COUNT"), O.Agg("MEDIAN", 1)])}
+    assert got[(1, "chr1", 100, 200, "+", "a")] == (2.0, 1.0) and got[(1, "chr1", 100, 200, "+", "b")] == (1.0, None)
+    assert O.merge_reference(ds, {1: 9})[0][0] == 9 and O.merge_reference(ds, {2: 9}) == []
