@@ -156,7 +156,16 @@ __global__ void __launch_bounds__(256) k_join_scan(LeftSide L, RightIndex<K> R, 
         bool ok = false;
         int p = -1;
         uint32_t rrow = 0;
-        if (k < hi) {
+        if (k < hi && R.packed) {                          // 32-bit right coordinates: one 16-byte record per candidate
+          const int4 en = R.packed[k];
+          int64_t d;
+          if (first_round_ok(cfg, lst, ls, le, en.w & 3, (int64_t)en.x, (int64_t)en.y, b0, &d)) {
+            p = pair_idx[(int64_t)la * n_rs + (en.w >> 2)];                 // :124 (the bin join has no sample in its key)
+            rrow = (uint32_t)en.z;
+            ok = p >= 0 && second_round_ok(cfg, lst, ls, le, (int64_t)en.x, (int64_t)en.y, d);
+            if (ok && cfg.has_eq) ok = R.eq[rrow] == leq;                   // :102-114
+          }
+        } else if (k < hi) {
           int64_t rs = (int64_t)((uint64_t)R.start[k] - cbase), re = (int64_t)((uint64_t)R.stop[k] - cbase);
           int64_t d;
           if (first_round_ok(cfg, lst, ls, le, (int)R.strand[k], rs, re, b0, &d)) {
@@ -749,10 +758,12 @@ __global__ void k_join_payload(const uint32_t* __restrict__ rows, int64_t n, con
 }
 
 // one 16-byte record per sorted entry: everything the MD round needs about a candidate in one load
-__global__ void k_join_packed(const uint32_t* __restrict__ rows, int64_t n, const int32_t* __restrict__ start, const int32_t* __restrict__ stop, const int8_t* __restrict__ strand, int4* __restrict__ out) {
+// `sample` given (the pooled index of joins without MD): w = strand | sample << 2, so a candidate is ONE 16-byte load
+__global__ void k_join_packed(const uint32_t* __restrict__ rows, int64_t n, const int32_t* __restrict__ start, const int32_t* __restrict__ stop, const int8_t* __restrict__ strand,
+                              const int32_t* __restrict__ sample, int4* __restrict__ out) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     uint32_t r = rows[k];
-    out[k] = make_int4(start[r], stop[r], (int)r, strand ? (int)strand[r] : 0);
+    out[k] = make_int4(start[r], stop[r], (int)r, (strand ? (int)strand[r] : 0) | (sample ? sample[r] << 2 : 0));
   }
 }
 
@@ -940,9 +951,10 @@ static void run_join(gmql_ctx* ctx, const DevRegions& left, const DevRegions& ri
   DevBuf<uint32_t> tbl(ctx, n_buckets + 2);
   LAUNCH(ctx, (k_start_table<K>), grid_for(ctx, n_buckets + 1, 256), 256, 0, ix.start, nr, tbl_shift, n_buckets, tbl.p);
   DevBuf<int4> packed;
-  if (cfg.has_md && right.coord_bits == 32 && nr) {
+  if (right.coord_bits == 32 && nr && (cfg.has_md || (right.sample != nullptr && n_rs < (1 << 29)))) {
     packed.alloc(ctx, nr);
-    LAUNCH(ctx, k_join_packed, grid_for(ctx, nr, 256), 256, 0, ix.row, nr, (const int32_t*)right.start, (const int32_t*)right.stop, right.strand, packed.p);
+    LAUNCH(ctx, k_join_packed, grid_for(ctx, nr, 256), 256, 0, ix.row, nr, (const int32_t*)right.start, (const int32_t*)right.stop, right.strand,
+           cfg.has_md ? (const int32_t*)nullptr : right.sample, packed.p);
   }
   RightIndex<K> R;
   R.packed = packed.p;
