@@ -860,6 +860,62 @@ __global__ void __launch_bounds__(256) k_gmap4_scatter(const K* __restrict__ xs,
   }
 }
 
+// ---- GMAP4, merge form: count and the four bounds without atomics (no value aggregates) ---------------------------------------
+// The scatter above issues five REDs per (input region, phase-1 region) pair — 1.1e9 for C2's HISTOGRAM (96 M segments), 7 ms.
+// Both lists are sorted, so a block takes a CHUNK of consecutive phase-1 regions and stages the slice of the input index they can
+// see — from the first entry whose running max stop exceeds the chunk's first start to the last entry starting before the chunk's
+// last stop — in shared memory (sorted starts, stops, running maxima); every thread then finds its own region's window inside
+// the slice by two binary searches in shared memory (inputs with start < c.stop; first index whose running max exceeds c.start:
+// exactly k_gmap4's bounds) and scans it: a handful of entries.  Plain stores, nothing to initialise; k_gmap4_finish reads the
+// same accumulators.  A slice larger than the stage (long regions, deep pile-ups) is read from global memory by the same code.
+constexpr int GM_T = 256, GM_PER = 8, GM_CHUNK = GM_T * GM_PER;
+template <typename K>
+__global__ void __launch_bounds__(GM_T) k_gmap4_merge(const K* __restrict__ xs, const K* __restrict__ xe, const K* __restrict__ xpmax, int64_t nx,
+                                                      const K* __restrict__ cs, const K* __restrict__ ce, int64_t nc, ScatterAcc<K> acc, const int* __restrict__ unsorted) {
+  if (*unsorted) return;                                   // the warp-per-region kernel takes over
+  constexpr int CAP = sizeof(K) == 4 ? 3072 : 1536;
+  __shared__ K s_xs[CAP], s_xe[CAP], s_pm[CAP];
+  __shared__ long long s_lo, s_hi;
+  const int tid = threadIdx.x;
+  for (int64_t c0 = (int64_t)blockIdx.x * GM_CHUNK; c0 < nc; c0 += (int64_t)gridDim.x * GM_CHUNK) {
+    const int64_t c1 = c0 + GM_CHUNK < nc ? c0 + GM_CHUNK : nc;
+    if (tid == 0) s_hi = lower_bound_dev<K>(xs, nx, ce[c1 - 1]);        // stops ascend: nothing of the chunk sees an entry from here on
+    if (tid == 32) s_lo = upper_bound_dev<K>(xpmax, nx, cs[c0]);         // starts ascend: nothing of the chunk sees an entry before this one
+    __syncthreads();
+    const int64_t LO = s_lo, HI = s_hi > s_lo ? s_hi : s_lo;
+    const int64_t m = HI - LO;
+    const bool staged = m <= CAP;
+    if (staged) for (int64_t i = tid; i < m; i += GM_T) { s_xs[i] = xs[LO + i]; s_xe[i] = xe[LO + i]; s_pm[i] = xpmax[LO + i]; }
+    __syncthreads();
+    const K* S = staged ? s_xs : xs + LO;
+    const K* E = staged ? s_xe : xe + LO;
+    const K* P = staged ? s_pm : xpmax + LO;
+#pragma unroll 1
+    for (int r = 0; r < GM_PER; ++r) {
+      const int64_t c = c0 + (int64_t)r * GM_T + tid;
+      if (c >= c1) break;
+      const K a = cs[c], b = ce[c];
+      int64_t lo = 0, hi = m;
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (S[mid] < b) lo = mid + 1; else hi = mid; }
+      const int64_t kb = lo;                                 // inputs (of the slice) with start < c.stop
+      lo = 0; hi = kb;
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (P[mid] <= a) lo = mid + 1; else hi = mid; }
+      int32_t cnt = 0;
+      K smin = ~(K)0, emax = 0, smax = 0, emin = ~(K)0;
+      for (int64_t k = lo; k < kb; ++k) {
+        const K e = E[k];
+        if (e <= a) continue;                                // strict overlap (GMAP4.scala:41)
+        const K st = S[k];
+        ++cnt;
+        smin = st < smin ? st : smin; emax = e > emax ? e : emax;
+        smax = st > smax ? st : smax; emin = e < emin ? e : emin;
+      }
+      acc.cnt[c] = cnt; acc.smin[c] = smin; acc.emax[c] = emax; acc.smax[c] = smax; acc.emin[c] = emin;
+    }
+    __syncthreads();                                         // the stage is rewritten by the next chunk
+  }
+}
+
 template <typename K>
 __global__ void k_p1_table(const K* __restrict__ cs, int64_t nc, int shift, int64_t n_buckets, uint32_t* __restrict__ tbl) {
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += (int64_t)gridDim.x * blockDim.x) {
@@ -1645,7 +1701,10 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
       memset(&sa, 0, sizeof sa);
       DevBuf<int32_t> a_cnt(ctx, nc);
       DevBuf<K> a_smin(ctx, nc), a_emax(ctx, nc), a_smax(ctx, nc), a_emin(ctx, nc);
-      a_cnt.zero(); a_emax.zero(); a_smax.zero(); a_smin.fill_byte(0xff); a_emin.fill_byte(0xff);
+      // without value aggregates the merge kernel writes count and bounds of every phase-1 region with plain stores
+      const char* g4 = ctx_opt(ctx, "cover.gmap4");           // "scatter": test hook (the RED form)
+      const bool merge_form = plan.n_cols == 0 && !(g4 && !strcmp(g4, "scatter"));
+      if (!merge_form) { a_cnt.zero(); a_emax.zero(); a_smax.zero(); a_smin.fill_byte(0xff); a_emin.fill_byte(0xff); }
       sa.cnt = a_cnt.p; sa.smin = a_smin.p; sa.emax = a_emax.p; sa.smax = a_smax.p; sa.emin = a_emin.p;
       std::vector<DevBuf<int32_t>> a_nn((size_t)plan.n_cols);
       std::vector<DevBuf<double>> a_sum((size_t)plan.n_cols);
@@ -1655,6 +1714,10 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
         a_vmin[q].alloc(ctx, nc); a_vmin[q].fill_byte(0xff); a_vmax[q].alloc(ctx, nc); a_vmax[q].zero();
         sa.nn[q] = a_nn[q].p; sa.sum[q] = a_sum[q].p; sa.vmin[q] = a_vmin[q].p; sa.vmax[q] = a_vmax[q].p;
       }
+      if (merge_form)
+        LAUNCH(ctx, (k_gmap4_merge<K>), (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nc, GM_CHUNK), (int64_t)ctx->num_sms * 4)), GM_T, 0,
+               (const K*)ix.start, (const K*)ix.stop.p, (const K*)ix.pmax.p, n, (const K*)cs.p, (const K*)ce.p, nc, sa, (const int*)unsorted.p);
+      else
       LAUNCH(ctx, (k_gmap4_scatter<K>), grid_for(ctx, n, 256), 256, 0, (const K*)ix.start, (const K*)ix.stop.p, (const uint32_t*)ix.row, n, (const K*)cs.p, (const K*)ce.p, nc,
              (const uint32_t*)tbl.p, tshift, nb, plan, cc, sa, (const int*)unsorted.p);
       LAUNCH(ctx, (k_gmap4_finish<K>), grid_for(ctx, nc, 256), 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, plan, sa, flag == GMQL_FLAT ? 1 : 0,

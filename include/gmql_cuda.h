@@ -151,6 +151,7 @@ int  gmql_ctx_sync(gmql_ctx* ctx);                      /* cudaStreamSynchronize
  *   "cover.logw"      "8".."16"          tile width of the tile-resident path
  *   "cover.kernel"    "rank" | "count"   tile kernel: bitmap-rank (round 1) or word-count (default where it applies)
  *   "cover.waves", "cover.stitch" ("split"), "cover.speculate" ("0"), "map.index" ("split"), "map.grouped" ("0" | "1"), "map.lean" ("0")
+ *   "cover.gmap4"     "scatter"          GMAP4 over many small phase-1 regions with REDs instead of the merge form
  *   "join.md"         "team" | "lane"    MD(k) kernel: a warp per 32 neighbouring left regions walking the right samples, or a lane per
  *                                        (left region, right sample) group (default: team when the pair table is dense)
  *   "join.md_memo"    "0"                the team kernel's write pass repeats the selection instead of reading the count pass's memo

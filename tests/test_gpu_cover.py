@@ -182,3 +182,34 @@ def test_cover_binwise_path_equals_oracle_for_ordinary_thresholds(ex, flag):
             _check(ex, flag, ds, ids, None, gp, op, [("SUM", 0), ("MIN", 0)])
     finally:
         ex.set_option("cover.path", None)
+
+
+@pytest.mark.parametrize("flag", ["SUMMIT", "HISTOGRAM", "COVER"])
+@pytest.mark.parametrize("form", ["merge", "scatter"])
+def test_gmap4_merge_and_scatter_forms(ex, flag, form):
+    """GMAP4 over many small phase-1 regions without value aggregates: the merge form (sorted phase-1 regions against the sorted
+    input index, staged per chunk, no atomics) and the RED scatter form against the oracle — short regions (slices that fit the
+    stage) and a deep pile-up of long regions (a slice beyond the stage, read from global memory)."""
+    import gmql_b200 as G
+    rng = random.Random(31337)
+    ids = list(range(6))
+    short = rand_regions(rng, 1500, ids, chroms=("chr1", "chr2"), strands="+-", span=40000, max_len=400, n_vals=1, aligned_p=0.2)   # (COUNT reads column 0 in the reference)
+    pile = rand_regions(rng, 3600, ids, chroms=("chr3",), strands="*", span=30000, max_len=25000, min_len=15000, n_vals=0, aligned_p=0.1)
+    ex.set_option("cover.path", "sort")
+    ex.set_option("cover.gmap4", "scatter" if form == "scatter" else None)
+    try:
+        _check(ex, flag, short, ids, None, (G.N(2), G.ANY()), (O.CoverParam.N(2), O.CoverParam.ANY()), [("COUNT", 0)])
+        _check(ex, flag, short, ids, {i: (i % 2) for i in ids}, (G.N(1), G.N(3)), (O.CoverParam.N(1), O.CoverParam.N(3)), [])
+        if flag != "COVER":
+            # the pile-up against the C oracle (the literal Python GMAP4 takes minutes on 3 600 mutually overlapping regions)
+            from gmql_b200 import RegionDataset
+            from oracle import c_oracle as CO
+            d = RegionDataset.from_records(pile, sample_ids=ids)
+            got = ex.GenometricCover(flag, G.N(2), G.ANY(), [], None, d)
+            w = CO.cover_rows(d, {"SUMMIT": 2, "HISTOGRAM": 3}[flag], [2], [2 ** 31 - 1], None, 2000)
+            want = [(0, d.chrom_names[w["chrom"][k]], int(w["start"][k]), int(w["stop"][k]), "*+-"[w["strand"][k]],
+                     (float(w["acc"][k]), float(w["j1"][k]), float(w["j2"][k]))) for k in range(len(w["start"]))]
+            assert len(want) > 100 and canon(got, 12) == canon(want, 12)
+    finally:
+        ex.set_option("cover.path", None)
+        ex.set_option("cover.gmap4", None)
