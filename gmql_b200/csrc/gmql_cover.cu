@@ -1170,7 +1170,8 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
   DevBuf<uint64_t> ka(ctx, ne), kb(ctx, ne);
   LAUNCH(ctx, k_summit_events, g, 256, 0, in.chrom, in.start, in.stop, in.coord_bits, cls, n, B, coff2.p, G2, ecnt.p, ka.p);
   uint64_t* keys = nullptr;
-  radix_sort<uint64_t>(ctx, ka.p, kb.p, nullptr, nullptr, ne, bits_for(n_classes_total * G2) + 1, &keys, nullptr);
+  // (the sign bit below lin2 is only counted, never ordered: the sort starts at bit 1 — four passes instead of five on hg38)
+  radix_sort<uint64_t>(ctx, ka.p, kb.p, nullptr, nullptr, ne, bits_for(n_classes_total * G2) + 1, &keys, nullptr, 1);
   // coalesce
   DevBuf<int32_t> head(ctx, ne);
   DevBuf<int64_t> head_excl(ctx, ne + 1);
