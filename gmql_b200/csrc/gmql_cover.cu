@@ -576,29 +576,54 @@ __global__ void k_summit_bin_list(const int32_t* __restrict__ head, const int64_
 // restarts at depth 0); COVER / FLAT / HISTOGRAM only when minAcc < 1 makes depth 0 "in range": the reference's result then
 // depends on which bins hold events at all (:57-79 with the bins of :98-118), which only the bin-wise machine reproduces.
 enum { BINS_SUMMIT = 0, BINS_COVER = 1, BINS_HISTOGRAM = 2 };
-__global__ void k_summit_bins(const uint64_t* __restrict__ pkey, const int32_t* __restrict__ pdelta, int64_t np, const uint32_t* __restrict__ bin_first, int64_t n_bins,
-                              int64_t B, uint64_t G2, CoverCfg cfg, int kind, int32_t* __restrict__ emit, int64_t* __restrict__ pstart_off, int32_t* __restrict__ pval) {
+// A thread per bin walks its own ~60 points: neighbouring lanes read addresses a whole bin apart, every 8-byte key costs a
+// 32-byte sector and the working set of a full SM (1.4 MB) evicts the sectors before their reuse — ncu: 4.1 GB read for 1.1 GB of
+// points, issue 4.6 % (profiles/r02z_ncu_c2_summary.txt).  So a block of BINS_T consecutive bins first brings ITS points — one
+// contiguous range — into shared memory with coalesced loads (key as a 32-bit offset from the range's first key, net change), the
+// threads run their state machines out of shared memory, leave the emit flags in the net-change slots, and the block writes
+// them back coalesced.  A range beyond the stage (or wider than 2^32 keys: a chromosome / class boundary) is read in place.
+constexpr int BINS_T = 128;
+constexpr int BINS_CAP = 11264;                            // staged points per block (88 KB: two blocks per SM)
+__global__ void __launch_bounds__(BINS_T) k_summit_bins(const uint64_t* __restrict__ pkey, const int32_t* __restrict__ pdelta, int64_t np, const uint32_t* __restrict__ bin_first, int64_t n_bins,
+                              int64_t B, uint64_t G2, CoverCfg cfg, int kind, int cap, int32_t* __restrict__ emit, int64_t* __restrict__ pstart_off, int32_t* __restrict__ pval) {
+  extern __shared__ uint32_t bins_sm[];
+  uint32_t* s_k = bins_sm;                                 // [BINS_CAP] key - first key of the range
+  int32_t* s_d = (int32_t*)(bins_sm + BINS_CAP);           // [BINS_CAP] net change, then the emit flag
   const uint64_t W = (uint64_t)(B + 1);
-  for (int64_t bi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bi < n_bins; bi += (int64_t)gridDim.x * blockDim.x) {
+  const int tid = threadIdx.x;
+  for (int64_t b0 = (int64_t)blockIdx.x * BINS_T; b0 < n_bins; b0 += (int64_t)gridDim.x * BINS_T) {
+    const int64_t b1 = b0 + BINS_T < n_bins ? b0 + BINS_T : n_bins;
+    const int64_t m0 = bin_first[b0], m1 = b1 < n_bins ? (int64_t)bin_first[b1] : np;
+    const uint64_t key0 = pkey[m0];
+    const bool staged = m1 - m0 <= cap && pkey[m1 - 1] - key0 < 0xffffffffull;   // block-uniform
+    if (staged) {
+      for (int64_t i = tid; i < m1 - m0; i += BINS_T) { s_k[i] = (uint32_t)(pkey[m0 + i] - key0); s_d[i] = pdelta[m0 + i]; }
+    }
+    __syncthreads();
+    const int64_t bi = b0 + tid;
+    if (bi < b1) {
     const int64_t m = bin_first[bi];
     const int64_t m_end = bi + 1 < n_bins ? (int64_t)bin_first[bi + 1] : np;
-    const uint64_t bin = pkey[m] / W;
+    auto key_at = [&](int64_t q) -> uint64_t { return staged ? key0 + (uint64_t)s_k[q - m0] : pkey[q]; };
+    auto delta_at = [&](int64_t q) -> int { return staged ? s_d[q - m0] : pdelta[q]; };
+    auto put = [&](int64_t q, bool out) { if (staged) s_d[q - m0] = out ? 1 : 0; else emit[q] = out ? 1 : 0; };
+    const uint64_t bin = key_at(m) / W;
     const uint64_t bin_base = bin * W;
-    int g = (int)((pkey[m] / G2) / (uint64_t)cfg.n_classes);
+    int g = (int)((key_at(m) / G2) / (uint64_t)cfg.n_classes);
     int mn = cfg.mn[g], mx = cfg.mx[g];
     int64_t start = 0;
     int count = 0;
     if (kind == BINS_SUMMIT) {
       bool valid = false, reentered = false, growing = false;
       for (int64_t q = m; q < m_end; ++q) {
-        int64_t off = (int64_t)(pkey[q] - bin_base);
-        int nc = count + pdelta[q];
+        int64_t off = (int64_t)(key_at(q) - bin_base);
+        int nc = count + delta_at(q);
         bool nvalid = nc >= mn && nc <= mx;
         bool ngrow = nc > count || (growing && nc == count);
         bool nre = !valid && nvalid;
         int64_t nstart = (nvalid && nc != count) ? off : start;
         bool out = ((valid && growing && (!ngrow || !nvalid)) || (reentered && !ngrow)) && count != 0;
-        emit[q] = out ? 1 : 0;
+        put(q, out);
         if (out) { pstart_off[q] = start; pval[q] = count; }
         start = nstart; count = nc; valid = nvalid; reentered = nre; growing = ngrow;
       }
@@ -606,28 +631,32 @@ __global__ void k_summit_bins(const uint64_t* __restrict__ pkey, const int32_t* 
       int count_max = 0;
       bool recording = false;
       for (int64_t q = m; q < m_end; ++q) {
-        const int64_t off = (int64_t)(pkey[q] - bin_base);
-        const int nc = count + pdelta[q];
+        const int64_t off = (int64_t)(key_at(q) - bin_base);
+        const int nc = count + delta_at(q);
         const bool in_range = nc >= mn && nc <= mx;
         const bool nrec = in_range && q + 1 < m_end;       // `si.hasNext` (:180): the bin's last point never records
         const int ncmax = (!nrec && recording) ? 0 : ((nrec && nc > count_max) ? nc : count_max);
         const int64_t nstart = (in_range && !recording) ? off : start;
         const bool out = !nrec && recording;
-        emit[q] = out ? 1 : 0;
+        put(q, out);
         if (out) { pstart_off[q] = nstart; pval[q] = count_max; }
         count = nc; start = nstart; count_max = ncmax; recording = nrec;
       }
     } else {
       for (int64_t q = m; q < m_end; ++q) {
-        const int64_t off = (int64_t)(pkey[q] - bin_base);
-        const int nc = count + pdelta[q];
+        const int64_t off = (int64_t)(key_at(q) - bin_base);
+        const int nc = count + delta_at(q);
         const int64_t nstart = (nc >= mn && nc <= mx && nc != count) ? off : start;
         const bool out = count >= mn && count <= mx && nc != count && count != 0;
-        emit[q] = out ? 1 : 0;
+        put(q, out);
         if (out) { pstart_off[q] = start; pval[q] = count; }
         start = nstart; count = nc;
       }
     }
+    }
+    __syncthreads();
+    if (staged) for (int64_t i = tid; i < m1 - m0; i += BINS_T) emit[m0 + i] = s_d[i];
+    __syncthreads();                                       // the stage is rewritten by the next range
   }
 }
 
@@ -1195,7 +1224,14 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
     DevBuf<uint32_t> bin_first(ctx, n_bins);
     GMQL_REQUIRE(np < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "SUMMIT: too many event points");
     if (np) LAUNCH(ctx, k_summit_bin_list, grid_for(ctx, np, 256), 256, 0, bhead.p, bhead_excl.p, np, bin_first.p);
-    if (n_bins) LAUNCH(ctx, k_summit_bins, grid_for(ctx, n_bins, 128, 1), 128, 0, pkey.p, pdelta.p, np, bin_first.p, n_bins, B, G2, cfg, kind, emit.p, pso.p, pval.p);
+    if (n_bins) {
+      const size_t bsh = 8 * (size_t)BINS_CAP;
+      const char* bo = ctx_opt(ctx, "cover.bins");            // "inplace": test hook (no staging of the points)
+      const int bins_cap = (bo && !strcmp(bo, "inplace")) ? 0 : BINS_CAP;
+      CUDA_TRY(cudaFuncSetAttribute(k_summit_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsh));
+      LAUNCH(ctx, k_summit_bins, (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n_bins, BINS_T), (int64_t)ctx->num_sms * 2)), BINS_T, bsh,
+             pkey.p, pdelta.p, np, bin_first.p, n_bins, B, G2, cfg, kind, bins_cap, emit.p, pso.p, pval.p);
+    }
   }
   device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, emit.p, emit_excl.p, np, emit_excl.p + np);
   int64_t npieces = read_back<int64_t>(ctx, emit_excl.p + np);

@@ -213,3 +213,20 @@ def test_gmap4_merge_and_scatter_forms(ex, flag, form):
     finally:
         ex.set_option("cover.path", None)
         ex.set_option("cover.gmap4", None)
+
+
+@pytest.mark.parametrize("flag", FLAGS)
+def test_binwise_machines_in_place(ex, flag):
+    """The per-bin state machines without their shared-memory stage (option cover.bins = inplace: the route of ranges beyond the
+    stage): SUMMIT, and COVER / FLAT / HISTOGRAM with minAcc < 1, against the literal oracle."""
+    import gmql_b200 as G
+    rng = random.Random(606)
+    ids = [1, 2, 3, 4]
+    ds = rand_regions(rng, 400, ids, chroms=("chr1", "chr4"), strands="+-*", span=30000, max_len=5000, n_vals=1, aligned_p=0.3)
+    ex.set_option("cover.bins", "inplace")
+    try:
+        _check(ex, flag, ds, ids, None, (G.N(0), G.N(3)), (O.CoverParam.N(0), O.CoverParam.N(3)), [("SUM", 0)])
+        if flag == "SUMMIT":
+            _check(ex, flag, ds, ids, None, (G.N(2), G.ANY()), (O.CoverParam.N(2), O.CoverParam.ANY()), [])
+    finally:
+        ex.set_option("cover.bins", None)
