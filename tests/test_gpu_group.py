@@ -92,3 +92,23 @@ def test_merge(ex):
     groups = {1: 100, 2: 100, 3: 200}                              # sample 4 has no group: dropped by the join
     got = ex.MergeRD(groups, d)
     assert canon(got) == canon(O.merge_reference(ds, groups)) and {r[0] for r in got} == {100, 200}
+
+
+def test_group_edges(ex):
+    """Empty input; coordinates beyond 2^31 (int64 columns); a long run of records that share sample, chromosome and start but
+    differ in stop / strand (every row looks back over its whole run: O(run) per row)."""
+    from gmql_b200 import RegionDataset, Agg
+    d = RegionDataset.from_records([], sample_ids=[1], n_values=1)
+    assert ex.GroupRD(None, [Agg("COUNT", 0)], d) == []
+    off = 5_000_000_000
+    rng = random.Random(99)
+    base = rand_regions(rng, 80, [1, 2], n_vals=1, span=2000, max_len=300)
+    ds = [(r[0], r[1], r[2] + off, r[3] + off, r[4], r[5]) for r in base + base[:30] + base[10:25]]
+    aggs = [("COUNT", 0), ("SUM", 0), ("MEDIAN", 0), ("MAX", 0)]
+    got = ex.GroupRD(None, [Agg(k, i) for k, i in aggs], RegionDataset.from_records(ds, sample_ids=[1, 2]))
+    assert canon(got, 9) == canon(O.group_reference(ds, None, [O.Agg(k, i) for k, i in aggs]), 9)
+    run = [(1, "chr1", 1000, 1001 + (k % 700), "+-*"[k % 3], (float(k % 11),)) for k in range(3000)]
+    rng.shuffle(run)
+    got = ex.GroupRD(None, [Agg(k, i) for k, i in aggs], RegionDataset.from_records(run, sample_ids=[1]))
+    want = O.group_reference(run, None, [O.Agg(k, i) for k, i in aggs])
+    assert len(want) == 2100 and canon(got, 9) == canon(want, 9)
