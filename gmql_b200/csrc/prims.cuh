@@ -213,6 +213,11 @@ static void device_scan(gmql_ctx* ctx, const Tin* in, T* out, int64_t n, T* tota
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_BITS = 8;
 constexpr int RS_RADIX = 1 << RS_BITS;
+// resident blocks per SM the sort pass is compiled for: four with 32-bit keys (64 registers: the pass waits on its key loads,
+// 0.44 -> 0.39 ms per pass of 5e7 keys + payload); with 64-bit keys the compiler's own choice is the fastest of 2 / 3 / 4 (measured)
+#ifndef OS64_MINB
+#define OS64_MINB 0
+#endif
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 #define OS_FLAG_AGG (1u << 30)
@@ -255,7 +260,7 @@ static __global__ void __launch_bounds__(RS_RADIX) k_os_scan_hist(uint32_t* hist
 }
 
 template <typename K, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS) k_os_pass(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
+__global__ void __launch_bounds__(RS_THREADS, sizeof(K) == 4 ? 4 : OS64_MINB) k_os_pass(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                         int64_t n, int shift, const uint32_t* __restrict__ digit_start, volatile uint32_t* tile_state, uint32_t* ticket) {
   constexpr int ITEMS = OsCfg<K>::ITEMS;
   constexpr int TILE = OsCfg<K>::TILE;
