@@ -995,6 +995,51 @@ __global__ void k_gmap4_finish(const uint32_t* __restrict__ ccls, const int32_t*
   }
 }
 
+struct FinalCols {
+  int32_t* group; int32_t* chrom; int64_t* start; int64_t* stop; int8_t* strand; int32_t* acc; double* j1; double* j2;
+  double* value[16]; uint8_t* valid[16];
+};
+// merge form, second half: keep = count > 0 (GMAP4.scala:33-34,48), and — once the kept rows are numbered — the GMAP4 formulas
+// written straight into the compacted result columns: no intermediate start / stop / Jaccard arrays and no compaction pass over them
+// (k_gmap4_finish + k_cover_compact moved 206 bytes per phase-1 region for HISTOGRAM's 96 M segments; this moves 109)
+__global__ void k_keep_from_cnt(const int32_t* __restrict__ cnt, int64_t nc, int32_t* __restrict__ keep, const int* __restrict__ unsorted) {
+  if (*unsorted) return;                                   // k_gmap4 decides
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) keep[c] = cnt[c] > 0 ? 1 : 0;
+}
+template <typename K>
+__global__ void k_gmap4_finish_direct(const int32_t* __restrict__ keep, const int64_t* __restrict__ keep_excl, const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom,
+                                      const int64_t* __restrict__ cstart, const int64_t* __restrict__ cstop, const int32_t* __restrict__ cacc, int64_t nc, LinMap lm, CovAggPlan plan,
+                                      ScatterAcc<K> acc, int flat, int n_classes, int unified, FinalCols f, double* __restrict__ acc_d) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    if (!keep[c]) continue;
+    const int64_t o = keep_excl[c];
+    const uint32_t cls = ccls[c];
+    const uint64_t base = (uint64_t)cls * lm.G + lm.coff[cchrom[c]];
+    const long long cnt = acc.cnt[c];
+    const unsigned long long smin = acc.smin[c], emax = acc.emax[c], smax = acc.smax[c], emin = acc.emin[c];
+    const int64_t start_min = (int64_t)(smin - base), end_max = (int64_t)(emax - base);
+    const int64_t os = flat ? start_min : cstart[c], oe = flat ? end_max : cstop[c];   // GMAP4.scala:83-84
+    const long long den = (long long)(emax - smin);
+    double num2;
+    if (cnt == 1) num2 = (double)(long long)(emin - smax);
+    else num2 = smax < emin ? (double)(long long)(emin - smax) : 0.0;                  // :74
+    f.group[o] = (int32_t)(cls / (uint32_t)n_classes);
+    f.strand[o] = unified ? (int8_t)0 : (int8_t)(cls % (uint32_t)n_classes + 1);
+    f.chrom[o] = cchrom[c];
+    f.start[o] = os;
+    f.stop[o] = oe;
+    f.acc[o] = cacc[c];
+    acc_d[o] = (double)cacc[c];
+    f.j1[o] = den != 0 ? fabs(((double)oe - (double)os) / (double)den) : 0.0;          // :91
+    f.j2[o] = den != 0 ? fabs(num2 / (double)den) : 0.0;                               // :93
+    for (int a = 0; a < plan.n_aggs; ++a) {                // no value columns in this form: COUNT, or a host-built BAG string
+      const bool is_count = plan.kind[a] == GMQL_AGG_COUNT;
+      f.value[a][o] = is_count ? (double)cnt : 0.0;
+      f.valid[a][o] = is_count ? 1 : 0;
+    }
+  }
+}
+
 // ---- aggregates for the tile-resident path: a region-driven post-pass over the runs ------------------------------------------
 // The tile kernel leaves count / startMin / endMax / startMax / endMin per run; value aggregates are added by one more read of the
 // input columns in their ORIGINAL order (values are fetched by row, no gather): every region finds the runs it overlaps through a
@@ -1057,10 +1102,6 @@ __global__ void k_run_agg_finish(int64_t nr, CovAggPlan plan, RunAgg acc, const 
   }
 }
 
-struct FinalCols {
-  int32_t* group; int32_t* chrom; int64_t* start; int64_t* stop; int8_t* strand; int32_t* acc; double* j1; double* j2;
-  double* value[16]; uint8_t* valid[16];
-};
 __global__ void k_cover_compact(int64_t nc, const int32_t* __restrict__ keep, const int64_t* __restrict__ keep_excl, const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom,
                                 const int64_t* __restrict__ fstart, const int64_t* __restrict__ fstop, const int32_t* __restrict__ cacc, const double* __restrict__ j1, const double* __restrict__ j2,
                                 CovOut in, int n_aggs, int n_classes, int unified, FinalCols f, double* __restrict__ acc_d, tiled::ShardRaw raw_in, tiled::ShardRaw raw_out) {
@@ -1599,6 +1640,11 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
   }
 
   Phase1Out p1;
+  // merge form of GMAP4 (no value aggregates): count and bounds per phase-1 region, finished straight into the result columns
+  DevBuf<int32_t> m_cnt;
+  DevBuf<K> m_smin, m_emax, m_smax, m_emin;
+  DevBuf<int> m_unsorted;
+  bool m_direct = false;
   DevBuf<int32_t> keep, ocount;
   DevBuf<int64_t> keep_excl, fstart, fstop;
   DevBuf<double> j1, j2;
@@ -1725,7 +1771,8 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
       // many small phase-1 regions: region-driven accumulation; the warp-per-region kernel only runs if the phase-1 list
       // turns out not to be sorted and disjoint (decided on the device, no host round trip)
       DevBuf<K> cs(ctx, nc), ce(ctx, nc);
-      DevBuf<int> unsorted(ctx, 1);
+      m_unsorted.alloc(ctx, 1);
+      DevBuf<int>& unsorted = m_unsorted;
       unsorted.zero();
       LAUNCH(ctx, (k_p1_linear<K>), grid_for(ctx, nc, 256), 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, cs.p, ce.p, unsorted.p);
       const uint64_t max_key = n_classes_total * lm.G;
@@ -1736,8 +1783,9 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
       LAUNCH(ctx, (k_p1_table<K>), grid_for(ctx, nb + 1, 256), 256, 0, cs.p, nc, tshift, nb, tbl.p);
       ScatterAcc<K> sa;
       memset(&sa, 0, sizeof sa);
-      DevBuf<int32_t> a_cnt(ctx, nc);
-      DevBuf<K> a_smin(ctx, nc), a_emax(ctx, nc), a_smax(ctx, nc), a_emin(ctx, nc);
+      m_cnt.alloc(ctx, nc); m_smin.alloc(ctx, nc); m_emax.alloc(ctx, nc); m_smax.alloc(ctx, nc); m_emin.alloc(ctx, nc);
+      DevBuf<int32_t>& a_cnt = m_cnt;
+      DevBuf<K>&a_smin = m_smin, &a_emax = m_emax, &a_smax = m_smax, &a_emin = m_emin;
       // without value aggregates the merge kernel writes count and bounds of every phase-1 region with plain stores
       const char* g4 = ctx_opt(ctx, "cover.gmap4");           // "scatter": test hook (the RED form)
       const bool merge_form = plan.n_cols == 0 && !(g4 && !strcmp(g4, "scatter"));
@@ -1757,6 +1805,10 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
       else
       LAUNCH(ctx, (k_gmap4_scatter<K>), grid_for(ctx, n, 256), 256, 0, (const K*)ix.start, (const K*)ix.stop.p, (const uint32_t*)ix.row, n, (const K*)cs.p, (const K*)ce.p, nc,
              (const uint32_t*)tbl.p, tshift, nb, plan, cc, sa, (const int*)unsorted.p);
+      const char* fin = ctx_opt(ctx, "cover.finish");         // "split": test hook (k_gmap4_finish + k_cover_compact)
+      m_direct = merge_form && !shard && !(fin && !strcmp(fin, "split"));
+      if (m_direct) LAUNCH(ctx, k_keep_from_cnt, grid_for(ctx, nc, 256), 256, 0, (const int32_t*)a_cnt.p, nc, keep.p, (const int*)unsorted.p);
+      else
       LAUNCH(ctx, (k_gmap4_finish<K>), grid_for(ctx, nc, 256), 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, plan, sa, flag == GMQL_FLAT ? 1 : 0,
              keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp, (const int*)unsorted.p);
       LAUNCH(ctx, (k_gmap4<K>), blocks, 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, ix.start, ix.stop.p, ix.pmax.p, ix.row, n,
@@ -1781,6 +1833,12 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
   } else {
     keep_excl.alloc(ctx, nc + 1);
     device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, keep.p, keep_excl.p, nc, keep_excl.p + nc);
+    if (m_direct) {                                         // (one synchronisation for both words)
+      int h_uns = 0;
+      CUDA_TRY(cudaMemcpyAsync(&h_uns, m_unsorted.p, sizeof h_uns, cudaMemcpyDeviceToHost, ctx->stream));
+      n_out = read_back<int64_t>(ctx, keep_excl.p + nc);
+      if (h_uns) m_direct = false;                          // the generic kernel filled the intermediate arrays: compact them
+    } else
     n_out = read_back<int64_t>(ctx, keep_excl.p + nc);
     o_group.alloc(ctx, n_out); o_chrom.alloc(ctx, n_out); o_acc.alloc(ctx, n_out); o_start.alloc(ctx, n_out); o_stop.alloc(ctx, n_out);
     o_strand.alloc(ctx, n_out); o_j1.alloc(ctx, n_out); o_j2.alloc(ctx, n_out); o_accd.alloc(ctx, n_out > 0 ? n_out : 1);
@@ -1802,6 +1860,13 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
     raw_out.edge = so.edge.p; raw_out.cnt = so.cnt.p; raw_out.rstart = so.rstart.p; raw_out.rstop = so.rstop.p;
     raw_out.smin = so.smin.p; raw_out.emax = so.emax.p; raw_out.smax = so.smax.p; raw_out.emin = so.emin.p;
   }
+  if (nc && n_out && !fo.ready && m_direct) {
+    ScatterAcc<K> sa;
+    memset(&sa, 0, sizeof sa);
+    sa.cnt = m_cnt.p; sa.smin = m_smin.p; sa.emax = m_emax.p; sa.smax = m_smax.p; sa.emin = m_emin.p;
+    LAUNCH(ctx, (k_gmap4_finish_direct<K>), grid_for(ctx, nc, 256), 256, 0, (const int32_t*)keep.p, (const int64_t*)keep_excl.p, (const uint32_t*)p1.cls.p, (const int32_t*)p1.chrom.p,
+           (const int64_t*)p1.start.p, (const int64_t*)p1.stop.p, (const int32_t*)p1.acc.p, nc, lm, plan, sa, flag == GMQL_FLAT ? 1 : 0, cfg.n_classes, cfg.unified, f, o_accd.p);
+  } else
   if (nc && n_out && !fo.ready) LAUNCH(ctx, k_cover_compact, grid_for(ctx, nc, 256), 256, 0, nc, keep.p, keep_excl.p, p1.cls.p, p1.chrom.p, fstart.p, fstop.p, p1.acc.p, j1.p, j2.p,
                           tmp, plan.n_aggs, cfg.n_classes, cfg.unified, f, o_accd.p, raw_in, raw_out);
   cudaEventRecord(ctx->ev_k1, ctx->stream);

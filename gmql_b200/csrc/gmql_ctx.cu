@@ -69,7 +69,7 @@ extern "C" const char* gmql_last_error(const gmql_ctx* c) { return c ? c->err.c_
 extern "C" int gmql_ctx_set_option(gmql_ctx* c, const char* name, const char* value) {
   if (!c || !name) return GMQL_ERR_INVALID;
   static const char* known[] = {"cover.path", "cover.logw", "cover.waves", "cover.stitch", "cover.speculate", "cover.kernel", "cover.dbg", "cover.blocks", "map.index", "map.grouped", "map.lean",
-                                "defer_check", "join.md", "join.md_memo", "cover.gmap4", "cover.bins", nullptr};
+                                "defer_check", "join.md", "join.md_memo", "cover.gmap4", "cover.bins", "cover.finish", nullptr};
   bool ok = false;
   for (int k = 0; known[k]; ++k) if (!strcmp(known[k], name)) ok = true;
   if (!ok) { c->err = std::string("unknown option: ") + name; return GMQL_ERR_INVALID; }

@@ -10,7 +10,7 @@ import os
 ENV_OPTIONS = {
     "GMQL_COVER_PATH": b"cover.path", "GMQL_COVER_LOGW": b"cover.logw", "GMQL_COVER_WAVES": b"cover.waves",
     "GMQL_COVER_STITCH": b"cover.stitch", "GMQL_COVER_SPECULATE": b"cover.speculate", "GMQL_COVER_KERNEL": b"cover.kernel", "GMQL_COVER_DBG": b"cover.dbg", "GMQL_COVER_BLOCKS": b"cover.blocks",
-    "GMQL_MAP_INDEX": b"map.index", "GMQL_MAP_GROUPED": b"map.grouped", "GMQL_MAP_LEAN": b"map.lean", "GMQL_DEFER_CHECK": b"defer_check", "GMQL_COVER_GMAP4": b"cover.gmap4", "GMQL_COVER_BINS": b"cover.bins", "GMQL_JOIN_MD": b"join.md", "GMQL_JOIN_MD_MEMO": b"join.md_memo",
+    "GMQL_MAP_INDEX": b"map.index", "GMQL_MAP_GROUPED": b"map.grouped", "GMQL_MAP_LEAN": b"map.lean", "GMQL_DEFER_CHECK": b"defer_check", "GMQL_COVER_GMAP4": b"cover.gmap4", "GMQL_COVER_BINS": b"cover.bins", "GMQL_COVER_FINISH": b"cover.finish", "GMQL_JOIN_MD": b"join.md", "GMQL_JOIN_MD_MEMO": b"join.md_memo",
 }
 _OPERATORS = ("gmql_cover", "gmql_cover_shard", "gmql_map", "gmql_difference", "gmql_join")
 

@@ -152,6 +152,8 @@ int  gmql_ctx_sync(gmql_ctx* ctx);                      /* cudaStreamSynchronize
  *   "cover.kernel"    "rank" | "count"   tile kernel: bitmap-rank (round 1) or word-count (default where it applies)
  *   "cover.waves", "cover.stitch" ("split"), "cover.speculate" ("0"), "map.index" ("split"), "map.grouped" ("0" | "1"), "map.lean" ("0")
  *   "cover.gmap4"     "scatter"          GMAP4 over many small phase-1 regions with REDs instead of the merge form
+ *   "cover.finish"    "split"            merge-form GMAP4 through the intermediate arrays and the compaction pass instead of straight
+ *                                        into the result columns
  *   "cover.bins"      "inplace"          the per-bin state machines read their points in place instead of from a shared-memory stage
  *   "join.md"         "team" | "lane"    MD(k) kernel: a warp per 32 neighbouring left regions walking the right samples, or a lane per
  *                                        (left region, right sample) group (default: team when the pair table is dense)

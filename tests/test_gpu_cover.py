@@ -185,7 +185,7 @@ def test_cover_binwise_path_equals_oracle_for_ordinary_thresholds(ex, flag):
 
 
 @pytest.mark.parametrize("flag", ["SUMMIT", "HISTOGRAM", "COVER"])
-@pytest.mark.parametrize("form", ["merge", "scatter"])
+@pytest.mark.parametrize("form", ["merge", "merge-split", "scatter"])
 def test_gmap4_merge_and_scatter_forms(ex, flag, form):
     """GMAP4 over many small phase-1 regions without value aggregates: the merge form (sorted phase-1 regions against the sorted
     input index, staged per chunk, no atomics) and the RED scatter form against the oracle — short regions (slices that fit the
@@ -197,6 +197,7 @@ def test_gmap4_merge_and_scatter_forms(ex, flag, form):
     pile = rand_regions(rng, 3600, ids, chroms=("chr3",), strands="*", span=30000, max_len=25000, min_len=15000, n_vals=0, aligned_p=0.1)
     ex.set_option("cover.path", "sort")
     ex.set_option("cover.gmap4", "scatter" if form == "scatter" else None)
+    ex.set_option("cover.finish", "split" if form == "merge-split" else None)   # default: straight into the result columns
     try:
         _check(ex, flag, short, ids, None, (G.N(2), G.ANY()), (O.CoverParam.N(2), O.CoverParam.ANY()), [("COUNT", 0)])
         _check(ex, flag, short, ids, {i: (i % 2) for i in ids}, (G.N(1), G.N(3)), (O.CoverParam.N(1), O.CoverParam.N(3)), [])
@@ -213,6 +214,7 @@ def test_gmap4_merge_and_scatter_forms(ex, flag, form):
     finally:
         ex.set_option("cover.path", None)
         ex.set_option("cover.gmap4", None)
+        ex.set_option("cover.finish", None)
 
 
 @pytest.mark.parametrize("flag", FLAGS)
