@@ -900,7 +900,9 @@ __global__ void __launch_bounds__(256) k_gmap4_scatter(const K* __restrict__ xs,
 constexpr int GM_T = 256, GM_PER = 8, GM_CHUNK = GM_T * GM_PER;
 template <typename K>
 __global__ void __launch_bounds__(GM_T) k_gmap4_merge(const K* __restrict__ xs, const K* __restrict__ xe, const K* __restrict__ xpmax, int64_t nx,
-                                                      const K* __restrict__ cs, const K* __restrict__ ce, int64_t nc, ScatterAcc<K> acc, const int* __restrict__ unsorted) {
+                                                      const K* __restrict__ cs, const K* __restrict__ ce, int64_t nc, ScatterAcc<K> acc, const int* __restrict__ unsorted, int* __restrict__ check) {
+  // check (optional): the phase-1 lists come straight from the sweep, sorted and disjoint by construction; a violation is raised
+  // here and reported as an internal error by the host, never computed around
   if (*unsorted) return;                                   // the warp-per-region kernel takes over
   constexpr int CAP = sizeof(K) == 4 ? 3072 : 1536;
   __shared__ K s_xs[CAP], s_xe[CAP], s_pm[CAP];
@@ -924,6 +926,7 @@ __global__ void __launch_bounds__(GM_T) k_gmap4_merge(const K* __restrict__ xs, 
       const int64_t c = c0 + (int64_t)r * GM_T + tid;
       if (c >= c1) break;
       const K a = cs[c], b = ce[c];
+      if (check && c > 0 && ce[c - 1] > a) *check = 1;
       int64_t lo = 0, hi = m;
       while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (S[mid] < b) lo = mid + 1; else hi = mid; }
       const int64_t kb = lo;                                 // inputs (of the slice) with start < c.stop
@@ -1009,23 +1012,35 @@ __global__ void k_keep_from_cnt(const int32_t* __restrict__ cnt, int64_t nc, int
 template <typename K>
 __global__ void k_gmap4_finish_direct(const int32_t* __restrict__ keep, const int64_t* __restrict__ keep_excl, const uint32_t* __restrict__ ccls, const int32_t* __restrict__ cchrom,
                                       const int64_t* __restrict__ cstart, const int64_t* __restrict__ cstop, const int32_t* __restrict__ cacc, int64_t nc, LinMap lm, CovAggPlan plan,
-                                      ScatterAcc<K> acc, int flat, int n_classes, int unified, FinalCols f, double* __restrict__ acc_d) {
+                                      ScatterAcc<K> acc, int flat, int n_classes, int unified, FinalCols f, double* __restrict__ acc_d,
+                                      const K* __restrict__ lin_s, const K* __restrict__ lin_e /* the phase-1 regions in linear form (then ccls .. cstop are null) */) {
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
     if (!keep[c]) continue;
     const int64_t o = keep_excl[c];
-    const uint32_t cls = ccls[c];
-    const uint64_t base = (uint64_t)cls * lm.G + lm.coff[cchrom[c]];
+    uint32_t cls;
+    int chrom;
+    int64_t c_start, c_stop;
+    if (lin_s) {                                           // linear -> (class, chrom, pos), as k_lin_to_regions
+      const uint64_t x = (uint64_t)lin_s[c];
+      const uint64_t k = x / lm.G, r = x - k * lm.G;
+      int lo = 0, hi = lm.n_chrom;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lm.coff[mid] <= r) lo = mid; else hi = mid; }
+      cls = (uint32_t)k; chrom = lo;
+      c_start = (int64_t)(r - lm.coff[lo]);
+      c_stop = (int64_t)((uint64_t)lin_e[c] - k * lm.G - lm.coff[lo]);
+    } else { cls = ccls[c]; chrom = cchrom[c]; c_start = cstart[c]; c_stop = cstop[c]; }
+    const uint64_t base = (uint64_t)cls * lm.G + lm.coff[chrom];
     const long long cnt = acc.cnt[c];
     const unsigned long long smin = acc.smin[c], emax = acc.emax[c], smax = acc.smax[c], emin = acc.emin[c];
     const int64_t start_min = (int64_t)(smin - base), end_max = (int64_t)(emax - base);
-    const int64_t os = flat ? start_min : cstart[c], oe = flat ? end_max : cstop[c];   // GMAP4.scala:83-84
+    const int64_t os = flat ? start_min : c_start, oe = flat ? end_max : c_stop;       // GMAP4.scala:83-84
     const long long den = (long long)(emax - smin);
     double num2;
     if (cnt == 1) num2 = (double)(long long)(emin - smax);
     else num2 = smax < emin ? (double)(long long)(emin - smax) : 0.0;                  // :74
     f.group[o] = (int32_t)(cls / (uint32_t)n_classes);
     f.strand[o] = unified ? (int8_t)0 : (int8_t)(cls % (uint32_t)n_classes + 1);
-    f.chrom[o] = cchrom[c];
+    f.chrom[o] = chrom;
     f.start[o] = os;
     f.stop[o] = oe;
     f.acc[o] = cacc[c];
@@ -1167,7 +1182,9 @@ static int64_t read_back(gmql_ctx* ctx, const T* dev) {
 
 template <typename K>
 static void phase1_sweep(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const LinMap& lm, const CoverCfg& cfg, int flag, uint64_t n_classes_total,
-                         const K* sorted_starts /*may be null*/, DevBuf<K>& ek_a, bool ek_filled, Phase1Out* p1) {
+                         const K* sorted_starts /*may be null*/, DevBuf<K>& ek_a, bool ek_filled, Phase1Out* p1, DevBuf<K>* lin_s = nullptr, DevBuf<K>* lin_e = nullptr) {
+  // lin_s / lin_e given: the phase-1 regions are handed out as they are produced — sorted, disjoint linear (start, stop) pairs —
+  // and p1 gets only their number and AccIndex; p1_regions() converts them to (class, chrom, start, stop) if a consumer needs that
   const int64_t n = in.n;
   int g = grid_for(ctx, n, 256);
   DevBuf<K> sk_a, sk_b, ek_b(ctx, n);
@@ -1217,8 +1234,15 @@ static void phase1_sweep(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cl
     if (nr) LAUNCH(ctx, (k_hist_segments<K>), pg, 256, 0, px.p, pd.p, np, flags.p, excl.p, rs.p, re.p, p1->acc.p);
   }
   p1->n = nr;
+  if (lin_s && lin_e) { *lin_s = std::move(rs); *lin_e = std::move(re); return; }
   p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->start.alloc(ctx, nr); p1->stop.alloc(ctx, nr);
   if (nr) LAUNCH(ctx, (k_lin_to_regions<K>), grid_for(ctx, nr, 256), 256, 0, rs.p, re.p, nr, lm, p1->cls.p, p1->chrom.p, p1->start.p, p1->stop.p);
+}
+template <typename K>
+static void p1_regions(gmql_ctx* ctx, const DevBuf<K>& lin_s, const DevBuf<K>& lin_e, const LinMap& lm, Phase1Out* p1) {
+  const int64_t nr = p1->n;
+  p1->cls.alloc(ctx, nr); p1->chrom.alloc(ctx, nr); p1->start.alloc(ctx, nr); p1->stop.alloc(ctx, nr);
+  if (nr) LAUNCH(ctx, (k_lin_to_regions<K>), grid_for(ctx, nr, 256), 256, 0, (const K*)lin_s.p, (const K*)lin_e.p, nr, lm, p1->cls.p, p1->chrom.p, p1->start.p, p1->stop.p);
 }
 
 static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* cls, const SpanTable& spans, const CoverCfg& cfg, uint64_t n_classes_total, Phase1Out* p1, int kind) {
@@ -1645,6 +1669,9 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
   DevBuf<K> m_smin, m_emax, m_smax, m_emin;
   DevBuf<int> m_unsorted;
   bool m_direct = false;
+  DevBuf<K> lin_s, lin_e;                                  // phase-1 regions in linear form (the sweep's own output)
+  bool lin_form = false;                                   // ... and nothing ever converts them: merge form + direct finish
+  DevBuf<int> lin_check;
   DevBuf<int32_t> keep, ocount;
   DevBuf<int64_t> keep_excl, fstart, fstop;
   DevBuf<double> j1, j2;
@@ -1752,29 +1779,43 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
     phase1_summit(ctx, in, cls.p, spans, cfg, n_classes_total, &p1, flag == GMQL_SUMMIT ? BINS_SUMMIT : (flag == GMQL_HISTOGRAM ? BINS_HISTOGRAM : BINS_COVER));
   } else {
     // without zero-length regions the phase-1 start keys are exactly the index's sorted starts: reuse them
-    phase1_sweep<K>(ctx, in, cls.p, lm, cfg, flag, n_classes_total, has_zero ? (const K*)nullptr : ix.start, ek_a, fused_keys, &p1);
+    phase1_sweep<K>(ctx, in, cls.p, lm, cfg, flag, n_classes_total, has_zero ? (const K*)nullptr : ix.start, ek_a, fused_keys, &p1, &lin_s, &lin_e);
+    // many small phase-1 regions without value aggregates stay linear all the way (merge form, direct finish); everything else
+    // gets its (class, chrom, start, stop) columns now
+    const char* g4o = ctx_opt(ctx, "cover.gmap4");
+    const char* fino = ctx_opt(ctx, "cover.finish");
+    lin_form = p1.n > 0 && p1.n >= n / 8 && p1.n < (int64_t)0xfffffff0LL && plan.n_cols == 0 && !shard && !(g4o && !strcmp(g4o, "scatter")) && !(fino && !strcmp(fino, "split"));
+    if (!lin_form) p1_regions<K>(ctx, lin_s, lin_e, lm, &p1);
   }
 
   // phase 2
   nc = p1.n;
-  keep.alloc(ctx, nc); ocount.alloc(ctx, nc);
-  fstart.alloc(ctx, nc); fstop.alloc(ctx, nc);
-  j1.alloc(ctx, nc); j2.alloc(ctx, nc);
+  keep.alloc(ctx, nc);
+  if (!lin_form) {                                         // (the linear form writes the result columns directly)
+    ocount.alloc(ctx, nc);
+    fstart.alloc(ctx, nc); fstop.alloc(ctx, nc);
+    j1.alloc(ctx, nc); j2.alloc(ctx, nc);
+  }
   CovCols cc;
   memset(&cc, 0, sizeof cc);
   for (int q = 0; q < plan.n_cols; ++q) { cc.v[q] = in.cols[plan.col_id[q]]; cc.ok[q] = in.valid[plan.col_id[q]]; }
-  for (int a = 0; a < plan.n_aggs; ++a) { tv[a].alloc(ctx, nc); tk[a].alloc(ctx, nc); tmp.value[a] = tv[a].p; tmp.valid[a] = tk[a].p; }
+  if (!lin_form) for (int a = 0; a < plan.n_aggs; ++a) { tv[a].alloc(ctx, nc); tk[a].alloc(ctx, nc); tmp.value[a] = tv[a].p; tmp.valid[a] = tk[a].p; }
   if (nc) {
     int64_t warps_needed = nc;
     int blocks = (int)std::min<int64_t>(ceil_div64(warps_needed, 8), (int64_t)ctx->num_sms * 16);
     if (nc >= n / 8 && nc < (int64_t)0xfffffff0LL) {
       // many small phase-1 regions: region-driven accumulation; the warp-per-region kernel only runs if the phase-1 list
       // turns out not to be sorted and disjoint (decided on the device, no host round trip)
-      DevBuf<K> cs(ctx, nc), ce(ctx, nc);
+      DevBuf<K> cs_own, ce_own;
       m_unsorted.alloc(ctx, 1);
       DevBuf<int>& unsorted = m_unsorted;
       unsorted.zero();
-      LAUNCH(ctx, (k_p1_linear<K>), grid_for(ctx, nc, 256), 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, cs.p, ce.p, unsorted.p);
+      if (lin_form) { lin_check.alloc(ctx, 1); lin_check.zero(); }
+      else {
+        cs_own.alloc(ctx, nc); ce_own.alloc(ctx, nc);
+        LAUNCH(ctx, (k_p1_linear<K>), grid_for(ctx, nc, 256), 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, cs_own.p, ce_own.p, unsorted.p);
+      }
+      struct { K* p; } cs = {lin_form ? lin_s.p : cs_own.p}, ce = {lin_form ? lin_e.p : ce_own.p};
       const uint64_t max_key = n_classes_total * lm.G;
       int tshift = 0;
       { int64_t want = std::max<int64_t>(1024, std::min<int64_t>((int64_t)1 << 22, nc / 2 + 1)); while (tshift < 62 && (int64_t)(max_key >> tshift) + 2 > want) ++tshift; }
@@ -1801,7 +1842,7 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
       }
       if (merge_form)
         LAUNCH(ctx, (k_gmap4_merge<K>), (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(nc, GM_CHUNK), (int64_t)ctx->num_sms * 4)), GM_T, 0,
-               (const K*)ix.start, (const K*)ix.stop.p, (const K*)ix.pmax.p, n, (const K*)cs.p, (const K*)ce.p, nc, sa, (const int*)unsorted.p);
+               (const K*)ix.start, (const K*)ix.stop.p, (const K*)ix.pmax.p, n, (const K*)cs.p, (const K*)ce.p, nc, sa, (const int*)unsorted.p, lin_check.p);
       else
       LAUNCH(ctx, (k_gmap4_scatter<K>), grid_for(ctx, n, 256), 256, 0, (const K*)ix.start, (const K*)ix.stop.p, (const uint32_t*)ix.row, n, (const K*)cs.p, (const K*)ce.p, nc,
              (const uint32_t*)tbl.p, tshift, nb, plan, cc, sa, (const int*)unsorted.p);
@@ -1811,6 +1852,7 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
       else
       LAUNCH(ctx, (k_gmap4_finish<K>), grid_for(ctx, nc, 256), 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, plan, sa, flag == GMQL_FLAT ? 1 : 0,
              keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp, (const int*)unsorted.p);
+      if (!lin_form)
       LAUNCH(ctx, (k_gmap4<K>), blocks, 256, 0, p1.cls.p, p1.chrom.p, p1.start.p, p1.stop.p, nc, lm, ix.start, ix.stop.p, ix.pmax.p, ix.row, n,
              plan, cc, flag == GMQL_FLAT ? 1 : 0, keep.p, fstart.p, fstop.p, j1.p, j2.p, ocount.p, tmp, (const int*)unsorted.p);
     } else {
@@ -1833,10 +1875,12 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
   } else {
     keep_excl.alloc(ctx, nc + 1);
     device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, keep.p, keep_excl.p, nc, keep_excl.p + nc);
-    if (m_direct) {                                         // (one synchronisation for both words)
-      int h_uns = 0;
+    if (m_direct) {                                         // (one synchronisation for all three words)
+      int h_uns = 0, h_chk = 0;
       CUDA_TRY(cudaMemcpyAsync(&h_uns, m_unsorted.p, sizeof h_uns, cudaMemcpyDeviceToHost, ctx->stream));
+      if (lin_check.p) CUDA_TRY(cudaMemcpyAsync(&h_chk, lin_check.p, sizeof h_chk, cudaMemcpyDeviceToHost, ctx->stream));
       n_out = read_back<int64_t>(ctx, keep_excl.p + nc);
+      GMQL_REQUIRE(!h_chk, GMQL_ERR_INVALID, "internal: the sweep's phase-1 regions are not sorted and disjoint");
       if (h_uns) m_direct = false;                          // the generic kernel filled the intermediate arrays: compact them
     } else
     n_out = read_back<int64_t>(ctx, keep_excl.p + nc);
@@ -1865,7 +1909,8 @@ static void run_cover(gmql_ctx* ctx, DevRegions& in, const int32_t* h_sample_gro
     memset(&sa, 0, sizeof sa);
     sa.cnt = m_cnt.p; sa.smin = m_smin.p; sa.emax = m_emax.p; sa.smax = m_smax.p; sa.emin = m_emin.p;
     LAUNCH(ctx, (k_gmap4_finish_direct<K>), grid_for(ctx, nc, 256), 256, 0, (const int32_t*)keep.p, (const int64_t*)keep_excl.p, (const uint32_t*)p1.cls.p, (const int32_t*)p1.chrom.p,
-           (const int64_t*)p1.start.p, (const int64_t*)p1.stop.p, (const int32_t*)p1.acc.p, nc, lm, plan, sa, flag == GMQL_FLAT ? 1 : 0, cfg.n_classes, cfg.unified, f, o_accd.p);
+           (const int64_t*)p1.start.p, (const int64_t*)p1.stop.p, (const int32_t*)p1.acc.p, nc, lm, plan, sa, flag == GMQL_FLAT ? 1 : 0, cfg.n_classes, cfg.unified, f, o_accd.p,
+           (const K*)(lin_form ? lin_s.p : nullptr), (const K*)(lin_form ? lin_e.p : nullptr));
   } else
   if (nc && n_out && !fo.ready) LAUNCH(ctx, k_cover_compact, grid_for(ctx, nc, 256), 256, 0, nc, keep.p, keep_excl.p, p1.cls.p, p1.chrom.p, fstart.p, fstop.p, p1.acc.p, j1.p, j2.p,
                           tmp, plan.n_aggs, cfg.n_classes, cfg.unified, f, o_accd.p, raw_in, raw_out);
