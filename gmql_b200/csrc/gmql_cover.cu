@@ -570,6 +570,13 @@ __global__ void k_summit_bin_list(const int32_t* __restrict__ head, const int64_
     if (head[m]) bin_first[head_excl[m]] = (uint32_t)m;
 }
 
+// dense inputs: nearly every bin of the genome holds points, so the first point of EVERY bin (empty ones included) comes from
+// one binary search per bin instead of head flags + scan + compaction over all points
+__global__ void k_summit_bin_search(const uint64_t* __restrict__ pkey, int64_t np, uint64_t W, int64_t n_bins, uint32_t* __restrict__ bin_first) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += (int64_t)gridDim.x * blockDim.x)
+    bin_first[b] = (uint32_t)lower_bound_dev<uint64_t>(pkey, np, (uint64_t)b * W);
+}
+
 // one thread per bin: the reference's per-bin state machine over the bin's coalesced points — summitHelper (:269-316),
 // coverHelper (:172-218, also FLAT) or histogramHelper (:229-258), literally.  A piece is stored at the index of the point that
 // emits it (its stop is that point's offset, clipped at the bin size by k_summit_pieces).  SUMMIT always runs here (every bin
@@ -594,6 +601,7 @@ __global__ void __launch_bounds__(BINS_T) k_summit_bins(const uint64_t* __restri
   for (int64_t b0 = (int64_t)blockIdx.x * BINS_T; b0 < n_bins; b0 += (int64_t)gridDim.x * BINS_T) {
     const int64_t b1 = b0 + BINS_T < n_bins ? b0 + BINS_T : n_bins;
     const int64_t m0 = bin_first[b0], m1 = b1 < n_bins ? (int64_t)bin_first[b1] : np;
+    if (m1 == m0) continue;                                // (a stretch of empty bins of the dense table; block-uniform)
     const uint64_t key0 = pkey[m0];
     const bool staged = m1 - m0 <= cap && pkey[m1 - 1] - key0 < 0xffffffffull;   // block-uniform
     if (staged) {
@@ -604,6 +612,7 @@ __global__ void __launch_bounds__(BINS_T) k_summit_bins(const uint64_t* __restri
     if (bi < b1) {
     const int64_t m = bin_first[bi];
     const int64_t m_end = bi + 1 < n_bins ? (int64_t)bin_first[bi + 1] : np;
+    if (m < m_end) {
     auto key_at = [&](int64_t q) -> uint64_t { return staged ? key0 + (uint64_t)s_k[q - m0] : pkey[q]; };
     auto delta_at = [&](int64_t q) -> int { return staged ? s_d[q - m0] : pdelta[q]; };
     auto put = [&](int64_t q, bool out) { if (staged) s_d[q - m0] = out ? 1 : 0; else emit[q] = out ? 1 : 0; };
@@ -652,6 +661,7 @@ __global__ void __launch_bounds__(BINS_T) k_summit_bins(const uint64_t* __restri
         if (out) { pstart_off[q] = start; pval[q] = count; }
         start = nstart; count = nc;
       }
+    }
     }
     }
     __syncthreads();
@@ -1281,14 +1291,25 @@ static void phase1_summit(gmql_ctx* ctx, const DevRegions& in, const uint32_t* c
   DevBuf<int32_t> emit(ctx, np), pval(ctx, np);
   DevBuf<int64_t> pso(ctx, np), emit_excl(ctx, np + 1);
   {
+    GMQL_REQUIRE(np < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "SUMMIT: too many event points");
+    DevBuf<uint32_t> bin_first;
+    int64_t n_bins = 0;
+    const uint64_t all_bins = (n_classes_total * G2) / (uint64_t)(B + 1);      // G2 is a whole number of bins
+    const char* bo0 = ctx_opt(ctx, "cover.bins");             // "inplace": test hook (also: the bin list by head flags + scan)
+    if (np > 0 && all_bins <= (uint64_t)(2 * np + 1024) && !(bo0 && !strcmp(bo0, "inplace"))) {
+      // dense: one search per bin of the genome (empty bins are empty ranges)
+      n_bins = (int64_t)all_bins;
+      bin_first.alloc(ctx, n_bins);
+      LAUNCH(ctx, k_summit_bin_search, grid_for(ctx, n_bins, 256), 256, 0, pkey.p, np, (uint64_t)(B + 1), n_bins, bin_first.p);
+    } else {
     DevBuf<int32_t> bhead(ctx, np);
     DevBuf<int64_t> bhead_excl(ctx, np + 1);
     if (np) LAUNCH(ctx, k_summit_bin_heads, grid_for(ctx, np, 256), 256, 0, pkey.p, np, B, bhead.p);
     device_scan<int32_t, int64_t, OpSum<int64_t>, false>(ctx, bhead.p, bhead_excl.p, np, bhead_excl.p + np);
-    const int64_t n_bins = read_back<int64_t>(ctx, bhead_excl.p + np);
-    DevBuf<uint32_t> bin_first(ctx, n_bins);
-    GMQL_REQUIRE(np < (int64_t)0xffffffffLL, GMQL_ERR_UNSUPPORTED, "SUMMIT: too many event points");
+    n_bins = read_back<int64_t>(ctx, bhead_excl.p + np);
+    bin_first.alloc(ctx, n_bins);
     if (np) LAUNCH(ctx, k_summit_bin_list, grid_for(ctx, np, 256), 256, 0, bhead.p, bhead_excl.p, np, bin_first.p);
+    }
     if (n_bins) {
       const size_t bsh = 8 * (size_t)BINS_CAP;
       const char* bo = ctx_opt(ctx, "cover.bins");            // "inplace": test hook (no staging of the points)

@@ -154,7 +154,8 @@ int  gmql_ctx_sync(gmql_ctx* ctx);                      /* cudaStreamSynchronize
  *   "cover.gmap4"     "scatter"          GMAP4 over many small phase-1 regions with REDs instead of the merge form
  *   "cover.finish"    "split"            merge-form GMAP4 through the intermediate arrays and the compaction pass instead of straight
  *                                        into the result columns
- *   "cover.bins"      "inplace"          the per-bin state machines read their points in place instead of from a shared-memory stage
+ *   "cover.bins"      "inplace"          the per-bin state machines read their points in place instead of from a shared-memory stage,
+ *                                        and the bin list comes from head flags + scan instead of one search per bin
  *   "join.md"         "team" | "lane"    MD(k) kernel: a warp per 32 neighbouring left regions walking the right samples, or a lane per
  *                                        (left region, right sample) group (default: team when the pair table is dense)
  *   "join.md_memo"    "0"                the team kernel's write pass repeats the selection instead of reading the count pass's memo
