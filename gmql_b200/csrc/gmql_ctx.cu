@@ -354,7 +354,33 @@ static __global__ void __launch_bounds__(256) k_dataset_stats(const void* __rest
   }
   int has_star = 0, zero = 0, bad = 0;
   long long maxlen = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  int64_t i_begin = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // the narrow encodings without strand / sample columns (the production upload): four rows per thread from three vector loads,
+  // and the per-chromosome maximum is only touched when a row can raise it (a plain read first: the maximum only grows, so a
+  // stale value filters safely) — one shared-memory atomic per row on two dozen addresses kept this kernel at 0.9 TB/s
+  if (use_sh && chrom_bits == 8 && bits == 32 && len_bits == 16 && !strand && !sample &&
+      ((((uintptr_t)chrom) & 3u) | (((uintptr_t)start) & 15u) | (((uintptr_t)stop_or_len) & 7u)) == 0) {
+    const int64_t n4 = n >> 2;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (int64_t)gridDim.x * blockDim.x) {
+      const int4 vs = ((const int4*)start)[g];
+      const uint2 vl = ((const uint2*)stop_or_len)[g];
+      const uint32_t vc = ((const uint32_t*)chrom)[g];
+      const int ss[4] = {vs.x, vs.y, vs.z, vs.w};
+      const uint32_t ll[4] = {vl.x & 0xffffu, vl.x >> 16, vl.y & 0xffffu, vl.y >> 16};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = (int)((vc >> (8 * q)) & 0xffu);
+        const int64_t s0 = ss[q], e0 = s0 + (int64_t)ll[q];
+        if (c >= n_chrom || s0 < 0 || e0 > 0x7fffffffLL) { bad = 1; continue; }
+        if (ll[q] == 0u) zero = 1;
+        if ((long long)ll[q] > maxlen) maxlen = ll[q];
+        if ((unsigned long long)e0 > sspan[c]) atomicMax(&sspan[c], (unsigned long long)e0);
+      }
+    }
+    has_star = 1;                                          // no strand column: every region is '*'
+    i_begin += n4 << 2;                                    // the last n % 4 rows go through the loop below
+  }
+  for (int64_t i = i_begin; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = chrom_bits == 8 ? (int)((const uint8_t*)chrom)[i] : (chrom_bits == 16 ? (int)((const uint16_t*)chrom)[i] : ((const int32_t*)chrom)[i]);
     const int64_t s = ld_coord(start, bits, i);
     int64_t e;
@@ -367,7 +393,7 @@ static __global__ void __launch_bounds__(256) k_dataset_stats(const void* __rest
     if (c < 0 || c >= n_chrom || s < 0 || s > e || st < 0 || st > 2 || sm < 0 || sm >= n_samples || (bits == 32 && e > 0x7fffffffLL)) { bad = 1; continue; }
     if (s == e) zero = 1;
     if (e - s > maxlen) maxlen = e - s;
-    if (use_sh) atomicMax(&sspan[c], (unsigned long long)e); else atomicMax(&span[c], (unsigned long long)e);
+    if (use_sh) { if ((unsigned long long)e > sspan[c]) atomicMax(&sspan[c], (unsigned long long)e); } else atomicMax(&span[c], (unsigned long long)e);
   }
   __shared__ int s_fl[4];
   if (threadIdx.x < 4) s_fl[threadIdx.x] = 0;
